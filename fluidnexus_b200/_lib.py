@@ -1,0 +1,93 @@
+"""ctypes binding of libfnx.so (include/fnx.h).  The library is the product; there is no fallback.
+
+`lib()` raises if the shared library is missing -- build it with `python __graft_entry__.py build`
+(or `fluidnexus_b200.build.build()`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfnx.so")
+
+FNX_OK = 0
+FNX_ERR_INVALID, FNX_ERR_CUDA, FNX_ERR_UNSUPPORTED, FNX_ERR_CAPACITY, FNX_ERR_ALLOC = 1, 2, 3, 4, 5
+FNX_NO_HOST_SYNC = 1
+FNX_EXACT_RECT = 2
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class RasterArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("V", C.c_int32), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
+        ("means3D", C.c_void_p), ("colors", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
+        ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("sh", C.c_void_p),
+        ("view_matrix", C.c_void_p), ("proj_matrix", C.c_void_p), ("bg", C.c_void_p),
+        ("tan_fov_x", C.c_float), ("tan_fov_y", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("flags", C.c_uint32), ("instance_capacity_hint", C.c_int64),
+    ]
+
+
+class RasterScratch(C.Structure):
+    _fields_ = [
+        ("geom", C.c_void_p), ("geom_bytes", C.c_size_t), ("binning", C.c_void_p), ("binning_bytes", C.c_size_t),
+        ("image", C.c_void_p), ("image_bytes", C.c_size_t), ("binning_capacity", C.c_int64),
+        ("check_slot", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class RasterGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D")]
+
+
+class FnxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfnx error {code}: {msg}")
+        self.code = code
+
+
+# every symbol include/fnx.h declares: name -> (restype, argtypes)
+_V, _I, _I64, _SZ, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
+_FWD = (_I, [C.POINTER(RasterArgs), ALLOC_FN, _V, ALLOC_FN, _V, ALLOC_FN, _V, _V, _V, _V, C.POINTER(_I64),
+             C.POINTER(RasterScratch), _V])
+_BWD = (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), _I64, _V, _V, C.POINTER(RasterGrads), _V])
+SYMBOLS = {
+    "fnx_abi_version": (_I, []),
+    "fnx_last_error": (C.c_char_p, []),
+    "fnx_build_arch": (C.c_char_p, []),
+    "fnx_raster_geom_bytes": (_SZ, [_I, _I]),
+    "fnx_raster_image_bytes": (_SZ, [_I, _I, _I]),
+    "fnx_raster_binning_bytes": (_SZ, [_I64, _I]),
+    "fnx_raster_forward": _FWD, "fnx_raster_forward_ch1": _FWD, "fnx_raster_forward_ch3": _FWD,
+    "fnx_raster_backward": _BWD, "fnx_raster_backward_ch1": _BWD, "fnx_raster_backward_ch3": _BWD,
+    "fnx_raster_check": (_I, [C.POINTER(RasterScratch), C.POINTER(_I64), _V]),
+    "fnx_mark_visible": (_I, [_I, _V, _V, _V, _V, _V]),
+    "fnx_raster_read_geom": (_I, [C.POINTER(RasterScratch), _I, _I, _V, _V, _V, _V, _V]),
+    "fnx_raster_read_image": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _V, _V, _V]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA library is the only implementation of this path "
+                "(no CPU fallback).  Build it with `python __graft_entry__.py build`.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if l.fnx_abi_version() != 1:
+            raise ImportError("libfnx ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(code):
+    if code != FNX_OK:
+        raise FnxError(code, lib().fnx_last_error().decode())

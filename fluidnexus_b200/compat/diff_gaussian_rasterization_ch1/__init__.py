@@ -1,0 +1,12 @@
+"""Drop-in for the reference package `diff_gaussian_rasterization_ch1`
+(FluidDynamics/submodules/gaussian_rasterization_ch1/diff_gaussian_rasterization_ch1/__init__.py), backed by libfnx.
+
+    from diff_gaussian_rasterization_ch1 import GaussianRasterizationSettings, GaussianRasterizer
+
+is what FD/helpers/helper_pipe.py:14-41 imports; put `fluidnexus_b200/compat` on sys.path (or call
+`fluidnexus_b200.install_compat()`) and the reference's renderer/ and entries_* run unchanged.
+"""
+from fluidnexus_b200.rasterizer import make_module as _make
+
+GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, _RasterizeGaussians = _make(1)
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]

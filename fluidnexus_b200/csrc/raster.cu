@@ -1,0 +1,1144 @@
+// raster.cu -- tile-binned differentiable Gaussian rasterizer for sm_100a (B200).
+//
+// Replaces the reference extension modules diff_gaussian_rasterization_ch3 / _ch1
+// (R3 = FluidDynamics/submodules/gaussian_rasterization_ch3 in the reference tree):
+//   forward   R3/cuda_rasterizer/rasterizer_impl.cu:184-319, forward.cu:148-244 (preprocess), :249-373 (blend)
+//   backward  R3/cuda_rasterizer/rasterizer_impl.cu:323-414, backward.cu:384-536 (blend), :137-263, :267-381
+// It is a new design, not a translation:
+//   * V cameras per call (grid.y = view); the reference renders one.
+//   * Gaussians are depth-sorted once per view (V*P keys), instances are then emitted in depth order and only
+//     *stably partitioned by tile id* (2 radix passes over 8-byte pairs instead of 6 over 12-byte pairs).
+//   * opacity-aware exact tile culling: a (tile, Gaussian) instance is emitted only if some pixel of the tile can
+//     reach alpha >= 1/255.  Instances the reference would skip at every pixel anyway are never created, so
+//     images and gradients are unchanged (`radii` keeps the reference's 3-sigma value).
+//   * the sorted instances are re-packed into a contiguous record stream; blend kernels pull each tile's span
+//     into shared memory with 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier), double buffered.
+//   * no mid-forward host sync is required (capacity hint + device-side overflow flag, checked after queuing).
+//   * backward: warp-shuffle reduction of the per-pixel partials, then vector reductions (red.global.add.v4.f32)
+//     into one 32/48-byte accumulator row per (view, Gaussian); a single fused per-Gaussian kernel turns the
+//     rows into dL/d{mean, scale, rotation, opacity, colour} summed over the views.
+#include <cub/cub.cuh>
+
+#include "raster.cuh"
+
+namespace fnx {
+
+// ---------------------------------------------------------------------------------------------------------------
+// scratch layout
+// ---------------------------------------------------------------------------------------------------------------
+struct DepthScanIn {  // reads tiles_touched in depth-sorted order
+    const uint32_t *tiles_touched;
+    const uint32_t *order;
+    __host__ __device__ uint32_t operator()(uint32_t k) const { return tiles_touched[order[k]]; }
+};
+using DepthScanIter = cub::TransformInputIterator<uint32_t, DepthScanIn, cub::CountingInputIterator<uint32_t>>;
+
+static size_t geom_cub_bytes(int n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 64);
+    DepthScanIter it(cub::CountingInputIterator<uint32_t>(0), DepthScanIn{nullptr, nullptr});
+    cub::DeviceScan::ExclusiveSum(nullptr, b, it, (uint32_t *)nullptr, n);
+    return a > b ? a : b;
+}
+
+GeomView geom_view(void *chunk, int P, int V) {
+    GeomView g;
+    char *p = (char *)chunk;
+    size_t n = (size_t)P * V;
+    g.hdr = carve<GeomHeader>(p, 1);
+    g.cov3D = carve<float>(p, (size_t)P * 6);
+    g.depth = carve<float>(p, n);
+    g.xy = carve<float2>(p, n);
+    g.conic_o = carve<float4>(p, n);
+    g.tiles_touched = carve<uint32_t>(p, n);
+    g.dkeys_in = carve<unsigned long long>(p, n);
+    g.dkeys_out = carve<unsigned long long>(p, n);
+    g.dvals_in = carve<uint32_t>(p, n);
+    g.dvals_out = carve<uint32_t>(p, n);
+    g.offsets = carve<uint32_t>(p, n + 1);
+    g.accum = carve<float>(p, n * 12);
+    g.cub_temp_bytes = geom_cub_bytes((int)n);
+    g.cub_temp = carve<char>(p, g.cub_temp_bytes);
+    return g;
+}
+size_t geom_bytes(int P, int V) {
+    GeomView g = geom_view((void *)0, P, V);
+    return (size_t)((char *)g.cub_temp - (char *)0) + g.cub_temp_bytes + 256;
+}
+
+ImageView image_view(void *chunk, int W, int H, int V) {
+    ImageView im;
+    char *p = (char *)chunk;
+    size_t hw = (size_t)W * H * V;
+    size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
+    im.final_T = carve<float>(p, hw);
+    im.n_contrib = carve<uint32_t>(p, hw);
+    im.ranges = carve<uint2>(p, nt);
+    im.tile_last = carve<uint32_t>(p, nt);
+    return im;
+}
+size_t image_bytes(int W, int H, int V) {
+    ImageView im = image_view((void *)0, W, H, V);
+    size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
+    return (size_t)((char *)im.tile_last - (char *)0) + nt * 4 + 256;
+}
+
+static size_t bin_cub_bytes(long long cap) {
+    size_t a = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)cap, 0, 32);
+    return a;
+}
+BinView bin_view(void *chunk, long long cap, int C) {
+    BinView b;
+    char *p = (char *)chunk;
+    size_t n = (size_t)(cap > 0 ? cap : 1);
+    b.tkeys_in = carve<uint32_t>(p, n);
+    b.tkeys_out = carve<uint32_t>(p, n);
+    b.tvals_in = carve<uint32_t>(p, n);
+    b.tvals_out = carve<uint32_t>(p, n);
+    b.records = carve<char>(p, n * (size_t)(C == 3 ? 48 : 32));
+    b.cub_temp_bytes = bin_cub_bytes((long long)n);
+    b.cub_temp = carve<char>(p, b.cub_temp_bytes);
+    return b;
+}
+size_t binning_bytes(long long cap, int C) {
+    BinView b = bin_view((void *)0, cap, C);
+    return (size_t)((char *)b.cub_temp - (char *)0) + b.cub_temp_bytes + 256;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small column-major 3x3 helper.  m[c][r] = column c, row r; the product sums k = 0,1,2 left to right.
+// (The reference does its 3x3 algebra in that storage/ordering; keeping the same expression trees keeps the
+// fp32 roundings, hence tile assignment and depth order, identical.)
+// ---------------------------------------------------------------------------------------------------------------
+struct M3 {
+    float m[3][3];
+};
+__device__ __forceinline__ M3 m3_mul(const M3 &A, const M3 &B) {
+    M3 R;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+    return R;
+}
+__device__ __forceinline__ M3 m3_T(const M3 &A) {
+    M3 R;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+    return R;
+}
+__device__ __forceinline__ M3 m3_cols(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1,
+                                      float c2) {
+    M3 R;
+    R.m[0][0] = a0; R.m[0][1] = a1; R.m[0][2] = a2;
+    R.m[1][0] = b0; R.m[1][1] = b1; R.m[1][2] = b2;
+    R.m[2][0] = c0; R.m[2][1] = c1; R.m[2][2] = c2;
+    return R;
+}
+
+__device__ __forceinline__ float3 xform4x3(const float3 &p, const float *m) {
+    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float4 xform4x4(const float3 &p, const float *m) {
+    return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+
+// rotation matrix of the un-normalised quaternion (r,x,y,z) in the reference's column order (forward.cu:121-132)
+__device__ __forceinline__ M3 quat_to_R(const float4 q) {
+    float r = q.x, x = q.y, y = q.z, z = q.w;
+    return m3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y), 2.f * (x * y + r * z),
+                   1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x), 2.f * (x * z - r * y), 2.f * (y * z + r * x),
+                   1.f - 2.f * (x * x + y * y));
+}
+
+// Sigma = (S R)^T (S R), upper triangle (forward.cu:113-145)
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 s, float mod, const float4 q, float *cov) {
+    M3 S = m3_cols(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
+    S.m[0][0] = mod * s.x;
+    S.m[1][1] = mod * s.y;
+    S.m[2][2] = mod * s.z;
+    M3 R = quat_to_R(q);
+    M3 M = m3_mul(S, R);
+    M3 Sig = m3_mul(m3_T(M), M);
+    cov[0] = Sig.m[0][0]; cov[1] = Sig.m[0][1]; cov[2] = Sig.m[0][2];
+    cov[3] = Sig.m[1][1]; cov[4] = Sig.m[1][2]; cov[5] = Sig.m[2][2];
+}
+
+// T = W * J with the FoV-clamped view-space mean (forward.cu:70-96 == backward.cu:159-193)
+struct ProjJac {
+    float3 t;
+    float txtz, tytz;
+    M3 W, T;
+};
+__device__ __forceinline__ ProjJac proj_jacobian(const float3 &mean, float fx, float fy, float tfx, float tfy,
+                                                 const float *V) {
+    ProjJac o;
+    float3 t = xform4x3(mean, V);
+    const float limx = 1.3f * tfx, limy = 1.3f * tfy;
+    o.txtz = t.x / t.z;
+    o.tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, o.txtz)) * t.z;
+    t.y = min(limy, max(-limy, o.tytz)) * t.z;
+    M3 J = m3_cols(fx / t.z, 0.0f, -(fx * t.x) / (t.z * t.z), 0.0f, fy / t.z, -(fy * t.y) / (t.z * t.z), 0, 0, 0);
+    o.W = m3_cols(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
+    o.T = m3_mul(o.W, J);
+    o.t = t;
+    return o;
+}
+__device__ __forceinline__ M3 vrk_of(const float *c) { return m3_cols(c[0], c[1], c[2], c[1], c[3], c[4], c[2], c[4], c[5]); }
+
+// auxiliary.h:39-41 -- evaluated in double by the reference (1.0 literals), result rounded to float
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// auxiliary.h:43-50
+__device__ __forceinline__ void get_rect(const float2 p, int max_radius, uint2 &rmin, uint2 &rmax, int gx, int gy) {
+    rmin.x = min(gx, max(0, (int)((p.x - max_radius) / TILE)));
+    rmin.y = min(gy, max(0, (int)((p.y - max_radius) / TILE)));
+    rmax.x = min(gx, max(0, (int)((p.x + max_radius + TILE - 1) / TILE)));
+    rmax.y = min(gy, max(0, (int)((p.y + max_radius + TILE - 1) / TILE)));
+}
+
+// Opacity-aware tile test.  A pixel at offset u from the mean gets alpha = min(.99, o*exp(-q(u))) with
+// q(u) = .5*(a ux^2 + c uy^2) + b ux uy, and is blended only if alpha >= 1/255, i.e. q(u) <= tau = ln(255 o).
+// The tile is needed iff min over its pixel-centre box of q <= tau.  q is convex (checked), so the minimum is 0 if
+// the box contains the mean, else it lies on one of the 4 edges (1-D clamped quadratic).  Conservative margins
+// cover fp32 differences between this bound and the per-pixel evaluation.
+struct TileCull {
+    float a, b, c, tau;
+    bool active;
+};
+__device__ __forceinline__ TileCull make_cull(const float4 con_o, bool exact_rect) {
+    TileCull t;
+    t.a = con_o.x; t.b = con_o.y; t.c = con_o.z;
+    float o = con_o.w;
+    bool pd = (t.a > 0.f) && (t.c > 0.f) && (t.a * t.c - t.b * t.b > 0.f);
+    t.active = !exact_rect && pd && (o == o);
+    t.tau = (o > 0.f) ? __logf(255.0f * o) * 1.001f + 0.05f : -1.0f;  // o <= 0 can never reach 1/255
+    return t;
+}
+__device__ __forceinline__ float edge_min(float A, float B, float Cq, float X, float y0, float y1) {
+    // min over y in [y0,y1] of .5*A*X^2 + B*X*y + .5*Cq*y^2   (Cq > 0)
+    float ys = min(y1, max(y0, -B * X / Cq));
+    return 0.5f * A * X * X + B * X * ys + 0.5f * Cq * ys * ys;
+}
+__device__ __forceinline__ bool tile_needed(const TileCull &t, const float2 mean, int tx, int ty) {
+    if (!t.active) return true;
+    if (t.tau < 0.f) return false;
+    float x0 = tx * TILE - mean.x, x1 = x0 + (TILE - 1);
+    float y0 = ty * TILE - mean.y, y1 = y0 + (TILE - 1);
+    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;
+    float m = edge_min(t.a, t.b, t.c, x0, y0, y1);
+    m = min(m, edge_min(t.a, t.b, t.c, x1, y0, y1));
+    m = min(m, edge_min(t.c, t.b, t.a, y0, x0, x1));
+    m = min(m, edge_min(t.c, t.b, t.a, y1, x0, x1));
+    return m <= t.tau;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: per (view, Gaussian) preprocess.  forward.cu:148-244
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+preprocess_kernel(int P, int V, const float *__restrict__ means3D, const float3 *__restrict__ scales, float scale_modifier,
+                  const float4 *__restrict__ rotations, const float *__restrict__ opacities,
+                  const float *__restrict__ cov3D_precomp, const float *__restrict__ view_matrix,
+                  const float *__restrict__ proj_matrix, int W, int H, float tan_fov_x, float tan_fov_y, float focal_x,
+                  float focal_y, int gx, int gy, bool exact_rect, int *__restrict__ radii, GeomView g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (i >= P) return;
+    const size_t slot = (size_t)v * P + i;
+    const float *Vm = view_matrix + 16 * v;
+    const float *Pm = proj_matrix + 16 * v;
+
+    radii[slot] = 0;
+    g.tiles_touched[slot] = 0;
+    g.dvals_in[slot] = (uint32_t)slot;
+    unsigned long long key = ((unsigned long long)v << 32) | 0xFFFFFFFFull;  // invisible: sorts last in its view
+    g.dkeys_in[slot] = key;
+
+    const float3 p_orig = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    const float4 p_hom = xform4x4(p_orig, Pm);
+    const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+    const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+    const float3 p_view = xform4x3(p_orig, Vm);
+    if (p_view.z <= 0.2f) return;  // auxiliary.h:138
+
+    float cov_local[6];
+    const float *cov3D;
+    if (cov3D_precomp != nullptr) {
+        cov3D = cov3D_precomp + 6 * (size_t)i;
+    } else {
+        cov3d_from_scale_rot(scales[i], scale_modifier, rotations[i], cov_local);
+        // every view writes the same six values (benign); a Gaussian culled in view 0 may be visible in view 1
+#pragma unroll
+        for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = cov_local[k];
+        cov3D = cov_local;
+    }
+    float c6[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) c6[k] = cov3D[k];
+
+    ProjJac pj = proj_jacobian(p_orig, focal_x, focal_y, tan_fov_x, tan_fov_y, Vm);
+    M3 Vrk = vrk_of(c6);
+    M3 cov2 = m3_mul(m3_mul(m3_T(pj.T), m3_T(Vrk)), pj.T);
+    const float ca = cov2.m[0][0] + 0.3f, cb = cov2.m[0][1], cc = cov2.m[1][1] + 0.3f;
+
+    const float det = (ca * cc - cb * cb);
+    if (det == 0.0f) return;
+    const float det_inv = 1.f / det;
+    const float3 conic = make_float3(cc * det_inv, -cb * det_inv, ca * det_inv);
+
+    const float mid = 0.5f * (ca + cc);
+    const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+    const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+    const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+    const float2 point_image = make_float2(ndc2pix(p_proj.x, W), ndc2pix(p_proj.y, H));
+    uint2 rmin, rmax;
+    get_rect(point_image, (int)my_radius, rmin, rmax, gx, gy);
+    if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) return;
+
+    const float4 con_o = make_float4(conic.x, conic.y, conic.z, opacities[i]);
+    // count the tiles that can actually receive a contribution
+    TileCull tc = make_cull(con_o, exact_rect);
+    uint32_t cnt = 0;
+    if (!tc.active) {
+        cnt = (rmax.y - rmin.y) * (rmax.x - rmin.x);
+    } else {
+        for (int ty = rmin.y; ty < (int)rmax.y; ty++)
+            for (int tx = rmin.x; tx < (int)rmax.x; tx++) cnt += tile_needed(tc, point_image, tx, ty) ? 1u : 0u;
+    }
+    g.depth[slot] = p_view.z;
+    radii[slot] = (int)my_radius;
+    g.xy[slot] = point_image;
+    g.conic_o[slot] = con_o;
+    g.tiles_touched[slot] = cnt;
+    g.dkeys_in[slot] = ((unsigned long long)v << 32) | (unsigned long long)__float_as_uint(p_view.z);
+}
+
+// writes total instance count + overflow flag after the scan (one thread)
+__global__ void finish_scan_kernel(int n, GeomView g, long long capacity, long long *pinned_out) {
+    uint32_t last = g.dvals_out[n - 1];
+    long long total = (long long)g.offsets[n - 1] + (long long)g.tiles_touched[last];
+    g.hdr->num_rendered = total;
+    g.hdr->capacity = capacity;
+    g.hdr->overflow = (capacity >= 0 && total > capacity) ? 1 : 0;
+    if (pinned_out) *pinned_out = total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: emit (tile id, slot) instances in depth order.  Replaces duplicateWithKeys, rasterizer_impl.cu:67-104.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emit_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict__ radii, GeomView g, BinView b) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (g.hdr->overflow) return;
+    const uint32_t slot = g.dvals_out[k];
+    const uint32_t cnt = g.tiles_touched[slot];
+    if (cnt == 0) return;
+    uint32_t off = g.offsets[k];
+    const int v = slot / P;
+    const float2 xy = g.xy[slot];
+    const float4 con_o = g.conic_o[slot];
+    uint2 rmin, rmax;
+    get_rect(xy, radii[slot], rmin, rmax, gx, gy);
+    TileCull tc = make_cull(con_o, exact_rect);
+    const uint32_t tile_base = (uint32_t)v * gx * gy;
+    for (int ty = rmin.y; ty < (int)rmax.y; ty++)
+        for (int tx = rmin.x; tx < (int)rmax.x; tx++) {
+            if (!tile_needed(tc, xy, tx, ty)) continue;
+            b.tkeys_in[off] = tile_base + ty * gx + tx;
+            b.tvals_in[off] = slot;
+            off++;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6: pack the sorted instances into the record stream + per-tile ranges (identifyTileRanges, rasterizer_impl.cu:109-128)
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+pack_kernel(long long cap, int P, const float *__restrict__ colors, GeomView g, BinView b, uint2 *__restrict__ ranges) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long R = g.hdr->num_rendered;
+    if (i >= R || i >= cap || g.hdr->overflow) return;
+    const uint32_t slot = b.tvals_out[i];
+    const uint32_t tile = b.tkeys_out[i];
+    const float2 xy = g.xy[slot];
+    const float4 co = g.conic_o[slot];
+    const uint32_t gi = slot % (uint32_t)P;
+    float4 *rec = reinterpret_cast<float4 *>(b.records + (size_t)i * RecBytes<C>::value);
+    rec[0] = make_float4(xy.x, xy.y, co.x, co.y);
+    if (C == 3) {
+        const float c0 = colors[3 * (size_t)gi], c1 = colors[3 * (size_t)gi + 1], c2 = colors[3 * (size_t)gi + 2];
+        rec[1] = make_float4(co.z, co.w, c0, c1);
+        rec[2] = make_float4(c2, __uint_as_float(slot), g.depth[slot], 0.f);
+    } else {
+        rec[1] = make_float4(co.z, co.w, colors[gi], __uint_as_float(slot));
+    }
+    if (i == 0) ranges[tile].x = 0;
+    else {
+        const uint32_t prev = b.tkeys_out[i - 1];
+        if (prev != tile) {
+            ranges[prev].y = (uint32_t)i;
+            ranges[tile].x = (uint32_t)i;
+        }
+    }
+    if (i == R - 1) ranges[tile].y = (uint32_t)R;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// alpha of one (pixel, record) pair -- the ONE place the blend decision is made, shared by forward and backward.
+// The reference evaluates expf() (forward.cu:330, backward.cu:479).  We use the fast ex2-based path and fall back to
+// expf() only inside a narrow band around the 1/255 cut so that the keep/skip decision is the reference's.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_alpha(float x, float y, float a, float b, float c, float o, float px, float py,
+                                           float &dx, float &dy, float &G, float &alpha) {
+    dx = x - px;
+    dy = y - py;
+    const float power = -0.5f * (a * dx * dx + c * dy * dy) - b * dx * dy;
+    if (power > 0.0f) return false;
+    G = __expf(power);
+    alpha = min(ALPHA_MAX, o * G);
+    if (fabsf(alpha - ALPHA_MIN) < 4e-6f) {
+        G = expf(power);
+        alpha = min(ALPHA_MAX, o * G);
+    }
+    return !(alpha < ALPHA_MIN);
+}
+
+constexpr int BATCH = 128;  // records per smem stage
+constexpr int STAGES = 2;
+
+// ---------------------------------------------------------------------------------------------------------------
+// K7: blend forward.  One CTA per (tile, view); warp w owns the 8x4 pixel patch (w&1, w>>1).  forward.cu:249-373
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(TILE_PIX)
+blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records, const float *__restrict__ depth_of_slot,
+                 const float *__restrict__ bg, const GeomHeader *__restrict__ hdr, ImageView im,
+                 float *__restrict__ out_color, float *__restrict__ out_depth) {
+    constexpr int REC = RecBytes<C>::value;
+    __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
+    __shared__ __align__(8) uint64_t s_bar[STAGES];
+
+    const int tile = blockIdx.x, v = blockIdx.y;
+    const int ntiles = gx * gy;
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t HW = (size_t)W * H;
+    const size_t pix_id = (size_t)v * HW + (size_t)py * W + px;
+
+    uint2 range = im.ranges[(size_t)v * ntiles + tile];
+    if (hdr->overflow) range = make_uint2(0, 0);
+    const int total = (int)(range.y - range.x);
+    const int nbatch = (total + BATCH - 1) / BATCH;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&s_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++)
+            if (s < nbatch) {
+                const int n = min(BATCH, total - s * BATCH);
+                mbar_arrive_expect_tx(&s_bar[s], n * REC);
+                bulk_g2s(s_rec[s], records + ((size_t)range.x + (size_t)s * BATCH) * REC, n * REC, &s_bar[s]);
+            }
+    }
+
+    float T = 1.0f;
+    float Cacc[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) Cacc[ch] = 0.f;
+    float D = DEPTH_DEFAULT;
+    uint32_t last_contributor = 0;
+    bool done = !inside;
+
+    int issued = min(STAGES, nbatch);  // batches whose copy has been issued (meaningful in thread 0)
+    int bi = 0;
+    for (; bi < nbatch; bi++) {
+        const int s = bi % STAGES;
+        // whole tile finished?  (also orders the previous stage's reads before its buffer is refilled)
+        if (__syncthreads_count(done) == TILE_PIX) break;
+        if (threadIdx.x == 0 && bi >= 1 && bi + STAGES - 1 < nbatch) {
+            // refill the stage consumed in the previous iteration
+            const int nb = bi + STAGES - 1, ns = nb % STAGES;
+            const int n = min(BATCH, total - nb * BATCH);
+            mbar_arrive_expect_tx(&s_bar[ns], n * REC);
+            bulk_g2s(s_rec[ns], records + ((size_t)range.x + (size_t)nb * BATCH) * REC, n * REC, &s_bar[ns]);
+            issued = nb + 1;
+        }
+        mbar_wait(&s_bar[s], (bi / STAGES) & 1);
+        const int n = min(BATCH, total - bi * BATCH);
+        const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
+        if (!done) {
+            for (int j = 0; j < n; j++) {
+                const float4 r0 = rec[j * (REC / 16)];
+                const float4 r1 = rec[j * (REC / 16) + 1];
+                float dx, dy, G, alpha;
+                if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf, dx, dy, G, alpha)) continue;
+                const float test_T = T * (1 - alpha);
+                if (test_T < T_EPS) {
+                    done = true;
+                    break;
+                }
+                if (C == 3) {
+                    const float4 r2 = rec[j * 3 + 2];
+                    Cacc[0] += r1.z * alpha * T;
+                    Cacc[1 % C] += r1.w * alpha * T;
+                    Cacc[2 % C] += r2.x * alpha * T;
+                    if (T > 0.5f && test_T < 0.5) D = r2.z;
+                } else {
+                    Cacc[0] += r1.z * alpha * T;
+                    if (T > 0.5f && test_T < 0.5) D = depth_of_slot[__float_as_uint(r1.w)];
+                }
+                T = test_T;
+                last_contributor = (uint32_t)(bi * BATCH + j + 1);
+            }
+        }
+    }
+
+    // early exit: bulk copies still in flight must land before this CTA's shared memory is released
+    if (threadIdx.x == 0)
+        for (int nb = bi; nb < issued; nb++) mbar_wait(&s_bar[nb % STAGES], (nb / STAGES) & 1);
+
+    // tile-wide max of last_contributor: where the backward starts
+    uint32_t wl = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+    __shared__ uint32_t s_last[TILE_PIX / 32];
+    if (lane == 0) s_last[warp] = wl;
+    if (inside) {
+        im.final_T[pix_id] = T;
+        im.n_contrib[pix_id] = last_contributor;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) out_color[((size_t)v * C + ch) * HW + (size_t)py * W + px] = Cacc[ch] + T * bg[ch];
+        out_depth[pix_id] = D;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < TILE_PIX / 32; w++) m = max(m, s_last[w]);
+        im.tile_last[(size_t)v * ntiles + tile] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K8: blend backward.  backward.cu:384-536.  Walks the tile's records back to front starting at the last record any
+// pixel of the tile used; per record the 32 pixels of a warp are reduced with shuffles, then lane 0 issues
+// 2-3 vector reductions into the (view, Gaussian) accumulator row.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(TILE_PIX)
+blend_bwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records, const float *__restrict__ bg,
+                 const GeomHeader *__restrict__ hdr, ImageView im, const float *__restrict__ dL_dpixels,
+                 float *__restrict__ accum) {
+    constexpr int REC = RecBytes<C>::value;
+    constexpr int ACC = AccFloats<C>::value;
+    __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
+    __shared__ __align__(8) uint64_t s_bar[STAGES];
+
+    const int tile = blockIdx.x, v = blockIdx.y;
+    const int ntiles = gx * gy;
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t HW = (size_t)W * H;
+    const size_t pix_id = (size_t)v * HW + (size_t)py * W + px;
+
+    const uint2 range = im.ranges[(size_t)v * ntiles + tile];
+    int total = (int)im.tile_last[(size_t)v * ntiles + tile];  // records [0,total) of the span matter
+    if (hdr->overflow) total = 0;
+    if (total == 0) return;
+    const int nbatch = (total + BATCH - 1) / BATCH;
+    // batch bi (processing order) covers span indices [lo, hi) with hi = total - bi*BATCH
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&s_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++)
+            if (s < nbatch) {
+                const int hi = total - s * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+                mbar_arrive_expect_tx(&s_bar[s], n * REC);
+                bulk_g2s(s_rec[s], records + ((size_t)range.x + lo) * REC, n * REC, &s_bar[s]);
+            }
+    }
+
+    const float T_final = inside ? im.final_T[pix_id] : 0.f;
+    float T = T_final;
+    const int last_contributor = inside ? (int)im.n_contrib[pix_id] : 0;
+    float accum_rec[C], dL_dpixel[C], last_color[C];
+    float bg_dot_dpixel = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+        accum_rec[ch] = 0.f;
+        last_color[ch] = 0.f;
+        dL_dpixel[ch] = inside ? dL_dpixels[((size_t)v * C + ch) * HW + (size_t)py * W + px] : 0.f;
+        bg_dot_dpixel += bg[ch] * dL_dpixel[ch];
+    }
+    float last_alpha = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    for (int bi = 0; bi < nbatch; bi++) {
+        const int s = bi % STAGES;
+        if (bi >= 1) {
+            __syncthreads();  // everyone finished reading the stage that is about to be refilled
+            if (threadIdx.x == 0 && bi + STAGES - 1 < nbatch) {
+                const int nb = bi + STAGES - 1, ns = nb % STAGES;
+                const int hi = total - nb * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+                mbar_arrive_expect_tx(&s_bar[ns], n * REC);
+                bulk_g2s(s_rec[ns], records + ((size_t)range.x + lo) * REC, n * REC, &s_bar[ns]);
+            }
+        }
+        mbar_wait(&s_bar[s], (bi / STAGES) & 1);
+        const int hi = total - bi * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+        const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
+        for (int j = n - 1; j >= 0; j--) {
+            const int idx = lo + j;  // 0-based position in the tile's span
+            const float4 r0 = rec[j * (REC / 16)];
+            const float4 r1 = rec[j * (REC / 16) + 1];
+            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+            bool contrib = (idx < last_contributor) && pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf, dx, dy, G, alpha);
+            if (!__any_sync(0xffffffffu, contrib)) continue;
+
+            float g_col[C];
+            float g_mx = 0.f, g_my = 0.f, g_ca = 0.f, g_cb = 0.f, g_cc = 0.f, g_op = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) g_col[ch] = 0.f;
+            uint32_t slot_bits;
+            float col[C];
+            if (C == 3) {
+                const float4 r2 = rec[j * 3 + 2];
+                col[0] = r1.z; col[1 % C] = r1.w; col[2 % C] = r2.x;
+                slot_bits = __float_as_uint(r2.y);
+            } else {
+                col[0] = r1.z;
+                slot_bits = __float_as_uint(r1.w);
+            }
+            if (contrib) {
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.0f;
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) {
+                    const float c = col[ch];
+                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                    last_color[ch] = c;
+                    dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
+                    g_col[ch] = dchannel_dcolor * dL_dpixel[ch];
+                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                const float dL_dG = r1.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+                const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+                g_mx = dL_dG * dG_ddelx * ddelx_dx;
+                g_my = dL_dG * dG_ddely * ddely_dy;
+                g_ca = -0.5f * gdx * dx * dL_dG;
+                g_cb = -0.5f * gdx * dy * dL_dG;
+                g_cc = -0.5f * gdy * dy * dL_dG;
+                g_op = G * dL_dalpha;
+            }
+            g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
+            g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb); g_cc = warp_sum(g_cc);
+            g_op = warp_sum(g_op);
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) g_col[ch] = warp_sum(g_col[ch]);
+            if (lane == 0) {
+                float *row = accum + (size_t)slot_bits * ACC;
+                red_add_v4(row, g_mx, g_my, g_ca, g_cb);
+                if (C == 3) {
+                    red_add_v4(row + 4, g_cc, g_op, g_col[0], g_col[1 % C]);
+                    red_add(row + 8, g_col[2 % C]);
+                } else {
+                    red_add_v4(row + 4, g_cc, g_op, g_col[0], 0.f);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K9: per-Gaussian backward, fusing computeCov2DCUDA (backward.cu:137-263), preprocessCUDA (:332-381) and
+// computeCov3D (:267-327), summed over the V views.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+geom_bwd_kernel(int P, int V, const float *__restrict__ means3D, const float3 *__restrict__ scales, float scale_modifier,
+                const float4 *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
+                const float *__restrict__ view_matrix, const float *__restrict__ proj_matrix, int W, int H,
+                float tan_fov_x, float tan_fov_y, float focal_x, float focal_y, const int *__restrict__ radii,
+                const float *__restrict__ cov3D_geom, const float *__restrict__ accum, fnx_raster_grads out) {
+    constexpr int ACC = AccFloats<C>::value;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float3 mean = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    const float *cov3D = (cov3D_precomp != nullptr ? cov3D_precomp : cov3D_geom) + 6 * (size_t)i;
+    float c6[6];
+    bool any_visible = false;
+    for (int v = 0; v < V; v++) any_visible |= radii[(size_t)v * P + i] > 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) c6[k] = any_visible ? cov3D[k] : 0.f;
+    const M3 Vrk = vrk_of(c6);
+
+    float3 d_mean = make_float3(0.f, 0.f, 0.f);
+    float d_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float d_op = 0.f, d_col[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) d_col[ch] = 0.f;
+
+    for (int v = 0; v < V; v++) {
+        const size_t slot = (size_t)v * P + i;
+        const float *row = accum + slot * ACC;
+        const float4 a0 = *reinterpret_cast<const float4 *>(row);
+        const float4 a1 = *reinterpret_cast<const float4 *>(row + 4);
+        const float g2x = a0.x, g2y = a0.y;
+        if (out.dL_dmeans2D) {
+            out.dL_dmeans2D[3 * slot] = g2x;
+            out.dL_dmeans2D[3 * slot + 1] = g2y;
+            out.dL_dmeans2D[3 * slot + 2] = 0.f;
+        }
+        d_op += a1.y;
+        d_col[0] += a1.z;
+        if (C == 3) {
+            d_col[1 % C] += a1.w;
+            d_col[2 % C] += row[8];
+        }
+        if (!(radii[slot] > 0)) continue;
+        const float *Vm = view_matrix + 16 * v;
+        const float *Pm = proj_matrix + 16 * v;
+        const float3 dL_dconic = make_float3(a0.z, a0.w, a1.x);
+
+        // ---- cov2D backward ----
+        ProjJac pj = proj_jacobian(mean, focal_x, focal_y, tan_fov_x, tan_fov_y, Vm);
+        const float limx = 1.3f * tan_fov_x, limy = 1.3f * tan_fov_y;
+        const float x_grad_mul = pj.txtz < -limx || pj.txtz > limx ? 0 : 1;
+        const float y_grad_mul = pj.tytz < -limy || pj.tytz > limy ? 0 : 1;
+        const M3 &T = pj.T;
+        const M3 &Wm = pj.W;
+        M3 cov2D = m3_mul(m3_mul(m3_T(T), m3_T(Vrk)), T);
+        const float a = cov2D.m[0][0] + 0.3f, b = cov2D.m[0][1], c = cov2D.m[1][1] + 0.3f;
+        const float denom = a * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+            dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+            d_cov[0] += (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+            d_cov[3] += (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+            d_cov[5] += (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+            d_cov[1] += 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
+            d_cov[2] += 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
+            d_cov[4] += 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+        }
+        const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da + (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
+        const float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da + (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
+        const float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da + (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
+        const float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc + (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
+        const float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc + (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
+        const float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc + (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
+        const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
+        const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
+        const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
+        const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
+        const float tz = 1.f / pj.t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+        const float dL_dtx = x_grad_mul * -focal_x * tz2 * dL_dJ02;
+        const float dL_dty = y_grad_mul * -focal_y * tz2 * dL_dJ12;
+        const float dL_dtz = -focal_x * tz2 * dL_dJ00 - focal_y * tz2 * dL_dJ11 + (2 * focal_x * pj.t.x) * tz3 * dL_dJ02 + (2 * focal_y * pj.t.y) * tz3 * dL_dJ12;
+        // transformVec4x3Transpose (auxiliary.h:79-86)
+        float3 dm = make_float3(Vm[0] * dL_dtx + Vm[1] * dL_dty + Vm[2] * dL_dtz, Vm[4] * dL_dtx + Vm[5] * dL_dty + Vm[6] * dL_dtz,
+                                Vm[8] * dL_dtx + Vm[9] * dL_dty + Vm[10] * dL_dtz);
+        // ---- projection backward (backward.cu:357-372) ----
+        const float4 m_hom = xform4x4(mean, Pm);
+        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        const float mul1 = (Pm[0] * mean.x + Pm[4] * mean.y + Pm[8] * mean.z + Pm[12]) * m_w * m_w;
+        const float mul2 = (Pm[1] * mean.x + Pm[5] * mean.y + Pm[9] * mean.z + Pm[13]) * m_w * m_w;
+        float3 dm2;
+        dm2.x = (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
+        dm2.y = (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
+        dm2.z = (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
+        dm.x += dm2.x; dm.y += dm2.y; dm.z += dm2.z;
+        d_mean.x += dm.x; d_mean.y += dm.y; d_mean.z += dm.z;
+    }
+
+    if (out.dL_dmeans3D) {
+        out.dL_dmeans3D[3 * i] = d_mean.x; out.dL_dmeans3D[3 * i + 1] = d_mean.y; out.dL_dmeans3D[3 * i + 2] = d_mean.z;
+    }
+    if (out.dL_dopacity) out.dL_dopacity[i] = d_op;
+    if (out.dL_dcolors) {
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) out.dL_dcolors[(size_t)i * C + ch] = d_col[ch];
+    }
+    if (out.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) out.dL_dcov3D[6 * (size_t)i + k] = d_cov[k];
+    }
+    if (scales != nullptr && (out.dL_dscales || out.dL_drotations)) {
+        float3 ds = make_float3(0.f, 0.f, 0.f);
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any_visible) {
+            // computeCov3D backward (backward.cu:267-327)
+            const float4 q = rotations[i];
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            const M3 R = quat_to_R(q);
+            const float3 sc = scales[i];
+            const float3 s = make_float3(scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z);
+            M3 S = m3_cols(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
+            S.m[0][0] = s.x; S.m[1][1] = s.y; S.m[2][2] = s.z;
+            const M3 M = m3_mul(S, R);
+            const M3 dSig = m3_cols(d_cov[0], 0.5f * d_cov[1], 0.5f * d_cov[2], 0.5f * d_cov[1], d_cov[3], 0.5f * d_cov[4],
+                                    0.5f * d_cov[2], 0.5f * d_cov[4], d_cov[5]);
+            M3 M2;
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) M2.m[cc][rr] = 2.0f * M.m[cc][rr];
+            const M3 dM = m3_mul(M2, dSig);
+            const M3 Rt = m3_T(R);
+            M3 dMt = m3_T(dM);
+            ds.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+            ds.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+            ds.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                dMt.m[0][rr] *= s.x;
+                dMt.m[1][rr] *= s.y;
+                dMt.m[2][rr] *= s.z;
+            }
+            dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+            dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+            dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+            dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        }
+        if (out.dL_dscales) {
+            out.dL_dscales[3 * i] = ds.x; out.dL_dscales[3 * i + 1] = ds.y; out.dL_dscales[3 * i + 2] = ds.z;
+        }
+        if (out.dL_drotations) *reinterpret_cast<float4 *>(out.dL_drotations + 4 * (size_t)i) = dq;
+    }
+}
+
+__global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ view_matrix,
+                                    uint8_t *__restrict__ present) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float3 p = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    const float3 pv = xform4x3(p, view_matrix);
+    present[i] = !(pv.z <= 0.2f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct PinnedSlots {  // ring of pinned int64 slots + events for the sync-free instance count read-back
+    static constexpr int N = 64;
+    long long *host = nullptr;
+    cudaEvent_t ev[N];
+    int next = 0;
+    bool ok = false;
+    int init() {
+        if (ok) return FNX_OK;
+        FNX_CUDA_TRY(cudaHostAlloc((void **)&host, sizeof(long long) * N, cudaHostAllocDefault));
+        for (int i = 0; i < N; i++) FNX_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        ok = true;
+        return FNX_OK;
+    }
+};
+static thread_local PinnedSlots g_slots;
+
+static int validate(const fnx_raster_args *a) {
+    FNX_REQUIRE(a != nullptr, "args is NULL");
+    FNX_REQUIRE(a->C == 1 || a->C == 3, "C must be 1 or 3 (got %d)", a->C);
+    FNX_REQUIRE(a->P >= 0 && a->V >= 1 && a->W > 0 && a->H > 0, "bad sizes P=%d V=%d W=%d H=%d", a->P, a->V, a->W, a->H);
+    if (a->sh != nullptr) {
+        set_error("SH colours are not supported: FluidNexus pipes always pass colors_precomp (FD/renderer/pipe_fluid.py:107-118)");
+        return FNX_ERR_UNSUPPORTED;
+    }
+    if (a->P > 0) {
+        FNX_REQUIRE(a->means3D && a->colors && a->opacities, "means3D / colors / opacities must be given");
+        FNX_REQUIRE((a->scales && a->rotations) || a->cov3D_precomp, "need scales+rotations or cov3D_precomp");
+        FNX_REQUIRE(a->view_matrix && a->proj_matrix && a->bg, "view_matrix / proj_matrix / bg must be given");
+    }
+    FNX_REQUIRE((long long)a->P * a->V < (1ll << 31), "P*V too large");
+    return FNX_OK;
+}
+
+template <int C>
+static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g, BinView &b, ImageView &im,
+                         long long cap, long long sort_items, const int *radii, float *out_color, float *out_depth) {
+    const int P = a->P, V = a->V, n = P * V;
+    const int gx = (a->W + TILE - 1) / TILE, gy = (a->H + TILE - 1) / TILE, ntiles = gx * gy;
+    const bool exact_rect = (a->flags & FNX_EXACT_RECT) != 0;
+    FNX_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)ntiles * V, st));
+    if (sort_items > 0) {
+        const bool padded = (a->flags & FNX_NO_HOST_SYNC) != 0 || a->instance_capacity_hint > 0;
+        if (padded) FNX_CUDA_TRY(cudaMemsetAsync(b.tkeys_in, 0xFF, sizeof(uint32_t) * (size_t)sort_items, st));
+        emit_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, P, gx, gy, exact_rect, radii, g, b);
+        FNX_LAUNCH_CHECK("emit_kernel");
+        const int end_bit = ceil_log2_u64((uint64_t)ntiles * V + 1);
+        size_t tb = b.cub_temp_bytes;
+        FNX_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, b.tkeys_in, b.tkeys_out, b.tvals_in, b.tvals_out,
+                                                     (int)sort_items, 0, end_bit, st));
+        pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, a->colors, g, b, im.ranges);
+        FNX_LAUNCH_CHECK("pack_kernel");
+    }
+    dim3 grid(ntiles, V);
+    blend_fwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(a->W, a->H, gx, gy, b.records, g.depth, a->bg, g.hdr, im, out_color, out_depth);
+    FNX_LAUNCH_CHECK("blend_fwd_kernel");
+    return FNX_OK;
+}
+
+template <int C>
+static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx_alloc_fn ab, void *cb, fnx_alloc_fn ai,
+                        void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                        fnx_raster_scratch *scratch, cudaStream_t st) {
+    FNX_REQUIRE(ag && ab && ai && scratch && num_rendered_host, "allocators / scratch / num_rendered_host must be given");
+    FNX_REQUIRE(out_color && out_depth, "out_color / out_depth must be given");
+    const int P = a->P, V = a->V, W = a->W, H = a->H;
+    const size_t HW = (size_t)W * H;
+    memset(scratch, 0, sizeof(*scratch));
+    *num_rendered_host = 0;
+    if (P == 0) {  // rasterize_points.cu:81: zero outputs
+        FNX_CUDA_TRY(cudaMemsetAsync(out_color, 0, sizeof(float) * HW * C * V, st));
+        FNX_CUDA_TRY(cudaMemsetAsync(out_depth, 0, sizeof(float) * HW * V, st));
+        return FNX_OK;
+    }
+    FNX_REQUIRE(radii != nullptr, "radii must be given");
+    int rc = g_slots.init();
+    if (rc) return rc;
+    const int n = P * V;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const float focal_y = H / (2.0f * a->tan_fov_y), focal_x = W / (2.0f * a->tan_fov_x);
+    const bool exact_rect = (a->flags & FNX_EXACT_RECT) != 0;
+    const bool no_sync = (a->flags & FNX_NO_HOST_SYNC) != 0;
+
+    scratch->geom_bytes = geom_bytes(P, V);
+    scratch->geom = ag(cg, scratch->geom_bytes);
+    scratch->image_bytes = image_bytes(W, H, V);
+    scratch->image = ai(ci, scratch->image_bytes);
+    if (!scratch->geom || !scratch->image) {
+        set_error("allocation callback returned NULL");
+        return FNX_ERR_ALLOC;
+    }
+    GeomView g = geom_view(scratch->geom, P, V);
+    ImageView im = image_view(scratch->image, W, H, V);
+
+    dim3 pgrid((P + 255) / 256, V);
+    preprocess_kernel<<<pgrid, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
+                                             (const float4 *)a->rotations, a->opacities, a->cov3D_precomp, a->view_matrix,
+                                             a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y, gx, gy,
+                                             exact_rect, radii, g);
+    FNX_LAUNCH_CHECK("preprocess_kernel");
+    size_t tb = g.cub_temp_bytes;
+    const int dbits = 32 + ceil_log2_u64((uint64_t)V);
+    FNX_CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.dkeys_in, g.dkeys_out, g.dvals_in, g.dvals_out, n, 0, dbits, st));
+    DepthScanIter it(cub::CountingInputIterator<uint32_t>(0), DepthScanIn{g.tiles_touched, g.dvals_out});
+    tb = g.cub_temp_bytes;
+    FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, it, g.offsets, n, st));
+
+    const int slot_id = g_slots.next;
+    g_slots.next = (g_slots.next + 1) % PinnedSlots::N;
+    long long *pinned = g_slots.host + slot_id;
+    *pinned = -1;
+    long long cap = a->instance_capacity_hint > 0 ? a->instance_capacity_hint : -1;
+    finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, pinned);
+    FNX_LAUNCH_CHECK("finish_scan_kernel");
+    FNX_CUDA_TRY(cudaEventRecord(g_slots.ev[slot_id], st));
+    scratch->binning = nullptr;
+
+    long long R = -1;
+    const bool exact = cap < 0;
+    if (exact) {  // exact sizing: one host sync, like the reference (rasterizer_impl.cu:263-264)
+        FNX_REQUIRE(!no_sync, "FNX_NO_HOST_SYNC needs instance_capacity_hint > 0");
+        FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[slot_id]));
+        R = *pinned;
+        cap = R;
+    }
+    for (int attempt = 0; attempt < 3; attempt++) {
+        scratch->binning_bytes = binning_bytes(cap, C);
+        scratch->binning = ab(cb, scratch->binning_bytes);
+        if (!scratch->binning) {
+            set_error("allocation callback returned NULL");
+            return FNX_ERR_ALLOC;
+        }
+        scratch->binning_capacity = cap;
+        BinView b = bin_view(scratch->binning, cap, C);
+        if (attempt >= 1) {  // re-arm capacity / overflow flag for the retry
+            finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, nullptr);
+            FNX_LAUNCH_CHECK("finish_scan_kernel");
+        }
+        rc = bin_and_blend<C>(a, st, g, b, im, cap, exact ? R : cap, radii, out_color, out_depth);
+        if (rc) return rc;
+        if (exact) break;
+        if (no_sync) {
+            R = -1;
+            break;
+        }
+        // everything is queued; the count has almost surely landed already -- this wait does not stall the GPU
+        FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[slot_id]));
+        R = *pinned;
+        if (R <= cap) break;
+        cap = R + R / 8 + 1024;  // overflow: grow and redo binning + blend
+    }
+    *num_rendered_host = R;
+    scratch->check_slot = slot_id;
+    return FNX_OK;
+}
+
+template <int C>
+static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                         const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *gr, cudaStream_t st) {
+    FNX_REQUIRE(scratch && gr, "scratch / grads must be given");
+    const int P = a->P, V = a->V, W = a->W, H = a->H;
+    if (P == 0) return FNX_OK;
+    FNX_REQUIRE(scratch->geom && scratch->image && scratch->binning, "scratch buffers missing (forward not run?)");
+    FNX_REQUIRE(radii && dL_dout_color, "radii / dL_dout_color must be given");
+    (void)num_rendered;
+    constexpr int ACC = AccFloats<C>::value;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
+    const float focal_y = H / (2.0f * a->tan_fov_y), focal_x = W / (2.0f * a->tan_fov_x);
+    GeomView g = geom_view(scratch->geom, P, V);
+    ImageView im = image_view(scratch->image, W, H, V);
+    // capacity is only needed to locate the record stream, which sits at a capacity-dependent offset
+    long long cap = 0;
+    {
+        // binning_bytes is monotone in cap; recover cap from the header written by the forward (host copy kept in scratch)
+        cap = scratch->binning_capacity;
+    }
+    BinView b = bin_view(scratch->binning, cap, C);
+    FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
+    dim3 grid(ntiles, V);
+    blend_bwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(W, H, gx, gy, b.records, a->bg, g.hdr, im, dL_dout_color, g.accum);
+    FNX_LAUNCH_CHECK("blend_bwd_kernel");
+    geom_bwd_kernel<C><<<(P + 255) / 256, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
+                                                        (const float4 *)a->rotations, a->cov3D_precomp, a->view_matrix,
+                                                        a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y,
+                                                        radii, g.cov3D, g.accum, *gr);
+    FNX_LAUNCH_CHECK("geom_bwd_kernel");
+    return FNX_OK;
+}
+
+}  // namespace fnx
+
+using namespace fnx;
+
+extern "C" {
+
+size_t fnx_raster_geom_bytes(int32_t P, int32_t V) { return geom_bytes(P, V); }
+size_t fnx_raster_image_bytes(int32_t W, int32_t H, int32_t V) { return image_bytes(W, H, V); }
+size_t fnx_raster_binning_bytes(int64_t cap, int32_t C) { return binning_bytes(cap, C); }
+
+int fnx_raster_forward(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx_alloc_fn ab, void *cb, fnx_alloc_fn ai,
+                       void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                       fnx_raster_scratch *scratch, fnx_stream_t stream) {
+    int rc = validate(a);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->C == 3) return forward_impl<3>(a, ag, cg, ab, cb, ai, ci, out_color, out_depth, radii, num_rendered_host, scratch, st);
+    return forward_impl<1>(a, ag, cg, ab, cb, ai, ci, out_color, out_depth, radii, num_rendered_host, scratch, st);
+}
+int fnx_raster_forward_ch1(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx_alloc_fn ab, void *cb, fnx_alloc_fn ai,
+                           void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                           fnx_raster_scratch *scratch, fnx_stream_t stream) {
+    if (a && a->C != 1) { set_error("fnx_raster_forward_ch1 needs C == 1 (got %d)", a->C); return FNX_ERR_INVALID; }
+    return fnx_raster_forward(a, ag, cg, ab, cb, ai, ci, out_color, out_depth, radii, num_rendered_host, scratch, stream);
+}
+int fnx_raster_forward_ch3(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx_alloc_fn ab, void *cb, fnx_alloc_fn ai,
+                           void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                           fnx_raster_scratch *scratch, fnx_stream_t stream) {
+    if (a && a->C != 3) { set_error("fnx_raster_forward_ch3 needs C == 3 (got %d)", a->C); return FNX_ERR_INVALID; }
+    return fnx_raster_forward(a, ag, cg, ab, cb, ai, ci, out_color, out_depth, radii, num_rendered_host, scratch, stream);
+}
+
+int fnx_raster_backward(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                        const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g, fnx_stream_t stream) {
+    int rc = validate(a);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->C == 3) return backward_impl<3>(a, scratch, num_rendered, radii, dL_dout_color, g, st);
+    return backward_impl<1>(a, scratch, num_rendered, radii, dL_dout_color, g, st);
+}
+int fnx_raster_backward_ch1(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                            const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g, fnx_stream_t stream) {
+    if (a && a->C != 1) { set_error("fnx_raster_backward_ch1 needs C == 1 (got %d)", a->C); return FNX_ERR_INVALID; }
+    return fnx_raster_backward(a, scratch, num_rendered, radii, dL_dout_color, g, stream);
+}
+int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                            const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g, fnx_stream_t stream) {
+    if (a && a->C != 3) { set_error("fnx_raster_backward_ch3 needs C == 3 (got %d)", a->C); return FNX_ERR_INVALID; }
+    return fnx_raster_backward(a, scratch, num_rendered, radii, dL_dout_color, g, stream);
+}
+
+int fnx_raster_check(const fnx_raster_scratch *scratch, int64_t *num_rendered_host, fnx_stream_t stream) {
+    (void)stream;
+    FNX_REQUIRE(scratch && num_rendered_host, "scratch / num_rendered_host must be given");
+    FNX_REQUIRE(g_slots.ok && scratch->check_slot >= 0 && scratch->check_slot < PinnedSlots::N, "no forward to check");
+    FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[scratch->check_slot]));
+    const long long R = g_slots.host[scratch->check_slot];
+    *num_rendered_host = R;
+    if (R > scratch->binning_capacity) {
+        set_error("instance capacity %lld too small for %lld instances", (long long)scratch->binning_capacity, R);
+        return FNX_ERR_CAPACITY;
+    }
+    return FNX_OK;
+}
+
+int fnx_raster_read_geom(const fnx_raster_scratch *scratch, int32_t P, int32_t V, float *xy, float *depth,
+                         float *conic_opacity, uint32_t *tiles_touched, fnx_stream_t stream) {
+    FNX_REQUIRE(scratch && scratch->geom, "no geom scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    GeomView g = geom_view(scratch->geom, P, V);
+    const size_t n = (size_t)P * V;
+    if (xy) FNX_CUDA_TRY(cudaMemcpyAsync(xy, g.xy, n * 8, cudaMemcpyDeviceToDevice, st));
+    if (depth) FNX_CUDA_TRY(cudaMemcpyAsync(depth, g.depth, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (conic_opacity) FNX_CUDA_TRY(cudaMemcpyAsync(conic_opacity, g.conic_o, n * 16, cudaMemcpyDeviceToDevice, st));
+    if (tiles_touched) FNX_CUDA_TRY(cudaMemcpyAsync(tiles_touched, g.tiles_touched, n * 4, cudaMemcpyDeviceToDevice, st));
+    return FNX_OK;
+}
+int fnx_raster_read_image(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, float *final_T,
+                          uint32_t *n_contrib, fnx_stream_t stream) {
+    FNX_REQUIRE(scratch && scratch->image, "no image scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    ImageView im = image_view(scratch->image, W, H, V);
+    const size_t n = (size_t)W * H * V;
+    if (final_T) FNX_CUDA_TRY(cudaMemcpyAsync(final_T, im.final_T, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (n_contrib) FNX_CUDA_TRY(cudaMemcpyAsync(n_contrib, im.n_contrib, n * 4, cudaMemcpyDeviceToDevice, st));
+    return FNX_OK;
+}
+
+int fnx_mark_visible(int32_t P, const float *means3D, const float *view_matrix, const float *proj_matrix, uint8_t *present,
+                     fnx_stream_t stream) {
+    (void)proj_matrix;
+    if (P == 0) return FNX_OK;
+    FNX_REQUIRE(P > 0 && means3D && view_matrix && present, "bad arguments");
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, means3D, view_matrix, present);
+    FNX_LAUNCH_CHECK("mark_visible_kernel");
+    return FNX_OK;
+}
+
+}  // extern "C"

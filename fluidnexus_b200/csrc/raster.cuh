@@ -1,0 +1,74 @@
+// raster.cuh -- private layout of the rasterizer scratch + kernel launch prototypes.
+#pragma once
+#include "common.cuh"
+
+namespace fnx {
+
+constexpr int TILE = 16;                 // 16x16 pixel tiles (R3/cuda_rasterizer/config.h:16-17)
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float DEPTH_DEFAULT = 15.0f;   // forward.cu:295
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_EPS = 0.0001f;
+
+// Per-instance record in the depth-sorted, tile-partitioned stream the blend kernels consume.
+// One contiguous span per tile => a span is a 1-D bulk (TMA) copy into shared memory.
+//   C == 3 : 48 B  {x, y, a, b | c, opacity, r, g | b, slot(int bits), depth, pad}
+//   C == 1 : 32 B  {x, y, a, b | c, opacity, col, slot(int bits)}   (median depth is fetched from geom.depth[slot])
+template <int C>
+struct RecBytes {
+    static constexpr int value = (C == 3) ? 48 : 32;
+};
+
+// accumulator floats per (view, Gaussian) written by the blend backward with vector reductions:
+//   {dmean2D.x, dmean2D.y, dconic.x, dconic.y | dconic.w, dopacity, dcol0, dcol1 | dcol2, -, -, -}
+template <int C>
+struct AccFloats {
+    static constexpr int value = (C == 3) ? 12 : 8;
+};
+
+struct GeomHeader {
+    long long num_rendered;   // instances actually needed (device-written by the scan epilogue)
+    long long capacity;       // instances the binning buffers can hold
+    int overflow;             // 1 if num_rendered > capacity (nothing rendered)
+    int pad[3];
+};
+
+struct GeomView {  // pointers into the geom scratch
+    GeomHeader *hdr;
+    float *cov3D;             // [P,6]
+    float *depth;             // [V*P]
+    float2 *xy;               // [V*P]
+    float4 *conic_o;          // [V*P]
+    uint32_t *tiles_touched;  // [V*P] (after tile culling)
+    unsigned long long *dkeys_in, *dkeys_out;  // [V*P] (view<<32 | depth bits)
+    uint32_t *dvals_in, *dvals_out;            // [V*P] slot = v*P + i
+    uint32_t *offsets;        // [V*P] exclusive scan of tiles_touched in depth order
+    float *accum;             // [V*P*AccFloats] (backward)
+    void *cub_temp;
+    size_t cub_temp_bytes;
+};
+
+struct BinView {
+    uint32_t *tkeys_in, *tkeys_out;  // [cap] global tile id = v*ntiles + tile
+    uint32_t *tvals_in, *tvals_out;  // [cap] slot
+    char *records;                   // [cap * RecBytes]
+    void *cub_temp;
+    size_t cub_temp_bytes;
+};
+
+struct ImageView {
+    float *final_T;          // [V*H*W]
+    uint32_t *n_contrib;     // [V*H*W]
+    uint2 *ranges;           // [V*ntiles]
+    uint32_t *tile_last;     // [V*ntiles] max n_contrib over the tile's pixels (backward start)
+};
+
+size_t geom_bytes(int P, int V);
+size_t image_bytes(int W, int H, int V);
+size_t binning_bytes(long long cap, int C);
+GeomView geom_view(void *chunk, int P, int V);
+ImageView image_view(void *chunk, int W, int H, int V);
+BinView bin_view(void *chunk, long long cap, int C);
+
+}  // namespace fnx

@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference rasterizer interface, on top of libfnx's C ABI.
+
+Mirrors (same names, argument meaning and error behaviour):
+  R3/diff_gaussian_rasterization_ch3/__init__.py:143-154  GaussianRasterizationSettings (11 fields)
+  R3/diff_gaussian_rasterization_ch3/__init__.py:157-215  GaussianRasterizer.forward / .mark_visible
+  R3/diff_gaussian_rasterization_ch3/__init__.py:33-140   _RasterizeGaussians (autograd boundary, 9 grads)
+  R3/rasterize_points.cu:35-215                           allocation of outputs / scratch, P == 0 short-circuit
+(R1 = same with one channel.)  `make_module(C)` builds the class set for a channel count; the drop-in
+packages in fluidnexus_b200/compat/ re-export them under the reference's module names.
+
+Everything runs on torch's *current* stream and the tensors' device (the reference launches on the legacy
+default stream, rasterizer_impl.cu:137,272,296 -- that breaks multi-GPU ranks and stream capture).
+"""
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+
+from . import _lib as L
+
+__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext"]
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _f32c(t):
+    """contiguous float32 view/copy (the reference calls .contiguous().data<float>() on everything)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _Buf:
+    """A growable uint8 CUDA buffer handed to libfnx through an allocation callback
+    (the reference's resizeFunctional, R3/rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t = None
+        self.cb = L.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, nbytes):
+        try:
+            if self.t is None or self.t.numel() < nbytes:
+                self.t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.t.data_ptr()
+        except Exception:  # never let an exception cross the C boundary
+            return None
+
+
+class RasterContext:
+    """Everything the backward needs from a forward (the reference keeps the same in `ctx`)."""
+    __slots__ = ("args", "scratch", "bufs", "num_rendered", "radii", "keep", "C", "V", "P")
+
+
+# running estimate of the instance count per (device, C, V, W, H): lets the forward size its binning buffers
+# without blocking on the device-side count (see FNX_NO_HOST_SYNC / instance_capacity_hint in include/fnx.h)
+_capacity_hint = {}
+
+
+def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_modifier, cov3D_precomp, view_matrix,
+                   proj_matrix, tan_fov_x, tan_fov_y, H, W, sh=None, prefiltered=False, exact_rect=False,
+                   speculative=True):
+    """One forward through libfnx.  view_matrix/proj_matrix may be [4,4] (one camera, reference API) or
+    [V,4,4] (V cameras batched into one launch sequence).  Returns (ctx, color, radii, depth) with shapes
+    [C,H,W]/[P]/[1,H,W] for a single camera and [V,C,H,W]/[V,P]/[V,1,H,W] for a batch."""
+    lib = L.lib()
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:56-58
+    if not means3D.is_cuda:
+        raise RuntimeError("libfnx needs CUDA tensors (there is no CPU fallback)")
+    dev = means3D.device
+    P = means3D.size(0)
+    batched = view_matrix.dim() == 3
+    V = view_matrix.size(0) if batched else 1
+    if sh is not None and sh.numel() != 0:
+        raise RuntimeError("SH colours are not supported by libfnx: FluidNexus always passes colors_precomp")
+    if colors is None or colors.numel() == 0:
+        if C_ != 3:
+            raise RuntimeError("For non-RGB, provide precomputed Gaussian colors!")  # rasterizer_impl.cu:226-228
+        raise RuntimeError("SH colours are not supported by libfnx: FluidNexus always passes colors_precomp")
+
+    keep = dict(
+        means3D=_f32c(means3D), colors=_f32c(colors), opacities=_f32c(opacities),
+        scales=_f32c(scales) if scales is not None and scales.numel() else None,
+        rotations=_f32c(rotations) if rotations is not None and rotations.numel() else None,
+        cov=_f32c(cov3D_precomp) if cov3D_precomp is not None and cov3D_precomp.numel() else None,
+        view=_f32c(view_matrix), proj=_f32c(proj_matrix), bg=_f32c(bg),
+    )
+    if P and keep["colors"].numel() != P * C_:
+        raise RuntimeError(f"colors_precomp must have {C_} channels per Gaussian")
+    out_shape = (V, C_, H, W) if batched else (C_, H, W)
+    with torch.cuda.device(dev):
+        color = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        depth = torch.empty((V, 1, H, W) if batched else (1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((V, P) if batched else (P,), dtype=torch.int32, device=dev)
+        a = L.RasterArgs()
+        a.P, a.V, a.C, a.W, a.H = P, V, C_, W, H
+        a.means3D, a.colors, a.opacities = _ptr(keep["means3D"]), _ptr(keep["colors"]), _ptr(keep["opacities"])
+        a.scales, a.rotations, a.cov3D_precomp, a.sh = _ptr(keep["scales"]), _ptr(keep["rotations"]), _ptr(keep["cov"]), None
+        a.view_matrix, a.proj_matrix, a.bg = _ptr(keep["view"]), _ptr(keep["proj"]), _ptr(keep["bg"])
+        a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
+        a.prefiltered = int(bool(prefiltered))
+        a.flags = L.FNX_EXACT_RECT if exact_rect else 0
+        key = (dev.index, C_, V, W, H, P)
+        a.instance_capacity_hint = _capacity_hint.get(key, 0) if speculative else 0
+        bufs = (_Buf(dev), _Buf(dev), _Buf(dev))
+        scratch = L.RasterScratch()
+        nr = C.c_int64(0)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        fwd = lib.fnx_raster_forward_ch3 if C_ == 3 else lib.fnx_raster_forward_ch1
+        L.check(fwd(C.byref(a), bufs[0].cb, None, bufs[1].cb, None, bufs[2].cb, None, color.data_ptr(), depth.data_ptr(),
+                    radii.data_ptr() if P else None, C.byref(nr), C.byref(scratch), stream))
+    if speculative and P:
+        _capacity_hint[key] = int(nr.value * 1.25) + 4096
+    ctx = RasterContext()
+    ctx.args, ctx.scratch, ctx.bufs, ctx.num_rendered, ctx.radii, ctx.keep = a, scratch, bufs, int(nr.value), radii, keep
+    ctx.C, ctx.V, ctx.P = C_, V, P
+    return ctx, color, radii, depth
+
+
+def raster_backward(ctx, dL_dout_color, want_means2D=True):
+    """Backward through libfnx.  Returns a dict of gradient tensors summed over the ctx's views
+    (means2D is per view: [P,3] or [V,P,3])."""
+    lib = L.lib()
+    P, V, C_ = ctx.P, ctx.V, ctx.C
+    dev = ctx.keep["means3D"].device
+    g = {}
+    with torch.cuda.device(dev):
+        g["means3D"] = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        g["means2D"] = torch.empty((V, P, 3) if V > 1 or ctx.radii.dim() == 2 else (P, 3), dtype=torch.float32, device=dev)
+        g["colors"] = torch.empty((P, C_), dtype=torch.float32, device=dev)
+        g["opacity"] = torch.empty((P, 1), dtype=torch.float32, device=dev)
+        g["cov3D"] = torch.empty((P, 6), dtype=torch.float32, device=dev)
+        has_sr = ctx.keep["scales"] is not None
+        # rasterize_points.cu:150-158 returns zero tensors for the paths that are not taken
+        g["scales"] = torch.empty((P, 3), dtype=torch.float32, device=dev) if has_sr else torch.zeros((P, 3), device=dev)
+        g["rotations"] = torch.empty((P, 4), dtype=torch.float32, device=dev) if has_sr else torch.zeros((P, 4), device=dev)
+        if P == 0:
+            return g
+        dpix = _f32c(dL_dout_color)
+        gr = L.RasterGrads()
+        gr.dL_dmeans3D, gr.dL_dmeans2D = g["means3D"].data_ptr(), g["means2D"].data_ptr() if want_means2D else None
+        gr.dL_dcolors, gr.dL_dopacity, gr.dL_dcov3D = g["colors"].data_ptr(), g["opacity"].data_ptr(), g["cov3D"].data_ptr()
+        gr.dL_dscales = g["scales"].data_ptr() if has_sr else None
+        gr.dL_drotations = g["rotations"].data_ptr() if has_sr else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        bwd = lib.fnx_raster_backward_ch3 if C_ == 3 else lib.fnx_raster_backward_ch1
+        L.check(bwd(C.byref(ctx.args), C.byref(ctx.scratch), ctx.num_rendered, ctx.radii.data_ptr(), dpix.data_ptr(),
+                    C.byref(gr), stream))
+    return g
+
+
+def mark_visible(positions, view_matrix, proj_matrix):
+    lib = L.lib()
+    pos = _f32c(positions)
+    P = pos.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=pos.device)
+    if P:
+        with torch.cuda.device(pos.device):
+            L.check(lib.fnx_mark_visible(P, pos.data_ptr(), _f32c(view_matrix).data_ptr(), _f32c(proj_matrix).data_ptr(),
+                                         present.data_ptr(), torch.cuda.current_stream(pos.device).cuda_stream))
+    return present
+
+
+def make_module(C_):
+    """Build (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, _C-like namespace)
+    for a channel count, with the reference's names and call signatures."""
+
+    class GaussianRasterizationSettings(NamedTuple):
+        image_height: int
+        image_width: int
+        tan_fov_x: float
+        tan_fov_y: float
+        bg: torch.Tensor
+        scale_modifier: float
+        view_matrix: torch.Tensor
+        proj_matrix: torch.Tensor
+        sh_degree: int
+        campos: torch.Tensor
+        prefiltered: bool
+
+    class _RasterizeGaussians(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+            fctx, color, radii, depth = raster_forward(
+                C_, rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                rs.view_matrix, rs.proj_matrix, rs.tan_fov_x, rs.tan_fov_y, rs.image_height, rs.image_width, sh=sh,
+                prefiltered=rs.prefiltered)
+            ctx.fctx = fctx
+            ctx.mark_non_differentiable(radii, depth)
+            return color, radii, depth
+
+        @staticmethod
+        def backward(ctx, grad_out_color, _grad_radii, _grad_depth):
+            g = raster_backward(ctx.fctx, grad_out_color)
+            has_cov = ctx.fctx.keep["cov"] is not None
+            # order of R3/diff_gaussian_rasterization_ch3/__init__.py:128-138
+            return (g["means3D"], g["means2D"], None, g["colors"], g["opacity"],
+                    None if has_cov else g["scales"], None if has_cov else g["rotations"],
+                    g["cov3D"] if has_cov else None, None)
+
+    def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+        return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                         cov3Ds_precomp, rs)
+
+    class GaussianRasterizer(torch.nn.Module):
+        def __init__(self, raster_settings):
+            super().__init__()
+            self.raster_settings = raster_settings
+
+        def mark_visible(self, positions):
+            with torch.no_grad():
+                rs = self.raster_settings
+                return mark_visible(positions, rs.view_matrix, rs.proj_matrix)
+
+        def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                    cov3D_precomp=None):
+            rs = self.raster_settings
+            if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+                raise Exception("Please provide exactly one of either SHs or precomputed colors!")
+            if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                    (scales is not None or rotations is not None) and cov3D_precomp is not None):
+                raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+            empty = torch.Tensor([])
+            return rasterize_gaussians(
+                means3D, means2D, empty if shs is None else shs, empty if colors_precomp is None else colors_precomp,
+                opacities, empty if scales is None else scales, empty if rotations is None else rotations,
+                empty if cov3D_precomp is None else cov3D_precomp, rs)
+
+    return GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, _RasterizeGaussians
+
+
+def read_geom(ctx):
+    """Intermediate per-(view, Gaussian) state of a forward (parity tests): xy, depth, conic_opacity, tiles_touched."""
+    dev = ctx.keep["means3D"].device
+    P, V = ctx.P, ctx.V
+    out = dict(xy=torch.zeros((V, P, 2), device=dev), depth=torch.zeros((V, P), device=dev),
+               conic_opacity=torch.zeros((V, P, 4), device=dev),
+               tiles_touched=torch.zeros((V, P), dtype=torch.int32, device=dev))
+    if P:
+        L.check(L.lib().fnx_raster_read_geom(C.byref(ctx.scratch), P, V, out["xy"].data_ptr(), out["depth"].data_ptr(),
+                                             out["conic_opacity"].data_ptr(), out["tiles_touched"].data_ptr(),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+def read_image_state(ctx):
+    dev = ctx.keep["means3D"].device
+    W, H, V = ctx.args.W, ctx.args.H, ctx.V
+    out = dict(final_T=torch.zeros((V, H, W), device=dev), n_contrib=torch.zeros((V, H, W), dtype=torch.int32, device=dev))
+    if ctx.P:
+        L.check(L.lib().fnx_raster_read_image(C.byref(ctx.scratch), W, H, V, out["final_T"].data_ptr(),
+                                              out["n_contrib"].data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return out

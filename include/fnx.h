@@ -1,0 +1,167 @@
+/*
+ * fnx.h -- C ABI of libfnx.so, the B200 (sm_100a) hot path of FluidNexus' FluidDynamics stage.
+ *
+ * Everything here takes raw DEVICE pointers (unless a parameter says "host"), plain sizes and a
+ * cudaStream_t (passed as void*), and returns an int status (FNX_OK == 0).  After a non-zero
+ * status `fnx_last_error()` returns a thread-local description.  No torch types cross this line.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root; R3 = FluidDynamics/submodules/gaussian_rasterization_ch3, R1 = ..._ch1 (same
+ * code, NUM_CHANNELS 1), KNN = FluidDynamics/submodules/simple-knn, FD = FluidDynamics).
+ *
+ * Conventions shared with the reference:
+ *   - view / proj matrices: 16 floats each, the row-major storage of the TRANSPOSED matrices, exactly
+ *     what Camera.world_view_transform / full_proj_transform hold (FD/scene/camera.py:90-108).
+ *   - quaternions are (r,x,y,z) and are NOT normalised inside (R3/cuda_rasterizer/forward.cu:121).
+ *   - colours are always "precomputed" [P,C]; the SH path is dead in FluidNexus (all pipes pass
+ *     colors_precomp, FD/renderer/pipe_fluid.py:107-118) and passing sh != NULL returns
+ *     FNX_ERR_UNSUPPORTED.
+ *   - all scratch is caller-owned and grown through an allocation callback, like the reference's
+ *     resize lambdas (R3/rasterize_points.cu:27-33); its layout is private to the library.
+ */
+#ifndef FNX_H_INCLUDED
+#define FNX_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNX_OK 0
+#define FNX_ERR_INVALID 1     /* bad argument (shape / null / range) */
+#define FNX_ERR_CUDA 2        /* a CUDA runtime call or kernel launch failed */
+#define FNX_ERR_UNSUPPORTED 3 /* feature of the reference interface that is dead on the FluidNexus path */
+#define FNX_ERR_CAPACITY 4    /* FNX_NO_HOST_SYNC was given and the instance capacity was too small */
+#define FNX_ERR_ALLOC 5       /* allocation callback returned NULL */
+
+#define FNX_ABI_VERSION 1
+
+typedef void *fnx_stream_t; /* cudaStream_t */
+
+/* Allocation callback: must return a device pointer to at least `bytes` bytes (256-B aligned) that stays
+ * valid until the paired backward has run.  `ctx` is passed through.  Mirrors resizeFunctional,
+ * R3/rasterize_points.cu:27-33. */
+typedef void *(*fnx_alloc_fn)(void *ctx, size_t bytes);
+
+int fnx_abi_version(void);
+const char *fnx_last_error(void);
+/* Compiled-for architecture string, e.g. "sm_100a". */
+const char *fnx_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasterizer  (replaces R3|R1 `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward`,
+ * `_C.mark_visible`: R3/rasterize_points.h:18-64, R3/ext.cpp:15-19, host orchestration
+ * R3/cuda_rasterizer/rasterizer_impl.cu:131-414, kernels forward.cu / backward.cu)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* flags */
+#define FNX_NO_HOST_SYNC 1u /* never block the host: trust `instance_capacity_hint`; on overflow nothing is
+                               rendered, *num_rendered_host is left at -1 and fnx_raster_check() reports it */
+#define FNX_EXACT_RECT 2u   /* bin with the reference's full 3-sigma tile rectangle (no opacity-aware tile
+                               culling).  Results are identical either way; this exists for A/B tests. */
+
+typedef struct fnx_raster_args {
+    /* sizes */
+    int32_t P;        /* Gaussians */
+    int32_t V;        /* cameras rendered by this call (>=1). The reference renders one; V>1 batches views */
+    int32_t C;        /* colour channels: 1 (R1) or 3 (R3) */
+    int32_t W, H;     /* image size */
+    /* per-Gaussian inputs, shared by all V views (reference arg names in brackets) */
+    const float *means3D;       /* [P,3] */
+    const float *colors;        /* [P,C]  (colors_precomp) */
+    const float *opacities;     /* [P]    (opacity [P,1]) */
+    const float *scales;        /* [P,3] or NULL when cov3D_precomp is given */
+    const float *rotations;     /* [P,4] or NULL */
+    const float *cov3D_precomp; /* [P,6] or NULL */
+    const float *sh;            /* must be NULL (FNX_ERR_UNSUPPORTED otherwise) */
+    /* per-view inputs */
+    const float *view_matrix;   /* [V,16] */
+    const float *proj_matrix;   /* [V,16] */
+    const float *bg;            /* [C] (R1 reads bg[0]) */
+    float tan_fov_x, tan_fov_y, scale_modifier;
+    int32_t prefiltered;        /* accepted, unused (reference only traps on inconsistency) */
+    uint32_t flags;
+    int64_t instance_capacity_hint; /* 0 = size exactly (one host sync, like the reference) */
+} fnx_raster_args;
+
+/* Opaque handles to the three scratch buffers of one forward (what the reference returns as
+ * geomBuffer / binningBuffer / imgBuffer and hands back to backward). */
+typedef struct fnx_raster_scratch {
+    void *geom;    size_t geom_bytes;
+    void *binning; size_t binning_bytes;
+    void *image;   size_t image_bytes;
+    int64_t binning_capacity; /* instances the binning buffer was sized for */
+    int32_t check_slot;       /* private: which read-back slot carries this forward's instance count */
+    int32_t reserved;
+} fnx_raster_scratch;
+
+/* Sizes, for callers that pre-allocate instead of using callbacks. */
+size_t fnx_raster_geom_bytes(int32_t P, int32_t V);
+size_t fnx_raster_image_bytes(int32_t W, int32_t H, int32_t V);
+size_t fnx_raster_binning_bytes(int64_t instance_capacity, int32_t C);
+
+/* Forward.  Outputs: out_color [V,C,H,W], out_depth [V,1,H,W] (median depth, default 15), radii [V,P] int32.
+ * `*num_rendered_host` receives the number of (tile, Gaussian) instances binned (after tile culling, so it
+ * can be smaller than the reference's).  The three allocators are called at most a few times each; the final
+ * pointers/sizes are reported in *scratch.  Replaces RasterizeGaussiansCUDA, R3/rasterize_points.cu:35-115. */
+int fnx_raster_forward(const fnx_raster_args *a, fnx_alloc_fn alloc_geom, void *geom_ctx, fnx_alloc_fn alloc_binning,
+                       void *binning_ctx, fnx_alloc_fn alloc_image, void *image_ctx, float *out_color,
+                       float *out_depth, int32_t *radii, int64_t *num_rendered_host, fnx_raster_scratch *scratch,
+                       fnx_stream_t stream);
+/* Channel-count-specific names, one per reference extension module. */
+int fnx_raster_forward_ch1(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx_alloc_fn ab, void *cb, fnx_alloc_fn ai,
+                           void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                           fnx_raster_scratch *scratch, fnx_stream_t stream);
+int fnx_raster_forward_ch3(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx_alloc_fn ab, void *cb, fnx_alloc_fn ai,
+                           void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                           fnx_raster_scratch *scratch, fnx_stream_t stream);
+
+/* Gradient outputs of the backward.  Any pointer may be NULL (that gradient is then not written).
+ * All non-NULL outputs are fully overwritten (no pre-zeroing needed), summed over the V views. */
+typedef struct fnx_raster_grads {
+    float *dL_dmeans3D;  /* [P,3] */
+    float *dL_dmeans2D;  /* [V,P,3]: screen-space gradient, z == 0, x,y scaled by 0.5*W, 0.5*H (backward.cu:444-445) */
+    float *dL_dcolors;   /* [P,C] */
+    float *dL_dopacity;  /* [P] */
+    float *dL_dscales;   /* [P,3] (written only when scales were given) */
+    float *dL_drotations;/* [P,4] raw un-normalised quaternion gradient (backward.cu:326) */
+    float *dL_dcov3D;    /* [P,6] */
+} fnx_raster_grads;
+
+/* Backward.  dL_dout_color [V,C,H,W].  `a` must equal the forward's args; `scratch` is what forward reported;
+ * `num_rendered` what it returned.  Depth has no gradient (R3/README.md:13).
+ * Replaces RasterizeGaussiansBackwardCUDA, R3/rasterize_points.cu:117-194. */
+int fnx_raster_backward(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                        const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g,
+                        fnx_stream_t stream);
+int fnx_raster_backward_ch1(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                            const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g,
+                            fnx_stream_t stream);
+int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
+                            const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g,
+                            fnx_stream_t stream);
+
+/* After a FNX_NO_HOST_SYNC forward: blocks until the forward's instance count is known and returns FNX_OK or
+ * FNX_ERR_CAPACITY; *num_rendered_host is set either way. */
+int fnx_raster_check(const fnx_raster_scratch *scratch, int64_t *num_rendered_host, fnx_stream_t stream);
+
+/* present[i] = (view-space z of means3D[i] > 0.2).  present is uint8/bool [P].
+ * Replaces markVisible, R3/rasterize_points.cu:196-215 (checkFrustum, rasterizer_impl.cu:52-63). */
+int fnx_mark_visible(int32_t P, const float *means3D, const float *view_matrix, const float *proj_matrix,
+                     uint8_t *present, fnx_stream_t stream);
+
+/* Introspection for parity tests: device-to-device copies of the forward's intermediate state.  Any destination may
+ * be NULL.  xy [V,P,2], depth [V,P], conic_opacity [V,P,4] (R3 GeometryState means2D/depths/conic_opacity,
+ * rasterizer_impl.h:28-46), tiles_touched [V,P] (after tile culling); final_T / n_contrib [V,H,W]
+ * (ImageState accum_alpha / n_contrib; n_contrib indexes the culled tile list). */
+int fnx_raster_read_geom(const fnx_raster_scratch *scratch, int32_t P, int32_t V, float *xy, float *depth,
+                         float *conic_opacity, uint32_t *tiles_touched, fnx_stream_t stream);
+int fnx_raster_read_image(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, float *final_T,
+                          uint32_t *n_contrib, fnx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNX_H_INCLUDED */
