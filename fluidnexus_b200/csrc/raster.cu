@@ -242,6 +242,29 @@ __device__ __forceinline__ bool tile_needed(const TileCull &t, const float2 mean
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative tile enumeration.  A Gaussian whose 3-sigma rectangle covers many tiles is handled by all 32
+// lanes of its warp (one candidate tile per lane per step) instead of one thread looping over hundreds of tiles.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SERIAL_TILES = 6;  // rectangles up to this many candidate tiles are handled by the owning thread
+
+struct TileJob {  // what a lane needs to enumerate the tiles of one Gaussian
+    float2 xy;
+    TileCull tc;
+    int x0, y0, w, n;  // rect origin, width in tiles, number of candidate tiles
+};
+__device__ __forceinline__ TileJob bcast_job(const TileJob &j, int src) {
+    TileJob o;
+    const unsigned m = 0xffffffffu;
+    o.xy.x = __shfl_sync(m, j.xy.x, src); o.xy.y = __shfl_sync(m, j.xy.y, src);
+    o.tc.a = __shfl_sync(m, j.tc.a, src); o.tc.b = __shfl_sync(m, j.tc.b, src); o.tc.c = __shfl_sync(m, j.tc.c, src);
+    o.tc.tau = __shfl_sync(m, j.tc.tau, src);
+    o.tc.active = __shfl_sync(m, (int)j.tc.active, src) != 0;
+    o.x0 = __shfl_sync(m, j.x0, src); o.y0 = __shfl_sync(m, j.y0, src);
+    o.w = __shfl_sync(m, j.w, src); o.n = __shfl_sync(m, j.n, src);
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1: per (view, Gaussian) preprocess.  forward.cu:148-244
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -252,74 +275,101 @@ preprocess_kernel(int P, int V, const float *__restrict__ means3D, const float3 
                   float focal_y, int gx, int gy, bool exact_rect, int *__restrict__ radii, GeomView g) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
-    if (i >= P) return;
-    const size_t slot = (size_t)v * P + i;
+    const int lane = threadIdx.x & 31;
+    const size_t slot = (size_t)v * P + (i < P ? i : 0);
     const float *Vm = view_matrix + 16 * v;
     const float *Pm = proj_matrix + 16 * v;
 
-    radii[slot] = 0;
-    g.tiles_touched[slot] = 0;
-    g.dvals_in[slot] = (uint32_t)slot;
-    unsigned long long key = ((unsigned long long)v << 32) | 0xFFFFFFFFull;  // invisible: sorts last in its view
-    g.dkeys_in[slot] = key;
-
-    const float3 p_orig = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
-    const float4 p_hom = xform4x4(p_orig, Pm);
-    const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-    const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
-    const float3 p_view = xform4x3(p_orig, Vm);
-    if (p_view.z <= 0.2f) return;  // auxiliary.h:138
-
-    float cov_local[6];
-    const float *cov3D;
-    if (cov3D_precomp != nullptr) {
-        cov3D = cov3D_precomp + 6 * (size_t)i;
-    } else {
-        cov3d_from_scale_rot(scales[i], scale_modifier, rotations[i], cov_local);
-        // every view writes the same six values (benign); a Gaussian culled in view 0 may be visible in view 1
-#pragma unroll
-        for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = cov_local[k];
-        cov3D = cov_local;
-    }
-    float c6[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) c6[k] = cov3D[k];
-
-    ProjJac pj = proj_jacobian(p_orig, focal_x, focal_y, tan_fov_x, tan_fov_y, Vm);
-    M3 Vrk = vrk_of(c6);
-    M3 cov2 = m3_mul(m3_mul(m3_T(pj.T), m3_T(Vrk)), pj.T);
-    const float ca = cov2.m[0][0] + 0.3f, cb = cov2.m[0][1], cc = cov2.m[1][1] + 0.3f;
-
-    const float det = (ca * cc - cb * cb);
-    if (det == 0.0f) return;
-    const float det_inv = 1.f / det;
-    const float3 conic = make_float3(cc * det_inv, -cb * det_inv, ca * det_inv);
-
-    const float mid = 0.5f * (ca + cc);
-    const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-    const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
-    const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
-    const float2 point_image = make_float2(ndc2pix(p_proj.x, W), ndc2pix(p_proj.y, H));
-    uint2 rmin, rmax;
-    get_rect(point_image, (int)my_radius, rmin, rmax, gx, gy);
-    if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) return;
-
-    const float4 con_o = make_float4(conic.x, conic.y, conic.z, opacities[i]);
-    // count the tiles that can actually receive a contribution
-    TileCull tc = make_cull(con_o, exact_rect);
+    bool visible = false;   // passes every test of the reference's preprocess
+    bool big = false;       // tile count is done cooperatively
     uint32_t cnt = 0;
-    if (!tc.active) {
-        cnt = (rmax.y - rmin.y) * (rmax.x - rmin.x);
-    } else {
-        for (int ty = rmin.y; ty < (int)rmax.y; ty++)
-            for (int tx = rmin.x; tx < (int)rmax.x; tx++) cnt += tile_needed(tc, point_image, tx, ty) ? 1u : 0u;
+    float depth = 0.f;
+    int radius = 0;
+    float4 con_o = make_float4(0.f, 0.f, 0.f, 0.f);
+    TileJob job;
+    job.xy = make_float2(0.f, 0.f);
+    job.tc.a = job.tc.b = job.tc.c = job.tc.tau = 0.f;
+    job.tc.active = false;
+    job.x0 = job.y0 = job.w = job.n = 0;
+
+    if (i < P) do {
+        const float3 p_orig = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+        const float4 p_hom = xform4x4(p_orig, Pm);
+        const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+        const float3 p_view = xform4x3(p_orig, Vm);
+        if (p_view.z <= 0.2f) break;  // auxiliary.h:138
+
+        float c6[6];
+        if (cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c6[k] = cov3D_precomp[6 * (size_t)i + k];
+        } else {
+            cov3d_from_scale_rot(scales[i], scale_modifier, rotations[i], c6);
+            // every view writes the same six values (benign); a Gaussian culled in view 0 may be visible in view 1
+#pragma unroll
+            for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = c6[k];
+        }
+        ProjJac pj = proj_jacobian(p_orig, focal_x, focal_y, tan_fov_x, tan_fov_y, Vm);
+        M3 Vrk = vrk_of(c6);
+        M3 cov2 = m3_mul(m3_mul(m3_T(pj.T), m3_T(Vrk)), pj.T);
+        const float ca = cov2.m[0][0] + 0.3f, cb = cov2.m[0][1], cc = cov2.m[1][1] + 0.3f;
+
+        const float det = (ca * cc - cb * cb);
+        if (det == 0.0f) break;
+        const float det_inv = 1.f / det;
+        const float3 conic = make_float3(cc * det_inv, -cb * det_inv, ca * det_inv);
+
+        const float mid = 0.5f * (ca + cc);
+        const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+        const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+        const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+        const float2 point_image = make_float2(ndc2pix(p_proj.x, W), ndc2pix(p_proj.y, H));
+        uint2 rmin, rmax;
+        get_rect(point_image, (int)my_radius, rmin, rmax, gx, gy);
+        if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) break;
+
+        visible = true;
+        depth = p_view.z;
+        radius = (int)my_radius;
+        con_o = make_float4(conic.x, conic.y, conic.z, opacities[i]);
+        job.xy = point_image;
+        job.tc = make_cull(con_o, exact_rect);
+        job.x0 = rmin.x; job.y0 = rmin.y;
+        job.w = rmax.x - rmin.x;
+        job.n = job.w * (rmax.y - rmin.y);
+        // count the tiles that can actually receive a contribution
+        if (!job.tc.active) {
+            cnt = job.n;
+        } else if (job.n <= SERIAL_TILES) {
+            for (int t = 0; t < job.n; t++) cnt += tile_needed(job.tc, job.xy, job.x0 + t % job.w, job.y0 + t / job.w) ? 1u : 0u;
+        } else {
+            big = true;
+        }
+    } while (0);
+
+    unsigned pending = __ballot_sync(0xffffffffu, big);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const TileJob j = bcast_job(job, src);
+        uint32_t c = 0;
+        for (int t = lane; t < j.n; t += 32) c += tile_needed(j.tc, j.xy, j.x0 + t % j.w, j.y0 + t / j.w) ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == src) cnt = c;
     }
-    g.depth[slot] = p_view.z;
-    radii[slot] = (int)my_radius;
-    g.xy[slot] = point_image;
-    g.conic_o[slot] = con_o;
+
+    if (i >= P) return;
+    radii[slot] = visible ? radius : 0;
     g.tiles_touched[slot] = cnt;
-    g.dkeys_in[slot] = ((unsigned long long)v << 32) | (unsigned long long)__float_as_uint(p_view.z);
+    g.dvals_in[slot] = (uint32_t)slot;
+    // invisible Gaussians sort last in their view
+    g.dkeys_in[slot] = ((unsigned long long)v << 32) | (visible ? (unsigned long long)__float_as_uint(depth) : 0xFFFFFFFFull);
+    if (visible) {
+        g.depth[slot] = depth;
+        g.xy[slot] = job.xy;
+        g.conic_o[slot] = con_o;
+    }
 }
 
 // writes total instance count + overflow flag after the scan (one thread)
@@ -338,26 +388,63 @@ __global__ void finish_scan_kernel(int n, GeomView g, long long capacity, long l
 __global__ void __launch_bounds__(256)
 emit_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict__ radii, GeomView g, BinView b) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const int lane = threadIdx.x & 31;
     if (g.hdr->overflow) return;
-    const uint32_t slot = g.dvals_out[k];
-    const uint32_t cnt = g.tiles_touched[slot];
-    if (cnt == 0) return;
-    uint32_t off = g.offsets[k];
-    const int v = slot / P;
-    const float2 xy = g.xy[slot];
-    const float4 con_o = g.conic_o[slot];
-    uint2 rmin, rmax;
-    get_rect(xy, radii[slot], rmin, rmax, gx, gy);
-    TileCull tc = make_cull(con_o, exact_rect);
-    const uint32_t tile_base = (uint32_t)v * gx * gy;
-    for (int ty = rmin.y; ty < (int)rmax.y; ty++)
-        for (int tx = rmin.x; tx < (int)rmax.x; tx++) {
-            if (!tile_needed(tc, xy, tx, ty)) continue;
-            b.tkeys_in[off] = tile_base + ty * gx + tx;
-            b.tvals_in[off] = slot;
-            off++;
+    uint32_t slot = 0, cnt = 0, off = 0, tile_base = 0;
+    bool big = false;
+    TileJob job;
+    job.xy = make_float2(0.f, 0.f);
+    job.tc.a = job.tc.b = job.tc.c = job.tc.tau = 0.f;
+    job.tc.active = false;
+    job.x0 = job.y0 = job.w = job.n = 0;
+    if (k < n) {
+        slot = g.dvals_out[k];
+        cnt = g.tiles_touched[slot];
+    }
+    if (cnt != 0) {
+        off = g.offsets[k];
+        const int v = slot / P;
+        tile_base = (uint32_t)v * gx * gy;
+        job.xy = g.xy[slot];
+        uint2 rmin, rmax;
+        get_rect(job.xy, radii[slot], rmin, rmax, gx, gy);
+        job.tc = make_cull(g.conic_o[slot], exact_rect);
+        job.x0 = rmin.x; job.y0 = rmin.y;
+        job.w = rmax.x - rmin.x;
+        job.n = job.w * (rmax.y - rmin.y);
+        if (job.n <= SERIAL_TILES) {
+            for (int t = 0; t < job.n; t++) {
+                const int tx = job.x0 + t % job.w, ty = job.y0 + t / job.w;
+                if (!tile_needed(job.tc, job.xy, tx, ty)) continue;
+                b.tkeys_in[off] = tile_base + ty * gx + tx;
+                b.tvals_in[off] = slot;
+                off++;
+            }
+        } else {
+            big = true;
         }
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, big);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const TileJob j = bcast_job(job, src);
+        uint32_t o = __shfl_sync(0xffffffffu, off, src);
+        const uint32_t sl = __shfl_sync(0xffffffffu, slot, src);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tile_base, src);
+        for (int t0 = 0; t0 < j.n; t0 += 32) {
+            const int t = t0 + lane;
+            const int tx = j.x0 + t % j.w, ty = j.y0 + t / j.w;
+            const bool need = t < j.n && tile_needed(j.tc, j.xy, tx, ty);
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                const uint32_t pos = o + __popc(m & ((1u << lane) - 1u));
+                b.tkeys_in[pos] = tb + ty * gx + tx;
+                b.tvals_in[pos] = sl;
+            }
+            o += __popc(m);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -79,7 +79,7 @@ def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_
     V = view_matrix.size(0) if batched else 1
     if sh is not None and sh.numel() != 0:
         raise RuntimeError("SH colours are not supported by libfnx: FluidNexus always passes colors_precomp")
-    if colors is None or colors.numel() == 0:
+    if P and (colors is None or colors.numel() == 0):
         if C_ != 3:
             raise RuntimeError("For non-RGB, provide precomputed Gaussian colors!")  # rasterizer_impl.cu:226-228
         raise RuntimeError("SH colours are not supported by libfnx: FluidNexus always passes colors_precomp")

@@ -134,12 +134,36 @@ def fluid_gaussians(P, channels, seed=0, radius=0.1, height=0.6, log_scale=-5.9)
     return GaussianSet(xyz, scales, _rotations(rng, P), opacity, colors)
 
 
-def background_gaussians(P, channels, seed=1):
-    """Frozen background: uniform on a box shell 0.5-1.5 from the plume centre."""
+def _in_frustum_count(xyz, cams, margin=1.0):
+    """number of cameras whose image (scaled by `margin`) contains each point, z > 0.2"""
+    cnt = np.zeros(xyz.shape[0], dtype=np.int32)
+    for cam in cams:
+        Vm = cam.world_view_transform.cpu().numpy().astype(np.float64)  # transposed storage: p_view = p_h @ Vm
+        ph = np.concatenate([xyz, np.ones((xyz.shape[0], 1))], 1) @ Vm
+        z = ph[:, 2]
+        ok = z > 0.2
+        tx, ty = math.tan(cam.FoVx / 2) * margin, math.tan(cam.FoVy / 2) * margin
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ok &= (np.abs(ph[:, 0] / z) < tx) & (np.abs(ph[:, 1] / z) < ty)
+        cnt += ok
+    return cnt
+
+
+def background_gaussians(P, channels, seed=1, cams=None, min_views=3):
+    """Frozen background: uniform on a box shell 0.5-1.5 from the plume centre, kept only where at least
+    `min_views` of the cameras see it (a reconstructed static scene lives in the cameras' common frustum)."""
     rng = np.random.default_rng(seed)
-    d = rng.normal(size=(P, 3))
-    d /= np.abs(d).max(axis=1, keepdims=True)  # on the unit cube surface
-    xyz = PLUME_CENTER + d * rng.uniform(0.5, 1.5, (P, 1))
+    cams = make_cameras(5, 512) if cams is None else cams
+    chunks, have = [], 0
+    while have < P:
+        n = max(4 * (P - have), 1024)
+        d = rng.normal(size=(n, 3))
+        d /= np.abs(d).max(axis=1, keepdims=True)  # on the unit cube surface
+        cand = PLUME_CENTER + d * rng.uniform(0.5, 1.5, (n, 1))
+        cand = cand[_in_frustum_count(cand, cams) >= min(min_views, len(cams))]
+        chunks.append(cand)
+        have += cand.shape[0]
+    xyz = np.concatenate(chunks, 0)[:P]
     scales = np.exp(rng.uniform(-5.0, -3.0, (P, 3)))
     opacity = rng.uniform(0.2, 0.9, (P, 1))
     colors = rng.uniform(0, 1, (P, channels))

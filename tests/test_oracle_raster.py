@@ -150,7 +150,7 @@ def test_oracle_matches_compiled_reference(oracle_built, path):
     assert np.abs(out["color"] - z["color"]).max() < 1e-4
     assert (out["radii"] == z["radii"]).mean() > 0.999
     assert int(out["num_rendered"]) == pytest.approx(int(z["num_rendered"]), rel=2e-3)
-    dmis = (out["depth"] != z["depth"]).mean()
+    dmis = (np.abs(out["depth"] - z["depth"]) > 1e-5).mean()  # CPU (unfused) depths differ by an ulp
     assert dmis < 2e-3, dmis
     dL = scenes.dL_dpix(name, out["color"].shape)
     g = RasterOracle("f64")

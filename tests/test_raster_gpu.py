@@ -52,7 +52,8 @@ def test_forward_matches_oracle(libfnx, oracle_built, name, exact_rect):
     assert color.shape == ref["color"].shape and depth.shape == ref["depth"].shape
     assert np.abs(color - ref["color"]).max() < PIX_TOL
     assert (radii == ref["radii"]).mean() > 0.999
-    assert (depth != ref["depth"]).mean() < 2e-3  # median depth flips only where T crosses .5 within rounding
+    # median depth flips only where T crosses .5 within rounding (CPU depths are unfused: compare with a tolerance)
+    assert (np.abs(depth - ref["depth"]) > 1e-5).mean() < 2e-3
     if exact_rect:
         assert abs(ctx.num_rendered - ref["num_rendered"]) <= max(2, 2e-3 * ref["num_rendered"])
         st = R.read_image_state(ctx)
