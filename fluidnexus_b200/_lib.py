@@ -63,6 +63,21 @@ SYMBOLS = {
     "fnx_raster_backward": _BWD, "fnx_raster_backward_ch1": _BWD, "fnx_raster_backward_ch3": _BWD,
     "fnx_raster_check": (_I, [C.POINTER(RasterScratch), C.POINTER(_I64), _V]),
     "fnx_mark_visible": (_I, [_I, _V, _V, _V, _V, _V]),
+    "fnx_grid_bytes": (_SZ, [_I]),
+    "fnx_grid_build": (_I, [_V, _I, _F, _V, _V]),
+    "fnx_radius_count": (_I, [_V, _I, _F, _V, _I, _F, _I, _V, _V, _V]),
+    "fnx_radius_fill": (_I, [_V, _I, _F, _V, _I, _F, _V, _V, _V, _V, _V]),
+    "fnx_pbf_density_fwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V]),
+    "fnx_pbf_density_bwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V, _I, _V]),
+    "fnx_visual_advect_fwd": (_I, [_V, _V, _V, _I, _V, _I, _V, _F, _F, _V, _V, _V, _V]),
+    "fnx_visual_advect_bwd": (_I, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _F, _F, _V, _I, _V]),
+    "fnx_pair_distance_loss": (_I, [_V, _V, _I, _F, _F, _F, _V, _V, _V]),
+    "fnx_knn3_mean_dist2": (_I, [_V, _V, _I, _F, _V, _V]),
+    "fnx_pbf_next_tick_fwd": (_I, [_I, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V]),
+    "fnx_pbf_combine_grad": (_I, [_I, _V, _V, _F, _F, _F, _V, _V, _V, _F, _V, _V, _V]),
+    "fnx_pbf_ratio_loss": (_I, [_I, _V, _F, _V, _V, _V]),
+    "fnx_adam_step": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _I, _V]),
+    "fnx_scatter_min": (_I, [_I64, _V, _V, _I, _V, _V, _V]),
     "fnx_raster_read_geom": (_I, [C.POINTER(RasterScratch), _I, _I, _V, _V, _V, _V, _V]),
     "fnx_raster_read_image": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _V, _V, _V]),
 }

@@ -152,6 +152,80 @@ int fnx_raster_check(const fnx_raster_scratch *scratch, int64_t *num_rendered_ho
 int fnx_mark_visible(int32_t P, const float *means3D, const float *view_matrix, const float *proj_matrix,
                      uint8_t *present, fnx_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fixed-radius neighbour grid + particle physics  (replaces torch_cluster.radius / radius_graph
+ * [torch-cluster 1.6.3] and torch_scatter.scatter_min [torch-scatter 2.1.2] as called from
+ * FD/gaussian_splatting/gm_fluid.py:873,909,1076,1088,1114,1140,1206,1256,1272,1301, the poly6 gather /
+ * index_add_ chains of gm_fluid.py:846-862,1107-1158,1291-1336, FD/utils/loss_utils.py:98-121 (distance_loss),
+ * simple_knn distCUDA2 KNN/spatial.h:14, and torch.optim.Adam at gm_fluid.py:349)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* A hashed uniform grid over n points [n,3] with the given cell size, built into caller-owned scratch of
+ * fnx_grid_bytes(n) bytes.  Searches need radius <= cell. */
+size_t fnx_grid_bytes(int32_t n);
+int fnx_grid_build(const float *pts, int32_t n, float cell, void *grid, fnx_stream_t stream);
+
+/* torch_cluster.radius(x, y, r, max_num_neighbors) semantics: for query y_c the neighbours are the x_j with
+ * sum((x_j-y_c)^2) < r^2 (strict), truncated to the first `max_num_neighbors` in x-index order.
+ * counts[c] = number of neighbours kept (int32 [ny], may be NULL); kth[c] = largest x index kept when the cap
+ * binds, INT32_MAX otherwise (int32 [ny], may be NULL): "j is kept  <=>  j within r and j <= kth[c]". */
+int fnx_radius_count(const void *grid_x, int32_t nx, float cell, const float *y, int32_t ny, float r,
+                     int32_t max_num_neighbors, int32_t *counts, int32_t *kth, fnx_stream_t stream);
+/* Edge list like torch_cluster: offsets = exclusive prefix sum of counts (int64 [ny]); writes edge_query (index into
+ * y) and edge_x (index into x, ascending per query), int64 each. */
+int fnx_radius_fill(const void *grid_x, int32_t nx, float cell, const float *y, int32_t ny, float r, const int32_t *kth,
+                    const int64_t *offsets, int64_t *edge_query, int64_t *edge_x, fnx_stream_t stream);
+
+/* P2/P3 density constraint (gm_fluid.py:1107-1158): p_ratio[i] = sum_j poly6(|X_i-X_j|^2) / imass[i] / p0 over the
+ * radius_graph(X, H, loop=True, K) edges (kth from fnx_radius_count(grid(X), X)); grid must be built on X with cell H.
+ * bwd: dL_dX (+)= d/dX of sum_i dL_dpratio[i] * p_ratio[i]   (deterministic gather, no atomics). */
+int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H,
+                        float p0, float *p_ratio, fnx_stream_t stream);
+int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H,
+                        float p0, const float *dL_dpratio, float *dL_dX, int32_t accumulate, fnx_stream_t stream);
+
+/* P1 (gm_fluid.py:1291-1336): visual_out = visual + secs * sum_j w u_j / max(sum_j w, 1e-8), w = poly6(|visual-X_j|^2),
+ * u_j = (X_j - xyz_j)/secs over radius(x=X, y=visual, H, K) edges.  grid_hidden is built on X (cell H); kthV from
+ * fnx_radius_count(grid_hidden, visual).  num_out [V,3] / den_out [V] are saved for the backward.
+ * bwd gathers per hidden particle over grid_visual (built on `visual`, cell H): dL_dX (+)= J^T dL_dvisual_out. */
+int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual,
+                          int32_t V, const int32_t *kthV, float H, float secs, float *visual_out, float *num_out,
+                          float *den_out, fnx_stream_t stream);
+int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *xyz, int32_t N, int32_t V,
+                          const int32_t *kthV, const float *num, const float *den, const float *dL_dvisual_out, float H,
+                          float secs, float *dL_dX, int32_t accumulate, fnx_stream_t stream);
+
+/* P5 distance_loss (loss_utils.py:98-121): *loss = sum_{i != j, d_ij < thr} (thr - d_ij)^2 (device scalar),
+ * dL_dpts [n,3] = grad_scale * dloss/dpts (may be NULL).  grid built on pts with cell >= threshold. */
+int fnx_pair_distance_loss(const void *grid, const float *pts, int32_t n, float cell, float threshold, float grad_scale,
+                           float *loss, float *dL_dpts, fnx_stream_t stream);
+
+/* distCUDA2 (KNN/simple_knn.cu:134-202): mean squared distance to the 3 nearest other points, [n]. */
+int fnx_knn3_mean_dist2(const void *grid, const float *pts, int32_t n, float cell, float *mean_dist2, fnx_stream_t stream);
+
+/* P3 map (gm_fluid.py:846-862): X = scale*e, Y = X + secs*((X-xyz)/secs + b*secs + secs*force),
+ * b = buoyancy*(1 - e_y/buoyancy_max_y) if buoyancy_max_y > 0 else buoyancy.  X or Y may be NULL. */
+int fnx_pbf_next_tick_fwd(int32_t N, const float *e, const float *xyz, const float *buoyancy, const float *force,
+                          float secs, float buoyancy_max_y, float scale_factor, float *X, float *Y, fnx_stream_t stream);
+/* dL_de = scale*dL_dX + (dY/de)^T dL_dY + lambda_exyz * d/de mean((scale*e - estimate_xyz)^2)  (P4,
+ * train_physical_particle.py:333-334); *exyz_loss (device scalar, may be NULL) receives the un-weighted mean.
+ * dL_dX, dL_dY, estimate_xyz may be NULL. */
+int fnx_pbf_combine_grad(int32_t N, const float *e, const float *buoyancy, float secs, float buoyancy_max_y,
+                         float scale_factor, const float *dL_dX, const float *dL_dY, const float *estimate_xyz,
+                         float lambda_exyz, float *dL_de, float *exyz_loss, fnx_stream_t stream);
+/* *loss = mean((p_ratio-1)^2) (l2_loss vs ones, train_physical_particle.py:336-342); dL_dpratio = weight * d loss. */
+int fnx_pbf_ratio_loss(int32_t N, const float *p_ratio, float weight, float *loss, float *dL_dpratio, fnx_stream_t stream);
+
+/* torch.optim.Adam step on a flat fp32 tensor (gm_fluid.py:349: eps 1e-15); grad is multiplied by grad_scale first
+ * (= 1/batch of set_batch_gradient_*, gm_fluid.py:428-430).  step >= 1 is the step count AFTER this update. */
+int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale,
+                  float lr, float beta1, float beta2, float eps, int32_t step, fnx_stream_t stream);
+
+/* torch_scatter.scatter_min(src, index, dim_size=n_out) for 1-D fp32 src and int64 index (gm_fluid.py:1088,1272):
+ * out [n_out] (0 for empty groups), arg [n_out] int64 (n for empty groups). */
+int fnx_scatter_min(int64_t n, const float *src, const int64_t *index, int32_t n_out, float *out, int64_t *arg,
+                    fnx_stream_t stream);
+
 /* Introspection for parity tests: device-to-device copies of the forward's intermediate state.  Any destination may
  * be NULL.  xy [V,P,2], depth [V,P], conic_opacity [V,P,4] (R3 GeometryState means2D/depths/conic_opacity,
  * rasterizer_impl.h:28-46), tiles_touched [V,P] (after tile culling); final_T / n_contrib [V,H,W]

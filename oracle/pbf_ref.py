@@ -1,0 +1,247 @@
+"""oracle/pbf_ref.py -- torch-CPU restatement of the particle-physics terms.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, bench.py's cpu_baseline/reference legs and __graft_entry__.smoke() may import this; the product
+(fluidnexus_b200/) never does.
+
+Restates, op for op, from the reference (FD = FluidDynamics):
+  poly6 kernel                               FD/gaussian_splatting/gm_fluid.py:124,166-169
+  P1 get_visual_xyz_from_nn                  gm_fluid.py:1291-1336
+  P2 get_gas_constraints_from_exyz_nn        gm_fluid.py:1107-1132
+  P3 get_gas_constraints_from_vel_nn_guess   gm_fluid.py:1134-1158 + get_guess_hidden_particles_from_nn :846-862
+  P4 exyz tie, step loss assembly            FD/entries_scalar_real/train_physical_particle.py:328-355
+  P5 distance_loss                           FD/utils/loss_utils.py:98-121
+  P6 grad cache / batch average              gm_fluid.py:409-430
+  P7 Adam(eps=1e-15), lr never updated       gm_fluid.py:330-355,401-407
+
+PARITY UNPINNED for the neighbour search: the reference calls `torch_cluster.radius / radius_graph`
+(torch-cluster==1.6.3, fluid_nexus.yml:397) and `torch_scatter.scatter_min` (torch-scatter==2.1.2, :399), third-party
+CUDA extensions that are neither vendored in /root/reference nor installed here, and the reference has no tests
+or golden vectors for this path.  `radius` / `radius_graph` below restate the published
+algorithm of torch-cluster 1.6.3's CUDA kernel (csrc/cuda/radius_cuda.cu): for each query y_c scan x in index
+order, accept j iff sum_d (x_j - y_c)^2 < r^2 (strict), stop after max_num_neighbors hits; radius_graph(x, r, loop,
+K) = radius(x, x, r, K if loop else K+1), rows swapped for flow='source_to_target' (row = neighbour, col = query),
+self pairs dropped when loop=False.  Anchors are the reference's own call sites listed above and closed-form
+checks (two-particle density = poly6(0) + poly6(d^2), ...) in tests/test_oracle_pbf.py.
+
+`distance_loss` is restated with exact coordinate differences; the reference's `torch.cdist` switches to the
+|a|^2+|b|^2-2ab matmul form for more than 25 points, which carries ~1e-3 relative noise at the distances this
+term looks at (and needs O(V^2) memory).
+"""
+import math
+
+import numpy as np
+import torch
+
+SCALE_FACTOR = 100.0  # gm_fluid.py:122
+EPSILON = 1e-8        # gm_fluid.py:99
+
+
+# ------------------------------------------------------------------------------------------------------------
+# torch_cluster / torch_scatter semantics
+# ------------------------------------------------------------------------------------------------------------
+def radius(x, y, r, max_num_neighbors=32):
+    """edge_index[0] = index into y (query), [1] = index into x; first `max_num_neighbors` hits in x-index order."""
+    xn = x.detach().cpu().numpy().astype(np.float32)
+    yn = y.detach().cpu().numpy().astype(np.float32)
+    r2 = np.float32(r) * np.float32(r)
+    rows, cols = [], []
+    if xn.shape[0] * yn.shape[0] <= 4_000_000:
+        for c in range(yn.shape[0]):
+            d = ((xn - yn[c]) ** 2).sum(1, dtype=np.float32)
+            hit = np.nonzero(d < r2)[0][:max_num_neighbors]
+            rows.append(np.full(hit.shape, c, np.int64))
+            cols.append(hit.astype(np.int64))
+    else:
+        from scipy.spatial import cKDTree
+        tree = cKDTree(xn.astype(np.float64))
+        cand = tree.query_ball_point(yn.astype(np.float64), float(r) * (1 + 1e-5) + 1e-6, return_sorted=True)
+        for c, js in enumerate(cand):
+            js = np.asarray(js, np.int64)
+            d = ((xn[js] - yn[c]) ** 2).sum(1, dtype=np.float32)
+            hit = js[d < r2][:max_num_neighbors]
+            rows.append(np.full(hit.shape, c, np.int64))
+            cols.append(hit)
+    row = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    col = np.concatenate(cols) if cols else np.zeros(0, np.int64)
+    return torch.from_numpy(np.stack([row, col]))
+
+
+def radius_graph(x, r, loop=False, max_num_neighbors=32):
+    e = radius(x, x, r, max_num_neighbors if loop else max_num_neighbors + 1)
+    row, col = e[1], e[0]  # flow == 'source_to_target'
+    if not loop:
+        m = row != col
+        row, col = row[m], col[m]
+    return torch.stack([row, col])
+
+
+def scatter_min(src, index, dim=0, dim_size=None):
+    """torch_scatter.scatter_min for 1-D src: (min per index, argmin; empty groups -> (0, src.numel()))."""
+    n = int(index.max()) + 1 if dim_size is None else dim_size
+    out = torch.zeros(n, dtype=src.dtype)
+    arg = torch.full((n,), src.numel(), dtype=torch.long)
+    s, ix = src.detach().numpy(), index.numpy()
+    best = {}
+    for k in range(s.shape[0]):
+        i = int(ix[k])
+        if i not in best or s[k] < s[best[i]]:
+            best[i] = k
+    for i, k in best.items():
+        out[i] = float(s[k])
+        arg[i] = k
+    return out, arg
+
+
+# ------------------------------------------------------------------------------------------------------------
+# physics terms
+# ------------------------------------------------------------------------------------------------------------
+class PBFParams:
+    """The constants the reference reads from `optim_args` (FD/arguments/__init__.py:308,312 + configs)."""
+
+    def __init__(self, H=2.0, KNN_K=100, p0=1.5, secs=0.033, buoyancy_max_y=0.0, lambda_dssim=0.2, lambda_image=1.0,
+                 lambda_current_distance=0.1, lambda_exyz=0.1, lambda_gas_constraints=1.0,
+                 lambda_next_gas_constraints=0.1, distance_threshold_visual=0.002, lr=1.6e-4):
+        self.H, self.KNN_K, self.p0, self.secs, self.buoyancy_max_y = H, KNN_K, p0, secs, buoyancy_max_y
+        self.lambda_dssim, self.lambda_image = lambda_dssim, lambda_image
+        self.lambda_current_distance, self.lambda_exyz = lambda_current_distance, lambda_exyz
+        self.lambda_gas_constraints, self.lambda_next_gas_constraints = lambda_gas_constraints, lambda_next_gas_constraints
+        self.distance_threshold_visual, self.lr = distance_threshold_visual, lr
+        self.H2 = H * H
+        self.poly6_term1 = 315.0 / (64.0 * np.pi * H ** 9)  # gm_fluid.py:124
+
+
+def poly6(prm, r2):
+    term2 = prm.H2 - r2
+    mask = r2 < prm.H2
+    return mask * prm.poly6_term1 * (term2 ** 3)
+
+
+def visual_xyz_from_nn(prm, estimate_xyz_nn, xyz, visual_xyz):
+    """P1.  estimate_xyz_nn [N,3] (trainable, render units), xyz [N,3], visual_xyz [V,3] (scaled units)."""
+    visual_xyz = visual_xyz.detach()
+    est = estimate_xyz_nn * SCALE_FACTOR
+    velocity_nn = (est - xyz) / prm.secs
+    V = visual_xyz.shape[0]
+    e = radius(x=est, y=visual_xyz, r=prm.H, max_num_neighbors=prm.KNN_K)
+    row, col = e[0], e[1]
+    diff = visual_xyz[row] - est[col]
+    dist2 = torch.sum(diff ** 2, dim=1)
+    p6 = poly6(prm, dist2)
+    weighted_velocity = velocity_nn[col] * p6.unsqueeze(-1)
+    visual_velocity = torch.zeros(V, 3, dtype=est.dtype).index_add_(0, row, weighted_velocity)
+    sum_p6 = torch.zeros(V, dtype=est.dtype).index_add_(0, row, p6).clamp_min(EPSILON)
+    return visual_xyz + visual_velocity * prm.secs / sum_p6.unsqueeze(-1)
+
+
+def _density_ratio(prm, pos, imass):
+    N = pos.shape[0]
+    e = radius_graph(pos, r=prm.H, loop=True, max_num_neighbors=prm.KNN_K)
+    row, col = e
+    diff = pos[row] - pos[col]
+    dist2 = torch.sum(diff ** 2, dim=1)
+    pi = torch.zeros(N, dtype=pos.dtype).index_add_(0, row, poly6(prm, dist2))
+    return pi.unsqueeze(1) / imass / prm.p0
+
+
+def gas_constraints_from_exyz_nn(prm, estimate_xyz_nn, imass):
+    """P2: p_ratio [N,1] at the optimised positions."""
+    return _density_ratio(prm, estimate_xyz_nn * SCALE_FACTOR, imass)
+
+
+def guess_hidden_particles_from_nn(prm, estimate_xyz_nn, xyz, buoyancy, force):
+    """gm_fluid.py:846-862 (note: the UNSCALED parameter's y drives the buoyancy coefficient)."""
+    if prm.buoyancy_max_y > 0.0:
+        cur_buoyancy = buoyancy * (1.0 - (estimate_xyz_nn[:, 1:2] / prm.buoyancy_max_y))
+    else:
+        cur_buoyancy = buoyancy
+    tmp_velocity = (estimate_xyz_nn * SCALE_FACTOR - xyz) / prm.secs
+    estimate_velocity = tmp_velocity + cur_buoyancy * prm.secs + prm.secs * force
+    return estimate_xyz_nn * SCALE_FACTOR + prm.secs * estimate_velocity
+
+
+def gas_constraints_from_vel_nn_guess(prm, estimate_xyz_nn, xyz, buoyancy, force, imass):
+    """P3: p_ratio [N,1] one advection tick later."""
+    return _density_ratio(prm, guess_hidden_particles_from_nn(prm, estimate_xyz_nn, xyz, buoyancy, force), imass)
+
+
+def l2_loss(a, b):
+    return ((a - b) ** 2).mean()
+
+
+def distance_loss(positions, threshold):
+    """P5 (loss_utils.py:98-121) with exact differences instead of cdist's matmul form; O(V^2) memory."""
+    d = positions.unsqueeze(1) - positions.unsqueeze(0)
+    d2 = (d ** 2).sum(-1)
+    eye = torch.eye(positions.shape[0], dtype=torch.bool)
+    dist = torch.sqrt(torch.where(eye, torch.ones_like(d2), d2))  # keep sqrt'(0) off the diagonal-free graph
+    mask = (dist < threshold) & ~eye & (d2 > 0)
+    # exact duplicates (d == 0): value (thr-0)^2 with zero gradient, as cdist's backward gives
+    dup = (~eye) & (d2 <= 0)
+    loss = (((threshold - dist) * mask.to(dist.dtype)).clamp(min=0) ** 2).sum()
+    return loss + dup.sum().to(dist.dtype) * threshold ** 2
+
+
+def physics_loss_terms(prm, estimate_xyz_nn, st, with_distance=True, visual_xyz=None):
+    """The view-independent part of the step loss (train_physical_particle.py:331-355) and the advected visual
+    positions.  `st` holds torch tensors xyz, estimate_xyz, buoyancy, force, imass [,visual_xyz]."""
+    vis = visual_xyz_from_nn(prm, estimate_xyz_nn, st["xyz"], st["visual_xyz"] if visual_xyz is None else visual_xyz)
+    render_xyz = vis / SCALE_FACTOR
+    terms = {}
+    terms["dist"] = distance_loss(render_xyz, prm.distance_threshold_visual) if with_distance else torch.zeros(())
+    terms["exyz"] = l2_loss(estimate_xyz_nn * SCALE_FACTOR, st["estimate_xyz"])
+    p_ratio = gas_constraints_from_exyz_nn(prm, estimate_xyz_nn, st["imass"])
+    terms["gas"] = l2_loss(p_ratio, torch.ones_like(p_ratio))
+    p_next = gas_constraints_from_vel_nn_guess(prm, estimate_xyz_nn, st["xyz"], st["buoyancy"], st["force"], st["imass"])
+    terms["next_gas"] = l2_loss(p_next, torch.ones_like(p_next))
+    total = (prm.lambda_current_distance * terms["dist"] + prm.lambda_exyz * terms["exyz"]
+             + prm.lambda_gas_constraints * terms["gas"] + prm.lambda_next_gas_constraints * terms["next_gas"])
+    return total, terms, render_xyz, p_ratio, p_next
+
+
+# ------------------------------------------------------------------------------------------------------------
+# image losses (loss_utils.py:9-64) -- plain torch, used as the fp32 reference of the fused CUDA loss kernels
+# ------------------------------------------------------------------------------------------------------------
+def l1_loss(a, b):
+    return torch.abs(a - b).mean()
+
+
+def _window(window_size, channel):
+    g = torch.tensor([math.exp(-((x - window_size // 2) ** 2) / float(2 * 1.5 ** 2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    w2 = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0)
+    return w2.expand(channel, 1, window_size, window_size).contiguous()
+
+
+def ssim(img1, img2, window_size=11):
+    import torch.nn.functional as F
+    channel = img1.size(-3)
+    window = _window(window_size, channel).to(img1.dtype).to(img1.device)
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
+    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
+    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
+    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return ssim_map.mean()
+
+
+def image_loss(prm, image, gt, grey=False):
+    """0.8*l1 + 0.2*(1-ssim) (train_physical_particle.py:328-329,346-347); `grey` applies the FluidNexus entries'
+    channel-mean conversion to both images first (entries_fluid_nexus/train_physical_particle.py:356-360)."""
+    if grey:
+        gt = torch.cat([torch.mean(gt, dim=0, keepdim=True)] * 3, dim=0)
+        image = torch.cat([torch.mean(image, dim=0, keepdim=True)] * 3, dim=0)
+    l1 = l1_loss(image, gt)
+    s = 1.0 - ssim(image, gt)
+    return (1.0 - prm.lambda_dssim) * l1 * prm.lambda_image + prm.lambda_dssim * s * prm.lambda_image, l1, s
+
+
+def knn3_mean_dist2(points):
+    """distCUDA2 (KNN/simple_knn.cu:134-166): mean of the 3 smallest squared distances to OTHER points."""
+    from scipy.spatial import cKDTree
+    p = np.asarray(points, np.float64)
+    d, _ = cKDTree(p).query(p, k=4)
+    return (d[:, 1:4] ** 2).mean(1)

@@ -1,0 +1,89 @@
+"""CPU: pins for the physics oracle (oracle/pbf_ref.py).  The neighbour search is PARITY-UNPINNED against
+torch_cluster (not installable here); these tests anchor the restatement on closed forms and internal consistency."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from fluidnexus_b200 import synthetic as S
+from oracle import pbf_ref as O
+
+
+def test_radius_semantics_first_k_in_index_order():
+    x = torch.tensor([[0.0, 0, 0], [0.5, 0, 0], [1.0, 0, 0], [1.9, 0, 0], [2.0, 0, 0], [5.0, 0, 0]])
+    y = torch.tensor([[0.0, 0, 0], [5.0, 0, 0]])
+    e = O.radius(x, y, 2.0, max_num_neighbors=10)
+    # strict < r: the point at exactly distance 2.0 is excluded
+    assert e.tolist() == [[0, 0, 0, 0, 1], [0, 1, 2, 3, 5]]
+    e = O.radius(x, y, 2.0, max_num_neighbors=2)  # cap keeps the first two BY INDEX, not the nearest
+    assert e.tolist() == [[0, 0, 1], [0, 1, 5]]
+    g = O.radius_graph(x, 2.0, loop=True, max_num_neighbors=10)
+    assert g.shape[0] == 2 and (g[0] == g[1]).sum() == 6   # self loops kept; row = neighbour, col = query
+    g2 = O.radius_graph(x, 2.0, loop=False, max_num_neighbors=10)
+    assert (g2[0] == g2[1]).sum() == 0 and g2.shape[1] == g.shape[1] - 6
+
+
+def test_two_particle_density_closed_form():
+    prm = O.PBFParams(H=2.0, p0=1.5)
+    d = 0.7
+    e = torch.tensor([[0.0, 0, 0], [d / 100.0, 0, 0]])
+    pr = O.gas_constraints_from_exyz_nn(prm, e, torch.ones(2, 1))
+    t1 = 315.0 / (64 * math.pi * 2.0 ** 9)
+    expect = (t1 * 4.0 ** 3 + t1 * (4.0 - d * d) ** 3) / 1.5
+    assert torch.allclose(pr, torch.full((2, 1), expect), rtol=1e-5)
+
+
+def test_advect_uniform_velocity_moves_visual_by_secs_u():
+    """If every hidden particle has the same velocity u, the poly6-weighted mean is u and visual moves by secs*u."""
+    prm = O.PBFParams(secs=0.033)
+    hp = S.cube_lattice(8, seed=1)
+    xyz = torch.from_numpy(hp.xyz).float()
+    u = torch.tensor([1.0, 30.0, -2.0])
+    est = (xyz + prm.secs * u) / 100.0
+    vis = xyz[:50] + 0.3
+    out = O.visual_xyz_from_nn(prm, est, xyz, vis)
+    inside = ((out - vis) - prm.secs * u).abs().max()
+    assert inside < 2e-4
+
+
+def test_distance_loss_matches_reference_formula_small():
+    torch.manual_seed(0)
+    p = torch.rand(40, 3) * 0.01
+    thr = 0.004
+    d = torch.cdist(p.double(), p.double(), p=2, compute_mode="donot_use_mm_for_euclid_dist")
+    mask = d < thr
+    mask.fill_diagonal_(False)
+    ref = ((thr - d) * mask.double()).clamp(min=0).pow(2).sum()
+    assert abs(O.distance_loss(p.double(), thr) - ref) < 1e-12
+
+
+def test_guess_next_tick_formula():
+    prm = O.PBFParams(secs=0.033, buoyancy_max_y=0.8)
+    e = torch.tensor([[0.3, 0.4, -0.2]])
+    xyz = torch.tensor([[29.0, 39.5, -20.5]])
+    b = torch.tensor([[0.0, 1.96, 0.0]])
+    f = torch.tensor([[0.5, 0.0, 0.0]])
+    y = O.guess_hidden_particles_from_nn(prm, e, xyz, b, f)
+    coeff = 1 - 0.4 / 0.8
+    v = (e * 100 - xyz) / 0.033 + b * coeff * 0.033 + 0.033 * f
+    assert torch.allclose(y, e * 100 + 0.033 * v)
+
+
+def test_knn3_oracle():
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3], [10, 10, 10]], float)
+    out = O.knn3_mean_dist2(pts)
+    assert abs(out[0] - (1 + 4 + 9) / 3) < 1e-9
+
+
+def test_physics_loss_terms_backward_runs():
+    prm = O.PBFParams()
+    hp = S.cube_lattice(6, seed=4)
+    st = dict(xyz=torch.from_numpy(hp.xyz).float(), estimate_xyz=torch.from_numpy(hp.estimate_xyz).float(),
+              buoyancy=torch.from_numpy(hp.buoyancy).float(), force=torch.from_numpy(hp.force).float(),
+              imass=torch.from_numpy(hp.imass).float(), visual_xyz=torch.from_numpy(hp.xyz[:30] + 0.2).float())
+    e = (st["estimate_xyz"] / 100).clone().requires_grad_(True)
+    total, terms, render_xyz, p, pn = O.physics_loss_terms(prm, e, st)
+    total.backward()
+    assert torch.isfinite(e.grad).all() and e.grad.abs().sum() > 0
+    assert p.shape == (216, 1) and render_xyz.shape == (30, 3)
