@@ -69,8 +69,8 @@ SYMBOLS = {
     "fnx_radius_fill": (_I, [_V, _I, _F, _V, _I, _F, _V, _V, _V, _V, _V]),
     "fnx_pbf_density_fwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V]),
     "fnx_pbf_density_bwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V, _I, _V]),
-    "fnx_visual_advect_fwd": (_I, [_V, _V, _V, _I, _V, _I, _V, _F, _F, _V, _V, _V, _V]),
-    "fnx_visual_advect_bwd": (_I, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _F, _F, _V, _I, _V]),
+    "fnx_visual_advect_fwd": (_I, [_V, _V, _V, _I, _V, _I, _V, _F, _F, _F, _V, _V, _V, _V]),
+    "fnx_visual_advect_bwd": (_I, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _V, _F, _F, _F, _V, _I, _V]),
     "fnx_pair_distance_loss": (_I, [_V, _V, _I, _F, _F, _F, _V, _V, _V]),
     "fnx_knn3_mean_dist2": (_I, [_V, _V, _I, _F, _V, _V]),
     "fnx_pbf_next_tick_fwd": (_I, [_I, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V]),
@@ -78,6 +78,8 @@ SYMBOLS = {
     "fnx_pbf_ratio_loss": (_I, [_I, _V, _F, _V, _V, _V]),
     "fnx_adam_step": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _I, _V]),
     "fnx_scatter_min": (_I, [_I64, _V, _V, _I, _V, _V, _V]),
+    "fnx_image_loss_bytes": (_SZ, [_I, _I, _I, _I]),
+    "fnx_image_loss": (_I, [_I, _I, _I, _I, _V, _V, _I, _F, _F, _V, _V, _V, _V, _V]),
     "fnx_raster_read_geom": (_I, [C.POINTER(RasterScratch), _I, _I, _V, _V, _V, _V, _V]),
     "fnx_raster_read_image": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _V, _V, _V]),
 }

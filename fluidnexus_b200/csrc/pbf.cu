@@ -268,7 +268,8 @@ density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
 __global__ void __launch_bounds__(128)
 advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100*e*/, const float *__restrict__ xyz,
                   const float *__restrict__ vis, int V, const int *__restrict__ kthV, float H2, float term1, float secs,
-                  float eps, float *__restrict__ vis_out, float *__restrict__ num_out, float *__restrict__ den_out) {
+                  float eps, float out_div, float *__restrict__ vis_out, float *__restrict__ num_out,
+                  float *__restrict__ den_out) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     const float3 q = make_float3(vis[3 * v], vis[3 * v + 1], vis[3 * v + 2]);
@@ -284,9 +285,10 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
         den += w;
     });
     const float dc = fmaxf(den, eps);
-    vis_out[3 * v] = q.x + num.x * secs / dc;
-    vis_out[3 * v + 1] = q.y + num.y * secs / dc;
-    vis_out[3 * v + 2] = q.z + num.z * secs / dc;
+    // out_div = scale_factor when the caller wants render units (pipe_fluid.py:45: raw_render_xyz / gm.scale_factor)
+    vis_out[3 * v] = (q.x + num.x * secs / dc) / out_div;
+    vis_out[3 * v + 1] = (q.y + num.y * secs / dc) / out_div;
+    vis_out[3 * v + 2] = (q.z + num.z * secs / dc) / out_div;
     if (num_out) { num_out[3 * v] = num.x; num_out[3 * v + 1] = num.y; num_out[3 * v + 2] = num.z; }
     if (den_out) den_out[v] = den;
 }
@@ -297,8 +299,8 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
 __global__ void __launch_bounds__(128)
 advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, const float *__restrict__ xyz, int N,
                   const int *__restrict__ kthV, const float *__restrict__ num, const float *__restrict__ den,
-                  const float *__restrict__ G /*dL/dvis_out [V,3]*/, float H2, float term1, float secs, float eps,
-                  float *__restrict__ dL_dX, int accumulate) {
+                  const float *__restrict__ G /*dL/dvis_out [V,3]*/, const float *__restrict__ G2 /*optional second term*/,
+                  float g_scale, float H2, float term1, float secs, float eps, float *__restrict__ dL_dX, int accumulate) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     const float3 xj = make_float3(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
@@ -306,7 +308,9 @@ advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, cons
     float3 acc = make_float3(0.f, 0.f, 0.f);
     for_each_neighbor(gv, inv_cell, xj, H2, [&](int v, const float4 &pv, float d2) {
         if (j > kthV[v]) return;
-        const float3 Gv = make_float3(G[3 * v], G[3 * v + 1], G[3 * v + 2]);
+        float3 Gv = make_float3(G[3 * v], G[3 * v + 1], G[3 * v + 2]);
+        if (G2) { Gv.x += G2[3 * v]; Gv.y += G2[3 * v + 1]; Gv.z += G2[3 * v + 2]; }
+        Gv.x *= g_scale; Gv.y *= g_scale; Gv.z *= g_scale;
         const float dn = den[v];
         const float dc = fmaxf(dn, eps);
         const float w = poly6(d2, H2, term1);
@@ -571,27 +575,27 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
 }
 
 int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual, int32_t V,
-                          const int32_t *kthV, float H, float secs, float *visual_out, float *num_out, float *den_out,
-                          fnx_stream_t stream) {
-    FNX_REQUIRE(grid_hidden && X && xyz && kthV && visual_out && (visual || V == 0), "bad arguments");
+                          const int32_t *kthV, float H, float secs, float out_div, float *visual_out, float *num_out,
+                          float *den_out, fnx_stream_t stream) {
+    FNX_REQUIRE(grid_hidden && X && xyz && kthV && visual_out && (visual || V == 0) && out_div != 0.f, "bad arguments");
     if (V == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_hidden, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
     advect_fwd_kernel<<<(V + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, kthV, H * H, term1, secs, 1e-8f,
-                                                                       visual_out, num_out, den_out);
+                                                                       out_div, visual_out, num_out, den_out);
     FNX_LAUNCH_CHECK("advect_fwd_kernel");
     return FNX_OK;
 }
 
 int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *xyz, int32_t N, int32_t V, const int32_t *kthV,
-                          const float *num, const float *den, const float *dL_dvisual_out, float H, float secs, float *dL_dX,
-                          int32_t accumulate, fnx_stream_t stream) {
+                          const float *num, const float *den, const float *dL_dvisual_out, const float *dL_dvisual_out2,
+                          float g_scale, float H, float secs, float *dL_dX, int32_t accumulate, fnx_stream_t stream) {
     FNX_REQUIRE(grid_visual && X && xyz && kthV && num && den && dL_dvisual_out && dL_dX, "bad arguments");
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_visual, V);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    advect_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, kthV, num, den, dL_dvisual_out, H * H, term1,
-                                                                       secs, 1e-8f, dL_dX, accumulate);
+    advect_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, kthV, num, den, dL_dvisual_out, dL_dvisual_out2, g_scale,
+                                                                       H * H, term1, secs, 1e-8f, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("advect_bwd_kernel");
     return FNX_OK;
 }

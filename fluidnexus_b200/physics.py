@@ -190,8 +190,8 @@ class _VisualAdvect(torch.autograd.Function):
         den = torch.empty((V,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             L.check(L.lib().fnx_visual_advect_fwd(gh.buf.data_ptr(), Xc.data_ptr(), xc.data_ptr(), N, vc.data_ptr(), V,
-                                                  kthV.data_ptr(), float(H), float(secs), out.data_ptr(), num.data_ptr(),
-                                                  den.data_ptr(), _stream(dev)))
+                                                  kthV.data_ptr(), float(H), float(secs), 1.0, out.data_ptr(),
+                                                  num.data_ptr(), den.data_ptr(), _stream(dev)))
         ctx.saved = (Xc, xc, vc, kthV, num, den, float(H), float(secs))
         return out
 
@@ -204,8 +204,8 @@ class _VisualAdvect(torch.autograd.Function):
         dX = torch.empty((N, 3), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             L.check(L.lib().fnx_visual_advect_bwd(gv.buf.data_ptr(), Xc.data_ptr(), xc.data_ptr(), N, V, kthV.data_ptr(),
-                                                  num.data_ptr(), den.data_ptr(), G.data_ptr(), H, secs, dX.data_ptr(), 0,
-                                                  _stream(dev)))
+                                                  num.data_ptr(), den.data_ptr(), G.data_ptr(), None, 1.0, H, secs,
+                                                  dX.data_ptr(), 0, _stream(dev)))
         return dX, None, None, None, None, None
 
 

@@ -1,0 +1,225 @@
+"""The FluidDynamics physical-particle training step as ONE fused launch sequence on libfnx.
+
+Mirrors one iteration of the reference's hot loop (FD/entries_scalar_real/train_physical_particle.py:301-381 and its
+FluidNexus twin FD/entries_fluid_nexus/train_physical_particle.py:330-420) for one frame and a batch of views:
+
+    zero_gradient_cache_current()                                   gm_fluid.py:419-421
+    for each sampled camera:                                         train_physical_particle.py:310
+        render_func(..., pos_type="guess_visual_nn", scale=True)    pipe_fluid.py:8-135 / pipe_dynamics.py:8-180
+            gm.get_visual_xyz_from_nn()                              gm_fluid.py:1291-1336                [P1]
+        l1_loss, 1 - ssim (grey conversion for FluidNexus scenes)    loss_utils.py:9-64                   [L1-L3]
+        distance_loss(visual_xyz, thr)                               loss_utils.py:98-121                 [P5]
+        exyz l2, gas constraints now / next tick                     gm_fluid.py:1107-1158,846-862        [P2-P4]
+        loss.backward(); cache_gradient_current()                    gm_fluid.py:423-425
+    set_batch_gradient_current(batch); optimizer.step()              gm_fluid.py:427-430, Adam :349       [P6,P7]
+
+What is fused: all views are rendered by one batched rasterizer call; the view-independent physics terms are
+evaluated once (the reference re-evaluates them per view and averages, which gives weight 1); every term is a
+hand-written gather kernel (no edge lists, no autograd graph); there is no host synchronisation inside the step
+(losses stay on the device until the caller reads them).
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib as L
+from . import rasterizer as R
+
+
+@dataclass
+class StepParams:
+    """Constants of FD/arguments/__init__.py + configs (values: scalar_real.json / fluid_nexus_smoke_dynamics.json)."""
+    H: float = 2.0
+    KNN_K: int = 100
+    p0: float = 1.5
+    secs: float = 0.033
+    buoyancy_max_y: float = 0.0
+    scale_factor: float = 100.0
+    lambda_dssim: float = 0.2
+    lambda_image: float = 1.0
+    lambda_current_distance: float = 0.1
+    lambda_exyz: float = 0.1
+    lambda_gas_constraints: float = 1.0
+    lambda_next_gas_constraints: float = 0.1
+    distance_threshold_visual: float = 0.002
+    lr: float = 1.6e-4          # position_lr_init * spatial_lr_scale; never rescheduled (gm_fluid.py:401-407)
+    adam_eps: float = 1e-15
+    grey: bool = False          # FluidNexus entries compare channel-mean images (train_physical_particle.py:356-360)
+
+
+def _dev_f32(x, dev):
+    t = torch.as_tensor(x, dtype=torch.float32)
+    return t.to(dev).contiguous()
+
+
+class FrameState:
+    """Per-frame state the reference keeps in gm_fluid.GaussianModel, laid out for the fused step.
+
+    Gaussians rendered = [V fluid particles] ++ [Pb frozen background Gaussians] (pipe_dynamics.py:51-57,139-148);
+    the fluid rows of `means3D` are rewritten by P1 every step, everything else is static within a frame."""
+
+    def __init__(self, hidden, visual_xyz_scaled, fluid, background=None, device="cuda", prm: StepParams = None):
+        dev = torch.device(device)
+        self.dev = dev
+        self.N, self.V = hidden.N, visual_xyz_scaled.shape[0]
+        self.xyz = _dev_f32(hidden.xyz, dev)
+        self.estimate_xyz = _dev_f32(hidden.estimate_xyz, dev)
+        self.buoyancy = _dev_f32(hidden.buoyancy, dev)
+        self.force = _dev_f32(hidden.force, dev)
+        self.imass = _dev_f32(hidden.imass, dev).reshape(-1)
+        self.visual = _dev_f32(visual_xyz_scaled, dev)
+        sf = (prm or StepParams()).scale_factor
+        # training_setup_current(): _estimate_xyz_nn = estimate_xyz / scale_factor (gm_fluid.py:333-334)
+        self.e = (self.estimate_xyz / sf).contiguous()
+        self.m = torch.zeros_like(self.e)
+        self.v = torch.zeros_like(self.e)
+        self.adam_step = 0
+        f = fluid.torch(dev)
+        parts = [f] + ([background.torch(dev)] if background is not None else [])
+        self.Pb = background.P if background is not None else 0
+        self.P = self.V + self.Pb
+        self.C = f["colors"].shape[1]
+        cat = lambda k: torch.cat([p[k] for p in parts], 0).contiguous()
+        self.means3D = cat("xyz")          # rows [0,V) are overwritten each step
+        self.scales, self.rotations = cat("scales"), cat("rotations")
+        self.opacity, self.colors = cat("opacity").reshape(-1).contiguous(), cat("colors")
+        lib = L.lib()
+        N, V = self.N, self.V
+        nb = lambda n: torch.empty(lib.fnx_grid_bytes(n), dtype=torch.uint8, device=dev)
+        self.gridX, self.gridY, self.gridP, self.gridVis = nb(N), nb(N), nb(V), nb(V)
+        z = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)
+        self.X, self.Y, self.dX, self.dY, self.de = z(N, 3), z(N, 3), z(N, 3), z(N, 3), z(N, 3)
+        self.kthX, self.kthY, self.kthV = z(N, dt=torch.int32), z(N, dt=torch.int32), z(V, dt=torch.int32)
+        self.p, self.pn, self.gp, self.gpn = z(N), z(N), z(N), z(N)
+        self.num, self.den, self.dDist = z(V, 3), z(V), z(V, 3)
+        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)  # gas, next_gas, exyz, dist
+        self.vis_grid_built = False
+
+
+class PhysicalStep:
+    """step(frame, view_ids, gt) -> dict of device scalars.  `cams`: list of camera objects with the attributes of
+    FD/scene/camera.py (world_view_transform, full_proj_transform, FoVx, FoVy, image_width, image_height)."""
+
+    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda"):
+        import math
+        self.prm = prm or StepParams()
+        self.dev = torch.device(device)
+        self.C = channels
+        self.view_all = torch.stack([c.world_view_transform.float() for c in cams]).to(self.dev).contiguous()
+        self.proj_all = torch.stack([c.full_proj_transform.float() for c in cams]).to(self.dev).contiguous()
+        c0 = cams[0]
+        self.W, self.H = int(c0.image_width), int(c0.image_height)
+        self.tan_fov_x, self.tan_fov_y = math.tan(c0.FoVx * 0.5), math.tan(c0.FoVy * 0.5)
+        self.bg = _dev_f32([0.0] * channels if bg_color is None else bg_color, self.dev)
+        self._loss_scratch = {}
+        self.lib = L.lib()
+
+    # -- pieces ---------------------------------------------------------------------------------------------
+    def physics_forward(self, fr: FrameState):
+        """P2, P3, P1-forward, P5: fills fr.means3D[:V], fr.dX, fr.dY, fr.dDist and the loss scalars."""
+        lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
+        N, V = fr.N, fr.V
+        ck = L.check
+        ck(lib.fnx_pbf_next_tick_fwd(N, fr.e.data_ptr(), fr.xyz.data_ptr(), fr.buoyancy.data_ptr(), fr.force.data_ptr(), prm.secs,
+                                     prm.buoyancy_max_y, prm.scale_factor, fr.X.data_ptr(), fr.Y.data_ptr(), st))
+        for grid, pos, kth, p, gp, lam, slot in ((fr.gridX, fr.X, fr.kthX, fr.p, fr.gp, prm.lambda_gas_constraints, 0),
+                                                 (fr.gridY, fr.Y, fr.kthY, fr.pn, fr.gpn, prm.lambda_next_gas_constraints, 1)):
+            ck(lib.fnx_grid_build(pos.data_ptr(), N, prm.H, grid.data_ptr(), st))
+            ck(lib.fnx_radius_count(grid.data_ptr(), N, prm.H, pos.data_ptr(), N, prm.H, prm.KNN_K, None, kth.data_ptr(), st))
+            ck(lib.fnx_pbf_density_fwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
+                                       p.data_ptr(), st))
+            ck(lib.fnx_pbf_ratio_loss(N, p.data_ptr(), lam, fr.scalars[slot:].data_ptr(), gp.data_ptr(), st))
+        ck(lib.fnx_pbf_density_bwd(fr.gridX.data_ptr(), fr.X.data_ptr(), N, fr.imass.data_ptr(), fr.kthX.data_ptr(), prm.H, prm.p0,
+                                   fr.gp.data_ptr(), fr.dX.data_ptr(), 0, st))
+        ck(lib.fnx_pbf_density_bwd(fr.gridY.data_ptr(), fr.Y.data_ptr(), N, fr.imass.data_ptr(), fr.kthY.data_ptr(), prm.H, prm.p0,
+                                   fr.gpn.data_ptr(), fr.dY.data_ptr(), 0, st))
+        # P1 forward straight into the fluid rows of the rasterizer's means3D (render units)
+        ck(lib.fnx_radius_count(fr.gridX.data_ptr(), N, prm.H, fr.visual.data_ptr(), V, prm.H, prm.KNN_K, None, fr.kthV.data_ptr(), st))
+        ck(lib.fnx_visual_advect_fwd(fr.gridX.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, fr.visual.data_ptr(), V,
+                                     fr.kthV.data_ptr(), prm.H, prm.secs, prm.scale_factor, fr.means3D.data_ptr(), fr.num.data_ptr(),
+                                     fr.den.data_ptr(), st))
+        # P5 on the render-unit positions
+        if prm.lambda_current_distance > 0:
+            thr = prm.distance_threshold_visual
+            ck(lib.fnx_grid_build(fr.means3D.data_ptr(), V, thr, fr.gridP.data_ptr(), st))
+            ck(lib.fnx_pair_distance_loss(fr.gridP.data_ptr(), fr.means3D.data_ptr(), V, thr, thr, prm.lambda_current_distance,
+                                          fr.scalars[3:].data_ptr(), fr.dDist.data_ptr(), st))
+        else:
+            fr.dDist.zero_()
+            fr.scalars[3:].zero_()
+        if not fr.vis_grid_built:  # the un-advected visual particles are constant within a frame
+            ck(lib.fnx_grid_build(fr.visual.data_ptr(), V, prm.H, fr.gridVis.data_ptr(), st))
+            fr.vis_grid_built = True
+
+    def render(self, fr: FrameState, view_ids):
+        vm, pm = self.view_all[view_ids].contiguous(), self.proj_all[view_ids].contiguous()
+        return R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, vm, pm,
+                                self.tan_fov_x, self.tan_fov_y, self.H, self.W, speculative=True)
+
+    def image_loss(self, images, gt, batch):
+        prm, lib = self.prm, self.lib
+        V, Cc, H, W = images.shape
+        key = (V, Cc, H, W)
+        if key not in self._loss_scratch:
+            self._loss_scratch[key] = (torch.empty(lib.fnx_image_loss_bytes(V, Cc, H, W), dtype=torch.uint8, device=self.dev),
+                                       torch.empty(V, device=self.dev), torch.empty(V, device=self.dev),
+                                       torch.empty((V, Cc, H, W), device=self.dev))
+        scratch, l1, ss, g = self._loss_scratch[key]
+        w_l1 = (1.0 - prm.lambda_dssim) * prm.lambda_image / batch
+        w_ss = prm.lambda_dssim * prm.lambda_image / batch
+        L.check(lib.fnx_image_loss(V, Cc, H, W, images.data_ptr(), gt.data_ptr(), int(prm.grey), w_l1, w_ss, g.data_ptr(),
+                                   l1.data_ptr(), ss.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
+        return l1, ss, g
+
+    def physics_backward_and_update(self, fr: FrameState, dL_dmeans3D, grad_extra=None, update=True):
+        """P1-backward (image + distance gradients -> hidden particles), P3 chain, P4, Adam."""
+        lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
+        N, V = fr.N, fr.V
+        ck = L.check
+        ck(lib.fnx_visual_advect_bwd(fr.gridVis.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, V, fr.kthV.data_ptr(), fr.num.data_ptr(),
+                                     fr.den.data_ptr(), dL_dmeans3D.data_ptr(), fr.dDist.data_ptr(), 1.0 / prm.scale_factor, prm.H,
+                                     prm.secs, fr.dX.data_ptr(), 1, st))
+        ck(lib.fnx_pbf_combine_grad(N, fr.e.data_ptr(), fr.buoyancy.data_ptr(), prm.secs, prm.buoyancy_max_y, prm.scale_factor,
+                                    fr.dX.data_ptr(), fr.dY.data_ptr(), fr.estimate_xyz.data_ptr(), prm.lambda_exyz, fr.de.data_ptr(),
+                                    fr.scalars[2:].data_ptr(), st))
+        if grad_extra is not None:
+            fr.de.add_(grad_extra)
+        if update:
+            self.adam(fr)
+
+    def adam(self, fr: FrameState, grad=None, grad_scale=1.0):
+        fr.adam_step += 1
+        g = fr.de if grad is None else grad
+        L.check(self.lib.fnx_adam_step(fr.e.numel(), fr.e.data_ptr(), g.data_ptr(), fr.m.data_ptr(), fr.v.data_ptr(), grad_scale,
+                                       self.prm.lr, 0.9, 0.999, self.prm.adam_eps, fr.adam_step,
+                                       torch.cuda.current_stream(self.dev).cuda_stream))
+
+    # -- the step -------------------------------------------------------------------------------------------
+    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None):
+        """One optimiser iteration for one frame.  view_ids: list of camera indices rendered by THIS process;
+        gt [len(view_ids),C,H,W] on the device; `batch` = global number of views of the step (defaults to
+        len(view_ids); larger when views are sharded over ranks).  Returns device tensors, no host sync."""
+        batch = len(view_ids) if batch is None else batch
+        with torch.cuda.device(self.dev):
+            self.physics_forward(fr)
+            out = {}
+            if len(view_ids):
+                ctx, images, radii, depth = self.render(fr, view_ids)
+                l1, ss, g = self.image_loss(images, gt, batch)
+                grads = R.raster_backward(ctx, g, want_means2D=False)
+                dmeans = grads["means3D"]
+                out.update(l1=l1, ssim=ss, images=images, radii=radii, num_rendered=ctx.num_rendered)
+            else:
+                dmeans = torch.zeros((fr.P, 3), device=self.dev)
+            self.physics_backward_and_update(fr, dmeans, update=update)
+            out.update(gas=fr.scalars[0], next_gas=fr.scalars[1], exyz=fr.scalars[2], dist=fr.scalars[3], grad=fr.de)
+        return out
+
+    def total_loss(self, out, batch=None):
+        """The reference's per-view `loss`, averaged over the views (device scalar)."""
+        prm = self.prm
+        b = out["l1"].numel() if batch is None else batch
+        img = ((1.0 - prm.lambda_dssim) * prm.lambda_image * out["l1"] + prm.lambda_dssim * prm.lambda_image * (1.0 - out["ssim"])).sum() / b
+        return (img + prm.lambda_current_distance * out["dist"] + prm.lambda_exyz * out["exyz"]
+                + prm.lambda_gas_constraints * out["gas"] + prm.lambda_next_gas_constraints * out["next_gas"])

@@ -184,16 +184,19 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
 int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H,
                         float p0, const float *dL_dpratio, float *dL_dX, int32_t accumulate, fnx_stream_t stream);
 
-/* P1 (gm_fluid.py:1291-1336): visual_out = visual + secs * sum_j w u_j / max(sum_j w, 1e-8), w = poly6(|visual-X_j|^2),
- * u_j = (X_j - xyz_j)/secs over radius(x=X, y=visual, H, K) edges.  grid_hidden is built on X (cell H); kthV from
- * fnx_radius_count(grid_hidden, visual).  num_out [V,3] / den_out [V] are saved for the backward.
- * bwd gathers per hidden particle over grid_visual (built on `visual`, cell H): dL_dX (+)= J^T dL_dvisual_out. */
+/* P1 (gm_fluid.py:1291-1336): A = visual + secs * sum_j w u_j / max(sum_j w, 1e-8), w = poly6(|visual-X_j|^2),
+ * u_j = (X_j - xyz_j)/secs over radius(x=X, y=visual, H, K) edges; visual_out = A / out_div (out_div = 1, or the
+ * scale factor 100 to get render units directly, FD/renderer/pipe_fluid.py:44-45).  grid_hidden is built on X
+ * (cell H); kthV from fnx_radius_count(grid_hidden, visual).  num_out [V,3] / den_out [V] are saved for the backward.
+ * bwd gathers per hidden particle over grid_visual (built on `visual`, cell H):
+ *   dL_dX (+)= J_A^T ( g_scale * (dL_dvisual_out + dL_dvisual_out2) ),  dL_dvisual_out2 may be NULL. */
 int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual,
-                          int32_t V, const int32_t *kthV, float H, float secs, float *visual_out, float *num_out,
-                          float *den_out, fnx_stream_t stream);
+                          int32_t V, const int32_t *kthV, float H, float secs, float out_div, float *visual_out,
+                          float *num_out, float *den_out, fnx_stream_t stream);
 int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *xyz, int32_t N, int32_t V,
-                          const int32_t *kthV, const float *num, const float *den, const float *dL_dvisual_out, float H,
-                          float secs, float *dL_dX, int32_t accumulate, fnx_stream_t stream);
+                          const int32_t *kthV, const float *num, const float *den, const float *dL_dvisual_out,
+                          const float *dL_dvisual_out2, float g_scale, float H, float secs, float *dL_dX,
+                          int32_t accumulate, fnx_stream_t stream);
 
 /* P5 distance_loss (loss_utils.py:98-121): *loss = sum_{i != j, d_ij < thr} (thr - d_ij)^2 (device scalar),
  * dL_dpts [n,3] = grad_scale * dloss/dpts (may be NULL).  grid built on pts with cell >= threshold. */
@@ -225,6 +228,18 @@ int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, fl
  * out [n_out] (0 for empty groups), arg [n_out] int64 (n for empty groups). */
 int fnx_scatter_min(int64_t n, const float *src, const int64_t *index, int32_t n_out, float *out, int64_t *arg,
                     fnx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused image loss  (replaces l1_loss + ssim of FD/utils/loss_utils.py:9-64, the grey conversion of
+ * FD/entries_fluid_nexus/train_physical_particle.py:356-360 and the weighting of
+ * FD/entries_scalar_real/train_physical_particle.py:346-347)
+ * ---------------------------------------------------------------------------------------------- */
+size_t fnx_image_loss_bytes(int32_t V, int32_t C, int32_t H, int32_t W);
+/* img, gt [V,C,H,W].  l1_mean[v] = mean|img-gt|, ssim_mean[v] = mean SSIM (window 11, sigma 1.5, zero padding).
+ * If grey != 0 both images are first replaced by their channel mean repeated C times (FluidNexus entries).
+ * dL_dimg [V,C,H,W] (may be NULL) = d/dimg of  sum_v ( w_l1 * l1_mean[v] + w_ssim * (1 - ssim_mean[v]) ). */
+int fnx_image_loss(int32_t V, int32_t C, int32_t H, int32_t W, const float *img, const float *gt, int32_t grey, float w_l1,
+                   float w_ssim, float *dL_dimg, float *l1_mean, float *ssim_mean, void *scratch, fnx_stream_t stream);
 
 /* Introspection for parity tests: device-to-device copies of the forward's intermediate state.  Any destination may
  * be NULL.  xy [V,P,2], depth [V,P], conic_opacity [V,P,4] (R3 GeometryState means2D/depths/conic_opacity,

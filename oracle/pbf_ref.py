@@ -173,7 +173,7 @@ def distance_loss(positions, threshold):
     d = positions.unsqueeze(1) - positions.unsqueeze(0)
     d2 = (d ** 2).sum(-1)
     eye = torch.eye(positions.shape[0], dtype=torch.bool)
-    dist = torch.sqrt(torch.where(eye, torch.ones_like(d2), d2))  # keep sqrt'(0) off the diagonal-free graph
+    dist = torch.sqrt(torch.where(d2 > 0, d2, torch.ones_like(d2)))  # keep sqrt'(0) = inf out of the graph
     mask = (dist < threshold) & ~eye & (d2 > 0)
     # exact duplicates (d == 0): value (thr-0)^2 with zero gradient, as cdist's backward gives
     dup = (~eye) & (d2 <= 0)
