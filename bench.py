@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- FluidDynamics physical-particle train-step throughput (render + image loss + physics + backward + Adam).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fnx|reference] [--workload smoke|scalar|c2]
+
+Metric (BASELINE.json): train-step iterations per second.  One *iteration* = one pass of the reference's hot loop for
+one frame with `views` (5) cameras (FD/entries_fluid_nexus/train_physical_particle.py:330-420).  One bench *step*
+processes `frames_in_flight` (8) independent synthetic frames, each one iteration; the frames are sharded over the
+ranks (strong scaling: total work per step is fixed), gradients of all frames live in one flat bucket that is
+all-reduced (NCCL, sum) once per step and applied with one fused Adam launch on every rank (replicated parameters).
+value = frames_in_flight * K / T, T = max over ranks of the CUDA-event time of the K timed steps.
+
+Workloads:  smoke  = BASELINE config 4: P = 200k (20k fluid + 180k frozen background), C = 3, grey
+image loss, N = 28k hidden particles, 5 views 512x512 (the configuration north_star's target is quoted on);
+scalar = config 3 (P = V = 150k fluid, C = 1);  c2 = config 2 sizes (50k, 400x400).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #          fluid    bg      C  grey   size  N_hidden  p0   bmax  thr
+    "smoke": (20_000, 180_000, 3, True, 512, 28_000, 1.5, 0.0, 0.002),
+    "scalar": (150_000, 0, 1, False, 512, 28_000, 2.0, 0.8, 0.00625),
+    "c2": (50_000, 0, 3, False, 400, 28_000, 1.5, 0.0, 0.002),
+    "tiny": (2_000, 4_000, 3, True, 128, 3_000, 1.5, 0.0, 0.004),
+}
+
+
+def build_frames(workload, n_frames, device, need_device=True):
+    """Seeded scene: cameras, shared frozen background, per-frame fluid / hidden particles (numpy, host)."""
+    from fluidnexus_b200 import synthetic as S
+    nf, nb, C, grey, size, N, p0, bmax, thr = WORKLOADS[workload]
+    cams = S.make_cameras(5, size, device=device if need_device else "cpu")
+    bg = S.background_gaussians(nb, C, seed=1) if nb else None
+    frames = []
+    for f in range(n_frames):
+        fluid = S.fluid_gaussians(nf, C, seed=100 + f)
+        hidden = S.hidden_lattice(N, seed=200 + f, buoyancy=(0.0, 1.96, 0.0) if bmax > 0 else (0.0, 0.0, 0.0))
+        frames.append(dict(fluid=fluid, hidden=hidden, visual=fluid.xyz * S.SCALE_FACTOR))
+    return cams, bg, frames, dict(C=C, grey=grey, size=size, N=N, p0=p0, bmax=bmax, thr=thr, nf=nf, nb=nb)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_info():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    return rank, world, int(os.environ.get("LOCAL_RANK", 0))
+
+
+# ======================================================================================================================
+# our arm
+# ======================================================================================================================
+def run_fnx(args):
+    import torch.distributed as dist
+    from fluidnexus_b200 import _lib as L
+    from fluidnexus_b200 import rasterizer as R
+    from fluidnexus_b200.step import FrameState, PhysicalStep, StepParams
+    rank, world, local = dist_info()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+    G, views = args.frames_in_flight, list(range(5))
+    cams, bg, frames, cfg = build_frames(args.workload, G, dev)
+    prm = StepParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], grey=cfg["grey"], distance_threshold_visual=cfg["thr"])
+    ps = PhysicalStep(cams, cfg["C"], prm, device=dev)
+    N = cfg["N"]
+    # replicated parameters / Adam state / gradient bucket of ALL frames, flat
+    E = torch.zeros((G, N, 3), device=dev); M = torch.zeros_like(E); Vv = torch.zeros_like(E); DE = torch.zeros_like(E)
+    mine = [f for f in range(G) if f % world == rank]
+    states = {}
+    for f in mine:
+        fr = FrameState(frames[f]["hidden"], frames[f]["visual"], frames[f]["fluid"], bg, device=dev, prm=prm)
+        E[f].copy_(fr.e)
+        fr.e, fr.m, fr.v, fr.de = E[f], M[f], Vv[f], DE[f]  # views into the flat, replicated buffers
+        states[f] = fr
+    if world > 1:
+        dist.all_reduce(E)  # every slot was written by exactly one rank, the others hold zeros
+    # ground truth: the same scene with fluid positions perturbed by N(0, 0.002), rendered once by the rasterizer
+    gts_dev, gts_pinned = {}, {}
+    for f in mine:
+        fr = states[f]
+        rng = np.random.default_rng(300 + f)
+        pert = fr.means3D.clone()
+        pert[:fr.V] += torch.tensor(rng.normal(0, 0.002, (fr.V, 3)), dtype=torch.float32, device=dev)
+        ctx, img, _, _ = R.raster_forward(cfg["C"], ps.bg, pert, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, ps.view_all,
+                                          ps.proj_all, ps.tan_fov_x, ps.tan_fov_y, ps.H, ps.W, speculative=False)
+        gts_dev[f] = img.clone()
+        gts_pinned[f] = img.cpu().pin_memory()
+        del ctx
+    torch.cuda.synchronize()
+    step_no = [0]
+
+    def one_step(e2e):
+        last = None
+        for f in mine:
+            fr = states[f]
+            if e2e:
+                gt = gts_pinned[f].to(dev, non_blocking=True)   # host -> device every iteration (reference :325)
+            else:
+                gt = gts_dev[f]
+            last = ps.step(fr, views, gt, update=False, batch=len(views))
+        if world > 1:
+            dist.all_reduce(DE)
+        step_no[0] += 1
+        L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
+                                  prm.adam_eps, step_no[0], torch.cuda.current_stream(dev).cuda_stream))
+        if e2e and last is not None:
+            return float(ps.total_loss(last).item())            # device -> host read of the step's loss
+        return last
+
+    def timed(k, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(k):
+            out = one_step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    # timed region: device-resident inputs, section events on the dominant kernels
+    nsec = lib.fnx_profile_sections()
+    names = [lib.fnx_profile_section_name(i).decode() for i in range(nsec)]
+    lib.fnx_profile_enable((1 << names.index("blend_bwd")) | (1 << names.index("blend_fwd")))
+    lib.fnx_profile_collect(None, None)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.fnx_launch_count()
+    ms, out = timed(args.steps, False)
+    launches = lib.fnx_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    import ctypes as C
+    tot = (C.c_float * nsec)(); cnt = (C.c_int32 * nsec)()
+    L.check(lib.fnx_profile_collect(tot, cnt))
+    lib.fnx_profile_enable(0)
+    R_per_iter = float(out["num_rendered"]) if out else 0.0
+    # end to end: pinned host ground truth uploaded every iteration + loss read back
+    for _ in range(2):
+        one_step(True)
+    ms_e2e, _ = timed(args.steps, True)
+    value = G * args.steps / (ms / 1e3)
+    e2e = G * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    Cc, HW, P = cfg["C"], cfg["size"] ** 2, cfg["nf"] + cfg["nb"]
+    ib = names.index("blend_bwd")
+    n_launch = max(1, cnt[ib])
+    t_launch = tot[ib] / 1e3 / n_launch                               # seconds per blend_bwd launch (5 views each)
+    # algorithmic bytes of ONE blend_bwd launch: records R*rec + per pixel dL/dpix, final_T, n_contrib + accumulator rows
+    rec = 48 if Cc == 3 else 32
+    acc = 48 if Cc == 3 else 32
+    bytes_launch = R_per_iter * rec + len(views) * HW * (4 * Cc + 8) + len(views) * P * acc
+    achieved = bytes_launch / t_launch / 1e9 if t_launch > 0 else 0.0
+    line = {
+        "metric": "FluidDynamics train-step iters/sec (render+physics+bwd)", "value": round(value, 3), "unit": "iters/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={Cc}, "
+                               f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration",
+                   "frames_in_flight": G, "views_per_iteration": 5, "parallelism": f"frames sharded over {world} rank(s), "
+                   "one NCCL all-reduce of the flat gradient bucket per step" if world > 1 else "single GPU",
+                   "instances_per_iteration": R_per_iter,
+                   "l2": f"working set per iteration ~{(R_per_iter * (rec + 16) + 5 * HW * 40) / 1e6:.0f} MB and {G} frames "
+                         "cycle between iterations: larger than the 126 MB L2, no explicit flush"},
+        "e2e": {"value": round(e2e, 3), "unit": "iters/s", "h2d_bytes_per_step": int(len(mine) * 5 * Cc * HW * 4),
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                     "ms_per_launch": round(t_launch * 1e3, 4), "launches_timed": int(n_launch),
+                     "share_of_step": round(tot[ib] / ms, 4),
+                     "note": "fp32 ALU / shuffle-issue bound blend loop on an L2-resident working set; see DESIGN.md"},
+        "sections_ms_per_step": {names[i]: round(tot[i] / args.steps, 4) for i in range(nsec) if cnt[i]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, cfg, frames[0], bg, cams)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, cfg, frame, bg, cams):
+    """The oracle (CPU port of the reference algorithm) on a bounded sample of the same workload, 1 host thread:
+    one of the five views rendered forward+backward by oracle/raster_ref.c and one physics forward+backward."""
+    from fluidnexus_b200 import synthetic as S
+    from oracle import pbf_ref as O
+    from oracle.raster_oracle import RasterOracle
+    torch.set_num_threads(1)
+    gs = frame["fluid"] if bg is None else S.cat_sets(frame["fluid"], bg)
+    cam = cams[2]
+    cam_cpu = S.make_cameras(5, cfg["size"])[2]
+    inp = S.raster_inputs(gs, cam_cpu, np.zeros(cfg["C"], np.float32))
+    o = RasterOracle("f32")
+    t0 = time.time()
+    out = o.forward(**inp)
+    o.backward(np.ones_like(out["color"]))
+    t_view = time.time() - t0
+    o.free()
+    prm = O.PBFParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], distance_threshold_visual=cfg["thr"])
+    hp = frame["hidden"]
+    f32 = lambda a: torch.as_tensor(a, dtype=torch.float32)
+    st = dict(xyz=f32(hp.xyz), estimate_xyz=f32(hp.estimate_xyz), buoyancy=f32(hp.buoyancy), force=f32(hp.force), imass=f32(hp.imass),
+              visual_xyz=f32(frame["visual"]))
+    e = (st["estimate_xyz"] / 100).clone().requires_grad_(True)
+    t0 = time.time()
+    total, *_ = O.physics_loss_terms(prm, e, st, with_distance=False)
+    total.backward()
+    t_phys = time.time() - t0
+    t_iter = 5 * t_view + 5 * t_phys  # the reference re-evaluates the physics terms for every view
+    return {"value": round(1.0 / t_iter, 5), "unit": "iters/s", "cores": 1, "kind": "port",
+            "sample": f"1 of 5 views fwd+bwd with oracle/raster_ref.c ({t_view:.2f} s) + 1 physics fwd+bwd with oracle/pbf_ref.py "
+                      f"({t_phys:.2f} s, distance_loss excluded: O(V^2)); iteration = 5*(view + physics)"}
+
+
+# ======================================================================================================================
+# reference arm
+# ======================================================================================================================
+def run_reference(args):
+    rank, world, local = dist_info()
+    if rank != 0:
+        return
+    from oracle import pbf_ref as O
+    from oracle import ref_ext
+    from oracle.ref_step import ReferenceTrainer
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    cams, bg, frames, cfg = build_frames(args.workload, 1, dev)
+    prm = O.PBFParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], distance_threshold_visual=cfg["thr"])
+    fr = frames[0]
+    tr = ReferenceTrainer(prm, fr["hidden"], fr["visual"], fr["fluid"], bg, cfg["C"], cfg["grey"], device=dev)
+    # ground truth through the reference rasterizer itself
+    gts = []
+    with torch.no_grad():
+        rng = np.random.default_rng(300)
+        pert = torch.tensor(fr["fluid"].xyz + rng.normal(0, 0.002, fr["fluid"].xyz.shape), dtype=torch.float32, device=dev)
+        for cam in cams:
+            gts.append(tr.render(cam, pert).detach().cpu())
+    with_dist = cfg["nf"] <= 20_000  # dense cdist is O(V^2): feasible up to ~20k particles only
+    K, W = args.steps, max(args.warmup, 1)
+    # a reference iteration costs seconds (host physics): bound the run
+    K = min(K, args.ref_max_steps)
+    for _ in range(min(W, 2)):
+        tr.iteration(cams, gts, with_distance=with_dist)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(K):
+        tr.iteration(cams, gts, with_distance=with_dist)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    value = K / dt
+    P = cfg["nf"] + cfg["nb"]
+    line = {
+        "impl": "reference", "metric": "FluidDynamics train-step iters/sec (render+physics+bwd)", "value": round(value, 4),
+        "unit": "iters/s", "n_gpus": 1, "steps": K, "warmup": min(W, 2), "ms_per_step": round(dt / K * 1e3, 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={cfg['C']}, "
+                               f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration",
+                   "frames_in_flight": 1, "views_per_iteration": 5,
+                   "what": "unmodified reference CUDA rasterizer (oracle/_ref) on 1 GPU + torch image losses on the GPU + "
+                           "physics terms P1-P4 restated in torch on the host cores (torch_cluster not installable); "
+                           f"dense-cdist distance_loss {'on' if with_dist else 'OFF (O(V^2))'}"},
+        "cpu_baseline": {"value": round(value, 4), "unit": "iters/s", "cores": ncores, "kind": "reference",
+                         "sample": f"{K} full iterations (5 views each) of one frame"},
+        "e2e": {"value": round(value, 4), "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fnx", choices=["fnx", "reference"])
+    ap.add_argument("--workload", default="smoke", choices=list(WORKLOADS))
+    ap.add_argument("--frames-in-flight", type=int, default=8)
+    ap.add_argument("--ref-max-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_fnx(args)
+
+
+if __name__ == "__main__":
+    main()

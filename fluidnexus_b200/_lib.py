@@ -56,6 +56,7 @@ SYMBOLS = {
     "fnx_abi_version": (_I, []),
     "fnx_last_error": (C.c_char_p, []),
     "fnx_build_arch": (C.c_char_p, []),
+    "fnx_launch_count": (C.c_uint64, []),
     "fnx_raster_geom_bytes": (_SZ, [_I, _I]),
     "fnx_raster_image_bytes": (_SZ, [_I, _I, _I]),
     "fnx_raster_binning_bytes": (_SZ, [_I64, _I]),
@@ -80,6 +81,10 @@ SYMBOLS = {
     "fnx_scatter_min": (_I, [_I64, _V, _V, _I, _V, _V, _V]),
     "fnx_image_loss_bytes": (_SZ, [_I, _I, _I, _I]),
     "fnx_image_loss": (_I, [_I, _I, _I, _I, _V, _V, _I, _F, _F, _V, _V, _V, _V, _V]),
+    "fnx_profile_sections": (_I, []),
+    "fnx_profile_section_name": (C.c_char_p, [_I]),
+    "fnx_profile_enable": (_I, [C.c_uint32]),
+    "fnx_profile_collect": (_I, [_V, _V]),
     "fnx_raster_read_geom": (_I, [C.POINTER(RasterScratch), _I, _I, _V, _V, _V, _V, _V]),
     "fnx_raster_read_image": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _V, _V, _V]),
 }

@@ -25,8 +25,11 @@ void set_error(const char *fmt, ...);
         }                                                                                           \
     } while (0)
 
+extern unsigned long long g_launches;  // hand-written kernels launched by this process (fnx_launch_count)
+
 #define FNX_LAUNCH_CHECK(name)                                                                      \
     do {                                                                                            \
+        fnx::g_launches++;                                                                          \
         cudaError_t _e = cudaGetLastError();                                                        \
         if (_e != cudaSuccess) {                                                                    \
             fnx::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -107,4 +110,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 #endif
 
+}  // namespace fnx
+
+// ---------------------------------------------------------------------------------------------------------------
+// optional per-section CUDA-event timing (fnx_profile_*): lets bench.py measure a kernel's launch duration live,
+// on the launching stream, inside its timed region
+// ---------------------------------------------------------------------------------------------------------------
+namespace fnx {
+enum Section { SEC_PREPROCESS = 0, SEC_DEPTH_SORT, SEC_EMIT, SEC_TILE_SORT, SEC_PACK, SEC_BLEND_FWD, SEC_BLEND_BWD, SEC_GEOM_BWD,
+               SEC_IMAGE_LOSS, SEC_PHYSICS, SEC_COUNT };
+void prof_begin(int section, cudaStream_t st);
+void prof_end(int section, cudaStream_t st);
+struct ProfScope {
+    int s; cudaStream_t st;
+    ProfScope(int section, cudaStream_t stream) : s(section), st(stream) { prof_begin(s, st); }
+    ~ProfScope() { prof_end(s, st); }
+};
 }  // namespace fnx

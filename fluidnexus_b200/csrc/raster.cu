@@ -985,17 +985,25 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
     if (sort_items > 0) {
         const bool padded = (a->flags & FNX_NO_HOST_SYNC) != 0 || a->instance_capacity_hint > 0;
         if (padded) FNX_CUDA_TRY(cudaMemsetAsync(b.tkeys_in, 0xFF, sizeof(uint32_t) * (size_t)sort_items, st));
+        prof_begin(SEC_EMIT, st);
         emit_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, P, gx, gy, exact_rect, radii, g, b);
+        prof_end(SEC_EMIT, st);
         FNX_LAUNCH_CHECK("emit_kernel");
         const int end_bit = ceil_log2_u64((uint64_t)ntiles * V + 1);
         size_t tb = b.cub_temp_bytes;
+        prof_begin(SEC_TILE_SORT, st);
         FNX_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, b.tkeys_in, b.tkeys_out, b.tvals_in, b.tvals_out,
                                                      (int)sort_items, 0, end_bit, st));
+        prof_end(SEC_TILE_SORT, st);
+        prof_begin(SEC_PACK, st);
         pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, a->colors, g, b, im.ranges);
+        prof_end(SEC_PACK, st);
         FNX_LAUNCH_CHECK("pack_kernel");
     }
     dim3 grid(ntiles, V);
+    prof_begin(SEC_BLEND_FWD, st);
     blend_fwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(a->W, a->H, gx, gy, b.records, g.depth, a->bg, g.hdr, im, out_color, out_depth);
+    prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
     return FNX_OK;
 }
@@ -1036,17 +1044,21 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
     ImageView im = image_view(scratch->image, W, H, V);
 
     dim3 pgrid((P + 255) / 256, V);
+    prof_begin(SEC_PREPROCESS, st);
     preprocess_kernel<<<pgrid, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
                                              (const float4 *)a->rotations, a->opacities, a->cov3D_precomp, a->view_matrix,
                                              a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y, gx, gy,
                                              exact_rect, radii, g);
+    prof_end(SEC_PREPROCESS, st);
     FNX_LAUNCH_CHECK("preprocess_kernel");
+    prof_begin(SEC_DEPTH_SORT, st);
     size_t tb = g.cub_temp_bytes;
     const int dbits = 32 + ceil_log2_u64((uint64_t)V);
     FNX_CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.dkeys_in, g.dkeys_out, g.dvals_in, g.dvals_out, n, 0, dbits, st));
     DepthScanIter it(cub::CountingInputIterator<uint32_t>(0), DepthScanIn{g.tiles_touched, g.dvals_out});
     tb = g.cub_temp_bytes;
     FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, it, g.offsets, n, st));
+    prof_end(SEC_DEPTH_SORT, st);
 
     const int slot_id = g_slots.next;
     g_slots.next = (g_slots.next + 1) % PinnedSlots::N;
@@ -1120,12 +1132,16 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     BinView b = bin_view(scratch->binning, cap, C);
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
     dim3 grid(ntiles, V);
+    prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(W, H, gx, gy, b.records, a->bg, g.hdr, im, dL_dout_color, g.accum);
+    prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
+    prof_begin(SEC_GEOM_BWD, st);
     geom_bwd_kernel<C><<<(P + 255) / 256, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
                                                         (const float4 *)a->rotations, a->cov3D_precomp, a->view_matrix,
                                                         a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y,
                                                         radii, g.cov3D, g.accum, *gr);
+    prof_end(SEC_GEOM_BWD, st);
     FNX_LAUNCH_CHECK("geom_bwd_kernel");
     return FNX_OK;
 }

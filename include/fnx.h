@@ -49,6 +49,8 @@ int fnx_abi_version(void);
 const char *fnx_last_error(void);
 /* Compiled-for architecture string, e.g. "sm_100a". */
 const char *fnx_build_arch(void);
+/* Number of libfnx's own kernels launched so far by this process (library calls such as CUB sorts not counted). */
+unsigned long long fnx_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Rasterizer  (replaces R3|R1 `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward`,
@@ -240,6 +242,15 @@ size_t fnx_image_loss_bytes(int32_t V, int32_t C, int32_t H, int32_t W);
  * dL_dimg [V,C,H,W] (may be NULL) = d/dimg of  sum_v ( w_l1 * l1_mean[v] + w_ssim * (1 - ssim_mean[v]) ). */
 int fnx_image_loss(int32_t V, int32_t C, int32_t H, int32_t W, const float *img, const float *gt, int32_t grey, float w_l1,
                    float w_ssim, float *dL_dimg, float *l1_mean, float *ssim_mean, void *scratch, fnx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section profiler (measurement only): CUDA events recorded around the library's own kernel launches on the
+ * launching stream.  Sections: fnx_profile_section_name(0..fnx_profile_sections()-1).
+ * ---------------------------------------------------------------------------------------------- */
+int fnx_profile_sections(void);
+const char *fnx_profile_section_name(int32_t section);
+int fnx_profile_enable(uint32_t section_mask);            /* 0 disables */
+int fnx_profile_collect(float *total_ms, int32_t *launches); /* arrays of fnx_profile_sections() entries; blocks */
 
 /* Introspection for parity tests: device-to-device copies of the forward's intermediate state.  Any destination may
  * be NULL.  xy [V,P,2], depth [V,P], conic_opacity [V,P,4] (R3 GeometryState means2D/depths/conic_opacity,

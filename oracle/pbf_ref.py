@@ -44,26 +44,32 @@ def radius(x, y, r, max_num_neighbors=32):
     xn = x.detach().cpu().numpy().astype(np.float32)
     yn = y.detach().cpu().numpy().astype(np.float32)
     r2 = np.float32(r) * np.float32(r)
-    rows, cols = [], []
-    if xn.shape[0] * yn.shape[0] <= 4_000_000:
+    if xn.shape[0] == 0 or yn.shape[0] == 0:
+        return torch.zeros((2, 0), dtype=torch.long)
+    if xn.shape[0] * yn.shape[0] <= 250_000:  # literal scan, the form of torch-cluster's CUDA kernel
+        rows, cols = [], []
         for c in range(yn.shape[0]):
             d = ((xn - yn[c]) ** 2).sum(1, dtype=np.float32)
             hit = np.nonzero(d < r2)[0][:max_num_neighbors]
             rows.append(np.full(hit.shape, c, np.int64))
             cols.append(hit.astype(np.int64))
-    else:
-        from scipy.spatial import cKDTree
-        tree = cKDTree(xn.astype(np.float64))
-        cand = tree.query_ball_point(yn.astype(np.float64), float(r) * (1 + 1e-5) + 1e-6, return_sorted=True)
-        for c, js in enumerate(cand):
-            js = np.asarray(js, np.int64)
-            d = ((xn[js] - yn[c]) ** 2).sum(1, dtype=np.float32)
-            hit = js[d < r2][:max_num_neighbors]
-            rows.append(np.full(hit.shape, c, np.int64))
-            cols.append(hit)
-    row = np.concatenate(rows) if rows else np.zeros(0, np.int64)
-    col = np.concatenate(cols) if cols else np.zeros(0, np.int64)
-    return torch.from_numpy(np.stack([row, col]))
+        return torch.from_numpy(np.stack([np.concatenate(rows), np.concatenate(cols)]))
+    # same result through a k-d tree candidate search (vectorised): candidates within r(1+eps), exact fp32 test after
+    from scipy.spatial import cKDTree
+    tx, ty = cKDTree(xn.astype(np.float64)), cKDTree(yn.astype(np.float64))
+    pairs = ty.sparse_distance_matrix(tx, float(r) * (1 + 1e-5) + 1e-6, output_type="ndarray")
+    q, j = pairs["i"].astype(np.int64), pairs["j"].astype(np.int64)
+    d = ((xn[j] - yn[q]) ** 2).sum(1, dtype=np.float32)
+    keep = d < r2
+    q, j = q[keep], j[keep]
+    order = np.lexsort((j, q))
+    q, j = q[order], j[order]
+    if q.size:
+        start = np.r_[0, np.nonzero(np.diff(q))[0] + 1]
+        rank = np.arange(q.size) - np.repeat(start, np.diff(np.r_[start, q.size]))
+        keep = rank < max_num_neighbors
+        q, j = q[keep], j[keep]
+    return torch.from_numpy(np.stack([q, j]))
 
 
 def radius_graph(x, r, loop=False, max_num_neighbors=32):
