@@ -190,6 +190,7 @@ int fnx_image_loss(int32_t V, int32_t C, int32_t H, int32_t W, const float *img,
     FNX_CUDA_TRY(cudaMemsetAsync(l1_mean, 0, sizeof(float) * V, st));
     FNX_CUDA_TRY(cudaMemsetAsync(ssim_mean, 0, sizeof(float) * V, st));
     dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, V * Ce), block(LT, LT);
+    prof_begin(SEC_IMAGE_LOSS, st);
     ssim_fwd_kernel<<<grid, block, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, maps, l1_mean, ssim_mean);
     FNX_LAUNCH_CHECK("ssim_fwd_kernel");
     if (dL_dimg) {
@@ -197,6 +198,7 @@ int fnx_image_loss(int32_t V, int32_t C, int32_t H, int32_t W, const float *img,
         FNX_LAUNCH_CHECK("ssim_bwd_kernel");
     }
     scale_means_kernel<<<1, 32, 0, st>>>(V, 1.0f / ((float)Ce * (float)H * (float)W), l1_mean, ssim_mean);
+    prof_end(SEC_IMAGE_LOSS, st);
     FNX_LAUNCH_CHECK("scale_means_kernel");
     return FNX_OK;
 }

@@ -50,8 +50,18 @@ static GridView grid_view(void *chunk, int n) {
     g.bucket_fill = carve<uint32_t>(p, (size_t)g.M);
     g.sorted_idx = carve<uint32_t>(p, (size_t)(n > 0 ? n : 1));
     g.sorted_pos = carve<float4>(p, (size_t)(n > 0 ? n : 1));
+    // memoised CUB size query (its dispatch layer is slow); a handful of distinct table sizes per process
+    static thread_local int cached_M[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static thread_local size_t cached[8];
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, g.M + 1);
+    bool hit = false;
+    for (int k = 0; k < 8; k++)
+        if (cached_M[k] == g.M) { tb = cached[k]; hit = true; break; }
+    if (!hit) {
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, g.M + 1);
+        static thread_local int next = 0;
+        cached_M[next] = g.M; cached[next] = tb; next = (next + 1) & 7;
+    }
     g.cub_temp_bytes = tb;
     g.cub_temp = carve<char>(p, tb);
     return g;
@@ -527,12 +537,14 @@ extern "C" {
 size_t fnx_grid_bytes(int32_t n) { return grid_bytes(n); }
 
 int fnx_grid_build(const float *pts, int32_t n, float cell, void *grid, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(n >= 0 && cell > 0.f && grid && (pts || n == 0), "bad arguments");
     return grid_build(pts, n, cell, grid, (cudaStream_t)stream);
 }
 
 int fnx_radius_count(const void *grid_x, int32_t nx, float cell, const float *y, int32_t ny, float r, int32_t max_num_neighbors,
                      int32_t *counts, int32_t *kth, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid_x && nx >= 0 && ny >= 0 && r > 0.f && r <= cell * 1.000001f && max_num_neighbors > 0, "bad arguments (need r <= cell)");
     if (ny == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_x, nx);
@@ -543,6 +555,7 @@ int fnx_radius_count(const void *grid_x, int32_t nx, float cell, const float *y,
 
 int fnx_radius_fill(const void *grid_x, int32_t nx, float cell, const float *y, int32_t ny, float r, const int32_t *kth,
                     const int64_t *offsets, int64_t *edge_query, int64_t *edge_x, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid_x && kth && offsets && edge_query && edge_x && r <= cell * 1.000001f, "bad arguments");
     if (ny == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_x, nx);
@@ -554,6 +567,7 @@ int fnx_radius_fill(const void *grid_x, int32_t nx, float cell, const float *y, 
 
 int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H, float p0,
                         float *p_ratio, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid && X && imass && kth && p_ratio && N >= 0 && H > 0.f && p0 > 0.f, "bad arguments");
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, N);
@@ -565,6 +579,7 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
 
 int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H, float p0,
                         const float *dL_dpratio, float *dL_dX, int32_t accumulate, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid && X && imass && kth && dL_dpratio && dL_dX && N >= 0, "bad arguments");
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, N);
@@ -577,6 +592,7 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
 int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual, int32_t V,
                           const int32_t *kthV, float H, float secs, float out_div, float *visual_out, float *num_out,
                           float *den_out, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid_hidden && X && xyz && kthV && visual_out && (visual || V == 0) && out_div != 0.f, "bad arguments");
     if (V == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_hidden, N);
@@ -590,6 +606,7 @@ int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *
 int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *xyz, int32_t N, int32_t V, const int32_t *kthV,
                           const float *num, const float *den, const float *dL_dvisual_out, const float *dL_dvisual_out2,
                           float g_scale, float H, float secs, float *dL_dX, int32_t accumulate, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid_visual && X && xyz && kthV && num && den && dL_dvisual_out && dL_dX, "bad arguments");
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_visual, V);
@@ -602,6 +619,7 @@ int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *
 
 int fnx_pair_distance_loss(const void *grid, const float *pts, int32_t n, float cell, float threshold, float grad_scale, float *loss,
                            float *dL_dpts, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid && loss && (pts || n == 0) && threshold > 0.f && threshold <= cell * 1.000001f, "bad arguments (need threshold <= cell)");
     FNX_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
     if (n == 0) return FNX_OK;
@@ -612,6 +630,7 @@ int fnx_pair_distance_loss(const void *grid, const float *pts, int32_t n, float 
 }
 
 int fnx_knn3_mean_dist2(const void *grid, const float *pts, int32_t n, float cell, float *mean_dist2, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(grid && mean_dist2 && (pts || n == 0) && cell > 0.f, "bad arguments");
     if (n == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, n);
@@ -622,6 +641,7 @@ int fnx_knn3_mean_dist2(const void *grid, const float *pts, int32_t n, float cel
 
 int fnx_pbf_next_tick_fwd(int32_t N, const float *e, const float *xyz, const float *buoyancy, const float *force, float secs,
                           float buoyancy_max_y, float scale_factor, float *X, float *Y, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(N >= 0 && e && xyz && buoyancy && force && (X || Y), "bad arguments");
     if (N == 0) return FNX_OK;
     next_tick_fwd_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, e, xyz, buoyancy, force, secs, buoyancy_max_y, scale_factor, X, Y);
@@ -632,6 +652,7 @@ int fnx_pbf_next_tick_fwd(int32_t N, const float *e, const float *xyz, const flo
 int fnx_pbf_combine_grad(int32_t N, const float *e, const float *buoyancy, float secs, float buoyancy_max_y, float scale_factor,
                          const float *dL_dX, const float *dL_dY, const float *estimate_xyz, float lambda_exyz, float *dL_de,
                          float *exyz_loss, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(N >= 0 && e && buoyancy && dL_de, "bad arguments");
     if (exyz_loss) FNX_CUDA_TRY(cudaMemsetAsync(exyz_loss, 0, sizeof(float), (cudaStream_t)stream));
     if (N == 0) return FNX_OK;
@@ -642,6 +663,7 @@ int fnx_pbf_combine_grad(int32_t N, const float *e, const float *buoyancy, float
 }
 
 int fnx_pbf_ratio_loss(int32_t N, const float *p_ratio, float weight, float *loss, float *dL_dpratio, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(N >= 0 && p_ratio && loss && dL_dpratio, "bad arguments");
     FNX_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
     if (N == 0) return FNX_OK;
@@ -652,6 +674,7 @@ int fnx_pbf_ratio_loss(int32_t N, const float *p_ratio, float weight, float *los
 
 int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale, float lr,
                   float beta1, float beta2, float eps, int32_t step, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(n >= 0 && param && grad && exp_avg && exp_avg_sq && step >= 1, "bad arguments");
     if (n == 0) return FNX_OK;
     const float bc1 = (float)(1.0 - pow((double)beta1, step));
@@ -663,6 +686,7 @@ int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, fl
 }
 
 int fnx_scatter_min(int64_t n, const float *src, const int64_t *index, int32_t n_out, float *out, int64_t *arg, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(n >= 0 && n_out >= 0 && out && arg && ((src && index) || n == 0), "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_out == 0) return FNX_OK;

@@ -33,13 +33,19 @@ struct DepthScanIn {  // reads tiles_touched in depth-sorted order
 };
 using DepthScanIter = cub::TransformInputIterator<uint32_t, DepthScanIn, cub::CountingInputIterator<uint32_t>>;
 
+// CUB's size queries walk its dispatch layer (device attribute / occupancy calls): memoise per problem size
 static size_t geom_cub_bytes(int n) {
+    static thread_local int cached_n = -1;
+    static thread_local size_t cached = 0;
+    if (n == cached_n) return cached;
     size_t a = 0, b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 64);
     DepthScanIter it(cub::CountingInputIterator<uint32_t>(0), DepthScanIn{nullptr, nullptr});
     cub::DeviceScan::ExclusiveSum(nullptr, b, it, (uint32_t *)nullptr, n);
-    return a > b ? a : b;
+    cached_n = n;
+    cached = a > b ? a : b;
+    return cached;
 }
 
 GeomView geom_view(void *chunk, int P, int V) {
@@ -85,9 +91,17 @@ size_t image_bytes(int W, int H, int V) {
 }
 
 static size_t bin_cub_bytes(long long cap) {
+    static thread_local long long cached_cap[4] = {-1, -1, -1, -1};
+    static thread_local size_t cached[4] = {0, 0, 0, 0};
+    static thread_local int next = 0;
+    for (int k = 0; k < 4; k++)
+        if (cached_cap[k] == cap) return cached[k];
     size_t a = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (uint32_t *)nullptr, (int)cap, 0, 32);
+    cached_cap[next] = cap;
+    cached[next] = a;
+    next = (next + 1) & 3;
     return a;
 }
 BinView bin_view(void *chunk, long long cap, int C) {
