@@ -25,6 +25,7 @@ class RasterArgs(C.Structure):
         ("view_matrix", C.c_void_p), ("proj_matrix", C.c_void_p), ("bg", C.c_void_p),
         ("tan_fov_x", C.c_float), ("tan_fov_y", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("flags", C.c_uint32), ("instance_capacity_hint", C.c_int64),
+        ("num_rendered_pinned", C.c_void_p),
     ]
 
 
@@ -78,6 +79,7 @@ SYMBOLS = {
     "fnx_pbf_combine_grad": (_I, [_I, _V, _V, _F, _F, _F, _V, _V, _V, _F, _V, _V, _V]),
     "fnx_pbf_ratio_loss": (_I, [_I, _V, _F, _V, _V, _V]),
     "fnx_adam_step": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _I, _V]),
+    "fnx_adam_step_dev": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _V, _V, _V]),
     "fnx_scatter_min": (_I, [_I64, _V, _V, _I, _V, _V, _V]),
     "fnx_image_loss_bytes": (_SZ, [_I, _I, _I, _I]),
     "fnx_image_loss": (_I, [_I, _I, _I, _I, _V, _V, _I, _F, _F, _V, _V, _V, _V, _V]),

@@ -30,6 +30,7 @@ struct GridView {
     uint32_t *bucket_start;  // [M+1]
     uint32_t *bucket_fill;   // [M]
     uint32_t *sorted_idx;    // [n]
+    uint32_t *tmp_idx;       // [n] bucket contents in atomic arrival order (before the per-bucket index sort)
     float4 *sorted_pos;      // [n] xyz + idx bits
     void *cub_temp;
     size_t cub_temp_bytes;
@@ -49,6 +50,7 @@ static GridView grid_view(void *chunk, int n) {
     g.bucket_start = carve<uint32_t>(p, (size_t)g.M + 1);
     g.bucket_fill = carve<uint32_t>(p, (size_t)g.M);
     g.sorted_idx = carve<uint32_t>(p, (size_t)(n > 0 ? n : 1));
+    g.tmp_idx = carve<uint32_t>(p, (size_t)(n > 0 ? n : 1));
     g.sorted_pos = carve<float4>(p, (size_t)(n > 0 ? n : 1));
     // memoised CUB size query (its dispatch layer is slow); a handful of distinct table sizes per process
     static thread_local int cached_M[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -91,26 +93,21 @@ __global__ void grid_scatter_kernel(const float *__restrict__ pts, int n, float 
     const uint32_t b = hash_cell(cell_of(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], inv_cell), M);
     sorted_idx[start[b] + atomicAdd(&fill[b], 1u)] = (uint32_t)i;
 }
-// order every bucket by point index (buckets are tiny) so results do not depend on atomic arrival order, then
-// write the position copy the gathers read
-__global__ void grid_finalize_kernel(const float *__restrict__ pts, int M, const uint32_t *__restrict__ start,
-                                     uint32_t *__restrict__ sorted_idx, float4 *__restrict__ sorted_pos) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= M) return;
+// order every bucket by point index so that results do not depend on atomic arrival order: each entry finds its
+// rank inside its bucket (buckets are tiny) and writes itself + the position copy the gathers read
+__global__ void grid_finalize_kernel(const float *__restrict__ pts, int n, float inv_cell, int M, const uint32_t *__restrict__ start,
+                                     const uint32_t *__restrict__ tmp_idx, uint32_t *__restrict__ sorted_idx,
+                                     float4 *__restrict__ sorted_pos) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint32_t i = tmp_idx[a];
+    const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const uint32_t b = hash_cell(cell_of(x, y, z, inv_cell), M);
     const uint32_t s = start[b], e = start[b + 1];
-    for (uint32_t a = s + 1; a < e; a++) {
-        const uint32_t key = sorted_idx[a];
-        uint32_t k = a;
-        while (k > s && sorted_idx[k - 1] > key) {
-            sorted_idx[k] = sorted_idx[k - 1];
-            k--;
-        }
-        sorted_idx[k] = key;
-    }
-    for (uint32_t a = s; a < e; a++) {
-        const uint32_t i = sorted_idx[a];
-        sorted_pos[a] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __uint_as_float(i));
-    }
+    uint32_t rank = 0;
+    for (uint32_t k = s; k < e; k++) rank += tmp_idx[k] < i ? 1u : 0u;
+    sorted_idx[s + rank] = i;
+    sorted_pos[s + rank] = make_float4(x, y, z, __uint_as_float(i));
 }
 __global__ void grid_header_kernel(GridHeader *h, int n, int M, float cell, uint32_t *bucket_start) {
     h->n = n; h->M = M; h->cell = cell; h->inv_cell = 1.0f / cell;
@@ -130,9 +127,9 @@ static int grid_build(const float *pts, int n, float cell, void *scratch, cudaSt
     FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, g.bucket_fill, g.bucket_start, g.M, st));
     FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
     if (n > 0) {
-        grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_start, g.bucket_fill, g.sorted_idx);
+        grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_start, g.bucket_fill, g.tmp_idx);
         FNX_LAUNCH_CHECK("grid_scatter_kernel");
-        grid_finalize_kernel<<<(g.M + 255) / 256, 256, 0, st>>>(pts, g.M, g.bucket_start, g.sorted_idx, g.sorted_pos);
+        grid_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_start, g.tmp_idx, g.sorted_idx, g.sorted_pos);
         FNX_LAUNCH_CHECK("grid_finalize_kernel");
     }
     return FNX_OK;
@@ -162,32 +159,58 @@ __device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_c
             }
 }
 
+// Warp-cooperative variant: the 32 lanes of a warp share ONE query; lane l < 27 walks neighbour cell l.  Callers reduce
+// their per-lane partials with warp_sum().  (28k queries x 27 cells x ~10 points is latency bound with one thread per
+// query; a warp per query gives the memory system 27 independent bucket walks per query.)
+template <typename F>
+__device__ __forceinline__ void warp_for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, int lane, F f) {
+    if (lane >= 27) return;
+    const int3 c = cell_of(q.x, q.y, q.z, inv_cell);
+    const int3 cc = make_int3(c.x + (lane % 3) - 1, c.y + ((lane / 3) % 3) - 1, c.z + (lane / 9) - 1);
+    const uint32_t b = hash_cell(cc, g.M);
+    const uint32_t s = g.bucket_start[b], e = g.bucket_start[b + 1];
+    for (uint32_t a = s; a < e; a++) {
+        const float4 p = g.sorted_pos[a];
+        const int3 pc = cell_of(p.x, p.y, p.z, inv_cell);
+        if (pc.x != cc.x || pc.y != cc.y || pc.z != cc.z) continue;
+        const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        if (d2 < r2) f((int)__float_as_uint(p.w), p, d2);
+    }
+}
+constexpr int QPB = 4;  // queries (warps) per 128-thread block
+
 // ---------------------------------------------------------------------------------------------------------------
 // neighbour counts + the index cut-off that realises torch_cluster's max_num_neighbors rule
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 radius_count_kernel(GridView g, float inv_cell, const float *__restrict__ y, int ny, float r2, int K, int n_x,
                     int *__restrict__ counts, int *__restrict__ kth) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (c >= ny) return;
     const float3 q = make_float3(y[3 * c], y[3 * c + 1], y[3 * c + 2]);
     int cnt = 0;
-    for_each_neighbor(g, inv_cell, q, r2, [&](int, const float4 &, float) { cnt++; });
+    warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int, const float4 &, float) { cnt++; });
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     int cut = 0x7fffffff;
     if (cnt > K) {
-        // K-th smallest neighbour index by bisection on the index value
+        // K-th smallest neighbour index by bisection on the index value (rare path)
         int lo = 0, hi = n_x - 1;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             int below = 0;
-            for_each_neighbor(g, inv_cell, q, r2, [&](int j, const float4 &, float) { below += (j <= mid); });
+            warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float) { below += (j <= mid); });
+            below = __reduce_add_sync(0xffffffffu, below);
             if (below >= K) hi = mid; else lo = mid + 1;
         }
         cut = lo;
         cnt = K;
     }
-    if (counts) counts[c] = cnt;
-    if (kth) kth[c] = cut;
+    if (lane == 0) {
+        if (counts) counts[c] = cnt;
+        if (kth) kth[c] = cut;
+    }
 }
 
 // fills a torch_cluster-style edge list: for query c the (<= K) neighbours in ascending index order
@@ -236,14 +259,16 @@ __device__ __forceinline__ float dpoly6_dd2(float d2, float H2, float term1) {
 __global__ void __launch_bounds__(128)
 density_fwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
-    for_each_neighbor(g, inv_cell, q, H2, [&](int c, const float4 &, float d2) {
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2) {
         if (r <= kth[c]) pi += poly6(d2, H2, term1);
     });
-    p_ratio[r] = pi / imass[r] / p0;
+    pi = warp_sum(pi);
+    if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
 }
 
 // dL/dX_k = sum_{j in N(k)} dpoly6(d2) * 2 (X_k - X_j) * ( gp_k [k <= kth[j]] + gp_j [j <= kth[k]] ),
@@ -252,23 +277,24 @@ __global__ void __launch_bounds__(128)
 density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, const float *__restrict__ dL_dpratio,
                    float *__restrict__ dL_dX, int accumulate) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (k >= N) return;
     const float3 q = make_float3(X[3 * k], X[3 * k + 1], X[3 * k + 2]);
     const float gpk = dL_dpratio[k] / imass[k] / p0;
     const int kth_k = kth[k];
     float3 acc = make_float3(0.f, 0.f, 0.f);
-    for_each_neighbor(g, inv_cell, q, H2, [&](int j, const float4 &pj, float d2) {
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2) {
         float w = 0.f;
         if (k <= kth[j]) w += gpk;
         if (j <= kth_k) w += dL_dpratio[j] / imass[j] / p0;
         const float s = 2.f * dpoly6_dd2(d2, H2, term1) * w;
         acc.x += s * (q.x - pj.x); acc.y += s * (q.y - pj.y); acc.z += s * (q.z - pj.z);
     });
-    if (accumulate) {
-        dL_dX[3 * k] += acc.x; dL_dX[3 * k + 1] += acc.y; dL_dX[3 * k + 2] += acc.z;
-    } else {
-        dL_dX[3 * k] = acc.x; dL_dX[3 * k + 1] = acc.y; dL_dX[3 * k + 2] = acc.z;
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z);
+    if (lane < 3) {
+        const float v = lane == 0 ? acc.x : (lane == 1 ? acc.y : acc.z);
+        if (accumulate) dL_dX[3 * k + lane] += v; else dL_dX[3 * k + lane] = v;
     }
 }
 
@@ -280,13 +306,14 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
                   const float *__restrict__ vis, int V, const int *__restrict__ kthV, float H2, float term1, float secs,
                   float eps, float out_div, float *__restrict__ vis_out, float *__restrict__ num_out,
                   float *__restrict__ den_out) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (v >= V) return;
     const float3 q = make_float3(vis[3 * v], vis[3 * v + 1], vis[3 * v + 2]);
     const int cut = kthV[v];
     float3 num = make_float3(0.f, 0.f, 0.f);
     float den = 0.f;
-    for_each_neighbor(gh, inv_cell, q, H2, [&](int j, const float4 &pj, float d2) {
+    warp_for_each_neighbor(gh, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2) {
         if (j > cut) return;
         const float w = poly6(d2, H2, term1);
         num.x += w * ((pj.x - xyz[3 * j]) / secs);
@@ -294,6 +321,8 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
         num.z += w * ((pj.z - xyz[3 * j + 2]) / secs);
         den += w;
     });
+    num.x = warp_sum(num.x); num.y = warp_sum(num.y); num.z = warp_sum(num.z); den = warp_sum(den);
+    if (lane != 0) return;
     const float dc = fmaxf(den, eps);
     // out_div = scale_factor when the caller wants render units (pipe_fluid.py:45: raw_render_xyz / gm.scale_factor)
     vis_out[3 * v] = (q.x + num.x * secs / dc) / out_div;
@@ -311,12 +340,13 @@ advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, cons
                   const int *__restrict__ kthV, const float *__restrict__ num, const float *__restrict__ den,
                   const float *__restrict__ G /*dL/dvis_out [V,3]*/, const float *__restrict__ G2 /*optional second term*/,
                   float g_scale, float H2, float term1, float secs, float eps, float *__restrict__ dL_dX, int accumulate) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (j >= N) return;
     const float3 xj = make_float3(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
     const float3 u = make_float3((xj.x - xyz[3 * j]) / secs, (xj.y - xyz[3 * j + 1]) / secs, (xj.z - xyz[3 * j + 2]) / secs);
     float3 acc = make_float3(0.f, 0.f, 0.f);
-    for_each_neighbor(gv, inv_cell, xj, H2, [&](int v, const float4 &pv, float d2) {
+    warp_for_each_neighbor(gv, inv_cell, xj, H2, lane, [&](int v, const float4 &pv, float d2) {
         if (j > kthV[v]) return;
         float3 Gv = make_float3(G[3 * v], G[3 * v + 1], G[3 * v + 2]);
         if (G2) { Gv.x += G2[3 * v]; Gv.y += G2[3 * v + 1]; Gv.z += G2[3 * v + 2]; }
@@ -334,10 +364,10 @@ advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, cons
         acc.y += s * (xj.y - pv.y) + t * Gv.y;
         acc.z += s * (xj.z - pv.z) + t * Gv.z;
     });
-    if (accumulate) {
-        dL_dX[3 * j] += acc.x; dL_dX[3 * j + 1] += acc.y; dL_dX[3 * j + 2] += acc.z;
-    } else {
-        dL_dX[3 * j] = acc.x; dL_dX[3 * j + 1] = acc.y; dL_dX[3 * j + 2] = acc.z;
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z);
+    if (lane < 3) {
+        const float val = lane == 0 ? acc.x : (lane == 1 ? acc.y : acc.z);
+        if (accumulate) dL_dX[3 * j + lane] += val; else dL_dX[3 * j + lane] = val;
     }
 }
 
@@ -504,6 +534,27 @@ __global__ void adam_kernel(long long n, float *__restrict__ p, const float *__r
     p[i] = p[i] - (lr / bc1) * (mi / denom);
 }
 
+// device-side step counter variant (CUDA-graph replay safe): bumps *step and derives the bias corrections in double
+__global__ void adam_prepare_kernel(int *step, float beta1, float beta2, float *bc /*[2]*/) {
+    const int t = ++(*step);
+    bc[0] = (float)(1.0 - pow((double)beta1, (double)t));
+    bc[1] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
+}
+__global__ void adam_dev_kernel(long long n, float *__restrict__ p, const float *__restrict__ grad, float *__restrict__ m,
+                                float *__restrict__ v, float grad_scale, float lr, float beta1, float beta2, float eps,
+                                const float *__restrict__ bc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float bc1 = bc[0], bc2_sqrt = bc[1];
+    const float gI = grad[i] * grad_scale;
+    const float mi = m[i] + (gI - m[i]) * (1.0f - beta1);
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gI * gI;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
 // scatter_min over int64 index (torch_scatter 2.1.2): out[idx] = min, arg = position of the min (ties: smallest position)
 __global__ void scatter_min_init_kernel(int n_out, float *out, long long *arg, long long n_src) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,7 +599,7 @@ int fnx_radius_count(const void *grid_x, int32_t nx, float cell, const float *y,
     FNX_REQUIRE(grid_x && nx >= 0 && ny >= 0 && r > 0.f && r <= cell * 1.000001f && max_num_neighbors > 0, "bad arguments (need r <= cell)");
     if (ny == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_x, nx);
-    radius_count_kernel<<<(ny + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / cell, y, ny, r * r, max_num_neighbors, nx, counts, kth);
+    radius_count_kernel<<<(ny + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / cell, y, ny, r * r, max_num_neighbors, nx, counts, kth);
     FNX_LAUNCH_CHECK("radius_count_kernel");
     return FNX_OK;
 }
@@ -572,7 +623,7 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    density_fwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, p_ratio);
+    density_fwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, p_ratio);
     FNX_LAUNCH_CHECK("density_fwd_kernel");
     return FNX_OK;
 }
@@ -584,7 +635,7 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    density_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
+    density_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("density_bwd_kernel");
     return FNX_OK;
 }
@@ -597,7 +648,7 @@ int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *
     if (V == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_hidden, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    advect_fwd_kernel<<<(V + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, kthV, H * H, term1, secs, 1e-8f,
+    advect_fwd_kernel<<<(V + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, kthV, H * H, term1, secs, 1e-8f,
                                                                        out_div, visual_out, num_out, den_out);
     FNX_LAUNCH_CHECK("advect_fwd_kernel");
     return FNX_OK;
@@ -611,7 +662,7 @@ int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_visual, V);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    advect_bwd_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, kthV, num, den, dL_dvisual_out, dL_dvisual_out2, g_scale,
+    advect_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, kthV, num, den, dL_dvisual_out, dL_dvisual_out2, g_scale,
                                                                        H * H, term1, secs, 1e-8f, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("advect_bwd_kernel");
     return FNX_OK;
@@ -682,6 +733,18 @@ int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, fl
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, grad_scale, lr, beta1, beta2,
                                                                              eps, bc1, bc2_sqrt);
     FNX_LAUNCH_CHECK("adam_kernel");
+    return FNX_OK;
+}
+
+int fnx_adam_step_dev(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale, float lr,
+                      float beta1, float beta2, float eps, int32_t *step_dev, float *bc_dev, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(n >= 0 && param && grad && exp_avg && exp_avg_sq && step_dev && bc_dev, "bad arguments");
+    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, beta1, beta2, bc_dev);
+    if (n > 0)
+        adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, grad_scale, lr,
+                                                                                     beta1, beta2, eps, bc_dev);
+    FNX_LAUNCH_CHECK("adam_dev_kernel");
     return FNX_OK;
 }
 

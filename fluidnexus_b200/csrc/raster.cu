@@ -1038,13 +1038,17 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         return FNX_OK;
     }
     FNX_REQUIRE(radii != nullptr, "radii must be given");
-    int rc = g_slots.init();
-    if (rc) return rc;
     const int n = P * V;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const float focal_y = H / (2.0f * a->tan_fov_y), focal_x = W / (2.0f * a->tan_fov_x);
     const bool exact_rect = (a->flags & FNX_EXACT_RECT) != 0;
     const bool no_sync = (a->flags & FNX_NO_HOST_SYNC) != 0;
+    FNX_REQUIRE(!no_sync || a->instance_capacity_hint > 0, "FNX_NO_HOST_SYNC needs instance_capacity_hint > 0");
+    int rc = FNX_OK;
+    if (!no_sync) {
+        rc = g_slots.init();
+        if (rc) return rc;
+    }
 
     scratch->geom_bytes = geom_bytes(P, V);
     scratch->geom = ag(cg, scratch->geom_bytes);
@@ -1074,20 +1078,37 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
     FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, it, g.offsets, n, st));
     prof_end(SEC_DEPTH_SORT, st);
 
+    long long cap = a->instance_capacity_hint > 0 ? a->instance_capacity_hint : -1;
+    scratch->binning = nullptr;
+    scratch->check_slot = -1;
+
+    if (no_sync) {  // no events, no waits: capturable into a CUDA graph
+        finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, (long long *)a->num_rendered_pinned);
+        FNX_LAUNCH_CHECK("finish_scan_kernel");
+        scratch->binning_bytes = binning_bytes(cap, C);
+        scratch->binning = ab(cb, scratch->binning_bytes);
+        if (!scratch->binning) {
+            set_error("allocation callback returned NULL");
+            return FNX_ERR_ALLOC;
+        }
+        scratch->binning_capacity = cap;
+        BinView b = bin_view(scratch->binning, cap, C);
+        rc = bin_and_blend<C>(a, st, g, b, im, cap, cap, radii, out_color, out_depth);
+        *num_rendered_host = -1;
+        return rc;
+    }
+
     const int slot_id = g_slots.next;
     g_slots.next = (g_slots.next + 1) % PinnedSlots::N;
     long long *pinned = g_slots.host + slot_id;
     *pinned = -1;
-    long long cap = a->instance_capacity_hint > 0 ? a->instance_capacity_hint : -1;
     finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, pinned);
     FNX_LAUNCH_CHECK("finish_scan_kernel");
     FNX_CUDA_TRY(cudaEventRecord(g_slots.ev[slot_id], st));
-    scratch->binning = nullptr;
 
     long long R = -1;
     const bool exact = cap < 0;
     if (exact) {  // exact sizing: one host sync, like the reference (rasterizer_impl.cu:263-264)
-        FNX_REQUIRE(!no_sync, "FNX_NO_HOST_SYNC needs instance_capacity_hint > 0");
         FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[slot_id]));
         R = *pinned;
         cap = R;
@@ -1108,10 +1129,6 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         rc = bin_and_blend<C>(a, st, g, b, im, cap, exact ? R : cap, radii, out_color, out_depth);
         if (rc) return rc;
         if (exact) break;
-        if (no_sync) {
-            R = -1;
-            break;
-        }
         // everything is queued; the count has almost surely landed already -- this wait does not stall the GPU
         FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[slot_id]));
         R = *pinned;
@@ -1119,6 +1136,7 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         cap = R + R / 8 + 1024;  // overflow: grow and redo binning + blend
     }
     *num_rendered_host = R;
+    if (a->num_rendered_pinned) *a->num_rendered_pinned = R;
     scratch->check_slot = slot_id;
     return FNX_OK;
 }
@@ -1214,9 +1232,18 @@ int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *
 int fnx_raster_check(const fnx_raster_scratch *scratch, int64_t *num_rendered_host, fnx_stream_t stream) {
     (void)stream;
     FNX_REQUIRE(scratch && num_rendered_host, "scratch / num_rendered_host must be given");
-    FNX_REQUIRE(g_slots.ok && scratch->check_slot >= 0 && scratch->check_slot < PinnedSlots::N, "no forward to check");
-    FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[scratch->check_slot]));
-    const long long R = g_slots.host[scratch->check_slot];
+    long long R = -1;
+    if (scratch->check_slot >= 0) {
+        FNX_REQUIRE(g_slots.ok && scratch->check_slot < PinnedSlots::N, "no forward to check");
+        FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[scratch->check_slot]));
+        R = g_slots.host[scratch->check_slot];
+    } else {  // FNX_NO_HOST_SYNC forward: read the device-side header (blocks on the stream)
+        FNX_REQUIRE(scratch->geom, "no forward to check");
+        GeomHeader h;
+        FNX_CUDA_TRY(cudaMemcpyAsync(&h, scratch->geom, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        FNX_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        R = h.num_rendered;
+    }
     *num_rendered_host = R;
     if (R > scratch->binning_capacity) {
         set_error("instance capacity %lld too small for %lld instances", (long long)scratch->binning_capacity, R);

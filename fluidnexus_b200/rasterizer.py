@@ -18,7 +18,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext"]
+__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace"]
 
 
 def _ptr(t):
@@ -153,6 +153,72 @@ def raster_backward(ctx, dL_dout_color, want_means2D=True):
         L.check(bwd(C.byref(ctx.args), C.byref(ctx.scratch), ctx.num_rendered, ctx.radii.data_ptr(), dpix.data_ptr(),
                     C.byref(gr), stream))
     return g
+
+
+class RasterWorkspace:
+    """Persistent buffers for repeated forward/backward of one fixed-size problem with NO allocation, NO host
+    synchronisation and no events inside the calls (FNX_NO_HOST_SYNC), so a whole training iteration can be captured
+    into a CUDA graph.  `capacity` = instances the binning buffers hold; `overflowed()` reports (after a sync) whether a
+    forward needed more -- in that case that forward rendered only the background."""
+
+    def __init__(self, dev, C_, P, V, H, W, capacity, want=("means3D",)):
+        lib = L.lib()
+        self.dev, self.C, self.P, self.V, self.H, self.W, self.capacity = torch.device(dev), C_, P, V, H, W, int(capacity)
+        u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self.geom, self.image = u8(lib.fnx_raster_geom_bytes(P, V)), u8(lib.fnx_raster_image_bytes(W, H, V))
+            self.binning = u8(lib.fnx_raster_binning_bytes(self.capacity, C_))
+            self.color = torch.empty((V, C_, H, W), device=self.dev)
+            self.depth = torch.empty((V, 1, H, W), device=self.dev)
+            self.radii = torch.empty((V, P), dtype=torch.int32, device=self.dev)
+            shapes = dict(means3D=(P, 3), means2D=(V, P, 3), colors=(P, C_), opacity=(P, 1), scales=(P, 3), rotations=(P, 4),
+                          cov3D=(P, 6))
+            self.grads = {k: torch.empty(shapes[k], device=self.dev) for k in want}
+        self.count = torch.full((1,), -1, dtype=torch.int64).pin_memory()
+        self._cbs = tuple(L.ALLOC_FN(self._fixed(t)) for t in (self.geom, self.binning, self.image))
+        self.args, self.scratch, self._keep = L.RasterArgs(), L.RasterScratch(), None
+
+    @staticmethod
+    def _fixed(t):
+        def alloc(_ctx, nbytes):
+            return t.data_ptr() if nbytes <= t.numel() else None
+        return alloc
+
+    def forward(self, bg, means3D, colors, opacities, scales, rotations, scale_modifier, view_matrix, proj_matrix, tan_fov_x,
+                tan_fov_y, exact_rect=False):
+        """All tensors must be contiguous float32 CUDA tensors that stay alive and in place (graph replays read them)."""
+        a = self.args
+        a.P, a.V, a.C, a.W, a.H = self.P, self.V, self.C, self.W, self.H
+        a.means3D, a.colors, a.opacities = means3D.data_ptr(), colors.data_ptr(), opacities.data_ptr()
+        a.scales, a.rotations, a.cov3D_precomp, a.sh = scales.data_ptr(), rotations.data_ptr(), None, None
+        a.view_matrix, a.proj_matrix, a.bg = view_matrix.data_ptr(), proj_matrix.data_ptr(), bg.data_ptr()
+        a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
+        a.prefiltered, a.flags = 0, L.FNX_NO_HOST_SYNC | (L.FNX_EXACT_RECT if exact_rect else 0)
+        a.instance_capacity_hint, a.num_rendered_pinned = self.capacity, self.count.data_ptr()
+        self._keep = (bg, means3D, colors, opacities, scales, rotations, view_matrix, proj_matrix)
+        nr = C.c_int64(0)
+        fwd = L.lib().fnx_raster_forward_ch3 if self.C == 3 else L.lib().fnx_raster_forward_ch1
+        L.check(fwd(C.byref(a), self._cbs[0], None, self._cbs[1], None, self._cbs[2], None, self.color.data_ptr(),
+                    self.depth.data_ptr(), self.radii.data_ptr(), C.byref(nr), C.byref(self.scratch),
+                    torch.cuda.current_stream(self.dev).cuda_stream))
+        return self.color
+
+    def backward(self, dL_dout_color):
+        gr = L.RasterGrads()
+        for name, field in (("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("colors", "dL_dcolors"), ("opacity", "dL_dopacity"),
+                            ("scales", "dL_dscales"), ("rotations", "dL_drotations"), ("cov3D", "dL_dcov3D")):
+            setattr(gr, field, self.grads[name].data_ptr() if name in self.grads else None)
+        bwd = L.lib().fnx_raster_backward_ch3 if self.C == 3 else L.lib().fnx_raster_backward_ch1
+        L.check(bwd(C.byref(self.args), C.byref(self.scratch), -1, self.radii.data_ptr(), dL_dout_color.data_ptr(), C.byref(gr),
+                    torch.cuda.current_stream(self.dev).cuda_stream))
+        return self.grads
+
+    def num_rendered(self):
+        """Instance count of the last finished forward (call after a synchronisation point)."""
+        return int(self.count[0])
+
+    def overflowed(self):
+        return self.num_rendered() > self.capacity
 
 
 def mark_visible(positions, view_matrix, proj_matrix):

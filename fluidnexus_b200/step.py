@@ -95,6 +95,11 @@ class FrameState:
         self.num, self.den, self.dDist = z(V, 3), z(V), z(V, 3)
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)  # gas, next_gas, exyz, dist
         self.vis_grid_built = False
+        self.zero_dmeans = None
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # Adam step count (device side: graph-replay safe)
+        self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.ws = {}       # number of views -> RasterWorkspace
+        self.graphs = {}   # (view ids, update) -> (CUDAGraph, outputs, gt buffer)
 
 
 class PhysicalStep:
@@ -112,7 +117,8 @@ class PhysicalStep:
         self.W, self.H = int(c0.image_width), int(c0.image_height)
         self.tan_fov_x, self.tan_fov_y = math.tan(c0.FoVx * 0.5), math.tan(c0.FoVy * 0.5)
         self.bg = _dev_f32([0.0] * channels if bg_color is None else bg_color, self.dev)
-        self._loss_scratch = {}
+        self._loss_scratch, self._views = {}, {}
+        self.capacity_margin = 1.2   # binning capacity = margin * instances of the sizing forward + 64k
         self.lib = L.lib()
 
     # -- pieces ---------------------------------------------------------------------------------------------
@@ -152,10 +158,35 @@ class PhysicalStep:
             ck(lib.fnx_grid_build(fr.visual.data_ptr(), V, prm.H, fr.gridVis.data_ptr(), st))
             fr.vis_grid_built = True
 
+    def _view_mats(self, view_ids):
+        key = tuple(view_ids)
+        if key not in self._views:
+            idx = torch.tensor(list(key), dtype=torch.long, device=self.dev)
+            self._views[key] = (self.view_all[idx].contiguous(), self.proj_all[idx].contiguous())
+        return self._views[key]
+
+    def workspace(self, fr: FrameState, nviews, view_ids):
+        """Persistent rasterizer buffers for this frame; sized from one exact forward (the only one that blocks)."""
+        ws = fr.ws.get(nviews)
+        if ws is not None and ws.num_rendered() > ws.capacity:   # the last finished forward overflowed: grow
+            torch.cuda.synchronize(self.dev)
+            ws = None
+        if ws is None:
+            vm, pm = self._view_mats(view_ids)
+            ctx, _, _, _ = R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, vm,
+                                            pm, self.tan_fov_x, self.tan_fov_y, self.H, self.W, speculative=False)
+            cap = int(ctx.num_rendered * self.capacity_margin) + 65536
+            del ctx
+            ws = R.RasterWorkspace(self.dev, self.C, fr.P, nviews, self.H, self.W, cap)
+            fr.ws[nviews] = ws
+            fr.graphs.clear()
+        return ws
+
     def render(self, fr: FrameState, view_ids):
-        vm, pm = self.view_all[view_ids].contiguous(), self.proj_all[view_ids].contiguous()
-        return R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, vm, pm,
-                                self.tan_fov_x, self.tan_fov_y, self.H, self.W, speculative=True)
+        ws = self.workspace(fr, len(view_ids), view_ids)
+        vm, pm = self._view_mats(view_ids)
+        ws.forward(self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, vm, pm, self.tan_fov_x, self.tan_fov_y)
+        return ws
 
     def image_loss(self, images, gt, batch):
         prm, lib = self.prm, self.lib
@@ -189,32 +220,66 @@ class PhysicalStep:
             self.adam(fr)
 
     def adam(self, fr: FrameState, grad=None, grad_scale=1.0):
-        fr.adam_step += 1
         g = fr.de if grad is None else grad
-        L.check(self.lib.fnx_adam_step(fr.e.numel(), fr.e.data_ptr(), g.data_ptr(), fr.m.data_ptr(), fr.v.data_ptr(), grad_scale,
-                                       self.prm.lr, 0.9, 0.999, self.prm.adam_eps, fr.adam_step,
-                                       torch.cuda.current_stream(self.dev).cuda_stream))
+        L.check(self.lib.fnx_adam_step_dev(fr.e.numel(), fr.e.data_ptr(), g.data_ptr(), fr.m.data_ptr(), fr.v.data_ptr(), grad_scale,
+                                           self.prm.lr, 0.9, 0.999, self.prm.adam_eps, fr.step_dev.data_ptr(), fr.bc_dev.data_ptr(),
+                                           torch.cuda.current_stream(self.dev).cuda_stream))
 
     # -- the step -------------------------------------------------------------------------------------------
-    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None):
-        """One optimiser iteration for one frame.  view_ids: list of camera indices rendered by THIS process;
-        gt [len(view_ids),C,H,W] on the device; `batch` = global number of views of the step (defaults to
-        len(view_ids); larger when views are sharded over ranks).  Returns device tensors, no host sync."""
+    def _iteration(self, fr: FrameState, view_ids, gt, update, batch):
+        self.physics_forward(fr)
+        out = {}
+        if len(view_ids):
+            ws = self.render(fr, view_ids)
+            l1, ss, g = self.image_loss(ws.color, gt, batch)
+            dmeans = ws.backward(g)["means3D"]
+            out.update(l1=l1, ssim=ss, images=ws.color, radii=ws.radii, ws=ws)
+        else:
+            if fr.zero_dmeans is None:
+                fr.zero_dmeans = torch.zeros((fr.P, 3), device=self.dev)
+            dmeans = fr.zero_dmeans
+        self.physics_backward_and_update(fr, dmeans, update=update)
+        out.update(gas=fr.scalars[0], next_gas=fr.scalars[1], exyz=fr.scalars[2], dist=fr.scalars[3], grad=fr.de)
+        return out
+
+    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None, graph=False):
+        """One optimiser iteration for one frame.  view_ids: camera indices rendered by THIS process; gt
+        [len(view_ids),C,H,W] (device tensor, or a pinned host tensor); `batch` = global number of views of the step
+        (defaults to len(view_ids); larger when views are sharded over ranks).  graph=True captures the iteration
+        into a CUDA graph on first use and replays it afterwards (one host call per iteration).
+        Returns device tensors that are overwritten by the next step; there is no host synchronisation."""
         batch = len(view_ids) if batch is None else batch
         with torch.cuda.device(self.dev):
-            self.physics_forward(fr)
-            out = {}
-            if len(view_ids):
-                ctx, images, radii, depth = self.render(fr, view_ids)
-                l1, ss, g = self.image_loss(images, gt, batch)
-                grads = R.raster_backward(ctx, g, want_means2D=False)
-                dmeans = grads["means3D"]
-                out.update(l1=l1, ssim=ss, images=images, radii=radii, num_rendered=ctx.num_rendered)
-            else:
-                dmeans = torch.zeros((fr.P, 3), device=self.dev)
-            self.physics_backward_and_update(fr, dmeans, update=update)
-            out.update(gas=fr.scalars[0], next_gas=fr.scalars[1], exyz=fr.scalars[2], dist=fr.scalars[3], grad=fr.de)
-        return out
+            if not graph:
+                if not gt.is_cuda:
+                    gt = gt.to(self.dev, non_blocking=True)
+                return self._iteration(fr, view_ids, gt, update, batch)
+            key = (tuple(view_ids), bool(update), batch)
+            ent = fr.graphs.get(key)
+            if ent is None:
+                # everything that allocates or blocks happens eagerly first (workspace sizing, visual grid, scratch)
+                gt_buf = torch.empty((len(view_ids), self.C, self.H, self.W), device=self.dev)
+                gt_buf.copy_(gt, non_blocking=True)
+                snap = (fr.e.clone(), fr.m.clone(), fr.v.clone(), fr.step_dev.clone())
+                self._iteration(fr, view_ids, gt_buf, update, batch)         # eager warm-up (also sizes the workspace)
+                for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # undo its parameter update
+                    dst.copy_(src)
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self._iteration(fr, view_ids, gt_buf, update, batch)
+                ent = (g, out, gt_buf)
+                fr.graphs[key] = ent
+                for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # capture does not execute, but be explicit
+                    dst.copy_(src)
+            g, out, gt_buf = ent
+            ws = out.get("ws")
+            if ws is not None and ws.num_rendered() > ws.capacity:
+                raise RuntimeError("rasterizer instance capacity exceeded inside a captured iteration; re-capture "
+                                   f"(needed {ws.num_rendered()}, capacity {ws.capacity})")
+            gt_buf.copy_(gt, non_blocking=True)
+            g.replay()
+            return out
 
     def total_loss(self, out, batch=None):
         """The reference's per-view `loss`, averaged over the views (device scalar)."""

@@ -59,8 +59,9 @@ unsigned long long fnx_launch_count(void);
  * ---------------------------------------------------------------------------------------------- */
 
 /* flags */
-#define FNX_NO_HOST_SYNC 1u /* never block the host: trust `instance_capacity_hint`; on overflow nothing is
-                               rendered, *num_rendered_host is left at -1 and fnx_raster_check() reports it */
+#define FNX_NO_HOST_SYNC 1u /* never block the host and use no events (the call can be captured into a CUDA graph):
+                               trust `instance_capacity_hint`; on overflow nothing is rendered (images = background),
+                               *num_rendered_host is left at -1 and fnx_raster_check() / num_rendered_pinned report it */
 #define FNX_EXACT_RECT 2u   /* bin with the reference's full 3-sigma tile rectangle (no opacity-aware tile
                                culling).  Results are identical either way; this exists for A/B tests. */
 
@@ -86,6 +87,8 @@ typedef struct fnx_raster_args {
     int32_t prefiltered;        /* accepted, unused (reference only traps on inconsistency) */
     uint32_t flags;
     int64_t instance_capacity_hint; /* 0 = size exactly (one host sync, like the reference) */
+    int64_t *num_rendered_pinned;   /* optional PINNED HOST int64 the device writes the instance count to (it can be
+                                       polled at any later time; with FNX_NO_HOST_SYNC it is the only read-back) */
 } fnx_raster_args;
 
 /* Opaque handles to the three scratch buffers of one forward (what the reference returns as
@@ -225,6 +228,11 @@ int fnx_pbf_ratio_loss(int32_t N, const float *p_ratio, float weight, float *los
  * (= 1/batch of set_batch_gradient_*, gm_fluid.py:428-430).  step >= 1 is the step count AFTER this update. */
 int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale,
                   float lr, float beta1, float beta2, float eps, int32_t step, fnx_stream_t stream);
+
+/* Same update with the step count kept on the device (*step_dev is incremented first; bc_dev is 2 floats of scratch):
+ * safe to capture once into a CUDA graph and replay. */
+int fnx_adam_step_dev(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale,
+                      float lr, float beta1, float beta2, float eps, int32_t *step_dev, float *bc_dev, fnx_stream_t stream);
 
 /* torch_scatter.scatter_min(src, index, dim_size=n_out) for 1-D fp32 src and int64 index (gm_fluid.py:1088,1272):
  * out [n_out] (0 for empty groups), arg [n_out] int64 (n for empty groups). */

@@ -92,3 +92,24 @@ def test_step_is_deterministic_and_descends(libfnx):
     assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
     assert (runs[0][1] - runs[1][1]).abs().max() < 1e-6
     assert runs[0][0][-1] < runs[0][0][0]
+
+
+def test_cuda_graph_replay_equals_eager(libfnx):
+    """The captured iteration (one host call per iteration, no host sync) must follow the eager one bit for bit in the
+    atomics-free physics and to rounding level in the rasterizer gradient; pinned-host ground truth is accepted."""
+    hp, vis, fluid, bg, cams = _scene(3, True, seed=4)
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    ps = PhysicalStep(cams, 3, prm)
+    gt = (torch.rand(5, 3, 64, 64, generator=torch.Generator().manual_seed(1)) * 0.5)
+    gt_pinned = gt.pin_memory()
+    res = {}
+    for mode in ("eager", "graph"):
+        fr = FrameState(hp, vis, fluid, bg, prm=prm)
+        losses = []
+        for it in range(6):
+            out = ps.step(fr, [0, 1, 2, 3, 4], gt.cuda() if mode == "eager" else gt_pinned, graph=(mode == "graph"))
+            losses.append(float(ps.total_loss(out)))
+        res[mode] = (losses, fr.e.clone(), int(fr.step_dev.item()))
+    assert res["eager"][2] == res["graph"][2] == 6
+    assert np.allclose(res["eager"][0], res["graph"][0], rtol=1e-5)
+    assert (res["eager"][1] - res["graph"][1]).abs().max() < 1e-6
