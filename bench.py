@@ -103,6 +103,7 @@ def run_fnx(args):
     import torch.distributed as dist
     from fluidnexus_b200 import _lib as L
     from fluidnexus_b200 import rasterizer as R
+    from fluidnexus_b200.parallel import FlatBucket, assign_items
     from fluidnexus_b200.step import FrameState, PhysicalStep, StepParams
     rank, world, local = dist_info()
     torch.cuda.set_device(local)
@@ -115,17 +116,19 @@ def run_fnx(args):
     prm = StepParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], grey=cfg["grey"], distance_threshold_visual=cfg["thr"])
     ps = PhysicalStep(cams, cfg["C"], prm, device=dev)
     N = cfg["N"]
-    # replicated parameters / Adam state / gradient bucket of ALL frames, flat
-    E = torch.zeros((G, N, 3), device=dev); M = torch.zeros_like(E); Vv = torch.zeros_like(E); DE = torch.zeros_like(E)
-    mine = [f for f in range(G) if f % world == rank]
+    # replicated parameters / Adam state / gradient bucket of ALL frames, flat (fluidnexus_b200/parallel.py)
+    fb = FlatBucket(G, N, dev)
+    E, M, Vv, DE = fb.param, fb.exp_avg, fb.exp_avg_sq, fb.grad
+    by_frame, physics_frames = assign_items(G, len(views), world, rank)
+    mine = sorted(by_frame)
     states = {}
     for f in mine:
         fr = FrameState(frames[f]["hidden"], frames[f]["visual"], frames[f]["fluid"], bg, device=dev, prm=prm)
-        E[f].copy_(fr.e)
-        fr.e, fr.m, fr.v, fr.de = E[f], M[f], Vv[f], DE[f]  # views into the flat, replicated buffers
+        if f in physics_frames:
+            E[f].copy_(fr.e)
+        fr.e, fr.m, fr.v, fr.de = fb.views(f)               # views into the flat, replicated buffers
         states[f] = fr
-    if world > 1:
-        dist.all_reduce(E)  # every slot was written by exactly one rank, the others hold zeros
+    fb.broadcast_params_from_owners()
     # ground truth: the same scene with fluid positions perturbed by N(0, 0.002), rendered once by the rasterizer
     gts_dev, gts_pinned = {}, {}
     for f in mine:
@@ -135,8 +138,8 @@ def run_fnx(args):
         pert[:fr.V] += torch.tensor(rng.normal(0, 0.002, (fr.V, 3)), dtype=torch.float32, device=dev)
         ctx, img, _, _ = R.raster_forward(cfg["C"], ps.bg, pert, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, ps.view_all,
                                           ps.proj_all, ps.tan_fov_x, ps.tan_fov_y, ps.H, ps.W, speculative=False)
-        gts_dev[f] = img.clone()
-        gts_pinned[f] = img.cpu().pin_memory()
+        gts_dev[f] = img[by_frame[f]].clone()
+        gts_pinned[f] = gts_dev[f].cpu().pin_memory()
         del ctx
     torch.cuda.synchronize()
     step_no = [0]
@@ -149,9 +152,8 @@ def run_fnx(args):
             fr = states[f]
             # e2e: ground truth comes from pinned HOST memory every iteration (the reference uploads it at :325)
             gt = gts_pinned[f] if e2e else gts_dev[f]
-            last = ps.step(fr, views, gt, update=False, batch=len(views), graph=use_graph[0])
-        if world > 1:
-            dist.all_reduce(DE)
+            last = ps.step(fr, by_frame[f], gt, update=False, batch=len(views), graph=use_graph[0], physics=f in physics_frames)
+        fb.all_reduce()
         step_no[0] += 1
         L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
                                   prm.adam_eps, step_no[0], torch.cuda.current_stream(dev).cuda_stream))
@@ -195,7 +197,7 @@ def run_fnx(args):
     launches = launches_per_step * args.steps
     R_per_iter = float(out["ws"].num_rendered()) if out and "ws" in out else 0.0
     for f in mine:
-        assert not states[f].ws[len(views)].overflowed(), "instance capacity overflow inside the timed region"
+        assert not states[f].ws[len(by_frame[f])].overflowed(), "instance capacity overflow inside the timed region"
     # ---- end to end: pinned host ground truth uploaded every iteration + loss read back every step ----
     for _ in range(2):
         one_step(True)
@@ -246,7 +248,8 @@ def run_fnx(args):
                    "instances_per_iteration": R_per_iter,
                    "l2": f"working set per iteration ~{(R_per_iter * (rec + 16) + 5 * HW * 40) / 1e6:.0f} MB and {G} frames "
                          "cycle between iterations: larger than the 126 MB L2, no explicit flush"},
-        "e2e": {"value": round(e2e, 3), "unit": "iters/s", "h2d_bytes_per_step": int(len(mine) * 5 * Cc * HW * 4),
+        "e2e": {"value": round(e2e, 3), "unit": "iters/s",
+                "h2d_bytes_per_step": int(sum(len(v) for v in by_frame.values()) * Cc * HW * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -242,6 +242,19 @@ __device__ __forceinline__ float edge_min(float A, float B, float Cq, float X, f
     float ys = min(y1, max(y0, -B * X / Cq));
     return 0.5f * A * X * X + B * X * ys + 0.5f * Cq * ys * ys;
 }
+// does the pixel-centre box [bx, bx+w-1] x [by, by+h-1] contain a pixel that can reach alpha >= 1/255 ?
+__device__ __forceinline__ bool box_needed(const TileCull &t, const float2 mean, int bx, int by, int w, int h) {
+    if (!t.active) return true;
+    if (t.tau < 0.f) return false;
+    float x0 = bx - mean.x, x1 = x0 + (w - 1);
+    float y0 = by - mean.y, y1 = y0 + (h - 1);
+    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return true;
+    float m = edge_min(t.a, t.b, t.c, x0, y0, y1);
+    m = min(m, edge_min(t.a, t.b, t.c, x1, y0, y1));
+    m = min(m, edge_min(t.c, t.b, t.a, y0, x0, x1));
+    m = min(m, edge_min(t.c, t.b, t.a, y1, x0, x1));
+    return m <= t.tau;
+}
 __device__ __forceinline__ bool tile_needed(const TileCull &t, const float2 mean, int tx, int ty) {
     if (!t.active) return true;
     if (t.tau < 0.f) return false;
@@ -464,23 +477,49 @@ emit_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict
 // ---------------------------------------------------------------------------------------------------------------
 // K6: pack the sorted instances into the record stream + per-tile ranges (identifyTileRanges, rasterizer_impl.cu:109-128)
 // ---------------------------------------------------------------------------------------------------------------
+// Sub-tile mask: bit w set <=> the 8x4 pixel patch of warp w can receive a contribution from this instance.  The blend
+// kernels iterate only over the set bits of their own patch (a small splat touches 1-2 of a tile's 8 patches).
+constexpr uint32_t SLOT_BITS = 24;  // slot id lives in the low 24 bits of the record's slot word when it fits
+__device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co, int tx, int ty, bool exact_rect) {
+    const TileCull tc = make_cull(co, exact_rect);
+    if (!tc.active) return 0xFFu;
+    if (tc.tau < 0.f) return 0u;
+    // axis-aligned extent of the ellipse q <= tau: |ux| <= sqrt(2 tau c / det), |uy| <= sqrt(2 tau a / det)
+    const float det = tc.a * tc.c - tc.b * tc.b;
+    const float hx = sqrtf(2.f * tc.tau * tc.c / det) * 1.0001f + 0.01f, hy = sqrtf(2.f * tc.tau * tc.a / det) * 1.0001f + 0.01f;
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int bx = tx * TILE + (w & 1) * 8, by = ty * TILE + (w >> 1) * 4;
+        const bool bbox = (xy.x + hx >= bx) && (xy.x - hx <= bx + 7) && (xy.y + hy >= by) && (xy.y - hy <= by + 3);
+        if (bbox && box_needed(tc, xy, bx, by, 8, 4)) m |= 1u << w;
+    }
+    return m;
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
-pack_kernel(long long cap, int P, const float *__restrict__ colors, GeomView g, BinView b, uint2 *__restrict__ ranges) {
+pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_mask, const float *__restrict__ colors, GeomView g,
+            BinView b, uint2 *__restrict__ ranges) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long R = g.hdr->num_rendered;
     if (i >= R || i >= cap || g.hdr->overflow) return;
-    const uint32_t slot = b.tvals_out[i];
+    uint32_t slot = b.tvals_out[i];
     const uint32_t tile = b.tkeys_out[i];
     const float2 xy = g.xy[slot];
     const float4 co = g.conic_o[slot];
     const uint32_t gi = slot % (uint32_t)P;
+    const float depth = g.depth[slot];
+    if (use_mask) {
+        const uint32_t tl = tile % (uint32_t)ntiles;
+        slot |= patch_mask(xy, co, tl % gx, tl / gx, exact_rect) << SLOT_BITS;
+    }
     float4 *rec = reinterpret_cast<float4 *>(b.records + (size_t)i * RecBytes<C>::value);
     rec[0] = make_float4(xy.x, xy.y, co.x, co.y);
     if (C == 3) {
         const float c0 = colors[3 * (size_t)gi], c1 = colors[3 * (size_t)gi + 1], c2 = colors[3 * (size_t)gi + 2];
         rec[1] = make_float4(co.z, co.w, c0, c1);
-        rec[2] = make_float4(c2, __uint_as_float(slot), g.depth[slot], 0.f);
+        rec[2] = make_float4(c2, __uint_as_float(slot), depth, 0.f);
     } else {
         rec[1] = make_float4(co.z, co.w, colors[gi], __uint_as_float(slot));
     }
@@ -521,11 +560,29 @@ constexpr int STAGES = 2;
 // ---------------------------------------------------------------------------------------------------------------
 // K7: blend forward.  One CTA per (tile, view); warp w owns the 8x4 pixel patch (w&1, w>>1).  forward.cu:249-373
 // ---------------------------------------------------------------------------------------------------------------
+// slot word of record j (slot id in the low SLOT_BITS bits, patch mask above when use_mask)
+template <int C>
+__device__ __forceinline__ uint32_t rec_slot_word(const float4 *rec, int j) {
+    const float *f = reinterpret_cast<const float *>(rec);
+    return __float_as_uint(C == 3 ? f[j * 12 + 9] : f[j * 8 + 7]);
+}
+// this warp's bitmask over the n (<= 128) staged records: bit set <=> the record can touch the warp's 8x4 patch
+template <int C>
+__device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int warp, int lane, bool use_mask, uint32_t (&words)[BATCH / 32]) {
+#pragma unroll
+    for (int k = 0; k < BATCH / 32; k++) {
+        const int r = k * 32 + lane;
+        bool need = r < n;
+        if (need && use_mask) need = ((rec_slot_word<C>(rec, r) >> (SLOT_BITS + warp)) & 1u) != 0;
+        words[k] = __ballot_sync(0xffffffffu, need);
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(TILE_PIX)
-blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records, const float *__restrict__ depth_of_slot,
-                 const float *__restrict__ bg, const GeomHeader *__restrict__ hdr, ImageView im,
-                 float *__restrict__ out_color, float *__restrict__ out_depth) {
+blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records,
+                 const float *__restrict__ depth_of_slot, const float *__restrict__ bg, const GeomHeader *__restrict__ hdr,
+                 ImageView im, float *__restrict__ out_color, float *__restrict__ out_depth) {
     constexpr int REC = RecBytes<C>::value;
     __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
@@ -540,6 +597,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
     const float pxf = (float)px, pyf = (float)py;
     const size_t HW = (size_t)W * H;
     const size_t pix_id = (size_t)v * HW + (size_t)py * W + px;
+    const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
 
     uint2 range = im.ranges[(size_t)v * ntiles + tile];
     if (hdr->overflow) range = make_uint2(0, 0);
@@ -587,8 +645,16 @@ blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
         mbar_wait(&s_bar[s], (bi / STAGES) & 1);
         const int n = min(BATCH, total - bi * BATCH);
         const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
-        if (!done) {
-            for (int j = 0; j < n; j++) {
+        if (__all_sync(0xffffffffu, done)) continue;  // this warp's patch is finished
+        uint32_t words[BATCH / 32];
+        warp_record_mask<C>(rec, n, warp, lane, use_mask, words);
+#pragma unroll
+        for (int k = 0; k < BATCH / 32; k++) {
+            uint32_t w = words[k];
+            while (w) {
+                const int j = k * 32 + __ffs(w) - 1;
+                w &= w - 1;
+                if (done) continue;
                 const float4 r0 = rec[j * (REC / 16)];
                 const float4 r1 = rec[j * (REC / 16) + 1];
                 float dx, dy, G, alpha;
@@ -596,7 +662,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
                 const float test_T = T * (1 - alpha);
                 if (test_T < T_EPS) {
                     done = true;
-                    break;
+                    continue;
                 }
                 if (C == 3) {
                     const float4 r2 = rec[j * 3 + 2];
@@ -606,7 +672,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
                     if (T > 0.5f && test_T < 0.5) D = r2.z;
                 } else {
                     Cacc[0] += r1.z * alpha * T;
-                    if (T > 0.5f && test_T < 0.5) D = depth_of_slot[__float_as_uint(r1.w)];
+                    if (T > 0.5f && test_T < 0.5) D = depth_of_slot[__float_as_uint(r1.w) & slot_mask];
                 }
                 T = test_T;
                 last_contributor = (uint32_t)(bi * BATCH + j + 1);
@@ -641,13 +707,66 @@ blend_fwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Warp reduction of N per-lane values with a value-splitting butterfly.  A plain butterfly costs 5 shuffles per
+// value (45 for N = 9) and shuffles run on the LSU pipe (1 warp-instruction / clk / SM) -- the first profile of the
+// backward showed that pipe at 74 % with shuffles as ~85 % of its traffic.  Here, at xor-mask m, the lanes with bit m
+// clear keep the first half of their values and the others the second half; each lane sends the half it drops and
+// adds the half it receives, so the value count halves every round: 5+3+2+1+1 = 12 shuffles for N = 9 (9 for N = 7).
+// Afterwards every lane holds ONE fully reduced value; split_index() tells which (or -1), split_dup_mask() which
+// lane bits hold duplicates.
+// ---------------------------------------------------------------------------------------------------------------
+template <int N, int M>
+struct SplitReduce {
+    static __device__ __forceinline__ float run(const float *v, int lane) {
+        if constexpr (M == 0) {
+            return v[0];
+        } else if constexpr (N == 1) {
+            float w[1] = {v[0] + __shfl_xor_sync(0xffffffffu, v[0], M)};
+            return SplitReduce<1, M / 2>::run(w, lane);
+        } else {
+            constexpr int H0 = (N + 1) / 2;
+            const bool bit = (lane & M) != 0;
+            float w[H0];
+#pragma unroll
+            for (int k = 0; k < H0; k++) {
+                const float a = v[k];
+                const float b = (H0 + k < N) ? v[H0 + k] : 0.f;
+                const float send = bit ? a : b, keep = bit ? b : a;
+                w[k] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+            }
+            return SplitReduce<H0, M / 2>::run(w, lane);
+        }
+    }
+    // index (into the original N values) of the value this lane ends up holding, or -1
+    static __device__ __forceinline__ int index(int lane) {
+        if constexpr (M == 0) {
+            return 0;
+        } else if constexpr (N == 1) {
+            return SplitReduce<1, M / 2>::index(lane);
+        } else {
+            constexpr int H0 = (N + 1) / 2;
+            const int sub = SplitReduce<H0, M / 2>::index(lane);
+            if (sub < 0) return -1;
+            const int orig = (lane & M) ? H0 + sub : sub;
+            return orig < N ? orig : -1;
+        }
+    }
+    static __device__ __forceinline__ constexpr int dup_mask() {
+        if constexpr (M == 0) return 0;
+        else if constexpr (N == 1) return M | SplitReduce<1, M / 2>::dup_mask();
+        else return SplitReduce<(N + 1) / 2, M / 2>::dup_mask();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // K8: blend backward.  backward.cu:384-536.  Walks the tile's records back to front starting at the last record any
-// pixel of the tile used; per record the 32 pixels of a warp are reduced with shuffles, then lane 0 issues
-// 2-3 vector reductions into the (view, Gaussian) accumulator row.
+// pixel of the tile used; per record the 32 pixels of a warp are reduced with the value-splitting butterfly above,
+// then the 6+C lanes that hold a result issue ONE reduction instruction into the (view, Gaussian) accumulator row
+// (their 6+C addresses are contiguous: 1-2 L2 sectors).
 // ---------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(TILE_PIX)
-blend_bwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records, const float *__restrict__ bg,
+blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records, const float *__restrict__ bg,
                  const GeomHeader *__restrict__ hdr, ImageView im, const float *__restrict__ dL_dpixels,
                  float *__restrict__ accum) {
     constexpr int REC = RecBytes<C>::value;
@@ -665,6 +784,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
     const float pxf = (float)px, pyf = (float)py;
     const size_t HW = (size_t)W * H;
     const size_t pix_id = (size_t)v * HW + (size_t)py * W + px;
+    const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
 
     const uint2 range = im.ranges[(size_t)v * ntiles + tile];
     int total = (int)im.tile_last[(size_t)v * ntiles + tile];  // records [0,total) of the span matter
@@ -688,9 +808,16 @@ blend_bwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
             }
     }
 
+    constexpr int NV = 6 + C;  // {dmean2D.xy, dconic.xyw, dopacity, dcolor[C]} == accumulator row order
+    using Red = SplitReduce<NV, 16>;
+    const int my_val = ((lane & Red::dup_mask()) == 0) ? Red::index(lane) : -1;  // which reduced value this lane publishes
+
     const float T_final = inside ? im.final_T[pix_id] : 0.f;
     float T = T_final;
     const int last_contributor = inside ? (int)im.n_contrib[pix_id] : 0;
+    int warp_last = last_contributor;  // records at or beyond this position touch no pixel of this warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
     float accum_rec[C], dL_dpixel[C], last_color[C];
     float bg_dot_dpixel = 0.f;
 #pragma unroll
@@ -716,69 +843,65 @@ blend_bwd_kernel(int W, int H, int gx, int gy, const char *__restrict__ records,
         }
         mbar_wait(&s_bar[s], (bi / STAGES) & 1);
         const int hi = total - bi * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+        if (lo >= warp_last) continue;  // nothing in this batch reaches this warp's pixels
         const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
-        for (int j = n - 1; j >= 0; j--) {
-            const int idx = lo + j;  // 0-based position in the tile's span
-            const float4 r0 = rec[j * (REC / 16)];
-            const float4 r1 = rec[j * (REC / 16) + 1];
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            bool contrib = (idx < last_contributor) && pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf, dx, dy, G, alpha);
-            if (!__any_sync(0xffffffffu, contrib)) continue;
+        uint32_t words[BATCH / 32];
+        warp_record_mask<C>(rec, min(n, warp_last - lo), warp, lane, use_mask, words);
+#pragma unroll
+        for (int k = BATCH / 32 - 1; k >= 0; k--) {
+            uint32_t w = words[k];
+            while (w) {
+                const int bit = 31 - __clz(w);
+                w &= ~(1u << bit);
+                const int j = k * 32 + bit;
+                const int idx = lo + j;  // 0-based position in the tile's span
+                const float4 r0 = rec[j * (REC / 16)];
+                const float4 r1 = rec[j * (REC / 16) + 1];
+                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+                const bool contrib = (idx < last_contributor) && pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf, dx, dy, G, alpha);
+                if (!__any_sync(0xffffffffu, contrib)) continue;
 
-            float g_col[C];
-            float g_mx = 0.f, g_my = 0.f, g_ca = 0.f, g_cb = 0.f, g_cc = 0.f, g_op = 0.f;
+                float vals[NV];
 #pragma unroll
-            for (int ch = 0; ch < C; ch++) g_col[ch] = 0.f;
-            uint32_t slot_bits;
-            float col[C];
-            if (C == 3) {
-                const float4 r2 = rec[j * 3 + 2];
-                col[0] = r1.z; col[1 % C] = r1.w; col[2 % C] = r2.x;
-                slot_bits = __float_as_uint(r2.y);
-            } else {
-                col[0] = r1.z;
-                slot_bits = __float_as_uint(r1.w);
-            }
-            if (contrib) {
-                T = T / (1.f - alpha);
-                const float dchannel_dcolor = alpha * T;
-                float dL_dalpha = 0.0f;
-#pragma unroll
-                for (int ch = 0; ch < C; ch++) {
-                    const float c = col[ch];
-                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                    last_color[ch] = c;
-                    dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
-                    g_col[ch] = dchannel_dcolor * dL_dpixel[ch];
-                }
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                const float dL_dG = r1.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-                const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                g_mx = dL_dG * dG_ddelx * ddelx_dx;
-                g_my = dL_dG * dG_ddely * ddely_dy;
-                g_ca = -0.5f * gdx * dx * dL_dG;
-                g_cb = -0.5f * gdx * dy * dL_dG;
-                g_cc = -0.5f * gdy * dy * dL_dG;
-                g_op = G * dL_dalpha;
-            }
-            g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
-            g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb); g_cc = warp_sum(g_cc);
-            g_op = warp_sum(g_op);
-#pragma unroll
-            for (int ch = 0; ch < C; ch++) g_col[ch] = warp_sum(g_col[ch]);
-            if (lane == 0) {
-                float *row = accum + (size_t)slot_bits * ACC;
-                red_add_v4(row, g_mx, g_my, g_ca, g_cb);
+                for (int q = 0; q < NV; q++) vals[q] = 0.f;
+                uint32_t slot_bits;
+                float col[C];
                 if (C == 3) {
-                    red_add_v4(row + 4, g_cc, g_op, g_col[0], g_col[1 % C]);
-                    red_add(row + 8, g_col[2 % C]);
+                    const float4 r2 = rec[j * 3 + 2];
+                    col[0] = r1.z; col[1 % C] = r1.w; col[2 % C] = r2.x;
+                    slot_bits = __float_as_uint(r2.y) & slot_mask;
                 } else {
-                    red_add_v4(row + 4, g_cc, g_op, g_col[0], 0.f);
+                    col[0] = r1.z;
+                    slot_bits = __float_as_uint(r1.w) & slot_mask;
                 }
+                if (contrib) {
+                    T = T / (1.f - alpha);
+                    const float dchannel_dcolor = alpha * T;
+                    float dL_dalpha = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) {
+                        const float c = col[ch];
+                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                        last_color[ch] = c;
+                        dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
+                        vals[6 + ch] = dchannel_dcolor * dL_dpixel[ch];
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                    const float dL_dG = r1.y * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+                    const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+                    vals[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    vals[1] = dL_dG * dG_ddely * ddely_dy;
+                    vals[2] = -0.5f * gdx * dx * dL_dG;
+                    vals[3] = -0.5f * gdx * dy * dL_dG;
+                    vals[4] = -0.5f * gdy * dy * dL_dG;
+                    vals[5] = G * dL_dalpha;
+                }
+                const float red = Red::run(vals, lane);
+                if (my_val >= 0) red_add(accum + (size_t)slot_bits * ACC + my_val, red);
             }
         }
     }
@@ -1010,13 +1133,16 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
                                                      (int)sort_items, 0, end_bit, st));
         prof_end(SEC_TILE_SORT, st);
         prof_begin(SEC_PACK, st);
-        pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, a->colors, g, b, im.ranges);
+        const bool use_mask = (long long)P * V < (1ll << SLOT_BITS);
+        pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, gx, ntiles, exact_rect, use_mask, a->colors, g, b,
+                                                                            im.ranges);
         prof_end(SEC_PACK, st);
         FNX_LAUNCH_CHECK("pack_kernel");
     }
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(a->W, a->H, gx, gy, b.records, g.depth, a->bg, g.hdr, im, out_color, out_depth);
+    blend_fwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, g.depth, a->bg,
+                                                   g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
     return FNX_OK;
@@ -1165,7 +1291,8 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_BWD, st);
-    blend_bwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(W, H, gx, gy, b.records, a->bg, g.hdr, im, dL_dout_color, g.accum);
+    blend_bwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, a->bg, g.hdr, im,
+                                                   dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
     prof_begin(SEC_GEOM_BWD, st);

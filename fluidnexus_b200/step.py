@@ -122,31 +122,40 @@ class PhysicalStep:
         self.lib = L.lib()
 
     # -- pieces ---------------------------------------------------------------------------------------------
-    def physics_forward(self, fr: FrameState):
-        """P2, P3, P1-forward, P5: fills fr.means3D[:V], fr.dX, fr.dY, fr.dDist and the loss scalars."""
+    def physics_forward(self, fr: FrameState, physics=True):
+        """P2, P3, P1-forward, P5: fills fr.means3D[:V], fr.dX, fr.dY, fr.dDist and the loss scalars.
+        physics=False (a rank that renders some views of a frame whose view-independent terms another rank owns)
+        runs only P1, which the rasterizer needs."""
         lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
         N, V = fr.N, fr.V
         ck = L.check
         ck(lib.fnx_pbf_next_tick_fwd(N, fr.e.data_ptr(), fr.xyz.data_ptr(), fr.buoyancy.data_ptr(), fr.force.data_ptr(), prm.secs,
-                                     prm.buoyancy_max_y, prm.scale_factor, fr.X.data_ptr(), fr.Y.data_ptr(), st))
-        for grid, pos, kth, p, gp, lam, slot in ((fr.gridX, fr.X, fr.kthX, fr.p, fr.gp, prm.lambda_gas_constraints, 0),
-                                                 (fr.gridY, fr.Y, fr.kthY, fr.pn, fr.gpn, prm.lambda_next_gas_constraints, 1)):
+                                     prm.buoyancy_max_y, prm.scale_factor, fr.X.data_ptr(), fr.Y.data_ptr() if physics else None, st))
+        sets = ((fr.gridX, fr.X, fr.kthX, fr.p, fr.gp, prm.lambda_gas_constraints, 0),
+                (fr.gridY, fr.Y, fr.kthY, fr.pn, fr.gpn, prm.lambda_next_gas_constraints, 1))
+        for grid, pos, kth, p, gp, lam, slot in (sets if physics else sets[:1]):
             ck(lib.fnx_grid_build(pos.data_ptr(), N, prm.H, grid.data_ptr(), st))
+            if not physics:
+                break
             ck(lib.fnx_radius_count(grid.data_ptr(), N, prm.H, pos.data_ptr(), N, prm.H, prm.KNN_K, None, kth.data_ptr(), st))
             ck(lib.fnx_pbf_density_fwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
                                        p.data_ptr(), st))
             ck(lib.fnx_pbf_ratio_loss(N, p.data_ptr(), lam, fr.scalars[slot:].data_ptr(), gp.data_ptr(), st))
-        ck(lib.fnx_pbf_density_bwd(fr.gridX.data_ptr(), fr.X.data_ptr(), N, fr.imass.data_ptr(), fr.kthX.data_ptr(), prm.H, prm.p0,
-                                   fr.gp.data_ptr(), fr.dX.data_ptr(), 0, st))
-        ck(lib.fnx_pbf_density_bwd(fr.gridY.data_ptr(), fr.Y.data_ptr(), N, fr.imass.data_ptr(), fr.kthY.data_ptr(), prm.H, prm.p0,
-                                   fr.gpn.data_ptr(), fr.dY.data_ptr(), 0, st))
+        if physics:
+            ck(lib.fnx_pbf_density_bwd(fr.gridX.data_ptr(), fr.X.data_ptr(), N, fr.imass.data_ptr(), fr.kthX.data_ptr(), prm.H, prm.p0,
+                                       fr.gp.data_ptr(), fr.dX.data_ptr(), 0, st))
+            ck(lib.fnx_pbf_density_bwd(fr.gridY.data_ptr(), fr.Y.data_ptr(), N, fr.imass.data_ptr(), fr.kthY.data_ptr(), prm.H, prm.p0,
+                                       fr.gpn.data_ptr(), fr.dY.data_ptr(), 0, st))
+        else:
+            fr.dX.zero_()
+            fr.scalars.zero_()
         # P1 forward straight into the fluid rows of the rasterizer's means3D (render units)
         ck(lib.fnx_radius_count(fr.gridX.data_ptr(), N, prm.H, fr.visual.data_ptr(), V, prm.H, prm.KNN_K, None, fr.kthV.data_ptr(), st))
         ck(lib.fnx_visual_advect_fwd(fr.gridX.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, fr.visual.data_ptr(), V,
                                      fr.kthV.data_ptr(), prm.H, prm.secs, prm.scale_factor, fr.means3D.data_ptr(), fr.num.data_ptr(),
                                      fr.den.data_ptr(), st))
         # P5 on the render-unit positions
-        if prm.lambda_current_distance > 0:
+        if prm.lambda_current_distance > 0 and physics:
             thr = prm.distance_threshold_visual
             ck(lib.fnx_grid_build(fr.means3D.data_ptr(), V, thr, fr.gridP.data_ptr(), st))
             ck(lib.fnx_pair_distance_loss(fr.gridP.data_ptr(), fr.means3D.data_ptr(), V, thr, thr, prm.lambda_current_distance,
@@ -203,7 +212,7 @@ class PhysicalStep:
                                    l1.data_ptr(), ss.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
         return l1, ss, g
 
-    def physics_backward_and_update(self, fr: FrameState, dL_dmeans3D, grad_extra=None, update=True):
+    def physics_backward_and_update(self, fr: FrameState, dL_dmeans3D, grad_extra=None, update=True, physics=True):
         """P1-backward (image + distance gradients -> hidden particles), P3 chain, P4, Adam."""
         lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
         N, V = fr.N, fr.V
@@ -212,8 +221,9 @@ class PhysicalStep:
                                      fr.den.data_ptr(), dL_dmeans3D.data_ptr(), fr.dDist.data_ptr(), 1.0 / prm.scale_factor, prm.H,
                                      prm.secs, fr.dX.data_ptr(), 1, st))
         ck(lib.fnx_pbf_combine_grad(N, fr.e.data_ptr(), fr.buoyancy.data_ptr(), prm.secs, prm.buoyancy_max_y, prm.scale_factor,
-                                    fr.dX.data_ptr(), fr.dY.data_ptr(), fr.estimate_xyz.data_ptr(), prm.lambda_exyz, fr.de.data_ptr(),
-                                    fr.scalars[2:].data_ptr(), st))
+                                    fr.dX.data_ptr(), fr.dY.data_ptr() if physics else None,
+                                    fr.estimate_xyz.data_ptr() if physics else None, prm.lambda_exyz, fr.de.data_ptr(),
+                                    fr.scalars[2:].data_ptr() if physics else None, st))
         if grad_extra is not None:
             fr.de.add_(grad_extra)
         if update:
@@ -226,8 +236,8 @@ class PhysicalStep:
                                            torch.cuda.current_stream(self.dev).cuda_stream))
 
     # -- the step -------------------------------------------------------------------------------------------
-    def _iteration(self, fr: FrameState, view_ids, gt, update, batch):
-        self.physics_forward(fr)
+    def _iteration(self, fr: FrameState, view_ids, gt, update, batch, physics=True):
+        self.physics_forward(fr, physics)
         out = {}
         if len(view_ids):
             ws = self.render(fr, view_ids)
@@ -238,14 +248,15 @@ class PhysicalStep:
             if fr.zero_dmeans is None:
                 fr.zero_dmeans = torch.zeros((fr.P, 3), device=self.dev)
             dmeans = fr.zero_dmeans
-        self.physics_backward_and_update(fr, dmeans, update=update)
+        self.physics_backward_and_update(fr, dmeans, update=update, physics=physics)
         out.update(gas=fr.scalars[0], next_gas=fr.scalars[1], exyz=fr.scalars[2], dist=fr.scalars[3], grad=fr.de)
         return out
 
-    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None, graph=False):
+    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None, graph=False, physics=True):
         """One optimiser iteration for one frame.  view_ids: camera indices rendered by THIS process; gt
         [len(view_ids),C,H,W] (device tensor, or a pinned host tensor); `batch` = global number of views of the step
-        (defaults to len(view_ids); larger when views are sharded over ranks).  graph=True captures the iteration
+        (defaults to len(view_ids); larger when views are sharded over ranks); physics=False skips the
+        view-independent terms (another rank owns them).  graph=True captures the iteration
         into a CUDA graph on first use and replays it afterwards (one host call per iteration).
         Returns device tensors that are overwritten by the next step; there is no host synchronisation."""
         batch = len(view_ids) if batch is None else batch
@@ -253,21 +264,21 @@ class PhysicalStep:
             if not graph:
                 if not gt.is_cuda:
                     gt = gt.to(self.dev, non_blocking=True)
-                return self._iteration(fr, view_ids, gt, update, batch)
-            key = (tuple(view_ids), bool(update), batch)
+                return self._iteration(fr, view_ids, gt, update, batch, physics)
+            key = (tuple(view_ids), bool(update), batch, bool(physics))
             ent = fr.graphs.get(key)
             if ent is None:
                 # everything that allocates or blocks happens eagerly first (workspace sizing, visual grid, scratch)
                 gt_buf = torch.empty((len(view_ids), self.C, self.H, self.W), device=self.dev)
                 gt_buf.copy_(gt, non_blocking=True)
                 snap = (fr.e.clone(), fr.m.clone(), fr.v.clone(), fr.step_dev.clone())
-                self._iteration(fr, view_ids, gt_buf, update, batch)         # eager warm-up (also sizes the workspace)
+                self._iteration(fr, view_ids, gt_buf, update, batch, physics)  # eager warm-up (also sizes the workspace)
                 for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # undo its parameter update
                     dst.copy_(src)
                 torch.cuda.synchronize(self.dev)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    out = self._iteration(fr, view_ids, gt_buf, update, batch)
+                    out = self._iteration(fr, view_ids, gt_buf, update, batch, physics)
                 ent = (g, out, gt_buf)
                 fr.graphs[key] = ent
                 for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # capture does not execute, but be explicit

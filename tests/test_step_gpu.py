@@ -113,3 +113,17 @@ def test_cuda_graph_replay_equals_eager(libfnx):
     assert res["eager"][2] == res["graph"][2] == 6
     assert np.allclose(res["eager"][0], res["graph"][0], rtol=1e-5)
     assert (res["eager"][1] - res["graph"][1]).abs().max() < 1e-6
+
+
+def test_view_sharded_gradients_sum_to_the_full_step(libfnx):
+    """What the all-reduce adds up: a rank rendering views {0,1,2} and owning the frame's physics terms plus a rank
+    rendering views {3,4} without them give the full 5-view gradient (P1's backward is linear in dL/dmeans3D)."""
+    hp, vis, fluid, bg, cams = _scene(3, True, seed=6)
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    ps = PhysicalStep(cams, 3, prm)
+    gt = torch.rand(5, 3, 64, 64, generator=torch.Generator().manual_seed(2)).cuda() * 0.5
+    full = ps.step(FrameState(hp, vis, fluid, bg, prm=prm), [0, 1, 2, 3, 4], gt, update=False)["grad"].clone()
+    a = ps.step(FrameState(hp, vis, fluid, bg, prm=prm), [0, 1, 2], gt[:3], update=False, batch=5, physics=True)["grad"].clone()
+    b = ps.step(FrameState(hp, vis, fluid, bg, prm=prm), [3, 4], gt[3:], update=False, batch=5, physics=False)["grad"].clone()
+    r = ((a + b) - full).norm() / full.norm()
+    assert r < 1e-5, r
