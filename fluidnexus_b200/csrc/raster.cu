@@ -487,12 +487,15 @@ __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co,
     // axis-aligned extent of the ellipse q <= tau: |ux| <= sqrt(2 tau c / det), |uy| <= sqrt(2 tau a / det)
     const float det = tc.a * tc.c - tc.b * tc.b;
     const float hx = sqrtf(2.f * tc.tau * tc.c / det) * 1.0001f + 0.01f, hy = sqrtf(2.f * tc.tau * tc.a / det) * 1.0001f + 0.01f;
+    // splats much larger than a patch touch (almost) every patch their bounding box overlaps: the exact test is
+    // only worth its cost for small ones (any superset of the true mask is correct)
+    const bool exact = fmaxf(hx, hy) < 10.f;
     uint32_t m = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         const int bx = tx * TILE + (w & 1) * 8, by = ty * TILE + (w >> 1) * 4;
         const bool bbox = (xy.x + hx >= bx) && (xy.x - hx <= bx + 7) && (xy.y + hy >= by) && (xy.y - hy <= by + 3);
-        if (bbox && box_needed(tc, xy, bx, by, 8, 4)) m |= 1u << w;
+        if (bbox && (!exact || box_needed(tc, xy, bx, by, 8, 4))) m |= 1u << w;
     }
     return m;
 }
@@ -875,7 +878,10 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     slot_bits = __float_as_uint(r1.w) & slot_mask;
                 }
                 if (contrib) {
-                    T = T / (1.f - alpha);
+                    // one approximate reciprocal (MUFU.RCP, 1-alpha is in [0.01, 1)) replaces the reference's two IEEE
+                    // divisions (backward.cu:484,513): ~2 ulp per step, far inside the gradient tolerance
+                    const float inv_1ma = __fdividef(1.f, 1.f - alpha);
+                    T = T * inv_1ma;
                     const float dchannel_dcolor = alpha * T;
                     float dL_dalpha = 0.0f;
 #pragma unroll
@@ -888,7 +894,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                    dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
                     const float dL_dG = r1.y * dL_dalpha;
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * r0.z - gdy * r0.w;

@@ -106,7 +106,7 @@ class PhysicalStep:
     """step(frame, view_ids, gt) -> dict of device scalars.  `cams`: list of camera objects with the attributes of
     FD/scene/camera.py (world_view_transform, full_proj_transform, FoVx, FoVy, image_width, image_height)."""
 
-    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda"):
+    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda", overlap=True):
         import math
         self.prm = prm or StepParams()
         self.dev = torch.device(device)
@@ -120,52 +120,75 @@ class PhysicalStep:
         self._loss_scratch, self._views = {}, {}
         self.capacity_margin = 1.2   # binning capacity = margin * instances of the sizing forward + 64k
         self.lib = L.lib()
+        # the view-independent physics terms run on a side stream next to the rasterizer (fork/join with events, also
+        # inside a captured graph); overlap=False keeps everything on one stream
+        self.side = torch.cuda.Stream(device=self.dev) if overlap else None
+        self._ev_fork, self._ev_means, self._ev_join = (torch.cuda.Event() for _ in range(3))
+        self._side_pending = False
 
     # -- pieces ---------------------------------------------------------------------------------------------
     def physics_forward(self, fr: FrameState, physics=True):
-        """P2, P3, P1-forward, P5: fills fr.means3D[:V], fr.dX, fr.dY, fr.dDist and the loss scalars.
-        physics=False (a rank that renders some views of a frame whose view-independent terms another rank owns)
-        runs only P1, which the rasterizer needs."""
-        lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
+        """P1-forward on the current stream (the rasterizer needs its output) and, when physics=True, P2, P3 and P5
+        on a side stream that runs concurrently with the rasterizer (joined in physics_backward_and_update).
+        Fills fr.means3D[:V], fr.dX, fr.dY, fr.dDist and the loss scalars.
+        physics=False: a rank that renders some views of a frame whose view-independent terms another rank owns."""
+        lib, prm = self.lib, self.prm
         N, V = fr.N, fr.V
         ck = L.check
+        main = torch.cuda.current_stream(self.dev)
+        st = main.cuda_stream
         ck(lib.fnx_pbf_next_tick_fwd(N, fr.e.data_ptr(), fr.xyz.data_ptr(), fr.buoyancy.data_ptr(), fr.force.data_ptr(), prm.secs,
                                      prm.buoyancy_max_y, prm.scale_factor, fr.X.data_ptr(), fr.Y.data_ptr() if physics else None, st))
-        sets = ((fr.gridX, fr.X, fr.kthX, fr.p, fr.gp, prm.lambda_gas_constraints, 0),
-                (fr.gridY, fr.Y, fr.kthY, fr.pn, fr.gpn, prm.lambda_next_gas_constraints, 1))
-        for grid, pos, kth, p, gp, lam, slot in (sets if physics else sets[:1]):
-            ck(lib.fnx_grid_build(pos.data_ptr(), N, prm.H, grid.data_ptr(), st))
-            if not physics:
-                break
-            ck(lib.fnx_radius_count(grid.data_ptr(), N, prm.H, pos.data_ptr(), N, prm.H, prm.KNN_K, None, kth.data_ptr(), st))
-            ck(lib.fnx_pbf_density_fwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
-                                       p.data_ptr(), st))
-            ck(lib.fnx_pbf_ratio_loss(N, p.data_ptr(), lam, fr.scalars[slot:].data_ptr(), gp.data_ptr(), st))
-        if physics:
-            ck(lib.fnx_pbf_density_bwd(fr.gridX.data_ptr(), fr.X.data_ptr(), N, fr.imass.data_ptr(), fr.kthX.data_ptr(), prm.H, prm.p0,
-                                       fr.gp.data_ptr(), fr.dX.data_ptr(), 0, st))
-            ck(lib.fnx_pbf_density_bwd(fr.gridY.data_ptr(), fr.Y.data_ptr(), N, fr.imass.data_ptr(), fr.kthY.data_ptr(), prm.H, prm.p0,
-                                       fr.gpn.data_ptr(), fr.dY.data_ptr(), 0, st))
-        else:
-            fr.dX.zero_()
-            fr.scalars.zero_()
+        ck(lib.fnx_grid_build(fr.X.data_ptr(), N, prm.H, fr.gridX.data_ptr(), st))
+        if not fr.vis_grid_built:  # the un-advected visual particles are constant within a frame
+            ck(lib.fnx_grid_build(fr.visual.data_ptr(), V, prm.H, fr.gridVis.data_ptr(), st))
+            fr.vis_grid_built = True
+        if physics and self.side is not None:
+            self._ev_fork.record(main)
         # P1 forward straight into the fluid rows of the rasterizer's means3D (render units)
         ck(lib.fnx_radius_count(fr.gridX.data_ptr(), N, prm.H, fr.visual.data_ptr(), V, prm.H, prm.KNN_K, None, fr.kthV.data_ptr(), st))
         ck(lib.fnx_visual_advect_fwd(fr.gridX.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, fr.visual.data_ptr(), V,
                                      fr.kthV.data_ptr(), prm.H, prm.secs, prm.scale_factor, fr.means3D.data_ptr(), fr.num.data_ptr(),
                                      fr.den.data_ptr(), st))
-        # P5 on the render-unit positions
-        if prm.lambda_current_distance > 0 and physics:
-            thr = prm.distance_threshold_visual
-            ck(lib.fnx_grid_build(fr.means3D.data_ptr(), V, thr, fr.gridP.data_ptr(), st))
-            ck(lib.fnx_pair_distance_loss(fr.gridP.data_ptr(), fr.means3D.data_ptr(), V, thr, thr, prm.lambda_current_distance,
-                                          fr.scalars[3:].data_ptr(), fr.dDist.data_ptr(), st))
-        else:
+        if not physics:
+            fr.dX.zero_()
             fr.dDist.zero_()
-            fr.scalars[3:].zero_()
-        if not fr.vis_grid_built:  # the un-advected visual particles are constant within a frame
-            ck(lib.fnx_grid_build(fr.visual.data_ptr(), V, prm.H, fr.gridVis.data_ptr(), st))
-            fr.vis_grid_built = True
+            fr.scalars.zero_()
+            return
+        if self.side is not None:
+            self._ev_means.record(main)
+            self.side.wait_event(self._ev_fork)
+            ctx = torch.cuda.stream(self.side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            for k, (grid, pos, kth, p, gp, lam, dpos) in enumerate((
+                    (fr.gridX, fr.X, fr.kthX, fr.p, fr.gp, prm.lambda_gas_constraints, fr.dX),
+                    (fr.gridY, fr.Y, fr.kthY, fr.pn, fr.gpn, prm.lambda_next_gas_constraints, fr.dY))):
+                if k == 1:
+                    ck(lib.fnx_grid_build(pos.data_ptr(), N, prm.H, grid.data_ptr(), st))
+                ck(lib.fnx_radius_count(grid.data_ptr(), N, prm.H, pos.data_ptr(), N, prm.H, prm.KNN_K, None, kth.data_ptr(), st))
+                ck(lib.fnx_pbf_density_fwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
+                                           p.data_ptr(), st))
+                ck(lib.fnx_pbf_ratio_loss(N, p.data_ptr(), lam, fr.scalars[k:].data_ptr(), gp.data_ptr(), st))
+                ck(lib.fnx_pbf_density_bwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
+                                           gp.data_ptr(), dpos.data_ptr(), 0, st))
+            # P5 on the render-unit positions written by P1
+            if prm.lambda_current_distance > 0:
+                if self.side is not None:
+                    self.side.wait_event(self._ev_means)
+                thr = prm.distance_threshold_visual
+                ck(lib.fnx_grid_build(fr.means3D.data_ptr(), V, thr, fr.gridP.data_ptr(), st))
+                ck(lib.fnx_pair_distance_loss(fr.gridP.data_ptr(), fr.means3D.data_ptr(), V, thr, thr, prm.lambda_current_distance,
+                                              fr.scalars[3:].data_ptr(), fr.dDist.data_ptr(), st))
+            else:
+                fr.dDist.zero_()
+                fr.scalars[3:].zero_()
+            if self.side is not None:
+                self._ev_join.record(self.side)
+        self._side_pending = self.side is not None
 
     def _view_mats(self, view_ids):
         key = tuple(view_ids)
@@ -217,6 +240,9 @@ class PhysicalStep:
         lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
         N, V = fr.N, fr.V
         ck = L.check
+        if self._side_pending:  # join the side stream: dX, dY, dDist and the loss scalars are complete after this
+            torch.cuda.current_stream(self.dev).wait_event(self._ev_join)
+            self._side_pending = False
         ck(lib.fnx_visual_advect_bwd(fr.gridVis.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, V, fr.kthV.data_ptr(), fr.num.data_ptr(),
                                      fr.den.data_ptr(), dL_dmeans3D.data_ptr(), fr.dDist.data_ptr(), 1.0 / prm.scale_factor, prm.H,
                                      prm.secs, fr.dX.data_ptr(), 1, st))

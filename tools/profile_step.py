@@ -44,7 +44,7 @@ def main():
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t0
         print(f"[{label}] per iteration: host queue {t_queue / iters * 1e3:.3f} ms, wall {t_wall / iters * 1e3:.3f} ms, "
-              f"GPU events {e0.elapsed_time(e1) / iters:.3f} ms, instances {out['num_rendered']}")
+              f"GPU events {e0.elapsed_time(e1) / iters:.3f} ms, instances {out['ws'].num_rendered()}")
         tot = (C.c_float * nsec)(); cnt = (C.c_int32 * nsec)()
         lib.fnx_profile_collect(tot, cnt)
         if mask:
