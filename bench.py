@@ -237,6 +237,11 @@ def run_fnx(args):
     acc = 48 if Cc == 3 else 32
     bytes_launch = R_per_iter * rec + len(views) * HW * (4 * Cc + 8) + len(views) * P * acc
     achieved = bytes_launch / t_launch / 1e9 if t_launch > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["blend_bwd_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": "FluidDynamics train-step iters/sec (render+physics+bwd)", "value": round(value, 3), "unit": "iters/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
@@ -254,10 +259,12 @@ def run_fnx(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 5), "traffic": traffic, "algorithmic_bytes_per_launch": int(bytes_launch),
+                     "peak_source": peak_src,
                      "ms_per_launch": round(t_launch * 1e3, 4), "launches_timed": int(n_launch),
                      "share_of_step": round(tot[ib] / sum(tot[i] for i in range(nsec)), 4),
-                     "note": "fp32 ALU / shuffle-issue bound blend loop on an L2-resident working set; see DESIGN.md"},
+                     "note": "instruction-issue bound (82 % issue-active, ncu) on an L2-resident working set: DRAM traffic is far "
+                             "BELOW the algorithmic bytes because the record stream is still in L2 from the pack kernel; see DESIGN.md 6"},
         "sections_ms_per_step": {names[i]: round(tot[i] / args.steps, 4) for i in range(nsec) if cnt[i]},
         "cuda_graph": bool(graph_flag),
     }
@@ -340,6 +347,20 @@ def run_reference(args):
     dt = time.time() - t0
     value = K / dt
     P = cfg["nf"] + cfg["nb"]
+    # extra information: the GPU-only part of the reference iteration (its CUDA rasterizer fwd+bwd + torch image losses,
+    # 5 views), CUDA-event timed -- the part that libfnx's rasterizer and loss kernels replace one for one
+    gts_gpu = [g.to(dev) for g in gts]
+    rx = torch.tensor(fr["fluid"].xyz, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        tr.gpu_part(cams, gts_gpu, rx)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        tr.gpu_part(cams, gts_gpu, rx)
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_part_ms = e0.elapsed_time(e1) / 10
     line = {
         "impl": "reference", "metric": "FluidDynamics train-step iters/sec (render+physics+bwd)", "value": round(value, 4),
         "unit": "iters/s", "n_gpus": 1, "steps": K, "warmup": min(W, 2), "ms_per_step": round(dt / K * 1e3, 2),
@@ -353,6 +374,7 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 4), "unit": "iters/s", "cores": ncores, "kind": "reference",
                          "sample": f"{K} full iterations (5 views each) of one frame"},
         "e2e": {"value": round(value, 4), "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_gpu_part_ms_per_iteration": round(gpu_part_ms, 3),
     }
     print(json.dumps(line), flush=True)
 

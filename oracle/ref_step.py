@@ -73,6 +73,16 @@ class ReferenceTrainer:
                                                 cam.full_proj_transform, tfx, tfy, int(cam.image_height), int(cam.image_width))
         return img
 
+    def gpu_part(self, cams, gts_gpu, render_xyz_gpu):
+        """Only what the reference runs on the GPU for one iteration: per view render + image loss + backward to the
+        Gaussian means (no host physics, no .item()): the tightest comparison with libfnx's rasterizer + loss kernels."""
+        leaf = render_xyz_gpu.detach().clone().requires_grad_(True)
+        for cam, gt in zip(cams, gts_gpu):
+            image = self.render(cam, leaf)
+            img_loss, l1, ss = O.image_loss(self.prm, image, gt, grey=self.grey)
+            img_loss.backward()
+        return leaf.grad
+
     def iteration(self, cams, gts_cpu, with_distance=True, do_step=True):
         prm, st = self.prm, self.st
         batch = len(cams)

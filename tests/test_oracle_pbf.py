@@ -87,3 +87,21 @@ def test_physics_loss_terms_backward_runs():
     total.backward()
     assert torch.isfinite(e.grad).all() and e.grad.abs().sum() > 0
     assert p.shape == (216, 1) and render_xyz.shape == (30, 3)
+
+
+def test_kdtree_radius_path_equals_literal_scan():
+    """oracle.radius switches to a k-d tree candidate search for large inputs; both paths must give the same edges,
+    including under a binding max_num_neighbors cap."""
+    rng = np.random.default_rng(3)
+    x = torch.tensor(rng.uniform(0, 6, (900, 3)), dtype=torch.float32)
+    y = torch.tensor(rng.uniform(0, 6, (700, 3)), dtype=torch.float32)   # 630k pairs > literal-scan limit
+    for K in (100, 5):
+        got = O.radius(x, y, 2.0, K)
+        rows, cols = [], []
+        xn, yn = x.numpy(), y.numpy()
+        for c in range(yn.shape[0]):
+            d = ((xn - yn[c]) ** 2).sum(1, dtype=np.float32)
+            hit = np.nonzero(d < np.float32(4.0))[0][:K]
+            rows += [c] * len(hit)
+            cols += hit.tolist()
+        assert got.tolist() == [rows, cols]
