@@ -477,12 +477,19 @@ emit_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict
 // ---------------------------------------------------------------------------------------------------------------
 // K6: pack the sorted instances into the record stream + per-tile ranges (identifyTileRanges, rasterizer_impl.cu:109-128)
 // ---------------------------------------------------------------------------------------------------------------
-// Sub-tile mask: bit w set <=> the 8x4 pixel patch of warp w can receive a contribution from this instance.  The blend
-// kernels iterate only over the set bits of their own patch (a small splat touches 1-2 of a tile's 8 patches).
+// Sub-tile mask: bit w set <=> the 8x8 pixel patch of warp w can receive a contribution from this instance.  The blend
+// kernels iterate only over the set bits of their own patch (a small splat touches 1-2 of a tile's 4 patches).
 constexpr uint32_t SLOT_BITS = 24;  // slot id lives in the low 24 bits of the record's slot word when it fits
+// Blend kernels: a warp owns an 8x8 pixel patch of the tile and every thread blends PPT = 2 pixels of it, (lx, ly) and
+// (lx, ly + 4): the per-record costs that do not depend on the pixel (record loads, bit iteration, the warp reduction of
+// the backward) are paid once per 64 pixels.  4 warps = 128 threads per tile.
+constexpr int PPT = 2;
+constexpr int PATCH = 8;
+constexpr int BLEND_WARPS = (TILE / PATCH) * (TILE / PATCH);  // 4
+constexpr int BLEND_THREADS = BLEND_WARPS * 32;               // 128
 __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co, int tx, int ty, bool exact_rect) {
     const TileCull tc = make_cull(co, exact_rect);
-    if (!tc.active) return 0xFFu;
+    if (!tc.active) return (1u << BLEND_WARPS) - 1u;
     if (tc.tau < 0.f) return 0u;
     // axis-aligned extent of the ellipse q <= tau: |ux| <= sqrt(2 tau c / det), |uy| <= sqrt(2 tau a / det)
     const float det = tc.a * tc.c - tc.b * tc.b;
@@ -492,10 +499,10 @@ __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co,
     const bool exact = fmaxf(hx, hy) < 10.f;
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const int bx = tx * TILE + (w & 1) * 8, by = ty * TILE + (w >> 1) * 4;
-        const bool bbox = (xy.x + hx >= bx) && (xy.x - hx <= bx + 7) && (xy.y + hy >= by) && (xy.y - hy <= by + 3);
-        if (bbox && (!exact || box_needed(tc, xy, bx, by, 8, 4))) m |= 1u << w;
+    for (int w = 0; w < BLEND_WARPS; w++) {
+        const int bx = tx * TILE + (w & 1) * PATCH, by = ty * TILE + (w >> 1) * PATCH;
+        const bool bbox = (xy.x + hx >= bx) && (xy.x - hx <= bx + PATCH - 1) && (xy.y + hy >= by) && (xy.y - hy <= by + PATCH - 1);
+        if (bbox && (!exact || box_needed(tc, xy, bx, by, PATCH, PATCH))) m |= 1u << w;
     }
     return m;
 }
@@ -561,7 +568,8 @@ constexpr int BATCH = 128;  // records per smem stage
 constexpr int STAGES = 2;
 
 // ---------------------------------------------------------------------------------------------------------------
-// K7: blend forward.  One CTA per (tile, view); warp w owns the 8x4 pixel patch (w&1, w>>1).  forward.cu:249-373
+// K7: blend forward.  One CTA (4 warps) per (tile, view); warp w owns the 8x8 pixel patch (w&1, w>>1), 2 pixels per
+// thread.  forward.cu:249-373
 // ---------------------------------------------------------------------------------------------------------------
 // slot word of record j (slot id in the low SLOT_BITS bits, patch mask above when use_mask)
 template <int C>
@@ -582,7 +590,7 @@ __device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int w
 }
 
 template <int C>
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(BLEND_THREADS)
 blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records,
                  const float *__restrict__ depth_of_slot, const float *__restrict__ bg, const GeomHeader *__restrict__ hdr,
                  ImageView im, float *__restrict__ out_color, float *__restrict__ out_depth) {
@@ -594,13 +602,25 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const int ntiles = gx * gy;
     const int tx = tile % gx, ty = tile / gx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
+    const int px = tx * TILE + (warp & 1) * PATCH + (lane & 7);
+    const int py0 = ty * TILE + (warp >> 1) * PATCH + (lane >> 3);  // pixel p of this thread is (px, py0 + 4p)
+    const float pxf = (float)px;
     const size_t HW = (size_t)W * H;
-    const size_t pix_id = (size_t)v * HW + (size_t)py * W + px;
     const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
+    bool inside[PPT], done[PPT];
+    float pyf[PPT], T[PPT], D[PPT], Cacc[PPT][C];
+    uint32_t last_contributor[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+        inside[p] = px < W && (py0 + 4 * p) < H;
+        done[p] = !inside[p];
+        pyf[p] = (float)(py0 + 4 * p);
+        T[p] = 1.0f;
+        D[p] = DEPTH_DEFAULT;
+        last_contributor[p] = 0;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) Cacc[p][ch] = 0.f;
+    }
 
     uint2 range = im.ranges[(size_t)v * ntiles + tile];
     if (hdr->overflow) range = make_uint2(0, 0);
@@ -623,20 +643,15 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
             }
     }
 
-    float T = 1.0f;
-    float Cacc[C];
-#pragma unroll
-    for (int ch = 0; ch < C; ch++) Cacc[ch] = 0.f;
-    float D = DEPTH_DEFAULT;
-    uint32_t last_contributor = 0;
-    bool done = !inside;
-
     int issued = min(STAGES, nbatch);  // batches whose copy has been issued (meaningful in thread 0)
     int bi = 0;
     for (; bi < nbatch; bi++) {
         const int s = bi % STAGES;
+        bool all_done = true;
+#pragma unroll
+        for (int p = 0; p < PPT; p++) all_done = all_done && done[p];
         // whole tile finished?  (also orders the previous stage's reads before its buffer is refilled)
-        if (__syncthreads_count(done) == TILE_PIX) break;
+        if (__syncthreads_count(all_done) == BLEND_THREADS) break;
         if (threadIdx.x == 0 && bi >= 1 && bi + STAGES - 1 < nbatch) {
             // refill the stage consumed in the previous iteration
             const int nb = bi + STAGES - 1, ns = nb % STAGES;
@@ -648,7 +663,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         mbar_wait(&s_bar[s], (bi / STAGES) & 1);
         const int n = min(BATCH, total - bi * BATCH);
         const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
-        if (__all_sync(0xffffffffu, done)) continue;  // this warp's patch is finished
+        if (__all_sync(0xffffffffu, all_done)) continue;  // this warp's patch is finished
         uint32_t words[BATCH / 32];
         warp_record_mask<C>(rec, n, warp, lane, use_mask, words);
 #pragma unroll
@@ -657,28 +672,31 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
             while (w) {
                 const int j = k * 32 + __ffs(w) - 1;
                 w &= w - 1;
-                if (done) continue;
                 const float4 r0 = rec[j * (REC / 16)];
                 const float4 r1 = rec[j * (REC / 16) + 1];
-                float dx, dy, G, alpha;
-                if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf, dx, dy, G, alpha)) continue;
-                const float test_T = T * (1 - alpha);
-                if (test_T < T_EPS) {
-                    done = true;
-                    continue;
+#pragma unroll
+                for (int p = 0; p < PPT; p++) {
+                    if (done[p]) continue;
+                    float dx, dy, G, alpha;
+                    if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx, dy, G, alpha)) continue;
+                    const float test_T = T[p] * (1 - alpha);
+                    if (test_T < T_EPS) {
+                        done[p] = true;
+                        continue;
+                    }
+                    if (C == 3) {
+                        const float4 r2 = rec[j * 3 + 2];
+                        Cacc[p][0] += r1.z * alpha * T[p];
+                        Cacc[p][1 % C] += r1.w * alpha * T[p];
+                        Cacc[p][2 % C] += r2.x * alpha * T[p];
+                        if (T[p] > 0.5f && test_T < 0.5) D[p] = r2.z;
+                    } else {
+                        Cacc[p][0] += r1.z * alpha * T[p];
+                        if (T[p] > 0.5f && test_T < 0.5) D[p] = depth_of_slot[__float_as_uint(r1.w) & slot_mask];
+                    }
+                    T[p] = test_T;
+                    last_contributor[p] = (uint32_t)(bi * BATCH + j + 1);
                 }
-                if (C == 3) {
-                    const float4 r2 = rec[j * 3 + 2];
-                    Cacc[0] += r1.z * alpha * T;
-                    Cacc[1 % C] += r1.w * alpha * T;
-                    Cacc[2 % C] += r2.x * alpha * T;
-                    if (T > 0.5f && test_T < 0.5) D = r2.z;
-                } else {
-                    Cacc[0] += r1.z * alpha * T;
-                    if (T > 0.5f && test_T < 0.5) D = depth_of_slot[__float_as_uint(r1.w) & slot_mask];
-                }
-                T = test_T;
-                last_contributor = (uint32_t)(bi * BATCH + j + 1);
             }
         }
     }
@@ -688,23 +706,28 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         for (int nb = bi; nb < issued; nb++) mbar_wait(&s_bar[nb % STAGES], (nb / STAGES) & 1);
 
     // tile-wide max of last_contributor: where the backward starts
-    uint32_t wl = last_contributor;
+    uint32_t wl = 0;
+#pragma unroll
+    for (int p = 0; p < PPT; p++) wl = max(wl, last_contributor[p]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-    __shared__ uint32_t s_last[TILE_PIX / 32];
+    __shared__ uint32_t s_last[BLEND_WARPS];
     if (lane == 0) s_last[warp] = wl;
-    if (inside) {
-        im.final_T[pix_id] = T;
-        im.n_contrib[pix_id] = last_contributor;
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) out_color[((size_t)v * C + ch) * HW + (size_t)py * W + px] = Cacc[ch] + T * bg[ch];
-        out_depth[pix_id] = D;
+    for (int p = 0; p < PPT; p++) {
+        if (!inside[p]) continue;
+        const size_t pix = (size_t)(py0 + 4 * p) * W + px;
+        im.final_T[(size_t)v * HW + pix] = T[p];
+        im.n_contrib[(size_t)v * HW + pix] = last_contributor[p];
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) out_color[((size_t)v * C + ch) * HW + pix] = Cacc[p][ch] + T[p] * bg[ch];
+        out_depth[(size_t)v * HW + pix] = D[p];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t m = 0;
 #pragma unroll
-        for (int w = 0; w < TILE_PIX / 32; w++) m = max(m, s_last[w]);
+        for (int w = 0; w < BLEND_WARPS; w++) m = max(m, s_last[w]);
         im.tile_last[(size_t)v * ntiles + tile] = m;
     }
 }
@@ -768,7 +791,7 @@ struct SplitReduce {
 // (their 6+C addresses are contiguous: 1-2 L2 sectors).
 // ---------------------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records, const float *__restrict__ bg,
                  const GeomHeader *__restrict__ hdr, ImageView im, const float *__restrict__ dL_dpixels,
                  float *__restrict__ accum) {
@@ -781,12 +804,10 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const int ntiles = gx * gy;
     const int tx = tile % gx, ty = tile / gx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
+    const int px = tx * TILE + (warp & 1) * PATCH + (lane & 7);
+    const int py0 = ty * TILE + (warp >> 1) * PATCH + (lane >> 3);
+    const float pxf = (float)px;
     const size_t HW = (size_t)W * H;
-    const size_t pix_id = (size_t)v * HW + (size_t)py * W + px;
     const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
 
     const uint2 range = im.ranges[(size_t)v * ntiles + tile];
@@ -815,22 +836,32 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     using Red = SplitReduce<NV, 16>;
     const int my_val = ((lane & Red::dup_mask()) == 0) ? Red::index(lane) : -1;  // which reduced value this lane publishes
 
-    const float T_final = inside ? im.final_T[pix_id] : 0.f;
-    float T = T_final;
-    const int last_contributor = inside ? (int)im.n_contrib[pix_id] : 0;
-    int warp_last = last_contributor;  // records at or beyond this position touch no pixel of this warp
+    float pyf[PPT], T_final[PPT], T[PPT], last_alpha[PPT], bg_dot_dpixel[PPT];
+    float accum_rec[PPT][C], dL_dpixel[PPT][C], last_color[PPT][C];
+    int last_contributor[PPT];
+    int warp_last = 0;  // records at or beyond this position touch no pixel of this warp
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+        const int py = py0 + 4 * p;
+        const bool inside = px < W && py < H;
+        const size_t pix = (size_t)py * W + px;
+        pyf[p] = (float)py;
+        T_final[p] = inside ? im.final_T[(size_t)v * HW + pix] : 0.f;
+        T[p] = T_final[p];
+        last_contributor[p] = inside ? (int)im.n_contrib[(size_t)v * HW + pix] : 0;
+        warp_last = max(warp_last, last_contributor[p]);
+        last_alpha[p] = 0.f;
+        bg_dot_dpixel[p] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) {
+            accum_rec[p][ch] = 0.f;
+            last_color[p][ch] = 0.f;
+            dL_dpixel[p][ch] = inside ? dL_dpixels[((size_t)v * C + ch) * HW + pix] : 0.f;
+            bg_dot_dpixel[p] += bg[ch] * dL_dpixel[p][ch];
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    float accum_rec[C], dL_dpixel[C], last_color[C];
-    float bg_dot_dpixel = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < C; ch++) {
-        accum_rec[ch] = 0.f;
-        last_color[ch] = 0.f;
-        dL_dpixel[ch] = inside ? dL_dpixels[((size_t)v * C + ch) * HW + (size_t)py * W + px] : 0.f;
-        bg_dot_dpixel += bg[ch] * dL_dpixel[ch];
-    }
-    float last_alpha = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
     for (int bi = 0; bi < nbatch; bi++) {
@@ -860,9 +891,16 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                 const int idx = lo + j;  // 0-based position in the tile's span
                 const float4 r0 = rec[j * (REC / 16)];
                 const float4 r1 = rec[j * (REC / 16) + 1];
-                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-                const bool contrib = (idx < last_contributor) && pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf, dx, dy, G, alpha);
-                if (!__any_sync(0xffffffffu, contrib)) continue;
+                float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
+                bool contrib[PPT], any = false;
+#pragma unroll
+                for (int p = 0; p < PPT; p++) {
+                    dx[p] = dy[p] = G[p] = alpha[p] = 0.f;
+                    contrib[p] = (idx < last_contributor[p]) &&
+                                 pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx[p], dy[p], G[p], alpha[p]);
+                    any = any || contrib[p];
+                }
+                if (!__any_sync(0xffffffffu, any)) continue;
 
                 float vals[NV];
 #pragma unroll
@@ -877,34 +915,36 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     col[0] = r1.z;
                     slot_bits = __float_as_uint(r1.w) & slot_mask;
                 }
-                if (contrib) {
+#pragma unroll
+                for (int p = 0; p < PPT; p++) {
+                    if (!contrib[p]) continue;
                     // one approximate reciprocal (MUFU.RCP, 1-alpha is in [0.01, 1)) replaces the reference's two IEEE
                     // divisions (backward.cu:484,513): ~2 ulp per step, far inside the gradient tolerance
-                    const float inv_1ma = __fdividef(1.f, 1.f - alpha);
-                    T = T * inv_1ma;
-                    const float dchannel_dcolor = alpha * T;
+                    const float inv_1ma = __fdividef(1.f, 1.f - alpha[p]);
+                    T[p] = T[p] * inv_1ma;
+                    const float dchannel_dcolor = alpha[p] * T[p];
                     float dL_dalpha = 0.0f;
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
                         const float c = col[ch];
-                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                        last_color[ch] = c;
-                        dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
-                        vals[6 + ch] = dchannel_dcolor * dL_dpixel[ch];
+                        accum_rec[p][ch] = last_alpha[p] * last_color[p][ch] + (1.f - last_alpha[p]) * accum_rec[p][ch];
+                        last_color[p][ch] = c;
+                        dL_dalpha += (c - accum_rec[p][ch]) * dL_dpixel[p][ch];
+                        vals[6 + ch] += dchannel_dcolor * dL_dpixel[p][ch];
                     }
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
+                    dL_dalpha *= T[p];
+                    last_alpha[p] = alpha[p];
+                    dL_dalpha += (-T_final[p] * inv_1ma) * bg_dot_dpixel[p];
                     const float dL_dG = r1.y * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
+                    const float gdx = G[p] * dx[p], gdy = G[p] * dy[p];
                     const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
                     const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                    vals[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    vals[1] = dL_dG * dG_ddely * ddely_dy;
-                    vals[2] = -0.5f * gdx * dx * dL_dG;
-                    vals[3] = -0.5f * gdx * dy * dL_dG;
-                    vals[4] = -0.5f * gdy * dy * dL_dG;
-                    vals[5] = G * dL_dalpha;
+                    vals[0] += dL_dG * dG_ddelx * ddelx_dx;
+                    vals[1] += dL_dG * dG_ddely * ddely_dy;
+                    vals[2] += -0.5f * gdx * dx[p] * dL_dG;
+                    vals[3] += -0.5f * gdx * dy[p] * dL_dG;
+                    vals[4] += -0.5f * gdy * dy[p] * dL_dG;
+                    vals[5] += G[p] * dL_dalpha;
                 }
                 const float red = Red::run(vals, lane);
                 if (my_val >= 0) red_add(accum + (size_t)slot_bits * ACC + my_val, red);
@@ -1147,7 +1187,7 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
     }
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, g.depth, a->bg,
+    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, g.depth, a->bg,
                                                    g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
@@ -1297,7 +1337,7 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_BWD, st);
-    blend_bwd_kernel<C><<<grid, TILE_PIX, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, a->bg, g.hdr, im,
+    blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, a->bg, g.hdr, im,
                                                    dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
