@@ -25,7 +25,7 @@ class RasterArgs(C.Structure):
         ("view_matrix", C.c_void_p), ("proj_matrix", C.c_void_p), ("bg", C.c_void_p),
         ("tan_fov_x", C.c_float), ("tan_fov_y", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("flags", C.c_uint32), ("instance_capacity_hint", C.c_int64),
-        ("num_rendered_pinned", C.c_void_p),
+        ("num_rendered_pinned", C.c_void_p), ("grad_begin", C.c_int32), ("grad_end", C.c_int32),
     ]
 
 

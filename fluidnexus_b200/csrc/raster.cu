@@ -480,6 +480,7 @@ emit_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict
 // Sub-tile mask: bit w set <=> the 8x8 pixel patch of warp w can receive a contribution from this instance.  The blend
 // kernels iterate only over the set bits of their own patch (a small splat touches 1-2 of a tile's 4 patches).
 constexpr uint32_t SLOT_BITS = 24;  // slot id lives in the low 24 bits of the record's slot word when it fits
+constexpr uint32_t FROZEN_BIT = 1u << 31;  // record of a Gaussian that needs no gradient (fnx_raster_args.grad_begin/end)
 // Blend kernels: a warp owns an 8x8 pixel patch of the tile and every thread blends PPT = 2 pixels of it, (lx, ly) and
 // (lx, ly + 4): the per-record costs that do not depend on the pixel (record loads, bit iteration, the warp reduction of
 // the backward) are paid once per 64 pixels.  4 warps = 128 threads per tile.
@@ -509,8 +510,8 @@ __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co,
 
 template <int C>
 __global__ void __launch_bounds__(256)
-pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_mask, const float *__restrict__ colors, GeomView g,
-            BinView b, uint2 *__restrict__ ranges) {
+pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_mask, int grad_begin, int grad_end,
+            const float *__restrict__ colors, GeomView g, BinView b, uint2 *__restrict__ ranges) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long R = g.hdr->num_rendered;
     if (i >= R || i >= cap || g.hdr->overflow) return;
@@ -523,6 +524,7 @@ pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_
     if (use_mask) {
         const uint32_t tl = tile % (uint32_t)ntiles;
         slot |= patch_mask(xy, co, tl % gx, tl / gx, exact_rect) << SLOT_BITS;
+        if ((int)gi < grad_begin || (int)gi >= grad_end) slot |= FROZEN_BIT;
     }
     float4 *rec = reinterpret_cast<float4 *>(b.records + (size_t)i * RecBytes<C>::value);
     rec[0] = make_float4(xy.x, xy.y, co.x, co.y);
@@ -905,15 +907,31 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                 float vals[NV];
 #pragma unroll
                 for (int q = 0; q < NV; q++) vals[q] = 0.f;
-                uint32_t slot_bits;
+                uint32_t slot_word;
                 float col[C];
                 if (C == 3) {
                     const float4 r2 = rec[j * 3 + 2];
                     col[0] = r1.z; col[1 % C] = r1.w; col[2 % C] = r2.x;
-                    slot_bits = __float_as_uint(r2.y) & slot_mask;
+                    slot_word = __float_as_uint(r2.y);
                 } else {
                     col[0] = r1.z;
-                    slot_bits = __float_as_uint(r1.w) & slot_mask;
+                    slot_word = __float_as_uint(r1.w);
+                }
+                const uint32_t slot_bits = slot_word & slot_mask;
+                if (use_mask && (slot_word & FROZEN_BIT)) {
+                    // frozen Gaussian: it occludes (T, accumulated colour behind) but nobody wants its gradient
+#pragma unroll
+                    for (int p = 0; p < PPT; p++) {
+                        if (!contrib[p]) continue;
+                        T[p] = T[p] * __fdividef(1.f, 1.f - alpha[p]);
+#pragma unroll
+                        for (int ch = 0; ch < C; ch++) {
+                            accum_rec[p][ch] = last_alpha[p] * last_color[p][ch] + (1.f - last_alpha[p]) * accum_rec[p][ch];
+                            last_color[p][ch] = col[ch];
+                        }
+                        last_alpha[p] = alpha[p];
+                    }
+                    continue;
                 }
 #pragma unroll
                 for (int p = 0; p < PPT; p++) {
@@ -963,10 +981,29 @@ geom_bwd_kernel(int P, int V, const float *__restrict__ means3D, const float3 *_
                 const float4 *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                 const float *__restrict__ view_matrix, const float *__restrict__ proj_matrix, int W, int H,
                 float tan_fov_x, float tan_fov_y, float focal_x, float focal_y, const int *__restrict__ radii,
-                const float *__restrict__ cov3D_geom, const float *__restrict__ accum, fnx_raster_grads out) {
+                const float *__restrict__ cov3D_geom, const float *__restrict__ accum, int grad_begin, int grad_end,
+                fnx_raster_grads out) {
     constexpr int ACC = AccFloats<C>::value;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    if (i < grad_begin || i >= grad_end) {  // frozen: zero rows
+        if (out.dL_dmeans3D) { out.dL_dmeans3D[3 * i] = 0.f; out.dL_dmeans3D[3 * i + 1] = 0.f; out.dL_dmeans3D[3 * i + 2] = 0.f; }
+        if (out.dL_dmeans2D)
+            for (int v = 0; v < V; v++) {
+                const size_t sl = (size_t)v * P + i;
+                out.dL_dmeans2D[3 * sl] = 0.f; out.dL_dmeans2D[3 * sl + 1] = 0.f; out.dL_dmeans2D[3 * sl + 2] = 0.f;
+            }
+        if (out.dL_dopacity) out.dL_dopacity[i] = 0.f;
+        if (out.dL_dcolors)
+            for (int ch = 0; ch < C; ch++) out.dL_dcolors[(size_t)i * C + ch] = 0.f;
+        if (out.dL_dcov3D)
+            for (int k = 0; k < 6; k++) out.dL_dcov3D[6 * (size_t)i + k] = 0.f;
+        if (scales != nullptr) {
+            if (out.dL_dscales) { out.dL_dscales[3 * i] = 0.f; out.dL_dscales[3 * i + 1] = 0.f; out.dL_dscales[3 * i + 2] = 0.f; }
+            if (out.dL_drotations) *reinterpret_cast<float4 *>(out.dL_drotations + 4 * (size_t)i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
     const float3 mean = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
     const float *cov3D = (cov3D_precomp != nullptr ? cov3D_precomp : cov3D_geom) + 6 * (size_t)i;
     float c6[6];
@@ -1180,8 +1217,10 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
         prof_end(SEC_TILE_SORT, st);
         prof_begin(SEC_PACK, st);
         const bool use_mask = (long long)P * V < (1ll << SLOT_BITS);
-        pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, gx, ntiles, exact_rect, use_mask, a->colors, g, b,
-                                                                            im.ranges);
+        const bool all_grad = a->grad_end <= a->grad_begin;
+        pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, gx, ntiles, exact_rect, use_mask,
+                                                                            all_grad ? 0 : a->grad_begin, all_grad ? P : a->grad_end,
+                                                                            a->colors, g, b, im.ranges);
         prof_end(SEC_PACK, st);
         FNX_LAUNCH_CHECK("pack_kernel");
     }
@@ -1345,7 +1384,8 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     geom_bwd_kernel<C><<<(P + 255) / 256, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
                                                         (const float4 *)a->rotations, a->cov3D_precomp, a->view_matrix,
                                                         a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y,
-                                                        radii, g.cov3D, g.accum, *gr);
+                                                        radii, g.cov3D, g.accum, (a->grad_end <= a->grad_begin) ? 0 : a->grad_begin,
+                                                        (a->grad_end <= a->grad_begin) ? P : a->grad_end, *gr);
     prof_end(SEC_GEOM_BWD, st);
     FNX_LAUNCH_CHECK("geom_bwd_kernel");
     return FNX_OK;

@@ -64,7 +64,7 @@ _capacity_hint = {}
 
 def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_modifier, cov3D_precomp, view_matrix,
                    proj_matrix, tan_fov_x, tan_fov_y, H, W, sh=None, prefiltered=False, exact_rect=False,
-                   speculative=True):
+                   speculative=True, grad_range=None):
     """One forward through libfnx.  view_matrix/proj_matrix may be [4,4] (one camera, reference API) or
     [V,4,4] (V cameras batched into one launch sequence).  Returns (ctx, color, radii, depth) with shapes
     [C,H,W]/[P]/[1,H,W] for a single camera and [V,C,H,W]/[V,P]/[V,1,H,W] for a batch."""
@@ -106,6 +106,7 @@ def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_
         a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
         a.prefiltered = int(bool(prefiltered))
         a.flags = L.FNX_EXACT_RECT if exact_rect else 0
+        a.grad_begin, a.grad_end = (0, 0) if grad_range is None else (int(grad_range[0]), int(grad_range[1]))
         key = (dev.index, C_, V, W, H, P)
         a.instance_capacity_hint = _capacity_hint.get(key, 0) if speculative else 0
         bufs = (_Buf(dev), _Buf(dev), _Buf(dev))
@@ -185,7 +186,7 @@ class RasterWorkspace:
         return alloc
 
     def forward(self, bg, means3D, colors, opacities, scales, rotations, scale_modifier, view_matrix, proj_matrix, tan_fov_x,
-                tan_fov_y, exact_rect=False):
+                tan_fov_y, exact_rect=False, grad_range=None):
         """All tensors must be contiguous float32 CUDA tensors that stay alive and in place (graph replays read them)."""
         a = self.args
         a.P, a.V, a.C, a.W, a.H = self.P, self.V, self.C, self.W, self.H
@@ -195,6 +196,7 @@ class RasterWorkspace:
         a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
         a.prefiltered, a.flags = 0, L.FNX_NO_HOST_SYNC | (L.FNX_EXACT_RECT if exact_rect else 0)
         a.instance_capacity_hint, a.num_rendered_pinned = self.capacity, self.count.data_ptr()
+        a.grad_begin, a.grad_end = (0, 0) if grad_range is None else (int(grad_range[0]), int(grad_range[1]))
         self._keep = (bg, means3D, colors, opacities, scales, rotations, view_matrix, proj_matrix)
         nr = C.c_int64(0)
         fwd = L.lib().fnx_raster_forward_ch3 if self.C == 3 else L.lib().fnx_raster_forward_ch1

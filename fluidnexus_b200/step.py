@@ -217,7 +217,10 @@ class PhysicalStep:
     def render(self, fr: FrameState, view_ids):
         ws = self.workspace(fr, len(view_ids), view_ids)
         vm, pm = self._view_mats(view_ids)
-        ws.forward(self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, vm, pm, self.tan_fov_x, self.tan_fov_y)
+        # only the fluid rows [0, V) are trainable in the physical stage; the background set is frozen
+        # (pipe_dynamics.py:51-57 concatenates it behind the fluid particles) and needs no gradient
+        ws.forward(self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, vm, pm, self.tan_fov_x, self.tan_fov_y,
+                   grad_range=(0, fr.V) if fr.Pb > 0 else None)
         return ws
 
     def image_loss(self, images, gt, batch):

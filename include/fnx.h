@@ -89,6 +89,10 @@ typedef struct fnx_raster_args {
     int64_t instance_capacity_hint; /* 0 = size exactly (one host sync, like the reference) */
     int64_t *num_rendered_pinned;   /* optional PINNED HOST int64 the device writes the instance count to (it can be
                                        polled at any later time; with FNX_NO_HOST_SYNC it is the only read-back) */
+    int32_t grad_begin, grad_end;   /* Gaussians [grad_begin, grad_end) receive gradients in the backward; the others are
+                                       FROZEN (e.g. the background set that FD/renderer/pipe_dynamics.py:51-57 concatenates
+                                       behind the fluid particles): they still occlude, but their gradient rows are
+                                       written as zeros.  grad_end <= grad_begin means "all" (the reference's behaviour). */
 } fnx_raster_args;
 
 /* Opaque handles to the three scratch buffers of one forward (what the reference returns as

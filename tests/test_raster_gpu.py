@@ -202,3 +202,22 @@ def test_matches_compiled_reference_fixture(libfnx, path):
     for k in ("means2D", "colors", "opacity", "means3D", "scales", "rotations"):
         r = rel(g[k].cpu().numpy().reshape(z["g_" + k].shape), z["g_" + k])
         assert r < 1e-3, (k, r)
+
+
+def test_frozen_range_gives_identical_gradients_for_the_trainable_rows(libfnx):
+    """grad_begin/grad_end: frozen Gaussians still occlude; the trainable rows get exactly the gradients of a full
+    backward (to the rounding of float atomics), the frozen rows read zero."""
+    gs, cam, bg, inp = scenes.build("mixed_ch3_96")
+    P = inp["means3D"].shape[0]
+    nb = 1500  # the first 1500 (fluid) trainable, the background frozen
+    args = (3, _t(inp["bg"]), _t(inp["means3D"]), _t(inp["colors"]), _t(inp["opacities"]), _t(inp["scales"]), _t(inp["rotations"]),
+            1.0, None, _t(inp["view"]), _t(inp["proj"]), inp["tan_fov_x"], inp["tan_fov_y"], inp["H"], inp["W"])
+    c_all, col_all, _, _ = R.raster_forward(*args, speculative=False)
+    c_frz, col_frz, _, _ = R.raster_forward(*args, speculative=False, grad_range=(0, nb))
+    assert torch.equal(col_all, col_frz)
+    dL = _t(scenes.dL_dpix("mixed_ch3_96", tuple(col_all.shape)))
+    g_all, g_frz = R.raster_backward(c_all, dL), R.raster_backward(c_frz, dL)
+    for k in ("means3D", "means2D", "colors", "opacity", "scales", "rotations", "cov3D"):
+        a, f = g_all[k].reshape(P, -1), g_frz[k].reshape(P, -1)
+        assert rel(f[:nb].cpu().numpy(), a[:nb].cpu().numpy()) < 1e-5, k
+        assert torch.all(f[nb:] == 0), k
