@@ -197,7 +197,7 @@ def run_fnx(args):
     launches = launches_per_step * args.steps
     R_per_iter = float(out["ws"].num_rendered()) if out and "ws" in out else 0.0
     for f in mine:
-        assert not states[f].ws[len(by_frame[f])].overflowed(), "instance capacity overflow inside the timed region"
+        assert not any(w_.overflowed() for w_ in states[f].ws.values()), "instance capacity overflow inside the timed region"
     # ---- end to end: pinned host ground truth uploaded every iteration + loss read back every step ----
     for _ in range(2):
         one_step(True)

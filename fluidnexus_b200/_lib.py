@@ -13,6 +13,8 @@ FNX_OK = 0
 FNX_ERR_INVALID, FNX_ERR_CUDA, FNX_ERR_UNSUPPORTED, FNX_ERR_CAPACITY, FNX_ERR_ALLOC = 1, 2, 3, 4, 5
 FNX_NO_HOST_SYNC = 1
 FNX_EXACT_RECT = 2
+FNX_BIN_ONLY = 4
+FNX_ALL_FROZEN = 8
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -63,6 +65,9 @@ SYMBOLS = {
     "fnx_raster_binning_bytes": (_SZ, [_I64, _I]),
     "fnx_raster_forward": _FWD, "fnx_raster_forward_ch1": _FWD, "fnx_raster_forward_ch3": _FWD,
     "fnx_raster_backward": _BWD, "fnx_raster_backward_ch1": _BWD, "fnx_raster_backward_ch3": _BWD,
+    "fnx_raster_blend_merged": (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), C.POINTER(RasterScratch), _I, _V, _V, _V, _V]),
+    "fnx_raster_backward_merged": (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), C.POINTER(RasterScratch), _V, _V, _V,
+                                        C.POINTER(RasterGrads), _V]),
     "fnx_raster_check": (_I, [C.POINTER(RasterScratch), C.POINTER(_I64), _V]),
     "fnx_mark_visible": (_I, [_I, _V, _V, _V, _V, _V]),
     "fnx_grid_bytes": (_SZ, [_I]),

@@ -82,12 +82,14 @@ ImageView image_view(void *chunk, int W, int H, int V) {
     im.n_contrib = carve<uint32_t>(p, hw);
     im.ranges = carve<uint2>(p, nt);
     im.tile_last = carve<uint32_t>(p, nt);
+    im.mranges = carve<uint2>(p, nt);
+    im.tile_src = carve<uint32_t>(p, nt);
     return im;
 }
 size_t image_bytes(int W, int H, int V) {
     ImageView im = image_view((void *)0, W, H, V);
     size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
-    return (size_t)((char *)im.tile_last - (char *)0) + nt * 4 + 256;
+    return (size_t)((char *)im.tile_src - (char *)0) + nt * 4 + 256;
 }
 
 static size_t bin_cub_bytes(long long cap) {
@@ -406,6 +408,7 @@ __global__ void finish_scan_kernel(int n, GeomView g, long long capacity, long l
     g.hdr->num_rendered = total;
     g.hdr->capacity = capacity;
     g.hdr->overflow = (capacity >= 0 && total > capacity) ? 1 : 0;
+    g.hdr->merge_cursor = 0ull;
     if (pinned_out) *pinned_out = total;
 }
 
@@ -593,7 +596,8 @@ __device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int w
 
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS)
-blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records,
+blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
+                 const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
                  const float *__restrict__ depth_of_slot, const float *__restrict__ bg, const GeomHeader *__restrict__ hdr,
                  ImageView im, float *__restrict__ out_color, float *__restrict__ out_depth) {
     constexpr int REC = RecBytes<C>::value;
@@ -624,7 +628,8 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         for (int ch = 0; ch < C; ch++) Cacc[p][ch] = 0.f;
     }
 
-    uint2 range = im.ranges[(size_t)v * ntiles + tile];
+    uint2 range = ranges[(size_t)v * ntiles + tile];
+    const char *records = (tile_src != nullptr && tile_src[(size_t)v * ntiles + tile] != 0) ? records_static : records_own;
     if (hdr->overflow) range = make_uint2(0, 0);
     const int total = (int)(range.y - range.x);
     const int nbatch = (total + BATCH - 1) / BATCH;
@@ -794,9 +799,10 @@ struct SplitReduce {
 // ---------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS)
-blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records, const float *__restrict__ bg,
-                 const GeomHeader *__restrict__ hdr, ImageView im, const float *__restrict__ dL_dpixels,
-                 float *__restrict__ accum) {
+blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
+                 const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
+                 const float *__restrict__ bg, const GeomHeader *__restrict__ hdr, ImageView im,
+                 const float *__restrict__ dL_dpixels, float *__restrict__ accum) {
     constexpr int REC = RecBytes<C>::value;
     constexpr int ACC = AccFloats<C>::value;
     __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
@@ -812,7 +818,8 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const size_t HW = (size_t)W * H;
     const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
 
-    const uint2 range = im.ranges[(size_t)v * ntiles + tile];
+    const uint2 range = ranges[(size_t)v * ntiles + tile];
+    const char *records = (tile_src != nullptr && tile_src[(size_t)v * ntiles + tile] != 0) ? records_static : records_own;
     int total = (int)im.tile_last[(size_t)v * ntiles + tile];  // records [0,total) of the span matter
     if (hdr->overflow) total = 0;
     if (total == 0) return;
@@ -1217,17 +1224,20 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
         prof_end(SEC_TILE_SORT, st);
         prof_begin(SEC_PACK, st);
         const bool use_mask = (long long)P * V < (1ll << SLOT_BITS);
-        const bool all_grad = a->grad_end <= a->grad_begin;
+        const bool all_frozen = (a->flags & FNX_ALL_FROZEN) != 0;
+        const bool all_grad = !all_frozen && a->grad_end <= a->grad_begin;
         pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, gx, ntiles, exact_rect, use_mask,
-                                                                            all_grad ? 0 : a->grad_begin, all_grad ? P : a->grad_end,
-                                                                            a->colors, g, b, im.ranges);
+                                                                            all_grad ? 0 : (all_frozen ? 0 : a->grad_begin),
+                                                                            all_grad ? P : (all_frozen ? 0 : a->grad_end), a->colors, g, b,
+                                                                            im.ranges);
         prof_end(SEC_PACK, st);
         FNX_LAUNCH_CHECK("pack_kernel");
     }
+    if (a->flags & FNX_BIN_ONLY) return FNX_OK;  // the caller blends a merged stream (fnx_raster_blend_merged)
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, g.depth, a->bg,
-                                                   g.hdr, im, out_color, out_depth);
+    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr,
+                                                        im.ranges, nullptr, g.depth, a->bg, g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
     return FNX_OK;
@@ -1238,12 +1248,13 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
                         void *ci, float *out_color, float *out_depth, int32_t *radii, int64_t *num_rendered_host,
                         fnx_raster_scratch *scratch, cudaStream_t st) {
     FNX_REQUIRE(ag && ab && ai && scratch && num_rendered_host, "allocators / scratch / num_rendered_host must be given");
-    FNX_REQUIRE(out_color && out_depth, "out_color / out_depth must be given");
+    FNX_REQUIRE((out_color && out_depth) || (a->flags & FNX_BIN_ONLY), "out_color / out_depth must be given");
     const int P = a->P, V = a->V, W = a->W, H = a->H;
     const size_t HW = (size_t)W * H;
     memset(scratch, 0, sizeof(*scratch));
     *num_rendered_host = 0;
     if (P == 0) {  // rasterize_points.cu:81: zero outputs
+        FNX_REQUIRE(!(a->flags & FNX_BIN_ONLY), "FNX_BIN_ONLY needs P > 0");
         FNX_CUDA_TRY(cudaMemsetAsync(out_color, 0, sizeof(float) * HW * C * V, st));
         FNX_CUDA_TRY(cudaMemsetAsync(out_depth, 0, sizeof(float) * HW * V, st));
         return FNX_OK;
@@ -1376,8 +1387,8 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_BWD, st);
-    blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, a->bg, g.hdr, im,
-                                                   dL_dout_color, g.accum);
+    blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr, im.ranges,
+                                                        nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
     prof_begin(SEC_GEOM_BWD, st);
@@ -1386,6 +1397,127 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
                                                         a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y,
                                                         radii, g.cov3D, g.accum, (a->grad_end <= a->grad_begin) ? 0 : a->grad_begin,
                                                         (a->grad_end <= a->grad_begin) ? P : a->grad_end, *gr);
+    prof_end(SEC_GEOM_BWD, st);
+    FNX_LAUNCH_CHECK("geom_bwd_kernel");
+    return FNX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Static + dynamic record streams.  The frozen background set and the cameras do not change within a frame, so
+// its depth-sorted, tile-partitioned record stream is built ONCE (FNX_BIN_ONLY | FNX_ALL_FROZEN) and kept in HBM; each
+// iteration bins only the moving Gaussians and merges the two streams per tile by depth (dynamic first on ties:
+// the dynamic Gaussians precede the static ones in the reference's concatenated array, pipe_dynamics.py:51-57, and
+// its sort is stable in the index).  Tiles without dynamic instances are not copied at all: the blend kernels read
+// their span straight from the static stream (tile_src = 1).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MERGE_SMEM = 2048;  // dynamic depths staged per tile
+
+__device__ __forceinline__ float rec48_depth(const char *recs, size_t i) { return reinterpret_cast<const float *>(recs + i * 48)[10]; }
+
+__global__ void __launch_bounds__(256)
+merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat, const char *__restrict__ rec_dyn,
+             const char *__restrict__ rec_stat, char *__restrict__ rec_merged, GeomHeader *__restrict__ hdr_dyn,
+             uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src) {
+    __shared__ float s_depth[MERGE_SMEM];
+    __shared__ unsigned long long s_base;
+    const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
+    const uint2 f = ranges_dyn[t], b = ranges_stat[t];
+    int nf = (int)(f.y - f.x);
+    const int nb = (int)(b.y - b.x);
+    if (hdr_dyn->overflow) nf = 0;
+    if (nf == 0) {
+        if (threadIdx.x == 0) { mranges[t] = b; tile_src[t] = 1u; }
+        return;
+    }
+    // the merged span of this tile is bump-allocated (tile order inside the merged stream does not matter; the ranges
+    // of tiles without instances are (0,0), so they cannot serve as prefix sums)
+    if (threadIdx.x == 0) {
+        s_base = atomicAdd(&hdr_dyn->merge_cursor, (unsigned long long)(nf + nb));
+        mranges[t] = make_uint2((uint32_t)s_base, (uint32_t)(s_base + nf + nb));
+        tile_src[t] = 0u;
+    }
+    const bool staged = nf <= MERGE_SMEM;
+    if (staged)
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) s_depth[i] = rec48_depth(rec_dyn, (size_t)f.x + i);
+    __syncthreads();
+    const size_t ms = (size_t)s_base;
+    // static records: shifted by the number of dynamic records in front of them (depth <= theirs)
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(rec_stat + ((size_t)b.x + j) * 48);
+        const float4 r0 = src[0], r1 = src[1], r2 = src[2];
+        const float d = r2.z;
+        int lo = 0, hi = nf;  // upper bound: first dynamic depth > d
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const float dm = staged ? s_depth[mid] : rec48_depth(rec_dyn, (size_t)f.x + mid);
+            if (dm <= d) lo = mid + 1; else hi = mid;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(rec_merged + (ms + j + lo) * 48);
+        dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    }
+    // dynamic records: shifted by the number of static records strictly in front of them
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(rec_dyn + ((size_t)f.x + i) * 48);
+        const float4 r0 = src[0], r1 = src[1], r2 = src[2];
+        const float d = r2.z;
+        int lo = 0, hi = nb;  // lower bound: first static depth >= d
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (rec48_depth(rec_stat, (size_t)b.x + mid) < d) lo = mid + 1; else hi = mid;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(rec_merged + (ms + i + lo) * 48);
+        dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    }
+}
+
+static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat, int P_static,
+                        void *merged_records, float *out_color, float *out_depth, cudaStream_t st) {
+    FNX_REQUIRE(a && dyn && stat && merged_records && out_color && out_depth, "bad arguments");
+    FNX_REQUIRE(a->C == 3, "merged static+dynamic streams are implemented for 3-channel records (they carry the depth)");
+    FNX_REQUIRE(dyn->geom && dyn->binning && dyn->image && stat->geom && stat->binning && stat->image, "scratch missing");
+    const int P = a->P, V = a->V, W = a->W, H = a->H;
+    FNX_REQUIRE((long long)P * V < (1ll << SLOT_BITS) && (long long)P_static * V < (1ll << SLOT_BITS), "too many Gaussians for masked records");
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
+    GeomView g = geom_view(dyn->geom, P, V);
+    ImageView im = image_view(dyn->image, W, H, V);
+    ImageView ims = image_view(stat->image, W, H, V);
+    BinView b = bin_view(dyn->binning, dyn->binning_capacity, 3);
+    BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
+    dim3 grid(ntiles, V);
+    prof_begin(SEC_PACK, st);
+    merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, im.mranges, im.tile_src);
+    prof_end(SEC_PACK, st);
+    FNX_LAUNCH_CHECK("merge_kernel");
+    prof_begin(SEC_BLEND_FWD, st);
+    blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
+                                                        g.depth, a->bg, g.hdr, im, out_color, out_depth);
+    prof_end(SEC_BLEND_FWD, st);
+    FNX_LAUNCH_CHECK("blend_fwd_kernel");
+    return FNX_OK;
+}
+
+static int backward_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat, const void *merged_records,
+                           const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *gr, cudaStream_t st) {
+    FNX_REQUIRE(a && dyn && stat && merged_records && radii && dL_dout_color && gr, "bad arguments");
+    FNX_REQUIRE(a->C == 3, "merged streams need C == 3");
+    const int P = a->P, V = a->V, W = a->W, H = a->H;
+    constexpr int ACC = AccFloats<3>::value;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
+    const float focal_y = H / (2.0f * a->tan_fov_y), focal_x = W / (2.0f * a->tan_fov_x);
+    GeomView g = geom_view(dyn->geom, P, V);
+    ImageView im = image_view(dyn->image, W, H, V);
+    BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
+    FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
+    dim3 grid(ntiles, V);
+    prof_begin(SEC_BLEND_BWD, st);
+    blend_bwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
+                                                        a->bg, g.hdr, im, dL_dout_color, g.accum);
+    prof_end(SEC_BLEND_BWD, st);
+    FNX_LAUNCH_CHECK("blend_bwd_kernel");
+    prof_begin(SEC_GEOM_BWD, st);
+    geom_bwd_kernel<3><<<(P + 255) / 256, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
+                                                        (const float4 *)a->rotations, a->cov3D_precomp, a->view_matrix, a->proj_matrix, W, H,
+                                                        a->tan_fov_x, a->tan_fov_y, focal_x, focal_y, radii, g.cov3D, g.accum, 0, P, *gr);
     prof_end(SEC_GEOM_BWD, st);
     FNX_LAUNCH_CHECK("geom_bwd_kernel");
     return FNX_OK;
@@ -1440,6 +1572,16 @@ int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *
                             const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g, fnx_stream_t stream) {
     if (a && a->C != 3) { set_error("fnx_raster_backward_ch3 needs C == 3 (got %d)", a->C); return FNX_ERR_INVALID; }
     return fnx_raster_backward(a, scratch, num_rendered, radii, dL_dout_color, g, stream);
+}
+
+int fnx_raster_blend_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
+                            int32_t P_static, void *merged_records, float *out_color, float *out_depth, fnx_stream_t stream) {
+    return blend_merged(dyn_args, dyn, stat, P_static, merged_records, out_color, out_depth, (cudaStream_t)stream);
+}
+int fnx_raster_backward_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
+                               const void *merged_records, const int32_t *radii, const float *dL_dout_color,
+                               const fnx_raster_grads *g, fnx_stream_t stream) {
+    return backward_merged(dyn_args, dyn, stat, merged_records, radii, dL_dout_color, g, (cudaStream_t)stream);
 }
 
 int fnx_raster_check(const fnx_raster_scratch *scratch, int64_t *num_rendered_host, fnx_stream_t stream) {

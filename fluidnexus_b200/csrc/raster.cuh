@@ -31,7 +31,8 @@ struct GeomHeader {
     long long num_rendered;   // instances actually needed (device-written by the scan epilogue)
     long long capacity;       // instances the binning buffers can hold
     int overflow;             // 1 if num_rendered > capacity (nothing rendered)
-    int pad[3];
+    int pad;
+    unsigned long long merge_cursor;  // bump allocator of fnx_raster_blend_merged's merged stream (reset per forward)
 };
 
 struct GeomView {  // pointers into the geom scratch
@@ -62,6 +63,8 @@ struct ImageView {
     uint32_t *n_contrib;     // [V*H*W]
     uint2 *ranges;           // [V*ntiles]
     uint32_t *tile_last;     // [V*ntiles] max n_contrib over the tile's pixels (backward start)
+    uint2 *mranges;          // [V*ntiles] merged ranges (static + dynamic streams), see fnx_raster_blend_merged
+    uint32_t *tile_src;      // [V*ntiles] 0: the tile's span lives in the call's own record stream, 1: in the static one
 };
 
 size_t geom_bytes(int P, int V);

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace"]
+__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace", "MergedRasterWorkspace"]
 
 
 def _ptr(t):
@@ -221,6 +221,100 @@ class RasterWorkspace:
 
     def overflowed(self):
         return self.num_rendered() > self.capacity
+
+
+def _fill_args(a, C_, P, V, H, W, bg, means3D, colors, opacities, scales, rotations, scale_modifier, view_matrix, proj_matrix,
+               tan_fov_x, tan_fov_y, flags, capacity=0, pinned=None):
+    a.P, a.V, a.C, a.W, a.H = P, V, C_, W, H
+    a.means3D, a.colors, a.opacities = means3D.data_ptr(), colors.data_ptr(), opacities.data_ptr()
+    a.scales, a.rotations, a.cov3D_precomp, a.sh = scales.data_ptr(), rotations.data_ptr(), None, None
+    a.view_matrix, a.proj_matrix, a.bg = view_matrix.data_ptr(), proj_matrix.data_ptr(), bg.data_ptr()
+    a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
+    a.prefiltered, a.flags = 0, flags
+    a.instance_capacity_hint, a.num_rendered_pinned = int(capacity), (pinned.data_ptr() if pinned is not None else None)
+    a.grad_begin, a.grad_end = 0, 0
+    return a
+
+
+class MergedRasterWorkspace:
+    """Rasterizer workspace for [dynamic ; static] Gaussian sets (FD/renderer/pipe_dynamics.py:51-57 concatenates the
+    moving fluid particles with a frozen background set).  The static set's depth-sorted record stream is built once
+    at construction (cameras and the set must not change afterwards); every forward bins only the dynamic set and
+    merges the two streams per tile (fnx_raster_blend_merged).  Results equal one forward over the concatenated set;
+    gradients are produced for the dynamic Gaussians only.  3 channels.  No allocation / host sync / events inside
+    forward() and backward() (CUDA-graph capturable)."""
+
+    def __init__(self, dev, P_dyn, V, H, W, bg, dyn, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, margin=1.2):
+        """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations."""
+        lib = L.lib()
+        self.dev, self.C, self.P, self.V, self.H, self.W = torch.device(dev), 3, P_dyn, V, H, W
+        self.P_static = static["means3D"].size(0)
+        self.cam = (bg, view_matrix, proj_matrix, float(tan_fov_x), float(tan_fov_y))
+        self._static = static
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.device(self.dev):
+            # ---- static stream: exact sizing, once ----
+            self._sbufs = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
+            self.sargs, self.sscratch = L.RasterArgs(), L.RasterScratch()
+            self.sradii = torch.empty((V, self.P_static), dtype=torch.int32, device=self.dev)
+            _fill_args(self.sargs, 3, self.P_static, V, H, W, bg, static["means3D"], static["colors"], static["opacities"],
+                       static["scales"], static["rotations"], 1.0, view_matrix, proj_matrix, tan_fov_x, tan_fov_y,
+                       L.FNX_BIN_ONLY | L.FNX_ALL_FROZEN)
+            nr = C.c_int64(0)
+            L.check(lib.fnx_raster_forward_ch3(C.byref(self.sargs), self._sbufs[0].cb, None, self._sbufs[1].cb, None, self._sbufs[2].cb,
+                                               None, None, None, self.sradii.data_ptr(), C.byref(nr), C.byref(self.sscratch), st))
+            self.R_static = int(nr.value)
+            # ---- dynamic stream: one exact binning to size the capacity ----
+            tmp = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
+            targs, tscratch = L.RasterArgs(), L.RasterScratch()
+            self.radii = torch.empty((V, P_dyn), dtype=torch.int32, device=self.dev)
+            _fill_args(targs, 3, P_dyn, V, H, W, bg, dyn["means3D"], dyn["colors"], dyn["opacities"], dyn["scales"], dyn["rotations"],
+                       1.0, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, L.FNX_BIN_ONLY)
+            L.check(lib.fnx_raster_forward_ch3(C.byref(targs), tmp[0].cb, None, tmp[1].cb, None, tmp[2].cb, None, None, None,
+                                               self.radii.data_ptr(), C.byref(nr), C.byref(tscratch), st))
+            torch.cuda.synchronize(self.dev)
+            self.capacity = int(nr.value * margin) + 65536
+            del tmp
+            u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=self.dev)
+            self.geom, self.image = u8(lib.fnx_raster_geom_bytes(P_dyn, V)), u8(lib.fnx_raster_image_bytes(W, H, V))
+            self.binning = u8(lib.fnx_raster_binning_bytes(self.capacity, 3))
+            self.merged = u8(48 * (self.capacity + self.R_static) + 256)
+            self.color = torch.empty((V, 3, H, W), device=self.dev)
+            self.depth = torch.empty((V, 1, H, W), device=self.dev)
+            self.grads = {"means3D": torch.empty((P_dyn, 3), device=self.dev)}
+        self.count = torch.full((1,), -1, dtype=torch.int64).pin_memory()
+        self._cbs = tuple(L.ALLOC_FN(RasterWorkspace._fixed(t)) for t in (self.geom, self.binning, self.image))
+        self.args, self.scratch, self._keep = L.RasterArgs(), L.RasterScratch(), None
+
+    def forward(self, means3D, colors, opacities, scales, rotations):
+        lib = L.lib()
+        bg, vm, pm, tfx, tfy = self.cam
+        _fill_args(self.args, 3, self.P, self.V, self.H, self.W, bg, means3D, colors, opacities, scales, rotations, 1.0, vm, pm, tfx, tfy,
+                   L.FNX_BIN_ONLY | L.FNX_NO_HOST_SYNC, self.capacity, self.count)
+        self._keep = (means3D, colors, opacities, scales, rotations)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        nr = C.c_int64(0)
+        L.check(lib.fnx_raster_forward_ch3(C.byref(self.args), self._cbs[0], None, self._cbs[1], None, self._cbs[2], None, None, None,
+                                           self.radii.data_ptr(), C.byref(nr), C.byref(self.scratch), st))
+        L.check(lib.fnx_raster_blend_merged(C.byref(self.args), C.byref(self.scratch), C.byref(self.sscratch), self.P_static,
+                                            self.merged.data_ptr(), self.color.data_ptr(), self.depth.data_ptr(), st))
+        return self.color
+
+    def backward(self, dL_dout_color):
+        gr = L.RasterGrads()
+        gr.dL_dmeans3D = self.grads["means3D"].data_ptr()
+        L.check(L.lib().fnx_raster_backward_merged(C.byref(self.args), C.byref(self.scratch), C.byref(self.sscratch), self.merged.data_ptr(),
+                                                   self.radii.data_ptr(), dL_dout_color.data_ptr(), C.byref(gr),
+                                                   torch.cuda.current_stream(self.dev).cuda_stream))
+        return self.grads
+
+    def num_rendered(self):
+        """Dynamic instances of the last finished forward + the static stream's instances."""
+        n = int(self.count[0])
+        return n + self.R_static if n >= 0 else n
+
+    def overflowed(self):
+        return int(self.count[0]) > self.capacity
 
 
 def mark_visible(positions, view_matrix, proj_matrix):

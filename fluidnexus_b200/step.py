@@ -106,7 +106,7 @@ class PhysicalStep:
     """step(frame, view_ids, gt) -> dict of device scalars.  `cams`: list of camera objects with the attributes of
     FD/scene/camera.py (world_view_transform, full_proj_transform, FoVx, FoVy, image_width, image_height)."""
 
-    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda", overlap=True):
+    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda", overlap=True, static_cache=True):
         import math
         self.prm = prm or StepParams()
         self.dev = torch.device(device)
@@ -119,6 +119,7 @@ class PhysicalStep:
         self.bg = _dev_f32([0.0] * channels if bg_color is None else bg_color, self.dev)
         self._loss_scratch, self._views = {}, {}
         self.capacity_margin = 1.2   # binning capacity = margin * instances of the sizing forward + 64k
+        self.static_cache = static_cache  # bin the frozen background once per frame (MergedRasterWorkspace)
         self.lib = L.lib()
         # the view-independent physics terms run on a side stream next to the rasterizer (fork/join with events, also
         # inside a captured graph); overlap=False keeps everything on one stream
@@ -198,24 +199,42 @@ class PhysicalStep:
         return self._views[key]
 
     def workspace(self, fr: FrameState, nviews, view_ids):
-        """Persistent rasterizer buffers for this frame; sized from one exact forward (the only one that blocks)."""
-        ws = fr.ws.get(nviews)
-        if ws is not None and ws.num_rendered() > ws.capacity:   # the last finished forward overflowed: grow
+        """Persistent rasterizer buffers for this frame; sized from one exact forward (the only one that blocks).
+        With a frozen background set (3 channels) the static stream is binned here once and only the fluid rows are
+        re-binned per iteration (MergedRasterWorkspace)."""
+        key = (nviews, tuple(view_ids))
+        ws = fr.ws.get(key)
+        if ws is not None and ws.overflowed():   # the last finished forward overflowed: grow
             torch.cuda.synchronize(self.dev)
             ws = None
         if ws is None:
             vm, pm = self._view_mats(view_ids)
-            ctx, _, _, _ = R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, vm,
-                                            pm, self.tan_fov_x, self.tan_fov_y, self.H, self.W, speculative=False)
-            cap = int(ctx.num_rendered * self.capacity_margin) + 65536
-            del ctx
-            ws = R.RasterWorkspace(self.dev, self.C, fr.P, nviews, self.H, self.W, cap)
-            fr.ws[nviews] = ws
+            if self.static_cache and fr.Pb > 0 and self.C == 3:
+                V = fr.V
+                sl = lambda t, a, b: t[a:b]
+                dyn = dict(means3D=sl(fr.means3D, 0, V), colors=sl(fr.colors, 0, V), opacities=sl(fr.opacity, 0, V),
+                           scales=sl(fr.scales, 0, V), rotations=sl(fr.rotations, 0, V))
+                sta = dict(means3D=sl(fr.means3D, V, fr.P), colors=sl(fr.colors, V, fr.P), opacities=sl(fr.opacity, V, fr.P),
+                           scales=sl(fr.scales, V, fr.P), rotations=sl(fr.rotations, V, fr.P))
+                ws = R.MergedRasterWorkspace(self.dev, V, nviews, self.H, self.W, self.bg, dyn, sta, vm, pm, self.tan_fov_x,
+                                             self.tan_fov_y, margin=self.capacity_margin)
+                ws.dyn = dyn
+            else:
+                ctx, _, _, _ = R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None,
+                                                vm, pm, self.tan_fov_x, self.tan_fov_y, self.H, self.W, speculative=False)
+                cap = int(ctx.num_rendered * self.capacity_margin) + 65536
+                del ctx
+                ws = R.RasterWorkspace(self.dev, self.C, fr.P, nviews, self.H, self.W, cap)
+            fr.ws[key] = ws
             fr.graphs.clear()
         return ws
 
     def render(self, fr: FrameState, view_ids):
         ws = self.workspace(fr, len(view_ids), view_ids)
+        if isinstance(ws, R.MergedRasterWorkspace):
+            d = ws.dyn
+            ws.forward(d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"])
+            return ws
         vm, pm = self._view_mats(view_ids)
         # only the fluid rows [0, V) are trainable in the physical stage; the background set is frozen
         # (pipe_dynamics.py:51-57 concatenates it behind the fluid particles) and needs no gradient
@@ -314,9 +333,9 @@ class PhysicalStep:
                     dst.copy_(src)
             g, out, gt_buf = ent
             ws = out.get("ws")
-            if ws is not None and ws.num_rendered() > ws.capacity:
+            if ws is not None and ws.overflowed():
                 raise RuntimeError("rasterizer instance capacity exceeded inside a captured iteration; re-capture "
-                                   f"(needed {ws.num_rendered()}, capacity {ws.capacity})")
+                                   f"(capacity {ws.capacity})")
             gt_buf.copy_(gt, non_blocking=True)
             g.replay()
             return out

@@ -65,6 +65,10 @@ unsigned long long fnx_launch_count(void);
 #define FNX_EXACT_RECT 2u   /* bin with the reference's full 3-sigma tile rectangle (no opacity-aware tile
                                culling).  Results are identical either way; this exists for A/B tests. */
 
+#define FNX_BIN_ONLY 4u     /* forward: stop after the record stream is packed (no blending; out_color/out_depth may be
+                               NULL).  Used to build a stream that fnx_raster_blend_merged consumes. */
+#define FNX_ALL_FROZEN 8u   /* every Gaussian of this call is frozen (no gradients): marks all its records */
+
 typedef struct fnx_raster_args {
     /* sizes */
     int32_t P;        /* Gaussians */
@@ -151,6 +155,21 @@ int fnx_raster_backward_ch1(const fnx_raster_args *a, const fnx_raster_scratch *
 int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
                             const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g,
                             fnx_stream_t stream);
+
+/* Static + dynamic streams (3 channels).  The frozen background set that FD/renderer/pipe_dynamics.py:51-57 concatenates
+ * behind the fluid particles does not change within a frame (nor do the cameras), so it is binned ONCE with
+ * fnx_raster_forward(FNX_BIN_ONLY | FNX_ALL_FROZEN) -> `stat`; every iteration bins only the moving Gaussians
+ * (FNX_BIN_ONLY) -> `dyn`, then this call merges the two depth-sorted streams per tile (dynamic first on equal depth,
+ * which reproduces the reference's order for the concatenated array [dynamic; static]) and blends.  Results are
+ * identical to one forward over the concatenated set.  merged_records: 48 * (dyn capacity + static instances) bytes.
+ * Same V, W, H, cameras and bg for both sets.  out_color [V,3,H,W], out_depth [V,1,H,W]. */
+int fnx_raster_blend_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
+                            int32_t P_static, void *merged_records, float *out_color, float *out_depth, fnx_stream_t stream);
+/* Backward of the above: gradients for the DYNAMIC Gaussians only (g sized for dyn_args->P); radii = the dynamic
+ * forward's radii. */
+int fnx_raster_backward_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
+                               const void *merged_records, const int32_t *radii, const float *dL_dout_color,
+                               const fnx_raster_grads *g, fnx_stream_t stream);
 
 /* After a FNX_NO_HOST_SYNC forward: blocks until the forward's instance count is known and returns FNX_OK or
  * FNX_ERR_CAPACITY; *num_rendered_host is set either way. */

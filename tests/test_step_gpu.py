@@ -127,3 +127,24 @@ def test_view_sharded_gradients_sum_to_the_full_step(libfnx):
     b = ps.step(FrameState(hp, vis, fluid, bg, prm=prm), [3, 4], gt[3:], update=False, batch=5, physics=False)["grad"].clone()
     r = ((a + b) - full).norm() / full.norm()
     assert r < 1e-5, r
+
+
+def test_static_background_cache_equals_full_rebinning(libfnx):
+    """Binning the frozen background once and merging it with the per-iteration fluid stream must give the same image
+    bit for bit and the same parameter trajectory as re-binning everything every iteration."""
+    hp, vis, fluid, bg, cams = _scene(3, True, seed=8, size=96)
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    gt = torch.rand(5, 3, 96, 96, generator=torch.Generator().manual_seed(3)).cuda() * 0.5
+    res = {}
+    for cache in (False, True):
+        ps = PhysicalStep(cams, 3, prm, static_cache=cache)
+        fr = FrameState(hp, vis, fluid, bg, prm=prm)
+        imgs, losses = [], []
+        for it in range(4):
+            out = ps.step(fr, [0, 1, 2, 3, 4], gt)
+            imgs.append(out["images"].clone())
+            losses.append(float(ps.total_loss(out)))
+        res[cache] = (imgs, losses, fr.e.clone())
+    assert torch.equal(res[False][0][0], res[True][0][0])           # first iteration: identical inputs -> identical image
+    assert np.allclose(res[False][1], res[True][1], rtol=1e-5)
+    assert (res[False][2] - res[True][2]).abs().max() < 1e-6
