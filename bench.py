@@ -217,6 +217,20 @@ def run_fnx(args):
     use_graph[0] = graph_flag
     value = G * args.steps / (ms / 1e3)
     e2e = G * args.steps / (ms_e2e / 1e3)
+    ws_last = out["ws"] if out and "ws" in out else None
+    tile_state = ws_last.tile_state() if ws_last is not None and hasattr(ws_last, "tile_state") else None
+    # ---- A/B: the same timed region with every tile blended every iteration (static tile cache off) ----
+    cache_on = any(getattr(w_, "static_tile_cache", False) for f in mine for w_ in states[f].ws.values())
+    value_nocache = None
+    if cache_on:
+        for f in mine:
+            for w_ in states[f].ws.values():
+                w_.static_tile_cache = False
+            states[f].graphs.clear()
+        for _ in range(3):
+            one_step(False)
+        ms_nc, _ = timed(args.steps, False)
+        value_nocache = G * args.steps / (ms_nc / 1e3)
 
     if rank != 0:
         if world > 1:
@@ -229,17 +243,39 @@ def run_fnx(args):
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     Cc, HW, P = cfg["C"], cfg["size"] ** 2, cfg["nf"] + cfg["nb"]
-    ib = names.index("blend_bwd")
+    # dominant kernel = the larger of the two blend kernels (sections_ms_per_step lists everything else)
+    kname = "blend_bwd" if tot[names.index("blend_bwd")] >= tot[names.index("blend_fwd")] else "blend_fwd"
+    ib = names.index(kname)
     n_launch = max(1, cnt[ib])
-    t_launch = tot[ib] / 1e3 / n_launch                               # seconds per blend_bwd launch (5 views each)
-    # algorithmic bytes of ONE blend_bwd launch: records R*rec + per pixel dL/dpix, final_T, n_contrib + accumulator rows
+    t_launch = tot[ib] / 1e3 / n_launch                               # seconds per launch (5 views each)
+    # ALGORITHMIC bytes of one launch: the records the kernel has to read once + the per-pixel state of the
+    # tiles it has to touch + (backward) the accumulator rows it writes once.  With the static/dynamic streams the
+    # per-tile record counts come from the tile state of the last forward (fnx_raster_read_tiles).
     rec = 48 if Cc == 3 else 32
     acc = 48 if Cc == 3 else 32
-    bytes_launch = R_per_iter * rec + len(views) * HW * (4 * Cc + 8) + len(views) * P * acc
+    tile_info = None
+    if tile_state is not None:
+        ts = tile_state
+        dyn_t = ts["tile_src"] == 0
+        fwd_rec = float(ts["tile_last"][dyn_t].sum())                  # static-only tiles are not blended again (tile cache)
+        bwd_rec = float(np.minimum(ts["tile_last"], ts["tile_dyn_last"])[dyn_t].sum())
+        pix = float(dyn_t.sum()) * 256.0
+        bytes_fwd = fwd_rec * rec + pix * (4 * Cc + 4 + 8 + 16)        # colour, depth, final_T + n_contrib, snapshot
+        bytes_bwd = bwd_rec * rec + pix * (4 * Cc + 8 + 16) + len(views) * cfg["nf"] * acc
+        if not cache_on:
+            fwd_rec = float(ts["tile_last"].sum())
+            bytes_fwd = fwd_rec * rec + len(views) * HW * (4 * Cc + 4 + 8) + pix * 16
+        tile_info = {"tiles": int(ts["tile_src"].size), "tiles_with_dynamic_instances": int(dyn_t.sum()),
+                     "records_blended_fwd": fwd_rec, "records_walked_bwd": bwd_rec,
+                     "records_in_merged_spans": float((ts["end"] - ts["begin"])[dyn_t].sum())}
+    else:
+        bytes_fwd = R_per_iter * rec + len(views) * HW * (4 * Cc + 4 + 8)
+        bytes_bwd = R_per_iter * rec + len(views) * HW * (4 * Cc + 8) + len(views) * P * acc
+    bytes_launch = bytes_bwd if kname == "blend_bwd" else bytes_fwd
     achieved = bytes_launch / t_launch / 1e9 if t_launch > 0 else 0.0
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["blend_bwd_kernel"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][kname + "_kernel"]["dram_bytes_per_launch"]
     except Exception:
         pass
     line = {
@@ -258,15 +294,21 @@ def run_fnx(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "blend_bwd_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kname + "_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 5), "traffic": traffic, "algorithmic_bytes_per_launch": int(bytes_launch),
                      "peak_source": peak_src,
                      "ms_per_launch": round(t_launch * 1e3, 4), "launches_timed": int(n_launch),
                      "share_of_step": round(tot[ib] / sum(tot[i] for i in range(nsec)), 4),
-                     "note": "instruction-issue bound (82 % issue-active, ncu) on an L2-resident working set: DRAM traffic is far "
-                             "BELOW the algorithmic bytes because the record stream is still in L2 from the pack kernel; see DESIGN.md 6"},
+                     "tile_state": tile_info,
+                     "note": "instruction-issue bound blend loop (ncu: issue-active 70-80 %) on a mostly L2-resident working set; "
+                             "see DESIGN.md 6"},
         "sections_ms_per_step": {names[i]: round(tot[i] / args.steps, 4) for i in range(nsec) if cnt[i]},
         "cuda_graph": bool(graph_flag),
+        "static_tile_cache": {"on": bool(cache_on), "value_with_cache_off": None if value_nocache is None else round(value_nocache, 3),
+                              "what": "tiles that hold no fluid instance keep the pixels of the static-only render (frozen background + "
+                                      "fixed cameras cannot change them) instead of being blended again every iteration; `value` and "
+                                      "`e2e` are measured with it on, value_with_cache_off is the same timed region with every tile "
+                                      "blended every iteration"},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, frames[0], bg, cams)

@@ -15,6 +15,7 @@ FNX_NO_HOST_SYNC = 1
 FNX_EXACT_RECT = 2
 FNX_BIN_ONLY = 4
 FNX_ALL_FROZEN = 8
+FNX_STATIC_TILE_CACHE = 16
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -66,6 +67,8 @@ SYMBOLS = {
     "fnx_raster_forward": _FWD, "fnx_raster_forward_ch1": _FWD, "fnx_raster_forward_ch3": _FWD,
     "fnx_raster_backward": _BWD, "fnx_raster_backward_ch1": _BWD, "fnx_raster_backward_ch3": _BWD,
     "fnx_raster_blend_merged": (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), C.POINTER(RasterScratch), _I, _V, _V, _V, _V]),
+    "fnx_raster_static_prepare": (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), _V, _V, _V]),
+    "fnx_raster_read_tiles": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _I, _V, _V, _V, _V, _V]),
     "fnx_raster_backward_merged": (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), C.POINTER(RasterScratch), _V, _V, _V,
                                         C.POINTER(RasterGrads), _V]),
     "fnx_raster_check": (_I, [C.POINTER(RasterScratch), C.POINTER(_I64), _V]),

@@ -84,12 +84,14 @@ ImageView image_view(void *chunk, int W, int H, int V) {
     im.tile_last = carve<uint32_t>(p, nt);
     im.mranges = carve<uint2>(p, nt);
     im.tile_src = carve<uint32_t>(p, nt);
+    im.tile_dyn_last = carve<uint32_t>(p, nt);
+    im.tile_cached = carve<uint32_t>(p, nt);
+    im.snap = carve<float4>(p, hw);
     return im;
 }
 size_t image_bytes(int W, int H, int V) {
     ImageView im = image_view((void *)0, W, H, V);
-    size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
-    return (size_t)((char *)im.tile_src - (char *)0) + nt * 4 + 256;
+    return (size_t)((char *)im.snap - (char *)0) + (size_t)W * H * V * sizeof(float4) + 256;
 }
 
 static size_t bin_cub_bytes(long long cap) {
@@ -409,6 +411,7 @@ __global__ void finish_scan_kernel(int n, GeomView g, long long capacity, long l
     g.hdr->capacity = capacity;
     g.hdr->overflow = (capacity >= 0 && total > capacity) ? 1 : 0;
     g.hdr->merge_cursor = 0ull;
+    g.hdr->static_prepared = 0;
     if (pinned_out) *pinned_out = total;
 }
 
@@ -594,10 +597,29 @@ __device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int w
     }
 }
 
+// bits [lo, hi) of a 32-bit word, clipped to the word
+__device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
+    lo = max(lo, 0);
+    hi = min(hi, 32);
+    if (hi <= lo) return 0u;
+    const uint32_t upto_hi = (hi == 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+    return upto_hi & ~((1u << lo) - 1u);
+}
+
+// Optional per-tile state of the merged (static + dynamic) streams, all NULL for a plain forward:
+//   tile_src       1: the tile has no dynamic instance and is blended straight from the static stream
+//   tile_cached    (persistent, with the static stream) 1: the caller's out_color / out_depth already hold this
+//                  tile's static-only render -- cameras and the frozen set are fixed, so a static-only tile renders the
+//                  same pixels every iteration and is blended once, not once per iteration
+//   tile_dyn_last  L = 1 + span index of the tile's last dynamic record.  Records at or behind L are all frozen: the
+//                  backward needs from them only the transmittance T and the colour behind, per pixel, at L.  The
+//                  forward snapshots {T, C} when it passes L and stores {T, (C_final - C) / T} in `snap`, so the
+//                  backward starts at L instead of at the last contributor.
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
+                 uint32_t *__restrict__ tile_cached, const uint32_t *__restrict__ tile_dyn_last, float4 *__restrict__ snap,
                  const float *__restrict__ depth_of_slot, const float *__restrict__ bg, const GeomHeader *__restrict__ hdr,
                  ImageView im, float *__restrict__ out_color, float *__restrict__ out_depth) {
     constexpr int REC = RecBytes<C>::value;
@@ -606,6 +628,14 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
 
     const int tile = blockIdx.x, v = blockIdx.y;
     const int ntiles = gx * gy;
+    const size_t tslot = (size_t)v * ntiles + tile;
+    const bool from_static = tile_src != nullptr && tile_src[tslot] != 0;
+    if (tile_cached != nullptr) {
+        if (from_static) {
+            if (tile_cached[tslot] != 0) return;  // uniform over the CTA; the pixels are already in place
+        }
+        // (the flag is updated at the end, after the pixels are written)
+    }
     const int tx = tile % gx, ty = tile / gx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = tx * TILE + (warp & 1) * PATCH + (lane & 7);
@@ -615,6 +645,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
     bool inside[PPT], done[PPT];
     float pyf[PPT], T[PPT], D[PPT], Cacc[PPT][C];
+    float T_snap[PPT], C_snap[PPT][C];
     uint32_t last_contributor[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
@@ -624,15 +655,18 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         T[p] = 1.0f;
         D[p] = DEPTH_DEFAULT;
         last_contributor[p] = 0;
+        T_snap[p] = 1.0f;
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) Cacc[p][ch] = 0.f;
+        for (int ch = 0; ch < C; ch++) Cacc[p][ch] = C_snap[p][ch] = 0.f;
     }
 
-    uint2 range = ranges[(size_t)v * ntiles + tile];
-    const char *records = (tile_src != nullptr && tile_src[(size_t)v * ntiles + tile] != 0) ? records_static : records_own;
+    uint2 range = ranges[tslot];
+    const char *records = from_static ? records_static : records_own;
     if (hdr->overflow) range = make_uint2(0, 0);
     const int total = (int)(range.y - range.x);
     const int nbatch = (total + BATCH - 1) / BATCH;
+    // snapshot position (span index); -1: no snapshot
+    const int L = (snap != nullptr && !from_static && tile_dyn_last != nullptr) ? (int)tile_dyn_last[tslot] : -1;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -673,36 +707,51 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         if (__all_sync(0xffffffffu, all_done)) continue;  // this warp's patch is finished
         uint32_t words[BATCH / 32];
         warp_record_mask<C>(rec, n, warp, lane, use_mask, words);
-#pragma unroll
-        for (int k = 0; k < BATCH / 32; k++) {
-            uint32_t w = words[k];
-            while (w) {
-                const int j = k * 32 + __ffs(w) - 1;
-                w &= w - 1;
-                const float4 r0 = rec[j * (REC / 16)];
-                const float4 r1 = rec[j * (REC / 16) + 1];
+        // the batch holding the snapshot position is walked in two segments, [0, Lrel) and [Lrel, BATCH)
+        const int Lrel = L - bi * BATCH;
+        const int cut = (Lrel >= 0 && Lrel < BATCH) ? Lrel : BATCH;
+        for (int seg = 0; seg < 2; seg++) {
+            const int lo = seg == 0 ? 0 : cut, hi = seg == 0 ? cut : BATCH;
+            if (seg == 1) {
+                if (cut == BATCH) break;
 #pragma unroll
                 for (int p = 0; p < PPT; p++) {
-                    if (done[p]) continue;
-                    float dx, dy, G, alpha;
-                    if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx, dy, G, alpha)) continue;
-                    const float test_T = T[p] * (1 - alpha);
-                    if (test_T < T_EPS) {
-                        done[p] = true;
-                        continue;
+                    T_snap[p] = T[p];
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) C_snap[p][ch] = Cacc[p][ch];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BATCH / 32; k++) {
+                uint32_t w = words[k] & bit_range(lo - 32 * k, hi - 32 * k);
+                while (w) {
+                    const int j = k * 32 + __ffs(w) - 1;
+                    w &= w - 1;
+                    const float4 r0 = rec[j * (REC / 16)];
+                    const float4 r1 = rec[j * (REC / 16) + 1];
+#pragma unroll
+                    for (int p = 0; p < PPT; p++) {
+                        if (done[p]) continue;
+                        float dx, dy, G, alpha;
+                        if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx, dy, G, alpha)) continue;
+                        const float test_T = T[p] * (1 - alpha);
+                        if (test_T < T_EPS) {
+                            done[p] = true;
+                            continue;
+                        }
+                        if (C == 3) {
+                            const float4 r2 = rec[j * 3 + 2];
+                            Cacc[p][0] += r1.z * alpha * T[p];
+                            Cacc[p][1 % C] += r1.w * alpha * T[p];
+                            Cacc[p][2 % C] += r2.x * alpha * T[p];
+                            if (T[p] > 0.5f && test_T < 0.5) D[p] = r2.z;
+                        } else {
+                            Cacc[p][0] += r1.z * alpha * T[p];
+                            if (T[p] > 0.5f && test_T < 0.5) D[p] = depth_of_slot[__float_as_uint(r1.w) & slot_mask];
+                        }
+                        T[p] = test_T;
+                        last_contributor[p] = (uint32_t)(bi * BATCH + j + 1);
                     }
-                    if (C == 3) {
-                        const float4 r2 = rec[j * 3 + 2];
-                        Cacc[p][0] += r1.z * alpha * T[p];
-                        Cacc[p][1 % C] += r1.w * alpha * T[p];
-                        Cacc[p][2 % C] += r2.x * alpha * T[p];
-                        if (T[p] > 0.5f && test_T < 0.5) D[p] = r2.z;
-                    } else {
-                        Cacc[p][0] += r1.z * alpha * T[p];
-                        if (T[p] > 0.5f && test_T < 0.5) D[p] = depth_of_slot[__float_as_uint(r1.w) & slot_mask];
-                    }
-                    T[p] = test_T;
-                    last_contributor[p] = (uint32_t)(bi * BATCH + j + 1);
                 }
             }
         }
@@ -729,13 +778,21 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
 #pragma unroll
         for (int ch = 0; ch < C; ch++) out_color[((size_t)v * C + ch) * HW + pix] = Cacc[p][ch] + T[p] * bg[ch];
         out_depth[(size_t)v * HW + pix] = D[p];
+        if (L >= 0) {
+            // colour accumulated behind the snapshot position, normalised by the transmittance there: what the
+            // reference's back-to-front recursion (backward.cu:488-496) holds in accum_rec when it arrives at L
+            const float inv = 1.f / T_snap[p];
+            snap[(size_t)v * HW + pix] = make_float4(T_snap[p], (Cacc[p][0] - C_snap[p][0]) * inv, (Cacc[p][1 % C] - C_snap[p][1 % C]) * inv,
+                                                     (Cacc[p][2 % C] - C_snap[p][2 % C]) * inv);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t m = 0;
 #pragma unroll
         for (int w = 0; w < BLEND_WARPS; w++) m = max(m, s_last[w]);
-        im.tile_last[(size_t)v * ntiles + tile] = m;
+        im.tile_last[tslot] = m;
+        if (tile_cached != nullptr) tile_cached[tslot] = from_static ? 1u : 0u;
     }
 }
 
@@ -801,6 +858,7 @@ template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
+                 const uint32_t *__restrict__ tile_dyn_last, const float4 *__restrict__ snap,
                  const float *__restrict__ bg, const GeomHeader *__restrict__ hdr, ImageView im,
                  const float *__restrict__ dL_dpixels, float *__restrict__ accum) {
     constexpr int REC = RecBytes<C>::value;
@@ -818,9 +876,16 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const size_t HW = (size_t)W * H;
     const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
 
-    const uint2 range = ranges[(size_t)v * ntiles + tile];
-    const char *records = (tile_src != nullptr && tile_src[(size_t)v * ntiles + tile] != 0) ? records_static : records_own;
-    int total = (int)im.tile_last[(size_t)v * ntiles + tile];  // records [0,total) of the span matter
+    const size_t tslot = (size_t)v * ntiles + tile;
+    // merged streams: a tile blended straight from the static stream holds frozen records only -- nothing to do
+    if (tile_src != nullptr && tile_src[tslot] != 0) return;
+    const uint2 range = ranges[tslot];
+    const char *records = records_own;
+    (void)records_static;
+    int total = (int)im.tile_last[tslot];  // records [0,total) of the span matter
+    // merged streams: everything at or behind L is frozen; the forward left {T, colour behind} at L in `snap`
+    const int L = (snap != nullptr && tile_dyn_last != nullptr) ? (int)tile_dyn_last[tslot] : 0x7FFFFFFF;
+    total = min(total, L);
     if (hdr->overflow) total = 0;
     if (total == 0) return;
     const int nbatch = (total + BATCH - 1) / BATCH;
@@ -858,7 +923,6 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         T_final[p] = inside ? im.final_T[(size_t)v * HW + pix] : 0.f;
         T[p] = T_final[p];
         last_contributor[p] = inside ? (int)im.n_contrib[(size_t)v * HW + pix] : 0;
-        warp_last = max(warp_last, last_contributor[p]);
         last_alpha[p] = 0.f;
         bg_dot_dpixel[p] = 0.f;
 #pragma unroll
@@ -868,6 +932,17 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
             dL_dpixel[p][ch] = inside ? dL_dpixels[((size_t)v * C + ch) * HW + pix] : 0.f;
             bg_dot_dpixel[p] += bg[ch] * dL_dpixel[p][ch];
         }
+        if (last_contributor[p] > L) {  // this pixel blended frozen records behind L: resume from the forward's snapshot
+            const float4 sn = snap[(size_t)v * HW + pix];
+            T[p] = sn.x;
+            accum_rec[p][0] = sn.y;
+            if (C == 3) {
+                accum_rec[p][1 % C] = sn.z;
+                accum_rec[p][2 % C] = sn.w;
+            }
+            last_contributor[p] = L;
+        }
+        warp_last = max(warp_last, last_contributor[p]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
@@ -1237,7 +1312,8 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_FWD, st);
     blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr,
-                                                        im.ranges, nullptr, g.depth, a->bg, g.hdr, im, out_color, out_depth);
+                                                        im.ranges, nullptr, nullptr, nullptr, nullptr, g.depth, a->bg, g.hdr, im, out_color,
+                                                        out_depth);
     prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
     return FNX_OK;
@@ -1388,7 +1464,7 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr, im.ranges,
-                                                        nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
+                                                        nullptr, nullptr, nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
     prof_begin(SEC_GEOM_BWD, st);
@@ -1417,16 +1493,21 @@ __device__ __forceinline__ float rec48_depth(const char *recs, size_t i) { retur
 __global__ void __launch_bounds__(256)
 merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat, const char *__restrict__ rec_dyn,
              const char *__restrict__ rec_stat, char *__restrict__ rec_merged, GeomHeader *__restrict__ hdr_dyn,
-             uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src) {
+             const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, uint2 *__restrict__ mranges,
+             uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
     __shared__ float s_depth[MERGE_SMEM];
     __shared__ unsigned long long s_base;
     const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
     const uint2 f = ranges_dyn[t], b = ranges_stat[t];
     int nf = (int)(f.y - f.x);
-    const int nb = (int)(b.y - b.x);
+    int nb = (int)(b.y - b.x);
+    // Static records behind the last one that the static-only blend of this tile used can never be reached once more
+    // occluders are inserted: a pixel's transmittance at a given static record only shrinks (rounding is monotone),
+    // so it terminates no later, and the alpha test does not depend on what lies in front.
+    if (hdr_stat->static_prepared) nb = min(nb, (int)static_last[t]);
     if (hdr_dyn->overflow) nf = 0;
     if (nf == 0) {
-        if (threadIdx.x == 0) { mranges[t] = b; tile_src[t] = 1u; }
+        if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
         return;
     }
     // the merged span of this tile is bump-allocated (tile order inside the merged stream does not matter; the ranges
@@ -1467,8 +1548,12 @@ merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__re
         }
         float4 *dst = reinterpret_cast<float4 *>(rec_merged + (ms + i + lo) * 48);
         dst[0] = r0; dst[1] = r1; dst[2] = r2;
+        if (i == nf - 1) tile_dyn_last[t] = (uint32_t)(i + lo + 1);  // dynamic depths ascend: this is the deepest one
     }
 }
+
+// marks a static stream as blended (its image scratch now holds tile_last of the static-only blend; tile_cached set by the blend)
+__global__ void static_prepared_kernel(GeomHeader *hdr) { hdr->static_prepared = 1; }
 
 static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat, int P_static,
                         void *merged_records, float *out_color, float *out_depth, cudaStream_t st) {
@@ -1479,20 +1564,48 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     FNX_REQUIRE((long long)P * V < (1ll << SLOT_BITS) && (long long)P_static * V < (1ll << SLOT_BITS), "too many Gaussians for masked records");
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
     GeomView g = geom_view(dyn->geom, P, V);
+    GeomView gs = geom_view(stat->geom, P_static, V);
     ImageView im = image_view(dyn->image, W, H, V);
     ImageView ims = image_view(stat->image, W, H, V);
     BinView b = bin_view(dyn->binning, dyn->binning_capacity, 3);
     BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
+    const bool tile_cache = (a->flags & FNX_STATIC_TILE_CACHE) != 0;
     dim3 grid(ntiles, V);
     prof_begin(SEC_PACK, st);
-    merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, im.mranges, im.tile_src);
+    merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, gs.hdr,
+                                       ims.tile_last, im.mranges, im.tile_src, im.tile_dyn_last);
     prof_end(SEC_PACK, st);
     FNX_LAUNCH_CHECK("merge_kernel");
     prof_begin(SEC_BLEND_FWD, st);
     blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
-                                                        g.depth, a->bg, g.hdr, im, out_color, out_depth);
+                                                        tile_cache ? ims.tile_cached : nullptr, im.tile_dyn_last, im.snap, g.depth, a->bg,
+                                                        g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
+    return FNX_OK;
+}
+
+// Blend the static stream alone, once: leaves the static-only image in out_color / out_depth (the buffers every later
+// fnx_raster_blend_merged(FNX_STATIC_TILE_CACHE) call must be given), the per-tile depth the static-only blend reaches
+// (bounds the static records a merge has to copy) and sets every tile's cached flag.
+static int static_prepare(const fnx_raster_args *a, const fnx_raster_scratch *stat, float *out_color, float *out_depth, cudaStream_t st) {
+    FNX_REQUIRE(a && stat && out_color && out_depth, "bad arguments");
+    FNX_REQUIRE(a->C == 3, "static streams are implemented for 3-channel records");
+    FNX_REQUIRE(stat->geom && stat->binning && stat->image, "scratch missing (run fnx_raster_forward(FNX_BIN_ONLY | FNX_ALL_FROZEN) first)");
+    const int P = a->P, V = a->V, W = a->W, H = a->H;
+    FNX_REQUIRE((long long)P * V < (1ll << SLOT_BITS), "too many Gaussians for masked records");
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
+    GeomView gs = geom_view(stat->geom, P, V);
+    ImageView ims = image_view(stat->image, W, H, V);
+    BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
+    FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_cached, 0, sizeof(uint32_t) * (size_t)ntiles * V, st));
+    FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_src, 0xFF, sizeof(uint32_t) * (size_t)ntiles * V, st));  // every tile: "from the static stream"
+    dim3 grid(ntiles, V);
+    blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, bs.records, bs.records, ims.ranges, ims.tile_src, ims.tile_cached,
+                                                        nullptr, nullptr, gs.depth, a->bg, gs.hdr, ims, out_color, out_depth);
+    FNX_LAUNCH_CHECK("blend_fwd_kernel");
+    static_prepared_kernel<<<1, 1, 0, st>>>(gs.hdr);
+    FNX_LAUNCH_CHECK("static_prepared_kernel");
     return FNX_OK;
 }
 
@@ -1511,7 +1624,7 @@ static int backward_merged(const fnx_raster_args *a, const fnx_raster_scratch *d
     dim3 grid(ntiles, V);
     prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
-                                                        a->bg, g.hdr, im, dL_dout_color, g.accum);
+                                                        im.tile_dyn_last, im.snap, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
     prof_begin(SEC_GEOM_BWD, st);
@@ -1577,6 +1690,22 @@ int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *
 int fnx_raster_blend_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
                             int32_t P_static, void *merged_records, float *out_color, float *out_depth, fnx_stream_t stream) {
     return blend_merged(dyn_args, dyn, stat, P_static, merged_records, out_color, out_depth, (cudaStream_t)stream);
+}
+int fnx_raster_static_prepare(const fnx_raster_args *static_args, const fnx_raster_scratch *stat, float *out_color, float *out_depth,
+                              fnx_stream_t stream) {
+    return static_prepare(static_args, stat, out_color, out_depth, (cudaStream_t)stream);
+}
+int fnx_raster_read_tiles(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, int32_t merged, uint32_t *ranges,
+                          uint32_t *tile_last, uint32_t *tile_src, uint32_t *tile_dyn_last, fnx_stream_t stream) {
+    FNX_REQUIRE(scratch && scratch->image, "no image scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    ImageView im = image_view(scratch->image, W, H, V);
+    const size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
+    if (ranges) FNX_CUDA_TRY(cudaMemcpyAsync(ranges, merged ? im.mranges : im.ranges, nt * 8, cudaMemcpyDeviceToDevice, st));
+    if (tile_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_last, im.tile_last, nt * 4, cudaMemcpyDeviceToDevice, st));
+    if (tile_src) FNX_CUDA_TRY(cudaMemcpyAsync(tile_src, im.tile_src, nt * 4, cudaMemcpyDeviceToDevice, st));
+    if (tile_dyn_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_dyn_last, im.tile_dyn_last, nt * 4, cudaMemcpyDeviceToDevice, st));
+    return FNX_OK;
 }
 int fnx_raster_backward_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
                                const void *merged_records, const int32_t *radii, const float *dL_dout_color,

@@ -33,6 +33,8 @@ struct GeomHeader {
     int overflow;             // 1 if num_rendered > capacity (nothing rendered)
     int pad;
     unsigned long long merge_cursor;  // bump allocator of fnx_raster_blend_merged's merged stream (reset per forward)
+    int static_prepared;      // static stream only: fnx_raster_static_prepare has blended it (tile_last / tile_cached valid)
+    int pad2;
 };
 
 struct GeomView {  // pointers into the geom scratch
@@ -65,6 +67,9 @@ struct ImageView {
     uint32_t *tile_last;     // [V*ntiles] max n_contrib over the tile's pixels (backward start)
     uint2 *mranges;          // [V*ntiles] merged ranges (static + dynamic streams), see fnx_raster_blend_merged
     uint32_t *tile_src;      // [V*ntiles] 0: the tile's span lives in the call's own record stream, 1: in the static one
+    uint32_t *tile_dyn_last; // [V*ntiles] merged streams: 1 + span index of the tile's last dynamic record (0: none)
+    uint32_t *tile_cached;   // [V*ntiles] static stream: 1 <=> the caller's out_color/out_depth hold this tile's static-only render
+    float4 *snap;            // [V*H*W] merged streams: {T, colour behind} right after the tile's last dynamic record
 };
 
 size_t geom_bytes(int P, int V);

@@ -244,15 +244,22 @@ class MergedRasterWorkspace:
     gradients are produced for the dynamic Gaussians only.  3 channels.  No allocation / host sync / events inside
     forward() and backward() (CUDA-graph capturable)."""
 
-    def __init__(self, dev, P_dyn, V, H, W, bg, dyn, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, margin=1.2):
-        """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations."""
+    def __init__(self, dev, P_dyn, V, H, W, bg, dyn, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, margin=1.2,
+                 static_prepare=True, static_tile_cache=True):
+        """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations.
+        static_prepare: blend the static stream alone once (fnx_raster_static_prepare), which bounds the static records
+        every later merge has to copy; static_tile_cache (needs static_prepare): tiles without a dynamic instance keep
+        their static-only pixels in self.color / self.depth instead of being re-blended every forward."""
         lib = L.lib()
         self.dev, self.C, self.P, self.V, self.H, self.W = torch.device(dev), 3, P_dyn, V, H, W
         self.P_static = static["means3D"].size(0)
         self.cam = (bg, view_matrix, proj_matrix, float(tan_fov_x), float(tan_fov_y))
         self._static = static
+        self.static_tile_cache = bool(static_tile_cache and static_prepare)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         with torch.cuda.device(self.dev):
+            self.color = torch.empty((V, 3, H, W), device=self.dev)
+            self.depth = torch.empty((V, 1, H, W), device=self.dev)
             # ---- static stream: exact sizing, once ----
             self._sbufs = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
             self.sargs, self.sscratch = L.RasterArgs(), L.RasterScratch()
@@ -264,6 +271,9 @@ class MergedRasterWorkspace:
             L.check(lib.fnx_raster_forward_ch3(C.byref(self.sargs), self._sbufs[0].cb, None, self._sbufs[1].cb, None, self._sbufs[2].cb,
                                                None, None, None, self.sradii.data_ptr(), C.byref(nr), C.byref(self.sscratch), st))
             self.R_static = int(nr.value)
+            if static_prepare:
+                L.check(lib.fnx_raster_static_prepare(C.byref(self.sargs), C.byref(self.sscratch), self.color.data_ptr(),
+                                                      self.depth.data_ptr(), st))
             # ---- dynamic stream: one exact binning to size the capacity ----
             tmp = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
             targs, tscratch = L.RasterArgs(), L.RasterScratch()
@@ -279,8 +289,6 @@ class MergedRasterWorkspace:
             self.geom, self.image = u8(lib.fnx_raster_geom_bytes(P_dyn, V)), u8(lib.fnx_raster_image_bytes(W, H, V))
             self.binning = u8(lib.fnx_raster_binning_bytes(self.capacity, 3))
             self.merged = u8(48 * (self.capacity + self.R_static) + 256)
-            self.color = torch.empty((V, 3, H, W), device=self.dev)
-            self.depth = torch.empty((V, 1, H, W), device=self.dev)
             self.grads = {"means3D": torch.empty((P_dyn, 3), device=self.dev)}
         self.count = torch.full((1,), -1, dtype=torch.int64).pin_memory()
         self._cbs = tuple(L.ALLOC_FN(RasterWorkspace._fixed(t)) for t in (self.geom, self.binning, self.image))
@@ -290,7 +298,8 @@ class MergedRasterWorkspace:
         lib = L.lib()
         bg, vm, pm, tfx, tfy = self.cam
         _fill_args(self.args, 3, self.P, self.V, self.H, self.W, bg, means3D, colors, opacities, scales, rotations, 1.0, vm, pm, tfx, tfy,
-                   L.FNX_BIN_ONLY | L.FNX_NO_HOST_SYNC, self.capacity, self.count)
+                   L.FNX_BIN_ONLY | L.FNX_NO_HOST_SYNC | (L.FNX_STATIC_TILE_CACHE if self.static_tile_cache else 0), self.capacity,
+                   self.count)
         self._keep = (means3D, colors, opacities, scales, rotations)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         nr = C.c_int64(0)
@@ -307,6 +316,19 @@ class MergedRasterWorkspace:
                                                    self.radii.data_ptr(), dL_dout_color.data_ptr(), C.byref(gr),
                                                    torch.cuda.current_stream(self.dev).cuda_stream))
         return self.grads
+
+    def tile_state(self):
+        """Per-tile state of the last forward as numpy arrays [V, tiles] (synchronises): merged span begin/end, records the
+        forward blended (tile_last), tile_src (1: static-only tile) and tile_dyn_last (where the backward starts)."""
+        nt = self.V * ((self.W + 15) // 16) * ((self.H + 15) // 16)
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=self.dev)
+        ranges, last, src, dyn = i32(nt, 2), i32(nt), i32(nt), i32(nt)
+        L.check(L.lib().fnx_raster_read_tiles(C.byref(self.scratch), self.W, self.H, self.V, 1, ranges.data_ptr(), last.data_ptr(),
+                                              src.data_ptr(), dyn.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
+        torch.cuda.synchronize(self.dev)
+        r = ranges.cpu().numpy().astype("int64")
+        return dict(begin=r[:, 0], end=r[:, 1], tile_last=last.cpu().numpy().astype("int64"), tile_src=src.cpu().numpy(),
+                    tile_dyn_last=dyn.cpu().numpy().astype("int64"))
 
     def num_rendered(self):
         """Dynamic instances of the last finished forward + the static stream's instances."""

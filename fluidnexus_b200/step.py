@@ -106,7 +106,8 @@ class PhysicalStep:
     """step(frame, view_ids, gt) -> dict of device scalars.  `cams`: list of camera objects with the attributes of
     FD/scene/camera.py (world_view_transform, full_proj_transform, FoVx, FoVy, image_width, image_height)."""
 
-    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda", overlap=True, static_cache=True):
+    def __init__(self, cams, channels, prm: StepParams = None, bg_color=None, device="cuda", overlap=True, static_cache=True,
+                 static_tile_cache=True):
         import math
         self.prm = prm or StepParams()
         self.dev = torch.device(device)
@@ -120,6 +121,7 @@ class PhysicalStep:
         self._loss_scratch, self._views = {}, {}
         self.capacity_margin = 1.2   # binning capacity = margin * instances of the sizing forward + 64k
         self.static_cache = static_cache  # bin the frozen background once per frame (MergedRasterWorkspace)
+        self.static_tile_cache = static_tile_cache  # ... and keep the pixels of tiles that hold no fluid instance
         self.lib = L.lib()
         # the view-independent physics terms run on a side stream next to the rasterizer (fork/join with events, also
         # inside a captured graph); overlap=False keeps everything on one stream
@@ -217,7 +219,7 @@ class PhysicalStep:
                 sta = dict(means3D=sl(fr.means3D, V, fr.P), colors=sl(fr.colors, V, fr.P), opacities=sl(fr.opacity, V, fr.P),
                            scales=sl(fr.scales, V, fr.P), rotations=sl(fr.rotations, V, fr.P))
                 ws = R.MergedRasterWorkspace(self.dev, V, nviews, self.H, self.W, self.bg, dyn, sta, vm, pm, self.tan_fov_x,
-                                             self.tan_fov_y, margin=self.capacity_margin)
+                                             self.tan_fov_y, margin=self.capacity_margin, static_tile_cache=self.static_tile_cache)
                 ws.dyn = dyn
             else:
                 ctx, _, _, _ = R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None,

@@ -68,6 +68,10 @@ unsigned long long fnx_launch_count(void);
 #define FNX_BIN_ONLY 4u     /* forward: stop after the record stream is packed (no blending; out_color/out_depth may be
                                NULL).  Used to build a stream that fnx_raster_blend_merged consumes. */
 #define FNX_ALL_FROZEN 8u   /* every Gaussian of this call is frozen (no gradients): marks all its records */
+#define FNX_STATIC_TILE_CACHE 16u /* fnx_raster_blend_merged only: tiles without any dynamic instance keep the pixels that
+                               fnx_raster_static_prepare (or an earlier call) left in out_color / out_depth instead of being
+                               blended again -- the frozen set and the cameras are fixed, so those pixels cannot change.
+                               The SAME out_color / out_depth buffers must be passed to every call. */
 
 typedef struct fnx_raster_args {
     /* sizes */
@@ -165,7 +169,15 @@ int fnx_raster_backward_ch3(const fnx_raster_args *a, const fnx_raster_scratch *
  * Same V, W, H, cameras and bg for both sets.  out_color [V,3,H,W], out_depth [V,1,H,W]. */
 int fnx_raster_blend_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
                             int32_t P_static, void *merged_records, float *out_color, float *out_depth, fnx_stream_t stream);
-/* Backward of the above: gradients for the DYNAMIC Gaussians only (g sized for dyn_args->P); radii = the dynamic
+/* Optional, once per static stream (after the FNX_BIN_ONLY | FNX_ALL_FROZEN forward, `static_args` = its args): blends
+ * the static stream alone into out_color / out_depth and records, per tile, how deep that blend reaches.  Afterwards
+ *   - merges copy only the static records a blend can reach (inserting occluders in front can only make a pixel
+ *     terminate earlier), and
+ *   - fnx_raster_blend_merged(FNX_STATIC_TILE_CACHE) skips tiles that hold no dynamic instance.
+ * Results of blend_merged / backward_merged are unchanged. */
+int fnx_raster_static_prepare(const fnx_raster_args *static_args, const fnx_raster_scratch *stat, float *out_color,
+                              float *out_depth, fnx_stream_t stream);
+/* Backward of fnx_raster_blend_merged: gradients for the DYNAMIC Gaussians only (g sized for dyn_args->P); radii = the dynamic
  * forward's radii. */
 int fnx_raster_backward_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
                                const void *merged_records, const int32_t *radii, const float *dL_dout_color,
@@ -291,6 +303,12 @@ int fnx_raster_read_geom(const fnx_raster_scratch *scratch, int32_t P, int32_t V
                          float *conic_opacity, uint32_t *tiles_touched, fnx_stream_t stream);
 int fnx_raster_read_image(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, float *final_T,
                           uint32_t *n_contrib, fnx_stream_t stream);
+/* Per-tile state [V, tiles] of the last forward (measurement / tests): ranges uint32 [.,2] (begin, end of the tile's
+ * span; merged != 0: in the merged stream of fnx_raster_blend_merged), tile_last (records of the span the blend
+ * used), and for merged streams tile_src (1: blended straight from the static stream) and tile_dyn_last (1 + span
+ * index of the last dynamic record: where the backward starts). */
+int fnx_raster_read_tiles(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, int32_t merged, uint32_t *ranges,
+                          uint32_t *tile_last, uint32_t *tile_src, uint32_t *tile_dyn_last, fnx_stream_t stream);
 
 #ifdef __cplusplus
 }

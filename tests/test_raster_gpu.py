@@ -221,3 +221,48 @@ def test_frozen_range_gives_identical_gradients_for_the_trainable_rows(libfnx):
         a, f = g_all[k].reshape(P, -1), g_frz[k].reshape(P, -1)
         assert rel(f[:nb].cpu().numpy(), a[:nb].cpu().numpy()) < 1e-5, k
         assert torch.all(f[nb:] == 0), k
+
+
+@pytest.mark.parametrize("prepare,tile_cache", [(False, False), (True, False), (True, True)])
+def test_merged_static_dynamic_streams_equal_concatenated_set(libfnx, prepare, tile_cache):
+    """MergedRasterWorkspace (static stream binned once, truncated to the depth the static-only blend reaches, tiles
+    without dynamic instances kept from the static-only render, backward resumed from the forward's snapshot at the
+    last dynamic record) against one plain forward/backward over [dynamic ; static] -- over several iterations in
+    which the dynamic set moves across tiles, leaves the image and comes back."""
+    dev = torch.device("cuda")
+    V, size, nd = 3, 128, 900
+    cams = S.make_cameras(5, size, device=dev)[:V]
+    view = torch.stack([c.world_view_transform.float() for c in cams]).contiguous()
+    proj = torch.stack([c.full_proj_transform.float() for c in cams]).contiguous()
+    import math
+    tfx, tfy = math.tan(cams[0].FoVx * 0.5), math.tan(cams[0].FoVy * 0.5)
+    dyn_np, sta_np = S.fluid_gaussians(nd, 3, seed=60, log_scale=-4.8), S.background_gaussians(5000, 3, seed=61)
+    d, s = dyn_np.torch(dev), sta_np.torch(dev)
+    key = dict(means3D="xyz", colors="colors", opacities="opacity", scales="scales", rotations="rotations")
+    dyn = {k: d[v].reshape(-1).contiguous() if k == "opacities" else d[v].contiguous() for k, v in key.items()}
+    sta = {k: s[v].reshape(-1).contiguous() if k == "opacities" else s[v].contiguous() for k, v in key.items()}
+    bg = torch.tensor([0.05, 0.1, 0.2], device=dev)
+    ws = R.MergedRasterWorkspace(dev, nd, V, size, size, bg, dyn, sta, view, proj, tfx, tfy, margin=3.0, static_prepare=prepare,
+                                 static_tile_cache=tile_cache)
+    base = dyn["means3D"].clone()
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    offsets = [(0.0, 0.0, 0.0), (0.08, 0.0, 0.0), (-0.1, 0.05, 0.02), (5.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.02, -0.04, 0.0)]
+    seen_static_only = 0
+    for it, off in enumerate(offsets):
+        dyn["means3D"].copy_(base + torch.tensor(off, device=dev))
+        img = ws.forward(dyn["means3D"], dyn["colors"], dyn["opacities"], dyn["scales"], dyn["rotations"])
+        dL = (torch.randn(V, 3, size, size, generator=gen)).to(dev)
+        g = ws.backward(dL)["means3D"].clone()
+        cat = lambda k: torch.cat([dyn[k], sta[k]], 0).contiguous()
+        ctx, ref_img, _, ref_depth = R.raster_forward(3, bg, cat("means3D"), cat("colors"), cat("opacities"), cat("scales"),
+                                                      cat("rotations"), 1.0, None, view, proj, tfx, tfy, size, size, speculative=False)
+        assert torch.equal(img, ref_img), f"iteration {it}: image differs, max|d| = {(img - ref_img).abs().max().item()}"
+        assert torch.equal(ws.depth, ref_depth), f"iteration {it}: depth differs"
+        gref = R.raster_backward(ctx, dL)["means3D"][:nd]
+        r = rel(g.cpu().numpy(), gref.cpu().numpy()) if float(gref.abs().max()) > 0 else float(g.abs().max())
+        assert r < 2e-5, (it, r)
+        ts = ws.tile_state()
+        seen_static_only += int((ts["tile_src"] != 0).sum())
+        assert np.all(ts["tile_dyn_last"][ts["tile_src"] != 0] == 0)
+        assert np.all(ts["tile_dyn_last"][ts["tile_src"] == 0] >= 1)
+    assert seen_static_only > 0

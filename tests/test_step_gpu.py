@@ -146,5 +146,7 @@ def test_static_background_cache_equals_full_rebinning(libfnx):
             losses.append(float(ps.total_loss(out)))
         res[cache] = (imgs, losses, fr.e.clone())
     assert torch.equal(res[False][0][0], res[True][0][0])           # first iteration: identical inputs -> identical image
+    for a, b in zip(res[False][0], res[True][0]):                   # later ones: parameters agree to ~1e-7, images to rounding
+        assert (a - b).abs().max() < 1e-4
     assert np.allclose(res[False][1], res[True][1], rtol=1e-5)
     assert (res[False][2] - res[True][2]).abs().max() < 1e-6
