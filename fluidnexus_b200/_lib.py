@@ -16,6 +16,7 @@ FNX_EXACT_RECT = 2
 FNX_BIN_ONLY = 4
 FNX_ALL_FROZEN = 8
 FNX_STATIC_TILE_CACHE = 16
+FNX_BUCKET_BINNING = 32
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 

@@ -86,6 +86,8 @@ ImageView image_view(void *chunk, int W, int H, int V) {
     im.tile_src = carve<uint32_t>(p, nt);
     im.tile_dyn_last = carve<uint32_t>(p, nt);
     im.tile_cached = carve<uint32_t>(p, nt);
+    im.tile_count = carve<uint32_t>(p, 2 * nt);  // count and cursor are contiguous: one memset clears both
+    im.tile_cursor = im.tile_count + nt;
     im.snap = carve<float4>(p, hw);
     return im;
 }
@@ -117,6 +119,8 @@ BinView bin_view(void *chunk, long long cap, int C) {
     b.tvals_in = carve<uint32_t>(p, n);
     b.tvals_out = carve<uint32_t>(p, n);
     b.records = carve<char>(p, n * (size_t)(C == 3 ? 48 : 32));
+    b.bkeys = carve<unsigned long long>(p, n);
+    b.bkeys2 = carve<unsigned long long>(p, n);
     b.cub_temp_bytes = bin_cub_bytes((long long)n);
     b.cub_temp = carve<char>(p, b.cub_temp_bytes);
     return b;
@@ -303,7 +307,8 @@ preprocess_kernel(int P, int V, const float *__restrict__ means3D, const float3 
                   const float4 *__restrict__ rotations, const float *__restrict__ opacities,
                   const float *__restrict__ cov3D_precomp, const float *__restrict__ view_matrix,
                   const float *__restrict__ proj_matrix, int W, int H, float tan_fov_x, float tan_fov_y, float focal_x,
-                  float focal_y, int gx, int gy, bool exact_rect, int *__restrict__ radii, GeomView g) {
+                  float focal_y, int gx, int gy, bool exact_rect, int *__restrict__ radii, GeomView g,
+                  uint32_t *__restrict__ tile_count /* bucket binning: per-tile instance histogram, or NULL */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -370,10 +375,15 @@ preprocess_kernel(int P, int V, const float *__restrict__ means3D, const float3 
         job.w = rmax.x - rmin.x;
         job.n = job.w * (rmax.y - rmin.y);
         // count the tiles that can actually receive a contribution
-        if (!job.tc.active) {
+        if (!job.tc.active && tile_count == nullptr) {
             cnt = job.n;
         } else if (job.n <= SERIAL_TILES) {
-            for (int t = 0; t < job.n; t++) cnt += tile_needed(job.tc, job.xy, job.x0 + t % job.w, job.y0 + t / job.w) ? 1u : 0u;
+            for (int t = 0; t < job.n; t++) {
+                const int tx = job.x0 + t % job.w, ty = job.y0 + t / job.w;
+                if (!tile_needed(job.tc, job.xy, tx, ty)) continue;
+                cnt++;
+                if (tile_count != nullptr) atomicAdd(&tile_count[(size_t)v * gx * gy + ty * gx + tx], 1u);
+            }
         } else {
             big = true;
         }
@@ -385,7 +395,12 @@ preprocess_kernel(int P, int V, const float *__restrict__ means3D, const float3 
         pending &= pending - 1;
         const TileJob j = bcast_job(job, src);
         uint32_t c = 0;
-        for (int t = lane; t < j.n; t += 32) c += tile_needed(j.tc, j.xy, j.x0 + t % j.w, j.y0 + t / j.w) ? 1u : 0u;
+        for (int t = lane; t < j.n; t += 32) {
+            const int tx = j.x0 + t % j.w, ty = j.y0 + t / j.w;
+            if (!tile_needed(j.tc, j.xy, tx, ty)) continue;
+            c++;
+            if (tile_count != nullptr) atomicAdd(&tile_count[(size_t)v * gx * gy + ty * gx + tx], 1u);
+        }
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == src) cnt = c;
     }
@@ -393,9 +408,11 @@ preprocess_kernel(int P, int V, const float *__restrict__ means3D, const float3 
     if (i >= P) return;
     radii[slot] = visible ? radius : 0;
     g.tiles_touched[slot] = cnt;
-    g.dvals_in[slot] = (uint32_t)slot;
-    // invisible Gaussians sort last in their view
-    g.dkeys_in[slot] = ((unsigned long long)v << 32) | (visible ? (unsigned long long)__float_as_uint(depth) : 0xFFFFFFFFull);
+    if (tile_count == nullptr) {
+        g.dvals_in[slot] = (uint32_t)slot;
+        // invisible Gaussians sort last in their view
+        g.dkeys_in[slot] = ((unsigned long long)v << 32) | (visible ? (unsigned long long)__float_as_uint(depth) : 0xFFFFFFFFull);
+    }
     if (visible) {
         g.depth[slot] = depth;
         g.xy[slot] = job.xy;
@@ -476,6 +493,115 @@ emit_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict
                 b.tvals_in[pos] = sl;
             }
             o += __popc(m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bucket binning (the dynamic set of merged streams): no global sort at all.  The preprocess histograms the instances
+// per tile, one CTA scans the histogram into bucket offsets, the emit below drops each instance's (depth, slot) key
+// into its tile's bucket in arbitrary order, and the per-tile merge kernel sorts its bucket in shared memory.  The key
+// (depth bits, slot) is a total order equal to the reference's stable (tile, depth) radix sort over index-ordered
+// instances (rasterizer_impl.cu:67-104, :285-290), so the result does not depend on the order of the atomics.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int nt, const uint32_t *__restrict__ tile_count, uint2 *__restrict__ ranges, GeomHeader *__restrict__ hdr,
+                 long long capacity, long long *pinned_out) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nt; base += 1024) {
+        const int t = base + threadIdx.x;
+        const uint32_t c = t < nt ? tile_count[t] : 0u;
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (warp > 0 ? s_warp[warp - 1] : 0u) + s_carry;
+        if (t < nt) ranges[t] = make_uint2(incl - c, incl);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long total = (long long)s_carry;
+        hdr->num_rendered = total;
+        hdr->capacity = capacity;
+        hdr->overflow = (capacity >= 0 && total > capacity) ? 1 : 0;
+        hdr->merge_cursor = 0ull;
+        hdr->static_prepared = 0;
+        if (pinned_out) *pinned_out = total;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+emit_bucket_kernel(int n, int P, int gx, int gy, bool exact_rect, const int *__restrict__ radii, GeomView g,
+                   const uint2 *__restrict__ ranges, uint32_t *__restrict__ tile_cursor, unsigned long long *__restrict__ bkeys) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (g.hdr->overflow) return;
+    uint32_t slot = 0, cnt = 0, tile_base = 0;
+    unsigned long long key = 0ull;
+    bool big = false;
+    TileJob job;
+    job.xy = make_float2(0.f, 0.f);
+    job.tc.a = job.tc.b = job.tc.c = job.tc.tau = 0.f;
+    job.tc.active = false;
+    job.x0 = job.y0 = job.w = job.n = 0;
+    if (k < n) {
+        slot = (uint32_t)k;
+        cnt = g.tiles_touched[slot];
+    }
+    if (cnt != 0) {
+        const int v = slot / P;
+        tile_base = (uint32_t)v * gx * gy;
+        job.xy = g.xy[slot];
+        key = ((unsigned long long)__float_as_uint(g.depth[slot]) << 32) | slot;
+        uint2 rmin, rmax;
+        get_rect(job.xy, radii[slot], rmin, rmax, gx, gy);
+        job.tc = make_cull(g.conic_o[slot], exact_rect);
+        job.x0 = rmin.x; job.y0 = rmin.y;
+        job.w = rmax.x - rmin.x;
+        job.n = job.w * (rmax.y - rmin.y);
+        if (job.n <= SERIAL_TILES) {
+            for (int t = 0; t < job.n; t++) {
+                const int tx = job.x0 + t % job.w, ty = job.y0 + t / job.w;
+                if (!tile_needed(job.tc, job.xy, tx, ty)) continue;
+                const uint32_t tl = tile_base + ty * gx + tx;
+                bkeys[ranges[tl].x + atomicAdd(&tile_cursor[tl], 1u)] = key;
+            }
+        } else {
+            big = true;
+        }
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, big);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const TileJob j = bcast_job(job, src);
+        const unsigned long long ky = __shfl_sync(0xffffffffu, key, src);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tile_base, src);
+        for (int t = lane; t < j.n; t += 32) {
+            const int tx = j.x0 + t % j.w, ty = j.y0 + t / j.w;
+            if (!tile_needed(j.tc, j.xy, tx, ty)) continue;
+            const uint32_t tl = tb + ty * gx + tx;
+            bkeys[ranges[tl].x + atomicAdd(&tile_cursor[tl], 1u)] = ky;
         }
     }
 }
@@ -1360,13 +1486,40 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
     ImageView im = image_view(scratch->image, W, H, V);
 
     dim3 pgrid((P + 255) / 256, V);
+    const bool bucket = (a->flags & FNX_BUCKET_BINNING) != 0;
+    if (bucket) {
+        FNX_REQUIRE(C == 3 && no_sync && (a->flags & FNX_BIN_ONLY), "FNX_BUCKET_BINNING needs C == 3, FNX_BIN_ONLY and FNX_NO_HOST_SYNC");
+        const int nt = gx * gy * V;
+        FNX_CUDA_TRY(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)nt, st));  // histogram + cursors
+    }
     prof_begin(SEC_PREPROCESS, st);
     preprocess_kernel<<<pgrid, 256, 0, st>>>(P, V, a->means3D, (const float3 *)a->scales, a->scale_modifier,
                                              (const float4 *)a->rotations, a->opacities, a->cov3D_precomp, a->view_matrix,
                                              a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y, gx, gy,
-                                             exact_rect, radii, g);
+                                             exact_rect, radii, g, bucket ? im.tile_count : nullptr);
     prof_end(SEC_PREPROCESS, st);
     FNX_LAUNCH_CHECK("preprocess_kernel");
+    if (bucket) {  // histogram -> bucket offsets -> unsorted per-tile buckets; fnx_raster_blend_merged sorts and merges them
+        const long long bcap = a->instance_capacity_hint;
+        const int nt = gx * gy * V;
+        prof_begin(SEC_EMIT, st);
+        tile_scan_kernel<<<1, 1024, 0, st>>>(nt, im.tile_count, im.ranges, g.hdr, bcap, (long long *)a->num_rendered_pinned);
+        FNX_LAUNCH_CHECK("tile_scan_kernel");
+        scratch->binning_bytes = binning_bytes(bcap, C);
+        scratch->binning = ab(cb, scratch->binning_bytes);
+        if (!scratch->binning) {
+            set_error("allocation callback returned NULL");
+            return FNX_ERR_ALLOC;
+        }
+        scratch->binning_capacity = bcap;
+        scratch->check_slot = -1;
+        BinView b = bin_view(scratch->binning, bcap, C);
+        emit_bucket_kernel<<<(P * V + 255) / 256, 256, 0, st>>>(P * V, P, gx, gy, exact_rect, radii, g, im.ranges, im.tile_cursor, b.bkeys);
+        prof_end(SEC_EMIT, st);
+        FNX_LAUNCH_CHECK("emit_bucket_kernel");
+        *num_rendered_host = -1;
+        return FNX_OK;
+    }
     prof_begin(SEC_DEPTH_SORT, st);
     size_t tb = g.cub_temp_bytes;
     const int dbits = 32 + ceil_log2_u64((uint64_t)V);
@@ -1552,6 +1705,101 @@ merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__re
     }
 }
 
+// Bucket-binned dynamic set (emit_bucket_kernel): sort the tile's (depth, slot) keys in shared memory, build the dynamic
+// records from the per-Gaussian state (what pack_kernel does for a sorted stream) and merge them with the static span.
+constexpr int SORT_CAP = 2048;  // keys sorted in shared memory; larger buckets take the rank-sort path through bkeys2
+
+__global__ void __launch_bounds__(256)
+merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat,
+                    const unsigned long long *__restrict__ bkeys, unsigned long long *__restrict__ bkeys2, GeomView g,
+                    const float *__restrict__ colors, const char *__restrict__ rec_stat, char *__restrict__ rec_merged,
+                    const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, uint2 *__restrict__ mranges,
+                    uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
+    __shared__ unsigned long long s_key[SORT_CAP];
+    __shared__ unsigned long long s_base;
+    const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
+    const uint2 f = ranges_dyn[t], b = ranges_stat[t];
+    int nf = (int)(f.y - f.x);
+    int nb = (int)(b.y - b.x);
+    if (hdr_stat->static_prepared) nb = min(nb, (int)static_last[t]);  // see merge_kernel
+    if (g.hdr->overflow) nf = 0;
+    if (nf == 0) {
+        if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        s_base = atomicAdd(&g.hdr->merge_cursor, (unsigned long long)(nf + nb));
+        mranges[t] = make_uint2((uint32_t)s_base, (uint32_t)(s_base + nf + nb));
+        tile_src[t] = 0u;
+    }
+    const unsigned long long *sk;
+    if (nf <= SORT_CAP) {
+        int n2 = 2;
+        while (n2 < nf) n2 <<= 1;
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) s_key[i] = i < nf ? bkeys[(size_t)f.x + i] : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int idx = threadIdx.x; idx < (n2 >> 1); idx += blockDim.x) {
+                    const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));  // bit j clear
+                    const int l = i | j;
+                    const unsigned long long x = s_key[i], y = s_key[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_key[i] = y; s_key[l] = x; }
+                }
+                __syncthreads();
+            }
+        sk = s_key;
+    } else {  // rare: rank sort (keys are unique) into the global scratch
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+            const unsigned long long ki = bkeys[(size_t)f.x + i];
+            int r = 0;
+            for (int q = 0; q < nf; q++) r += bkeys[(size_t)f.x + q] < ki ? 1 : 0;
+            bkeys2[(size_t)f.x + r] = ki;
+        }
+        __syncthreads();
+        sk = bkeys2 + f.x;
+    }
+    const size_t ms = (size_t)s_base;
+    // static records: shifted by the number of dynamic records in front of them (depth <= theirs; depths are positive
+    // floats, so their bit patterns order like the values)
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(rec_stat + ((size_t)b.x + j) * 48);
+        const float4 r0 = src[0], r1 = src[1], r2 = src[2];
+        const uint32_t d = __float_as_uint(r2.z);
+        int lo = 0, hi = nf;  // upper bound: first dynamic depth > d
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)(sk[mid] >> 32) <= d) lo = mid + 1; else hi = mid;
+        }
+        float4 *dst = reinterpret_cast<float4 *>(rec_merged + (ms + j + lo) * 48);
+        dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    }
+    // dynamic records: built here, shifted by the number of static records strictly in front of them
+    const uint32_t tl = (uint32_t)blockIdx.x;
+    const int tx = tl % gx, ty = tl / gx;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const unsigned long long key = sk[i];
+        const uint32_t d = (uint32_t)(key >> 32);
+        uint32_t slot = (uint32_t)key;
+        int lo = 0, hi = nb;  // lower bound: first static depth >= d
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__float_as_uint(rec48_depth(rec_stat, (size_t)b.x + mid)) < d) lo = mid + 1; else hi = mid;
+        }
+        const float2 xy = g.xy[slot];
+        const float4 co = g.conic_o[slot];
+        const uint32_t gi = slot % (uint32_t)P;
+        const float c0 = colors[3 * (size_t)gi], c1 = colors[3 * (size_t)gi + 1], c2 = colors[3 * (size_t)gi + 2];
+        slot |= patch_mask(xy, co, tx, ty, exact_rect) << SLOT_BITS;
+        float4 *dst = reinterpret_cast<float4 *>(rec_merged + (ms + i + lo) * 48);
+        dst[0] = make_float4(xy.x, xy.y, co.x, co.y);
+        dst[1] = make_float4(co.z, co.w, c0, c1);
+        dst[2] = make_float4(c2, __uint_as_float(slot), __uint_as_float(d), 0.f);
+        if (i == nf - 1) tile_dyn_last[t] = (uint32_t)(i + lo + 1);
+    }
+}
+
 // marks a static stream as blended (its image scratch now holds tile_last of the static-only blend; tile_cached set by the blend)
 __global__ void static_prepared_kernel(GeomHeader *hdr) { hdr->static_prepared = 1; }
 
@@ -1572,8 +1820,13 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     const bool tile_cache = (a->flags & FNX_STATIC_TILE_CACHE) != 0;
     dim3 grid(ntiles, V);
     prof_begin(SEC_PACK, st);
-    merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, gs.hdr,
-                                       ims.tile_last, im.mranges, im.tile_src, im.tile_dyn_last);
+    if (a->flags & FNX_BUCKET_BINNING)
+        merge_bucket_kernel<<<grid, 256, 0, st>>>(ntiles, P, gx, (a->flags & FNX_EXACT_RECT) != 0, im.ranges, ims.ranges, b.bkeys, b.bkeys2, g,
+                                                  a->colors, bs.records, (char *)merged_records, gs.hdr, ims.tile_last, im.mranges,
+                                                  im.tile_src, im.tile_dyn_last);
+    else
+        merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, gs.hdr,
+                                           ims.tile_last, im.mranges, im.tile_src, im.tile_dyn_last);
     prof_end(SEC_PACK, st);
     FNX_LAUNCH_CHECK("merge_kernel");
     prof_begin(SEC_BLEND_FWD, st);

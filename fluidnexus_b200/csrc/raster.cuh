@@ -56,6 +56,8 @@ struct BinView {
     uint32_t *tkeys_in, *tkeys_out;  // [cap] global tile id = v*ntiles + tile
     uint32_t *tvals_in, *tvals_out;  // [cap] slot
     char *records;                   // [cap * RecBytes]
+    unsigned long long *bkeys;       // [cap] bucket binning: (depth bits << 32 | slot), grouped by tile, unsorted inside a tile
+    unsigned long long *bkeys2;      // [cap] sorted copy, used only by tiles whose bucket exceeds the shared-memory sort
     void *cub_temp;
     size_t cub_temp_bytes;
 };
@@ -70,6 +72,8 @@ struct ImageView {
     uint32_t *tile_dyn_last; // [V*ntiles] merged streams: 1 + span index of the tile's last dynamic record (0: none)
     uint32_t *tile_cached;   // [V*ntiles] static stream: 1 <=> the caller's out_color/out_depth hold this tile's static-only render
     float4 *snap;            // [V*H*W] merged streams: {T, colour behind} right after the tile's last dynamic record
+    uint32_t *tile_count;    // [V*ntiles] bucket binning: instances per tile (histogram written by the preprocess)
+    uint32_t *tile_cursor;   // [V*ntiles] bucket binning: fill cursor of the tile's bucket
 };
 
 size_t geom_bytes(int P, int V);

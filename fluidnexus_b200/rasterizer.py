@@ -245,7 +245,7 @@ class MergedRasterWorkspace:
     forward() and backward() (CUDA-graph capturable)."""
 
     def __init__(self, dev, P_dyn, V, H, W, bg, dyn, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, margin=1.2,
-                 static_prepare=True, static_tile_cache=True):
+                 static_prepare=True, static_tile_cache=True, bucket_binning=True):
         """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations.
         static_prepare: blend the static stream alone once (fnx_raster_static_prepare), which bounds the static records
         every later merge has to copy; static_tile_cache (needs static_prepare): tiles without a dynamic instance keep
@@ -256,6 +256,7 @@ class MergedRasterWorkspace:
         self.cam = (bg, view_matrix, proj_matrix, float(tan_fov_x), float(tan_fov_y))
         self._static = static
         self.static_tile_cache = bool(static_tile_cache and static_prepare)
+        self.bucket_binning = bool(bucket_binning)  # per-tile buckets sorted inside the merge instead of two global radix sorts
         st = torch.cuda.current_stream(self.dev).cuda_stream
         with torch.cuda.device(self.dev):
             self.color = torch.empty((V, 3, H, W), device=self.dev)
@@ -298,8 +299,8 @@ class MergedRasterWorkspace:
         lib = L.lib()
         bg, vm, pm, tfx, tfy = self.cam
         _fill_args(self.args, 3, self.P, self.V, self.H, self.W, bg, means3D, colors, opacities, scales, rotations, 1.0, vm, pm, tfx, tfy,
-                   L.FNX_BIN_ONLY | L.FNX_NO_HOST_SYNC | (L.FNX_STATIC_TILE_CACHE if self.static_tile_cache else 0), self.capacity,
-                   self.count)
+                   L.FNX_BIN_ONLY | L.FNX_NO_HOST_SYNC | (L.FNX_STATIC_TILE_CACHE if self.static_tile_cache else 0)
+                   | (L.FNX_BUCKET_BINNING if self.bucket_binning else 0), self.capacity, self.count)
         self._keep = (means3D, colors, opacities, scales, rotations)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         nr = C.c_int64(0)

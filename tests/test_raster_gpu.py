@@ -223,27 +223,34 @@ def test_frozen_range_gives_identical_gradients_for_the_trainable_rows(libfnx):
         assert torch.all(f[nb:] == 0), k
 
 
-@pytest.mark.parametrize("prepare,tile_cache", [(False, False), (True, False), (True, True)])
-def test_merged_static_dynamic_streams_equal_concatenated_set(libfnx, prepare, tile_cache):
+@pytest.mark.parametrize("prepare,tile_cache,bucket,dense", [(False, False, False, False), (True, False, False, False),
+                                                             (True, True, False, False), (False, False, True, False),
+                                                             (True, True, True, False), (True, True, True, True)])
+def test_merged_static_dynamic_streams_equal_concatenated_set(libfnx, prepare, tile_cache, bucket, dense):
     """MergedRasterWorkspace (static stream binned once, truncated to the depth the static-only blend reaches, tiles
     without dynamic instances kept from the static-only render, backward resumed from the forward's snapshot at the
     last dynamic record) against one plain forward/backward over [dynamic ; static] -- over several iterations in
-    which the dynamic set moves across tiles, leaves the image and comes back."""
+    which the dynamic set moves across tiles, leaves the image and comes back.  bucket: per-tile buckets sorted in shared
+    memory instead of two global radix sorts; dense: > 2048 dynamic instances in one tile (the rank-sort path)."""
     dev = torch.device("cuda")
-    V, size, nd = 3, 128, 900
+    V, size, nd = (3, 128, 900) if not dense else (2, 64, 9000)
     cams = S.make_cameras(5, size, device=dev)[:V]
     view = torch.stack([c.world_view_transform.float() for c in cams]).contiguous()
     proj = torch.stack([c.full_proj_transform.float() for c in cams]).contiguous()
     import math
     tfx, tfy = math.tan(cams[0].FoVx * 0.5), math.tan(cams[0].FoVy * 0.5)
     dyn_np, sta_np = S.fluid_gaussians(nd, 3, seed=60, log_scale=-4.8), S.background_gaussians(5000, 3, seed=61)
+    if dense:  # squeeze the plume into a few tiles and make it nearly transparent so that nothing saturates early
+        c = dyn_np.xyz.mean(0, keepdims=True)
+        dyn_np.xyz = (c + (dyn_np.xyz - c) * 0.25).astype(np.float32)
+        dyn_np.opacity = (dyn_np.opacity * 0.1).astype(np.float32)
     d, s = dyn_np.torch(dev), sta_np.torch(dev)
     key = dict(means3D="xyz", colors="colors", opacities="opacity", scales="scales", rotations="rotations")
     dyn = {k: d[v].reshape(-1).contiguous() if k == "opacities" else d[v].contiguous() for k, v in key.items()}
     sta = {k: s[v].reshape(-1).contiguous() if k == "opacities" else s[v].contiguous() for k, v in key.items()}
     bg = torch.tensor([0.05, 0.1, 0.2], device=dev)
     ws = R.MergedRasterWorkspace(dev, nd, V, size, size, bg, dyn, sta, view, proj, tfx, tfy, margin=3.0, static_prepare=prepare,
-                                 static_tile_cache=tile_cache)
+                                 static_tile_cache=tile_cache, bucket_binning=bucket)
     base = dyn["means3D"].clone()
     gen = torch.Generator(device="cpu").manual_seed(5)
     offsets = [(0.0, 0.0, 0.0), (0.08, 0.0, 0.0), (-0.1, 0.05, 0.02), (5.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.02, -0.04, 0.0)]
@@ -266,3 +273,5 @@ def test_merged_static_dynamic_streams_equal_concatenated_set(libfnx, prepare, t
         assert np.all(ts["tile_dyn_last"][ts["tile_src"] != 0] == 0)
         assert np.all(ts["tile_dyn_last"][ts["tile_src"] == 0] >= 1)
     assert seen_static_only > 0
+    if dense:
+        assert int((ts["end"] - ts["begin"]).max()) > 2048
