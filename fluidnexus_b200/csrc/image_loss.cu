@@ -6,16 +6,21 @@
 //                                five grouped 11x11 conv2d forward + their backward)
 //   grey conversion              FD/entries_fluid_nexus/train_physical_particle.py:356-360
 //   weighting                    FD/entries_scalar_real/train_physical_particle.py:346-347
-// with two kernels: (1) per 16x16 tile with a 5-pixel halo, separable 11-tap Gaussian of {x, y, x^2, y^2, xy}, the SSIM
-// map, its three partial-derivative maps and the per-view loss sums; (2) separable Gaussian of the derivative maps ->
-// dL/dimage, with the L1 sign term added.  Zero padding like F.conv2d(padding=5).
+// with two kernels: (1) per 32x32 tile with a 5-pixel halo, register-tiled separable 11-tap Gaussian of
+// {x, y, x^2, y^2, xy}, the SSIM map, its three partial-derivative maps and the per-view loss means; (2) separable
+// Gaussian of the derivative maps -> dL/dimage, with the L1 sign term added.  Zero padding like F.conv2d(padding=5).
 #include "common.cuh"
 
 namespace fnx {
 
-constexpr int LT = 16;           // tile edge
-constexpr int HALO = 5;          // window 11
-constexpr int LE = LT + 2 * HALO;  // 26
+constexpr int TW = 32, TH = 32;    // output tile of one CTA
+constexpr int HALO = 5;            // window 11
+constexpr int EW = TW + 2 * HALO;  // 42 input columns
+constexpr int EH = TH + 2 * HALO;  // 42 input rows
+constexpr int ES = EW + 1;         // padded row stride of the input tile (conflict-free strip reads, see pass A)
+constexpr int NT = 256;            // threads per CTA
+constexpr int SEG = 8;             // pass A: outputs per thread along x
+constexpr int RSEG = 4;            // pass B: outputs per thread along y
 
 struct Win {
     float g[11];
@@ -43,60 +48,87 @@ __device__ __forceinline__ float load_px(const float *__restrict__ img, int C, i
     return s / C;  // torch.mean over the channel dim
 }
 
+// Register-tiled separable 11-tap Gaussian.  Pass A (rows): a thread owns SEG consecutive outputs of one input row: it
+// pulls SEG+10 inputs into registers once and produces SEG x Q filtered values.  Pass B (columns): a thread owns RSEG
+// consecutive outputs of one column and pulls RSEG+10 rows.  Per output that is (SEG+10)/SEG + (RSEG+10)/RSEG shared
+// loads per quantity instead of 22.
+
 // pass 1: SSIM map + derivative maps + loss sums.  grid (tiles_x, tiles_y, V*Ce), Ce = grey ? 1 : C
-__global__ void __launch_bounds__(LT *LT)
+__global__ void __launch_bounds__(NT, 3)
 ssim_fwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__restrict__ img, const float *__restrict__ gt,
-                Win win, float *__restrict__ maps /*[V*Ce][3][H][W]*/, float *__restrict__ l1_sum, float *__restrict__ ssim_sum) {
-    __shared__ float sx[LE][LE + 1], sy[LE][LE + 1];
-    __shared__ float hq[5][LE][LT + 1];
-    __shared__ float red[2][LT * LT / 32];
+                Win win, float inv_n, float *__restrict__ maps /*[V*Ce][3][H][W]*/, float *__restrict__ l1_sum,
+                float *__restrict__ ssim_sum) {
+    __shared__ float sx[EH][ES], sy[EH][ES];
+    __shared__ float hq[5][EH][TW];
+    __shared__ float red[2][NT / 32];
     const int vc = blockIdx.z, v = vc / Ce, c = vc % Ce;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
-    const int tid = threadIdx.y * LT + threadIdx.x;
-    for (int k = tid; k < LE * LE; k += LT * LT) {
-        const int ly = k / LE, lx = k % LE;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < EH * EW; k += NT) {
+        const int ly = k / EW, lx = k % EW;
         sx[ly][lx] = load_px(img, C, H, W, v, c, grey, y0 + ly - HALO, x0 + lx - HALO);
         sy[ly][lx] = load_px(gt, C, H, W, v, c, grey, y0 + ly - HALO, x0 + lx - HALO);
     }
     __syncthreads();
-    // horizontal 11-tap of the five products
-    for (int k = tid; k < LE * LT; k += LT * LT) {
-        const int ly = k / LT, lx = k % LT;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    // pass A: EH rows x (TW / SEG) strips
+    for (int k = tid; k < EH * (TW / SEG); k += NT) {
+        const int ly = k / (TW / SEG), s0 = (k % (TW / SEG)) * SEG;
+        float x[SEG + 10], y[SEG + 10];
 #pragma unroll
-        for (int t = 0; t < 11; t++) {
-            const float x = sx[ly][lx + t], y = sy[ly][lx + t], w = win.g[t];
-            a0 += w * x; a1 += w * y; a2 += w * x * x; a3 += w * y * y; a4 += w * x * y;
+        for (int i = 0; i < SEG + 10; i++) { x[i] = sx[ly][s0 + i]; y[i] = sy[ly][s0 + i]; }
+#pragma unroll
+        for (int o = 0; o < SEG; o++) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 11; t++) {
+                const float w = win.g[t], xv = x[o + t], yv = y[o + t];
+                a0 += w * xv; a1 += w * yv; a2 += w * xv * xv; a3 += w * yv * yv; a4 += w * xv * yv;
+            }
+            hq[0][ly][s0 + o] = a0; hq[1][ly][s0 + o] = a1; hq[2][ly][s0 + o] = a2; hq[3][ly][s0 + o] = a3; hq[4][ly][s0 + o] = a4;
         }
-        hq[0][ly][lx] = a0; hq[1][ly][lx] = a1; hq[2][ly][lx] = a2; hq[3][ly][lx] = a3; hq[4][ly][lx] = a4;
     }
     __syncthreads();
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int px = x0 + lx, py = y0 + ly;
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    // pass B: TW columns x (TH / RSEG) strips; lane = column
+    const int lx = tid % TW, r0 = (tid / TW) * RSEG;
+    float mu1[RSEG], mu2[RSEG], e11[RSEG], e22[RSEG], e12[RSEG];
 #pragma unroll
-    for (int t = 0; t < 11; t++) {
-        const float w = win.g[t];
-        mu1 += w * hq[0][ly + t][lx]; mu2 += w * hq[1][ly + t][lx];
-        e11 += w * hq[2][ly + t][lx]; e22 += w * hq[3][ly + t][lx]; e12 += w * hq[4][ly + t][lx];
+    for (int o = 0; o < RSEG; o++) mu1[o] = mu2[o] = e11[o] = e22[o] = e12[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < RSEG + 10; i++) {
+        const float q0 = hq[0][r0 + i][lx], q1 = hq[1][r0 + i][lx], q2 = hq[2][r0 + i][lx], q3 = hq[3][r0 + i][lx], q4 = hq[4][r0 + i][lx];
+#pragma unroll
+        for (int o = 0; o < RSEG; o++) {
+            const int t = i - o;
+            if (t >= 0 && t < 11) {
+                const float w = win.g[t];
+                mu1[o] += w * q0; mu2[o] += w * q1; e11[o] += w * q2; e22[o] += w * q3; e12[o] += w * q4;
+            }
+        }
     }
     float l1 = 0.f, ss = 0.f;
-    if (px < W && py < H) {
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
-        const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
-        const float A1 = 2.f * mu1_mu2 + C1, A2 = 2.f * sigma12 + C2;
-        const float B1 = mu1_sq + mu2_sq + C1, B2 = sigma1_sq + sigma2_sq + C2;
-        const float S = (A1 * A2) / (B1 * B2);
-        ss = S;
-        l1 = fabsf(sx[ly + HALO][lx + HALO] - sy[ly + HALO][lx + HALO]);
-        // partial derivatives of S w.r.t. mu1, E[x^2], E[xy] (the window-averaged quantities that depend on x)
-        const float dS_dmu1 = (2.f * mu2 * (A2 - A1)) / (B1 * B2) - S * (2.f * mu1 / B1 - 2.f * mu1 / B2);
-        const float dS_de11 = -S / B2;
-        const float dS_de12 = 2.f * A1 / (B1 * B2);
-        const size_t HW = (size_t)H * W, o = (size_t)py * W + px;
-        float *m = maps + (size_t)vc * 3 * HW;
-        m[o] = dS_dmu1; m[HW + o] = dS_de11; m[2 * HW + o] = dS_de12;
+    const int px = x0 + lx;
+    const size_t HW = (size_t)H * W;
+    float *m = maps + (size_t)vc * 3 * HW;
+#pragma unroll
+    for (int o = 0; o < RSEG; o++) {
+        const int py = y0 + r0 + o;
+        if (px < W && py < H) {
+            const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+            const float mu1_sq = mu1[o] * mu1[o], mu2_sq = mu2[o] * mu2[o], mu1_mu2 = mu1[o] * mu2[o];
+            const float sigma1_sq = e11[o] - mu1_sq, sigma2_sq = e22[o] - mu2_sq, sigma12 = e12[o] - mu1_mu2;
+            const float A1 = 2.f * mu1_mu2 + C1, A2 = 2.f * sigma12 + C2;
+            const float B1 = mu1_sq + mu2_sq + C1, B2 = sigma1_sq + sigma2_sq + C2;
+            const float invB = 1.f / (B1 * B2);
+            const float S = (A1 * A2) * invB;
+            ss += S;
+            l1 += fabsf(sx[r0 + o + HALO][lx + HALO] - sy[r0 + o + HALO][lx + HALO]);
+            // partial derivatives of S w.r.t. mu1, E[x^2], E[xy] (the window-averaged quantities that depend on x)
+            const float dS_dmu1 = (2.f * mu2[o] * (A2 - A1)) * invB - S * (2.f * mu1[o] / B1 - 2.f * mu1[o] / B2);
+            const float dS_de11 = -S / B2;
+            const float dS_de12 = 2.f * A1 * invB;
+            const size_t off = (size_t)py * W + px;
+            m[off] = dS_dmu1; m[HW + off] = dS_de11; m[2 * HW + off] = dS_de12;
+        }
     }
     l1 = warp_sum(l1);
     ss = warp_sum(ss);
@@ -104,25 +136,25 @@ ssim_fwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__re
     __syncthreads();
     if (tid == 0) {
         float a = 0.f, b = 0.f;
-        for (int k = 0; k < LT * LT / 32; k++) { a += red[0][k]; b += red[1][k]; }
-        atomicAdd(&l1_sum[v], a);
-        atomicAdd(&ssim_sum[v], b);
+        for (int k = 0; k < NT / 32; k++) { a += red[0][k]; b += red[1][k]; }
+        atomicAdd(&l1_sum[v], a * inv_n);   // the per-view means of the reference's .mean()
+        atomicAdd(&ssim_sum[v], b * inv_n);
     }
 }
 
 // pass 2: dL/dimg = w_l1/N * sign(x-y) - w_ssim/N * (G*M1 + 2x G*M2 + y G*M3)
-__global__ void __launch_bounds__(LT *LT)
+__global__ void __launch_bounds__(NT, 3)
 ssim_bwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__restrict__ img, const float *__restrict__ gt,
                 Win win, const float *__restrict__ maps, float w_l1, float w_ssim, float *__restrict__ dL_dimg) {
-    __shared__ float sm[3][LE][LE + 1];
-    __shared__ float hq[3][LE][LT + 1];
+    __shared__ float sm[3][EH][ES];
+    __shared__ float hq[3][EH][TW];
     const int vc = blockIdx.z, v = vc / Ce, c = vc % Ce;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
-    const int tid = threadIdx.y * LT + threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
     const size_t HW = (size_t)H * W;
     const float *m = maps + (size_t)vc * 3 * HW;
-    for (int k = tid; k < LE * LE; k += LT * LT) {
-        const int ly = k / LE, lx = k % LE;
+    for (int k = tid; k < EH * EW; k += NT) {
+        const int ly = k / EW, lx = k % EW;
         const int gx = x0 + lx - HALO, gy = y0 + ly - HALO;
         const bool in = gx >= 0 && gy >= 0 && gx < W && gy < H;
         const size_t o = (size_t)gy * W + gx;
@@ -131,43 +163,58 @@ ssim_bwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__re
         sm[2][ly][lx] = in ? m[2 * HW + o] : 0.f;
     }
     __syncthreads();
-    for (int k = tid; k < LE * LT; k += LT * LT) {
-        const int ly = k / LT, lx = k % LT;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = tid; k < EH * (TW / SEG); k += NT) {
+        const int ly = k / (TW / SEG), s0 = (k % (TW / SEG)) * SEG;
 #pragma unroll
-        for (int t = 0; t < 11; t++) {
-            const float w = win.g[t];
-            a0 += w * sm[0][ly][lx + t]; a1 += w * sm[1][ly][lx + t]; a2 += w * sm[2][ly][lx + t];
+        for (int q = 0; q < 3; q++) {
+            float x[SEG + 10];
+#pragma unroll
+            for (int i = 0; i < SEG + 10; i++) x[i] = sm[q][ly][s0 + i];
+#pragma unroll
+            for (int o = 0; o < SEG; o++) {
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < 11; t++) a += win.g[t] * x[o + t];
+                hq[q][ly][s0 + o] = a;
+            }
         }
-        hq[0][ly][lx] = a0; hq[1][ly][lx] = a1; hq[2][ly][lx] = a2;
     }
     __syncthreads();
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int px = x0 + lx, py = y0 + ly;
-    if (px >= W || py >= H) return;
-    float g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    const int lx = tid % TW, r0 = (tid / TW) * RSEG;
+    float g1[RSEG], g2[RSEG], g3[RSEG];
 #pragma unroll
-    for (int t = 0; t < 11; t++) {
-        const float w = win.g[t];
-        g1 += w * hq[0][ly + t][lx]; g2 += w * hq[1][ly + t][lx]; g3 += w * hq[2][ly + t][lx];
+    for (int o = 0; o < RSEG; o++) g1[o] = g2[o] = g3[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < RSEG + 10; i++) {
+        const float q0 = hq[0][r0 + i][lx], q1 = hq[1][r0 + i][lx], q2 = hq[2][r0 + i][lx];
+#pragma unroll
+        for (int o = 0; o < RSEG; o++) {
+            const int t = i - o;
+            if (t >= 0 && t < 11) {
+                const float w = win.g[t];
+                g1[o] += w * q0; g2[o] += w * q1; g3[o] += w * q2;
+            }
+        }
     }
-    const float x = load_px(img, C, H, W, v, c, grey, py, px), y = load_px(gt, C, H, W, v, c, grey, py, px);
+    const int px = x0 + lx;
     const float n = (float)Ce * (float)H * (float)W;  // elements the reference's .mean() runs over (per view)
-    const float d = x - y;
-    const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-    // in grey mode the reference's 3 identical channels each carry 1/3 of the mean, and d grey / d channel = 1/C
-    float gout = (w_l1 * sgn - w_ssim * (g1 + 2.f * x * g2 + y * g3)) / n;
-    const size_t o = (size_t)py * W + px;
-    if (!grey) {
-        dL_dimg[((size_t)v * C + c) * HW + o] = gout;
-    } else {
-        gout /= C;
-        for (int k = 0; k < C; k++) dL_dimg[((size_t)v * C + k) * HW + o] = gout;
+#pragma unroll
+    for (int o = 0; o < RSEG; o++) {
+        const int py = y0 + r0 + o;
+        if (px >= W || py >= H) continue;
+        const float x = load_px(img, C, H, W, v, c, grey, py, px), y = load_px(gt, C, H, W, v, c, grey, py, px);
+        const float d = x - y;
+        const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        // in grey mode the reference's 3 identical channels each carry 1/3 of the mean, and d grey / d channel = 1/C
+        float gout = (w_l1 * sgn - w_ssim * (g1[o] + 2.f * x * g2[o] + y * g3[o])) / n;
+        const size_t off = (size_t)py * W + px;
+        if (!grey) {
+            dL_dimg[((size_t)v * C + c) * HW + off] = gout;
+        } else {
+            gout /= C;
+            for (int k = 0; k < C; k++) dL_dimg[((size_t)v * C + k) * HW + off] = gout;
+        }
     }
-}
-
-__global__ void scale_means_kernel(int V, float inv_n, float *a, float *b) {
-    for (int i = threadIdx.x; i < V; i += blockDim.x) { a[i] *= inv_n; b[i] *= inv_n; }
 }
 
 }  // namespace fnx
@@ -189,17 +236,17 @@ int fnx_image_loss(int32_t V, int32_t C, int32_t H, int32_t W, const float *img,
     float *maps = (float *)align_up((size_t)scratch, 256);
     FNX_CUDA_TRY(cudaMemsetAsync(l1_mean, 0, sizeof(float) * V, st));
     FNX_CUDA_TRY(cudaMemsetAsync(ssim_mean, 0, sizeof(float) * V, st));
-    dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, V * Ce), block(LT, LT);
+    static_assert(NT == TW * (TH / RSEG), "pass B maps one thread to RSEG rows of one column");
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, V * Ce);
     prof_begin(SEC_IMAGE_LOSS, st);
-    ssim_fwd_kernel<<<grid, block, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, maps, l1_mean, ssim_mean);
+    ssim_fwd_kernel<<<grid, NT, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, 1.0f / ((float)Ce * (float)H * (float)W), maps, l1_mean,
+                                         ssim_mean);
     FNX_LAUNCH_CHECK("ssim_fwd_kernel");
     if (dL_dimg) {
-        ssim_bwd_kernel<<<grid, block, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, maps, w_l1, w_ssim, dL_dimg);
+        ssim_bwd_kernel<<<grid, NT, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, maps, w_l1, w_ssim, dL_dimg);
         FNX_LAUNCH_CHECK("ssim_bwd_kernel");
     }
-    scale_means_kernel<<<1, 32, 0, st>>>(V, 1.0f / ((float)Ce * (float)H * (float)W), l1_mean, ssim_mean);
     prof_end(SEC_IMAGE_LOSS, st);
-    FNX_LAUNCH_CHECK("scale_means_kernel");
     return FNX_OK;
 }
 

@@ -128,6 +128,9 @@ class PhysicalStep:
         self.side = torch.cuda.Stream(device=self.dev) if overlap else None
         self._ev_fork, self._ev_means, self._ev_join = (torch.cuda.Event() for _ in range(3))
         self._side_pending = False
+        # host ground truth is uploaded on its own stream so that the copy for the next frame / iteration overlaps the
+        # kernels of the current one (the reference uploads it inline, train_physical_particle.py:325)
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
 
     # -- pieces ---------------------------------------------------------------------------------------------
     def physics_forward(self, fr: FrameState, physics=True):
@@ -329,17 +332,27 @@ class PhysicalStep:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     out = self._iteration(fr, view_ids, gt_buf, update, batch, physics)
-                ent = (g, out, gt_buf)
+                ent = (g, out, gt_buf, torch.cuda.Event(), torch.cuda.Event())
                 fr.graphs[key] = ent
                 for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # capture does not execute, but be explicit
                     dst.copy_(src)
-            g, out, gt_buf = ent
+            g, out, gt_buf, ev_copied, ev_done = ent
             ws = out.get("ws")
             if ws is not None and ws.overflowed():
                 raise RuntimeError("rasterizer instance capacity exceeded inside a captured iteration; re-capture "
                                    f"(capacity {ws.capacity})")
-            gt_buf.copy_(gt, non_blocking=True)
+            main = torch.cuda.current_stream(self.dev)
+            if gt.is_cuda:
+                gt_buf.copy_(gt, non_blocking=True)
+            else:
+                cs = self.copy_stream
+                cs.wait_event(ev_done)          # the previous replay of this graph has finished reading gt_buf
+                with torch.cuda.stream(cs):
+                    gt_buf.copy_(gt, non_blocking=True)
+                    ev_copied.record(cs)
+                main.wait_event(ev_copied)
             g.replay()
+            ev_done.record(main)
             return out
 
     def total_loss(self, out, batch=None):
