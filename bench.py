@@ -103,18 +103,21 @@ def run_fnx(args):
     import torch.distributed as dist
     from fluidnexus_b200 import _lib as L
     from fluidnexus_b200 import rasterizer as R
-    from fluidnexus_b200.parallel import FlatBucket, assign_items
+    from fluidnexus_b200.parallel import FlatBucket, FrameLanes, assign_items
     from fluidnexus_b200.step import FrameState, PhysicalStep, StepParams
     rank, world, local = dist_info()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FNX_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
     G, views = args.frames_in_flight, list(range(5))
     cams, bg, frames, cfg = build_frames(args.workload, G, dev)
     prm = StepParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], grey=cfg["grey"], distance_threshold_visual=cfg["thr"])
-    ps = PhysicalStep(cams, cfg["C"], prm, device=dev)
+    # independent frames run on `lanes` streams (fluidnexus_b200/parallel.py:FrameLanes); one PhysicalStep per lane
+    lanes = FrameLanes(lambda k: PhysicalStep(cams, cfg["C"], prm, device=dev), args.lanes, dev)
+    ps = lanes.steps[0]
     N = cfg["N"]
     # replicated parameters / Adam state / gradient bucket of ALL frames, flat (fluidnexus_b200/parallel.py)
     fb = FlatBucket(G, N, dev)
@@ -147,12 +150,10 @@ def run_fnx(args):
     use_graph = [not args.no_graph]
 
     def one_step(e2e):
-        last = None
-        for f in mine:
-            fr = states[f]
-            # e2e: ground truth comes from pinned HOST memory every iteration (the reference uploads it at :325)
-            gt = gts_pinned[f] if e2e else gts_dev[f]
-            last = ps.step(fr, by_frame[f], gt, update=False, batch=len(views), graph=use_graph[0], physics=f in physics_frames)
+        # e2e: ground truth comes from pinned HOST memory every iteration (the reference uploads it at :325)
+        outs = lanes.run(mine, lambda step, f: step.step(states[f], by_frame[f], gts_pinned[f] if e2e else gts_dev[f], update=False,
+                                                         batch=len(views), graph=use_graph[0], physics=f in physics_frames))
+        last = outs[-1] if outs else None
         fb.all_reduce()
         step_no[0] += 1
         L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
@@ -284,7 +285,7 @@ def run_fnx(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={Cc}, "
                                f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration",
-                   "frames_in_flight": G, "views_per_iteration": 5, "parallelism": f"frames sharded over {world} rank(s), "
+                   "frames_in_flight": G, "lanes_per_gpu": lanes.n, "views_per_iteration": 5, "parallelism": f"frames sharded over {world} rank(s), "
                    "one NCCL all-reduce of the flat gradient bucket per step" if world > 1 else "single GPU",
                    "instances_per_iteration": R_per_iter,
                    "l2": f"working set per iteration ~{(R_per_iter * (rec + 16) + 5 * HW * 40) / 1e6:.0f} MB and {G} frames "
@@ -429,6 +430,7 @@ def main():
     ap.add_argument("--impl", default="fnx", choices=["fnx", "reference"])
     ap.add_argument("--workload", default="smoke", choices=list(WORKLOADS))
     ap.add_argument("--frames-in-flight", type=int, default=8)
+    ap.add_argument("--lanes", type=int, default=4, help="CUDA streams per GPU that independent frames are dealt to")
     ap.add_argument("--ref-max-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")

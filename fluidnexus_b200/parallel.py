@@ -55,3 +55,43 @@ class FlatBucket:
         """After each rank initialised only its own frames' slots (others zero): sum = every slot from its owner."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.param, op=dist.ReduceOp.SUM)
+
+
+class FrameLanes:
+    """Runs the iterations of independent frames on `lanes` CUDA streams of one GPU.
+
+    One iteration is a chain of ~45 dependent launches, several of them far too small to fill 148 SMs (grid builds,
+    per-tile scans) and the large ones end in a tail of a few long tiles; with two frames in flight on two streams the
+    tails and small kernels of one frame run next to the kernels of the other.  This is the single-GPU form of the
+    frame sharding of SURVEY.md 8(e): frames must be independent (separate FrameState, gradients into separate slots).
+    `make_step(lane)` builds one PhysicalStep per lane (each owns its side stream, copy stream and loss scratch)."""
+
+    def __init__(self, make_step, lanes, device):
+        self.dev = torch.device(device)
+        self.n = max(1, int(lanes))
+        self.steps = [make_step(k) for k in range(self.n)]
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n)] if self.n > 1 else [None]
+        self._fork = torch.cuda.Event()
+        self._join = [torch.cuda.Event() for _ in range(self.n)]
+
+    def run(self, frames, call):
+        """call(step, frame) for every frame, frame k on lane k % lanes; everything is ordered after the work already
+        queued on the current stream, and the current stream waits for all lanes before this returns.  Returns the
+        list of results in frame order."""
+        if self.n == 1:
+            return [call(self.steps[0], fr) for fr in frames]
+        main = torch.cuda.current_stream(self.dev)
+        self._fork.record(main)
+        used, out = set(), []
+        for k, fr in enumerate(frames):
+            lane = k % self.n
+            st = self.streams[lane]
+            if lane not in used:
+                st.wait_event(self._fork)
+                used.add(lane)
+            with torch.cuda.stream(st):
+                out.append(call(self.steps[lane], fr))
+        for lane in sorted(used):
+            self._join[lane].record(self.streams[lane])
+            main.wait_event(self._join[lane])
+        return out

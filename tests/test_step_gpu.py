@@ -150,3 +150,28 @@ def test_static_background_cache_equals_full_rebinning(libfnx):
         assert (a - b).abs().max() < 1e-4
     assert np.allclose(res[False][1], res[True][1], rtol=1e-5)
     assert (res[False][2] - res[True][2]).abs().max() < 1e-6
+
+
+def test_frame_lanes_equal_sequential_frames(libfnx):
+    """Independent frames dealt to two CUDA streams (FrameLanes) must give what running them one after the other gives:
+    same losses, same parameters after a few iterations (captured graphs, pinned host ground truth)."""
+    from fluidnexus_b200.parallel import FrameLanes
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    scenes_ = [_scene(3, True, seed=20 + k) for k in range(3)]
+    cams = scenes_[0][4]
+    gts = [(torch.rand(5, 3, 64, 64, generator=torch.Generator().manual_seed(30 + k)) * 0.5).pin_memory() for k in range(3)]
+    res = {}
+    for n in (1, 2):
+        lanes = FrameLanes(lambda k: PhysicalStep(cams, 3, prm), n, "cuda")
+        frs = [FrameState(hp, vis, fluid, bg, prm=prm) for (hp, vis, fluid, bg, _) in scenes_]
+        losses = []
+        for it in range(4):
+            # the returned loss tensors live in per-lane scratch that the lane's next frame overwrites: reduce them to
+            # the iteration's scalar on the lane's own stream, right behind the step
+            outs = lanes.run(list(range(3)), lambda step, k: step.total_loss(step.step(frs[k], [0, 1, 2, 3, 4], gts[k], graph=True)).clone())
+            torch.cuda.synchronize()
+            losses.append([float(o) for o in outs])
+        res[n] = (np.array(losses), [fr.e.clone() for fr in frs])
+    assert np.allclose(res[1][0], res[2][0], rtol=1e-5)
+    for a, b in zip(res[1][1], res[2][1]):
+        assert (a - b).abs().max() < 1e-6
