@@ -79,8 +79,10 @@ SYMBOLS = {
     "fnx_radius_count": (_I, [_V, _I, _F, _V, _I, _F, _I, _V, _V, _V]),
     "fnx_radius_fill": (_I, [_V, _I, _F, _V, _I, _F, _V, _V, _V, _V, _V]),
     "fnx_pbf_density_fwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V]),
+    "fnx_pbf_density_fwd_counted": (_I, [_V, _V, _I, _V, _I, _F, _F, _V, _V, _V, _V]),
     "fnx_pbf_density_bwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V, _I, _V]),
     "fnx_visual_advect_fwd": (_I, [_V, _V, _V, _I, _V, _I, _V, _F, _F, _F, _V, _V, _V, _V]),
+    "fnx_visual_advect_fwd_counted": (_I, [_V, _V, _V, _I, _V, _I, _I, _F, _F, _F, _V, _V, _V, _V, _V]),
     "fnx_visual_advect_bwd": (_I, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _V, _F, _F, _F, _V, _I, _V]),
     "fnx_pair_distance_loss": (_I, [_V, _V, _I, _F, _F, _F, _V, _V, _V]),
     "fnx_knn3_mean_dist2": (_I, [_V, _V, _I, _F, _V, _V]),

@@ -183,6 +183,20 @@ constexpr int QPB = 4;  // queries (warps) per 128-thread block
 // ---------------------------------------------------------------------------------------------------------------
 // neighbour counts + the index cut-off that realises torch_cluster's max_num_neighbors rule
 // ---------------------------------------------------------------------------------------------------------------
+// K-th smallest neighbour index of query q by bisection on the index value (rare path: only when more than K points
+// lie within the radius).  Warp-cooperative; every lane returns the same value.
+__device__ __forceinline__ int kth_by_bisection(const GridView &g, float inv_cell, float3 q, float r2, int lane, int K, int n_x) {
+    int lo = 0, hi = n_x - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        int below = 0;
+        warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float) { below += (j <= mid); });
+        below = __reduce_add_sync(0xffffffffu, below);
+        if (below >= K) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(128)
 radius_count_kernel(GridView g, float inv_cell, const float *__restrict__ y, int ny, float r2, int K, int n_x,
                     int *__restrict__ counts, int *__restrict__ kth) {
@@ -195,16 +209,7 @@ radius_count_kernel(GridView g, float inv_cell, const float *__restrict__ y, int
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     int cut = 0x7fffffff;
     if (cnt > K) {
-        // K-th smallest neighbour index by bisection on the index value (rare path)
-        int lo = 0, hi = n_x - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            int below = 0;
-            warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float) { below += (j <= mid); });
-            below = __reduce_add_sync(0xffffffffu, below);
-            if (below >= K) hi = mid; else lo = mid + 1;
-        }
-        cut = lo;
+        cut = kth_by_bisection(g, inv_cell, q, r2, lane, K, n_x);
         cnt = K;
     }
     if (lane == 0) {
@@ -271,6 +276,53 @@ density_fwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
     if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
 }
 
+// Neighbour count, cut-off index and density in ONE walk.  The density written here assumes that no neighbour's cap
+// binds (r <= kth[c] for every c); *cap_flag is raised when any particle has more than K neighbours, and the exact
+// kernel above then recomputes p_ratio with the cut-offs (it returns at once while the flag is down -- the normal case:
+// ~46 neighbours at the reference's lattice spacing against K = 100).
+__global__ void __launch_bounds__(128)
+density_fwd_counted_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass, int K,
+                           float H2, float term1, float p0, int *__restrict__ kth, float *__restrict__ p_ratio,
+                           int *__restrict__ cap_flag) {
+    const int r = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
+    float pi = 0.f;
+    int cnt = 0;
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int, const float4 &, float d2) {
+        cnt++;
+        pi += poly6(d2, H2, term1);
+    });
+    pi = warp_sum(pi);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    int cut = 0x7fffffff;
+    if (cnt > K) {
+        cut = kth_by_bisection(g, inv_cell, q, H2, lane, K, N);
+        if (lane == 0) *cap_flag = 1;
+    }
+    if (lane == 0) {
+        kth[r] = cut;
+        p_ratio[r] = pi / imass[r] / p0;
+    }
+}
+__global__ void __launch_bounds__(128)
+density_fwd_if_capped_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
+                             const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio,
+                             const int *__restrict__ cap_flag) {
+    if (*cap_flag == 0) return;
+    const int r = blockIdx.x * QPB + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
+    float pi = 0.f;
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2) {
+        if (r <= kth[c]) pi += poly6(d2, H2, term1);
+    });
+    pi = warp_sum(pi);
+    if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
+}
+
 // dL/dX_k = sum_{j in N(k)} dpoly6(d2) * 2 (X_k - X_j) * ( gp_k [k <= kth[j]] + gp_j [j <= kth[k]] ),
 // gp_i = dL/dp_ratio_i / (imass_i p0)
 __global__ void __launch_bounds__(128)
@@ -301,26 +353,43 @@ density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
 // ---------------------------------------------------------------------------------------------------------------
 // P1: advect visual particles with the poly6-interpolated hidden velocity (gm_fluid.py:1291-1336)
 // ---------------------------------------------------------------------------------------------------------------
+// COUNTED = false: the cut-off kthV[v] is an input (fnx_radius_count ran before).  COUNTED = true: the kernel counts the
+// neighbours while it sums; only a query with more than K of them (rare) finds its cut-off by bisection and sums
+// again with it, and kthV[v] is an OUTPUT for the backward.
+template <bool COUNTED>
 __global__ void __launch_bounds__(128)
 advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100*e*/, const float *__restrict__ xyz,
-                  const float *__restrict__ vis, int V, const int *__restrict__ kthV, float H2, float term1, float secs,
+                  const float *__restrict__ vis, int V, int *__restrict__ kthV, int K, int n_x, float H2, float term1, float secs,
                   float eps, float out_div, float *__restrict__ vis_out, float *__restrict__ num_out,
                   float *__restrict__ den_out) {
     const int v = blockIdx.x * QPB + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (v >= V) return;
     const float3 q = make_float3(vis[3 * v], vis[3 * v + 1], vis[3 * v + 2]);
-    const int cut = kthV[v];
+    int cut = COUNTED ? 0x7fffffff : kthV[v];
     float3 num = make_float3(0.f, 0.f, 0.f);
     float den = 0.f;
-    warp_for_each_neighbor(gh, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2) {
+    int cnt = 0;
+    auto gather = [&](int j, const float4 &pj, float d2) {
+        cnt++;
         if (j > cut) return;
         const float w = poly6(d2, H2, term1);
         num.x += w * ((pj.x - xyz[3 * j]) / secs);
         num.y += w * ((pj.y - xyz[3 * j + 1]) / secs);
         num.z += w * ((pj.z - xyz[3 * j + 2]) / secs);
         den += w;
-    });
+    };
+    warp_for_each_neighbor(gh, inv_cell, q, H2, lane, gather);
+    if (COUNTED) {
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt > K) {
+            cut = kth_by_bisection(gh, inv_cell, q, H2, lane, K, n_x);
+            num = make_float3(0.f, 0.f, 0.f);
+            den = 0.f;
+            warp_for_each_neighbor(gh, inv_cell, q, H2, lane, gather);
+        }
+        if (lane == 0) kthV[v] = cut;
+    }
     num.x = warp_sum(num.x); num.y = warp_sum(num.y); num.z = warp_sum(num.z); den = warp_sum(den);
     if (lane != 0) return;
     const float dc = fmaxf(den, eps);
@@ -628,6 +697,23 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
     return FNX_OK;
 }
 
+int fnx_pbf_density_fwd_counted(const void *grid, const float *X, int32_t N, const float *imass, int32_t max_num_neighbors, float H,
+                                float p0, int32_t *kth_out, float *p_ratio, int32_t *cap_flag, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid && X && imass && kth_out && p_ratio && cap_flag && N >= 0 && H > 0.f && p0 > 0.f && max_num_neighbors > 0, "bad arguments");
+    if (N == 0) return FNX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    GridView g = grid_view((void *)grid, N);
+    const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    FNX_CUDA_TRY(cudaMemsetAsync(cap_flag, 0, sizeof(int32_t), st));
+    density_fwd_counted_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, X, N, imass, max_num_neighbors, H * H, term1, p0, kth_out,
+                                                                    p_ratio, cap_flag);
+    FNX_LAUNCH_CHECK("density_fwd_counted_kernel");
+    density_fwd_if_capped_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, X, N, imass, kth_out, H * H, term1, p0, p_ratio, cap_flag);
+    FNX_LAUNCH_CHECK("density_fwd_if_capped_kernel");
+    return FNX_OK;
+}
+
 int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H, float p0,
                         const float *dL_dpratio, float *dL_dX, int32_t accumulate, fnx_stream_t stream) {
     ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
@@ -648,8 +734,23 @@ int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *
     if (V == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_hidden, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    advect_fwd_kernel<<<(V + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, kthV, H * H, term1, secs, 1e-8f,
-                                                                       out_div, visual_out, num_out, den_out);
+    advect_fwd_kernel<false><<<(V + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, (int *)kthV, 0, N, H * H, term1,
+                                                                              secs, 1e-8f, out_div, visual_out, num_out, den_out);
+    FNX_LAUNCH_CHECK("advect_fwd_kernel");
+    return FNX_OK;
+}
+
+int fnx_visual_advect_fwd_counted(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual, int32_t V,
+                                  int32_t max_num_neighbors, float H, float secs, float out_div, float *visual_out, float *num_out,
+                                  float *den_out, int32_t *kthV_out, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid_hidden && X && xyz && kthV_out && visual_out && (visual || V == 0) && out_div != 0.f && max_num_neighbors > 0,
+                "bad arguments");
+    if (V == 0) return FNX_OK;
+    GridView g = grid_view((void *)grid_hidden, N);
+    const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    advect_fwd_kernel<true><<<(V + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, kthV_out, max_num_neighbors, N,
+                                                                             H * H, term1, secs, 1e-8f, out_div, visual_out, num_out, den_out);
     FNX_LAUNCH_CHECK("advect_fwd_kernel");
     return FNX_OK;
 }

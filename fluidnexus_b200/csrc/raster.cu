@@ -683,19 +683,24 @@ pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_
 // The reference evaluates expf() (forward.cu:330, backward.cu:479).  We use the fast ex2-based path and fall back to
 // expf() only inside a narrow band around the 1/255 cut so that the keep/skip decision is the reference's.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr float ALPHA_BAND = 4e-6f;  // ~1000x the error of ex2.approx at alpha = 1/255
 __device__ __forceinline__ bool pair_alpha(float x, float y, float a, float b, float c, float o, float px, float py,
                                            float &dx, float &dy, float &G, float &alpha) {
     dx = x - px;
     dy = y - py;
     const float power = -0.5f * (a * dx * dx + c * dy * dy) - b * dx * dy;
     if (power > 0.0f) return false;
-    G = __expf(power);
+    // ex2.approx.ftz of power*log2(e): what __expf() compiles to minus its denormal-range rescaling (a G below 2^-126
+    // gives alpha = 0 < 1/255 either way)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(power * 1.4426950408889634f));
     alpha = min(ALPHA_MAX, o * G);
-    if (fabsf(alpha - ALPHA_MIN) < 4e-6f) {
+    if (alpha < ALPHA_MIN + ALPHA_BAND) {  // below the cut, or so close to it that the approximation could decide it
+        if (alpha < ALPHA_MIN - ALPHA_BAND) return false;
         G = expf(power);
         alpha = min(ALPHA_MAX, o * G);
+        return !(alpha < ALPHA_MIN);
     }
-    return !(alpha < ALPHA_MIN);
+    return true;
 }
 
 constexpr int BATCH = 128;  // records per smem stage
@@ -769,14 +774,15 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const float pxf = (float)px;
     const size_t HW = (size_t)W * H;
     const uint32_t slot_mask = use_mask ? ((1u << SLOT_BITS) - 1u) : 0xFFFFFFFFu;
-    bool inside[PPT], done[PPT];
+    bool inside[PPT];
+    int done[PPT];  // 0 / 1 (a 32-bit flag: bool arrays compile to byte shuffles in the hot loop)
     float pyf[PPT], T[PPT], D[PPT], Cacc[PPT][C];
     float T_snap[PPT], C_snap[PPT][C];
     uint32_t last_contributor[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
         inside[p] = px < W && (py0 + 4 * p) < H;
-        done[p] = !inside[p];
+        done[p] = inside[p] ? 0 : 1;
         pyf[p] = (float)(py0 + 4 * p);
         T[p] = 1.0f;
         D[p] = DEPTH_DEFAULT;
@@ -816,7 +822,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         const int s = bi % STAGES;
         bool all_done = true;
 #pragma unroll
-        for (int p = 0; p < PPT; p++) all_done = all_done && done[p];
+        for (int p = 0; p < PPT; p++) all_done = all_done && (done[p] != 0);
         // whole tile finished?  (also orders the previous stage's reads before its buffer is refilled)
         if (__syncthreads_count(all_done) == BLEND_THREADS) break;
         if (threadIdx.x == 0 && bi >= 1 && bi + STAGES - 1 < nbatch) {
@@ -862,7 +868,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                         if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx, dy, G, alpha)) continue;
                         const float test_T = T[p] * (1 - alpha);
                         if (test_T < T_EPS) {
-                            done[p] = true;
+                            done[p] = 1;
                             continue;
                         }
                         if (C == 3) {

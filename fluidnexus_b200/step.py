@@ -94,6 +94,7 @@ class FrameState:
         self.p, self.pn, self.gp, self.gpn = z(N), z(N), z(N), z(N)
         self.num, self.den, self.dDist = z(V, 3), z(V), z(V, 3)
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)  # gas, next_gas, exyz, dist
+        self.cap_flag = torch.zeros(2, dtype=torch.int32, device=dev)   # "max_num_neighbors binds" flags of P2 / P3
         self.vis_grid_built = False
         self.zero_dmeans = None
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # Adam step count (device side: graph-replay safe)
@@ -152,10 +153,10 @@ class PhysicalStep:
         if physics and self.side is not None:
             self._ev_fork.record(main)
         # P1 forward straight into the fluid rows of the rasterizer's means3D (render units)
-        ck(lib.fnx_radius_count(fr.gridX.data_ptr(), N, prm.H, fr.visual.data_ptr(), V, prm.H, prm.KNN_K, None, fr.kthV.data_ptr(), st))
-        ck(lib.fnx_visual_advect_fwd(fr.gridX.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, fr.visual.data_ptr(), V,
-                                     fr.kthV.data_ptr(), prm.H, prm.secs, prm.scale_factor, fr.means3D.data_ptr(), fr.num.data_ptr(),
-                                     fr.den.data_ptr(), st))
+        # (neighbour count, cut-off and the advection sums in one walk: fnx_radius_count + fnx_visual_advect_fwd)
+        ck(lib.fnx_visual_advect_fwd_counted(fr.gridX.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, fr.visual.data_ptr(), V, prm.KNN_K,
+                                             prm.H, prm.secs, prm.scale_factor, fr.means3D.data_ptr(), fr.num.data_ptr(),
+                                             fr.den.data_ptr(), fr.kthV.data_ptr(), st))
         if not physics:
             fr.dX.zero_()
             fr.dDist.zero_()
@@ -175,9 +176,8 @@ class PhysicalStep:
                     (fr.gridY, fr.Y, fr.kthY, fr.pn, fr.gpn, prm.lambda_next_gas_constraints, fr.dY))):
                 if k == 1:
                     ck(lib.fnx_grid_build(pos.data_ptr(), N, prm.H, grid.data_ptr(), st))
-                ck(lib.fnx_radius_count(grid.data_ptr(), N, prm.H, pos.data_ptr(), N, prm.H, prm.KNN_K, None, kth.data_ptr(), st))
-                ck(lib.fnx_pbf_density_fwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
-                                           p.data_ptr(), st))
+                ck(lib.fnx_pbf_density_fwd_counted(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), prm.KNN_K, prm.H, prm.p0,
+                                                   kth.data_ptr(), p.data_ptr(), fr.cap_flag[k:].data_ptr(), st))
                 ck(lib.fnx_pbf_ratio_loss(N, p.data_ptr(), lam, fr.scalars[k:].data_ptr(), gp.data_ptr(), st))
                 ck(lib.fnx_pbf_density_bwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
                                            gp.data_ptr(), dpos.data_ptr(), 0, st))

@@ -228,6 +228,11 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
                         float p0, float *p_ratio, fnx_stream_t stream);
 int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H,
                         float p0, const float *dL_dpratio, float *dL_dX, int32_t accumulate, fnx_stream_t stream);
+/* fnx_radius_count(grid(X), X, K) + fnx_pbf_density_fwd in one neighbour walk: kth_out [N] is written for the backward;
+ * cap_flag is one int32 of device scratch (raised when some particle has more than K neighbours; p_ratio is then
+ * recomputed with the cut-offs, so the result always equals the two-call sequence). */
+int fnx_pbf_density_fwd_counted(const void *grid, const float *X, int32_t N, const float *imass, int32_t max_num_neighbors,
+                                float H, float p0, int32_t *kth_out, float *p_ratio, int32_t *cap_flag, fnx_stream_t stream);
 
 /* P1 (gm_fluid.py:1291-1336): A = visual + secs * sum_j w u_j / max(sum_j w, 1e-8), w = poly6(|visual-X_j|^2),
  * u_j = (X_j - xyz_j)/secs over radius(x=X, y=visual, H, K) edges; visual_out = A / out_div (out_div = 1, or the
@@ -238,6 +243,11 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
 int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual,
                           int32_t V, const int32_t *kthV, float H, float secs, float out_div, float *visual_out,
                           float *num_out, float *den_out, fnx_stream_t stream);
+/* fnx_radius_count(grid_hidden, visual, K) + fnx_visual_advect_fwd in one neighbour walk; kthV_out [V] is written for
+ * the backward. */
+int fnx_visual_advect_fwd_counted(const void *grid_hidden, const float *X, const float *xyz, int32_t N, const float *visual,
+                                  int32_t V, int32_t max_num_neighbors, float H, float secs, float out_div, float *visual_out,
+                                  float *num_out, float *den_out, int32_t *kthV_out, fnx_stream_t stream);
 int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *xyz, int32_t N, int32_t V,
                           const int32_t *kthV, const float *num, const float *den, const float *dL_dvisual_out,
                           const float *dL_dvisual_out2, float g_scale, float H, float secs, float *dL_dX,

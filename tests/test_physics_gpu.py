@@ -159,3 +159,37 @@ def test_compat_imports_resolve_to_libfnx(libfnx):
     from torch_cluster import radius, radius_graph
     from torch_scatter import scatter_min
     assert radius is P.radius and radius_graph is P.radius_graph and scatter_min is P.scatter_min and distCUDA2 is P.distCUDA2
+
+
+@pytest.mark.parametrize("K", [100, 12])
+def test_counted_kernels_equal_count_then_gather(libfnx, K):
+    """fnx_pbf_density_fwd_counted / fnx_visual_advect_fwd_counted (neighbour count + cut-off + sums in one walk) against
+    the fnx_radius_count -> fnx_pbf_density_fwd / fnx_visual_advect_fwd sequences, cap not binding (K = 100) and
+    binding (K = 12): identical cut-offs, bitwise-identical sums."""
+    from fluidnexus_b200 import _lib as L
+    lib = L.lib()
+    hp = S.hidden_lattice(3000, seed=9)
+    st = {k: v.cuda() for k, v in _state(hp, 700, seed=4).items()}
+    X = (st["estimate_xyz"]).contiguous()
+    N, V, H = X.size(0), st["visual_xyz"].size(0), 2.0
+    stream = torch.cuda.current_stream().cuda_stream
+    g = P.Grid(X, H)
+    _, kth = g.count(X, H, K)
+    _, kthV = g.count(st["visual_xyz"], H, K)
+    z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device="cuda")
+    p_ref, p_got, kth_got, flag = z(N), z(N), z(N, dt=torch.int32), z(1, dt=torch.int32)
+    im = st["imass"].reshape(-1).contiguous()
+    L.check(lib.fnx_pbf_density_fwd(g.buf.data_ptr(), X.data_ptr(), N, im.data_ptr(), kth.data_ptr(), H, 1.5, p_ref.data_ptr(), stream))
+    L.check(lib.fnx_pbf_density_fwd_counted(g.buf.data_ptr(), X.data_ptr(), N, im.data_ptr(), K, H, 1.5, kth_got.data_ptr(),
+                                            p_got.data_ptr(), flag.data_ptr(), stream))
+    assert torch.equal(kth_got, kth) and torch.equal(p_got, p_ref)
+    assert int(flag.item()) == (1 if K == 12 else 0)
+    vis, xyz = st["visual_xyz"].contiguous(), st["xyz"].contiguous()
+    o_ref, n_ref, d_ref, o_got, n_got, d_got = z(V, 3), z(V, 3), z(V), z(V, 3), z(V, 3), z(V)
+    kthV_got = z(V, dt=torch.int32)
+    L.check(lib.fnx_visual_advect_fwd(g.buf.data_ptr(), X.data_ptr(), xyz.data_ptr(), N, vis.data_ptr(), V, kthV.data_ptr(), H, 0.033, 100.0,
+                                      o_ref.data_ptr(), n_ref.data_ptr(), d_ref.data_ptr(), stream))
+    L.check(lib.fnx_visual_advect_fwd_counted(g.buf.data_ptr(), X.data_ptr(), xyz.data_ptr(), N, vis.data_ptr(), V, K, H, 0.033, 100.0,
+                                              o_got.data_ptr(), n_got.data_ptr(), d_got.data_ptr(), kthV_got.data_ptr(), stream))
+    assert torch.equal(kthV_got, kthV)
+    assert torch.equal(o_got, o_ref) and torch.equal(n_got, n_ref) and torch.equal(d_got, d_ref)
