@@ -5,7 +5,7 @@
 
 Metric (BASELINE.json): train-step iterations per second.  One *iteration* = one pass of the reference's hot loop for
 one frame with `views` (5) cameras (FD/entries_fluid_nexus/train_physical_particle.py:330-420).  One bench *step*
-processes `frames_in_flight` (8) independent synthetic frames, each one iteration; the frames are sharded over the
+processes `frames_in_flight` (16) independent synthetic frames, each one iteration; the frames are sharded over the
 ranks (strong scaling: total work per step is fixed), gradients of all frames live in one flat bucket that is
 all-reduced (NCCL, sum) once per step and applied with one fused Adam launch on every rank (replicated parameters).
 value = frames_in_flight * K / T, T = max over ranks of the CUDA-event time of the K timed steps.
@@ -429,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="fnx", choices=["fnx", "reference"])
     ap.add_argument("--workload", default="smoke", choices=list(WORKLOADS))
-    ap.add_argument("--frames-in-flight", type=int, default=8)
+    ap.add_argument("--frames-in-flight", type=int, default=16)
     ap.add_argument("--lanes", type=int, default=4, help="CUDA streams per GPU that independent frames are dealt to")
     ap.add_argument("--ref-max-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")

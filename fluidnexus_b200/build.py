@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
                 [os.path.getmtime(src)] + [os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))]
                 + [os.path.getmtime(h) for h in glob.glob(os.path.join(HERE, "..", "include", "*.h"))])):
             continue
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", src, "-o", obj]
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("FNX_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -81,11 +81,11 @@ ImageView image_view(void *chunk, int W, int H, int V) {
     im.final_T = carve<float>(p, hw);
     im.n_contrib = carve<uint32_t>(p, hw);
     im.ranges = carve<uint2>(p, nt);
-    im.tile_last = carve<uint32_t>(p, nt);
+    im.tile_last = carve<uint32_t>(p, nt * TILE_PATCHES);  // per 8x8 patch
     im.mranges = carve<uint2>(p, nt);
     im.tile_src = carve<uint32_t>(p, nt);
     im.tile_dyn_last = carve<uint32_t>(p, nt);
-    im.tile_cached = carve<uint32_t>(p, nt);
+    im.tile_cached = carve<uint32_t>(p, nt * TILE_PATCHES);  // per 8x8 patch
     im.tile_count = carve<uint32_t>(p, 2 * nt);  // count and cursor are contiguous: one memset clears both
     im.tile_cursor = im.tile_count + nt;
     im.snap = carve<float4>(p, hw);
@@ -617,12 +617,27 @@ constexpr uint32_t FROZEN_BIT = 1u << 31;  // record of a Gaussian that needs no
 // (lx, ly + 4): the per-record costs that do not depend on the pixel (record loads, bit iteration, the warp reduction of
 // the backward) are paid once per 64 pixels.  4 warps = 128 threads per tile.
 constexpr int PPT = 2;
-constexpr int PATCH = 8;
-constexpr int BLEND_WARPS = (TILE / PATCH) * (TILE / PATCH);  // 4
-constexpr int BLEND_THREADS = BLEND_WARPS * 32;               // 128
+// Warps per blend CTA.  4: one CTA per tile sharing one staged copy of the span.  1: every 8x8 patch is its own CTA --
+// it streams the tile's span by itself, needs no block barrier and stops as soon as ITS 64 pixels are done.  Measured on
+// B200 (smoke workload, whole bench): 4 -> 1520 it/s, 2 -> 1414, 1 -> 1400 (at most 32 one-warp CTAs per SM, 4x the
+// L2 -> shared traffic and 4x the mask building outweigh the finer scheduling), so 4 is the default.
+#ifndef FNX_BLEND_WARPS
+#define FNX_BLEND_WARPS 4
+#endif
+constexpr int BLEND_WARPS = FNX_BLEND_WARPS;
+static_assert(BLEND_WARPS == 1 || BLEND_WARPS == 2 || BLEND_WARPS == 4, "1, 2 or 4 warps per blend CTA");
+constexpr int BLEND_THREADS = BLEND_WARPS * 32;
+constexpr int CTAS_PER_TILE = TILE_PATCHES / BLEND_WARPS;
+__device__ __forceinline__ void cta_sync() {
+    if (BLEND_WARPS == 1) __syncwarp(); else __syncthreads();
+}
+__device__ __forceinline__ bool cta_all(bool pred) {  // barrier + "pred holds in every thread of the CTA"
+    if (BLEND_WARPS == 1) return __all_sync(0xffffffffu, pred);
+    return __syncthreads_count(pred) == BLEND_THREADS;
+}
 __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co, int tx, int ty, bool exact_rect) {
     const TileCull tc = make_cull(co, exact_rect);
-    if (!tc.active) return (1u << BLEND_WARPS) - 1u;
+    if (!tc.active) return (1u << TILE_PATCHES) - 1u;
     if (tc.tau < 0.f) return 0u;
     // axis-aligned extent of the ellipse q <= tau: |ux| <= sqrt(2 tau c / det), |uy| <= sqrt(2 tau a / det)
     const float det = tc.a * tc.c - tc.b * tc.b;
@@ -632,7 +647,7 @@ __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co,
     const bool exact = fmaxf(hx, hy) < 10.f;
     uint32_t m = 0;
 #pragma unroll
-    for (int w = 0; w < BLEND_WARPS; w++) {
+    for (int w = 0; w < TILE_PATCHES; w++) {
         const int bx = tx * TILE + (w & 1) * PATCH, by = ty * TILE + (w >> 1) * PATCH;
         const bool bbox = (xy.x + hx >= bx) && (xy.x - hx <= bx + PATCH - 1) && (xy.y + hy >= by) && (xy.y - hy <= by + PATCH - 1);
         if (bbox && (!exact || box_needed(tc, xy, bx, by, PATCH, PATCH))) m |= 1u << w;
@@ -703,7 +718,7 @@ __device__ __forceinline__ bool pair_alpha(float x, float y, float a, float b, f
     return true;
 }
 
-constexpr int BATCH = 128;  // records per smem stage
+constexpr int BATCH = BLEND_WARPS == 1 ? 64 : 128;  // records per smem stage (32 one-warp CTAs per SM need <= 7 KB each)
 constexpr int STAGES = 2;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -746,8 +761,11 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
 //                  backward needs from them only the transmittance T and the colour behind, per pixel, at L.  The
 //                  forward snapshots {T, C} when it passes L and stores {T, (C_final - C) / T} in `snap`, so the
 //                  backward starts at L instead of at the last contributor.
+#ifndef FNX_FWD_MIN_CTAS
+#define FNX_FWD_MIN_CTAS 1
+#endif
 template <int C>
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, FNX_FWD_MIN_CTAS)
 blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
                  uint32_t *__restrict__ tile_cached, const uint32_t *__restrict__ tile_dyn_last, float4 *__restrict__ snap,
@@ -757,18 +775,19 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
-    const int tile = blockIdx.x, v = blockIdx.y;
+    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
     const int ntiles = gx * gy;
     const size_t tslot = (size_t)v * ntiles + tile;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x % CTAS_PER_TILE) * BLEND_WARPS + (threadIdx.x >> 5);  // which 8x8 patch of the tile
+    const size_t pslot = tslot * TILE_PATCHES + warp;
     const bool from_static = tile_src != nullptr && tile_src[tslot] != 0;
     if (tile_cached != nullptr) {
-        if (from_static) {
-            if (tile_cached[tslot] != 0) return;  // uniform over the CTA; the pixels are already in place
-        }
+        // the pixels are already in place (the flags of a CTA's patches are always written together: uniform over the CTA)
+        if (from_static && tile_cached[pslot - (threadIdx.x >> 5)] != 0) return;
         // (the flag is updated at the end, after the pixels are written)
     }
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = tx * TILE + (warp & 1) * PATCH + (lane & 7);
     const int py0 = ty * TILE + (warp >> 1) * PATCH + (lane >> 3);  // pixel p of this thread is (px, py0 + 4p)
     const float pxf = (float)px;
@@ -805,7 +824,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         for (int s = 0; s < STAGES; s++) mbar_init(&s_bar[s], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    cta_sync();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++)
@@ -824,7 +843,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
 #pragma unroll
         for (int p = 0; p < PPT; p++) all_done = all_done && (done[p] != 0);
         // whole tile finished?  (also orders the previous stage's reads before its buffer is refilled)
-        if (__syncthreads_count(all_done) == BLEND_THREADS) break;
+        if (cta_all(all_done)) break;
         if (threadIdx.x == 0 && bi >= 1 && bi + STAGES - 1 < nbatch) {
             // refill the stage consumed in the previous iteration
             const int nb = bi + STAGES - 1, ns = nb % STAGES;
@@ -899,8 +918,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     for (int p = 0; p < PPT; p++) wl = max(wl, last_contributor[p]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-    __shared__ uint32_t s_last[BLEND_WARPS];
-    if (lane == 0) s_last[warp] = wl;
+    if (lane == 0) im.tile_last[pslot] = wl;
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
         if (!inside[p]) continue;
@@ -918,13 +936,9 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                                                      (Cacc[p][2 % C] - C_snap[p][2 % C]) * inv);
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int w = 0; w < BLEND_WARPS; w++) m = max(m, s_last[w]);
-        im.tile_last[tslot] = m;
-        if (tile_cached != nullptr) tile_cached[tslot] = from_static ? 1u : 0u;
+    if (tile_cached != nullptr) {
+        cta_sync();  // every pixel of the CTA's patches is written before their flags say so
+        if (lane == 0) tile_cached[pslot] = from_static ? 1u : 0u;
     }
 }
 
@@ -998,10 +1012,11 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
-    const int tile = blockIdx.x, v = blockIdx.y;
+    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
     const int ntiles = gx * gy;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x % CTAS_PER_TILE) * BLEND_WARPS + (threadIdx.x >> 5);  // which 8x8 patch of the tile
     const int px = tx * TILE + (warp & 1) * PATCH + (lane & 7);
     const int py0 = ty * TILE + (warp >> 1) * PATCH + (lane >> 3);
     const float pxf = (float)px;
@@ -1014,7 +1029,11 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const uint2 range = ranges[tslot];
     const char *records = records_own;
     (void)records_static;
-    int total = (int)im.tile_last[tslot];  // records [0,total) of the span matter
+    // records [0,total) of the span matter to this CTA's patches
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < BLEND_WARPS; w++)
+        total = max(total, (int)im.tile_last[tslot * TILE_PATCHES + (blockIdx.x % CTAS_PER_TILE) * BLEND_WARPS + w]);
     // merged streams: everything at or behind L is frozen; the forward left {T, colour behind} at L in `snap`
     const int L = (snap != nullptr && tile_dyn_last != nullptr) ? (int)tile_dyn_last[tslot] : 0x7FFFFFFF;
     total = min(total, L);
@@ -1027,7 +1046,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         for (int s = 0; s < STAGES; s++) mbar_init(&s_bar[s], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    cta_sync();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++)
@@ -1083,7 +1102,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     for (int bi = 0; bi < nbatch; bi++) {
         const int s = bi % STAGES;
         if (bi >= 1) {
-            __syncthreads();  // everyone finished reading the stage that is about to be refilled
+            cta_sync();  // everyone finished reading the stage that is about to be refilled
             if (threadIdx.x == 0 && bi + STAGES - 1 < nbatch) {
                 const int nb = bi + STAGES - 1, ns = nb % STAGES;
                 const int hi = total - nb * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
@@ -1441,7 +1460,7 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
         FNX_LAUNCH_CHECK("pack_kernel");
     }
     if (a->flags & FNX_BIN_ONLY) return FNX_OK;  // the caller blends a merged stream (fnx_raster_blend_merged)
-    dim3 grid(ntiles, V);
+    dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_FWD, st);
     blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr,
                                                         im.ranges, nullptr, nullptr, nullptr, nullptr, g.depth, a->bg, g.hdr, im, out_color,
@@ -1620,7 +1639,7 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     }
     BinView b = bin_view(scratch->binning, cap, C);
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
-    dim3 grid(ntiles, V);
+    dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr, im.ranges,
                                                         nullptr, nullptr, nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
@@ -1663,7 +1682,7 @@ merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__re
     // Static records behind the last one that the static-only blend of this tile used can never be reached once more
     // occluders are inserted: a pixel's transmittance at a given static record only shrinks (rounding is monotone),
     // so it terminates no later, and the alpha test does not depend on what lies in front.
-    if (hdr_stat->static_prepared) nb = min(nb, (int)static_last[t]);
+    if (hdr_stat->static_prepared) nb = min(nb, (int)max(max(static_last[4 * t], static_last[4 * t + 1]), max(static_last[4 * t + 2], static_last[4 * t + 3])));
     if (hdr_dyn->overflow) nf = 0;
     if (nf == 0) {
         if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
@@ -1727,7 +1746,8 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
     const uint2 f = ranges_dyn[t], b = ranges_stat[t];
     int nf = (int)(f.y - f.x);
     int nb = (int)(b.y - b.x);
-    if (hdr_stat->static_prepared) nb = min(nb, (int)static_last[t]);  // see merge_kernel
+    if (hdr_stat->static_prepared)  // see merge_kernel
+        nb = min(nb, (int)max(max(static_last[4 * t], static_last[4 * t + 1]), max(static_last[4 * t + 2], static_last[4 * t + 3])));
     if (g.hdr->overflow) nf = 0;
     if (nf == 0) {
         if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
@@ -1836,7 +1856,7 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     prof_end(SEC_PACK, st);
     FNX_LAUNCH_CHECK("merge_kernel");
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
+    blend_fwd_kernel<3><<<dim3(ntiles * CTAS_PER_TILE, V), BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
                                                         tile_cache ? ims.tile_cached : nullptr, im.tile_dyn_last, im.snap, g.depth, a->bg,
                                                         g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);
@@ -1857,9 +1877,9 @@ static int static_prepare(const fnx_raster_args *a, const fnx_raster_scratch *st
     GeomView gs = geom_view(stat->geom, P, V);
     ImageView ims = image_view(stat->image, W, H, V);
     BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
-    FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_cached, 0, sizeof(uint32_t) * (size_t)ntiles * V, st));
+    FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_cached, 0, sizeof(uint32_t) * (size_t)ntiles * V * TILE_PATCHES, st));
     FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_src, 0xFF, sizeof(uint32_t) * (size_t)ntiles * V, st));  // every tile: "from the static stream"
-    dim3 grid(ntiles, V);
+    dim3 grid(ntiles * CTAS_PER_TILE, V);
     blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, bs.records, bs.records, ims.ranges, ims.tile_src, ims.tile_cached,
                                                         nullptr, nullptr, gs.depth, a->bg, gs.hdr, ims, out_color, out_depth);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
@@ -1880,7 +1900,7 @@ static int backward_merged(const fnx_raster_args *a, const fnx_raster_scratch *d
     ImageView im = image_view(dyn->image, W, H, V);
     BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
-    dim3 grid(ntiles, V);
+    dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
                                                         im.tile_dyn_last, im.snap, a->bg, g.hdr, im, dL_dout_color, g.accum);
@@ -1961,7 +1981,7 @@ int fnx_raster_read_tiles(const fnx_raster_scratch *scratch, int32_t W, int32_t 
     ImageView im = image_view(scratch->image, W, H, V);
     const size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
     if (ranges) FNX_CUDA_TRY(cudaMemcpyAsync(ranges, merged ? im.mranges : im.ranges, nt * 8, cudaMemcpyDeviceToDevice, st));
-    if (tile_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_last, im.tile_last, nt * 4, cudaMemcpyDeviceToDevice, st));
+    if (tile_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_last, im.tile_last, nt * 4 * TILE_PATCHES, cudaMemcpyDeviceToDevice, st));
     if (tile_src) FNX_CUDA_TRY(cudaMemcpyAsync(tile_src, im.tile_src, nt * 4, cudaMemcpyDeviceToDevice, st));
     if (tile_dyn_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_dyn_last, im.tile_dyn_last, nt * 4, cudaMemcpyDeviceToDevice, st));
     return FNX_OK;

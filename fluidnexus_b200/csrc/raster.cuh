@@ -6,6 +6,8 @@ namespace fnx {
 
 constexpr int TILE = 16;                 // 16x16 pixel tiles (R3/cuda_rasterizer/config.h:16-17)
 constexpr int TILE_PIX = TILE * TILE;
+constexpr int PATCH = 8;                 // a warp of the blend kernels owns an 8x8 pixel patch of a tile
+constexpr int TILE_PATCHES = (TILE / PATCH) * (TILE / PATCH);  // 4
 constexpr float DEPTH_DEFAULT = 15.0f;   // forward.cu:295
 constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr float ALPHA_MAX = 0.99f;
@@ -66,11 +68,11 @@ struct ImageView {
     float *final_T;          // [V*H*W]
     uint32_t *n_contrib;     // [V*H*W]
     uint2 *ranges;           // [V*ntiles]
-    uint32_t *tile_last;     // [V*ntiles] max n_contrib over the tile's pixels (backward start)
+    uint32_t *tile_last;     // [V*ntiles*4] per 8x8 patch: max n_contrib over its pixels (backward start)
     uint2 *mranges;          // [V*ntiles] merged ranges (static + dynamic streams), see fnx_raster_blend_merged
     uint32_t *tile_src;      // [V*ntiles] 0: the tile's span lives in the call's own record stream, 1: in the static one
     uint32_t *tile_dyn_last; // [V*ntiles] merged streams: 1 + span index of the tile's last dynamic record (0: none)
-    uint32_t *tile_cached;   // [V*ntiles] static stream: 1 <=> the caller's out_color/out_depth hold this tile's static-only render
+    uint32_t *tile_cached;   // [V*ntiles*4] static stream, per patch: 1 <=> the caller's out_color/out_depth hold its static-only render
     float4 *snap;            // [V*H*W] merged streams: {T, colour behind} right after the tile's last dynamic record
     uint32_t *tile_count;    // [V*ntiles] bucket binning: instances per tile (histogram written by the preprocess)
     uint32_t *tile_cursor;   // [V*ntiles] bucket binning: fill cursor of the tile's bucket

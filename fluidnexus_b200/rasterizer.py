@@ -289,7 +289,15 @@ class MergedRasterWorkspace:
             u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=self.dev)
             self.geom, self.image = u8(lib.fnx_raster_geom_bytes(P_dyn, V)), u8(lib.fnx_raster_image_bytes(W, H, V))
             self.binning = u8(lib.fnx_raster_binning_bytes(self.capacity, 3))
-            self.merged = u8(48 * (self.capacity + self.R_static) + 256)
+            # merged spans hold the tile's dynamic records + the static records a blend can reach: after the static-only
+            # blend that is sum(tile_last) static records instead of all R_static
+            n_static_reach = self.R_static
+            if static_prepare:
+                nt = V * ((W + 15) // 16) * ((H + 15) // 16)
+                last = torch.zeros((nt, 4), dtype=torch.int32, device=self.dev)  # per 8x8 patch
+                L.check(lib.fnx_raster_read_tiles(C.byref(self.sscratch), W, H, V, 0, None, last.data_ptr(), None, None, st))
+                n_static_reach = int(last.max(dim=1).values.sum().item())
+            self.merged = u8(48 * (self.capacity + n_static_reach) + 256)
             self.grads = {"means3D": torch.empty((P_dyn, 3), device=self.dev)}
         self.count = torch.full((1,), -1, dtype=torch.int64).pin_memory()
         self._cbs = tuple(L.ALLOC_FN(RasterWorkspace._fixed(t)) for t in (self.geom, self.binning, self.image))
@@ -323,12 +331,13 @@ class MergedRasterWorkspace:
         forward blended (tile_last), tile_src (1: static-only tile) and tile_dyn_last (where the backward starts)."""
         nt = self.V * ((self.W + 15) // 16) * ((self.H + 15) // 16)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=self.dev)
-        ranges, last, src, dyn = i32(nt, 2), i32(nt), i32(nt), i32(nt)
+        ranges, last, src, dyn = i32(nt, 2), i32(nt, 4), i32(nt), i32(nt)
         L.check(L.lib().fnx_raster_read_tiles(C.byref(self.scratch), self.W, self.H, self.V, 1, ranges.data_ptr(), last.data_ptr(),
                                               src.data_ptr(), dyn.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
         torch.cuda.synchronize(self.dev)
         r = ranges.cpu().numpy().astype("int64")
-        return dict(begin=r[:, 0], end=r[:, 1], tile_last=last.cpu().numpy().astype("int64"), tile_src=src.cpu().numpy(),
+        pl = last.cpu().numpy().astype("int64")   # per 8x8 patch of the tile
+        return dict(begin=r[:, 0], end=r[:, 1], tile_last=pl.max(axis=1), patch_last=pl, tile_src=src.cpu().numpy(),
                     tile_dyn_last=dyn.cpu().numpy().astype("int64"))
 
     def num_rendered(self):

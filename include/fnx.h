@@ -319,8 +319,8 @@ int fnx_raster_read_geom(const fnx_raster_scratch *scratch, int32_t P, int32_t V
 int fnx_raster_read_image(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, float *final_T,
                           uint32_t *n_contrib, fnx_stream_t stream);
 /* Per-tile state [V, tiles] of the last forward (measurement / tests): ranges uint32 [.,2] (begin, end of the tile's
- * span; merged != 0: in the merged stream of fnx_raster_blend_merged), tile_last (records of the span the blend
- * used), and for merged streams tile_src (1: blended straight from the static stream) and tile_dyn_last (1 + span
+ * span; merged != 0: in the merged stream of fnx_raster_blend_merged), tile_last uint32 [.,4] (records of the span
+ * that the blend used, per 8x8 pixel patch of the tile), and for merged streams tile_src (1: blended straight from the static stream) and tile_dyn_last (1 + span
  * index of the last dynamic record: where the backward starts). */
 int fnx_raster_read_tiles(const fnx_raster_scratch *scratch, int32_t W, int32_t H, int32_t V, int32_t merged, uint32_t *ranges,
                           uint32_t *tile_last, uint32_t *tile_src, uint32_t *tile_dyn_last, fnx_stream_t stream);

@@ -57,5 +57,32 @@ def main():
     lib.fnx_profile_enable(0)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("FNX_TILE_STATS"):
     main()
+
+
+def tile_stats():
+    """Distribution of the per-tile / per-patch span lengths of the last forward (what bounds the blend kernels' tail)."""
+    wl = os.environ.get("FNX_WORKLOAD", "smoke")
+    dev = torch.device("cuda", 0)
+    cams, bg, frames, cfg = bench.build_frames(wl, 1, dev)
+    prm = StepParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], grey=cfg["grey"], distance_threshold_visual=cfg["thr"])
+    ps = PhysicalStep(cams, cfg["C"], prm, device=dev)
+    fr = FrameState(frames[0]["hidden"], frames[0]["visual"], frames[0]["fluid"], bg, device=dev, prm=prm)
+    gt = torch.rand(5, cfg["C"], cfg["size"], cfg["size"], device=dev) * 0.5
+    for _ in range(3):
+        out = ps.step(fr, [0, 1, 2, 3, 4], gt)
+    ts = out["ws"].tile_state()
+    dyn = ts["tile_src"] == 0
+    q = lambda a: " ".join(f"{np.percentile(a, p):.0f}" for p in (50, 90, 99, 100))
+    print("dynamic tiles", int(dyn.sum()), "of", dyn.size)
+    print("merged span length (p50 p90 p99 max):", q((ts["end"] - ts["begin"])[dyn]))
+    print("tile_last fwd:", q(ts["tile_last"][dyn]), " sum", int(ts["tile_last"][dyn].sum()))
+    print("patch_last fwd:", q(ts["patch_last"][dyn].reshape(-1)))
+    print("dyn_last (bwd start):", q(ts["tile_dyn_last"][dyn]), " sum", int(np.minimum(ts["tile_last"], ts["tile_dyn_last"])[dyn].sum()))
+    nstat = ts["tile_last"][~dyn]
+    print("static-only tiles tile_last:", q(nstat))
+
+
+if os.environ.get("FNX_TILE_STATS"):
+    tile_stats()
