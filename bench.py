@@ -149,10 +149,13 @@ def run_fnx(args):
 
     use_graph = [not args.no_graph]
 
+    serial = [False]   # True: all frames on the current stream, one after the other (the kernel-duration leg)
+
     def one_step(e2e):
         # e2e: ground truth comes from pinned HOST memory every iteration (the reference uploads it at :325)
-        outs = lanes.run(mine, lambda step, f: step.step(states[f], by_frame[f], gts_pinned[f] if e2e else gts_dev[f], update=False,
-                                                         batch=len(views), graph=use_graph[0], physics=f in physics_frames))
+        call = lambda step, f: step.step(states[f], by_frame[f], gts_pinned[f] if e2e else gts_dev[f], update=False,
+                                         batch=len(views), graph=use_graph[0], physics=f in physics_frames)
+        outs = [call(ps, f) for f in mine] if serial[0] else lanes.run(mine, call)
         last = outs[-1] if outs else None
         fb.all_reduce()
         step_no[0] += 1
@@ -207,7 +210,9 @@ def run_fnx(args):
     import ctypes as C
     nsec = lib.fnx_profile_sections()
     names = [lib.fnx_profile_section_name(i).decode() for i in range(nsec)]
-    use_graph[0] = False
+    # (frames one after the other on one stream here: with several lanes the events of one frame's kernel would also span
+    # whatever the other lanes squeeze in between)
+    use_graph[0], serial[0] = False, True
     one_step(False)
     lib.fnx_profile_enable((1 << nsec) - 1)
     lib.fnx_profile_collect(None, None)
@@ -215,7 +220,7 @@ def run_fnx(args):
     tot = (C.c_float * nsec)(); cnt = (C.c_int32 * nsec)()
     L.check(lib.fnx_profile_collect(tot, cnt))
     lib.fnx_profile_enable(0)
-    use_graph[0] = graph_flag
+    use_graph[0], serial[0] = graph_flag, False
     value = G * args.steps / (ms / 1e3)
     e2e = G * args.steps / (ms_e2e / 1e3)
     ws_last = out["ws"] if out and "ws" in out else None
@@ -288,8 +293,10 @@ def run_fnx(args):
                    "frames_in_flight": G, "lanes_per_gpu": lanes.n, "views_per_iteration": 5, "parallelism": f"frames sharded over {world} rank(s), "
                    "one NCCL all-reduce of the flat gradient bucket per step" if world > 1 else "single GPU",
                    "instances_per_iteration": R_per_iter,
-                   "l2": f"working set per iteration ~{(R_per_iter * (rec + 16) + 5 * HW * 40) / 1e6:.0f} MB and {G} frames "
-                         "cycle between iterations: larger than the 126 MB L2, no explicit flush"},
+                   "l2": f"no explicit flush: {G} frames cycle between iterations and one iteration touches "
+                         f"~{((tile_info['records_in_merged_spans'] if tile_info else R_per_iter) * rec + 5 * HW * (16 * Cc + 44)) / 1e6:.0f} MB "
+                         "(record spans + images, ground truth, gradient and SSIM maps), so a frame's data has left the 126 MB L2 "
+                         "by the time its next iteration starts"},
         "e2e": {"value": round(e2e, 3), "unit": "iters/s",
                 "h2d_bytes_per_step": int(sum(len(v) for v in by_frame.values()) * Cc * HW * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},

@@ -76,8 +76,16 @@ static size_t grid_bytes(int n) {
 __device__ __forceinline__ int3 cell_of(float x, float y, float z, float inv_cell) {
     return make_int3(__float2int_rd(x * inv_cell), __float2int_rd(y * inv_cell), __float2int_rd(z * inv_cell));
 }
+// Cell -> bucket: the table is a periodic A x B x C box of cells (powers of two, each >= 8, A*B*C = M): bucket =
+// (x mod A, y mod B, z mod C).  Unlike a multiplicative hash this makes the 27 cells around any query map to 27
+// DIFFERENT buckets, and a point that shares a bucket with a neighbour cell without being in it lies at least A-1 >= 7
+// cells away along some axis, i.e. farther than the search radius (<= one cell): gathers therefore need no
+// "is this point really in that cell" test and no de-duplication, the distance test does it all.
 __device__ __forceinline__ uint32_t hash_cell(int3 c, int M) {
-    return ((uint32_t)c.x * 73856093u ^ (uint32_t)c.y * 19349663u ^ (uint32_t)c.z * 83492791u) & (uint32_t)(M - 1);
+    const int m = 31 - __clz(M);          // M = 2^m, m >= 10
+    const int ax = m / 3, az = m / 3, ay = m - ax - az;
+    return ((uint32_t)c.x & ((1u << ax) - 1u)) | (((uint32_t)c.y & ((1u << ay) - 1u)) << ax) |
+           (((uint32_t)c.z & ((1u << az) - 1u)) << (ax + ay));
 }
 
 __global__ void grid_count_kernel(const float *__restrict__ pts, int n, float inv_cell, int M, uint32_t *__restrict__ fill) {
@@ -135,7 +143,8 @@ static int grid_build(const float *pts, int n, float cell, void *scratch, cudaSt
     return FNX_OK;
 }
 
-// Visit every grid point within sqrt(r2) of q.  f(j, pj, d2).  Requires cell >= r.
+// Visit every grid point within sqrt(r2) of q.  f(j, pj, d2).  Requires cell >= r (see hash_cell for why the distance
+// test alone is exact).
 template <typename F>
 __device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, F f) {
     const int3 c = cell_of(q.x, q.y, q.z, inv_cell);
@@ -145,13 +154,10 @@ __device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_c
         for (int dy = -1; dy <= 1; dy++)
 #pragma unroll 1
             for (int dx = -1; dx <= 1; dx++) {
-                const int3 cc = make_int3(c.x + dx, c.y + dy, c.z + dz);
-                const uint32_t b = hash_cell(cc, g.M);
+                const uint32_t b = hash_cell(make_int3(c.x + dx, c.y + dy, c.z + dz), g.M);
                 const uint32_t s = g.bucket_start[b], e = g.bucket_start[b + 1];
                 for (uint32_t a = s; a < e; a++) {
                     const float4 p = g.sorted_pos[a];
-                    const int3 pc = cell_of(p.x, p.y, p.z, inv_cell);
-                    if (pc.x != cc.x || pc.y != cc.y || pc.z != cc.z) continue;  // hash collision / aliased cell
                     const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
                     const float d2 = ex * ex + ey * ey + ez * ez;
                     if (d2 < r2) f((int)__float_as_uint(p.w), p, d2);
@@ -159,26 +165,43 @@ __device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_c
             }
 }
 
-// Warp-cooperative variant: the 32 lanes of a warp share ONE query; lane l < 27 walks neighbour cell l.  Callers reduce
-// their per-lane partials with warp_sum().  (28k queries x 27 cells x ~10 points is latency bound with one thread per
-// query; a warp per query gives the memory system 27 independent bucket walks per query.)
+// Group-cooperative variant: GROUP = 8 consecutive lanes share ONE query; lane l walks neighbour cells l, l+8, l+16
+// (and l+24 < 27).  Callers reduce their per-lane partials with group_sum().  One thread per query is latency bound
+// (28k queries x 27 dependent bucket walks); a whole warp per query leaves 2/3 of the lanes idle (27 cells of ~11
+// points with very uneven fill: the first profile of density_bwd showed 10 of 32 lanes active per instruction and the
+// kernel issue bound); 8 lanes x 3-4 cells evens the fill out and still gives 16 independent queries per 128 threads.
+constexpr int GROUP = 8;
+constexpr int QPB = 128 / GROUP;  // queries per 128-thread block
 template <typename F>
 __device__ __forceinline__ void warp_for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, int lane, F f) {
-    if (lane >= 27) return;
     const int3 c = cell_of(q.x, q.y, q.z, inv_cell);
-    const int3 cc = make_int3(c.x + (lane % 3) - 1, c.y + ((lane / 3) % 3) - 1, c.z + (lane / 9) - 1);
-    const uint32_t b = hash_cell(cc, g.M);
-    const uint32_t s = g.bucket_start[b], e = g.bucket_start[b + 1];
-    for (uint32_t a = s; a < e; a++) {
-        const float4 p = g.sorted_pos[a];
-        const int3 pc = cell_of(p.x, p.y, p.z, inv_cell);
-        if (pc.x != cc.x || pc.y != cc.y || pc.z != cc.z) continue;
-        const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-        const float d2 = ex * ex + ey * ey + ez * ez;
-        if (d2 < r2) f((int)__float_as_uint(p.w), p, d2);
+#pragma unroll 1
+    for (int ci = lane; ci < 27; ci += GROUP) {
+        const uint32_t b = hash_cell(make_int3(c.x + (ci % 3) - 1, c.y + ((ci / 3) % 3) - 1, c.z + (ci / 9) - 1), g.M);
+        const uint32_t s = g.bucket_start[b], e = g.bucket_start[b + 1];
+        for (uint32_t a = s; a < e; a++) {
+            const float4 p = g.sorted_pos[a];
+            const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            if (d2 < r2) f((int)__float_as_uint(p.w), p, d2);
+        }
     }
 }
-constexpr int QPB = 4;  // queries (warps) per 128-thread block
+// sums over the 8 lanes of a query group (xor shuffles stay inside an aligned group; only the group's lanes are named
+// in the mask, so groups of one warp may diverge)
+__device__ __forceinline__ unsigned group_mask() { return 0xFFu << ((threadIdx.x & 31) & ~(GROUP - 1)); }
+__device__ __forceinline__ float group_sum(float v) {
+    const unsigned m = group_mask();
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+}
+__device__ __forceinline__ int group_sum(int v) {
+    const unsigned m = group_mask();
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // neighbour counts + the index cut-off that realises torch_cluster's max_num_neighbors rule
@@ -191,7 +214,7 @@ __device__ __forceinline__ int kth_by_bisection(const GridView &g, float inv_cel
         const int mid = (lo + hi) >> 1;
         int below = 0;
         warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float) { below += (j <= mid); });
-        below = __reduce_add_sync(0xffffffffu, below);
+        below = group_sum(below);
         if (below >= K) hi = mid; else lo = mid + 1;
     }
     return lo;
@@ -200,13 +223,13 @@ __device__ __forceinline__ int kth_by_bisection(const GridView &g, float inv_cel
 __global__ void __launch_bounds__(128)
 radius_count_kernel(GridView g, float inv_cell, const float *__restrict__ y, int ny, float r2, int K, int n_x,
                     int *__restrict__ counts, int *__restrict__ kth) {
-    const int c = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (c >= ny) return;
     const float3 q = make_float3(y[3 * c], y[3 * c + 1], y[3 * c + 2]);
     int cnt = 0;
     warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int, const float4 &, float) { cnt++; });
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    cnt = group_sum(cnt);
     int cut = 0x7fffffff;
     if (cnt > K) {
         cut = kth_by_bisection(g, inv_cell, q, r2, lane, K, n_x);
@@ -264,15 +287,15 @@ __device__ __forceinline__ float dpoly6_dd2(float d2, float H2, float term1) {
 __global__ void __launch_bounds__(128)
 density_fwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio) {
-    const int r = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
     warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2) {
         if (r <= kth[c]) pi += poly6(d2, H2, term1);
     });
-    pi = warp_sum(pi);
+    pi = group_sum(pi);
     if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
 }
 
@@ -284,8 +307,8 @@ __global__ void __launch_bounds__(128)
 density_fwd_counted_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass, int K,
                            float H2, float term1, float p0, int *__restrict__ kth, float *__restrict__ p_ratio,
                            int *__restrict__ cap_flag) {
-    const int r = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
@@ -294,8 +317,8 @@ density_fwd_counted_kernel(GridView g, float inv_cell, const float *__restrict__
         cnt++;
         pi += poly6(d2, H2, term1);
     });
-    pi = warp_sum(pi);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    pi = group_sum(pi);
+    cnt = group_sum(cnt);
     int cut = 0x7fffffff;
     if (cnt > K) {
         cut = kth_by_bisection(g, inv_cell, q, H2, lane, K, N);
@@ -311,15 +334,15 @@ density_fwd_if_capped_kernel(GridView g, float inv_cell, const float *__restrict
                              const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio,
                              const int *__restrict__ cap_flag) {
     if (*cap_flag == 0) return;
-    const int r = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
     warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2) {
         if (r <= kth[c]) pi += poly6(d2, H2, term1);
     });
-    pi = warp_sum(pi);
+    pi = group_sum(pi);
     if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
 }
 
@@ -329,8 +352,8 @@ __global__ void __launch_bounds__(128)
 density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, const float *__restrict__ dL_dpratio,
                    float *__restrict__ dL_dX, int accumulate) {
-    const int k = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (k >= N) return;
     const float3 q = make_float3(X[3 * k], X[3 * k + 1], X[3 * k + 2]);
     const float gpk = dL_dpratio[k] / imass[k] / p0;
@@ -343,7 +366,7 @@ density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
         const float s = 2.f * dpoly6_dd2(d2, H2, term1) * w;
         acc.x += s * (q.x - pj.x); acc.y += s * (q.y - pj.y); acc.z += s * (q.z - pj.z);
     });
-    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z);
+    acc.x = group_sum(acc.x); acc.y = group_sum(acc.y); acc.z = group_sum(acc.z);
     if (lane < 3) {
         const float v = lane == 0 ? acc.x : (lane == 1 ? acc.y : acc.z);
         if (accumulate) dL_dX[3 * k + lane] += v; else dL_dX[3 * k + lane] = v;
@@ -362,8 +385,8 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
                   const float *__restrict__ vis, int V, int *__restrict__ kthV, int K, int n_x, float H2, float term1, float secs,
                   float eps, float out_div, float *__restrict__ vis_out, float *__restrict__ num_out,
                   float *__restrict__ den_out) {
-    const int v = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int v = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (v >= V) return;
     const float3 q = make_float3(vis[3 * v], vis[3 * v + 1], vis[3 * v + 2]);
     int cut = COUNTED ? 0x7fffffff : kthV[v];
@@ -381,7 +404,7 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
     };
     warp_for_each_neighbor(gh, inv_cell, q, H2, lane, gather);
     if (COUNTED) {
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        cnt = group_sum(cnt);
         if (cnt > K) {
             cut = kth_by_bisection(gh, inv_cell, q, H2, lane, K, n_x);
             num = make_float3(0.f, 0.f, 0.f);
@@ -390,7 +413,7 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
         }
         if (lane == 0) kthV[v] = cut;
     }
-    num.x = warp_sum(num.x); num.y = warp_sum(num.y); num.z = warp_sum(num.z); den = warp_sum(den);
+    num.x = group_sum(num.x); num.y = group_sum(num.y); num.z = group_sum(num.z); den = group_sum(den);
     if (lane != 0) return;
     const float dc = fmaxf(den, eps);
     // out_div = scale_factor when the caller wants render units (pipe_fluid.py:45: raw_render_xyz / gm.scale_factor)
@@ -409,8 +432,8 @@ advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, cons
                   const int *__restrict__ kthV, const float *__restrict__ num, const float *__restrict__ den,
                   const float *__restrict__ G /*dL/dvis_out [V,3]*/, const float *__restrict__ G2 /*optional second term*/,
                   float g_scale, float H2, float term1, float secs, float eps, float *__restrict__ dL_dX, int accumulate) {
-    const int j = blockIdx.x * QPB + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     if (j >= N) return;
     const float3 xj = make_float3(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
     const float3 u = make_float3((xj.x - xyz[3 * j]) / secs, (xj.y - xyz[3 * j + 1]) / secs, (xj.z - xyz[3 * j + 2]) / secs);
@@ -433,7 +456,7 @@ advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, cons
         acc.y += s * (xj.y - pv.y) + t * Gv.y;
         acc.z += s * (xj.z - pv.z) + t * Gv.z;
     });
-    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z);
+    acc.x = group_sum(acc.x); acc.y = group_sum(acc.y); acc.z = group_sum(acc.z);
     if (lane < 3) {
         const float val = lane == 0 ? acc.x : (lane == 1 ? acc.y : acc.z);
         if (accumulate) dL_dX[3 * j + lane] += val; else dL_dX[3 * j + lane] = val;
