@@ -32,6 +32,8 @@ struct GridView {
     uint32_t *sorted_idx;    // [n]
     uint32_t *tmp_idx;       // [n] bucket contents in atomic arrival order (before the per-bucket index sort)
     float4 *sorted_pos;      // [n] xyz + idx bits
+    float4 *aux0, *aux1;     // [n] per-point payloads in the SAME (bucket-sorted) order, packed by a gather kernel's
+                             // pre-pass so that the walk reads them next to sorted_pos[a] instead of through the index
     void *cub_temp;
     size_t cub_temp_bytes;
     int M;
@@ -52,6 +54,8 @@ static GridView grid_view(void *chunk, int n) {
     g.sorted_idx = carve<uint32_t>(p, (size_t)(n > 0 ? n : 1));
     g.tmp_idx = carve<uint32_t>(p, (size_t)(n > 0 ? n : 1));
     g.sorted_pos = carve<float4>(p, (size_t)(n > 0 ? n : 1));
+    g.aux0 = carve<float4>(p, (size_t)(n > 0 ? n : 1));
+    g.aux1 = carve<float4>(p, (size_t)(n > 0 ? n : 1));
     // memoised CUB size query (its dispatch layer is slow); a handful of distinct table sizes per process
     static thread_local int cached_M[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     static thread_local size_t cached[8];
@@ -183,7 +187,7 @@ __device__ __forceinline__ void warp_for_each_neighbor(const GridView &g, float 
             const float4 p = g.sorted_pos[a];
             const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
             const float d2 = ex * ex + ey * ey + ez * ez;
-            if (d2 < r2) f((int)__float_as_uint(p.w), p, d2);
+            if (d2 < r2) f((int)__float_as_uint(p.w), p, d2, a);
         }
     }
 }
@@ -213,7 +217,7 @@ __device__ __forceinline__ int kth_by_bisection(const GridView &g, float inv_cel
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         int below = 0;
-        warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float) { below += (j <= mid); });
+        warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float, uint32_t) { below += (j <= mid); });
         below = group_sum(below);
         if (below >= K) hi = mid; else lo = mid + 1;
     }
@@ -228,7 +232,7 @@ radius_count_kernel(GridView g, float inv_cell, const float *__restrict__ y, int
     if (c >= ny) return;
     const float3 q = make_float3(y[3 * c], y[3 * c + 1], y[3 * c + 2]);
     int cnt = 0;
-    warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int, const float4 &, float) { cnt++; });
+    warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int, const float4 &, float, uint32_t) { cnt++; });
     cnt = group_sum(cnt);
     int cut = 0x7fffffff;
     if (cnt > K) {
@@ -292,7 +296,7 @@ density_fwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2) {
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
         if (r <= kth[c]) pi += poly6(d2, H2, term1);
     });
     pi = group_sum(pi);
@@ -313,7 +317,7 @@ density_fwd_counted_kernel(GridView g, float inv_cell, const float *__restrict__
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
     int cnt = 0;
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int, const float4 &, float d2) {
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int, const float4 &, float d2, uint32_t) {
         cnt++;
         pi += poly6(d2, H2, term1);
     });
@@ -339,7 +343,7 @@ density_fwd_if_capped_kernel(GridView g, float inv_cell, const float *__restrict
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2) {
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
         if (r <= kth[c]) pi += poly6(d2, H2, term1);
     });
     pi = group_sum(pi);
@@ -348,6 +352,14 @@ density_fwd_if_capped_kernel(GridView g, float inv_cell, const float *__restrict
 
 // dL/dX_k = sum_{j in N(k)} dpoly6(d2) * 2 (X_k - X_j) * ( gp_k [k <= kth[j]] + gp_j [j <= kth[k]] ),
 // gp_i = dL/dp_ratio_i / (imass_i p0)
+// pre-pass: aux1[a] = { gp_i = dL/dp_ratio_i / (imass_i p0), kth_i } for the point i stored at sorted position a
+__global__ void density_bwd_pack_kernel(GridView g, int N, const float *__restrict__ imass, const int *__restrict__ kth, float p0,
+                                        const float *__restrict__ dL_dpratio) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= N) return;
+    const uint32_t i = g.sorted_idx[a];
+    g.aux1[a] = make_float4(dL_dpratio[i] / imass[i] / p0, __int_as_float(kth[i]), 0.f, 0.f);
+}
 __global__ void __launch_bounds__(128)
 density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, const float *__restrict__ dL_dpratio,
@@ -359,10 +371,11 @@ density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
     const float gpk = dL_dpratio[k] / imass[k] / p0;
     const int kth_k = kth[k];
     float3 acc = make_float3(0.f, 0.f, 0.f);
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2) {
+    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2, uint32_t a) {
+        const float4 pay = g.aux1[a];  // { gp_j, kth_j }
         float w = 0.f;
-        if (k <= kth[j]) w += gpk;
-        if (j <= kth_k) w += dL_dpratio[j] / imass[j] / p0;
+        if (k <= __float_as_int(pay.y)) w += gpk;
+        if (j <= kth_k) w += pay.x;
         const float s = 2.f * dpoly6_dd2(d2, H2, term1) * w;
         acc.x += s * (q.x - pj.x); acc.y += s * (q.y - pj.y); acc.z += s * (q.z - pj.z);
     });
@@ -376,6 +389,14 @@ density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
 // ---------------------------------------------------------------------------------------------------------------
 // P1: advect visual particles with the poly6-interpolated hidden velocity (gm_fluid.py:1291-1336)
 // ---------------------------------------------------------------------------------------------------------------
+// pre-pass of P1: aux0[a] = u_j = (X_j - xyz_j) / secs for the hidden particle j stored at sorted position a
+__global__ void advect_pack_u_kernel(GridView gh, int N, const float *__restrict__ xyz, float secs) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= N) return;
+    const float4 p = gh.sorted_pos[a];
+    const uint32_t j = __float_as_uint(p.w);
+    gh.aux0[a] = make_float4((p.x - xyz[3 * j]) / secs, (p.y - xyz[3 * j + 1]) / secs, (p.z - xyz[3 * j + 2]) / secs, 0.f);
+}
 // COUNTED = false: the cut-off kthV[v] is an input (fnx_radius_count ran before).  COUNTED = true: the kernel counts the
 // neighbours while it sums; only a query with more than K of them (rare) finds its cut-off by bisection and sums
 // again with it, and kthV[v] is an OUTPUT for the backward.
@@ -393,13 +414,14 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
     float3 num = make_float3(0.f, 0.f, 0.f);
     float den = 0.f;
     int cnt = 0;
-    auto gather = [&](int j, const float4 &pj, float d2) {
+    auto gather = [&](int j, const float4 &, float d2, uint32_t a) {
         cnt++;
         if (j > cut) return;
         const float w = poly6(d2, H2, term1);
-        num.x += w * ((pj.x - xyz[3 * j]) / secs);
-        num.y += w * ((pj.y - xyz[3 * j + 1]) / secs);
-        num.z += w * ((pj.z - xyz[3 * j + 2]) / secs);
+        const float4 u = gh.aux0[a];  // hidden velocity (X_j - xyz_j) / secs, packed by advect_pack_u_kernel
+        num.x += w * u.x;
+        num.y += w * u.y;
+        num.z += w * u.z;
         den += w;
     };
     warp_for_each_neighbor(gh, inv_cell, q, H2, lane, gather);
@@ -427,34 +449,46 @@ advect_fwd_kernel(GridView gh, float inv_cell, const float *__restrict__ X /*100
 // dL/dX_j = sum_{v: j in N(v), j <= kthV[v]} [ dw/dX_j * (secs/dc_v) * (G_v.u_j - [den_v > eps] G_v.num_v/den_v)
 //                                              + w * (secs/dc_v) * G_v / secs ]
 // gathered per hidden particle over the grid of the (un-advected) visual particles.
+// pre-pass: per visual particle v (stored at sorted position a of the visual grid)
+//   aux0[a] = { g_scale * (G_v [+ G2_v]),  c1 = [den_v > eps] (Gs_v . num_v) / den_v }
+//   aux1[a] = { secs / dc_v, 1 / dc_v, kthV_v, - },  dc_v = max(den_v, eps)
+__global__ void advect_bwd_pack_kernel(GridView gv, int V, const int *__restrict__ kthV, const float *__restrict__ num,
+                                       const float *__restrict__ den, const float *__restrict__ G, const float *__restrict__ G2,
+                                       float g_scale, float secs, float eps) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= V) return;
+    const uint32_t v = gv.sorted_idx[a];
+    float3 Gv = make_float3(G[3 * v], G[3 * v + 1], G[3 * v + 2]);
+    if (G2) { Gv.x += G2[3 * v]; Gv.y += G2[3 * v + 1]; Gv.z += G2[3 * v + 2]; }
+    Gv.x *= g_scale; Gv.y *= g_scale; Gv.z *= g_scale;
+    const float dn = den[v];
+    const float dc = fmaxf(dn, eps);
+    const float c1 = dn > eps ? (Gv.x * num[3 * v] + Gv.y * num[3 * v + 1] + Gv.z * num[3 * v + 2]) / dn : 0.f;
+    gv.aux0[a] = make_float4(Gv.x, Gv.y, Gv.z, c1);
+    gv.aux1[a] = make_float4(secs / dc, 1.0f / dc, __int_as_float(kthV[v]), 0.f);
+}
 __global__ void __launch_bounds__(128)
-advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, const float *__restrict__ xyz, int N,
-                  const int *__restrict__ kthV, const float *__restrict__ num, const float *__restrict__ den,
-                  const float *__restrict__ G /*dL/dvis_out [V,3]*/, const float *__restrict__ G2 /*optional second term*/,
-                  float g_scale, float H2, float term1, float secs, float eps, float *__restrict__ dL_dX, int accumulate) {
+advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, const float *__restrict__ xyz, int N, float H2,
+                  float term1, float secs, float *__restrict__ dL_dX, int accumulate) {
     const int j = blockIdx.x * QPB + (threadIdx.x / GROUP);
     const int lane = threadIdx.x % GROUP;
     if (j >= N) return;
     const float3 xj = make_float3(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
     const float3 u = make_float3((xj.x - xyz[3 * j]) / secs, (xj.y - xyz[3 * j + 1]) / secs, (xj.z - xyz[3 * j + 2]) / secs);
     float3 acc = make_float3(0.f, 0.f, 0.f);
-    warp_for_each_neighbor(gv, inv_cell, xj, H2, lane, [&](int v, const float4 &pv, float d2) {
-        if (j > kthV[v]) return;
-        float3 Gv = make_float3(G[3 * v], G[3 * v + 1], G[3 * v + 2]);
-        if (G2) { Gv.x += G2[3 * v]; Gv.y += G2[3 * v + 1]; Gv.z += G2[3 * v + 2]; }
-        Gv.x *= g_scale; Gv.y *= g_scale; Gv.z *= g_scale;
-        const float dn = den[v];
-        const float dc = fmaxf(dn, eps);
+    warp_for_each_neighbor(gv, inv_cell, xj, H2, lane, [&](int, const float4 &pv, float d2, uint32_t a) {
+        const float4 p1 = gv.aux1[a];
+        if (j > __float_as_int(p1.z)) return;
+        const float4 p0 = gv.aux0[a];
         const float w = poly6(d2, H2, term1);
         const float dw = dpoly6_dd2(d2, H2, term1);
-        float coef = Gv.x * u.x + Gv.y * u.y + Gv.z * u.z;
-        if (dn > eps) coef -= (Gv.x * num[3 * v] + Gv.y * num[3 * v + 1] + Gv.z * num[3 * v + 2]) / dn;
+        const float coef = p0.x * u.x + p0.y * u.y + p0.z * u.z - p0.w;
         // d(d2)/dX_j = 2 (X_j - vis_v)
-        const float s = dw * 2.f * coef * (secs / dc);
-        const float t = w / dc;  // w * (secs/dc) * (1/secs)
-        acc.x += s * (xj.x - pv.x) + t * Gv.x;
-        acc.y += s * (xj.y - pv.y) + t * Gv.y;
-        acc.z += s * (xj.z - pv.z) + t * Gv.z;
+        const float s = dw * 2.f * coef * p1.x;
+        const float t = w * p1.y;  // w * (secs/dc) * (1/secs)
+        acc.x += s * (xj.x - pv.x) + t * p0.x;
+        acc.y += s * (xj.y - pv.y) + t * p0.y;
+        acc.z += s * (xj.z - pv.z) + t * p0.z;
     });
     acc.x = group_sum(acc.x); acc.y = group_sum(acc.y); acc.z = group_sum(acc.z);
     if (lane < 3) {
@@ -744,6 +778,8 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    density_bwd_pack_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, imass, kth, p0, dL_dpratio);
+    FNX_LAUNCH_CHECK("density_bwd_pack_kernel");
     density_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("density_bwd_kernel");
     return FNX_OK;
@@ -757,6 +793,10 @@ int fnx_visual_advect_fwd(const void *grid_hidden, const float *X, const float *
     if (V == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_hidden, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    if (N > 0) {
+        advect_pack_u_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, xyz, secs);
+        FNX_LAUNCH_CHECK("advect_pack_u_kernel");
+    }
     advect_fwd_kernel<false><<<(V + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, (int *)kthV, 0, N, H * H, term1,
                                                                               secs, 1e-8f, out_div, visual_out, num_out, den_out);
     FNX_LAUNCH_CHECK("advect_fwd_kernel");
@@ -772,6 +812,10 @@ int fnx_visual_advect_fwd_counted(const void *grid_hidden, const float *X, const
     if (V == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_hidden, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    if (N > 0) {
+        advect_pack_u_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, xyz, secs);
+        FNX_LAUNCH_CHECK("advect_pack_u_kernel");
+    }
     advect_fwd_kernel<true><<<(V + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, visual, V, kthV_out, max_num_neighbors, N,
                                                                              H * H, term1, secs, 1e-8f, out_div, visual_out, num_out, den_out);
     FNX_LAUNCH_CHECK("advect_fwd_kernel");
@@ -786,8 +830,12 @@ int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid_visual, V);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    advect_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, kthV, num, den, dL_dvisual_out, dL_dvisual_out2, g_scale,
-                                                                       H * H, term1, secs, 1e-8f, dL_dX, accumulate);
+    if (V > 0) {
+        advect_bwd_pack_kernel<<<(V + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, V, kthV, num, den, dL_dvisual_out, dL_dvisual_out2, g_scale,
+                                                                             secs, 1e-8f);
+        FNX_LAUNCH_CHECK("advect_bwd_pack_kernel");
+    }
+    advect_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, H * H, term1, secs, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("advect_bwd_kernel");
     return FNX_OK;
 }
