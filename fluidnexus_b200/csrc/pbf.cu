@@ -498,6 +498,152 @@ advect_bwd_kernel(GridView gv, float inv_cell, const float *__restrict__ X, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// No-grad PBF solver tick: guess_hidden_particles gm_fluid.py:809-844,
+// project_gas_constraints :896-1021, confirm_guess_hidden_particles :1160-1175, update_visual_particles :1197-1239.
+// The reference builds an edge list with radius_graph(exyz, H, loop=True, K) and runs ~40 gather / index_add_ kernels
+// over it per solver iteration; here an iteration is a grid build, a neighbour count and two gather passes.
+// Edge convention: row = neighbour j, col = query c, edge exists iff |x_j - x_c|^2 < H^2 and
+// j <= kth[c]; every index_add_(0, row, .) therefore is "for node r: sum over c in N(r) with r <= kth[c]".
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float PBF_EPS = 1e-8f;  // self.EPSILON, gm_fluid.py:98
+
+// spiky_grad(diff, rlen) of gm_fluid.py:171-177 for diff = x_r - x_c, rlen = sqrt(d2 + EPS)
+__device__ __forceinline__ float3 spiky_grad(float3 diff, float d2, float H, float sterm) {
+    const float rlen = sqrtf(d2 + PBF_EPS);
+    if (!(rlen < H && rlen > 0.f)) return make_float3(0.f, 0.f, 0.f);
+    const float inv = 1.0f / (rlen + PBF_EPS);
+    const float t = (H - rlen) * (H - rlen) * sterm;
+    return make_float3(-(diff.x * inv) * t, -(diff.y * inv) * t, -(diff.z * inv) * t);
+}
+
+// pass 1: density, neighbour count, gradient sums -> lambda; pressure force correction
+__global__ void __launch_bounds__(128)
+solver_lambda_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
+                     const int *__restrict__ kth, float H, float term1, float sterm, float p0, float relaxation, float k_force,
+                     const float *__restrict__ velocity, float *__restrict__ force, float *__restrict__ lambda_out,
+                     float *__restrict__ nlen_out, float *__restrict__ pratio_out) {
+    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
+    if (r >= N) return;
+    const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
+    float pi = 0.f, grad_dot = 0.f;
+    float3 gr = make_float3(0.f, 0.f, 0.f);
+    int cnt = 0;
+    warp_for_each_neighbor(g, inv_cell, q, H * H, lane, [&](int c, const float4 &pc, float d2, uint32_t) {
+        if (r > kth[c]) return;
+        cnt++;
+        pi += poly6(d2, H * H, term1);
+        if (c == r) return;  // self loop: density and count only
+        const float3 sg = spiky_grad(make_float3(q.x - pc.x, q.y - pc.y, q.z - pc.z), d2, H, sterm);
+        gr.x += sg.x; gr.y += sg.y; gr.z += sg.z;
+        const float ax = sg.x / p0, ay = sg.y / p0, az = sg.z / p0;
+        grad_dot += ax * ax + ay * ay + az * az;
+    });
+    pi = group_sum(pi); grad_dot = group_sum(grad_dot); cnt = group_sum(cnt);
+    gr.x = group_sum(gr.x); gr.y = group_sum(gr.y); gr.z = group_sum(gr.z);
+    if (lane != 0) return;
+    gr.x /= p0; gr.y /= p0; gr.z /= p0;
+    const float gr_dot = gr.x * gr.x + gr.y * gr.y + gr.z * gr.z;
+    const float p_ratio = pi / imass[r] / p0;
+    if (force != nullptr) {
+        const float f = (1.0f - p_ratio) * -k_force;
+        force[3 * r] += velocity[3 * r] * f; force[3 * r + 1] += velocity[3 * r + 1] * f; force[3 * r + 2] += velocity[3 * r + 2] * f;
+    }
+    lambda_out[r] = -(p_ratio - 1.0f) / ((grad_dot + gr_dot) + relaxation);
+    nlen_out[r] = (float)cnt;
+    if (pratio_out) pratio_out[r] = p_ratio;
+}
+
+// pass 2: position correction  exyz += sum_c (lambda_r + lambda_c + s_corr) spiky / p0 / (neighbours + counts)
+__global__ void __launch_bounds__(128)
+solver_delta_kernel(GridView g, float inv_cell, float *__restrict__ X, int N, const int *__restrict__ kth,
+                    const float *__restrict__ lambda, const float *__restrict__ nlen, const float *__restrict__ counts, float H,
+                    float term1, float sterm, float p0, float K_P, int E_P, float corr_denom) {
+    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
+    if (r >= N) return;
+    const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
+    const float lam_r = lambda[r];
+    float3 d = make_float3(0.f, 0.f, 0.f);
+    warp_for_each_neighbor(g, inv_cell, q, H * H, lane, [&](int c, const float4 &pc, float d2, uint32_t) {
+        if (c == r || r > kth[c]) return;
+        const float3 sg = spiky_grad(make_float3(q.x - pc.x, q.y - pc.y, q.z - pc.z), d2, H, sterm);
+        float base = poly6(d2, H * H, term1) / corr_denom, pw = 1.0f;
+        for (int e = 0; e < E_P; e++) pw *= base;   // (poly6 / denom) ** E_P, integer exponent (gm_fluid.py:102)
+        const float w = (lam_r + lambda[c]) + -K_P * pw;
+        d.x += w * sg.x; d.y += w * sg.y; d.z += w * sg.z;
+    });
+    d.x = group_sum(d.x); d.y = group_sum(d.y); d.z = group_sum(d.z);
+    if (lane >= 3) return;
+    const float den = nlen[r] + counts[r];
+    const float v = (lane == 0 ? d.x : (lane == 1 ? d.y : d.z)) / p0 / den;
+    // neighbours read the grid's snapshot of the positions (sorted_pos), so the in-place update is race free
+    X[3 * r + lane] = (lane == 0 ? q.x : (lane == 1 ? q.y : q.z)) + v;
+}
+
+// bincount(row) of radius_graph(X, r, loop, K): for node r the number of queries c that list r among their neighbours
+__global__ void __launch_bounds__(128)
+graph_degree_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const int *__restrict__ kth, float r2, int loop,
+                    int *__restrict__ degree) {
+    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
+    if (r >= N) return;
+    const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
+    int cnt = 0;
+    warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int c, const float4 &, float, uint32_t) {
+        if (r > kth[c] || (!loop && c == r)) return;
+        cnt++;
+    });
+    cnt = group_sum(cnt);
+    if (lane == 0) degree[r] = cnt;
+}
+
+// guess_hidden_particles (gm_fluid.py:809-844)
+__global__ void solver_guess_kernel(int N, const float *__restrict__ xyz, float *__restrict__ velocity, float *__restrict__ buoyancy,
+                                    float *__restrict__ force, float *__restrict__ estimate_xyz, float *__restrict__ counts,
+                                    float3 gravity_alpha, float secs, float buoyancy_max_y, float scale_factor, float decay,
+                                    int use_wind, float3 wind_force, float wind_power, float wind_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float y = xyz[3 * i + 1];
+    const float coeff = buoyancy_max_y > 0.f ? 1.0f - (y / (buoyancy_max_y * scale_factor)) : 1.0f;
+    const float b[3] = {gravity_alpha.x, gravity_alpha.y, gravity_alpha.z};   // ones_like(buoyancy) * gravity * alpha
+    const float wf[3] = {wind_force.x, wind_force.y, wind_force.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float v = velocity[3 * i + k] + (b[k] * coeff) * secs + secs * force[3 * i + k];
+        if (use_wind) {
+            const float w = fminf(fmaxf(powf(y / scale_factor, wind_power) * wf[k], 0.0f), wind_max);
+            v += w * secs;
+        }
+        velocity[3 * i + k] = v;
+        buoyancy[3 * i + k] = decay > 0.f ? b[k] * decay : b[k];
+        force[3 * i + k] = 0.f;
+        estimate_xyz[3 * i + k] = xyz[3 * i + k] + secs * v;
+    }
+    counts[i] = 0.f;
+}
+
+// confirm_guess_hidden_particles (gm_fluid.py:1160-1175)
+__global__ void solver_confirm_kernel(int N, float *__restrict__ xyz, const float *__restrict__ estimate_xyz,
+                                      float *__restrict__ velocity, float secs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float dx = estimate_xyz[3 * i] - xyz[3 * i], dy = estimate_xyz[3 * i + 1] - xyz[3 * i + 1], dz = estimate_xyz[3 * i + 2] - xyz[3 * i + 2];
+    const bool still = sqrtf(dx * dx + dy * dy + dz * dz) < PBF_EPS;
+    velocity[3 * i] = still ? 0.f : dx / secs; velocity[3 * i + 1] = still ? 0.f : dy / secs; velocity[3 * i + 2] = still ? 0.f : dz / secs;
+    if (!still) { xyz[3 * i] = estimate_xyz[3 * i]; xyz[3 * i + 1] = estimate_xyz[3 * i + 1]; xyz[3 * i + 2] = estimate_xyz[3 * i + 2]; }
+}
+
+// payload of update_visual_particles: the hidden particles' velocities in grid order
+__global__ void advect_pack_vel_kernel(GridView gh, int N, const float *__restrict__ velocity) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= N) return;
+    const uint32_t j = gh.sorted_idx[a];
+    gh.aux0[a] = make_float4(velocity[3 * j], velocity[3 * j + 1], velocity[3 * j + 2], 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // P5: pair distance loss  L = sum_{i != j, d_ij < thr} (thr - d_ij)^2  and dL/dp  (loss_utils.py:98-121)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -837,6 +983,97 @@ int fnx_visual_advect_bwd(const void *grid_visual, const float *X, const float *
     }
     advect_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, xyz, N, H * H, term1, secs, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("advect_bwd_kernel");
+    return FNX_OK;
+}
+
+int fnx_pbf_guess_hidden(int32_t N, const float *xyz, float *velocity, float *buoyancy, float *force, float *estimate_xyz, float *counts,
+                         const float *gravity3_host, float alpha, float secs, float buoyancy_max_y, float scale_factor,
+                         float buoyancy_decay_rate, int32_t use_wind, const float *wind_force3_host, float wind_power,
+                         float wind_force_max, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(N >= 0 && xyz && velocity && buoyancy && force && estimate_xyz && counts && gravity3_host, "bad arguments");
+    FNX_REQUIRE(!use_wind || wind_force3_host, "use_wind needs wind_force");
+    if (N == 0) return FNX_OK;
+    const float3 ga = make_float3(gravity3_host[0] * alpha, gravity3_host[1] * alpha, gravity3_host[2] * alpha);
+    const float3 wf = use_wind ? make_float3(wind_force3_host[0], wind_force3_host[1], wind_force3_host[2]) : make_float3(0.f, 0.f, 0.f);
+    solver_guess_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, xyz, velocity, buoyancy, force, estimate_xyz, counts, ga, secs,
+                                                                         buoyancy_max_y, scale_factor, buoyancy_decay_rate, use_wind, wf,
+                                                                         wind_power, wind_force_max);
+    FNX_LAUNCH_CHECK("solver_guess_kernel");
+    return FNX_OK;
+}
+
+int fnx_pbf_project_gas_constraints(void *grid, float *estimate_xyz, int32_t N, const float *imass, const float *velocity, float *force,
+                                    const float *counts, float H, float p0, float k, int32_t max_num_neighbors, float relaxation,
+                                    float K_P, int32_t E_P, float DQ_P, int32_t *kth_scratch, float *lambda_scratch,
+                                    float *nlen_scratch, float *p_ratio_out, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid && estimate_xyz && imass && counts && kth_scratch && lambda_scratch && nlen_scratch && N >= 0 && H > 0.f && p0 > 0.f &&
+                    max_num_neighbors > 0 && E_P >= 0 && (force == nullptr || velocity != nullptr), "bad arguments");
+    if (N == 0) return FNX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = grid_build(estimate_xyz, N, H, grid, st);
+    if (rc) return rc;
+    GridView g = grid_view(grid, N);
+    radius_count_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, estimate_xyz, N, H * H, max_num_neighbors, N, nullptr, kth_scratch);
+    FNX_LAUNCH_CHECK("radius_count_kernel");
+    const double H6 = pow((double)H, 6), H9 = pow((double)H, 9), PI = 3.14159265358979323846;
+    const float term1 = (float)(315.0 / (64.0 * PI * H9)), sterm = (float)(45.0 / (PI * H6));
+    // lamb_corr_denom = poly6(DQ_P^2 H^2), gm_fluid.py:126
+    const double t = (double)H * H - (double)DQ_P * DQ_P * H * H;
+    const float corr_denom = (float)((315.0 / (64.0 * PI * H9)) * t * t * t);
+    solver_lambda_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, estimate_xyz, N, imass, kth_scratch, H, term1, sterm, p0, relaxation, k,
+                                                              velocity, force, lambda_scratch, nlen_scratch, p_ratio_out);
+    FNX_LAUNCH_CHECK("solver_lambda_kernel");
+    solver_delta_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, estimate_xyz, N, kth_scratch, lambda_scratch, nlen_scratch, counts, H,
+                                                             term1, sterm, p0, K_P, E_P, corr_denom);
+    FNX_LAUNCH_CHECK("solver_delta_kernel");
+    return FNX_OK;
+}
+
+int fnx_radius_graph_degree(void *grid, const float *X, int32_t N, float r, int32_t loop, int32_t max_num_neighbors, int32_t *kth_scratch,
+                            int32_t *degree, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid && X && kth_scratch && degree && N >= 0 && r > 0.f && max_num_neighbors > 0, "bad arguments");
+    if (N == 0) return FNX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = grid_build(X, N, r, grid, st);
+    if (rc) return rc;
+    GridView g = grid_view(grid, N);
+    // radius_graph(x, r, loop, K) = radius(x, x, r, K if loop else K + 1) minus the self pairs (torch_cluster 1.6.3)
+    radius_count_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / r, X, N, r * r, loop ? max_num_neighbors : max_num_neighbors + 1, N, nullptr,
+                                                             kth_scratch);
+    FNX_LAUNCH_CHECK("radius_count_kernel");
+    graph_degree_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / r, X, N, kth_scratch, r * r, loop, degree);
+    FNX_LAUNCH_CHECK("graph_degree_kernel");
+    return FNX_OK;
+}
+
+int fnx_pbf_confirm_guess(int32_t N, float *xyz, const float *estimate_xyz, float *velocity, float secs, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(N >= 0 && xyz && estimate_xyz && velocity && secs != 0.f, "bad arguments");
+    if (N == 0) return FNX_OK;
+    solver_confirm_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, xyz, estimate_xyz, velocity, secs);
+    FNX_LAUNCH_CHECK("solver_confirm_kernel");
+    return FNX_OK;
+}
+
+int fnx_pbf_update_visual(void *grid, const float *estimate_xyz, const float *velocity, int32_t N, float *visual, int32_t V,
+                          int32_t max_num_neighbors, float H, float secs, int32_t *kthV_scratch, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid && estimate_xyz && velocity && (visual || V == 0) && kthV_scratch && N >= 0 && V >= 0 && max_num_neighbors > 0, "bad arguments");
+    if (V == 0 || N == 0) return FNX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = grid_build(estimate_xyz, N, H, grid, st);
+    if (rc) return rc;
+    GridView g = grid_view(grid, N);
+    advect_pack_vel_kernel<<<(N + 255) / 256, 256, 0, st>>>(g, N, velocity);
+    FNX_LAUNCH_CHECK("advect_pack_vel_kernel");
+    const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    // visual += secs * sum_j w v_j / max(sum_j w, EPS): the P1 gather with the stored velocities as payload
+    advect_fwd_kernel<true><<<(V + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, estimate_xyz, nullptr, visual, V, kthV_scratch, max_num_neighbors, N,
+                                                             H * H, term1, secs, PBF_EPS, 1.0f, visual, nullptr, nullptr);
+    FNX_LAUNCH_CHECK("advect_fwd_kernel");
     return FNX_OK;
 }
 

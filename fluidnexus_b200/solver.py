@@ -1,0 +1,148 @@
+"""No-grad PBF solver tick on libfnx.
+
+Host-side mirror of the simulation half of FD/gaussian_splatting/gm_fluid.py's GaussianModel -- the part that runs
+between the optimised frames (FD/entries_fluid_nexus/train_physical_particle.py:206-216,288) and in all of
+future_simulation.py:135-162:
+
+    guess_hidden_particles(stable, use_wind)        gm_fluid.py:809-844
+    update_solver_counts()                          gm_fluid.py:893-894
+    project_gas_constraints()                       gm_fluid.py:896-1021   (solver_iterations times per tick)
+    confirm_guess_hidden_particles()                gm_fluid.py:1160-1175
+    update_visual_particles()                       gm_fluid.py:1197-1239
+    remove_invalid_particles()                      gm_fluid.py:864-891
+
+Same method names, same in-place state updates (attributes `_xyz, _estimate_xyz, _velocity, _force, _buoyancy, _imass,
+_counts, _visual_xyz`), no CPU fallback.  One solver iteration is 9 kernel launches (grid build, neighbour count, two
+gather passes) instead of the reference's ~40 torch kernels over a materialised edge list plus 20 `.item()` syncs for its
+log dictionary; `project_gas_constraints(stats=True)` returns that dictionary's per-node entries on request only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class PBFSolver:
+    """State + the reference's solver methods.  Constants default to gm_fluid.py:98-106 / FD/arguments/__init__.py."""
+
+    def __init__(self, xyz, velocity=None, imass=None, visual_xyz=None, H=2.0, p0=1.5, k=10.0, KNN_K=100, secs=0.033, alpha=-0.2,
+                 buoyancy_max_y=0.0, buoyancy_decay_rate=0.0, scale_factor=100.0, gravity=(0.0, -9.8, 0.0), wind_force=(0.0, 0.0, 0.0),
+                 wind_power=1.0, min_neighbors=-1, device="cuda"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("PBFSolver runs on CUDA tensors only (no CPU fallback)")
+        f = lambda t: torch.as_tensor(t, dtype=torch.float32).to(dev).contiguous().clone()
+        self.dev = dev
+        self._xyz = f(xyz)
+        N = self._xyz.size(0)
+        self._velocity = f(velocity) if velocity is not None else torch.zeros((N, 3), device=dev)
+        self._imass = f(imass).reshape(N, 1) if imass is not None else torch.ones((N, 1), device=dev)
+        self._estimate_xyz = self._xyz.clone()
+        self._force = torch.zeros((N, 3), device=dev)
+        self._buoyancy = torch.zeros((N, 3), device=dev)
+        self._counts = torch.zeros((N, 1), device=dev)
+        self._visual_xyz = f(visual_xyz) if visual_xyz is not None else torch.zeros((0, 3), device=dev)
+        self.H, self.p0, self.k, self.KNN_K, self._secs, self.alpha = float(H), float(p0), float(k), int(KNN_K), float(secs), float(alpha)
+        self.buoyancy_max_y, self.buoyancy_decay_rate, self.scale_factor = float(buoyancy_max_y), float(buoyancy_decay_rate), float(scale_factor)
+        self.RELAXATION, self.K_P, self.E_P, self.DQ_P = 0.01, 0.2, 4, 0.25
+        self.min_neighbors = int(min_neighbors)
+        self._gravity = (C.c_float * 3)(*gravity)
+        self._wind = (C.c_float * 3)(*wind_force)
+        self.wind_force_max, self.wind_power = float(max(wind_force)), float(wind_power)
+        self._scratch_n = -1
+
+    # -- scratch (re-made when the particle count changes) -----------------------------------------------------
+    def _scratch(self):
+        N, V = self._xyz.size(0), self._visual_xyz.size(0)
+        if self._scratch_n != (N, V):
+            lib = L.lib()
+            self._grid = torch.empty(lib.fnx_grid_bytes(max(N, 1)), dtype=torch.uint8, device=self.dev)
+            self._kth = torch.empty(max(N, 1), dtype=torch.int32, device=self.dev)
+            self._kthV = torch.empty(max(V, 1), dtype=torch.int32, device=self.dev)
+            self._lambda = torch.empty(max(N, 1), device=self.dev)
+            self._nlen = torch.empty(max(N, 1), device=self.dev)
+            self._pratio = torch.empty(max(N, 1), device=self.dev)
+            self._scratch_n = (N, V)
+
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    # -- the reference's methods --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def guess_hidden_particles(self, stable=False, use_wind=False):
+        cur_secs, cur_alpha = (0.01, -1.0) if stable else (self._secs, self.alpha)
+        N = self._xyz.size(0)
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().fnx_pbf_guess_hidden(N, self._xyz.data_ptr(), self._velocity.data_ptr(), self._buoyancy.data_ptr(),
+                                                 self._force.data_ptr(), self._estimate_xyz.data_ptr(), self._counts.data_ptr(), self._gravity,
+                                                 cur_alpha, cur_secs, self.buoyancy_max_y, self.scale_factor, self.buoyancy_decay_rate,
+                                                 int(bool(use_wind)), self._wind, self.wind_power, self.wind_force_max, self._st()))
+
+    def update_solver_counts(self):
+        self._counts += 1.0
+
+    @torch.no_grad()
+    def project_gas_constraints(self, stats=False):
+        self._scratch()
+        N = self._estimate_xyz.size(0)
+        with torch.cuda.device(self.dev):
+            before = self._estimate_xyz.clone() if stats else None
+            L.check(L.lib().fnx_pbf_project_gas_constraints(
+                self._grid.data_ptr(), self._estimate_xyz.data_ptr(), N, self._imass.data_ptr(), self._velocity.data_ptr(),
+                self._force.data_ptr(), self._counts.data_ptr(), self.H, self.p0, self.k, self.KNN_K, self.RELAXATION, self.K_P, self.E_P,
+                self.DQ_P, self._kth.data_ptr(), self._lambda.data_ptr(), self._nlen.data_ptr(), self._pratio.data_ptr(), self._st()))
+        if not stats:
+            return None
+        # the per-node entries of the reference's log dictionary (gm_fluid.py:998-1019); one sync, on request only
+        m = lambda t: float(t[:N].mean())
+        return {"velocity": m(self._velocity), "xyz": m(self._xyz), "estimate_xyz": m(self._estimate_xyz), "p_ratio": m(self._pratio),
+                "pi": m(self._pratio) * self.p0, "lambdas": m(self._lambda), "estimate_xyz_delta": m(self._estimate_xyz - before),
+                "elapsed_time": 0.0}
+
+    @torch.no_grad()
+    def confirm_guess_hidden_particles(self):
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().fnx_pbf_confirm_guess(self._xyz.size(0), self._xyz.data_ptr(), self._estimate_xyz.data_ptr(),
+                                                  self._velocity.data_ptr(), self._secs, self._st()))
+
+    @torch.no_grad()
+    def update_visual_particles(self):
+        V, N = self._visual_xyz.size(0), self._estimate_xyz.size(0)
+        if V == 0:
+            return
+        self._scratch()
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().fnx_pbf_update_visual(self._grid.data_ptr(), self._estimate_xyz.data_ptr(), self._velocity.data_ptr(), N,
+                                                  self._visual_xyz.data_ptr(), V, self.KNN_K, self.H, self._secs, self._kthV.data_ptr(),
+                                                  self._st()))
+
+    @torch.no_grad()
+    def remove_invalid_particles(self):
+        """Drops particles with fewer than `min_neighbors` neighbours in radius_graph(xyz, H, loop=False) (torch_cluster's
+        default cap of 32 neighbours applies, as in the reference call)."""
+        if self.min_neighbors < 0:
+            return
+        self._scratch()
+        N = self._xyz.size(0)
+        degree = torch.empty(max(N, 1), dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().fnx_radius_graph_degree(self._grid.data_ptr(), self._xyz.data_ptr(), N, self.H, 0, 32, self._kth.data_ptr(),
+                                                    degree.data_ptr(), self._st()))
+        mask = degree[:N] >= self.min_neighbors
+        if not bool(mask.all()):
+            for name in ("_xyz", "_estimate_xyz", "_buoyancy", "_force", "_velocity", "_imass", "_counts"):
+                setattr(self, name, getattr(self, name)[mask].contiguous())
+
+    # -- one simulation tick as the entries run it ---------------------------------------------------------------
+    @torch.no_grad()
+    def tick(self, solver_iterations=3, stable=False, use_wind=False, count_first=False):
+        """future_simulation.py:135-162 (count_first=False) / train_physical_particle.py:206-216 (count_first=True)."""
+        self.guess_hidden_particles(stable=stable, use_wind=use_wind)
+        if count_first:
+            for _ in range(solver_iterations):
+                self.update_solver_counts()
+        for _ in range(solver_iterations):
+            self.project_gas_constraints()
+        self.confirm_guess_hidden_particles()
+        self.update_visual_particles()

@@ -274,6 +274,37 @@ int fnx_pbf_combine_grad(int32_t N, const float *e, const float *buoyancy, float
 /* *loss = mean((p_ratio-1)^2) (l2_loss vs ones, train_physical_particle.py:336-342); dL_dpratio = weight * d loss. */
 int fnx_pbf_ratio_loss(int32_t N, const float *p_ratio, float weight, float *loss, float *dL_dpratio, fnx_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * No-grad PBF solver tick  (replaces the torch chains of gm_fluid.py:809-844
+ * guess_hidden_particles, :896-1021 project_gas_constraints, :1160-1175 confirm_guess_hidden_particles and
+ * :1197-1239 update_visual_particles).  All state arrays are [N,3] / [N] device fp32 and updated in place.
+ * ---------------------------------------------------------------------------------------------- */
+/* velocity += (gravity*alpha) * coeff * secs + secs*force (+ clamp(pow(y/scale, wind_power)*wind_force, 0, wind_force_max)*secs),
+ * coeff = 1 - y/(buoyancy_max_y*scale_factor) if buoyancy_max_y > 0 else 1; buoyancy = gravity*alpha (* decay if decay > 0);
+ * force = 0; estimate_xyz = xyz + secs*velocity; counts = 0.  gravity3 / wind_force3 are HOST pointers to 3 floats. */
+int fnx_pbf_guess_hidden(int32_t N, const float *xyz, float *velocity, float *buoyancy, float *force, float *estimate_xyz,
+                         float *counts, const float *gravity3_host, float alpha, float secs, float buoyancy_max_y,
+                         float scale_factor, float buoyancy_decay_rate, int32_t use_wind, const float *wind_force3_host,
+                         float wind_power, float wind_force_max, fnx_stream_t stream);
+/* One solver iteration on estimate_xyz (in place): grid + radius_graph(exyz, H, loop=True, K) semantics, density
+ * p_ratio, lambda = -(p_ratio-1)/(sum|grad|^2 + |sum grad|^2 + relaxation), force += velocity*(1-p_ratio)*(-k)
+ * (skipped when force == NULL), exyz += sum (lambda_i+lambda_j+s_corr) spiky / p0 / (neighbours + counts),
+ * s_corr = -K_P (poly6/poly6(DQ_P^2 H^2))^E_P.  grid: fnx_grid_bytes(N) scratch; kth/lambda/nlen: [N] scratch;
+ * p_ratio_out [N] optional. */
+int fnx_pbf_project_gas_constraints(void *grid, float *estimate_xyz, int32_t N, const float *imass, const float *velocity,
+                                    float *force, const float *counts, float H, float p0, float k, int32_t max_num_neighbors,
+                                    float relaxation, float K_P, int32_t E_P, float DQ_P, int32_t *kth_scratch,
+                                    float *lambda_scratch, float *nlen_scratch, float *p_ratio_out, fnx_stream_t stream);
+/* degree[i] = bincount(row)[i] of radius_graph(X, r, loop, max_num_neighbors) (row = neighbour index): what
+ * remove_invalid_particles (gm_fluid.py:864-891) thresholds with min_neighbors.  grid: fnx_grid_bytes(N) scratch. */
+int fnx_radius_graph_degree(void *grid, const float *X, int32_t N, float r, int32_t loop, int32_t max_num_neighbors,
+                            int32_t *kth_scratch, int32_t *degree, fnx_stream_t stream);
+/* velocity = (estimate_xyz - xyz)/secs, zeroed (and xyz kept) where |estimate_xyz - xyz| < 1e-8, else xyz = estimate_xyz. */
+int fnx_pbf_confirm_guess(int32_t N, float *xyz, const float *estimate_xyz, float *velocity, float secs, fnx_stream_t stream);
+/* visual += secs * sum_j poly6 v_j / max(sum_j poly6, 1e-8) over radius(x=estimate_xyz, y=visual, H, K) (in place). */
+int fnx_pbf_update_visual(void *grid, const float *estimate_xyz, const float *velocity, int32_t N, float *visual, int32_t V,
+                          int32_t max_num_neighbors, float H, float secs, int32_t *kthV_scratch, fnx_stream_t stream);
+
 /* torch.optim.Adam step on a flat fp32 tensor (gm_fluid.py:349: eps 1e-15); grad is multiplied by grad_scale first
  * (= 1/batch of set_batch_gradient_*, gm_fluid.py:428-430).  step >= 1 is the step count AFTER this update. */
 int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale,

@@ -251,3 +251,131 @@ def knn3_mean_dist2(points):
     p = np.asarray(points, np.float64)
     d, _ = cKDTree(p).query(p, k=4)
     return (d[:, 1:4] ** 2).mean(1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# No-grad PBF solver tick.  Literal restatements of the reference methods on a plain state
+# dict {xyz, estimate_xyz, velocity, force, buoyancy, imass [N,1], counts [N,1], visual_xyz}; every function mutates
+# the dict the way the reference mutates `self`.  TEST INFRASTRUCTURE ONLY.  Parity unpinned at radius_graph (see the
+# module header); everything else follows the reference line by line.
+# ---------------------------------------------------------------------------------------------------------------------
+class SolverParams:
+    """gm_fluid.py:77-126 + FD/arguments/__init__.py:300-330."""
+
+    def __init__(self, H=2.0, p0=1.5, k=10.0, KNN_K=100, secs=0.033, alpha=-0.2, buoyancy_max_y=0.0, buoyancy_decay_rate=0.0,
+                 scale_factor=100.0, gravity=(0.0, -9.8, 0.0), wind_force=(0.0, 0.0, 0.0), wind_power=1.0, min_neighbors=-1):
+        self.H, self.p0, self.k, self.KNN_K, self.secs, self.alpha = H, p0, k, KNN_K, secs, alpha
+        self.buoyancy_max_y, self.buoyancy_decay_rate, self.scale_factor = buoyancy_max_y, buoyancy_decay_rate, scale_factor
+        self.gravity, self.wind_force, self.wind_power = gravity, wind_force, wind_power
+        self.wind_force_max = max(wind_force)
+        self.min_neighbors = min_neighbors
+        self.EPSILON, self.RELAXATION, self.K_P, self.E_P, self.DQ_P = 1e-8, 0.01, 0.2, 4, 0.25
+        self.H2, self.H6, self.H9 = H ** 2, H ** 6, H ** 9
+        self.poly6_term1 = 315.0 / (64.0 * np.pi * self.H9)
+        self.spiky_grad_term1 = 45.0 / (np.pi * self.H6)
+        t = self.H2 - self.DQ_P * self.DQ_P * H * H
+        self.lamb_corr_denom = self.poly6_term1 * t ** 3   # poly6(DQ_P^2 H^2), gm_fluid.py:126
+
+
+def spiky_grad(sp, r, rlen):
+    """gm_fluid.py:171-177."""
+    mask = (rlen < sp.H) & (rlen > 0)
+    r_norm = r / (rlen.unsqueeze(-1) + sp.EPSILON)
+    term2 = (sp.H - rlen).unsqueeze(-1) ** 2
+    grad = -r_norm * sp.spiky_grad_term1 * term2
+    grad[~mask] = 0.0
+    return grad
+
+
+def solver_guess_hidden_particles(sp, st, stable=False, use_wind=False):
+    """gm_fluid.py:809-844."""
+    cur_secs, cur_alpha = (0.01, -1.0) if stable else (sp.secs, sp.alpha)
+    dt = st["xyz"].dtype
+    g = torch.tensor(sp.gravity, dtype=dt).reshape(1, 3)
+    st["buoyancy"] = torch.ones_like(st["buoyancy"]) * g * cur_alpha
+    if sp.buoyancy_max_y > 0.0:
+        coeff = 1.0 - (st["xyz"][:, 1:2] / (sp.buoyancy_max_y * sp.scale_factor))
+        cur_buoyancy = st["buoyancy"] * coeff
+    else:
+        cur_buoyancy = st["buoyancy"]
+    st["velocity"] = st["velocity"] + cur_buoyancy * cur_secs + cur_secs * st["force"]
+    if use_wind:
+        y_scale = st["xyz"][:, 1:2] / sp.scale_factor
+        wf = (y_scale ** sp.wind_power) * torch.tensor(sp.wind_force, dtype=dt).reshape(1, 3)
+        st["velocity"] = st["velocity"] + torch.clamp(wf, 0.0, sp.wind_force_max) * cur_secs
+    if sp.buoyancy_decay_rate > 0.0:
+        st["buoyancy"] = st["buoyancy"] * sp.buoyancy_decay_rate
+    st["force"] = torch.zeros_like(st["force"])
+    st["estimate_xyz"] = st["xyz"] + cur_secs * st["velocity"]
+    st["counts"] = torch.zeros_like(st["counts"])
+
+
+def solver_project_gas_constraints(sp, st):
+    """gm_fluid.py:896-996 (the log dictionary of :998-1019 is not restated).  Returns (p_ratio, lambdas)."""
+    exyz = st["estimate_xyz"]
+    N = exyz.shape[0]
+    row, col = radius_graph(exyz, sp.H, loop=True, max_num_neighbors=sp.KNN_K)
+    non_self = row != col
+    diff = exyz[row] - exyz[col]
+    dist2 = torch.sum(diff ** 2, dim=1)
+    mask = (dist2 < sp.H2).to(dist2.dtype)   # (keeps the fp64 evaluation fp64: bool * python float would round to fp32)
+    poly6_values = mask * sp.poly6_term1 * ((sp.H2 - dist2) ** 3)
+    pi = torch.zeros(N, dtype=exyz.dtype).index_add_(0, row, poly6_values).unsqueeze(1) / st["imass"]
+    neighbors_len = torch.bincount(row, minlength=N).unsqueeze(1).to(exyz.dtype)
+    row_ns, col_ns, diff_ns, dist2_ns = row[non_self], col[non_self], diff[non_self], dist2[non_self]
+    rlen_ns = torch.sqrt(dist2_ns + sp.EPSILON)
+    sg = spiky_grad(sp, diff_ns, rlen_ns)
+    gr = torch.zeros(N, 3, dtype=exyz.dtype).index_add_(0, row_ns, sg) / sp.p0
+    gr_dot = torch.sum(gr ** 2, dim=1)
+    grad_dot = torch.zeros(N, dtype=exyz.dtype).index_add_(0, row_ns, torch.sum((sg / sp.p0) ** 2, dim=1))
+    denom = (grad_dot + gr_dot).unsqueeze(1)
+    p_ratio = pi / sp.p0
+    st["force"] = st["force"] + st["velocity"] * (1.0 - p_ratio) * -sp.k
+    lambdas = -(p_ratio - 1.0) / (denom + sp.RELAXATION)
+    lamb_corr = -sp.K_P * (poly6_values[non_self] / sp.lamb_corr_denom) ** sp.E_P
+    lam_sum = lambdas[row_ns].squeeze(1) + lambdas[col_ns].squeeze(1)
+    deltas = (lam_sum + lamb_corr).unsqueeze(-1) * sg
+    deltas_sum = torch.zeros(N, 3, dtype=exyz.dtype).index_add_(0, row_ns, deltas) / sp.p0
+    st["estimate_xyz"] = exyz + deltas_sum / (neighbors_len + st["counts"])
+    return p_ratio, lambdas
+
+
+def solver_confirm_guess_hidden_particles(sp, st):
+    """gm_fluid.py:1160-1175."""
+    st["velocity"] = (st["estimate_xyz"] - st["xyz"]) / sp.secs
+    mask = torch.norm(st["estimate_xyz"] - st["xyz"], dim=1) < sp.EPSILON
+    st["velocity"][mask] = 0.0
+    st["xyz"] = st["xyz"].clone()
+    st["xyz"][~mask] = st["estimate_xyz"][~mask]
+
+
+def solver_update_visual_particles(sp, st):
+    """gm_fluid.py:1197-1239."""
+    vis = st["visual_xyz"]
+    if vis.shape[0] == 0:
+        return
+    e = radius(st["estimate_xyz"], vis, sp.H, max_num_neighbors=sp.KNN_K)
+    row, col = e[0], e[1]
+    diff = vis[row] - st["estimate_xyz"][col]
+    dist2 = torch.sum(diff ** 2, dim=1)
+    p6 = (dist2 < sp.H2).to(dist2.dtype) * sp.poly6_term1 * ((sp.H2 - dist2) ** 3)
+    vv = torch.zeros(vis.shape[0], 3, dtype=vis.dtype).index_add_(0, row, st["velocity"][col] * p6.unsqueeze(-1))
+    s = torch.zeros(vis.shape[0], dtype=vis.dtype).index_add_(0, row, p6).clamp_min(sp.EPSILON)
+    st["visual_xyz"] = vis + vv * sp.secs / s.unsqueeze(-1)
+
+
+def solver_neighbor_degree(sp, xyz):
+    """bincount(row) of radius_graph(xyz, H, loop=False) with torch_cluster's default cap of 32 (gm_fluid.py:873-878)."""
+    row, _ = radius_graph(xyz, sp.H, loop=False, max_num_neighbors=32)
+    return torch.bincount(row, minlength=xyz.shape[0])
+
+
+def solver_tick(sp, st, solver_iterations=3, stable=False, use_wind=False, count_first=False):
+    """future_simulation.py:135-162 / train_physical_particle.py:206-216."""
+    solver_guess_hidden_particles(sp, st, stable=stable, use_wind=use_wind)
+    if count_first:
+        st["counts"] = st["counts"] + float(solver_iterations)
+    for _ in range(solver_iterations):
+        solver_project_gas_constraints(sp, st)
+    solver_confirm_guess_hidden_particles(sp, st)
+    solver_update_visual_particles(sp, st)

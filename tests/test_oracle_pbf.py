@@ -105,3 +105,34 @@ def test_kdtree_radius_path_equals_literal_scan():
             rows += [c] * len(hit)
             cols += hit.tolist()
         assert got.tolist() == [rows, cols]
+
+
+def test_solver_two_particle_closed_form():
+    """project_gas_constraints on two particles d apart (gm_fluid.py:896-996): pi = poly6(0) + poly6(d^2), one spiky
+    gradient each (equal and opposite), lambda and the position correction in closed form; confirm / still-particle
+    rule of gm_fluid.py:1160-1175."""
+    import math
+    sp = O.SolverParams(p0=1.5, k=10.0)
+    d = 0.7
+    st = dict(xyz=torch.tensor([[0.0, 0.0, 0.0], [d, 0.0, 0.0]], dtype=torch.float64), velocity=torch.ones(2, 3, dtype=torch.float64),
+              force=torch.zeros(2, 3, dtype=torch.float64), buoyancy=torch.zeros(2, 3, dtype=torch.float64),
+              imass=torch.ones(2, 1, dtype=torch.float64), counts=torch.ones(2, 1, dtype=torch.float64),
+              visual_xyz=torch.zeros(0, 3, dtype=torch.float64))
+    st["estimate_xyz"] = st["xyz"].clone()
+    p_ratio, lam = O.solver_project_gas_constraints(sp, st)
+    p6 = lambda r2: sp.poly6_term1 * (sp.H2 - r2) ** 3
+    pr = (p6(0.0) + p6(d * d)) / sp.p0
+    assert abs(float(p_ratio[0]) - pr) < 1e-12 and abs(float(p_ratio[1]) - pr) < 1e-12
+    rlen = math.sqrt(d * d + sp.EPSILON)
+    g = sp.spiky_grad_term1 * (sp.H - rlen) ** 2 * (d / (rlen + sp.EPSILON))       # |spiky|, pointing away from the neighbour...
+    lam_ref = -(pr - 1.0) / (2.0 * (g / sp.p0) ** 2 + sp.RELAXATION)               # grad_dot + gr_dot, one neighbour
+    assert abs(float(lam[0]) - lam_ref) < 1e-9 * abs(lam_ref)
+    corr = -sp.K_P * (p6(d * d) / sp.lamb_corr_denom) ** sp.E_P
+    # particle 0: diff = x0 - x1 = -d  =>  spiky = +g along x;  neighbours_len = 2 (self loop + 1), counts = 1
+    dx0 = (2.0 * lam_ref + corr) * g / sp.p0 / 3.0
+    assert abs(float(st["estimate_xyz"][0, 0]) - dx0) < 1e-9 * abs(dx0)
+    assert abs(float(st["estimate_xyz"][1, 0]) - (d - dx0)) < 1e-9
+    assert torch.allclose(st["force"], torch.ones(2, 3, dtype=torch.float64) * (1.0 - pr) * -sp.k)
+    st["estimate_xyz"][1] = st["xyz"][1]          # particle 1 did not move
+    O.solver_confirm_guess_hidden_particles(sp, st)
+    assert torch.all(st["velocity"][1] == 0) and abs(float(st["velocity"][0, 0]) - dx0 / sp.secs) < 1e-9

@@ -1,0 +1,97 @@
+"""GPU: the no-grad PBF solver tick (fluidnexus_b200.solver, through the C ABI) against the literal torch restatement of
+the reference methods in oracle/pbf_ref.py, evaluated in fp64.  fp32 sums: rel-L2 < 1e-5 per quantity after one call,
+< 1e-4 after a whole multi-iteration tick; neighbour degrees exact."""
+import numpy as np
+import pytest
+import torch
+
+from fluidnexus_b200 import synthetic as S
+from fluidnexus_b200.solver import PBFSolver
+from oracle import pbf_ref as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def _setup(N=3000, V=800, K=100, seed=0, **kw):
+    hp = S.hidden_lattice(N, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    vel = rng.normal(0, 5, hp.xyz.shape) + np.array([0.0, 30.0, 0.0])
+    vis = hp.xyz[rng.choice(hp.N, V, replace=False)] + rng.uniform(-0.4, 0.4, (V, 3))
+    imass = rng.uniform(0.8, 1.2, (hp.N, 1))
+    sp = O.SolverParams(KNN_K=K, **kw)
+    st = dict(xyz=torch.tensor(hp.xyz, dtype=torch.float64), estimate_xyz=torch.tensor(hp.xyz, dtype=torch.float64),
+              velocity=torch.tensor(vel, dtype=torch.float64), force=torch.zeros(hp.N, 3, dtype=torch.float64),
+              buoyancy=torch.zeros(hp.N, 3, dtype=torch.float64), imass=torch.tensor(imass, dtype=torch.float64),
+              counts=torch.zeros(hp.N, 1, dtype=torch.float64), visual_xyz=torch.tensor(vis, dtype=torch.float64))
+    sol = PBFSolver(hp.xyz, velocity=vel, imass=imass, visual_xyz=vis, H=sp.H, p0=sp.p0, k=sp.k, KNN_K=K, secs=sp.secs, alpha=sp.alpha,
+                    buoyancy_max_y=sp.buoyancy_max_y, buoyancy_decay_rate=sp.buoyancy_decay_rate, gravity=sp.gravity,
+                    wind_force=sp.wind_force, wind_power=sp.wind_power, min_neighbors=sp.min_neighbors)
+    return sp, st, sol
+
+
+def _compare(st, sol, tol):
+    for key, attr in (("xyz", "_xyz"), ("estimate_xyz", "_estimate_xyz"), ("velocity", "_velocity"), ("force", "_force"),
+                      ("buoyancy", "_buoyancy"), ("visual_xyz", "_visual_xyz")):
+        ref, got = st[key].numpy(), getattr(sol, attr).cpu().numpy()
+        if np.abs(ref).max() == 0:
+            assert np.abs(got).max() == 0, key
+        else:
+            assert rel(got, ref) < tol, (key, rel(got, ref))
+
+
+@pytest.mark.parametrize("K,bmax,wind", [(100, 0.0, False), (100, 0.8, True), (14, 0.0, False)])
+def test_each_solver_method_matches_the_reference_restatement(libfnx, K, bmax, wind):
+    sp, st, sol = _setup(K=K, buoyancy_max_y=bmax, wind_force=(0.3, 0.0, 0.1) if wind else (0.0, 0.0, 0.0), wind_power=2.0,
+                         buoyancy_decay_rate=0.9 if wind else 0.0)
+    O.solver_guess_hidden_particles(sp, st, use_wind=wind)
+    sol.guess_hidden_particles(use_wind=wind)
+    _compare(st, sol, 1e-6)
+    st["counts"] += 2.0
+    sol.update_solver_counts(); sol.update_solver_counts()
+    p_ratio, lambdas = O.solver_project_gas_constraints(sp, st)
+    stats = sol.project_gas_constraints(stats=True)
+    assert rel(sol._pratio.cpu().numpy(), p_ratio.numpy().reshape(-1)) < 1e-5
+    assert rel(sol._lambda.cpu().numpy(), lambdas.numpy().reshape(-1)) < 1e-4
+    assert abs(stats["p_ratio"] - float(p_ratio.mean())) < 1e-4 * abs(float(p_ratio.mean()))
+    _compare(st, sol, 1e-5)
+    O.solver_confirm_guess_hidden_particles(sp, st)
+    sol.confirm_guess_hidden_particles()
+    _compare(st, sol, 1e-4)   # velocity = (e - x)/secs amplifies the fp32 rounding of e - x
+    O.solver_update_visual_particles(sp, st)
+    sol.update_visual_particles()
+    _compare(st, sol, 1e-4)
+
+
+def test_whole_ticks_track_the_reference(libfnx):
+    """Three consecutive simulation ticks (guess, 3 solver iterations, confirm, visual update) as future_simulation.py runs
+    them, and one 'stable' tick with the counts raised first as train_physical_particle.py:206-216 does."""
+    sp, st, sol = _setup(N=2500, V=500, seed=3)
+    for t in range(3):
+        O.solver_tick(sp, st, solver_iterations=3)
+        sol.tick(solver_iterations=3)
+        _compare(st, sol, 2e-4)
+    O.solver_tick(sp, st, solver_iterations=2, stable=True, count_first=True)
+    sol.tick(solver_iterations=2, stable=True, count_first=True)
+    _compare(st, sol, 3e-4)
+
+
+def test_still_particles_and_neighbour_pruning(libfnx):
+    sp, st, sol = _setup(N=1500, V=0, seed=5, min_neighbors=20)
+    # particles that did not move keep their position and get zero velocity (gm_fluid.py:1166-1175)
+    sol._estimate_xyz.copy_(sol._xyz)
+    sol._estimate_xyz[::2] += 0.5
+    sol.confirm_guess_hidden_particles()
+    assert torch.all(sol._velocity[1::2] == 0) and torch.all(sol._velocity[::2] != 0)
+    # remove_invalid_particles: exact degrees, including torch_cluster's default cap of 32 neighbours
+    xyz = sol._xyz.cpu().double()
+    deg = O.solver_neighbor_degree(sp, xyz)
+    keep = int((deg >= 20).sum())
+    sol.remove_invalid_particles()
+    assert sol._xyz.size(0) == keep and sol._velocity.size(0) == keep and sol._imass.size(0) == keep
+    assert torch.equal(sol._xyz.cpu().double(), xyz[deg >= 20])
+    sol.update_visual_particles()   # V == 0: no-op
