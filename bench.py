@@ -91,6 +91,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner, ...) are sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
+
+
 def dist_info():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     return rank, world, int(os.environ.get("LOCAL_RANK", 0))
@@ -109,7 +126,6 @@ def run_fnx(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FNX_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
     G, views = args.frames_in_flight, list(range(5))
@@ -162,8 +178,24 @@ def run_fnx(args):
         L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
                                   prm.adam_eps, step_no[0], torch.cuda.current_stream(dev).cuda_stream))
         if e2e and last is not None:
-            return float(ps.total_loss(last).item())            # device -> host read of the step's loss
+            # device -> host read of the step's loss, every step, pipelined by one step: the copy into pinned memory is queued
+            # behind the step, and the host waits for (and reads) the PREVIOUS step's value, so the GPU never idles on it
+            k = step_no[0] % 2
+            loss_pinned[k].copy_(ps.total_loss(last).reshape(1), non_blocking=True)
+            loss_ev[k].record()
+            prev, pending[0] = pending[0], k
+            return drain(prev)
         return last
+
+    loss_pinned = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    pending = [None]
+
+    def drain(k):
+        if k is None:
+            return None
+        loss_ev[k].synchronize()
+        return float(loss_pinned[k][0])
 
     def timed(k, e2e):
         if world > 1:
@@ -174,6 +206,8 @@ def run_fnx(args):
         out = None
         for _ in range(k):
             out = one_step(e2e)
+        if e2e:                                   # the last step's loss is read inside the timed region too
+            out, pending[0] = drain(pending[0]), None
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -205,7 +239,10 @@ def run_fnx(args):
     # ---- end to end: pinned host ground truth uploaded every iteration + loss read back every step ----
     for _ in range(2):
         one_step(True)
-    ms_e2e, _ = timed(args.steps, True)
+    drain(pending[0]); pending[0] = None
+    ms_e2e, last_loss = timed(args.steps, True)
+    assert last_loss is not None and math.isfinite(last_loss), "end-to-end leg did not produce a finite loss"
+
     # ---- kernel durations: the same steps once more, eager, with CUDA events around the library's launches ----
     import ctypes as C
     nsec = lib.fnx_profile_sections()
@@ -320,7 +357,7 @@ def run_fnx(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, frames[0], bg, cams)
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -426,7 +463,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 4), "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_gpu_part_ms_per_iteration": round(gpu_part_ms, 3),
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def main():
@@ -442,6 +479,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
