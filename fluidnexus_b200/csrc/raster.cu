@@ -761,8 +761,10 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
 //                  backward needs from them only the transmittance T and the colour behind, per pixel, at L.  The
 //                  forward snapshots {T, C} when it passes L and stores {T, (C_final - C) / T} in `snap`, so the
 //                  backward starts at L instead of at the last contributor.
+// Minimum resident CTAs per SM the forward is compiled for (register cap).  Measured (whole bench, it/s): unconstrained
+// (77 registers, 6 CTAs/SM) 1454, 10 (48 registers) 1511, 12 (40 registers, 84 B of spills) 1512.
 #ifndef FNX_FWD_MIN_CTAS
-#define FNX_FWD_MIN_CTAS 1
+#define FNX_FWD_MIN_CTAS 10
 #endif
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_FWD_MIN_CTAS)
@@ -1000,8 +1002,11 @@ struct SplitReduce {
 // then the 6+C lanes that hold a result issue ONE reduction instruction into the (view, Gaussian) accumulator row
 // (their 6+C addresses are contiguous: 1-2 L2 sectors).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef FNX_BWD_MIN_CTAS
+#define FNX_BWD_MIN_CTAS 7
+#endif
 template <int C>
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, FNX_BWD_MIN_CTAS)
 blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
                  const uint32_t *__restrict__ tile_dyn_last, const float4 *__restrict__ snap,
