@@ -54,6 +54,22 @@ class FnxError(RuntimeError):
 
 # every symbol include/fnx.h declares: name -> (restype, argtypes)
 _V, _I, _I64, _SZ, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
+
+
+class GsState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("xyz", "color", "opacity", "scaling", "rotation", "m_xyz", "v_xyz", "m_color", "v_color",
+                                         "m_opacity", "v_opacity", "m_scaling", "v_scaling", "m_rotation", "v_rotation",
+                                         "max_radii2D", "xyz_gradient_accum", "denom")]
+
+
+class GsGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dscales", "dL_drotations")]
+
+
+class GsHparams(C.Structure):
+    _fields_ = [("lr_xyz", C.c_float), ("lr_color", C.c_float), ("lr_opacity", C.c_float), ("lr_scaling", C.c_float),
+                ("lr_rotation", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int32),
+                ("update_stats", C.c_int32), ("lambda_reg_scaling", C.c_float), ("reg_ratio_threshold", C.c_float)]
 _FWD = (_I, [C.POINTER(RasterArgs), ALLOC_FN, _V, ALLOC_FN, _V, ALLOC_FN, _V, _V, _V, _V, C.POINTER(_I64),
              C.POINTER(RasterScratch), _V])
 _BWD = (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), _I64, _V, _V, C.POINTER(RasterGrads), _V])
@@ -79,6 +95,8 @@ SYMBOLS = {
     "fnx_radius_count": (_I, [_V, _I, _F, _V, _I, _F, _I, _V, _V, _V]),
     "fnx_radius_fill": (_I, [_V, _I, _F, _V, _I, _F, _V, _V, _V, _V, _V]),
     "fnx_pbf_density_fwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V]),
+    "fnx_gs_activate": (_I, [_I, _V, _V, _V, _V, _V, _V, _V]),
+    "fnx_gs_update": (_I, [_I, _I, C.POINTER(GsState), C.POINTER(GsGrads), C.POINTER(GsHparams), _V, _V, _V]),
     "fnx_pbf_guess_hidden": (_I, [_I, _V, _V, _V, _V, _V, _V, C.POINTER(_F), _F, _F, _F, _F, _F, _I, C.POINTER(_F), _F, _F, _V]),
     "fnx_pbf_project_gas_constraints": (_I, [_V, _V, _I, _V, _V, _V, _V, _F, _F, _F, _I, _F, _F, _I, _F, _V, _V, _V, _V, _V]),
     "fnx_radius_graph_degree": (_I, [_V, _V, _I, _F, _I, _I, _V, _V, _V]),

@@ -321,6 +321,38 @@ int fnx_scatter_min(int64_t n, const float *src, const int64_t *index, int32_t n
                     fnx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Static-background training stage, per-Gaussian kernels  (replaces the activations of
+ * gm_background.py:29-37,90-107 and their autograd twins, the scaling regulariser of train_background.py:194-201, the
+ * densification statistics of train_background.py:238-243 / gm_background.py:472-476 and torch.optim.Adam over the five
+ * parameter groups of gm_background.py:155-168)
+ * ---------------------------------------------------------------------------------------------- */
+/* scales = exp(raw_scaling) [P,3], opacity = sigmoid(raw_opacity) [P], rotation = raw_rotation / max(|.|, 1e-12) [P,4]. */
+int fnx_gs_activate(int32_t P, const float *raw_scaling, const float *raw_opacity, const float *raw_rotation, float *scales,
+                    float *opacity, float *rotation, fnx_stream_t stream);
+
+typedef struct fnx_gs_state {   /* raw (pre-activation) parameters, Adam moments, densification statistics; all updated in place */
+    float *xyz, *color, *opacity, *scaling, *rotation;          /* [P,3] [P,C] [P] [P,3] [P,4] */
+    float *m_xyz, *v_xyz, *m_color, *v_color, *m_opacity, *v_opacity, *m_scaling, *v_scaling, *m_rotation, *v_rotation;
+    float *max_radii2D, *xyz_gradient_accum, *denom;            /* [P] each; may be NULL when update_stats == 0 */
+} fnx_gs_state;
+typedef struct fnx_gs_grads {   /* what fnx_raster_backward produced (w.r.t. the ACTIVATED attributes); any may be NULL = zero */
+    const float *dL_dmeans3D, *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dscales, *dL_drotations;
+} fnx_gs_grads;
+typedef struct fnx_gs_hparams {
+    float lr_xyz, lr_color, lr_opacity, lr_scaling, lr_rotation;
+    float beta1, beta2, eps;
+    int32_t step;                 /* Adam step count AFTER this update (>= 1) */
+    int32_t update_stats;         /* != 0: max_radii2D = max(., radii), xyz_gradient_accum += |dL_dmeans2D.xy|, denom += 1 where radii > 0 */
+    float lambda_reg_scaling;     /* > 0: adds lambda * mean(max(s_max/s_min - reg_ratio_threshold, 0)) to the loss being minimised */
+    float reg_ratio_threshold;
+} fnx_gs_hparams;
+/* Chains the gradients through the activations, adds the regulariser's gradient, updates the statistics and applies one
+ * Adam step to all five raw tensors -- one launch.  radii [P] int32 of the rendered view; *reg_loss (device scalar, may
+ * be NULL) receives the un-weighted regulariser value. */
+int fnx_gs_update(int32_t P, int32_t C, const fnx_gs_state *state, const fnx_gs_grads *grads, const fnx_gs_hparams *hp,
+                  const int32_t *radii, float *reg_loss, fnx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused image loss  (replaces l1_loss + ssim of FD/utils/loss_utils.py:9-64, the grey conversion of
  * FD/entries_fluid_nexus/train_physical_particle.py:356-360 and the weighting of
  * FD/entries_scalar_real/train_physical_particle.py:346-347)
