@@ -264,7 +264,7 @@ def run_fnx(args):
     tile_state = ws_last.tile_state() if ws_last is not None and hasattr(ws_last, "tile_state") else None
     # ---- A/B: the same timed region with every tile blended every iteration (static tile cache off) ----
     cache_on = any(getattr(w_, "static_tile_cache", False) for f in mine for w_ in states[f].ws.values())
-    value_nocache = None
+    value_nocache = e2e_nocache = None
     if cache_on:
         for f in mine:
             for w_ in states[f].ws.values():
@@ -274,6 +274,11 @@ def run_fnx(args):
             one_step(False)
         ms_nc, _ = timed(args.steps, False)
         value_nocache = G * args.steps / (ms_nc / 1e3)
+        for _ in range(2):
+            one_step(True)
+        drain(pending[0]); pending[0] = None
+        ms_nc_e2e, _ = timed(args.steps, True)
+        e2e_nocache = G * args.steps / (ms_nc_e2e / 1e3)
 
     if rank != 0:
         if world > 1:
@@ -350,6 +355,7 @@ def run_fnx(args):
         "sections_ms_per_step": {names[i]: round(tot[i] / args.steps, 4) for i in range(nsec) if cnt[i]},
         "cuda_graph": bool(graph_flag),
         "static_tile_cache": {"on": bool(cache_on), "value_with_cache_off": None if value_nocache is None else round(value_nocache, 3),
+                              "e2e_with_cache_off": None if e2e_nocache is None else round(e2e_nocache, 3),
                               "what": "tiles that hold no fluid instance keep the pixels of the static-only render (frozen background + "
                                       "fixed cameras cannot change them) instead of being blended again every iteration; `value` and "
                                       "`e2e` are measured with it on, value_with_cache_off is the same timed region with every tile "

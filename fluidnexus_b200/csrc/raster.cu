@@ -1433,14 +1433,113 @@ static int validate(const fnx_raster_args *a) {
     return FNX_OK;
 }
 
+constexpr int SORT_CAP = 2048;  // keys sorted in shared memory; larger buckets take the rank-sort path through bkeys2
+
+// Sorts the nf keys bkeys[base, base+nf) of one tile (whole CTA participates; ends with a barrier).  Up to `cap` keys:
+// bitonic network in the shared array s_key (cap entries); more: rank sort (keys are unique) into bkeys2.  Returns
+// where the sorted keys are.
+__device__ __forceinline__ const unsigned long long *sort_bucket(unsigned long long *s_key, int cap, const unsigned long long *__restrict__ bkeys,
+                                                                 unsigned long long *__restrict__ bkeys2, size_t base, int nf) {
+    if (nf <= cap) {
+        int n2 = 2;
+        while (n2 < nf) n2 <<= 1;
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) s_key[i] = i < nf ? bkeys[base + i] : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int idx = threadIdx.x; idx < (n2 >> 1); idx += blockDim.x) {
+                    const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));  // bit j clear
+                    const int l = i | j;
+                    const unsigned long long x = s_key[i], y = s_key[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_key[i] = y; s_key[l] = x; }
+                }
+                __syncthreads();
+            }
+        return s_key;
+    }
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const unsigned long long ki = bkeys[base + i];
+        int r = 0;
+        for (int q = 0; q < nf; q++) r += bkeys[base + q] < ki ? 1 : 0;
+        bkeys2[base + r] = ki;
+    }
+    __syncthreads();
+    return bkeys2 + base;
+}
+
+// General (single-stream) bucket binning: sort the tile's bucket and write its records in place -- the bucket offsets ARE
+// the tile ranges.  Replaces the depth sort, the scan, emit's ordered output, the tile sort and pack_kernel of the sorted
+// pipeline.  Dynamic shared memory: PACK_SORT_CAP keys.
+constexpr int PACK_SORT_CAP = 8192;
+template <int C>
+__global__ void __launch_bounds__(256)
+pack_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, bool use_mask, int grad_begin, int grad_end,
+                   const uint2 *__restrict__ ranges, const unsigned long long *__restrict__ bkeys, unsigned long long *__restrict__ bkeys2,
+                   GeomView g, const float *__restrict__ colors, char *__restrict__ records) {
+    extern __shared__ unsigned long long s_dyn_key[];
+    const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
+    const uint2 f = ranges[t];
+    const int nf = (int)(f.y - f.x);
+    if (nf == 0 || g.hdr->overflow) return;
+    const unsigned long long *sk = sort_bucket(s_dyn_key, PACK_SORT_CAP, bkeys, bkeys2, (size_t)f.x, nf);
+    const int tx = (int)blockIdx.x % gx, ty = (int)blockIdx.x / gx;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const unsigned long long key = sk[i];
+        uint32_t slot = (uint32_t)key;
+        const float depth = __uint_as_float((uint32_t)(key >> 32));
+        const float2 xy = g.xy[slot];
+        const float4 co = g.conic_o[slot];
+        const uint32_t gi = slot % (uint32_t)P;
+        if (use_mask) {
+            slot |= patch_mask(xy, co, tx, ty, exact_rect) << SLOT_BITS;
+            if ((int)gi < grad_begin || (int)gi >= grad_end) slot |= FROZEN_BIT;
+        }
+        float4 *rec = reinterpret_cast<float4 *>(records + ((size_t)f.x + i) * RecBytes<C>::value);
+        rec[0] = make_float4(xy.x, xy.y, co.x, co.y);
+        if (C == 3) {
+            const float c0 = colors[3 * (size_t)gi], c1 = colors[3 * (size_t)gi + 1], c2 = colors[3 * (size_t)gi + 2];
+            rec[1] = make_float4(co.z, co.w, c0, c1);
+            rec[2] = make_float4(c2, __uint_as_float(slot), depth, 0.f);
+        } else {
+            rec[1] = make_float4(co.z, co.w, colors[gi], __uint_as_float(slot));
+        }
+    }
+}
+
+
 template <int C>
 static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g, BinView &b, ImageView &im,
                          long long cap, long long sort_items, const int *radii, float *out_color, float *out_depth) {
     const int P = a->P, V = a->V, n = P * V;
     const int gx = (a->W + TILE - 1) / TILE, gy = (a->H + TILE - 1) / TILE, ntiles = gx * gy;
     const bool exact_rect = (a->flags & FNX_EXACT_RECT) != 0;
-    FNX_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)ntiles * V, st));
-    if (sort_items > 0) {
+    const bool bucket = (a->flags & FNX_BUCKET_BINNING) != 0;
+    if (bucket) {  // the tile ranges are the bucket offsets written by tile_scan_kernel; no global sort
+        const bool use_mask = (long long)P * V < (1ll << SLOT_BITS);
+        const bool all_frozen = (a->flags & FNX_ALL_FROZEN) != 0;
+        const bool all_grad = !all_frozen && a->grad_end <= a->grad_begin;
+        static bool attr_set = false;
+        if (!attr_set) {
+            FNX_CUDA_TRY(cudaFuncSetAttribute(pack_bucket_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SORT_CAP * 8));
+            attr_set = true;
+        }
+        FNX_CUDA_TRY(cudaMemsetAsync(im.tile_cursor, 0, sizeof(uint32_t) * (size_t)ntiles * V, st));
+        prof_begin(SEC_EMIT, st);
+        emit_bucket_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, P, gx, gy, exact_rect, radii, g, im.ranges, im.tile_cursor, b.bkeys);
+        prof_end(SEC_EMIT, st);
+        FNX_LAUNCH_CHECK("emit_bucket_kernel");
+        prof_begin(SEC_PACK, st);
+        pack_bucket_kernel<C><<<dim3(ntiles, V), 256, PACK_SORT_CAP * 8, st>>>(ntiles, P, gx, exact_rect, use_mask,
+                                                                            all_grad ? 0 : (all_frozen ? 0 : a->grad_begin),
+                                                                            all_grad ? P : (all_frozen ? 0 : a->grad_end), im.ranges, b.bkeys,
+                                                                            b.bkeys2, g, a->colors, b.records);
+        prof_end(SEC_PACK, st);
+        FNX_LAUNCH_CHECK("pack_bucket_kernel");
+    } else {
+        FNX_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)ntiles * V, st));
+    }
+    if (!bucket && sort_items > 0) {
         const bool padded = (a->flags & FNX_NO_HOST_SYNC) != 0 || a->instance_capacity_hint > 0;
         if (padded) FNX_CUDA_TRY(cudaMemsetAsync(b.tkeys_in, 0xFF, sizeof(uint32_t) * (size_t)sort_items, st));
         prof_begin(SEC_EMIT, st);
@@ -1517,8 +1616,9 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
 
     dim3 pgrid((P + 255) / 256, V);
     const bool bucket = (a->flags & FNX_BUCKET_BINNING) != 0;
+    const bool bucket_dyn = bucket && (a->flags & FNX_BIN_ONLY) != 0;  // dynamic set of merged streams: sorted inside the merge
     if (bucket) {
-        FNX_REQUIRE(C == 3 && no_sync && (a->flags & FNX_BIN_ONLY), "FNX_BUCKET_BINNING needs C == 3, FNX_BIN_ONLY and FNX_NO_HOST_SYNC");
+        FNX_REQUIRE(!bucket_dyn || (C == 3 && no_sync), "FNX_BUCKET_BINNING | FNX_BIN_ONLY needs C == 3 and FNX_NO_HOST_SYNC");
         const int nt = gx * gy * V;
         FNX_CUDA_TRY(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)nt, st));  // histogram + cursors
     }
@@ -1529,7 +1629,7 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
                                              exact_rect, radii, g, bucket ? im.tile_count : nullptr);
     prof_end(SEC_PREPROCESS, st);
     FNX_LAUNCH_CHECK("preprocess_kernel");
-    if (bucket) {  // histogram -> bucket offsets -> unsorted per-tile buckets; fnx_raster_blend_merged sorts and merges them
+    if (bucket_dyn) {  // histogram -> bucket offsets -> unsorted per-tile buckets; fnx_raster_blend_merged sorts and merges them
         const long long bcap = a->instance_capacity_hint;
         const int nt = gx * gy * V;
         prof_begin(SEC_EMIT, st);
@@ -1550,22 +1650,36 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         *num_rendered_host = -1;
         return FNX_OK;
     }
-    prof_begin(SEC_DEPTH_SORT, st);
-    size_t tb = g.cub_temp_bytes;
-    const int dbits = 32 + ceil_log2_u64((uint64_t)V);
-    FNX_CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.dkeys_in, g.dkeys_out, g.dvals_in, g.dvals_out, n, 0, dbits, st));
-    DepthScanIter it(cub::CountingInputIterator<uint32_t>(0), DepthScanIn{g.tiles_touched, g.dvals_out});
-    tb = g.cub_temp_bytes;
-    FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, it, g.offsets, n, st));
-    prof_end(SEC_DEPTH_SORT, st);
+    if (!bucket) {
+        prof_begin(SEC_DEPTH_SORT, st);
+        size_t tb = g.cub_temp_bytes;
+        const int dbits = 32 + ceil_log2_u64((uint64_t)V);
+        FNX_CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.dkeys_in, g.dkeys_out, g.dvals_in, g.dvals_out, n, 0, dbits, st));
+        DepthScanIter it(cub::CountingInputIterator<uint32_t>(0), DepthScanIn{g.tiles_touched, g.dvals_out});
+        tb = g.cub_temp_bytes;
+        FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, it, g.offsets, n, st));
+        prof_end(SEC_DEPTH_SORT, st);
+    }
+    // instance count + capacity / overflow header: from the depth-ordered scan (sorted pipeline) or the tile histogram (buckets)
+    const int nt_all = gx * gy * V;
+    auto write_header = [&](long long capacity, long long *pinned_dst) -> int {
+        if (bucket) {
+            tile_scan_kernel<<<1, 1024, 0, st>>>(nt_all, im.tile_count, im.ranges, g.hdr, capacity, pinned_dst);
+            FNX_LAUNCH_CHECK("tile_scan_kernel");
+        } else {
+            finish_scan_kernel<<<1, 1, 0, st>>>(n, g, capacity, pinned_dst);
+            FNX_LAUNCH_CHECK("finish_scan_kernel");
+        }
+        return FNX_OK;
+    };
 
     long long cap = a->instance_capacity_hint > 0 ? a->instance_capacity_hint : -1;
     scratch->binning = nullptr;
     scratch->check_slot = -1;
 
     if (no_sync) {  // no events, no waits: capturable into a CUDA graph
-        finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, (long long *)a->num_rendered_pinned);
-        FNX_LAUNCH_CHECK("finish_scan_kernel");
+        rc = write_header(cap, (long long *)a->num_rendered_pinned);
+        if (rc) return rc;
         scratch->binning_bytes = binning_bytes(cap, C);
         scratch->binning = ab(cb, scratch->binning_bytes);
         if (!scratch->binning) {
@@ -1583,8 +1697,8 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
     g_slots.next = (g_slots.next + 1) % PinnedSlots::N;
     long long *pinned = g_slots.host + slot_id;
     *pinned = -1;
-    finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, pinned);
-    FNX_LAUNCH_CHECK("finish_scan_kernel");
+    rc = write_header(cap, pinned);
+    if (rc) return rc;
     FNX_CUDA_TRY(cudaEventRecord(g_slots.ev[slot_id], st));
 
     long long R = -1;
@@ -1604,8 +1718,8 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         scratch->binning_capacity = cap;
         BinView b = bin_view(scratch->binning, cap, C);
         if (attempt >= 1) {  // re-arm capacity / overflow flag for the retry
-            finish_scan_kernel<<<1, 1, 0, st>>>(n, g, cap, nullptr);
-            FNX_LAUNCH_CHECK("finish_scan_kernel");
+            rc = write_header(cap, nullptr);
+            if (rc) return rc;
         }
         rc = bin_and_blend<C>(a, st, g, b, im, cap, exact ? R : cap, radii, out_color, out_depth);
         if (rc) return rc;
@@ -1737,8 +1851,6 @@ merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__re
 
 // Bucket-binned dynamic set (emit_bucket_kernel): sort the tile's (depth, slot) keys in shared memory, build the dynamic
 // records from the per-Gaussian state (what pack_kernel does for a sorted stream) and merge them with the static span.
-constexpr int SORT_CAP = 2048;  // keys sorted in shared memory; larger buckets take the rank-sort path through bkeys2
-
 __global__ void __launch_bounds__(256)
 merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat,
                     const unsigned long long *__restrict__ bkeys, unsigned long long *__restrict__ bkeys2, GeomView g,
@@ -1763,34 +1875,7 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
         mranges[t] = make_uint2((uint32_t)s_base, (uint32_t)(s_base + nf + nb));
         tile_src[t] = 0u;
     }
-    const unsigned long long *sk;
-    if (nf <= SORT_CAP) {
-        int n2 = 2;
-        while (n2 < nf) n2 <<= 1;
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) s_key[i] = i < nf ? bkeys[(size_t)f.x + i] : ~0ull;
-        __syncthreads();
-        for (int k = 2; k <= n2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int idx = threadIdx.x; idx < (n2 >> 1); idx += blockDim.x) {
-                    const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));  // bit j clear
-                    const int l = i | j;
-                    const unsigned long long x = s_key[i], y = s_key[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { s_key[i] = y; s_key[l] = x; }
-                }
-                __syncthreads();
-            }
-        sk = s_key;
-    } else {  // rare: rank sort (keys are unique) into the global scratch
-        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-            const unsigned long long ki = bkeys[(size_t)f.x + i];
-            int r = 0;
-            for (int q = 0; q < nf; q++) r += bkeys[(size_t)f.x + q] < ki ? 1 : 0;
-            bkeys2[(size_t)f.x + r] = ki;
-        }
-        __syncthreads();
-        sk = bkeys2 + f.x;
-    }
+    const unsigned long long *sk = sort_bucket(s_key, SORT_CAP, bkeys, bkeys2, (size_t)f.x, nf);
     const size_t ms = (size_t)s_base;
     // static records: shifted by the number of dynamic records in front of them (depth <= theirs; depths are positive
     // floats, so their bit patterns order like the values)

@@ -73,10 +73,11 @@ unsigned long long fnx_launch_count(void);
                                blended again -- the frozen set and the cameras are fixed, so those pixels cannot change.
                                The SAME out_color / out_depth buffers must be passed to every call. */
 
-#define FNX_BUCKET_BINNING 32u /* forward of the DYNAMIC set of merged streams (with FNX_BIN_ONLY | FNX_NO_HOST_SYNC, C == 3):
-                               no global sorts -- instances are histogrammed per tile and dropped into per-tile buckets;
-                               fnx_raster_blend_merged (same flags) sorts each bucket by (depth, index) in shared memory
-                               while merging.  Results are identical to the sorted path. */
+#define FNX_BUCKET_BINNING 32u /* no global sorts: instances are histogrammed per tile and dropped into per-tile buckets, each
+                               bucket is sorted by (depth, index) in shared memory.  Results are identical to the sorted
+                               path.  With FNX_BIN_ONLY (the DYNAMIC set of merged streams; needs FNX_NO_HOST_SYNC, C == 3)
+                               the buckets are left unsorted and fnx_raster_blend_merged (same flags) sorts them while it
+                               merges. */
 
 typedef struct fnx_raster_args {
     /* sizes */

@@ -275,3 +275,27 @@ def test_merged_static_dynamic_streams_equal_concatenated_set(libfnx, prepare, t
     assert seen_static_only > 0
     if dense:
         assert int((ts["end"] - ts["begin"]).max()) > 2048
+
+
+def test_bucket_binning_equals_sorted_binning(libfnx, monkeypatch):
+    """FNX_BUCKET_BINNING (per-tile buckets sorted in shared memory) against the two-radix-sort pipeline: identical images,
+    depth, radii, instance counts; gradients to the rounding of float atomics.  `dense` scenes put > 8192 instances into
+    one tile (the rank-sort path)."""
+    for name, dense in (("mixed_ch3_96", False), ("fluid_ch1_112", False), ("ragged_ch3_70x45", False), ("dense_ch1_64", True)):
+        gs, cam, bg, inp = scenes.build(name)
+        if dense:  # 12x the Gaussians squeezed into the same few tiles
+            rng = np.random.default_rng(1)
+            for k in ("means3D", "colors", "opacities", "scales", "rotations"):
+                inp[k] = np.concatenate([inp[k]] * 12, 0)
+            inp["means3D"] = (inp["means3D"] + rng.normal(0, 0.002, inp["means3D"].shape)).astype(np.float32)
+            inp["opacities"] = (inp["opacities"] * 0.05).astype(np.float32)
+        res = {}
+        for flag in (False, True):
+            monkeypatch.setattr(R, "BUCKET_BINNING", flag)
+            ctx, color, radii, depth = run_fnx(inp)
+            g = R.raster_backward(ctx, _t(scenes.dL_dpix(name, tuple(color.shape))))
+            res[flag] = (color, radii, depth, ctx.num_rendered, g)
+        a, b = res[False], res[True]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and a[3] == b[3], name
+        for k in ("means3D", "means2D", "colors", "opacity", "scales", "rotations"):
+            assert rel(b[4][k].cpu().numpy(), a[4][k].cpu().numpy()) < 2e-5, (name, k)
