@@ -321,9 +321,16 @@ def run_fnx(args):
         bytes_bwd = R_per_iter * rec + len(views) * HW * (4 * Cc + 8) + len(views) * P * acc
     bytes_launch = bytes_bwd if kname == "blend_bwd" else bytes_fwd
     achieved = bytes_launch / t_launch / 1e9 if t_launch > 0 else 0.0
-    traffic = None
+    traffic, issue = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][kname + "_kernel"]["dram_bytes_per_launch"]
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][kname + "_kernel"]
+        traffic = prof["dram_bytes_per_launch"]
+        # the bound that actually binds: warp instructions issued (ncu smsp__inst_executed.sum of the same capture) over the live
+        # launch duration, against 148 SMs x 4 schedulers x 1 instruction / clock at the sampled SM clock
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak_issue = 148 * 4 * sm_mhz * 1e6
+        issue = {"warp_instructions_per_launch": prof["warp_instructions_per_launch"], "achieved_ginst_s": round(prof["warp_instructions_per_launch"] / t_launch / 1e9, 1),
+                 "peak_ginst_s": round(peak_issue / 1e9, 1), "frac": round(prof["warp_instructions_per_launch"] / t_launch / peak_issue, 4)}
     except Exception:
         pass
     line = {
@@ -349,7 +356,7 @@ def run_fnx(args):
                      "peak_source": peak_src,
                      "ms_per_launch": round(t_launch * 1e3, 4), "launches_timed": int(n_launch),
                      "share_of_step": round(tot[ib] / sum(tot[i] for i in range(nsec)), 4),
-                     "tile_state": tile_info,
+                     "issue_rate": issue, "tile_state": tile_info,
                      "note": "instruction-issue bound blend loop (ncu: issue-active 70-80 %) on a mostly L2-resident working set; "
                              "see DESIGN.md 6"},
         "sections_ms_per_step": {names[i]: round(tot[i] / args.steps, 4) for i in range(nsec) if cnt[i]},
