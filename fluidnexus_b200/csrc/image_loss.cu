@@ -145,6 +145,7 @@ ssim_fwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__re
 // pass 2: dL/dimg = w_l1/N * sign(x-y) - w_ssim/N * (G*M1 + 2x G*M2 + y G*M3)
 __global__ void __launch_bounds__(NT, 3)
 ssim_bwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__restrict__ img, const float *__restrict__ gt,
+                int C_src, bool grey_src /* layout of img / gt: the originals, or the precomputed channel means (1, false) */,
                 Win win, const float *__restrict__ maps, float w_l1, float w_ssim, float *__restrict__ dL_dimg) {
     __shared__ float sm[3][EH][ES];
     __shared__ float hq[3][EH][TW];
@@ -202,7 +203,7 @@ ssim_bwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__re
     for (int o = 0; o < RSEG; o++) {
         const int py = y0 + r0 + o;
         if (px >= W || py >= H) continue;
-        const float x = load_px(img, C, H, W, v, c, grey, py, px), y = load_px(gt, C, H, W, v, c, grey, py, px);
+        const float x = load_px(img, C_src, H, W, v, c, grey_src, py, px), y = load_px(gt, C_src, H, W, v, c, grey_src, py, px);
         const float d = x - y;
         const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
         // in grey mode the reference's 3 identical channels each carry 1/3 of the mean, and d grey / d channel = 1/C
@@ -215,6 +216,19 @@ ssim_bwd_kernel(int V, int C, int Ce, int H, int W, bool grey, const float *__re
             for (int k = 0; k < C; k++) dL_dimg[((size_t)v * C + k) * HW + off] = gout;
         }
     }
+}
+
+// channel means of img and gt, once per call in grey mode: the SSIM kernels then read one value per pixel and image
+// (with their 1.7x halo re-reads) instead of C
+__global__ void grey_kernel(int V, int C, size_t HW, const float *__restrict__ img, const float *__restrict__ gt,
+                            float *__restrict__ grey_img, float *__restrict__ grey_gt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)V * HW) return;
+    const size_t v = i / HW, o = i % HW;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < C; k++) { a += img[(v * C + k) * HW + o]; b += gt[(v * C + k) * HW + o]; }
+    grey_img[i] = a / C;  // torch.mean over the channel dim
+    grey_gt[i] = b / C;
 }
 
 }  // namespace fnx
@@ -239,11 +253,21 @@ int fnx_image_loss(int32_t V, int32_t C, int32_t H, int32_t W, const float *img,
     static_assert(NT == TW * (TH / RSEG), "pass B maps one thread to RSEG rows of one column");
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, V * Ce);
     prof_begin(SEC_IMAGE_LOSS, st);
-    ssim_fwd_kernel<<<grid, NT, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, 1.0f / ((float)Ce * (float)H * (float)W), maps, l1_mean,
-                                         ssim_mean);
+    const size_t HW = (size_t)H * W;
+    const float *src_img = img, *src_gt = gt;
+    int C_src = C;
+    bool grey_src = grey != 0;
+    if (grey && C > 1) {  // scratch holds 3*V*C*HW floats, the maps of grey mode use 3*V*HW of them: room for the two means
+        float *grey_img = maps + 3 * (size_t)V * HW, *grey_gt = grey_img + (size_t)V * HW;
+        grey_kernel<<<(unsigned)(((size_t)V * HW + 255) / 256), 256, 0, st>>>(V, C, HW, img, gt, grey_img, grey_gt);
+        FNX_LAUNCH_CHECK("grey_kernel");
+        src_img = grey_img; src_gt = grey_gt; C_src = 1; grey_src = false;
+    }
+    ssim_fwd_kernel<<<grid, NT, 0, st>>>(V, C_src, Ce, H, W, grey_src, src_img, src_gt, win, 1.0f / ((float)Ce * (float)H * (float)W), maps,
+                                         l1_mean, ssim_mean);
     FNX_LAUNCH_CHECK("ssim_fwd_kernel");
     if (dL_dimg) {
-        ssim_bwd_kernel<<<grid, NT, 0, st>>>(V, C, Ce, H, W, grey != 0, img, gt, win, maps, w_l1, w_ssim, dL_dimg);
+        ssim_bwd_kernel<<<grid, NT, 0, st>>>(V, C, Ce, H, W, grey != 0, src_img, src_gt, C_src, grey_src, win, maps, w_l1, w_ssim, dL_dimg);
         FNX_LAUNCH_CHECK("ssim_bwd_kernel");
     }
     prof_end(SEC_IMAGE_LOSS, st);

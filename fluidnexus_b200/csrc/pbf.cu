@@ -92,8 +92,13 @@ __device__ __forceinline__ uint32_t hash_cell(int3 c, int M) {
            (((uint32_t)c.z & ((1u << az) - 1u)) << (ax + ay));
 }
 
-__global__ void grid_count_kernel(const float *__restrict__ pts, int n, float inv_cell, int M, uint32_t *__restrict__ fill) {
+__global__ void grid_count_kernel(const float *__restrict__ pts, int n, float inv_cell, int M, uint32_t *__restrict__ fill,
+                                  GridHeader *__restrict__ h, float cell, uint32_t *__restrict__ bucket_start) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {  // header + the scan's end sentinel (the scan writes entries [0, M))
+        h->n = n; h->M = M; h->cell = cell; h->inv_cell = 1.0f / cell;
+        bucket_start[M] = (uint32_t)n;
+    }
     if (i >= n) return;
     atomicAdd(&fill[hash_cell(cell_of(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], inv_cell), M)], 1u);
 }
@@ -129,11 +134,13 @@ __global__ void grid_header_kernel(GridHeader *h, int n, int M, float cell, uint
 static int grid_build(const float *pts, int n, float cell, void *scratch, cudaStream_t st) {
     GridView g = grid_view(scratch, n);
     const float inv_cell = 1.0f / cell;
-    grid_header_kernel<<<1, 1, 0, st>>>(g.hdr, n, g.M, cell, g.bucket_start);
     FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
     if (n > 0) {
-        grid_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_fill);
+        grid_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_fill, g.hdr, cell, g.bucket_start);
         FNX_LAUNCH_CHECK("grid_count_kernel");
+    } else {
+        grid_header_kernel<<<1, 1, 0, st>>>(g.hdr, n, g.M, cell, g.bucket_start);
+        FNX_LAUNCH_CHECK("grid_header_kernel");
     }
     size_t tb = g.cub_temp_bytes;
     FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, g.bucket_fill, g.bucket_start, g.M, st));

@@ -1434,6 +1434,7 @@ static int validate(const fnx_raster_args *a) {
 }
 
 constexpr int SORT_CAP = 2048;  // keys sorted in shared memory; larger buckets take the rank-sort path through bkeys2
+constexpr int STATIC_DEPTH_SMEM = 2048;  // static depths staged per tile by merge_bucket_kernel
 
 // Sorts the nf keys bkeys[base, base+nf) of one tile (whole CTA participates; ends with a barrier).  Up to `cap` keys:
 // bitonic network in the shared array s_key (cap entries); more: rank sort (keys are unique) into bkeys2.  Returns
@@ -1875,7 +1876,12 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
         mranges[t] = make_uint2((uint32_t)s_base, (uint32_t)(s_base + nf + nb));
         tile_src[t] = 0u;
     }
-    const unsigned long long *sk = sort_bucket(s_key, SORT_CAP, bkeys, bkeys2, (size_t)f.x, nf);
+    // depths of the (truncated) static span, staged once: the dynamic records binary-search them
+    __shared__ uint32_t s_sdepth[STATIC_DEPTH_SMEM];
+    const bool sdepth_staged = nb <= STATIC_DEPTH_SMEM;
+    if (sdepth_staged)
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) s_sdepth[j] = __float_as_uint(rec48_depth(rec_stat, (size_t)b.x + j));
+    const unsigned long long *sk = sort_bucket(s_key, SORT_CAP, bkeys, bkeys2, (size_t)f.x, nf);   // (ends with a barrier)
     const size_t ms = (size_t)s_base;
     // static records: shifted by the number of dynamic records in front of them (depth <= theirs; depths are positive
     // floats, so their bit patterns order like the values)
@@ -1901,7 +1907,8 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
         int lo = 0, hi = nb;  // lower bound: first static depth >= d
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (__float_as_uint(rec48_depth(rec_stat, (size_t)b.x + mid)) < d) lo = mid + 1; else hi = mid;
+            const uint32_t sd = sdepth_staged ? s_sdepth[mid] : __float_as_uint(rec48_depth(rec_stat, (size_t)b.x + mid));
+            if (sd < d) lo = mid + 1; else hi = mid;
         }
         const float2 xy = g.xy[slot];
         const float4 co = g.conic_o[slot];

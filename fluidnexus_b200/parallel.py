@@ -70,9 +70,10 @@ class FrameLanes:
         self.dev = torch.device(device)
         self.n = max(1, int(lanes))
         self.steps = [make_step(k) for k in range(self.n)]
+        # (one lane needs no streams or events: the frames simply run in order on the caller's stream)
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n)] if self.n > 1 else [None]
-        self._fork = torch.cuda.Event()
-        self._join = [torch.cuda.Event() for _ in range(self.n)]
+        self._fork = torch.cuda.Event() if self.n > 1 else None
+        self._join = [torch.cuda.Event() for _ in range(self.n)] if self.n > 1 else []
 
     def run(self, frames, call):
         """call(step, frame) for every frame, frame k on lane k % lanes; everything is ordered after the work already

@@ -88,3 +88,14 @@ def test_two_ranks_match_single_process(G):
         assert torch.allclose(g, grad, atol=1e-6), r
         assert torch.allclose(p, param.detach(), atol=1e-6), r
     assert torch.equal(out[0][0], out[1][0])   # replicated parameters stay bit-identical across ranks
+
+
+def test_frame_lanes_single_lane_runs_frames_in_order():
+    """lanes = 1 is plain sequential execution (no CUDA streams involved): results in frame order, one step object."""
+    from fluidnexus_b200.parallel import FrameLanes
+    made = []
+    lanes = FrameLanes(lambda k: made.append(k) or f"step{k}", 1, "cpu")
+    assert lanes.n == 1 and made == [0]
+    seen = []
+    out = lanes.run([3, 1, 2], lambda step, fr: seen.append((step, fr)) or fr * 10)
+    assert out == [30, 10, 20] and seen == [("step0", 3), ("step0", 1), ("step0", 2)]
