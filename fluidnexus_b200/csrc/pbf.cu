@@ -344,17 +344,17 @@ __global__ void __launch_bounds__(128)
 density_fwd_if_capped_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                              const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio,
                              const int *__restrict__ cap_flag) {
-    if (*cap_flag == 0) return;
-    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    if (*cap_flag == 0) return;  // the normal case: a small fixed grid returns at once
     const int lane = threadIdx.x % GROUP;
-    if (r >= N) return;
-    const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
-    float pi = 0.f;
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
-        if (r <= kth[c]) pi += poly6(d2, H2, term1);
-    });
-    pi = group_sum(pi);
-    if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
+    for (int r = blockIdx.x * QPB + (threadIdx.x / GROUP); r < N; r += gridDim.x * QPB) {  // (r is uniform over a query group)
+        const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
+        float pi = 0.f;
+        warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
+            if (r <= kth[c]) pi += poly6(d2, H2, term1);
+        });
+        pi = group_sum(pi);
+        if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
+    }
 }
 
 // dL/dX_k = sum_{j in N(k)} dpoly6(d2) * 2 (X_k - X_j) * ( gp_k [k <= kth[j]] + gp_j [j <= kth[k]] ),
@@ -656,12 +656,15 @@ __global__ void advect_pack_vel_kernel(GridView gh, int N, const float *__restri
 __global__ void __launch_bounds__(128)
 pair_distance_kernel(GridView g, float inv_cell, const float *__restrict__ pts, int n, float thr, float grad_scale,
                      float *__restrict__ loss_out, float *__restrict__ dL_dp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // 8 lanes per point (the grid is sparse at cell = threshold: 27 mostly empty buckets per query are pure latency for
+    // one thread); out-of-range groups keep running with no work so that the warp-wide loss reduction stays convergent
+    const int i = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
     float loss = 0.f;
+    float3 acc = make_float3(0.f, 0.f, 0.f);
     if (i < n) {
         const float3 q = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
-        float3 acc = make_float3(0.f, 0.f, 0.f);
-        for_each_neighbor(g, inv_cell, q, thr * thr, [&](int j, const float4 &pj, float d2) {
+        warp_for_each_neighbor(g, inv_cell, q, thr * thr, lane, [&](int j, const float4 &pj, float d2, uint32_t) {
             if (j == i) return;
             const float d = sqrtf(d2);
             if (!(d < thr)) return;
@@ -673,10 +676,9 @@ pair_distance_kernel(GridView g, float inv_cell, const float *__restrict__ pts, 
                 acc.x += s * (q.x - pj.x); acc.y += s * (q.y - pj.y); acc.z += s * (q.z - pj.z);
             }
         });
-        if (dL_dp) {
-            dL_dp[3 * i] = grad_scale * acc.x; dL_dp[3 * i + 1] = grad_scale * acc.y; dL_dp[3 * i + 2] = grad_scale * acc.z;
-        }
     }
+    acc.x = group_sum(acc.x); acc.y = group_sum(acc.y); acc.z = group_sum(acc.z);
+    if (i < n && dL_dp && lane < 3) dL_dp[3 * i + lane] = grad_scale * (lane == 0 ? acc.x : (lane == 1 ? acc.y : acc.z));
     loss = warp_sum(loss);
     if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(loss_out, loss);
 }
@@ -919,7 +921,7 @@ int fnx_pbf_density_fwd_counted(const void *grid, const float *X, int32_t N, con
     density_fwd_counted_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, X, N, imass, max_num_neighbors, H * H, term1, p0, kth_out,
                                                                     p_ratio, cap_flag);
     FNX_LAUNCH_CHECK("density_fwd_counted_kernel");
-    density_fwd_if_capped_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, X, N, imass, kth_out, H * H, term1, p0, p_ratio, cap_flag);
+    density_fwd_if_capped_kernel<<<min((N + QPB - 1) / QPB, 148 * 8), 128, 0, st>>>(g, 1.0f / H, X, N, imass, kth_out, H * H, term1, p0, p_ratio, cap_flag);
     FNX_LAUNCH_CHECK("density_fwd_if_capped_kernel");
     return FNX_OK;
 }
@@ -1091,7 +1093,7 @@ int fnx_pair_distance_loss(const void *grid, const float *pts, int32_t n, float 
     FNX_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
     if (n == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, n);
-    pair_distance_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / cell, pts, n, threshold, grad_scale, loss, dL_dpts);
+    pair_distance_kernel<<<(n + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / cell, pts, n, threshold, grad_scale, loss, dL_dpts);
     FNX_LAUNCH_CHECK("pair_distance_kernel");
     return FNX_OK;
 }
