@@ -1,0 +1,67 @@
+"""CPU: the solver-tick oracle (oracle/pbf_ref.py:solver_*) against invariants of the reference algorithm, and the
+no-fallback rule of the product class."""
+import numpy as np
+import pytest
+import torch
+
+from fluidnexus_b200 import synthetic as S
+from oracle import pbf_ref as O
+
+
+def _state(N=400, V=60, seed=0):
+    hp = S.hidden_lattice(N, seed=seed)
+    rng = np.random.default_rng(seed)
+    f = lambda a: torch.tensor(a, dtype=torch.float64)
+    return dict(xyz=f(hp.xyz), estimate_xyz=f(hp.xyz), velocity=f(rng.normal(0, 5, hp.xyz.shape)), force=torch.zeros(hp.N, 3, dtype=torch.float64),
+                buoyancy=torch.zeros(hp.N, 3, dtype=torch.float64), imass=torch.ones(hp.N, 1, dtype=torch.float64),
+                counts=torch.zeros(hp.N, 1, dtype=torch.float64), visual_xyz=f(hp.xyz[:V] + 0.2))
+
+
+def test_guess_then_confirm_without_solver_is_plain_euler():
+    """guess_hidden_particles + confirm_guess_hidden_particles with no solver iteration: x += secs * v', v' = v + g*alpha*secs
+    (gm_fluid.py:809-844, 1160-1175), forces cleared, counts cleared."""
+    sp, st = O.SolverParams(alpha=-0.2), _state()
+    x0, v0 = st["xyz"].clone(), st["velocity"].clone()
+    st["force"] += 1.0
+    O.solver_guess_hidden_particles(sp, st)
+    v1 = v0 + torch.tensor([0.0, -9.8 * -0.2, 0.0]) * sp.secs + sp.secs * 1.0
+    assert torch.allclose(st["velocity"], v1) and float(st["force"].abs().max()) == 0 and float(st["counts"].abs().max()) == 0
+    O.solver_confirm_guess_hidden_particles(sp, st)
+    assert torch.allclose(st["xyz"], x0 + sp.secs * v1) and torch.allclose(st["velocity"], v1)
+
+
+def test_projection_moves_momentum_free_when_cap_does_not_bind():
+    """With a symmetric neighbour graph (K not binding) and equal neighbour counts the pairwise corrections
+    (lambda_i + lambda_j + s_corr) * spiky are antisymmetric: two isolated particles move by equal and opposite amounts."""
+    sp = O.SolverParams()
+    st = _state(N=2)
+    st["xyz"] = torch.tensor([[0.0, 0.0, 0.0], [0.9, 0.2, -0.1]], dtype=torch.float64)
+    st["estimate_xyz"] = st["xyz"].clone()
+    st["velocity"], st["force"], st["buoyancy"] = (torch.zeros(2, 3, dtype=torch.float64) for _ in range(3))
+    st["imass"], st["counts"] = torch.ones(2, 1, dtype=torch.float64), torch.zeros(2, 1, dtype=torch.float64)
+    before = st["estimate_xyz"].clone()
+    O.solver_project_gas_constraints(sp, st)
+    d = st["estimate_xyz"] - before
+    assert torch.allclose(d[0], -d[1], atol=1e-12) and float(d.abs().max()) > 0
+
+
+def test_update_visual_moves_with_the_local_velocity():
+    sp, st = O.SolverParams(), _state()
+    st["velocity"] = torch.ones_like(st["velocity"]) * torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)   # uniform flow
+    v0 = st["visual_xyz"].clone()
+    O.solver_update_visual_particles(sp, st)
+    assert torch.allclose(st["visual_xyz"] - v0, torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64) * sp.secs)
+
+
+def test_neighbor_degree_is_capped_like_torch_cluster():
+    sp = O.SolverParams(H=500.0)                     # every particle sees every other: the default cap of 32 binds
+    xyz = torch.tensor(S.hidden_lattice(60, seed=1).xyz, dtype=torch.float64)
+    deg = O.solver_neighbor_degree(sp, xyz)
+    # a query keeps its first 33 hits in index order (self included, then dropped): low indices are everybody's neighbour
+    assert int(deg[0]) == 59 and int(deg[-1]) < 32 and int(deg.sum()) <= 60 * 33
+
+
+def test_solver_class_refuses_cpu():
+    from fluidnexus_b200.solver import PBFSolver
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PBFSolver(np.zeros((4, 3), np.float32), device="cpu")
