@@ -1002,8 +1002,10 @@ struct SplitReduce {
 // then the 6+C lanes that hold a result issue ONE reduction instruction into the (view, Gaussian) accumulator row
 // (their 6+C addresses are contiguous: 1-2 L2 sectors).
 // ---------------------------------------------------------------------------------------------------------------
+// Register cap of the backward (see FNX_FWD_MIN_CTAS).  Measured: 7 CTAs/SM (72 registers) 1989 it/s, 8 (64 registers) 1996,
+// 9 (56 registers, 48 B of spills) slower.
 #ifndef FNX_BWD_MIN_CTAS
-#define FNX_BWD_MIN_CTAS 7
+#define FNX_BWD_MIN_CTAS 8
 #endif
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_BWD_MIN_CTAS)
@@ -1067,7 +1069,11 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     const int my_val = ((lane & Red::dup_mask()) == 0) ? Red::index(lane) : -1;  // which reduced value this lane publishes
 
     float pyf[PPT], T_final[PPT], T[PPT], last_alpha[PPT], bg_dot_dpixel[PPT];
-    float accum_rec[PPT][C], dL_dpixel[PPT][C], last_color[PPT][C];
+    // The reference tracks the colour accumulated behind the current record per channel (accum_rec, last_color:
+    // backward.cu:488-496) and dots (c - accum_rec) with dL/dpixel.  dL/dpixel is constant along the walk and the
+    // recursion is linear, so the DOT PRODUCTS are tracked instead: accum_dot = accum_rec . dL/dpixel, last_dot = last_color .
+    // dL/dpixel -- 2 FMAs instead of 2C per record and 2 registers instead of 2C per pixel.
+    float accum_dot[PPT], last_dot[PPT], dL_dpixel[PPT][C];
     int last_contributor[PPT];
     int warp_last = 0;  // records at or beyond this position touch no pixel of this warp
 #pragma unroll
@@ -1081,21 +1087,18 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         last_contributor[p] = inside ? (int)im.n_contrib[(size_t)v * HW + pix] : 0;
         last_alpha[p] = 0.f;
         bg_dot_dpixel[p] = 0.f;
+        accum_dot[p] = 0.f;
+        last_dot[p] = 0.f;
 #pragma unroll
         for (int ch = 0; ch < C; ch++) {
-            accum_rec[p][ch] = 0.f;
-            last_color[p][ch] = 0.f;
             dL_dpixel[p][ch] = inside ? dL_dpixels[((size_t)v * C + ch) * HW + pix] : 0.f;
             bg_dot_dpixel[p] += bg[ch] * dL_dpixel[p][ch];
         }
         if (last_contributor[p] > L) {  // this pixel blended frozen records behind L: resume from the forward's snapshot
             const float4 sn = snap[(size_t)v * HW + pix];
             T[p] = sn.x;
-            accum_rec[p][0] = sn.y;
-            if (C == 3) {
-                accum_rec[p][1 % C] = sn.z;
-                accum_rec[p][2 % C] = sn.w;
-            }
+            accum_dot[p] = sn.y * dL_dpixel[p][0];
+            if (C == 3) accum_dot[p] += sn.z * dL_dpixel[p][1 % C] + sn.w * dL_dpixel[p][2 % C];
             last_contributor[p] = L;
         }
         warp_last = max(warp_last, last_contributor[p]);
@@ -1162,11 +1165,11 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     for (int p = 0; p < PPT; p++) {
                         if (!contrib[p]) continue;
                         T[p] = T[p] * __fdividef(1.f, 1.f - alpha[p]);
+                        accum_dot[p] = last_alpha[p] * last_dot[p] + (1.f - last_alpha[p]) * accum_dot[p];
+                        float cd = 0.f;
 #pragma unroll
-                        for (int ch = 0; ch < C; ch++) {
-                            accum_rec[p][ch] = last_alpha[p] * last_color[p][ch] + (1.f - last_alpha[p]) * accum_rec[p][ch];
-                            last_color[p][ch] = col[ch];
-                        }
+                        for (int ch = 0; ch < C; ch++) cd += col[ch] * dL_dpixel[p][ch];
+                        last_dot[p] = cd;
                         last_alpha[p] = alpha[p];
                     }
                     continue;
@@ -1179,16 +1182,15 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     const float inv_1ma = __fdividef(1.f, 1.f - alpha[p]);
                     T[p] = T[p] * inv_1ma;
                     const float dchannel_dcolor = alpha[p] * T[p];
-                    float dL_dalpha = 0.0f;
+                    accum_dot[p] = last_alpha[p] * last_dot[p] + (1.f - last_alpha[p]) * accum_dot[p];
+                    float cd = 0.f;
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
-                        const float c = col[ch];
-                        accum_rec[p][ch] = last_alpha[p] * last_color[p][ch] + (1.f - last_alpha[p]) * accum_rec[p][ch];
-                        last_color[p][ch] = c;
-                        dL_dalpha += (c - accum_rec[p][ch]) * dL_dpixel[p][ch];
+                        cd += col[ch] * dL_dpixel[p][ch];
                         vals[6 + ch] += dchannel_dcolor * dL_dpixel[p][ch];
                     }
-                    dL_dalpha *= T[p];
+                    last_dot[p] = cd;
+                    float dL_dalpha = (cd - accum_dot[p]) * T[p];
                     last_alpha[p] = alpha[p];
                     dL_dalpha += (-T_final[p] * inv_1ma) * bg_dot_dpixel[p];
                     const float dL_dG = r1.y * dL_dalpha;
