@@ -1105,7 +1105,9 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    // constant factor of the value this lane publishes: dmean2D.x: -(0.5 W), dmean2D.y: -(0.5 H) (backward.cu:444-445,
+    // 524-525), dconic.{x,y,w}: -0.5, dopacity and dcolour: 1
+    const float post_scale = my_val == 0 ? -0.5f * W : (my_val == 1 ? -0.5f * H : (my_val >= 2 && my_val <= 4 ? -0.5f : 1.0f));
 
     for (int bi = 0; bi < nbatch; bi++) {
         const int s = bi % STAGES;
@@ -1193,18 +1195,18 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     float dL_dalpha = (cd - accum_dot[p]) * T[p];
                     last_alpha[p] = alpha[p];
                     dL_dalpha += (-T_final[p] * inv_1ma) * bg_dot_dpixel[p];
-                    const float dL_dG = r1.y * dL_dalpha;
-                    const float gdx = G[p] * dx[p], gdy = G[p] * dy[p];
-                    const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-                    const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                    vals[0] += dL_dG * dG_ddelx * ddelx_dx;
-                    vals[1] += dL_dG * dG_ddely * ddely_dy;
-                    vals[2] += -0.5f * gdx * dx[p] * dL_dG;
-                    vals[3] += -0.5f * gdx * dy[p] * dL_dG;
-                    vals[4] += -0.5f * gdy * dy[p] * dL_dG;
+                    // geometric terms without their constant factors (-0.5 W, -0.5 H, -0.5: applied once per record after
+                    // the warp reduction, see `post_scale`): A = dL/dG * G * dx, B = dL/dG * G * dy
+                    const float gG = r1.y * dL_dalpha * G[p];
+                    const float A = gG * dx[p], B = gG * dy[p];
+                    vals[0] += A * r0.z + B * r0.w;      // -(dG/ddelx) dL/dG
+                    vals[1] += B * r1.x + A * r0.w;      // -(dG/ddely) dL/dG
+                    vals[2] += A * dx[p];
+                    vals[3] += A * dy[p];
+                    vals[4] += B * dy[p];
                     vals[5] += G[p] * dL_dalpha;
                 }
-                const float red = Red::run(vals, lane);
+                const float red = Red::run(vals, lane) * post_scale;
                 if (my_val >= 0) red_add(accum + (size_t)slot_bits * ACC + my_val, red);
             }
         }
