@@ -174,6 +174,22 @@ class BackgroundModel:
             prune = prune | (self.max_radii2D > max_screen_size) | (self.get_scaling.max(dim=1).values > 0.1 * extent)
         self.prune_points(prune)
 
+    # -- point-cloud file of the stage (gm_background.py:203-269), see fluidnexus_b200/io.py ------------------------------
+    def save_ply(self, path):
+        from . import io as IO
+        IO.save_background_ply(path, self._xyz, self._color, self._opacity, self._scaling, self._rotation)
+
+    def load_ply(self, path):
+        """Replaces the parameters with the file's (raw values), zeroes the Adam moments and the statistics."""
+        from . import io as IO
+        d = IO.load_background_ply(path)
+        t = lambda a: torch.tensor(a, dtype=torch.float32, device=self.dev).contiguous()
+        self._xyz, self._color, self._opacity = t(d["xyz"]), t(d["color"]), t(d["opacity"])
+        self._scaling, self._rotation = t(d["scaling"]), t(d["rotation"])
+        self.exp_avg = {k: torch.zeros_like(self._raw(k)) for k in _PARAMS}
+        self.exp_avg_sq = {k: torch.zeros_like(self._raw(k)) for k in _PARAMS}
+        self._reset_stats()
+
     def add_densification_stats(self, viewspace_point_tensor, update_filter):
         """For callers that run the drop-in rasterizer through autograd; BackgroundStep does this inside fnx_gs_update."""
         self.xyz_gradient_accum[update_filter] += torch.norm(viewspace_point_tensor.grad[update_filter, :2], dim=-1, keepdim=True)
