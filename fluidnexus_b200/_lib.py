@@ -100,6 +100,7 @@ SYMBOLS = {
     "fnx_pbf_guess_hidden": (_I, [_I, _V, _V, _V, _V, _V, _V, C.POINTER(_F), _F, _F, _F, _F, _F, _I, C.POINTER(_F), _F, _F, _V]),
     "fnx_pbf_project_gas_constraints": (_I, [_V, _V, _I, _V, _V, _V, _V, _F, _F, _F, _I, _F, _F, _I, _F, _V, _V, _V, _V, _V]),
     "fnx_radius_graph_degree": (_I, [_V, _V, _I, _F, _I, _I, _V, _V, _V]),
+    "fnx_rigid_project": (_I, [_V, _V, _I, _V, _I, _I, C.POINTER(_F), C.POINTER(_F), _F, _I, _V, _V]),
     "fnx_pbf_confirm_guess": (_I, [_I, _V, _V, _V, _F, _V]),
     "fnx_pbf_update_visual": (_I, [_V, _V, _V, _I, _V, _I, _I, _F, _F, _V, _V]),
     "fnx_pbf_density_fwd_counted": (_I, [_V, _V, _I, _V, _I, _F, _F, _V, _V, _V, _V]),

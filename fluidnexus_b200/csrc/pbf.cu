@@ -605,6 +605,60 @@ graph_degree_kernel(GridView g, float inv_cell, const float *__restrict__ X, int
     if (lane == 0) degree[r] = cnt;
 }
 
+// Rigid coupling (gm_fluid.py:1023-1105, 1241-1289): a particle inside the rigid body is moved onto the nearest rigid-body
+// sample among its radius() neighbours (x += -(x - nearest)); ties go to the smaller sample index, as scatter_min's argmin
+// over index-ordered edges does.  body: 0 cuboid (|x - c| <= half edge per axis), 1 sphere (|x - c| <= radius),
+// 2 cylinder (axis z: (x-cx)^2 + (y-cy)^2 <= radius^2, |z - cz| <= half height) -- check_inside_rigid_body, :1024-1056.
+struct RigidBody {
+    int kind;
+    float3 center, prm;
+};
+__device__ __forceinline__ bool inside_rigid(const RigidBody &b, float3 p) {
+    if (b.kind == 0)
+        return p.x >= b.center.x - b.prm.x && p.x <= b.center.x + b.prm.x && p.y >= b.center.y - b.prm.y && p.y <= b.center.y + b.prm.y &&
+               p.z >= b.center.z - b.prm.z && p.z <= b.center.z + b.prm.z;
+    const float dx = p.x - b.center.x, dy = p.y - b.center.y, dz = p.z - b.center.z;
+    if (b.kind == 1) return sqrtf(dx * dx + dy * dy + dz * dz) <= b.prm.x;
+    return dx * dx + dy * dy <= b.prm.x * b.prm.x && p.z >= b.center.z - b.prm.y && p.z <= b.center.z + b.prm.y;
+}
+__global__ void __launch_bounds__(128)
+rigid_project_kernel(GridView g, float inv_cell, float *__restrict__ xyz, int N, RigidBody body, float r2, int K, int M,
+                     int *__restrict__ n_inside) {
+    const int i = blockIdx.x * QPB + (threadIdx.x / GROUP);
+    const int lane = threadIdx.x % GROUP;
+    if (i >= N) return;
+    const float3 q = make_float3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (!inside_rigid(body, q)) return;   // uniform over the query group
+    int cut = 0x7fffffff;
+    if (K > 0) {
+        int cnt = 0;
+        warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int, const float4 &, float, uint32_t) { cnt++; });
+        if (group_sum(cnt) > K) cut = kth_by_bisection(g, inv_cell, q, r2, lane, K, M);
+    }
+    float best = 3.4e38f;
+    int best_j = 0x7fffffff;
+    float3 bp = q;
+    warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &pj, float d2, uint32_t) {
+        if (j > cut) return;
+        if (d2 < best || (d2 == best && j < best_j)) { best = d2; best_j = j; bp = make_float3(pj.x, pj.y, pj.z); }
+    });
+    const unsigned m = group_mask();
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(m, best, o);
+        const int oj = __shfl_xor_sync(m, best_j, o);
+        const float ox = __shfl_xor_sync(m, bp.x, o), oy = __shfl_xor_sync(m, bp.y, o), oz = __shfl_xor_sync(m, bp.z, o);
+        if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; bp = make_float3(ox, oy, oz); }
+    }
+    if (lane == 0) {
+        if (n_inside) atomicAdd(n_inside, 1);
+        if (best_j != 0x7fffffff) {
+            // x += -(x - nearest), evaluated like the reference (the result is `nearest` up to one rounding)
+            xyz[3 * i] = q.x + -(q.x - bp.x); xyz[3 * i + 1] = q.y + -(q.y - bp.y); xyz[3 * i + 2] = q.z + -(q.z - bp.z);
+        }
+    }
+}
+
 // guess_hidden_particles (gm_fluid.py:809-844)
 __global__ void solver_guess_kernel(int N, const float *__restrict__ xyz, float *__restrict__ velocity, float *__restrict__ buoyancy,
                                     float *__restrict__ force, float *__restrict__ estimate_xyz, float *__restrict__ counts,
@@ -1055,6 +1109,26 @@ int fnx_radius_graph_degree(void *grid, const float *X, int32_t N, float r, int3
     FNX_LAUNCH_CHECK("radius_count_kernel");
     graph_degree_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / r, X, N, kth_scratch, r * r, loop, degree);
     FNX_LAUNCH_CHECK("graph_degree_kernel");
+    return FNX_OK;
+}
+
+int fnx_rigid_project(void *grid, const float *rigid_xyz, int32_t M, float *xyz, int32_t N, int32_t body, const float *center3_host,
+                      const float *params3_host, float r, int32_t max_num_neighbors, int32_t *n_inside, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid && (rigid_xyz || M == 0) && (xyz || N == 0) && M >= 0 && N >= 0 && body >= 0 && body <= 2 && center3_host && params3_host &&
+                    r > 0.f, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_inside) FNX_CUDA_TRY(cudaMemsetAsync(n_inside, 0, sizeof(int32_t), st));
+    if (N == 0 || M == 0) return FNX_OK;
+    int rc = grid_build(rigid_xyz, M, r, grid, st);
+    if (rc) return rc;
+    GridView g = grid_view(grid, M);
+    RigidBody b;
+    b.kind = body;
+    b.center = make_float3(center3_host[0], center3_host[1], center3_host[2]);
+    b.prm = make_float3(params3_host[0], params3_host[1], params3_host[2]);
+    rigid_project_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / r, xyz, N, b, r * r, max_num_neighbors, M, n_inside);
+    FNX_LAUNCH_CHECK("rigid_project_kernel");
     return FNX_OK;
 }
 

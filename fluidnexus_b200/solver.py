@@ -134,6 +134,46 @@ class PBFSolver:
             for name in ("_xyz", "_estimate_xyz", "_buoyancy", "_force", "_velocity", "_imass", "_counts"):
                 setattr(self, name, getattr(self, name)[mask].contiguous())
 
+    # -- rigid coupling (gm_fluid.py:1023-1105, 1241-1289) ---------------------------------------------------------
+    def set_rigid_body(self, kind, center, rigid_xyz, cuboid_num=None, particle_radius=None, sphere_radius=None, cylinder_radius=None,
+                       cylinder_num=None):
+        """kind in {"cuboid", "sphere", "cylinder"}; center and rigid_xyz in scaled units.  cuboid: edge = num * 2 *
+        particle_radius per axis; cylinder: height = cylinder_num[1] * 2 * particle_radius (check_inside_rigid_body)."""
+        assert kind in ("cuboid", "sphere", "cylinder")
+        self.rigid_body = kind
+        self._rigid_xyz = torch.as_tensor(rigid_xyz, dtype=torch.float32).to(self.dev).contiguous()
+        self._rigid_center = (C.c_float * 3)(*[float(c) for c in center])
+        if kind == "cuboid":
+            prm = [n * 2.0 * particle_radius / 2.0 for n in cuboid_num]
+        elif kind == "sphere":
+            prm = [float(sphere_radius), 0.0, 0.0]
+        else:
+            prm = [float(cylinder_radius), cylinder_num[1] * 2.0 * particle_radius / 2.0, 0.0]
+        self._rigid_prm = (C.c_float * 3)(*prm)
+
+    def _rigid_project(self, pts, cap):
+        M, N = self._rigid_xyz.size(0), pts.size(0)
+        if N == 0 or M == 0:
+            return 0
+        lib = L.lib()
+        grid = torch.empty(lib.fnx_grid_bytes(M), dtype=torch.uint8, device=self.dev)
+        n_inside = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        kind = {"cuboid": 0, "sphere": 1, "cylinder": 2}[self.rigid_body]
+        with torch.cuda.device(self.dev):
+            L.check(lib.fnx_rigid_project(grid.data_ptr(), self._rigid_xyz.data_ptr(), M, pts.data_ptr(), N, kind, self._rigid_center,
+                                          self._rigid_prm, self.H, cap, n_inside.data_ptr(), self._st()))
+        return n_inside
+
+    @torch.no_grad()
+    def project_rigid_body_constraints(self):
+        """Hidden particles inside the body snap to their nearest rigid sample within H (no neighbour cap)."""
+        return self._rigid_project(self._estimate_xyz, 0)
+
+    @torch.no_grad()
+    def project_rigid_body_constraints_for_visual_particles(self):
+        """Same for the visual particles; the reference's radius() call keeps torch_cluster's default cap of 32."""
+        return self._rigid_project(self._visual_xyz, 32)
+
     # -- one simulation tick as the entries run it ---------------------------------------------------------------
     @torch.no_grad()
     def tick(self, solver_iterations=3, stable=False, use_wind=False, count_first=False):

@@ -300,6 +300,15 @@ int fnx_pbf_project_gas_constraints(void *grid, float *estimate_xyz, int32_t N, 
  * remove_invalid_particles (gm_fluid.py:864-891) thresholds with min_neighbors.  grid: fnx_grid_bytes(N) scratch. */
 int fnx_radius_graph_degree(void *grid, const float *X, int32_t N, float r, int32_t loop, int32_t max_num_neighbors,
                             int32_t *kth_scratch, int32_t *degree, fnx_stream_t stream);
+/* Rigid coupling (gm_fluid.py:1058-1105 project_rigid_body_constraints, :1241-1289 ..._for_visual_particles): every point
+ * of xyz [N,3] that lies inside the body is moved onto the nearest of the rigid-body samples rigid_xyz [M,3] found by
+ * radius(x=rigid_xyz, y=point, r, max_num_neighbors) (<= 0: no cap; ties: smaller sample index).  body 0 = cuboid
+ * (params = half edge lengths), 1 = sphere (params[0] = radius), 2 = z-axis cylinder (params = radius, half height);
+ * center3 / params3 are HOST pointers.  grid: fnx_grid_bytes(M) scratch; *n_inside (device int32, may be NULL) counts the
+ * points that were inside. */
+int fnx_rigid_project(void *grid, const float *rigid_xyz, int32_t M, float *xyz, int32_t N, int32_t body,
+                      const float *center3_host, const float *params3_host, float r, int32_t max_num_neighbors,
+                      int32_t *n_inside, fnx_stream_t stream);
 /* velocity = (estimate_xyz - xyz)/secs, zeroed (and xyz kept) where |estimate_xyz - xyz| < 1e-8, else xyz = estimate_xyz. */
 int fnx_pbf_confirm_guess(int32_t N, float *xyz, const float *estimate_xyz, float *velocity, float secs, fnx_stream_t stream);
 /* visual += secs * sum_j poly6 v_j / max(sum_j poly6, 1e-8) over radius(x=estimate_xyz, y=visual, H, K) (in place). */

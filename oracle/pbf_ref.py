@@ -379,3 +379,38 @@ def solver_tick(sp, st, solver_iterations=3, stable=False, use_wind=False, count
         solver_project_gas_constraints(sp, st)
     solver_confirm_guess_hidden_particles(sp, st)
     solver_update_visual_particles(sp, st)
+
+
+def check_inside_rigid_body(kind, center, xyz, cuboid_num=None, particle_diameter=None, sphere_radius=None, cylinder_radius=None,
+                            cylinder_num=None):
+    """gm_fluid.py:1024-1056."""
+    center = torch.as_tensor(center, dtype=xyz.dtype)
+    if kind == "cuboid":
+        half = torch.tensor([n * particle_diameter for n in cuboid_num], dtype=xyz.dtype) / 2.0
+        return torch.all((xyz >= center - half) & (xyz <= center + half), dim=1)
+    if kind == "sphere":
+        return torch.linalg.norm(xyz - center, dim=1) <= sphere_radius
+    height = cylinder_num[1] * particle_diameter
+    d2 = (xyz[:, 0] - center[0]) ** 2 + (xyz[:, 1] - center[1]) ** 2
+    return (d2 <= cylinder_radius ** 2) & (xyz[:, 2] >= center[2] - height / 2) & (xyz[:, 2] <= center[2] + height / 2)
+
+
+def project_rigid(xyz, rigid_xyz, mask_inside, r, max_num_neighbors):
+    """gm_fluid.py:1058-1105 / 1241-1289: the particles inside the body move onto their nearest rigid sample among the
+    radius() edges (scatter_min over index-ordered edges).  Returns the new positions."""
+    out = xyz.clone()
+    if int(mask_inside.sum()) == 0:
+        return out
+    inside = xyz[mask_inside]
+    e = radius(rigid_xyz, inside, r, max_num_neighbors=max_num_neighbors if max_num_neighbors else 10 ** 9)
+    if e.size(1) == 0:
+        return out
+    row, col = e[0], e[1]
+    dist2 = torch.sum((inside[row] - rigid_xyz[col]) ** 2, dim=1)
+    _, argmin = scatter_min(dist2, row, dim=0, dim_size=inside.shape[0])
+    has = argmin < row.numel()                    # (the reference assumes every inside particle has a neighbour)
+    nearest = col[argmin[has]]
+    moved = inside.clone()
+    moved[has] = inside[has] + -(inside[has] - rigid_xyz[nearest])
+    out[mask_inside] = moved
+    return out

@@ -95,3 +95,30 @@ def test_still_particles_and_neighbour_pruning(libfnx):
     assert sol._xyz.size(0) == keep and sol._velocity.size(0) == keep and sol._imass.size(0) == keep
     assert torch.equal(sol._xyz.cpu().double(), xyz[deg >= 20])
     sol.update_visual_particles()   # V == 0: no-op
+
+
+@pytest.mark.parametrize("kind", ["cuboid", "sphere", "cylinder"])
+def test_rigid_projection_matches_oracle(libfnx, kind):
+    """project_rigid_body_constraints (no cap) and ..._for_visual_particles (cap 32, index order) against the oracle's
+    radius + scatter_min restatement: same set of moved particles, same targets (bit-equal positions of rigid samples)."""
+    rng = np.random.default_rng(11)
+    center = np.array([10.0, 20.0, 5.0])
+    rigid = (center + rng.uniform(-3.0, 3.0, (4000, 3))).astype(np.float32)          # dense cloud: > 32 samples within H of most points
+    pts = (center + rng.uniform(-5.0, 5.0, (3000, 3))).astype(np.float32)
+    vis = (center + rng.uniform(-5.0, 5.0, (1500, 3))).astype(np.float32)
+    geo = dict(cuboid_num=(3, 4, 2), particle_diameter=1.0, sphere_radius=2.5, cylinder_radius=2.0, cylinder_num=(0, 5, 0))
+    sol = PBFSolver(pts, visual_xyz=vis, H=2.0)
+    sol._estimate_xyz = sol._xyz.clone()
+    sol.set_rigid_body(kind, center, rigid, cuboid_num=geo["cuboid_num"], particle_radius=0.5, sphere_radius=geo["sphere_radius"],
+                       cylinder_radius=geo["cylinder_radius"], cylinder_num=geo["cylinder_num"])
+    for attr, src, cap in (("_estimate_xyz", pts, 0), ("_visual_xyz", vis, 32)):
+        x = torch.tensor(src)
+        mask = O.check_inside_rigid_body(kind, center, x, **geo)
+        ref = O.project_rigid(x, torch.tensor(rigid), mask, 2.0, cap)
+        n = sol.project_rigid_body_constraints() if cap == 0 else sol.project_rigid_body_constraints_for_visual_particles()
+        got = getattr(sol, attr).cpu()
+        assert int(n.item()) == int(mask.sum()) and int(mask.sum()) > 20
+        assert torch.equal(got[~mask], x[~mask])
+        assert torch.allclose(got[mask], ref[mask], atol=1e-6), float((got[mask] - ref[mask]).abs().max())
+        moved = (ref[mask] != x[mask]).any(dim=1)
+        assert int(moved.sum()) > 10
