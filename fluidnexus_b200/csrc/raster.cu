@@ -14,9 +14,13 @@
 //   * the sorted instances are re-packed into a contiguous record stream; blend kernels pull each tile's span
 //     into shared memory with 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier), double buffered.
 //   * no mid-forward host sync is required (capacity hint + device-side overflow flag, checked after queuing).
-//   * backward: warp-shuffle reduction of the per-pixel partials, then vector reductions (red.global.add.v4.f32)
-//     into one 32/48-byte accumulator row per (view, Gaussian); a single fused per-Gaussian kernel turns the
-//     rows into dL/d{mean, scale, rotation, opacity, colour} summed over the views.
+//   * backward: a value-splitting warp-shuffle reduction of the per-pixel partials (12 shuffles for 9 values), then one
+//     red.global.add.f32 per value into a contiguous 32/48-byte accumulator row per (view, Gaussian); a single fused
+//     per-Gaussian kernel turns the rows into dL/d{mean, scale, rotation, opacity, colour} summed over the views.
+//   * static + dynamic streams (fnx_raster_static_prepare / _blend_merged / _backward_merged): a frozen set is binned
+//     once; per iteration only the moving Gaussians are binned (per-tile buckets sorted in shared memory, no global sort)
+//     and merged per tile; tiles without a moving instance keep their pixels; the backward starts at the tile's last
+//     moving record from a snapshot the forward took there.
 #include <cub/cub.cuh>
 
 #include "raster.cuh"
@@ -731,7 +735,7 @@ __device__ __forceinline__ uint32_t rec_slot_word(const float4 *rec, int j) {
     const float *f = reinterpret_cast<const float *>(rec);
     return __float_as_uint(C == 3 ? f[j * 12 + 9] : f[j * 8 + 7]);
 }
-// this warp's bitmask over the n (<= 128) staged records: bit set <=> the record can touch the warp's 8x4 patch
+// this warp's bitmask over the n (<= 128) staged records: bit set <=> the record can touch the warp's 8x8 patch
 template <int C>
 __device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int warp, int lane, bool use_mask, uint32_t (&words)[BATCH / 32]) {
 #pragma unroll
