@@ -100,7 +100,7 @@ class FrameState:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # Adam step count (device side: graph-replay safe)
         self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
         self.ws = {}       # number of views -> RasterWorkspace
-        self.graphs = {}   # (view ids, update) -> (CUDAGraph, outputs, gt buffer)
+        self.graphs = {}   # (view ids, update, batch, physics) -> two alternating (CUDAGraph, outputs, gt buffer, events) slots
 
 
 class PhysicalStep:
@@ -322,21 +322,28 @@ class PhysicalStep:
             ent = fr.graphs.get(key)
             if ent is None:
                 # everything that allocates or blocks happens eagerly first (workspace sizing, visual grid, scratch)
-                gt_buf = torch.empty((len(view_ids), self.C, self.H, self.W), device=self.dev)
-                gt_buf.copy_(gt, non_blocking=True)
+                gt_bufs = [torch.empty((len(view_ids), self.C, self.H, self.W), device=self.dev) for _ in range(2)]
+                gt_bufs[0].copy_(gt, non_blocking=True)
                 snap = (fr.e.clone(), fr.m.clone(), fr.v.clone(), fr.step_dev.clone())
-                self._iteration(fr, view_ids, gt_buf, update, batch, physics)  # eager warm-up (also sizes the workspace)
-                for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # undo its parameter update
+                self._iteration(fr, view_ids, gt_bufs[0], update, batch, physics)  # eager warm-up (also sizes the workspace)
+                for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):       # undo its parameter update
                     dst.copy_(src)
                 torch.cuda.synchronize(self.dev)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    out = self._iteration(fr, view_ids, gt_buf, update, batch, physics)
-                ent = (g, out, gt_buf, torch.cuda.Event(), torch.cuda.Event())
+                # The iteration is captured TWICE, once per ground-truth buffer, and the two graphs alternate: the upload
+                # of the next iteration's ground truth (copy stream) then never waits for the current iteration, which is
+                # still reading the other buffer.  Everything else the two graphs touch is the same memory.
+                slots = []
+                for gt_buf in gt_bufs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = self._iteration(fr, view_ids, gt_buf, update, batch, physics)
+                    slots.append((g, out, gt_buf, torch.cuda.Event(), torch.cuda.Event()))
+                    for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # capture does not execute, but be explicit
+                        dst.copy_(src)
+                ent = {"slots": slots, "next": 0}
                 fr.graphs[key] = ent
-                for dst, src in zip((fr.e, fr.m, fr.v, fr.step_dev), snap):   # capture does not execute, but be explicit
-                    dst.copy_(src)
-            g, out, gt_buf, ev_copied, ev_done = ent
+            g, out, gt_buf, ev_copied, ev_done = ent["slots"][ent["next"]]
+            ent["next"] ^= 1
             ws = out.get("ws")
             if ws is not None and ws.overflowed():
                 raise RuntimeError("rasterizer instance capacity exceeded inside a captured iteration; re-capture "
@@ -346,7 +353,7 @@ class PhysicalStep:
                 gt_buf.copy_(gt, non_blocking=True)
             else:
                 cs = self.copy_stream
-                cs.wait_event(ev_done)          # the previous replay of this graph has finished reading gt_buf
+                cs.wait_event(ev_done)          # the previous replay of THIS graph (two iterations ago) has finished reading gt_buf
                 with torch.cuda.stream(cs):
                     gt_buf.copy_(gt, non_blocking=True)
                     ev_copied.record(cs)
