@@ -8,7 +8,11 @@ one frame with `views` (5) cameras (FD/entries_fluid_nexus/train_physical_partic
 processes `frames_in_flight` (16) independent synthetic frames, each one iteration; the frames are sharded over the
 ranks (strong scaling: total work per step is fixed), gradients of all frames live in one flat bucket that is
 all-reduced (NCCL, sum) once per step and applied with one fused Adam launch on every rank (replicated parameters).
-value = frames_in_flight * K / T, T = max over ranks of the CUDA-event time of the K timed steps.
+Within a rank the frames are dealt to `--lanes` (4) CUDA streams (fluidnexus_b200/parallel.py:FrameLanes), every frame's iteration
+is a captured CUDA graph.  value = frames_in_flight * K / T, T = max over ranks of the CUDA-event time of the K timed steps
+(device-resident inputs); e2e = the same with the ground truth uploaded from pinned host memory every iteration and the
+loss read back every step; static_tile_cache reports both again with the static-only tile cache switched off; roofline is
+measured live on the larger blend kernel in a leg that runs the frames one after the other.
 
 Workloads:  smoke  = BASELINE config 4: P = 200k (20k fluid + 180k frozen background), C = 3, grey
 image loss, N = 28k hidden particles, 5 views 512x512 (the configuration north_star's target is quoted on);
