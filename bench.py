@@ -420,7 +420,6 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import pbf_ref as O
-    from oracle import ref_ext
     from oracle.ref_step import ReferenceTrainer
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -16,7 +16,6 @@ There is no CPU fallback and no host synchronisation inside an iteration.
 import ctypes as C
 import math
 
-import numpy as np
 import torch
 
 from . import _lib as L

@@ -11,8 +11,6 @@ and differentiable fused terms used by fluidnexus_b200.step (the reference build
     pair_distance_loss            P5     FD/utils/loss_utils.py:98-121
 All run on torch's current stream; CUDA tensors only (no CPU fallback).
 """
-import ctypes as C
-
 import torch
 
 from . import _lib as L

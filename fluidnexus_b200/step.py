@@ -18,7 +18,6 @@ evaluated once (the reference re-evaluates them per view and averages, which giv
 hand-written gather kernel (no edge lists, no autograd graph); there is no host synchronisation inside the step
 (losses stay on the device until the caller reads them).
 """
-import ctypes as C
 from dataclasses import dataclass
 
 import torch
