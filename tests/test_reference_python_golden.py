@@ -1,4 +1,4 @@
-"""The restatements against numbers the REFERENCE ITSELF computed: tests/golden/ref_python.npz was produced by importing
+"""The restatements against numbers the REFERENCE ITSELF computed: tests/golden/pyref_python.npz was produced by importing
 the reference's own pure-Python modules (utils/loss_utils.py, graphics_utils.py, general_utils.py, sh_utils.py) on the CPU
 (tools/make_python_golden.py).  CPU tests pin oracle/pbf_ref.py, the synthetic cameras and the host helpers; the GPU tests
 compare libfnx's fused kernels with the same fixtures directly."""
@@ -14,7 +14,7 @@ from fluidnexus_b200 import io as IO
 from fluidnexus_b200 import synthetic as S
 from oracle import pbf_ref as O
 
-Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python.npz"))
+Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pyref_python.npz"))
 
 
 def rel(a, b):

@@ -1,6 +1,6 @@
 """Run in the build container (needs /root/reference): imports the reference's OWN pure-Python modules on the CPU
 (FluidDynamics/utils/loss_utils.py, graphics_utils.py, general_utils.py, sh_utils.py -- none of them needs a GPU or the
-un-installable torch_cluster) and records their outputs on seeded inputs in tests/golden/ref_python.npz.  Those values pin
+un-installable torch_cluster) and records their outputs on seeded inputs in tests/golden/pyref_python.npz.  Those values pin
 oracle/pbf_ref.py's restatements of the image / distance losses, fluidnexus_b200/synthetic.py's camera matrices and the
 learning-rate schedule / colour conversion helpers (tests/test_reference_python_golden.py).  Nothing is copied from the
 reference; only numbers it computes are stored."""
@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 REF = "/root/reference/FluidDynamics"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_python.npz")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "pyref_python.npz")
 
 
 def images(C, H, W, seed):
