@@ -67,3 +67,34 @@ def test_compat_packages_export_the_reference_names():
         for n in names:
             assert n in src, (pkg, n)
     assert "distCUDA2" in open(os.path.join(compat, "simple_knn", "_C.py")).read()
+
+
+def test_hard_coded_constants_equal_the_reference_configs():
+    """StepParams defaults, bench.py's per-workload constants, the solver defaults and the background learning rates against the
+    reference's effective configs (arguments/__init__.py overridden by configs/*.json; tools/make_config_golden.py)."""
+    import sys
+    cfg = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pyref_configs.json")))
+    from fluidnexus_b200.step import StepParams
+    smoke, scalar = cfg["fluid_nexus_smoke_dynamics"], cfg["scalar_real"]
+    d = StepParams()
+    for mine, theirs in (("H", "H"), ("KNN_K", "KNN_K"), ("p0", "p0"), ("secs", "secs"), ("buoyancy_max_y", "buoyancy_max_y"),
+                         ("lambda_dssim", "lambda_dssim"), ("lambda_image", "lambda_image"), ("lambda_current_distance", "lambda_current_distance"),
+                         ("lambda_exyz", "lambda_exyz"), ("lambda_gas_constraints", "lambda_gas_constraints"),
+                         ("lambda_next_gas_constraints", "lambda_next_gas_constraints"), ("distance_threshold_visual", "distance_threshold_visual")):
+        assert getattr(d, mine) == pytest.approx(smoke[theirs]), mine
+    assert d.lr == pytest.approx(smoke["position_lr_init"])          # spatial_lr_scale 1; never rescheduled (gm_fluid.py:401-407)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for name, ref in (("smoke", smoke), ("scalar", scalar)):
+        nf, nb, C, grey, size, N, p0, bmax, thr = bench.WORKLOADS[name]
+        assert p0 == pytest.approx(ref["p0"]) and bmax == pytest.approx(ref["buoyancy_max_y"]) and thr == pytest.approx(ref["distance_threshold_visual"])
+    # the two scene families differ exactly where the workloads differ
+    assert smoke["p0"] != scalar["p0"] and smoke["buoyancy_max_y"] != scalar["buoyancy_max_y"]
+    from oracle import pbf_ref as O
+    sp = O.SolverParams()
+    assert sp.H == smoke["H"] and sp.KNN_K == smoke["KNN_K"] and sp.p0 == smoke["p0"] and sp.secs == smoke["secs"]
+    bgd = cfg["fluid_nexus_smoke_background"]
+    # the learning rates the background tests / tools train with are the reference's
+    for k, v in (("position_lr_init", 1.6e-4), ("position_lr_final", 1.6e-6), ("position_lr_delay_mult", 0.01), ("position_lr_max_steps", 30_000),
+                 ("color_lr", 2.5e-3), ("opacity_lr", 0.05), ("scaling_lr", 5e-3), ("rotation_lr", 1e-3), ("percent_dense", 0.01)):
+        assert bgd[k] == pytest.approx(v), k
