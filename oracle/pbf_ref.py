@@ -117,8 +117,10 @@ class PBFParams:
 
 
 def poly6(prm, r2):
+    """gm_fluid.py:166-169.  (The mask is cast to r2's dtype: `bool * python float` would round the constant to the default
+    dtype, fp32, inside an fp64 evaluation.)"""
     term2 = prm.H2 - r2
-    mask = r2 < prm.H2
+    mask = (r2 < prm.H2).to(r2.dtype)
     return mask * prm.poly6_term1 * (term2 ** 3)
 
 

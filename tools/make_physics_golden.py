@@ -1,0 +1,101 @@
+"""Run in the build container (needs /root/reference): executes the reference's OWN particle-physics methods
+(FluidDynamics/gaussian_splatting/gm_fluid.py: get_visual_xyz_from_nn, get_gas_constraints_from_exyz_nn,
+get_guess_hidden_particles_from_nn, get_gas_constraints_from_vel_nn_guess, project_gas_constraints, update_visual_particles,
+remove_invalid_particles) on the CPU and stores inputs + outputs in tests/golden/pyref_physics.npz.
+
+gm_fluid.py imports torch_cluster / torch_scatter / simple_knn at module top; none is installable here.  They are replaced,
+for this script only, by stub modules whose radius / radius_graph / scatter_min are the restatements in oracle/pbf_ref.py --
+so the fixture pins EVERYTHING the reference computes around the neighbour search (kernels, index conventions, scatter sums,
+the autograd chain, the solver update), while the neighbour search itself stays the documented unpinned part.  The model object
+is created without its constructor (which needs a GPU) and given exactly the attributes the methods read."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/FluidDynamics"
+OUT = os.path.join(ROOT, "tests", "golden", "pyref_physics.npz")
+sys.path.insert(0, ROOT)
+from fluidnexus_b200 import synthetic as S  # noqa: E402
+from oracle import pbf_ref as O  # noqa: E402
+
+
+def install_stubs():
+    tc = types.ModuleType("torch_cluster")
+    tc.radius = lambda x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32, **kw: O.radius(x, y, r, max_num_neighbors=max_num_neighbors)
+    tc.radius_graph = lambda x, r, batch=None, loop=False, max_num_neighbors=32, **kw: O.radius_graph(x, r, loop=loop, max_num_neighbors=max_num_neighbors)
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter_min = lambda src, index, dim=0, dim_size=None: O.scatter_min(src, index, dim=dim, dim_size=dim_size)
+    sk, skc = types.ModuleType("simple_knn"), types.ModuleType("simple_knn._C")
+    skc.distCUDA2 = lambda pts: torch.tensor(O.knn3_mean_dist2(pts.numpy()))
+    sk._C = skc
+    sys.modules.update({"torch_cluster": tc, "torch_scatter": ts, "simple_knn": sk, "simple_knn._C": skc})
+
+
+def make_model(GM, K, p0, bmax, seed):
+    hp = S.hidden_lattice(600, seed=seed, buoyancy=(0.0, 1.96, 0.0))
+    rng = np.random.default_rng(seed)
+    f = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    gm = object.__new__(GM)
+    gm.H, gm.KNN_K, gm.p0, gm.k, gm._secs, gm.scale_factor, gm.buoyancy_max_y = 2.0, K, p0, 3.0, 0.033, 100.0, bmax
+    gm.H2, gm.H6, gm.H9 = gm.H ** 2, gm.H ** 6, gm.H ** 9
+    gm.EPSILON, gm.RELAXATION, gm.K_P, gm.E_P, gm.DQ_P = 1e-8, 0.01, 0.2, 4, 0.25
+    gm.poly6_term1 = 315.0 / (64.0 * np.pi * gm.H9)
+    gm.spiky_grad_term1 = 45.0 / (np.pi * gm.H6)
+    gm.lamb_corr_denom = gm.poly6(torch.tensor(gm.DQ_P * gm.DQ_P * gm.H * gm.H, dtype=torch.float64))
+    gm.record_time, gm.min_neighbors = False, 20
+    gm._xyz, gm._estimate_xyz = f(hp.xyz), f(hp.estimate_xyz)
+    gm._buoyancy, gm._force = f(hp.buoyancy), f(rng.normal(0, 3, hp.force.shape))
+    gm._velocity = f(rng.normal(0, 5, hp.xyz.shape) + np.array([0.0, 30.0, 0.0]))
+    gm._imass = f(rng.uniform(0.8, 1.2, (hp.N, 1)))
+    gm._counts = torch.full((hp.N, 1), 2.0, dtype=torch.float64)
+    gm._particle_id = torch.arange(hp.N)
+    vis = hp.xyz[rng.choice(hp.N, 150, replace=False)] + rng.uniform(-0.4, 0.4, (150, 3))
+    gm._visual_xyz = f(vis)
+    gm._estimate_xyz_nn = (gm._estimate_xyz / gm.scale_factor).clone().requires_grad_(True)
+    return gm
+
+
+def main():
+    install_stubs()
+    # the reference allocates its scatter targets with the default dtype: run its code in fp64 end to end
+    torch.set_default_dtype(torch.float64)
+    sys.path.insert(0, REF)
+    from gaussian_splatting.gm_fluid import GaussianModel as GM
+    out = {}
+    for tag, (K, p0, bmax) in {"smoke": (100, 1.5, 0.0), "scalar": (100, 2.0, 0.8), "capped": (14, 1.5, 0.8)}.items():
+        gm = make_model(GM, K, p0, bmax, seed=5)
+        state0 = {k: getattr(gm, "_" + k).detach().numpy().copy() for k in ("xyz", "estimate_xyz", "buoyancy", "force", "velocity", "imass", "counts",
+                                                                             "visual_xyz")}
+        # ---- the differentiable terms of the training step and their gradient w.r.t. estimate_xyz_nn ----
+        rng = np.random.default_rng(1)
+        w_vis = torch.tensor(rng.normal(size=(150, 3)))
+        vis_out = gm.get_visual_xyz_from_nn()
+        p2 = gm.get_gas_constraints_from_exyz_nn()
+        Y = gm.get_guess_hidden_particles_from_nn()
+        p3 = gm.get_gas_constraints_from_vel_nn_guess()
+        loss = (vis_out * w_vis).sum() + ((p2 - 1.0) ** 2).mean() + 0.1 * ((p3 - 1.0) ** 2).mean()
+        loss.backward()
+        out.update({f"{tag}_{k}": v for k, v in state0.items()})
+        out.update({f"{tag}_K": K, f"{tag}_p0": p0, f"{tag}_bmax": bmax, f"{tag}_w_vis": w_vis.numpy(), f"{tag}_P1": vis_out.detach().numpy(),
+                    f"{tag}_P2": p2.detach().numpy(), f"{tag}_Y": Y.detach().numpy(), f"{tag}_P3": p3.detach().numpy(),
+                    f"{tag}_loss": loss.item(), f"{tag}_grad": gm._estimate_xyz_nn.grad.numpy().copy()})
+        # ---- no-grad solver pieces (in place on the model) ----
+        ret = gm.project_gas_constraints()
+        out.update({f"{tag}_proj_estimate_xyz": gm._estimate_xyz.numpy().copy(), f"{tag}_proj_force": gm._force.numpy().copy(),
+                    f"{tag}_proj_lambda_mean": ret["lambdas"], f"{tag}_proj_pratio_mean": ret["p_ratio"]})
+        gm.update_visual_particles()
+        out[f"{tag}_visual_after_update"] = gm._visual_xyz.numpy().copy()
+        n0 = gm._xyz.shape[0]
+        gm.remove_invalid_particles()
+        out[f"{tag}_kept_after_prune"] = np.int64(gm._xyz.shape[0])
+        out[f"{tag}_n0"] = np.int64(n0)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, "with", len(out), "arrays;", {k: int(out[k]) for k in out if k.endswith("kept_after_prune")})
+
+
+if __name__ == "__main__":
+    main()
