@@ -58,3 +58,33 @@ def test_solver_iteration_visual_update_and_pruning(tag):
     assert rel(st["visual_xyz"].numpy(), Z[f"{tag}_visual_after_update"]) < 1e-12
     deg = O.solver_neighbor_degree(sp, st["xyz"])
     assert int((deg >= sp.min_neighbors).sum()) == int(Z[f"{tag}_kept_after_prune"]) and st["xyz"].shape[0] == int(Z[f"{tag}_n0"])
+
+
+@pytest.mark.parametrize("tag", ["guess_plain", "guess_bmax_wind", "guess_stable"])
+def test_guess_and_confirm_equal_the_reference(tag):
+    """guess_hidden_particles / confirm_guess_hidden_particles were run by the reference in its own fp32 (they hard-wire
+    torch.float and device="cuda", redirected to the CPU by the generator script); the fp64 oracle agrees to fp32 rounding."""
+    wind = bool(Z[f"{tag}_wind"])
+    sp = O.SolverParams(buoyancy_max_y=float(Z[f"{tag}_bmax"]), buoyancy_decay_rate=float(Z[f"{tag}_decay"]), alpha=-0.2,
+                        wind_force=(0.3, 0.0, 0.1), wind_power=2.0)
+    sp.wind_force_max = 0.3
+    st = {k: _t(tag, k) for k in ("xyz", "velocity", "force", "buoyancy")}
+    st["estimate_xyz"], st["counts"] = st["xyz"].clone(), torch.ones(st["xyz"].shape[0], 1, dtype=torch.float64)
+    O.solver_guess_hidden_particles(sp, st, stable=bool(Z[f"{tag}_stable"]), use_wind=wind)
+    for k in ("velocity", "force", "buoyancy", "estimate_xyz", "counts"):
+        ref = Z[f"{tag}_after_{k}"]
+        if np.abs(ref).max() == 0:
+            assert float(st[k].abs().max()) == 0, k
+        else:
+            assert rel(st[k].numpy(), ref) < 2e-6, (k, rel(st[k].numpy(), ref))
+    st["estimate_xyz"] = torch.tensor(Z[f"{tag}_moved"], dtype=torch.float64)
+    st["xyz"] = _t(tag, "xyz")
+    O.solver_confirm_guess_hidden_particles(sp if not bool(Z[f"{tag}_stable"]) else sp, st)
+    assert rel(st["xyz"].numpy(), Z[f"{tag}_confirm_xyz"]) < 1e-7
+    v_ref = Z[f"{tag}_confirm_velocity"]
+    still = np.all(v_ref == 0, axis=1)
+    assert still[::3].all() and not still[1::3].all()                       # the particles left in place, and only they, stop
+    assert float(st["velocity"][torch.tensor(still)].abs().max()) == 0
+    # (e - x)/secs in fp32 loses ~ |x| * eps / |e - x| relative accuracy: compare with the matching absolute tolerance
+    err = np.abs(st["velocity"].numpy() - v_ref).max()
+    assert err < 3e-5 * np.abs(Z[f"{tag}_xyz"]).max() / 0.033, err

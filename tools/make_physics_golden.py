@@ -35,6 +35,33 @@ def install_stubs():
     sys.modules.update({"torch_cluster": tc, "torch_scatter": ts, "simple_knn": sk, "simple_knn._C": skc})
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def cuda_as_cpu():
+    """The reference hard-wires device="cuda" / .cuda() in some methods; inside this context those land on the CPU."""
+    names = ["zeros", "ones", "tensor", "empty", "full", "arange", "zeros_like", "ones_like", "normal", "rand", "randn"]
+    saved = {n: getattr(torch, n) for n in names}
+
+    def wrap(fn):
+        def inner(*a, **k):
+            if str(k.get("device", "")).startswith("cuda"):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return inner
+    saved_cuda = torch.Tensor.cuda
+    try:
+        for n in names:
+            setattr(torch, n, wrap(saved[n]))
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        yield
+    finally:
+        for n in names:
+            setattr(torch, n, saved[n])
+        torch.Tensor.cuda = saved_cuda
+
+
 def make_model(GM, K, p0, bmax, seed):
     hp = S.hidden_lattice(600, seed=seed, buoyancy=(0.0, 1.96, 0.0))
     rng = np.random.default_rng(seed)
@@ -93,6 +120,28 @@ def main():
         gm.remove_invalid_particles()
         out[f"{tag}_kept_after_prune"] = np.int64(gm._xyz.shape[0])
         out[f"{tag}_n0"] = np.int64(n0)
+    # ---- guess_hidden_particles / confirm_guess_hidden_particles (device="cuda" redirected to the CPU) ----
+    for tag, (bmax, stable, wind, decay) in {"guess_plain": (0.0, False, False, 0.0), "guess_bmax_wind": (0.8, False, True, 0.9),
+                                              "guess_stable": (0.8, True, False, 0.0)}.items():
+        torch.set_default_dtype(torch.float32)   # these two methods hard-wire torch.float: run them in the reference's own precision
+        gm = make_model(GM, 100, 1.5, bmax, seed=9)
+        for k in ("xyz", "estimate_xyz", "velocity", "force", "buoyancy", "imass", "counts", "visual_xyz"):
+            setattr(gm, "_" + k, getattr(gm, "_" + k).float())
+        gm._gravity = torch.tensor([0.0, -9.8, 0.0]).reshape((1, 3))
+        gm.alpha, gm.buoyancy_decay_rate = -0.2, decay
+        gm.wind_force, gm.wind_force_max, gm.wind_power = torch.tensor([0.3, 0.0, 0.1]).reshape((1, 3)), 0.3, 2.0
+        out.update({f"{tag}_{k}": getattr(gm, "_" + k).detach().numpy().copy() for k in ("xyz", "velocity", "force", "buoyancy")})
+        with cuda_as_cpu():
+            gm.guess_hidden_particles(stable=stable, use_wind=wind)
+            after_guess = {k: getattr(gm, "_" + k).detach().numpy().astype(np.float64).copy() for k in ("velocity", "force", "buoyancy", "estimate_xyz", "counts")}
+            # a solver-like displacement, with every third particle left exactly where it was
+            gm._estimate_xyz = gm._estimate_xyz + 0.05 * torch.sin(gm._xyz)
+            gm._estimate_xyz[::3] = gm._xyz[::3]
+            moved = gm._estimate_xyz.numpy().copy()
+            gm.confirm_guess_hidden_particles()
+        out.update({f"{tag}_after_{k}": v for k, v in after_guess.items()})
+        out.update({f"{tag}_moved": moved, f"{tag}_confirm_xyz": gm._xyz.numpy().copy(), f"{tag}_confirm_velocity": gm._velocity.numpy().copy(),
+                    f"{tag}_bmax": bmax, f"{tag}_stable": stable, f"{tag}_wind": wind, f"{tag}_decay": decay})
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "with", len(out), "arrays;", {k: int(out[k]) for k in out if k.endswith("kept_after_prune")})
 
