@@ -88,3 +88,24 @@ def test_guess_and_confirm_equal_the_reference(tag):
     # (e - x)/secs in fp32 loses ~ |x| * eps / |e - x| relative accuracy: compare with the matching absolute tolerance
     err = np.abs(st["velocity"].numpy() - v_ref).max()
     assert err < 3e-5 * np.abs(Z[f"{tag}_xyz"]).max() / 0.033, err
+
+
+def test_gradient_cache_and_adam_configuration_equal_the_reference():
+    """P6 / P7 (gm_fluid.py:330-355, 401-430): per-view gradients summed, times 1/batch, torch.optim.Adam with lr =
+    position_lr_init * spatial_lr_scale and eps = 1e-15; update_learning_rate_current never changes the rate.  This is what
+    oracle/step_ref.py inlines and what the flat-bucket all-reduce + fnx_adam_step reproduce."""
+    assert float(Z["plumb_lr"]) == pytest.approx(1.6e-4) and float(Z["plumb_lr_after"]) == pytest.approx(1.6e-4) and float(Z["plumb_eps"]) == 1e-15
+    e = torch.tensor(Z["plumb_e0"]).clone().requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [e], "lr": 1.6e-4, "name": "estimate_xyz_nn"}], lr=0.0, eps=1e-15)     # as oracle/step_ref.py builds it
+    vg = Z["plumb_view_grads"]
+    for it in range(2):
+        cache = torch.zeros_like(e)
+        for v in range(3):
+            cache += torch.tensor(vg[it, v])
+        e.grad = cache * (1.0 / 3)
+        assert np.array_equal(e.grad.numpy(), Z[f"plumb_batch_grad{it}"])
+        opt.step()
+        assert np.allclose(e.detach().numpy(), Z[f"plumb_e{it + 1}"], rtol=0, atol=1e-9)
+    # the first Adam step moves every coordinate by ~lr against the sign of its gradient
+    d = Z["plumb_e1"] - Z["plumb_e0"]
+    assert np.allclose(np.abs(d), 1.6e-4, rtol=1e-3) and np.all(np.sign(d) == -np.sign(Z["plumb_batch_grad0"]))

@@ -142,6 +142,34 @@ def main():
         out.update({f"{tag}_after_{k}": v for k, v in after_guess.items()})
         out.update({f"{tag}_moved": moved, f"{tag}_confirm_xyz": gm._xyz.numpy().copy(), f"{tag}_confirm_velocity": gm._velocity.numpy().copy(),
                     f"{tag}_bmax": bmax, f"{tag}_stable": stable, f"{tag}_wind": wind, f"{tag}_decay": decay})
+    # ---- P6 / P7: gradient cache over the view loop, 1/batch, Adam as training_setup_current configures it ----
+    torch.set_default_dtype(torch.float32)
+    gm = make_model(GM, 100, 1.5, 0.0, seed=13)
+    gm._estimate_xyz = gm._estimate_xyz.float()
+    gm.spatial_lr_scale = 1.0
+
+    class OptimArgs:
+        position_lr_init, position_lr_final, position_lr_delay_mult, position_lr_max_steps = 1.6e-4, 1.6e-6, 0.01, 30_000
+    rng = np.random.default_rng(21)
+    with cuda_as_cpu():
+        gm.training_setup_current(OptimArgs)
+        out["plumb_e0"] = gm._estimate_xyz_nn.detach().numpy().copy()
+        out["plumb_lr"] = gm.optimizer.param_groups[0]["lr"]
+        out["plumb_eps"] = gm.optimizer.param_groups[0]["eps"]
+        view_grads = rng.normal(0, 1e-2, (2, 3) + tuple(gm._estimate_xyz_nn.shape)).astype(np.float32)     # 2 iterations x 3 views
+        for it in range(2):
+            gm.update_learning_rate_current(it + 1)                # computes a rate but never assigns it (gm_fluid.py:401-407)
+            gm.zero_gradient_cache_current()
+            for v in range(3):
+                gm._estimate_xyz_nn.grad = torch.tensor(view_grads[it, v])
+                gm.cache_gradient_current()
+                gm.optimizer.zero_grad(set_to_none=True)
+            gm.set_batch_gradient_current(3)
+            out[f"plumb_batch_grad{it}"] = gm._estimate_xyz_nn.grad.numpy().copy()
+            gm.optimizer.step()
+            out[f"plumb_e{it + 1}"] = gm._estimate_xyz_nn.detach().numpy().copy()
+        out["plumb_lr_after"] = gm.optimizer.param_groups[0]["lr"]
+    out["plumb_view_grads"] = view_grads
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, "with", len(out), "arrays;", {k: int(out[k]) for k in out if k.endswith("kept_after_prune")})
 
