@@ -13,7 +13,15 @@ Restates, op for op, from the reference (FD = FluidDynamics):
   P6 grad cache / batch average              gm_fluid.py:409-430
   P7 Adam(eps=1e-15), lr never updated       gm_fluid.py:330-355,401-407
 
-PARITY UNPINNED for the neighbour search: the reference calls `torch_cluster.radius / radius_graph`
+PINNED by the reference's own code, for everything except the neighbour search: tools/make_physics_golden.py and
+tools/make_python_golden.py import the reference's modules from /root/reference on the CPU (gm_fluid.py with torch_cluster /
+torch_scatter / simple_knn replaced by stubs that call `radius` / `radius_graph` / `scatter_min` below; utils/loss_utils.py
+as it is) and store what ITS methods compute -- P1-P3 with their gradient, project_gas_constraints, update_visual_particles,
+remove_invalid_particles, guess / confirm, the gradient cache and Adam set-up, l1 / ssim / distance_loss -- in
+tests/golden/pyref_physics.npz and pyref_python.npz; tests/test_reference_physics_golden.py and
+tests/test_reference_python_golden.py hold this file to those numbers (1e-12 in fp64).
+
+PARITY UNPINNED for the neighbour search itself: the reference calls `torch_cluster.radius / radius_graph`
 (torch-cluster==1.6.3, fluid_nexus.yml:397) and `torch_scatter.scatter_min` (torch-scatter==2.1.2, :399), third-party
 CUDA extensions that are neither vendored in /root/reference nor installed here, and the reference has no tests
 or golden vectors for this path.  `radius` / `radius_graph` below restate the published
