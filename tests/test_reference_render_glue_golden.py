@@ -29,3 +29,14 @@ def test_mirror_hands_the_rasterizer_what_the_reference_glue_does(name):
             assert v.shape == ref.shape and np.array_equal(v, ref), (name, k)
         else:
             assert np.array_equal(np.asarray(v), ref), (name, k, v, ref)
+
+
+def test_synthetic_camera_equals_the_reference_camera_class():
+    """G4: the attributes the pipes and entries read, against an instance of the reference's own scene/camera.py:Camera."""
+    c = S.SyntheticCamera(Z["camera__R"], Z["camera__T"], float(Z["camera__fov"][0]), float(Z["camera__fov"][1]), int(Z["camera__hw"][1]),
+                          int(Z["camera__hw"][0]), "view_00", timestamp=float(Z["camera__timestamp"]))
+    for k in ("world_view_transform", "projection_matrix", "full_proj_transform", "camera_center"):
+        assert np.array_equal(getattr(c, k).numpy(), Z[f"camera__{k}"]), k
+    assert (c.z_near, c.z_far) == tuple(Z["camera__znear_zfar"]) and (c.image_height, c.image_width) == tuple(Z["camera__hw"])
+    # the ground truth the entries upload each iteration is the clamped input image (camera.py:57-70)
+    assert np.array_equal(np.clip(Z["camera__image_in"], 0.0, 1.0), Z["camera__original_image"])

@@ -125,6 +125,21 @@ def main():
         for name, (fn, kw) in CASES.items():
             for k, v in run_case(fns[fn], gm, cam, kw).items():
                 out[f"{name}__{k}"] = v
+        # ---- the reference's Camera class itself (scene/camera.py:14-110; kornia's meshgrid is only needed for rays) ----
+        kornia = types.ModuleType("kornia")
+        kornia.create_meshgrid = lambda *a, **k: None
+        sys.modules["kornia"] = kornia
+        from scene.camera import Camera
+        R = np.array([[0.36, 0.48, -0.8], [-0.8, 0.6, 0.0], [0.48, 0.64, 0.6]])
+        T = np.array([0.1, -0.2, 1.3])
+        img = torch.rand(3, 24, 32, generator=torch.Generator().manual_seed(3)) * 1.4 - 0.2        # exercises the clamp
+        c = Camera(colmap_id=1, R=R, T=T, FoVx=0.69, FoVy=0.55, image=img, gt_alpha_mask=None, image_name="view_00", uid=0,
+                   real_image=img.clone(), timestamp=0.5)
+        out.update(camera__R=R, camera__T=T, camera__image_in=img.numpy(), camera__original_image=c.original_image.numpy(),
+                   camera__hw=np.array([c.image_height, c.image_width]), camera__world_view_transform=c.world_view_transform.numpy(),
+                   camera__projection_matrix=c.projection_matrix.numpy(), camera__full_proj_transform=c.full_proj_transform.numpy(),
+                   camera__camera_center=c.camera_center.numpy(), camera__znear_zfar=np.array([c.z_near, c.z_far]),
+                   camera__fov=np.array([c.FoVx, c.FoVy]), camera__timestamp=c.timestamp)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, len(out), "arrays")
 
