@@ -109,3 +109,9 @@ def test_gradient_cache_and_adam_configuration_equal_the_reference():
     # the first Adam step moves every coordinate by ~lr against the sign of its gradient
     d = Z["plumb_e1"] - Z["plumb_e0"]
     assert np.allclose(np.abs(d), 1.6e-4, rtol=1e-3) and np.all(np.sign(d) == -np.sign(Z["plumb_batch_grad0"]))
+
+
+def test_the_dynamics_model_class_shares_the_physics():
+    """The FluidNexus scenes (smoke, ball) train gm_dynamics.GaussianModel, ScalarReal gm_fluid.GaussianModel; the generator ran
+    P1-P3 of both classes on the same state and found them bit-identical, so one set of fixtures covers both."""
+    assert bool(Z["gm_dynamics_bit_identical"])

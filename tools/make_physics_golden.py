@@ -120,6 +120,20 @@ def main():
         gm.remove_invalid_particles()
         out[f"{tag}_kept_after_prune"] = np.int64(gm._xyz.shape[0])
         out[f"{tag}_n0"] = np.int64(n0)
+    # ---- the FluidNexus scenes use gm_dynamics.GaussianModel (same physics code, gm_dynamics.py:1014-1030,1269-1320,1453-1498):
+    #      its methods must give what gm_fluid's gave ----
+    ply = types.ModuleType("plyfile")
+    ply.PlyData, ply.PlyElement = object, object
+    sys.modules["plyfile"] = ply
+    from gaussian_splatting.gm_dynamics import GaussianModel as GD
+    same = True
+    for tag, (K, p0, bmax) in {"smoke": (100, 1.5, 0.0), "scalar": (100, 2.0, 0.8), "capped": (14, 1.5, 0.8)}.items():
+        gd = make_model(GD, K, p0, bmax, seed=5)
+        same &= bool(np.array_equal(gd.get_visual_xyz_from_nn().detach().numpy(), out[f"{tag}_P1"]))
+        same &= bool(np.array_equal(gd.get_gas_constraints_from_exyz_nn().detach().numpy(), out[f"{tag}_P2"]))
+        same &= bool(np.array_equal(gd.get_gas_constraints_from_vel_nn_guess().detach().numpy(), out[f"{tag}_P3"]))
+    assert same, "gm_dynamics and gm_fluid disagree on P1-P3"
+    out["gm_dynamics_bit_identical"] = np.bool_(same)
     # ---- guess_hidden_particles / confirm_guess_hidden_particles (device="cuda" redirected to the CPU) ----
     for tag, (bmax, stable, wind, decay) in {"guess_plain": (0.0, False, False, 0.0), "guess_bmax_wind": (0.8, False, True, 0.9),
                                               "guess_stable": (0.8, True, False, 0.0)}.items():
