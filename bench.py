@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- FluidDynamics physical-particle train-step throughput (render + image loss + physics + backward + Adam).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fnx|reference] [--workload smoke|scalar|c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fnx|reference] [--workload smoke|scalar|c2|ball]
 
 Metric (BASELINE.json): train-step iterations per second.  One *iteration* = one pass of the reference's hot loop for
 one frame with `views` (5) cameras (FD/entries_fluid_nexus/train_physical_particle.py:330-420).  One bench *step*
@@ -16,7 +16,8 @@ measured live on the larger blend kernel in a leg that runs the frames one after
 
 Workloads:  smoke  = BASELINE config 4: P = 200k (20k fluid + 180k frozen background), C = 3, grey
 image loss, N = 28k hidden particles, 5 views 512x512 (the configuration north_star's target is quoted on);
-scalar = config 3 (P = V = 150k fluid, C = 1);  c2 = config 2 sizes (50k, 400x400).
+scalar = config 3 (P = V = 150k fluid, C = 1);  c2 = config 2 sizes (50k, 400x400);  ball = config 5 (P = 300k: 30k fluid +
+270k frozen background including the 30k-Gaussian ball that hangs in the plume).
 """
 import argparse
 import json
@@ -38,6 +39,9 @@ WORKLOADS = {
     "smoke": (20_000, 180_000, 3, True, 512, 28_000, 1.5, 0.0, 0.002),
     "scalar": (150_000, 0, 1, False, 512, 28_000, 2.0, 0.8, 0.00625),
     "c2": (50_000, 0, 3, False, 400, 28_000, 1.5, 0.0, 0.002),
+    # BASELINE config 5 (FluidNexus-Ball, configs/fluid_nexus_ball_dynamics.json: gm_dynamics + render_dynamics, p0 1.5, thr 0.002):
+    # 300k = 30k fluid + 270k frozen background of which 30k form the ball hanging in the plume
+    "ball": (30_000, 270_000, 3, True, 512, 28_000, 1.5, 0.0, 0.002),
     "tiny": (2_000, 4_000, 3, True, 128, 3_000, 1.5, 0.0, 0.004),
 }
 
@@ -48,6 +52,8 @@ def build_frames(workload, n_frames, device, need_device=True):
     nf, nb, C, grey, size, N, p0, bmax, thr = WORKLOADS[workload]
     cams = S.make_cameras(5, size, device=device if need_device else "cpu")
     bg = S.background_gaussians(nb, C, seed=1) if nb else None
+    if workload == "ball":
+        bg = S.cat_sets(S.background_gaussians(nb - 30_000, C, seed=1), S.ball_gaussians(30_000, C, seed=4))
     frames = []
     for f in range(n_frames):
         fluid = S.fluid_gaussians(nf, C, seed=100 + f)
@@ -120,15 +126,37 @@ def dist_info():
 # ======================================================================================================================
 # our arm
 # ======================================================================================================================
+def pin_to_gpu_numa_node(local):
+    """Run this rank (and allocate its pinned host buffers) on the CPU cores next to its GPU: with 8 ranks uploading ground
+    truth at once, buffers that sit on the other socket halve the host->device rate.  Best effort, silent when /sys is absent."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devid = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_fnx(args):
     import torch.distributed as dist
     from fluidnexus_b200 import _lib as L
     from fluidnexus_b200 import rasterizer as R
-    from fluidnexus_b200.parallel import FlatBucket, FrameLanes, assign_items
-    from fluidnexus_b200.step import FrameState, PhysicalStep, StepParams
+    from fluidnexus_b200.parallel import FlatBucket, FrameLanes, plan_items
+    from fluidnexus_b200.step import LOSS_ROW, FrameState, PhysicalStep, StepParams
     rank, world, local = dist_info()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
@@ -139,53 +167,68 @@ def run_fnx(args):
     lanes = FrameLanes(lambda k: PhysicalStep(cams, cfg["C"], prm, device=dev), args.lanes, dev)
     ps = lanes.steps[0]
     N = cfg["N"]
-    # replicated parameters / Adam state / gradient bucket of ALL frames, flat (fluidnexus_b200/parallel.py)
-    fb = FlatBucket(G, N, dev)
-    E, M, Vv, DE = fb.param, fb.exp_avg, fb.exp_avg_sq, fb.grad
-    by_frame, physics_frames = assign_items(G, len(views), world, rank)
+    # where the (frame, view) items live; flat parameter / moment / gradient / loss buffers of all frames in flight
+    plan = plan_items(G, len(views), world, rank)
+    assert FlatBucket.N_LOSS == LOSS_ROW
+    fb = FlatBucket(G, N, dev, plan)
+    by_frame, physics_frames, shared = plan.by_frame, plan.physics_frames, set(plan.shared)
     mine = sorted(by_frame)
+
+    def make_state(f):
+        return FrameState(frames[f]["hidden"], frames[f]["visual"], frames[f]["fluid"], bg, device=dev, prm=prm)
+
     states = {}
     for f in mine:
-        fr = FrameState(frames[f]["hidden"], frames[f]["visual"], frames[f]["fluid"], bg, device=dev, prm=prm)
-        if f in physics_frames:
-            E[f].copy_(fr.e)
-        fr.e, fr.m, fr.v, fr.de = fb.views(f)               # views into the flat, replicated buffers
+        fr = make_state(f)
+        if f not in physics_frames:
+            fr.e.zero_()                                    # the owner's value arrives with the broadcast below
+        fr.bind_flat(*fb.views(f), loss_row=fb.losses[f])   # aliases into the flat buffers
         states[f] = fr
     fb.broadcast_params_from_owners()
     # ground truth: the same scene with fluid positions perturbed by N(0, 0.002), rendered once by the rasterizer
-    gts_dev, gts_pinned = {}, {}
-    for f in mine:
-        fr = states[f]
+    def make_gt(f, fr, view_ids):
         rng = np.random.default_rng(300 + f)
         pert = fr.means3D.clone()
         pert[:fr.V] += torch.tensor(rng.normal(0, 0.002, (fr.V, 3)), dtype=torch.float32, device=dev)
         ctx, img, _, _ = R.raster_forward(cfg["C"], ps.bg, pert, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None, ps.view_all,
                                           ps.proj_all, ps.tan_fov_x, ps.tan_fov_y, ps.H, ps.W, speculative=False)
-        gts_dev[f] = img[by_frame[f]].clone()
-        gts_pinned[f] = gts_dev[f].cpu().pin_memory()
         del ctx
+        return img[view_ids].clone()
+
+    gts_dev, gts_pinned = {}, {}
+    for f in mine:
+        gts_dev[f] = make_gt(f, states[f], by_frame[f])
+        gts_pinned[f] = gts_dev[f].cpu().pin_memory()
     torch.cuda.synchronize()
     step_no = [0]
-
     use_graph = [not args.no_graph]
+    serial = [False]   # True: all frames on the current stream, one after the other (single-lane / kernel-duration legs)
+    lo, hi = fb.shared_range()
 
-    serial = [False]   # True: all frames on the current stream, one after the other (the kernel-duration leg)
-
-    def one_step(e2e):
+    def one_step(e2e, frames_now=None):
+        """One bench step = one iteration of every frame in flight.  Frames that live wholly on this rank carry their
+        Adam update inside the (captured) iteration; frames whose views straddle ranks exchange their gradient slots with
+        ONE all-reduce and every rank applies the same update to its replica (parallel.py).  The per-frame loss table is
+        all-reduced every step (rank 0 logs the job's loss)."""
+        todo = mine if frames_now is None else frames_now
+        fb.begin_step()
         # e2e: ground truth comes from pinned HOST memory every iteration (the reference uploads it at :325)
-        call = lambda step, f: step.step(states[f], by_frame[f], gts_pinned[f] if e2e else gts_dev[f], update=False,
+        call = lambda step, f: step.step(states[f], by_frame[f], gts_pinned[f] if e2e else gts_dev[f], update=f not in shared,
                                          batch=len(views), graph=use_graph[0], physics=f in physics_frames)
-        outs = [call(ps, f) for f in mine] if serial[0] else lanes.run(mine, call)
+        outs = [call(ps, f) for f in todo] if serial[0] else lanes.run(todo, call)
         last = outs[-1] if outs else None
-        fb.all_reduce()
         step_no[0] += 1
-        L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
-                                  prm.adam_eps, step_no[0], torch.cuda.current_stream(dev).cuda_stream))
-        if e2e and last is not None:
+        if hi > lo:
+            fb.all_reduce()
+            E, DE, M, Vv = fb.param[lo:hi], fb.grad[lo:hi], fb.exp_avg[lo:hi], fb.exp_avg_sq[lo:hi]
+            L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
+                                      prm.adam_eps, step_no[0], torch.cuda.current_stream(dev).cuda_stream))
+        table = fb.all_reduce_losses()
+        if e2e:
             # device -> host read of the step's loss, every step, pipelined by one step: the copy into pinned memory is queued
             # behind the step, and the host waits for (and reads) the PREVIOUS step's value, so the GPU never idles on it
             k = step_no[0] % 2
-            loss_pinned[k].copy_(ps.total_loss(last).reshape(1), non_blocking=True)
+            loss_pinned[k].copy_(ps.total_loss_from_rows(table, len(views)).mean().reshape(1), non_blocking=True)
             loss_ev[k].record()
             prev, pending[0] = pending[0], k
             return drain(prev)
@@ -201,7 +244,8 @@ def run_fnx(args):
         loss_ev[k].synchronize()
         return float(loss_pinned[k][0])
 
-    def timed(k, e2e):
+    def interval(k, e2e, frames_now=None):
+        """EXACTLY k steps between barrier + synchronize on both sides, CUDA-event time, max over ranks -> ms."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -209,7 +253,7 @@ def run_fnx(args):
         e0.record()
         out = None
         for _ in range(k):
-            out = one_step(e2e)
+            out = one_step(e2e, frames_now)
         if e2e:                                   # the last step's loss is read inside the timed region too
             out, pending[0] = drain(pending[0]), None
         e1.record()
@@ -220,7 +264,34 @@ def run_fnx(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
+    def timed(k, e2e, frames_now=None, min_seconds=None, min_intervals=5):
+        """A leg = repeated intervals of exactly k steps until it lasted `min_seconds` (>= min_intervals intervals); the
+        reported time is the MEDIAN interval.  Every rank takes the same decisions (the interval time is the max over ranks)."""
+        min_seconds = args.min_leg_seconds if min_seconds is None else min_seconds
+        if e2e:
+            for _ in range(2):
+                one_step(True, frames_now)
+            drain(pending[0]); pending[0] = None
+        ms_all, out, total = [], None, 0.0
+        while len(ms_all) < min_intervals or (total < min_seconds * 1e3 and len(ms_all) < 400):
+            ms, out = interval(k, e2e, frames_now)
+            ms_all.append(ms)
+            total += ms
+        med = float(np.median(ms_all))
+        return med, out, {"intervals": len(ms_all), "steps_per_interval": k, "total_s": round(total / 1e3, 3),
+                          "min_ms": round(min(ms_all), 4), "median_ms": round(med, 4), "max_ms": round(max(ms_all), 4)}
+
+    def snapshot():
+        return (fb.param.clone(), fb.exp_avg.clone(), fb.exp_avg_sq.clone(), {f: states[f].step_dev.clone() for f in states}, step_no[0])
+
+    def restore(snap):
+        fb.param.copy_(snap[0]); fb.exp_avg.copy_(snap[1]); fb.exp_avg_sq.copy_(snap[2])
+        for f, sd in snap[3].items():
+            states[f].step_dev.copy_(sd)
+        step_no[0] = snap[4]
+
     # count our own kernel launches of one bench step (eager), then warm up (captures the CUDA graphs)
+    snap0 = snapshot()
     graph_flag, use_graph[0] = use_graph[0], False
     one_step(False)
     torch.cuda.synchronize()
@@ -230,22 +301,33 @@ def run_fnx(args):
     use_graph[0] = graph_flag
     for _ in range(max(args.warmup, 3)):
         one_step(False)
+    restore(snap0)
+
+    # ---- parity of the sharded job with a single-rank run of the same frames (hard assertion) ----
+    parity = verify_sharding(args, locals()) if (world > 1 or args.verify) else None
+
     # ---- timed region: device-resident inputs ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, out = timed(args.steps, False)
+    ms, out, leg_value = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
     launches = launches_per_step * args.steps
     R_per_iter = float(out["ws"].num_rendered()) if out and "ws" in out else 0.0
     for f in mine:
         assert not any(w_.overflowed() for w_ in states[f].ws.values()), "instance capacity overflow inside the timed region"
     # ---- end to end: pinned host ground truth uploaded every iteration + loss read back every step ----
-    for _ in range(2):
-        one_step(True)
-    drain(pending[0]); pending[0] = None
-    ms_e2e, last_loss = timed(args.steps, True)
+    ms_e2e, last_loss, leg_e2e = timed(args.steps, True)
     assert last_loss is not None and math.isfinite(last_loss), "end-to-end leg did not produce a finite loss"
+    # ---- one lane (frames one after the other on one stream, still graph replays) and single-frame latency: what real,
+    #      time-sequential training sees ----
+    serial[0] = True
+    ms_l1, _, leg_l1 = timed(args.steps, False, min_seconds=min(1.0, args.min_leg_seconds))
+    lat_ms, leg_lat = None, None
+    if not plan.shared:                       # (every rank then owns whole frames; the condition is the same on all ranks)
+        ms_lat, _, leg_lat = timed(args.steps * 4, False, frames_now=[mine[0]], min_seconds=min(1.0, args.min_leg_seconds))
+        lat_ms = ms_lat / (args.steps * 4)
+    serial[0] = False
 
     # ---- kernel durations: the same steps once more, eager, with CUDA events around the library's launches ----
     import ctypes as C
@@ -257,31 +339,35 @@ def run_fnx(args):
     one_step(False)
     lib.fnx_profile_enable((1 << nsec) - 1)
     lib.fnx_profile_collect(None, None)
-    ms_prof, _ = timed(args.steps, False)
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        one_step(False)
+    torch.cuda.synchronize()
     tot = (C.c_float * nsec)(); cnt = (C.c_int32 * nsec)()
     L.check(lib.fnx_profile_collect(tot, cnt))
     lib.fnx_profile_enable(0)
     use_graph[0], serial[0] = graph_flag, False
     value = G * args.steps / (ms / 1e3)
     e2e = G * args.steps / (ms_e2e / 1e3)
+    value_lanes1 = G * args.steps / (ms_l1 / 1e3)
     ws_last = out["ws"] if out and "ws" in out else None
     tile_state = ws_last.tile_state() if ws_last is not None and hasattr(ws_last, "tile_state") else None
     # ---- A/B: the same timed region with every tile blended every iteration (static tile cache off) ----
     cache_on = any(getattr(w_, "static_tile_cache", False) for f in mine for w_ in states[f].ws.values())
+    cache_on_any = torch.tensor([int(cache_on)], device=dev)
+    if world > 1:
+        dist.all_reduce(cache_on_any, op=dist.ReduceOp.MAX)
     value_nocache = e2e_nocache = None
-    if cache_on:
+    if int(cache_on_any.item()) and not args.no_ab:
         for f in mine:
             for w_ in states[f].ws.values():
                 w_.static_tile_cache = False
             states[f].graphs.clear()
         for _ in range(3):
             one_step(False)
-        ms_nc, _ = timed(args.steps, False)
+        ms_nc, _, _ = timed(args.steps, False, min_seconds=min(1.0, args.min_leg_seconds))
         value_nocache = G * args.steps / (ms_nc / 1e3)
-        for _ in range(2):
-            one_step(True)
-        drain(pending[0]); pending[0] = None
-        ms_nc_e2e, _ = timed(args.steps, True)
+        ms_nc_e2e, _, _ = timed(args.steps, True, min_seconds=min(1.0, args.min_leg_seconds))
         e2e_nocache = G * args.steps / (ms_nc_e2e / 1e3)
 
     if rank != 0:
@@ -300,6 +386,7 @@ def run_fnx(args):
     ib = names.index(kname)
     n_launch = max(1, cnt[ib])
     t_launch = tot[ib] / 1e3 / n_launch                               # seconds per launch (5 views each)
+    nv_local = len(by_frame[mine[-1]]) if mine else len(views)        # views per launch on this rank
     # ALGORITHMIC bytes of one launch: the records the kernel has to read once + the per-pixel state of the
     # tiles it has to touch + (backward) the accumulator rows it writes once.  With the static/dynamic streams the
     # per-tile record counts come from the tile state of the last forward (fnx_raster_read_tiles).
@@ -313,58 +400,77 @@ def run_fnx(args):
         bwd_rec = float(np.minimum(ts["tile_last"], ts["tile_dyn_last"])[dyn_t].sum())
         pix = float(dyn_t.sum()) * 256.0
         bytes_fwd = fwd_rec * rec + pix * (4 * Cc + 4 + 8 + 16)        # colour, depth, final_T + n_contrib, snapshot
-        bytes_bwd = bwd_rec * rec + pix * (4 * Cc + 8 + 16) + len(views) * cfg["nf"] * acc
+        bytes_bwd = bwd_rec * rec + pix * (4 * Cc + 8 + 16) + nv_local * cfg["nf"] * acc
         if not cache_on:
             fwd_rec = float(ts["tile_last"].sum())
-            bytes_fwd = fwd_rec * rec + len(views) * HW * (4 * Cc + 4 + 8) + pix * 16
+            bytes_fwd = fwd_rec * rec + nv_local * HW * (4 * Cc + 4 + 8) + pix * 16
         tile_info = {"tiles": int(ts["tile_src"].size), "tiles_with_dynamic_instances": int(dyn_t.sum()),
                      "records_blended_fwd": fwd_rec, "records_walked_bwd": bwd_rec,
                      "records_in_merged_spans": float((ts["end"] - ts["begin"])[dyn_t].sum())}
     else:
-        bytes_fwd = R_per_iter * rec + len(views) * HW * (4 * Cc + 4 + 8)
-        bytes_bwd = R_per_iter * rec + len(views) * HW * (4 * Cc + 8) + len(views) * P * acc
+        bytes_fwd = R_per_iter * rec + nv_local * HW * (4 * Cc + 4 + 8)
+        bytes_bwd = R_per_iter * rec + nv_local * HW * (4 * Cc + 8) + nv_local * P * acc
     bytes_launch = bytes_bwd if kname == "blend_bwd" else bytes_fwd
     achieved = bytes_launch / t_launch / 1e9 if t_launch > 0 else 0.0
     traffic, issue = None, None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][kname + "_kernel"]
-        traffic = prof["dram_bytes_per_launch"]
-        # the bound that actually binds: warp instructions issued (ncu smsp__inst_executed.sum of the same capture) over the live
-        # launch duration, against 148 SMs x 4 schedulers x 1 instruction / clock at the sampled SM clock
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        peak_issue = 148 * 4 * sm_mhz * 1e6
-        issue = {"warp_instructions_per_launch": prof["warp_instructions_per_launch"], "achieved_ginst_s": round(prof["warp_instructions_per_launch"] / t_launch / 1e9, 1),
-                 "peak_ginst_s": round(peak_issue / 1e9, 1), "frac": round(prof["warp_instructions_per_launch"] / t_launch / peak_issue, 4)}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of THIS workload
+        # at one GPU (profiles/traffic.json names the capture file); not attached to multi-GPU lines (different launch shape)
+        if world == 1:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][kname + "_kernel"]
+            traffic = prof["dram_bytes_per_launch"]
+            # the bound that actually binds: warp instructions issued (ncu smsp__inst_executed.sum of the same capture) over the live
+            # launch duration, against 148 SMs x 4 schedulers x 1 instruction / clock at the sampled SM clock
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_issue = 148 * 4 * sm_mhz * 1e6
+            issue = {"warp_instructions_per_launch": prof["warp_instructions_per_launch"], "achieved_ginst_s": round(prof["warp_instructions_per_launch"] / t_launch / 1e9, 1),
+                     "peak_ginst_s": round(peak_issue / 1e9, 1), "frac": round(prof["warp_instructions_per_launch"] / t_launch / peak_issue, 4),
+                     "capture": prof.get("capture")}
     except Exception:
         pass
+    if plan.shared:
+        par = (f"views of {len(plan.shared)} frame(s) split over {world} ranks (rank r renders a block of the frame's 5 views, the frame's "
+               "owner adds the view-independent physics terms), ONE NCCL all-reduce of the frame's gradient slot per step, replicated Adam")
+    elif world > 1:
+        par = (f"whole frames dealt round-robin to {world} ranks; a frame's gradient is complete on its rank (no gradient exchange, "
+               "local Adam), ONE NCCL all-reduce of the per-frame loss table per step")
+    else:
+        par = "single GPU"
     line = {
         "metric": "FluidDynamics train-step iters/sec (render+physics+bwd)", "value": round(value, 3), "unit": "iters/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={Cc}, "
-                               f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration",
-                   "frames_in_flight": G, "lanes_per_gpu": lanes.n, "views_per_iteration": 5, "parallelism": f"frames sharded over {world} rank(s), "
-                   "one NCCL all-reduce of the flat gradient bucket per step" if world > 1 else "single GPU",
+        "config": {"workload": workload_text(args.workload, cfg),
+                   "frames_in_flight": G, "lanes_per_gpu": lanes.n, "views_per_iteration": 5, "parallelism": par,
                    "instances_per_iteration": R_per_iter,
+                   "timing": f"median of >= 5 intervals of exactly {args.steps} steps (barrier + synchronize on both sides, CUDA events, max "
+                             f"over ranks), repeated until the leg lasted >= {args.min_leg_seconds} s",
                    "l2": f"no explicit flush: {G} frames cycle between iterations and one iteration touches "
                          f"~{((tile_info['records_in_merged_spans'] if tile_info else R_per_iter) * rec + 5 * HW * (16 * Cc + 44)) / 1e6:.0f} MB "
                          "(record spans + images, ground truth, gradient and SSIM maps), so a frame's data has left the 126 MB L2 "
                          "by the time its next iteration starts"},
         "e2e": {"value": round(e2e, 3), "unit": "iters/s",
-                "h2d_bytes_per_step": int(sum(len(v) for v in by_frame.values()) * Cc * HW * 4),
-                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "h2d_bytes_per_step": int(G * len(views) * Cc * HW * 4),   # whole job: every (frame, view) image, fp32
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4), "leg": leg_e2e},
         "gpu_launches": int(launches),
+        "launches_per_iteration": round(launches_per_step / max(1, len(mine)), 1),
         "clocks": clocks,
+        "leg": leg_value,
+        "value_lanes1": round(value_lanes1, 3),
+        "latency_one_frame_ms": None if lat_ms is None else round(lat_ms, 4),
+        "latency_legs": {"lanes1": leg_l1, "one_frame": leg_lat,
+                         "what": "value_lanes1: the same frames one after the other on ONE stream (graph replays); latency_one_frame_ms: "
+                                 "one frame iterated alone -- what the reference's time-sequential training sees (SURVEY.md D4)"},
         "roofline": {"bound": "hbm", "kernel": kname + "_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 5), "traffic": traffic, "algorithmic_bytes_per_launch": int(bytes_launch),
                      "peak_source": peak_src,
                      "ms_per_launch": round(t_launch * 1e3, 4), "launches_timed": int(n_launch),
                      "share_of_step": round(tot[ib] / sum(tot[i] for i in range(nsec)), 4),
                      "issue_rate": issue, "tile_state": tile_info,
-                     "note": "instruction-issue bound blend loop (ncu: issue-active 70-80 %) on a mostly L2-resident working set; "
-                             "see DESIGN.md 6"},
-        "sections_ms_per_step": {names[i]: round(tot[i] / args.steps, 4) for i in range(nsec) if cnt[i]},
+                     "note": "instruction-issue bound blend loop on a mostly L2-resident working set; see DESIGN.md 6"},
+        "sections_ms_per_step": {names[i]: round(tot[i] / prof_steps, 4) for i in range(nsec) if cnt[i]},
         "cuda_graph": bool(graph_flag),
+        "sharding_parity": parity,
+        "numa_cpus_bound": numa_cpus,
         "static_tile_cache": {"on": bool(cache_on), "value_with_cache_off": None if value_nocache is None else round(value_nocache, 3),
                               "e2e_with_cache_off": None if e2e_nocache is None else round(e2e_nocache, 3),
                               "what": "tiles that hold no fluid instance keep the pixels of the static-only render (frozen background + "
@@ -377,6 +483,65 @@ def run_fnx(args):
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def verify_sharding(args, env):
+    """Hard check (every world size > 1, or --verify): after K optimiser steps the parameters of the sharded job equal those
+    of a single-rank run of the same frames from the same state.  Rank 0 re-runs up to 3 frames alone -- all 5 views, physics
+    and Adam on one GPU, no collective -- and compares them with the job's result gathered from the frames' owners.
+    Tolerance: the blend backward sums with float atomics (like the reference's), so two runs of the SAME configuration differ
+    in the last bits and Adam (eps 1e-15) turns a sign flip of a ~0 gradient component into a 2*lr step; the assertion is
+    max|delta| <= max(1e-6, 4 x the run-to-run difference of the single-rank run measured here) and
+    at most 1e-4 of the components beyond 1e-6."""
+    import torch.distributed as dist
+    fb, plan, states, one_step, snapshot, restore = env["fb"], env["plan"], env["states"], env["one_step"], env["snapshot"], env["restore"]
+    ps, dev, rank, world, views, prm = env["ps"], env["dev"], env["rank"], env["world"], env["views"], env["prm"]
+    K = args.verify_steps
+    snap = snapshot()
+    for _ in range(K):
+        one_step(False)
+    got = fb.gather_params()                       # [G, N, 3] on every rank
+    loss_job = fb.losses_global.clone()
+    restore(snap)
+    # frames to re-run on rank 0: prefer frames that other ranks own / share
+    cand = sorted(range(plan.n_frames), key=lambda f: (plan.ranks_of[f] == [0], f))[:3]
+    res = None
+    if rank == 0:
+        deltas, noise, frac_bad, loss_rel = [], [], [], []
+        for f in cand:
+            runs = []
+            for rep in range(2):
+                fr = env["make_state"](f)
+                fr.e.copy_(snap[0][f])             # the job's initial parameters of this frame
+                gt = env["make_gt"](f, fr, views)
+                for _ in range(K):
+                    o = ps.step(fr, views, gt, update=True, batch=len(views), graph=False, physics=True)
+                runs.append((fr.e.clone(), fr.loss_row.clone()))
+                del fr
+            d = (got[f] - runs[0][0]).abs()
+            deltas.append(float(d.max())); frac_bad.append(float((d > 1e-6).float().mean()))
+            noise.append(float((runs[0][0] - runs[1][0]).abs().max()))
+            l_one = float(ps.total_loss_from_rows(runs[0][1], len(views)))
+            l_job = float(ps.total_loss_from_rows(loss_job[f], len(views)))
+            loss_rel.append(abs(l_job - l_one) / max(abs(l_one), 1e-12))
+        tol = max(1e-6, 4.0 * max(noise))
+        ok = max(deltas) <= tol and max(frac_bad) <= 1e-4 and max(loss_rel) < 1e-4
+        res = {"frames_checked": cand, "owners": [plan.ranks_of[f] for f in cand], "steps": K, "max_abs_param_delta": max(deltas),
+               "run_to_run_noise_single_rank": max(noise), "tolerance": tol, "fraction_beyond_1e-6": max(frac_bad),
+               "loss_rel_delta_last_step": max(loss_rel), "lr": prm.lr, "ok": bool(ok)}
+        print("sharding parity:", json.dumps(res), file=sys.stderr)
+    flag = torch.tensor([1 if (res is None or res["ok"]) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    assert int(flag.item()) == 1, f"sharded job differs from the single-rank run: {res}"
+    torch.cuda.synchronize()
+    return res
+
+
+def workload_text(name, cfg):
+    P = cfg["nf"] + cfg["nb"]
+    return (f"{name}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={cfg['C']}, "
+            f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration")
 
 
 def cpu_baseline(args, cfg, frame, bg, cams):
@@ -416,64 +581,87 @@ def cpu_baseline(args, cfg, frame, bg, cams):
 # reference arm
 # ======================================================================================================================
 def run_reference(args):
+    """The reference's own step on this box: its unmodified CUDA rasterizer (oracle/_ref) on 1 GPU + its physics-loss path on
+    the host cores, driven by its OWN Python (stock GaussianModel / render pipe / loss_utils / loop body, oracle/ref_step.py:
+    StockTrainer) when that is staged, else by the restatement (ReferenceTrainer)."""
     rank, world, local = dist_info()
     if rank != 0:
         return
     from oracle import pbf_ref as O
-    from oracle.ref_step import ReferenceTrainer
+    from oracle import ref_python as RP
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    ncores = os.cpu_count() or 1
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(ncores)
     cams, bg, frames, cfg = build_frames(args.workload, 1, dev)
     prm = O.PBFParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], distance_threshold_visual=cfg["thr"])
     fr = frames[0]
-    tr = ReferenceTrainer(prm, fr["hidden"], fr["visual"], fr["fluid"], bg, cfg["C"], cfg["grey"], device=dev)
-    # ground truth through the reference rasterizer itself
-    gts = []
-    with torch.no_grad():
-        rng = np.random.default_rng(300)
-        pert = torch.tensor(fr["fluid"].xyz + rng.normal(0, 0.002, fr["fluid"].xyz.shape), dtype=torch.float32, device=dev)
-        for cam in cams:
-            gts.append(tr.render(cam, pert).detach().cpu())
     with_dist = cfg["nf"] <= 20_000  # dense cdist is O(V^2): feasible up to ~20k particles only (SURVEY.md D8)
-    K, W = args.steps, max(args.warmup, 1)
-    # a reference iteration costs seconds (host physics): bound the run
-    K = min(K, args.ref_max_steps)
-    for _ in range(min(W, 2)):
-        tr.iteration(cams, gts, with_distance=with_dist)
+    rng = np.random.default_rng(300)
+    pert = torch.tensor(fr["fluid"].xyz + rng.normal(0, 0.002, fr["fluid"].xyz.shape), dtype=torch.float32, device=dev)
+    rx = torch.tensor(fr["fluid"].xyz, dtype=torch.float32, device=dev)
+    stock = RP.staged() and not args.ref_restated
+    if stock:
+        from oracle.ref_step import StockTrainer
+        zeros = [torch.zeros(cfg["C"], cfg["size"], cfg["size"]) for _ in cams]
+        tr = StockTrainer(prm, fr["hidden"], fr["visual"], fr["fluid"], bg, cfg["C"], cams, zeros, with_distance=with_dist)
+        gts = [tr.render_gt(k, pert).cpu() for k in range(len(cams))]      # ground truth through the reference rasterizer itself
+        tr.set_ground_truth(gts)
+        iteration = tr.iteration
+        gpu_part = lambda gg: tr.gpu_part(gg, rx)
+        glue = f"stock: loop body of {tr.where[0]}:{tr.where[1][0]}-{tr.where[1][1]} executed unchanged"
+    else:
+        from oracle.ref_step import ReferenceTrainer
+        tr = ReferenceTrainer(prm, fr["hidden"], fr["visual"], fr["fluid"], bg, cfg["C"], cfg["grey"], device=dev)
+        with torch.no_grad():
+            gts = [tr.render(cam, pert).detach().cpu() for cam in cams]
+        iteration = lambda: tr.iteration(cams, gts, with_distance=with_dist)
+        gpu_part = lambda gg: tr.gpu_part(cams, gg, rx)
+        glue = "restated (oracle/ref_step.py:ReferenceTrainer): reference Python not staged"
+    # a reference iteration costs seconds (host physics): honour --steps / --warmup as far as --ref-max-seconds allows
+    W = max(1, args.warmup)
+    t0 = time.time()
+    iteration()
     torch.cuda.synchronize()
+    t_first = time.time() - t0
+    W_done = 1
+    while W_done < W and (W_done + 1) * t_first < 0.25 * args.ref_max_seconds:
+        iteration(); W_done += 1
+    torch.cuda.synchronize()
+    K = max(1, min(args.steps, int(args.ref_max_seconds / max(t_first, 1e-3))))
     t0 = time.time()
     for _ in range(K):
-        tr.iteration(cams, gts, with_distance=with_dist)
+        iteration()
     torch.cuda.synchronize()
     dt = time.time() - t0
     value = K / dt
-    P = cfg["nf"] + cfg["nb"]
     # extra information: the GPU-only part of the reference iteration (its CUDA rasterizer fwd+bwd + torch image losses,
     # 5 views), CUDA-event timed -- the part that libfnx's rasterizer and loss kernels replace one for one
     gts_gpu = [g.to(dev) for g in gts]
-    rx = torch.tensor(fr["fluid"].xyz, dtype=torch.float32, device=dev)
     for _ in range(3):
-        tr.gpu_part(cams, gts_gpu, rx)
+        gpu_part(gts_gpu)
     torch.cuda.synchronize()
+    n_gp = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10):
-        tr.gpu_part(cams, gts_gpu, rx)
+    for _ in range(n_gp):
+        gpu_part(gts_gpu)
     e1.record()
     torch.cuda.synchronize()
-    gpu_part_ms = e0.elapsed_time(e1) / 10
+    gpu_part_ms = e0.elapsed_time(e1) / n_gp
     line = {
         "impl": "reference", "metric": "FluidDynamics train-step iters/sec (render+physics+bwd)", "value": round(value, 4),
-        "unit": "iters/s", "n_gpus": 1, "steps": K, "warmup": min(W, 2), "ms_per_step": round(dt / K * 1e3, 2),
+        "unit": "iters/s", "n_gpus": 1, "steps": K, "warmup": W_done, "ms_per_step": round(dt / K * 1e3, 2),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={cfg['C']}, "
-                               f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration",
+        "config": {"workload": workload_text(args.workload, cfg),
                    "frames_in_flight": 1, "views_per_iteration": 5,
-                   "what": "unmodified reference CUDA rasterizer (oracle/_ref) on 1 GPU + torch image losses on the GPU + "
-                           "physics terms P1-P4 restated in torch on the host cores (torch_cluster not installable); "
-                           f"dense-cdist distance_loss {'on' if with_dist else 'OFF (O(V^2))'}"},
+                   "steps_requested": args.steps, "warmup_requested": args.warmup,
+                   "steps_note": None if (K == args.steps and W_done == W) else
+                   f"clamped: one reference iteration takes {t_first:.1f} s (host-side physics); --ref-max-seconds {args.ref_max_seconds:g}",
+                   "glue": glue,
+                   "what": "unmodified reference CUDA rasterizer (oracle/_ref) on 1 GPU + the reference's image losses on the GPU + its "
+                           "physics terms P1-P4 on the host cores (torch_cluster -- third party, not installable here -- replaced by the "
+                           f"host-side radius search of oracle/pbf_ref.py); dense-cdist distance_loss {'on' if with_dist else 'OFF (O(V^2))'}"},
         "cpu_baseline": {"value": round(value, 4), "unit": "iters/s", "cores": ncores, "kind": "reference",
                          "sample": f"{K} full iterations (5 views each) of one frame"},
         "e2e": {"value": round(value, 4), "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -491,8 +679,14 @@ def main():
     ap.add_argument("--workload", default="smoke", choices=list(WORKLOADS))
     ap.add_argument("--frames-in-flight", type=int, default=16)
     ap.add_argument("--lanes", type=int, default=4, help="CUDA streams per GPU that independent frames are dealt to")
-    ap.add_argument("--ref-max-steps", type=int, default=6)
+    ap.add_argument("--ref-max-seconds", type=float, default=150.0,
+                    help="reference arm: clamp --steps so that the timed region stays below this (an iteration costs seconds)")
+    ap.add_argument("--min-leg-seconds", type=float, default=2.0, help="every timed leg repeats its K-step interval until it lasted this long")
+    ap.add_argument("--verify", action="store_true", help="run the sharded-vs-single-rank parity check at 1 GPU too")
+    ap.add_argument("--verify-steps", type=int, default=3)
+    ap.add_argument("--no-ab", action="store_true", help="skip the static-tile-cache A/B legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-restated", action="store_true", help="reference arm: use the restated glue even when the reference's Python is staged")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     claim_stdout()

@@ -52,6 +52,10 @@ def _dev_f32(x, dev):
     return t.to(dev).contiguous()
 
 
+LOSS_ROW = 16      # floats per frame in the loss table (FrameState.loss_row)
+MAX_ROW_VIEWS = 5  # views whose l1 / ssim fit into the row
+
+
 class FrameState:
     """Per-frame state the reference keeps in gm_fluid.GaussianModel, laid out for the fused step.
 
@@ -92,7 +96,10 @@ class FrameState:
         self.kthX, self.kthY, self.kthV = z(N, dt=torch.int32), z(N, dt=torch.int32), z(V, dt=torch.int32)
         self.p, self.pn, self.gp, self.gpn = z(N), z(N), z(N), z(N)
         self.num, self.den, self.dDist = z(V, 3), z(V), z(V, 3)
-        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)  # gas, next_gas, exyz, dist
+        # loss row of this frame: [gas, next_gas, exyz, dist | l1 of this process' k-th view (5) | ssim of the k-th view (5) | pad]
+        # (one row of parallel.FlatBucket.losses when the frame is part of a sharded job: bind_flat)
+        self.loss_row = torch.zeros(LOSS_ROW, dtype=torch.float32, device=dev)
+        self.scalars = self.loss_row[:4]
         self.cap_flag = torch.zeros(2, dtype=torch.int32, device=dev)   # "max_num_neighbors binds" flags of P2 / P3
         self.vis_grid_built = False
         self.zero_dmeans = None
@@ -100,6 +107,16 @@ class FrameState:
         self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
         self.ws = {}       # number of views -> RasterWorkspace
         self.graphs = {}   # (view ids, update, batch, physics) -> two alternating (CUDAGraph, outputs, gt buffer, events) slots
+
+    def bind_flat(self, param, exp_avg, exp_avg_sq, grad, loss_row=None):
+        """Alias the trainable state into slots of flat buffers (parallel.FlatBucket.views(f)); the current parameter values
+        are kept.  Must be called before the first step (captured graphs hold the pointers)."""
+        assert not self.graphs, "bind_flat() after an iteration was captured"
+        param.copy_(self.e)
+        self.e, self.m, self.v, self.de = param, exp_avg, exp_avg_sq, grad
+        if loss_row is not None:
+            loss_row.zero_()
+            self.loss_row, self.scalars = loss_row, loss_row[:4]
 
 
 class PhysicalStep:
@@ -246,7 +263,8 @@ class PhysicalStep:
                    grad_range=(0, fr.V) if fr.Pb > 0 else None)
         return ws
 
-    def image_loss(self, images, gt, batch):
+    def image_loss(self, images, gt, batch, fr: FrameState = None):
+        """Fused L1 + SSIM (+ grey conversion) and dL/dimage.  With `fr` the per-view means land in the frame's loss row."""
         prm, lib = self.prm, self.lib
         V, Cc, H, W = images.shape
         key = (V, Cc, H, W)
@@ -255,6 +273,8 @@ class PhysicalStep:
                                        torch.empty(V, device=self.dev), torch.empty(V, device=self.dev),
                                        torch.empty((V, Cc, H, W), device=self.dev))
         scratch, l1, ss, g = self._loss_scratch[key]
+        if fr is not None and V <= MAX_ROW_VIEWS:
+            l1, ss = fr.loss_row[4:4 + V], fr.loss_row[4 + MAX_ROW_VIEWS:4 + MAX_ROW_VIEWS + V]
         w_l1 = (1.0 - prm.lambda_dssim) * prm.lambda_image / batch
         w_ss = prm.lambda_dssim * prm.lambda_image / batch
         L.check(lib.fnx_image_loss(V, Cc, H, W, images.data_ptr(), gt.data_ptr(), int(prm.grey), w_l1, w_ss, g.data_ptr(),
@@ -293,7 +313,7 @@ class PhysicalStep:
         out = {}
         if len(view_ids):
             ws = self.render(fr, view_ids)
-            l1, ss, g = self.image_loss(ws.color, gt, batch)
+            l1, ss, g = self.image_loss(ws.color, gt, batch, fr)
             dmeans = ws.backward(g)["means3D"]
             out.update(l1=l1, ssim=ss, images=ws.color, radii=ws.radii, ws=ws)
         else:
@@ -360,6 +380,16 @@ class PhysicalStep:
             g.replay()
             ev_done.record(main)
             return out
+
+    def total_loss_from_rows(self, rows, batch):
+        """The same from loss rows [..., LOSS_ROW] (FrameState.loss_row; summed over ranks when a frame's views are
+        sharded): `batch` = number of views of the frame's iteration."""
+        prm = self.prm
+        l1 = rows[..., 4:4 + MAX_ROW_VIEWS].sum(-1)
+        ss = rows[..., 4 + MAX_ROW_VIEWS:4 + 2 * MAX_ROW_VIEWS].sum(-1)
+        img = ((1.0 - prm.lambda_dssim) * prm.lambda_image * l1 + prm.lambda_dssim * prm.lambda_image * (batch - ss)) / batch
+        return (img + prm.lambda_current_distance * rows[..., 3] + prm.lambda_exyz * rows[..., 2]
+                + prm.lambda_gas_constraints * rows[..., 0] + prm.lambda_next_gas_constraints * rows[..., 1])
 
     def total_loss(self, out, batch=None):
         """The reference's per-view `loss`, averaged over the views (device scalar)."""

@@ -170,6 +170,25 @@ def background_gaussians(P, channels, seed=1, cams=None, min_views=3):
     return GaussianSet(xyz, scales, _rotations(rng, P), opacity, colors)
 
 
+BALL_CENTER = PLUME_CENTER + np.array([0.0, 0.32, 0.0])   # the rigid ball hangs in the plume (FluidNexus-Ball)
+BALL_RADIUS = 0.05
+
+
+def ball_gaussians(P, channels, seed=4, center=BALL_CENTER, radius=BALL_RADIUS):
+    """The ball of the FluidNexus-Ball scenes as the frozen background set holds it after train_background: an opaque shell
+    of small Gaussians (gm_dynamics.load_ply, FD/gaussian_splatting/gm_dynamics.py:1702-1744; there is no separate rigid
+    object at training time)."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(P, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    xyz = center + d * (radius * (1.0 - 0.08 * rng.uniform(0, 1, (P, 1))))
+    scales = np.exp(rng.uniform(-5.6, -4.6, (P, 3)))
+    opacity = rng.uniform(0.6, 0.95, (P, 1))
+    base = np.array([0.8, 0.25, 0.2])[:channels] if channels == 3 else np.array([0.6])
+    colors = np.clip(base + rng.normal(0, 0.05, (P, channels)), 0, 1)
+    return GaussianSet(xyz, scales, _rotations(rng, P), opacity, colors)
+
+
 def random_gaussians(P, channels, seed=0, spread=0.25, log_scale=(-5.0, -3.2)):
     """Small generic test scene in front of the default cameras."""
     rng = np.random.default_rng(seed)

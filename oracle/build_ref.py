@@ -13,6 +13,14 @@ vendored glm include path, no extra flags), KNN/setup.py.  The reference's own
 build system is NOT run; we hand the same source list to torch's ninja JIT
 builder with an explicit build directory.
 
+`stage_python()` additionally compiles the reference's *Python* (FluidDynamics/{arguments,gaussian_splatting,helpers,renderer,scene,
+utils,entries_*}/*.py and the two rasterizer wrapper packages) to SOURCELESS bytecode under ``oracle/_ref/FluidDynamics`` and
+``oracle/_ref/pkgs`` (py_compile of the files where they lie; no source text is written anywhere), copies the JSON configs
+(data), and stores the hot-loop bodies of the entry scripts -- `train()` is one long function, so the statements of its
+`for itr in ...` loops are cut out of the parsed module and compiled as they are -- as marshalled code objects in
+``oracle/_ref/FluidDynamics/_loop_bodies.marshal``.  That is what lets the `-m gpu` tests and bench.py's reference arm execute
+the reference's own, unmodified Python on the GPU box, where /root/reference does not exist.
+
 Only tests/, bench.py's reference/cpu_baseline legs and
 __graft_entry__.build()/smoke() may use what this produces.  The product
 (fluidnexus_b200) never imports it.
@@ -85,6 +93,103 @@ def build(keys=None, verbose=False):
     return built
 
 
+FD = "/root/reference/FluidDynamics"
+PY_OUT = os.path.join(OUT, "FluidDynamics")
+PKG_OUT = os.path.join(OUT, "pkgs")
+PY_DIRS = ["arguments", "gaussian_splatting", "helpers", "renderer", "scene", "utils", "entries_fluid_nexus", "entries_scalar_real"]
+WRAPPERS = {"diff_gaussian_rasterization_ch3": "submodules/gaussian_rasterization_ch3/diff_gaussian_rasterization_ch3/__init__.py",
+            "diff_gaussian_rasterization_ch1": "submodules/gaussian_rasterization_ch1/diff_gaussian_rasterization_ch1/__init__.py"}
+# entry script -> {name: how to find the loop inside train()}: "nested" = the `for itr` loop inside `for cur_time_index`,
+# "top" = the first `for itr` loop directly in train()
+LOOPS = {
+    "entries_fluid_nexus/train_physical_particle.py": {"fluid_nexus_physical_current": "nested", "fluid_nexus_physical_first": "top"},
+    "entries_scalar_real/train_physical_particle.py": {"scalar_real_physical_current": "nested", "scalar_real_physical_first": "top"},
+    "entries_fluid_nexus/train_visual_particle.py": {"fluid_nexus_visual_current": "nested"},
+    "entries_scalar_real/train_visual_particle.py": {"scalar_real_visual_current": "nested"},
+}
+
+
+def _loop_body_code(path, which):
+    """The statements of one optimisation loop of train(), up to (not including) its first top-level `if` (the periodic
+    np.save / report blocks that follow the optimiser step), compiled unchanged."""
+    import ast
+    tree = ast.parse(open(path).read(), filename=path)
+    train = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "train")
+
+    def is_itr_loop(n):
+        if not isinstance(n, ast.For):
+            return False
+        t = n.target
+        return isinstance(t, ast.Name) and t.id == "itr"
+
+    def find(nodes, nested):
+        for n in nodes:
+            if is_itr_loop(n) and not nested:
+                return n
+            if isinstance(n, ast.For) and isinstance(n.target, ast.Name) and n.target.id == "cur_time_index":
+                if nested:
+                    return find(n.body, False)
+        return None
+    loop = find(train.body, which == "nested")
+    if loop is None:
+        raise KeyError(f"{which} itr loop not found in {path}")
+    body = []
+    for st in loop.body:
+        if isinstance(st, ast.If):
+            break
+        body.append(st)
+    mod = ast.Module(body=body, type_ignores=[])
+    return compile(mod, path, "exec"), (loop.lineno, body[-1].end_lineno)
+
+
+def stage_python(verbose=False):
+    """Sourceless bytecode of the reference's Python + configs + loop bodies -> oracle/_ref (see the module docstring)."""
+    if not os.path.isdir(FD):
+        return False
+    import marshal
+    import py_compile
+    import shutil
+    n = 0
+    for d in PY_DIRS:
+        for root, _, files in os.walk(os.path.join(FD, d)):
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                src = os.path.join(root, f)
+                rel = os.path.relpath(src, FD)
+                dst = os.path.join(PY_OUT, rel + "c")
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                py_compile.compile(src, cfile=dst, dfile=os.path.join("FluidDynamics", rel), doraise=True,
+                                   invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+                n += 1
+    for pkg, rel in WRAPPERS.items():
+        dst = os.path.join(PKG_OUT, pkg, "__init__.pyc")
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        py_compile.compile(os.path.join(FD, rel), cfile=dst, dfile=os.path.join("FluidDynamics", rel), doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        n += 1
+    os.makedirs(os.path.join(PY_OUT, "configs"), exist_ok=True)
+    for f in os.listdir(os.path.join(FD, "configs")):
+        if f.endswith(".json"):
+            shutil.copyfile(os.path.join(FD, "configs", f), os.path.join(PY_OUT, "configs", f))
+    bodies, where = {}, {}
+    for rel, loops in LOOPS.items():
+        for name, which in loops.items():
+            code, lines = _loop_body_code(os.path.join(FD, rel), which)
+            bodies[name] = marshal.dumps(code)
+            where[name] = (rel, lines)
+    with open(os.path.join(PY_OUT, "_loop_bodies.marshal"), "wb") as fh:
+        marshal.dump({"bodies": bodies, "where": where, "python": sys.version_info[:2]}, fh)
+    if verbose:
+        print(f"staged {n} bytecode files, {len(bodies)} loop bodies:", where)
+    return True
+
+
+def python_staged():
+    return os.path.exists(os.path.join(PY_OUT, "_loop_bodies.marshal"))
+
+
 if __name__ == "__main__":
-    keys = sys.argv[1:] or None
+    keys = [k for k in sys.argv[1:] if k in TARGETS] or None
     print("built:", build(keys, verbose=True))
+    print("python staged:", stage_python(verbose=True))

@@ -67,5 +67,31 @@ class RefRaster:
         return dict(means2D=m2, colors=col, opacity=op, means3D=m3, cov3D=cov, scales=sc, rotations=rot)
 
 
+def carve_geom(buf, P):
+    """The reference's own per-Gaussian state out of its opaque geomBuffer.  GeometryState::fromChunk layout
+    (R3/cuda_rasterizer/rasterizer_impl.cu:144-160): depths f32[P], clamped bool[3P], radii i32[P], means2D f32[2P], cov3D
+    f32[6P], conic_opacity f32[4P], ... each aligned to 128 B from the chunk's own address.  Returns numpy
+    (depth [P], means2D [P,2], conic_opacity [P,4])."""
+    import numpy as np
+    base = buf.data_ptr()
+    off = 0
+
+    def take(nbytes):
+        nonlocal off
+        start = ((base + off + 127) // 128) * 128 - base
+        off = start + nbytes
+        return start
+
+    o_depth = take(4 * P)
+    take(3 * P)
+    take(4 * P)
+    o_m2 = take(8 * P)
+    take(24 * P)
+    o_co = take(16 * P)
+    raw = buf.cpu().numpy()
+    f = lambda o, n: raw[o:o + 4 * n].view(np.float32).copy()
+    return f(o_depth, P), f(o_m2, 2 * P).reshape(P, 2), f(o_co, 4 * P).reshape(P, 4)
+
+
 def dist_cuda2(points):
     return load("knn").distCUDA2(points)

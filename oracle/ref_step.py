@@ -113,3 +113,138 @@ class ReferenceTrainer:
             self.opt.step()
             self.opt.zero_grad()
         return log
+
+
+# ======================================================================================================================
+# Stock glue: the reference's OWN Python (oracle/_ref/FluidDynamics, see oracle/build_ref.py:stage_python) drives the iteration
+# ======================================================================================================================
+def make_host_physics_model(model_cls):
+    """The reference keeps every tensor on cuda:0 and reaches torch_cluster's CUDA kernels from there.  torch_cluster is
+    not installable here and north_star asks for the reference's physics-loss path on the HOST cores, so the particle state
+    and the trainable tensor live on the CPU while everything the rasterizer sees lives on the GPU.  Three methods of the
+    stock model hard-wire the device; this subclass re-places their tensors and changes nothing else:
+      get_visual_xyz_from_nn              stock result, moved to the GPU (autograd-aware H2D) for the stock render pipe
+      zero_gradient_cache_current         the stock body allocates the cache with device="cuda" (gm_fluid.py:419-421)
+      (cache_/set_batch_gradient_current  are inherited: they then add / scale CPU tensors)"""
+    class HostPhysicsModel(model_cls):
+        _gpu_leaf = None
+
+        def get_visual_xyz_from_nn(self):
+            if self._gpu_leaf is not None:            # gpu_part(): positions given on the GPU, no host physics
+                return self._gpu_leaf * self.scale_factor
+            return super().get_visual_xyz_from_nn().to("cuda")
+
+        def zero_gradient_cache_current(self):
+            self._estimate_xyz_nn_grad = torch.zeros_like(self._estimate_xyz_nn)
+    return HostPhysicsModel
+
+
+class StockTrainer:
+    """bench.py's reference arm on the reference's own code: stock GaussianModel (gm_dynamics / gm_fluid) built by its
+    constructor + setup_constants on the stock JSON config, stock Camera objects holding the ground truth on the CPU,
+    stock render pipe -> the reference's wrapper package -> the compiled, unmodified reference rasterizer (oracle/_ref),
+    stock loss_utils on the GPU, stock torch.optim.Adam; one iteration = the body of the hot loop of the stock entry script,
+    executed as it is (oracle/ref_python.loop_body)."""
+
+    CASES = {3: ("fluid_nexus_smoke_dynamics", "fluid_nexus_physical_current", "render_dynamics"),
+             1: ("scalar_real", "scalar_real_physical_current", "render_fluid")}
+
+    def __init__(self, prm, hidden, visual_scaled, fluid, background, channels, cams, gts_cpu, with_distance=True, config=None):
+        import random
+        import tempfile
+
+        from . import ref_python as RP
+        RP.use_reference_python("reference")
+        from helpers.helper_gaussian import get_model
+        from helpers.helper_pipe import get_render_pipe
+        from scene.camera import Camera
+        from utils.loss_utils import distance_loss, l1_loss, l2_loss, ssim
+        cfg_name, body, pipe = self.CASES[channels]
+        cfg_name = config or cfg_name
+        args, model_args, optim_args, pipe_args = RP.parse_args(cfg_name, tempfile.mkdtemp(prefix="fnx_ref_"))
+        # the synthetic workload's constants (bench.WORKLOADS) on top of the stock config
+        optim_args.p0, optim_args.buoyancy_max_y = prm.p0, prm.buoyancy_max_y
+        optim_args.distance_threshold_visual = prm.distance_threshold_visual
+        optim_args.batch = len(cams)
+        gm = make_host_physics_model(get_model(model_args.model))(model_args.sh_degree)
+        gm.setup_constants(optim_args)
+        gm.spatial_lr_scale = 1.0
+        f32 = lambda a: torch.as_tensor(a, dtype=torch.float32)
+        gm._xyz, gm._estimate_xyz = f32(hidden.xyz), f32(hidden.estimate_xyz)
+        gm._velocity, gm._force, gm._buoyancy, gm._imass = f32(hidden.velocity), f32(hidden.force), f32(hidden.buoyancy), f32(hidden.imass)
+        gm._counts = torch.zeros((hidden.N, 1))
+        gm._visual_xyz = f32(visual_scaled)
+        gm.training_setup_current(optim_args)           # CPU Parameter: _estimate_xyz is on the CPU
+        # rendering attributes of the fluid particles and the frozen background set: on the GPU, as raw (pre-activation) values
+        dev = "cuda"
+        g = lambda s, k: f32(getattr(s, k)).to(dev)
+        gm._visual_color = g(fluid, "colors")[:, :1].contiguous() if pipe == "render_dynamics" else g(fluid, "colors")
+        gm._visual_scales, gm._visual_rotation = torch.log(g(fluid, "scales")), g(fluid, "rotations")
+        gm._visual_opacity = torch.logit(g(fluid, "opacity"))
+        if background is not None:
+            gm._gs_xyz, gm._gs_color = g(background, "xyz"), g(background, "colors")
+            gm._gs_scales, gm._gs_rotation, gm._gs_opacity = torch.log(g(background, "scales")), g(background, "rotations"), torch.logit(g(background, "opacity"))
+        elif pipe == "render_dynamics":                  # no frozen set: zero-row tensors where load_ply would have put it
+            z = lambda *sh: torch.zeros(sh, device=dev)
+            gm._gs_xyz, gm._gs_color, gm._gs_scales, gm._gs_rotation, gm._gs_opacity = z(0, 3), z(0, 3), z(0, 3), z(0, 4), z(0, 1)
+        self.gm, self.optim_args, self.pipe_args = gm, optim_args, pipe_args
+        self.render_func, self.GRsetting, self.GRzer = get_render_pipe(pipe)
+        self.background = torch.zeros(3 if pipe == "render_dynamics" else 1, device=dev)
+        self.cams = [Camera(colmap_id=k, R=c.R, T=c.T, FoVx=c.FoVx, FoVy=c.FoVy, image=gt, gt_alpha_mask=None, image_name=f"train0{k}", uid=k,
+                            real_image=gt.clone()) for k, (c, gt) in enumerate(zip(cams, gts_cpu))]
+        self.code, self.where = RP.loop_body(body)
+        self.tb = RP.NullWriter()
+        self.with_distance = with_distance
+        if not with_distance:
+            optim_args.lambda_current_distance = 0.0     # the FluidNexus body then skips the dense cdist (O(V^2) memory)
+            zero = lambda positions, threshold: torch.zeros((), device=positions.device)
+        self.ns = dict(gaussians=gm, optim_args=optim_args, random=random, cur_viewpoint_set=self.cams, render_func=self.render_func,
+                       pipe_args=pipe_args, background=self.background, GRsetting=self.GRsetting, GRzer=self.GRzer, torch=torch,
+                       l1_loss=l1_loss, ssim=ssim, distance_loss=distance_loss if with_distance else zero, l2_loss=l2_loss,
+                       tb_writer=self.tb, cur_time_index=1)
+        self.l1_loss, self.ssim = l1_loss, ssim
+        self.itr = 0
+        self.grey = pipe == "render_dynamics"
+
+    def render_gt(self, cam_index, render_xyz_gpu):
+        """Ground truth through the reference rasterizer itself (positions given in render units on the GPU)."""
+        gm = self.gm
+        gm._gpu_leaf = render_xyz_gpu
+        try:
+            with torch.no_grad():
+                pkg = self.render_func(self.cams[cam_index], gm, self.pipe_args, self.background, GRsetting=self.GRsetting, GRzer=self.GRzer,
+                                       pos_type="guess_visual_nn", scale=True)
+            return pkg["render"].detach()
+        finally:
+            gm._gpu_leaf = None
+
+    def set_ground_truth(self, gts_cpu):
+        for cam, gt in zip(self.cams, gts_cpu):
+            cam.original_image = gt.clamp(0.0, 1.0)
+
+    def iteration(self):
+        self.itr += 1
+        self.ns["itr"] = self.itr
+        exec(self.code, self.ns)
+        return self.tb.scalars
+
+    def gpu_part(self, gts_gpu, render_xyz_gpu):
+        """Only what the reference runs on the GPU for one iteration: per view the stock render pipe + stock image losses +
+        backward to the Gaussian means (no host physics, no .item()): the tightest comparison with libfnx's rasterizer + loss
+        kernels."""
+        gm, oa = self.gm, self.optim_args
+        leaf = render_xyz_gpu.detach().clone().requires_grad_(True)
+        gm._gpu_leaf = leaf
+        try:
+            for cam, gt in zip(self.cams, gts_gpu):
+                pkg = self.render_func(cam, gm, self.pipe_args, self.background, GRsetting=self.GRsetting, GRzer=self.GRzer,
+                                       pos_type="guess_visual_nn", scale=True)
+                image, gt_image = pkg["render"], gt
+                if self.grey:
+                    gt_image = torch.cat([torch.mean(gt_image, dim=0, keepdim=True)] * 3, dim=0)
+                    image = torch.cat([torch.mean(image, dim=0, keepdim=True)] * 3, dim=0)
+                loss = (1.0 - oa.lambda_dssim) * self.l1_loss(image, gt_image) * oa.lambda_image + oa.lambda_dssim * (1.0 - self.ssim(image, gt_image)) * oa.lambda_image
+                loss.backward()
+        finally:
+            gm._gpu_leaf = None
+        return leaf.grad

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fluidnexus_b200.parallel import FlatBucket, assign_items
+from fluidnexus_b200.parallel import FlatBucket, assign_items, plan_items
 
 
 def test_assignment_covers_every_item_once():
@@ -37,57 +37,84 @@ def _fake_physics_grad(f, n):
     return torch.randn(n, 3, generator=g)
 
 
+def _adam(p, g, m, v, step, lr=1e-2, b1=0.9, b2=0.999, eps=1e-15):
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    p.sub_(lr * (m / (1 - b1 ** step)) / ((v / (1 - b2 ** step)).sqrt() + eps))
+
+
 def _worker(rank, world, port, G, V, N, out):
+    """Mirrors bench.py:one_step: NO zero_grad anywhere -- a rank OVERWRITES the slots of the frames it holds items of (as
+    fnx_pbf_combine_grad does), begin_step() clears the shared slots it holds nothing of, frames wholly on one rank are updated
+    locally, shared frames after the all-reduce on every rank."""
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        by_frame, phys = assign_items(G, V, world, rank)
-        fb = FlatBucket(G, N, "cpu")
-        for f in phys:                       # owners initialise their frames' parameters
+        plan = plan_items(G, V, world, rank)
+        fb = FlatBucket(G, N, "cpu", plan)
+        for f in plan.physics_frames:        # owners initialise their frames' parameters
             fb.param[f] = torch.full((N, 3), float(f + 1))
         fb.broadcast_params_from_owners()
-        opt = torch.optim.Adam([fb.param], lr=1e-2, eps=1e-15)
-        for step in range(3):
-            fb.zero_grad()
-            for f, views in by_frame.items():
+        lo, hi = fb.shared_range()
+        for step in range(1, 4):
+            fb.begin_step()
+            for f, views in plan.by_frame.items():
                 p, m, v, g = fb.views(f)
+                part = torch.zeros(N, 3)
                 for vw in views:             # image-loss gradients of this rank's views, already scaled by 1/batch
-                    g += _fake_item_grad(f, vw, N) * (1.0 / V) * (step + 1)
-            for f in phys:                   # view-independent terms: once per frame
-                fb.views(f)[3].add_(_fake_physics_grad(f, N))
+                    part += _fake_item_grad(f, vw, N) * (1.0 / V) * step
+                if f in plan.physics_frames:  # view-independent terms: once per frame, on its owner
+                    part += _fake_physics_grad(f, N)
+                g.copy_(part)                # overwrite, like the fused step
+                if f not in plan.shared:
+                    _adam(p, g, m, v, step)
+                fb.losses[f, 0] = float(len(views))
             fb.all_reduce()
-            fb.param.grad = fb.grad.clone()
-            opt.step()
-        out[rank] = (fb.param.clone(), fb.grad.clone())
+            for f in range(lo, hi):
+                _adam(*fb.views(f)[:1], fb.grad[f], fb.exp_avg[f], fb.exp_avg_sq[f], step)
+            table = fb.all_reduce_losses()
+        out[rank] = (fb.gather_params().clone(), fb.grad.clone(), table.clone(), sorted(plan.shared))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("G", [4, 1])
-def test_two_ranks_match_single_process(G):
+@pytest.mark.parametrize("G,world", [(4, 2), (1, 2), (3, 2), (2, 3)])
+def test_ranks_match_single_process(G, world):
     V, N = 5, 16
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, G, V, N, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, G, V, N, out), nprocs=world, join=True)
     # single-process reference of the same 3 steps
     param = torch.stack([torch.full((N, 3), float(f + 1)) for f in range(G)])
-    opt = torch.optim.Adam([param], lr=1e-2, eps=1e-15)
-    for step in range(3):
+    m, v = torch.zeros_like(param), torch.zeros_like(param)
+    for step in range(1, 4):
         grad = torch.zeros_like(param)
         for f in range(G):
             for vw in range(V):
-                grad[f] += _fake_item_grad(f, vw, N) * (1.0 / V) * (step + 1)
+                grad[f] += _fake_item_grad(f, vw, N) * (1.0 / V) * step
             grad[f] += _fake_physics_grad(f, N)
-        param.grad = grad
-        opt.step()
-    for r in range(2):
-        p, g = out[r]
-        assert torch.allclose(g, grad, atol=1e-6), r
-        assert torch.allclose(p, param.detach(), atol=1e-6), r
-    assert torch.equal(out[0][0], out[1][0])   # replicated parameters stay bit-identical across ranks
+        _adam(param, grad, m, v, step)
+    for r in range(world):
+        p, g, table, shared = out[r]
+        assert torch.allclose(p, param, atol=1e-6), r
+        for f in shared:                       # the reduced slots hold the full gradient on every rank
+            assert torch.allclose(g[f], grad[f], atol=1e-6), (r, f)
+        assert torch.equal(table[:, 0], torch.full((G,), float(V)))   # every (frame, view) item was processed exactly once
+    assert torch.equal(out[0][0], out[1][0])
+
+
+def test_plan_shapes():
+    p = plan_items(16, 5, 8, 3)
+    assert p.shared == [] and p.local == [3, 11] and p.physics_frames == {3, 11}
+    p = plan_items(1, 5, 2, 1)
+    assert p.shared == [0] and p.local == [] and p.by_frame == {0: [3, 4]} and p.physics_frames == set() and p.owner(0) == 0
+    p = plan_items(2, 5, 3, 1)   # 10 items in blocks of 4: rank 1 holds the tail of frame 0 and the head of frame 1
+    assert p.shared == [0, 1] and p.by_frame == {0: [4], 1: [0, 1, 2]} and p.physics_frames == {1}
+    p = plan_items(1, 5, 8, 6)   # more ranks than items: this rank idles but still takes part in the collectives
+    assert p.by_frame == {} and p.shared == [0]
 
 
 def test_frame_lanes_single_lane_runs_frames_in_order():

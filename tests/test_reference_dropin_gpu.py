@@ -1,0 +1,237 @@
+"""GPU: the reference's OWN, UNMODIFIED Python running on CUDA through libfnx's drop-ins.
+
+`oracle/build_ref.py:stage_python` compiled FluidDynamics/{gaussian_splatting,renderer,utils,helpers,scene,arguments,entries_*}
+to sourceless bytecode under oracle/_ref/FluidDynamics (git-ignored, shipped with the snapshot); here
+`fluidnexus_b200.install_compat()` makes `diff_gaussian_rasterization_ch1/_ch3`, `simple_knn`, `torch_cluster`, `torch_scatter`
+resolve to libfnx, and then
+
+  (a) gm_dynamics / gm_fluid `get_visual_xyz_from_nn`, `get_gas_constraints_from_exyz_nn`, `get_gas_constraints_from_vel_nn_guess`
+      (gm_fluid.py:1291-1336, 1107-1158) + their autograd gradient run on the GPU and are held to the fp64 oracle and to
+      libfnx's fused kernels,
+  (b) `render_dynamics` / `render_fluid` (renderer/pipe_dynamics.py:8-180, pipe_fluid.py:8-135) render through the drop-in
+      rasterizer and are held to the C oracle and to this package's batched workspace,
+  (c) the body of the hot loop of entries_fluid_nexus/train_physical_particle.py:329-432 (and its ScalarReal twin :301-381),
+      cut out of the parsed entry script and executed as it is -- stock GaussianModel, stock Camera objects, stock
+      get_parser() on the stock JSON config, stock loss_utils, torch.optim.Adam -- is compared with PhysicalStep.step on
+      the same state: per-term losses rel 1e-4, averaged gradient rel-L2 2e-3, parameters after 3 iterations.
+"""
+import math
+import random
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from fluidnexus_b200 import synthetic as S
+from oracle import ref_python as RP
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not RP.staged(), reason="oracle/_ref/FluidDynamics not staged (needs /root/reference at build time)")]
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ref(libfnx):
+    RP.use_reference_python("fnx")
+    import diff_gaussian_rasterization_ch3 as ch3
+    import torch_cluster
+    assert "fluidnexus_b200/compat" in ch3.__file__ and "fluidnexus_b200/compat" in torch_cluster.__file__
+    return True
+
+
+def _t(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype, device=DEV)
+
+
+def _scene(C, with_bg, size=64, N=1500, V=600, seed=0, bmax=0.0):
+    hp = S.hidden_lattice(N, seed=seed + 1, buoyancy=(0.0, 1.96, 0.0) if bmax > 0 else (0.0, 0.0, 0.0))
+    rng = np.random.default_rng(seed)
+    vis = hp.xyz[rng.choice(hp.N, V, replace=False)] + rng.uniform(-0.3, 0.3, (V, 3))
+    hp.force = rng.normal(0, 3, hp.force.shape)
+    bg = S.background_gaussians(400, C, seed=seed + 3) if with_bg else None
+    cams = S.make_cameras(5, size)
+    return hp, vis, bg, cams
+
+
+def _stock_model(config, model_name, hp, vis, bg):
+    """A stock GaussianModel (its real constructor + setup_constants on the stock config) holding the synthetic state."""
+    from helpers.helper_gaussian import get_model
+    args, model_args, optim_args, pipe_args = RP.parse_args(config, tempfile.mkdtemp(prefix="fnx_ref_"))
+    assert model_args.model == model_name
+    gm = get_model(model_args.model)(model_args.sh_degree)
+    gm.setup_constants(optim_args)
+    gm.spatial_lr_scale = 1.0                                    # Scene -> create_from_pcd(cameras_extent) in the entries
+    gm._xyz, gm._estimate_xyz = _t(hp.xyz), _t(hp.estimate_xyz)
+    gm._velocity, gm._force, gm._buoyancy = _t(hp.velocity), _t(hp.force), _t(hp.buoyancy)
+    gm._imass = _t(hp.imass)
+    gm._counts = torch.zeros((hp.N, 1), device=DEV)
+    gm._particle_id = torch.arange(hp.N, device=DEV).unsqueeze(1)
+    gm._visual_xyz = _t(vis)
+    if bg is not None:                                           # what gm_dynamics.load_ply leaves behind (gm_dynamics.py:1702-1744)
+        gm._gs_xyz, gm._gs_color = _t(bg.xyz), _t(bg.colors)
+        gm._gs_scales, gm._gs_rotation = torch.log(_t(bg.scales)), _t(bg.rotations)
+        gm._gs_opacity = torch.logit(_t(bg.opacity))
+    gm.training_setup_current(optim_args)                        # _estimate_xyz_nn = Parameter(estimate_xyz / 100), Adam eps 1e-15
+    gm.prepare_visual_particles_for_rendering()                  # constant colour 0.7 / log-scale -5.9 / opacity 0.1
+    return gm, optim_args, pipe_args
+
+
+def _activated_sets(gm, C):
+    """The activated attributes the stock render pipe hands to the rasterizer, as GaussianSets for this package's FrameState."""
+    n = lambda t: t.detach().cpu().numpy().astype(np.float64)
+    col = gm.get_visual_color
+    col = col.repeat(1, 3) if (C == 3 and col.shape[1] == 1) else col
+    fluid = S.GaussianSet(n(gm._visual_xyz) / 100.0, n(gm.get_visual_scaling), n(gm.get_visual_rotation), n(gm.get_visual_opacity), n(col))
+    bg = None
+    if getattr(gm, "_gs_xyz", torch.empty(0)).numel():
+        bg = S.GaussianSet(n(gm.get_gs_xyz), n(gm.get_gs_scaling), n(gm.get_gs_rotation), n(gm.get_gs_opacity), n(gm.get_gs_color))
+    return fluid, bg
+
+
+def _stock_cameras(cams, gts):
+    from scene.camera import Camera
+    out = []
+    for k, (c, g) in enumerate(zip(cams, gts)):
+        img = torch.tensor(g)
+        out.append(Camera(colmap_id=k, R=c.R, T=c.T, FoVx=c.FoVx, FoVy=c.FoVy, image=img, gt_alpha_mask=None, image_name=f"train0{k}", uid=k,
+                          real_image=img.clone()))
+    return out
+
+
+CASES = {
+    # name: (config, model, loop body, pipe, C, with_bg, grey, bmax)
+    "fluid_nexus_smoke": ("fluid_nexus_smoke_dynamics", "gm_dynamics", "fluid_nexus_physical_current", "render_dynamics", 3, True, True, 0.0),
+    "scalar_real": ("scalar_real", "gm_fluid", "scalar_real_physical_current", "render_fluid", 1, False, False, 0.8),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_reference_physics_methods_on_cuda(ref, case):
+    """(a) P1-P3 of the stock model on the GPU (neighbour search = libfnx behind torch_cluster's names) vs the fp64 oracle."""
+    from oracle import pbf_ref as O
+    config, model, _, _, C, with_bg, _, bmax = CASES[case]
+    hp, vis, bg, _ = _scene(C, with_bg, bmax=bmax)
+    gm, optim_args, _ = _stock_model(config, model, hp, vis, bg)
+    assert abs(gm.buoyancy_max_y - bmax) < 1e-12 and gm.KNN_K == 100 and gm.H == 2.0
+    w = _t(np.random.default_rng(1).normal(size=(vis.shape[0], 3)))
+    P1 = gm.get_visual_xyz_from_nn()
+    P2 = gm.get_gas_constraints_from_exyz_nn()
+    P3 = gm.get_gas_constraints_from_vel_nn_guess()
+    loss = (P1 * w).sum() + ((P2 - 1.0) ** 2).mean() + 0.1 * ((P3 - 1.0) ** 2).mean()
+    loss.backward()
+    g = gm._estimate_xyz_nn.grad.detach().cpu().double()
+    # fp64 oracle on the float32-rounded state
+    d = lambda t: t.detach().cpu().double()
+    oprm = O.PBFParams(p0=gm.p0, buoyancy_max_y=bmax, H=gm.H, KNN_K=gm.KNN_K, secs=gm._secs)
+    e = d(gm._estimate_xyz_nn).clone().requires_grad_(True)
+    o1 = O.visual_xyz_from_nn(oprm, e, d(gm._xyz), d(gm._visual_xyz))
+    o2 = O.gas_constraints_from_exyz_nn(oprm, e, d(gm._imass))
+    o3 = O.gas_constraints_from_vel_nn_guess(oprm, e, d(gm._xyz), d(gm._buoyancy), d(gm._force), d(gm._imass))
+    lo = (o1 * w.cpu().double()).sum() + ((o2 - 1.0) ** 2).mean() + 0.1 * ((o3 - 1.0) ** 2).mean()
+    lo.backward()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(d(P1), o1.detach()) < 1e-6
+    assert rel(d(P2), o2.detach()) < 1e-5 and rel(d(P3), o3.detach()) < 1e-5
+    assert rel(g, e.grad) < 1e-4, rel(g, e.grad)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_reference_render_pipe_on_cuda(ref, oracle_built, case):
+    """(b) the stock render pipe through the drop-in rasterizer: vs the C oracle (pixels < 1e-3) and bit-identical to
+    this package's batched workspace path for the same view."""
+    from helpers.helper_pipe import get_render_pipe
+    from oracle.raster_oracle import RasterOracle
+    config, model, _, pipe, C, with_bg, _, bmax = CASES[case]
+    hp, vis, bg, cams = _scene(C, with_bg, bmax=bmax)
+    gm, optim_args, pipe_args = _stock_model(config, model, hp, vis, bg)
+    render_func, GRsetting, GRzer = get_render_pipe(pipe)
+    gts = [np.zeros((C if C == 1 else 3, 64, 64), np.float32)] * 5
+    scams = _stock_cameras(cams, gts)
+    background = torch.zeros(3 if pipe == "render_dynamics" else 1, device=DEV)
+    pkg = render_func(scams[2], gm, pipe_args, background, GRsetting=GRsetting, GRzer=GRzer, pos_type="guess_visual_nn", scale=True)
+    img = pkg["render"]
+    assert img.shape == (C, 64, 64) and pkg["radii"].shape[0] == vis.shape[0] + (bg.P if bg is not None else 0)
+    # C oracle on exactly the tensors the pipe handed over
+    n = lambda t: t.detach().cpu().numpy().astype(np.float32)
+    inp = dict(bg=n(background), means3D=n(pkg["means3D"]), colors=n(pkg["colors_precomp"]), opacities=n(pkg["opacity"]), scales=n(pkg["scales"]),
+               rotations=n(pkg["rotations"]), scale_modifier=1.0, view=n(scams[2].world_view_transform), proj=n(scams[2].full_proj_transform),
+               tan_fov_x=math.tan(scams[2].FoVx * 0.5), tan_fov_y=math.tan(scams[2].FoVy * 0.5), H=64, W=64)
+    o = RasterOracle("f64")
+    ref_img = o.forward(**inp)["color"]
+    assert float(np.abs(n(img) - ref_img).max()) < 1e-3
+    # gradient reaches the trainable tensor through the drop-in autograd function and the stock P1 chain
+    img.sum().backward()
+    assert gm._estimate_xyz_nn.grad is not None and float(gm._estimate_xyz_nn.grad.abs().max()) > 0
+    # stock camera == synthetic camera (the scene code of this package is pinned to it)
+    assert torch.equal(scams[2].world_view_transform.cpu(), cams[2].world_view_transform)
+    assert torch.equal(scams[2].full_proj_transform.cpu(), cams[2].full_proj_transform)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_reference_training_loop_body_matches_fused_step(ref, case):
+    """(c) three iterations of the stock loop body (5 views per iteration) vs three PhysicalStep.step calls."""
+    from helpers.helper_pipe import get_render_pipe
+    from utils.loss_utils import distance_loss, l1_loss, l2_loss, ssim
+    from fluidnexus_b200.step import FrameState, PhysicalStep, StepParams
+    config, model, body_name, pipe, C, with_bg, grey, bmax = CASES[case]
+    hp, vis, bg, cams = _scene(C, with_bg, bmax=bmax)
+    gm, optim_args, pipe_args = _stock_model(config, model, hp, vis, bg)
+    optim_args.batch = 5                       # the shipped configs use 1; the loop body is the same for any batch
+    optim_args.distance_threshold_visual = 0.004
+    render_func, GRsetting, GRzer = get_render_pipe(pipe)
+    rng = np.random.default_rng(5)
+    gts = [np.clip(0.3 + 0.3 * rng.random((C, 64, 64)), 0, 1).astype(np.float32) for _ in range(5)]
+    scams = _stock_cameras(cams, gts)
+    background = torch.zeros(3 if pipe == "render_dynamics" else 1, device=DEV)
+    code, where = RP.loop_body(body_name)
+
+    # ---- this package: same state, same constants (read from the stock objects) ----
+    fluid, bgset = _activated_sets(gm, C)
+    lr = gm.optimizer.param_groups[0]["lr"]
+    prm = StepParams(H=gm.H, KNN_K=gm.KNN_K, p0=gm.p0, secs=gm._secs, buoyancy_max_y=gm.buoyancy_max_y, lambda_dssim=optim_args.lambda_dssim,
+                     lambda_image=optim_args.lambda_image, lambda_current_distance=optim_args.lambda_current_distance,
+                     lambda_exyz=optim_args.lambda_exyz, lambda_gas_constraints=optim_args.lambda_gas_constraints,
+                     lambda_next_gas_constraints=optim_args.lambda_next_gas_constraints,
+                     distance_threshold_visual=optim_args.distance_threshold_visual, lr=lr, adam_eps=gm.optimizer.param_groups[0]["eps"], grey=grey)
+    fr = FrameState(hp, vis, fluid, bgset, device=DEV, prm=prm)
+    assert torch.equal(fr.e, gm._estimate_xyz_nn.detach())
+    ps = PhysicalStep(cams, C, prm, device=DEV)
+    gt_dev = torch.tensor(np.stack(gts), device=DEV)
+
+    tb = RP.NullWriter()
+    grads = []
+    step0 = gm.optimizer.step
+
+    def recording_step(*a, **k):
+        grads.append(gm._estimate_xyz_nn.grad.detach().clone())
+        return step0(*a, **k)
+    gm.optimizer.step = recording_step
+    ns = dict(gaussians=gm, optim_args=optim_args, random=random, cur_viewpoint_set=scams, render_func=render_func, pipe_args=pipe_args,
+              background=background, GRsetting=GRsetting, GRzer=GRzer, torch=torch, l1_loss=l1_loss, ssim=ssim, distance_loss=distance_loss,
+              l2_loss=l2_loss, tb_writer=tb, cur_time_index=1)
+    random.seed(0)
+    for itr in range(1, 4):
+        ns["itr"] = itr
+        exec(code, ns)                                           # the reference's own loop body, as cut from `where`
+        out = ps.step(fr, [0, 1, 2, 3, 4], gt_dev)
+        torch.cuda.synchronize()
+        pre = "train_loss_frame_001/"
+        ref_total = float(np.mean([tb.scalars[f"{pre}total_train0{k}"] for k in range(5)]))
+        mine_total = float(ps.total_loss(out))
+        assert abs(mine_total - ref_total) < 1e-4 * abs(ref_total), (itr, mine_total, ref_total)
+        for k, key in (("gas_cs", "gas"), ("next_gas_cs", "next_gas"), ("exyz", "exyz"), ("dist", "dist")):
+            r = tb.scalars[f"{pre}{k}_train00"]
+            assert abs(float(out[key]) - r) <= 1e-4 * abs(r) + 1e-9, (itr, k, float(out[key]), r)
+        for v in range(5):
+            assert abs(float(out["l1"][v]) - tb.scalars[f"{pre}l1_train0{v}"]) < 1e-4 * tb.scalars[f"{pre}l1_train0{v}"]
+            assert abs((1.0 - float(out["ssim"][v])) - tb.scalars[f"{pre}ssim_train0{v}"]) < 1e-4
+        g_ref = grads[-1].double()
+        rel = float((out["grad"].double() - g_ref).norm() / g_ref.norm())
+        assert rel < 2e-3, (itr, rel)
+        # parameters: Adam's first steps move every component by ~lr (eps 1e-15: m/sqrt(v) ~ +-1).  All but a handful of components
+        # agree to 1 % of a step; a component whose gradient is ~0 may take the other sign (2*lr per step at most)
+        dp = (fr.e - gm._estimate_xyz_nn.detach()).abs().flatten()
+        assert float(torch.quantile(dp, 0.999)) < 0.01 * lr * itr, (itr, float(torch.quantile(dp, 0.999)))
+        assert float(dp.max()) <= 2.0 * lr * itr * 1.001, (itr, float(dp.max()))
+    assert where[0].startswith("entries_")

@@ -22,27 +22,7 @@ import scenes  # noqa: E402
 from oracle.ref_ext import RefRaster  # noqa: E402
 
 
-def carve_geom(buf, P):
-    """GeometryState::fromChunk layout: depths f32[P], clamped bool[3P], radii i32[P], means2D f32[2P], cov3D f32[6P],
-    conic_opacity f32[4P], ... each aligned to 128 B from the chunk's own address."""
-    base = buf.data_ptr()
-    off = 0
-
-    def take(nbytes):
-        nonlocal off
-        start = ((base + off + 127) // 128) * 128 - base
-        off = start + nbytes
-        return start
-
-    o_depth = take(4 * P)
-    take(3 * P)
-    take(4 * P)
-    o_m2 = take(8 * P)
-    take(24 * P)
-    o_co = take(16 * P)
-    raw = buf.cpu().numpy()
-    f = lambda o, n: raw[o:o + 4 * n].view(np.float32).copy()
-    return f(o_depth, P), f(o_m2, 2 * P).reshape(P, 2), f(o_co, 4 * P).reshape(P, 4)
+from oracle.ref_ext import carve_geom  # noqa: E402,F401
 
 
 def main(outdir):
