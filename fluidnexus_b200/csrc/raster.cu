@@ -699,27 +699,35 @@ pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_
 
 // ---------------------------------------------------------------------------------------------------------------
 // alpha of one (pixel, record) pair -- the ONE place the blend decision is made, shared by forward and backward.
-// The reference evaluates expf() (forward.cu:330, backward.cu:479).  We use the fast ex2-based path and fall back to
-// expf() only inside a narrow band around the 1/255 cut so that the keep/skip decision is the reference's.
+//
+// Bit parity with the compiled reference (forward.cu:322-338, backward.cu:470-486) needs three things:
+//  (1) `power` rounded like the reference's kernel rounds it.  Its SASS (sm_100, nvcc 12.9) evaluates
+//      -0.5f * (a*dx*dx + c*dy*dy) - b*dx*dy  as  s = fma(dx, a*dx, (c*dy)*dy);  power = fma(s, -0.5, -((b*dx)*dy)),
+//      i.e. the product c*dy*dy is rounded and a*dx*dx is the fused one.  Left to itself nvcc fuses the OTHER product here
+//      (dx is shared by this thread's pixels and gets hoisted), which moves `power` by one ulp for some pairs and with it the
+//      1/255 keep/skip decision of pairs that sit on the cut: one pixel in ~10^6 then differs by up to 0.0039 * T * |dc|
+//      (measured 1.35e-3 on the 300k-Gaussian scene).  The intrinsics below pin the reference's rounding.
+//  (2) alpha = o * expf(power) with the accurate expf of every pair that is KEPT, so that T, the T(1-alpha) < 1e-4
+//      termination test, the T < 0.5 median-depth pick and the colour sums see the reference's values.
+//  (3) no cost for that on the pairs that are skipped -- most of them: alpha >= 1/255 <=> power >= -ln(255 o) =: the record's
+//      cut, computed once per staged record (warp_record_mask) with a margin of 2e-4 (about 1000 ulp of power, far beyond the
+//      error of __logf and of the exponentials), so a skipped pair costs one compare and no MUFU at all.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr float ALPHA_BAND = 4e-6f;  // ~1000x the error of ex2.approx at alpha = 1/255
-__device__ __forceinline__ bool pair_alpha(float x, float y, float a, float b, float c, float o, float px, float py,
+constexpr float POWER_CUT_MARGIN = 2e-4f;
+__device__ __forceinline__ float record_power_cut(float opacity) {
+    // power below this can not reach alpha = 1/255 (opacity <= 0 -> +inf: never kept)
+    return opacity > 0.f ? -__logf(255.0f * opacity) - POWER_CUT_MARGIN : __int_as_float(0x7f800000);
+}
+__device__ __forceinline__ bool pair_alpha(float x, float y, float a, float b, float c, float o, float pcut, float px, float py,
                                            float &dx, float &dy, float &G, float &alpha) {
     dx = x - px;
     dy = y - py;
-    const float power = -0.5f * (a * dx * dx + c * dy * dy) - b * dx * dy;
-    if (power > 0.0f) return false;
-    // ex2.approx.ftz of power*log2(e): what __expf() compiles to minus its denormal-range rescaling (a G below 2^-126
-    // gives alpha = 0 < 1/255 either way)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(G) : "f"(power * 1.4426950408889634f));
+    const float s = __fmaf_rn(dx, __fmul_rn(a, dx), __fmul_rn(__fmul_rn(c, dy), dy));
+    const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(__fmul_rn(b, dx), dy));
+    if (power > 0.0f || power < pcut) return false;
+    G = expf(power);
     alpha = min(ALPHA_MAX, o * G);
-    if (alpha < ALPHA_MIN + ALPHA_BAND) {  // below the cut, or so close to it that the approximation could decide it
-        if (alpha < ALPHA_MIN - ALPHA_BAND) return false;
-        G = expf(power);
-        alpha = min(ALPHA_MAX, o * G);
-        return !(alpha < ALPHA_MIN);
-    }
-    return true;
+    return !(alpha < ALPHA_MIN);
 }
 
 constexpr int BATCH = BLEND_WARPS == 1 ? 64 : 128;  // records per smem stage (32 one-warp CTAs per SM need <= 7 KB each)
@@ -736,15 +744,20 @@ __device__ __forceinline__ uint32_t rec_slot_word(const float4 *rec, int j) {
     return __float_as_uint(C == 3 ? f[j * 12 + 9] : f[j * 8 + 7]);
 }
 // this warp's bitmask over the n (<= 128) staged records: bit set <=> the record can touch the warp's 8x8 patch
+// ... and the staged records' power cuts (pair_alpha): every warp writes the entries of all n records (the four warps of a
+// CTA store identical values), so after the __syncwarp a lane only ever reads what its own warp wrote.
 template <int C>
-__device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int warp, int lane, bool use_mask, uint32_t (&words)[BATCH / 32]) {
+__device__ __forceinline__ void warp_record_mask(const float4 *rec, int n, int warp, int lane, bool use_mask, uint32_t (&words)[BATCH / 32],
+                                                 float *pcut) {
 #pragma unroll
     for (int k = 0; k < BATCH / 32; k++) {
         const int r = k * 32 + lane;
         bool need = r < n;
+        if (need) pcut[r] = record_power_cut(rec[r * (RecBytes<C>::value / 16) + 1].y);
         if (need && use_mask) need = ((rec_slot_word<C>(rec, r) >> (SLOT_BITS + warp)) & 1u) != 0;
         words[k] = __ballot_sync(0xffffffffu, need);
     }
+    __syncwarp();
 }
 
 // bits [lo, hi) of a 32-bit word, clipped to the word
@@ -779,6 +792,7 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                  ImageView im, float *__restrict__ out_color, float *__restrict__ out_depth) {
     constexpr int REC = RecBytes<C>::value;
     __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
+    __shared__ float s_pcut[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
     const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
@@ -863,7 +877,8 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
         if (__all_sync(0xffffffffu, all_done)) continue;  // this warp's patch is finished
         uint32_t words[BATCH / 32];
-        warp_record_mask<C>(rec, n, warp, lane, use_mask, words);
+        warp_record_mask<C>(rec, n, warp, lane, use_mask, words, s_pcut[s]);
+        const float *pcut = s_pcut[s];
         // the batch holding the snapshot position is walked in two segments, [0, Lrel) and [Lrel, BATCH)
         const int Lrel = L - bi * BATCH;
         const int cut = (Lrel >= 0 && Lrel < BATCH) ? Lrel : BATCH;
@@ -886,11 +901,12 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                     w &= w - 1;
                     const float4 r0 = rec[j * (REC / 16)];
                     const float4 r1 = rec[j * (REC / 16) + 1];
+                    const float pc = pcut[j];
 #pragma unroll
                     for (int p = 0; p < PPT; p++) {
                         if (done[p]) continue;
                         float dx, dy, G, alpha;
-                        if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx, dy, G, alpha)) continue;
+                        if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pc, pxf, pyf[p], dx, dy, G, alpha)) continue;
                         const float test_T = T[p] * (1 - alpha);
                         if (test_T < T_EPS) {
                             done[p] = 1;
@@ -1021,6 +1037,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     constexpr int REC = RecBytes<C>::value;
     constexpr int ACC = AccFloats<C>::value;
     __shared__ __align__(128) char s_rec[STAGES][BATCH * REC];
+    __shared__ float s_pcut[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
     const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
@@ -1129,7 +1146,8 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
         if (lo >= warp_last) continue;  // nothing in this batch reaches this warp's pixels
         const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
         uint32_t words[BATCH / 32];
-        warp_record_mask<C>(rec, min(n, warp_last - lo), warp, lane, use_mask, words);
+        warp_record_mask<C>(rec, min(n, warp_last - lo), warp, lane, use_mask, words, s_pcut[s]);
+        const float *pcut = s_pcut[s];
 #pragma unroll
         for (int k = BATCH / 32 - 1; k >= 0; k--) {
             uint32_t w = words[k];
@@ -1140,13 +1158,14 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
                 const int idx = lo + j;  // 0-based position in the tile's span
                 const float4 r0 = rec[j * (REC / 16)];
                 const float4 r1 = rec[j * (REC / 16) + 1];
+                const float pc = pcut[j];
                 float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
                 bool contrib[PPT], any = false;
 #pragma unroll
                 for (int p = 0; p < PPT; p++) {
                     dx[p] = dy[p] = G[p] = alpha[p] = 0.f;
                     contrib[p] = (idx < last_contributor[p]) &&
-                                 pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pxf, pyf[p], dx[p], dy[p], G[p], alpha[p]);
+                                 pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pc, pxf, pyf[p], dx[p], dy[p], G[p], alpha[p]);
                     any = any || contrib[p];
                 }
                 if (!__any_sync(0xffffffffu, any)) continue;

@@ -95,7 +95,8 @@ def build(keys=None, verbose=False):
 
 FD = "/root/reference/FluidDynamics"
 PY_OUT = os.path.join(OUT, "FluidDynamics")
-PKG_OUT = os.path.join(OUT, "pkgs")
+PY_ZIP = os.path.join(PY_OUT, "reference_python.zip")        # sys.path entry: FluidDynamics/ as sourceless bytecode
+PKG_ZIP = os.path.join(PY_OUT, "reference_wrappers.zip")      # sys.path entry: diff_gaussian_rasterization_ch{1,3}/__init__
 PY_DIRS = ["arguments", "gaussian_splatting", "helpers", "renderer", "scene", "utils", "entries_fluid_nexus", "entries_scalar_real"]
 WRAPPERS = {"diff_gaussian_rasterization_ch3": "submodules/gaussian_rasterization_ch3/diff_gaussian_rasterization_ch3/__init__.py",
             "diff_gaussian_rasterization_ch1": "submodules/gaussian_rasterization_ch1/diff_gaussian_rasterization_ch1/__init__.py"}
@@ -143,31 +144,43 @@ def _loop_body_code(path, which):
 
 
 def stage_python(verbose=False):
-    """Sourceless bytecode of the reference's Python + configs + loop bodies -> oracle/_ref (see the module docstring)."""
+    """Sourceless bytecode of the reference's Python (two zip archives: zipimport loads .pyc members, and loose .pyc files do not
+    travel with gpurun snapshots) + configs + loop bodies -> oracle/_ref (see the module docstring)."""
     if not os.path.isdir(FD):
         return False
     import marshal
     import py_compile
     import shutil
+    import tempfile
+    import zipfile
+    os.makedirs(PY_OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="fnx_stage_")
+
+    def bytecode(src, dfile):
+        dst = os.path.join(tmp, "x.pyc")
+        py_compile.compile(src, cfile=dst, dfile=dfile, doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        return open(dst, "rb").read()
+    empty = os.path.join(tmp, "empty.py")
+    open(empty, "w").close()
     n = 0
-    for d in PY_DIRS:
-        for root, _, files in os.walk(os.path.join(FD, d)):
-            for f in files:
-                if not f.endswith(".py"):
-                    continue
-                src = os.path.join(root, f)
-                rel = os.path.relpath(src, FD)
-                dst = os.path.join(PY_OUT, rel + "c")
-                os.makedirs(os.path.dirname(dst), exist_ok=True)
-                py_compile.compile(src, cfile=dst, dfile=os.path.join("FluidDynamics", rel), doraise=True,
-                                   invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-                n += 1
-    for pkg, rel in WRAPPERS.items():
-        dst = os.path.join(PKG_OUT, pkg, "__init__.pyc")
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        py_compile.compile(os.path.join(FD, rel), cfile=dst, dfile=os.path.join("FluidDynamics", rel), doraise=True,
-                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-        n += 1
+    with zipfile.ZipFile(PY_ZIP, "w", zipfile.ZIP_DEFLATED) as z:
+        for d in PY_DIRS:
+            has_init = False
+            for root, _, files in os.walk(os.path.join(FD, d)):
+                for f in sorted(files):
+                    if not f.endswith(".py"):
+                        continue
+                    src = os.path.join(root, f)
+                    rel = os.path.relpath(src, FD)
+                    has_init |= rel == os.path.join(d, "__init__.py")
+                    z.writestr(rel + "c", bytecode(src, os.path.join("FluidDynamics", rel)))
+                    n += 1
+            if not has_init:   # the reference uses implicit namespace packages here; inside a zip an (empty) regular package is the safe form
+                z.writestr(os.path.join(d, "__init__.pyc"), bytecode(empty, os.path.join("FluidDynamics", d, "__init__.py")))
+    with zipfile.ZipFile(PKG_ZIP, "w", zipfile.ZIP_DEFLATED) as z:
+        for pkg, rel in WRAPPERS.items():
+            z.writestr(os.path.join(pkg, "__init__.pyc"), bytecode(os.path.join(FD, rel), os.path.join("FluidDynamics", rel)))
+            n += 1
     os.makedirs(os.path.join(PY_OUT, "configs"), exist_ok=True)
     for f in os.listdir(os.path.join(FD, "configs")):
         if f.endswith(".json"):
@@ -180,13 +193,14 @@ def stage_python(verbose=False):
             where[name] = (rel, lines)
     with open(os.path.join(PY_OUT, "_loop_bodies.marshal"), "wb") as fh:
         marshal.dump({"bodies": bodies, "where": where, "python": sys.version_info[:2]}, fh)
+    shutil.rmtree(tmp, ignore_errors=True)
     if verbose:
-        print(f"staged {n} bytecode files, {len(bodies)} loop bodies:", where)
+        print(f"staged {n} bytecode modules, {len(bodies)} loop bodies:", where)
     return True
 
 
 def python_staged():
-    return os.path.exists(os.path.join(PY_OUT, "_loop_bodies.marshal"))
+    return all(os.path.exists(p) for p in (PY_ZIP, PKG_ZIP, os.path.join(PY_OUT, "_loop_bodies.marshal")))
 
 
 if __name__ == "__main__":

