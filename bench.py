@@ -365,6 +365,9 @@ def run_fnx(args):
             states[f].graphs.clear()
         for _ in range(3):
             one_step(False)
+        for f in mine:                        # the work per tile changed (static-only tiles are blended again): re-rank the start order
+            for w_ in states[f].ws.values():
+                w_.update_tile_order()
         ms_nc, _, _ = timed(args.steps, False, min_seconds=min(1.0, args.min_leg_seconds))
         value_nocache = G * args.steps / (ms_nc / 1e3)
         ms_nc_e2e, _, _ = timed(args.steps, True, min_seconds=min(1.0, args.min_leg_seconds))
@@ -480,6 +483,11 @@ def run_fnx(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, frames[0], bg, cams)
+    if world == 1 and not args.no_dropin:
+        try:
+            line["dropin_unchanged_python"] = dropin_leg(args, cfg, frames[0], bg, cams, prm, dev)
+        except Exception as e:  # measurement extra: never lose the line over it
+            line["dropin_unchanged_python"] = {"error": f"{type(e).__name__}: {e}"}
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -542,6 +550,36 @@ def workload_text(name, cfg):
     P = cfg["nf"] + cfg["nb"]
     return (f"{name}: P={P} Gaussians ({cfg['nf']} fluid + {cfg['nb']} frozen background), C={cfg['C']}, "
             f"N={cfg['N']} hidden particles, 5 views {cfg['size']}x{cfg['size']} per iteration")
+
+
+def dropin_leg(args, cfg, frame, bg, cams, prm, dev):
+    """What a user of the UNCHANGED reference scripts gets from the drop-ins alone (no fused step): the reference's own loop body
+    (oracle/ref_python.loop_body), stock GaussianModel / render pipe / loss_utils / torch.optim.Adam, everything on the GPU, with
+    diff_gaussian_rasterization_ch*, torch_cluster, torch_scatter and simple_knn resolving to libfnx (fluidnexus_b200/compat).  One
+    frame, bounded: 3 warm-up + 10 timed iterations (5 views each, ground truth uploaded per view, ~10 .item() per view)."""
+    from oracle import pbf_ref as O
+    from oracle import ref_python as RP
+    if not RP.staged():
+        return {"unavailable": "oracle/_ref/FluidDynamics not staged"}
+    from oracle.ref_step import StockTrainer
+    oprm = O.PBFParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], distance_threshold_visual=cfg["thr"])
+    with_dist = cfg["nf"] <= 20_000
+    zeros = [torch.zeros(cfg["C"], cfg["size"], cfg["size"]) for _ in cams]
+    tr = StockTrainer(oprm, frame["hidden"], frame["visual"], frame["fluid"], bg, cfg["C"], cams, zeros, with_distance=with_dist, native="fnx")
+    rng = np.random.default_rng(300)
+    pert = torch.tensor(frame["fluid"].xyz + rng.normal(0, 0.002, frame["fluid"].xyz.shape), dtype=torch.float32, device=dev)
+    tr.set_ground_truth([tr.render_gt(k, pert).cpu() for k in range(len(cams))])
+    for _ in range(3):
+        tr.iteration()
+    torch.cuda.synchronize()
+    t0, n = time.time(), 10
+    for _ in range(n):
+        tr.iteration()
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / n
+    return {"value": round(1.0 / dt, 3), "unit": "iters/s", "ms_per_iteration": round(dt * 1e3, 3), "frames_in_flight": 1,
+            "loop_body": f"{tr.where[0]}:{tr.where[1][0]}-{tr.where[1][1]}", "distance_loss": "dense cdist (stock)" if with_dist else "off (O(V^2))",
+            "what": "the reference's own training-loop body and Python modules, unchanged, on the GPU through libfnx's drop-in packages"}
 
 
 def cpu_baseline(args, cfg, frame, bg, cams):
@@ -685,6 +723,7 @@ def main():
     ap.add_argument("--verify", action="store_true", help="run the sharded-vs-single-rank parity check at 1 GPU too")
     ap.add_argument("--verify-steps", type=int, default=3)
     ap.add_argument("--no-ab", action="store_true", help="skip the static-tile-cache A/B legs")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the leg that runs the reference's own loop body through the drop-ins")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-restated", action="store_true", help="reference arm: use the restated glue even when the reference's Python is staged")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")

@@ -30,6 +30,7 @@ class RasterArgs(C.Structure):
         ("tan_fov_x", C.c_float), ("tan_fov_y", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("flags", C.c_uint32), ("instance_capacity_hint", C.c_int64),
         ("num_rendered_pinned", C.c_void_p), ("grad_begin", C.c_int32), ("grad_end", C.c_int32),
+        ("tile_order", C.c_void_p), ("static_view_map", C.c_void_p), ("static_views", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -88,6 +89,9 @@ SYMBOLS = {
     "fnx_raster_read_tiles": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _I, _V, _V, _V, _V, _V]),
     "fnx_raster_backward_merged": (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), C.POINTER(RasterScratch), _V, _V, _V,
                                         C.POINTER(RasterGrads), _V]),
+    "fnx_raster_overflow_flag": (_I, [C.POINTER(RasterScratch), C.POINTER(_V)]),
+    "fnx_raster_tile_cache_set": (_I, [C.POINTER(RasterScratch), _I, _I, _I, _I, _V]),
+    "fnx_raster_tile_order": (_I, [C.POINTER(RasterScratch), C.POINTER(RasterScratch), _I, _I, _I, _V, _V]),
     "fnx_raster_check": (_I, [C.POINTER(RasterScratch), C.POINTER(_I64), _V]),
     "fnx_mark_visible": (_I, [_I, _V, _V, _V, _V, _V]),
     "fnx_grid_bytes": (_SZ, [_I]),
@@ -115,6 +119,7 @@ SYMBOLS = {
     "fnx_pbf_ratio_loss": (_I, [_I, _V, _F, _V, _V, _V]),
     "fnx_adam_step": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _I, _V]),
     "fnx_adam_step_dev": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _V, _V, _V]),
+    "fnx_adam_step_dev_gated": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _V, _V, _V, _V]),
     "fnx_scatter_min": (_I, [_I64, _V, _V, _I, _V, _V, _V]),
     "fnx_image_loss_bytes": (_SZ, [_I, _I, _I, _I]),
     "fnx_image_loss": (_I, [_I, _I, _I, _I, _V, _V, _I, _F, _F, _V, _V, _V, _V, _V]),

@@ -870,7 +870,11 @@ __global__ void adam_kernel(long long n, float *__restrict__ p, const float *__r
 }
 
 // device-side step counter variant (CUDA-graph replay safe): bumps *step and derives the bias corrections in double
-__global__ void adam_prepare_kernel(int *step, float beta1, float beta2, float *bc /*[2]*/) {
+__global__ void adam_prepare_kernel(int *step, float beta1, float beta2, float *bc /*[2]*/, const int *__restrict__ skip_flag) {
+    if (skip_flag != nullptr && *skip_flag != 0) {  // the iteration that produced `grad` is void (e.g. the rasterizer's instance
+        bc[0] = 0.f;                                // capacity overflowed and it rendered nothing): leave parameters, moments and
+        return;                                     // the step count alone.  bc[0] == 0 tells adam_dev_kernel (1 - beta1^t > 0 otherwise)
+    }
     const int t = ++(*step);
     bc[0] = (float)(1.0 - pow((double)beta1, (double)t));
     bc[1] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
@@ -881,6 +885,7 @@ __global__ void adam_dev_kernel(long long n, float *__restrict__ p, const float 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float bc1 = bc[0], bc2_sqrt = bc[1];
+    if (bc1 == 0.f) return;  // gated off by adam_prepare_kernel
     const float gI = grad[i] * grad_scale;
     const float mi = m[i] + (gI - m[i]) * (1.0f - beta1);
     const float vi = beta2 * v[i] + (1.0f - beta2) * gI * gI;
@@ -1230,9 +1235,15 @@ int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, fl
 
 int fnx_adam_step_dev(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale, float lr,
                       float beta1, float beta2, float eps, int32_t *step_dev, float *bc_dev, fnx_stream_t stream) {
+    return fnx_adam_step_dev_gated(n, param, grad, exp_avg, exp_avg_sq, grad_scale, lr, beta1, beta2, eps, step_dev, bc_dev, nullptr, stream);
+}
+
+int fnx_adam_step_dev_gated(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale, float lr,
+                            float beta1, float beta2, float eps, int32_t *step_dev, float *bc_dev, const int32_t *skip_flag,
+                            fnx_stream_t stream) {
     ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
     FNX_REQUIRE(n >= 0 && param && grad && exp_avg && exp_avg_sq && step_dev && bc_dev, "bad arguments");
-    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, beta1, beta2, bc_dev);
+    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, beta1, beta2, bc_dev, skip_flag);
     if (n > 0)
         adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, grad_scale, lr,
                                                                                      beta1, beta2, eps, bc_dev);

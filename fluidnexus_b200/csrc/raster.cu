@@ -769,6 +769,17 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
     return upto_hi & ~((1u << lo) - 1u);
 }
 
+// Which (view, tile) a CTA works on.  The grid is (tiles * CTAS_PER_TILE, views); CTAs are dispatched in linear block order, so
+// with `tile_order` (a permutation of [0, views * tiles): fnx_raster_tile_order lists the units by decreasing work of the last
+// forward) the long tiles start first and the short ones fill the tail -- longest-processing-time-first scheduling.  Without it
+// the natural order.  An out-of-range entry (a caller's stale buffer) is skipped instead of followed.
+__device__ __forceinline__ uint32_t work_unit(const uint32_t *__restrict__ tile_order, int nunits) {
+    const uint32_t linear = blockIdx.y * (gridDim.x / CTAS_PER_TILE) + blockIdx.x / CTAS_PER_TILE;
+    if (tile_order == nullptr) return linear;
+    const uint32_t u = tile_order[linear];
+    return u < (uint32_t)nunits ? u : 0xFFFFFFFFu;
+}
+
 // Optional per-tile state of the merged (static + dynamic) streams, all NULL for a plain forward:
 //   tile_src       1: the tile has no dynamic instance and is blended straight from the static stream
 //   tile_cached    (persistent, with the static stream) 1: the caller's out_color / out_depth already hold this
@@ -785,7 +796,7 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
 #endif
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_FWD_MIN_CTAS)
-blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
+blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__restrict__ tile_order, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
                  uint32_t *__restrict__ tile_cached, const uint32_t *__restrict__ tile_dyn_last, float4 *__restrict__ snap,
                  const float *__restrict__ depth_of_slot, const float *__restrict__ bg, const GeomHeader *__restrict__ hdr,
@@ -795,8 +806,10 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     __shared__ float s_pcut[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
-    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
     const int ntiles = gx * gy;
+    const uint32_t unit = work_unit(tile_order, ntiles * gridDim.y);
+    if (unit == 0xFFFFFFFFu) return;
+    const int tile = (int)(unit % (uint32_t)ntiles), v = (int)(unit / (uint32_t)ntiles);
     const size_t tslot = (size_t)v * ntiles + tile;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x % CTAS_PER_TILE) * BLEND_WARPS + (threadIdx.x >> 5);  // which 8x8 patch of the tile
@@ -1029,7 +1042,7 @@ struct SplitReduce {
 #endif
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_BWD_MIN_CTAS)
-blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__restrict__ records_own,
+blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__restrict__ tile_order, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
                  const uint32_t *__restrict__ tile_dyn_last, const float4 *__restrict__ snap,
                  const float *__restrict__ bg, const GeomHeader *__restrict__ hdr, ImageView im,
@@ -1040,8 +1053,10 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const char *__rest
     __shared__ float s_pcut[STAGES][BATCH];
     __shared__ __align__(8) uint64_t s_bar[STAGES];
 
-    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
     const int ntiles = gx * gy;
+    const uint32_t unit = work_unit(tile_order, ntiles * gridDim.y);
+    if (unit == 0xFFFFFFFFu) return;
+    const int tile = (int)(unit % (uint32_t)ntiles), v = (int)(unit / (uint32_t)ntiles);
     const int tx = tile % gx, ty = tile / gx;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x % CTAS_PER_TILE) * BLEND_WARPS + (threadIdx.x >> 5);  // which 8x8 patch of the tile
@@ -1594,7 +1609,7 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
     if (a->flags & FNX_BIN_ONLY) return FNX_OK;  // the caller blends a merged stream (fnx_raster_blend_merged)
     dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr,
+    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), a->tile_order, b.records, nullptr,
                                                         im.ranges, nullptr, nullptr, nullptr, nullptr, g.depth, a->bg, g.hdr, im, out_color,
                                                         out_depth);
     prof_end(SEC_BLEND_FWD, st);
@@ -1788,7 +1803,7 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
     dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_BWD, st);
-    blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), b.records, nullptr, im.ranges,
+    blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), a->tile_order, b.records, nullptr, im.ranges,
                                                         nullptr, nullptr, nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
@@ -1818,18 +1833,20 @@ __device__ __forceinline__ float rec48_depth(const char *recs, size_t i) { retur
 __global__ void __launch_bounds__(256)
 merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat, const char *__restrict__ rec_dyn,
              const char *__restrict__ rec_stat, char *__restrict__ rec_merged, GeomHeader *__restrict__ hdr_dyn,
-             const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, uint2 *__restrict__ mranges,
-             uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
+             const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, const int32_t *__restrict__ view_map,
+             uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
     __shared__ float s_depth[MERGE_SMEM];
     __shared__ unsigned long long s_base;
     const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
-    const uint2 f = ranges_dyn[t], b = ranges_stat[t];
+    // the static stream may hold more cameras than this call renders: view_map[v] = this call's view v in the static stream
+    const size_t ts = (size_t)(view_map ? view_map[blockIdx.y] : (int)blockIdx.y) * ntiles + blockIdx.x;
+    const uint2 f = ranges_dyn[t], b = ranges_stat[ts];
     int nf = (int)(f.y - f.x);
     int nb = (int)(b.y - b.x);
     // Static records behind the last one that the static-only blend of this tile used can never be reached once more
     // occluders are inserted: a pixel's transmittance at a given static record only shrinks (rounding is monotone),
     // so it terminates no later, and the alpha test does not depend on what lies in front.
-    if (hdr_stat->static_prepared) nb = min(nb, (int)max(max(static_last[4 * t], static_last[4 * t + 1]), max(static_last[4 * t + 2], static_last[4 * t + 3])));
+    if (hdr_stat->static_prepared) nb = min(nb, (int)max(max(static_last[4 * ts], static_last[4 * ts + 1]), max(static_last[4 * ts + 2], static_last[4 * ts + 3])));
     if (hdr_dyn->overflow) nf = 0;
     if (nf == 0) {
         if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
@@ -1883,16 +1900,17 @@ __global__ void __launch_bounds__(256)
 merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat,
                     const unsigned long long *__restrict__ bkeys, unsigned long long *__restrict__ bkeys2, GeomView g,
                     const float *__restrict__ colors, const char *__restrict__ rec_stat, char *__restrict__ rec_merged,
-                    const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, uint2 *__restrict__ mranges,
-                    uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
+                    const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, const int32_t *__restrict__ view_map,
+                    uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
     __shared__ unsigned long long s_key[SORT_CAP];
     __shared__ unsigned long long s_base;
     const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
-    const uint2 f = ranges_dyn[t], b = ranges_stat[t];
+    const size_t ts = (size_t)(view_map ? view_map[blockIdx.y] : (int)blockIdx.y) * ntiles + blockIdx.x;   // see merge_kernel
+    const uint2 f = ranges_dyn[t], b = ranges_stat[ts];
     int nf = (int)(f.y - f.x);
     int nb = (int)(b.y - b.x);
     if (hdr_stat->static_prepared)  // see merge_kernel
-        nb = min(nb, (int)max(max(static_last[4 * t], static_last[4 * t + 1]), max(static_last[4 * t + 2], static_last[4 * t + 3])));
+        nb = min(nb, (int)max(max(static_last[4 * ts], static_last[4 * ts + 1]), max(static_last[4 * ts + 2], static_last[4 * ts + 3])));
     if (g.hdr->overflow) nf = 0;
     if (nf == 0) {
         if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
@@ -1961,10 +1979,13 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     const int P = a->P, V = a->V, W = a->W, H = a->H;
     FNX_REQUIRE((long long)P * V < (1ll << SLOT_BITS) && (long long)P_static * V < (1ll << SLOT_BITS), "too many Gaussians for masked records");
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
+    const int Vs = a->static_views > 0 ? a->static_views : V;   // cameras the static stream was built for
+    FNX_REQUIRE(a->static_view_map != nullptr || Vs == V, "static_views differs from V: static_view_map must be given");
+    FNX_REQUIRE((long long)P_static * Vs < (1ll << SLOT_BITS), "too many Gaussians for masked records");
     GeomView g = geom_view(dyn->geom, P, V);
-    GeomView gs = geom_view(stat->geom, P_static, V);
+    GeomView gs = geom_view(stat->geom, P_static, Vs);
     ImageView im = image_view(dyn->image, W, H, V);
-    ImageView ims = image_view(stat->image, W, H, V);
+    ImageView ims = image_view(stat->image, W, H, Vs);
     BinView b = bin_view(dyn->binning, dyn->binning_capacity, 3);
     BinView bs = bin_view(stat->binning, stat->binning_capacity, 3);
     const bool tile_cache = (a->flags & FNX_STATIC_TILE_CACHE) != 0;
@@ -1972,16 +1993,16 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     prof_begin(SEC_PACK, st);
     if (a->flags & FNX_BUCKET_BINNING)
         merge_bucket_kernel<<<grid, 256, 0, st>>>(ntiles, P, gx, (a->flags & FNX_EXACT_RECT) != 0, im.ranges, ims.ranges, b.bkeys, b.bkeys2, g,
-                                                  a->colors, bs.records, (char *)merged_records, gs.hdr, ims.tile_last, im.mranges,
-                                                  im.tile_src, im.tile_dyn_last);
+                                                  a->colors, bs.records, (char *)merged_records, gs.hdr, ims.tile_last, a->static_view_map,
+                                                  im.mranges, im.tile_src, im.tile_dyn_last);
     else
         merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, gs.hdr,
-                                           ims.tile_last, im.mranges, im.tile_src, im.tile_dyn_last);
+                                           ims.tile_last, a->static_view_map, im.mranges, im.tile_src, im.tile_dyn_last);
     prof_end(SEC_PACK, st);
     FNX_LAUNCH_CHECK("merge_kernel");
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<3><<<dim3(ntiles * CTAS_PER_TILE, V), BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
-                                                        tile_cache ? ims.tile_cached : nullptr, im.tile_dyn_last, im.snap, g.depth, a->bg,
+    blend_fwd_kernel<3><<<dim3(ntiles * CTAS_PER_TILE, V), BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, a->tile_order, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
+                                                        tile_cache ? im.tile_cached : nullptr, im.tile_dyn_last, im.snap, g.depth, a->bg,
                                                         g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
@@ -2004,7 +2025,7 @@ static int static_prepare(const fnx_raster_args *a, const fnx_raster_scratch *st
     FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_cached, 0, sizeof(uint32_t) * (size_t)ntiles * V * TILE_PATCHES, st));
     FNX_CUDA_TRY(cudaMemsetAsync(ims.tile_src, 0xFF, sizeof(uint32_t) * (size_t)ntiles * V, st));  // every tile: "from the static stream"
     dim3 grid(ntiles * CTAS_PER_TILE, V);
-    blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, bs.records, bs.records, ims.ranges, ims.tile_src, ims.tile_cached,
+    blend_fwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, nullptr, bs.records, bs.records, ims.ranges, ims.tile_src, ims.tile_cached,
                                                         nullptr, nullptr, gs.depth, a->bg, gs.hdr, ims, out_color, out_depth);
     FNX_LAUNCH_CHECK("blend_fwd_kernel");
     static_prepared_kernel<<<1, 1, 0, st>>>(gs.hdr);
@@ -2026,7 +2047,7 @@ static int backward_merged(const fnx_raster_args *a, const fnx_raster_scratch *d
     FNX_CUDA_TRY(cudaMemsetAsync(g.accum, 0, sizeof(float) * (size_t)P * V * ACC, st));
     dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_BWD, st);
-    blend_bwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
+    blend_bwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, a->tile_order, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
                                                         im.tile_dyn_last, im.snap, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
@@ -2037,6 +2058,48 @@ static int backward_merged(const fnx_raster_args *a, const fnx_raster_scratch *d
     prof_end(SEC_GEOM_BWD, st);
     FNX_LAUNCH_CHECK("geom_bwd_kernel");
     return FNX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Longest-processing-time-first order of the (view, tile) units for the blend kernels (work_unit): a counting sort, by
+// decreasing work of the LAST forward (records the slowest 8x8 patch of the tile walked; 0 for tiles that were served from the
+// static tile cache), one CTA.  Cameras and the frozen set are fixed within a frame and the fluid moves little per iteration,
+// so an order taken once per frame (or refreshed now and then) stays a good schedule; a stale order costs time, never
+// correctness (it is a permutation).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ORDER_BINS = 2048;
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(int nunits, const uint32_t *__restrict__ tile_last, const uint32_t *__restrict__ tile_src,
+                  const uint32_t *__restrict__ tile_cached, uint32_t *__restrict__ order) {
+    __shared__ uint32_t hist[ORDER_BINS];
+    __shared__ uint32_t part[1024];
+    for (int b = threadIdx.x; b < ORDER_BINS; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    auto bin_of = [&](int u) -> int {
+        uint32_t w = 0;
+#pragma unroll
+        for (int q = 0; q < TILE_PATCHES; q++) w = max(w, tile_last[(size_t)u * TILE_PATCHES + q]);
+        if (tile_src != nullptr && tile_src[u] != 0 && tile_cached != nullptr && tile_cached[(size_t)u * TILE_PATCHES] != 0) w = 0;
+        const uint32_t b = (w + 7u) >> 3;                       // 8 records per bin
+        return ORDER_BINS - 1 - (int)min(b, (uint32_t)(ORDER_BINS - 1));   // bin 0 = most work
+    };
+    for (int u = threadIdx.x; u < nunits; u += blockDim.x) atomicAdd(&hist[bin_of(u)], 1u);
+    __syncthreads();
+    // exclusive prefix sum over the bins: two bins per thread + a block scan of the per-thread sums
+    const uint32_t a0 = hist[2 * threadIdx.x], a1 = hist[2 * threadIdx.x + 1];
+    part[threadIdx.x] = a0 + a1;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const uint32_t add = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += add;
+        __syncthreads();
+    }
+    const uint32_t base = part[threadIdx.x] - (a0 + a1);
+    hist[2 * threadIdx.x] = base;
+    hist[2 * threadIdx.x + 1] = base + a0;
+    __syncthreads();
+    for (int u = threadIdx.x; u < nunits; u += blockDim.x) order[atomicAdd(&hist[bin_of(u)], 1u)] = (uint32_t)u;
 }
 
 }  // namespace fnx
@@ -2108,6 +2171,34 @@ int fnx_raster_read_tiles(const fnx_raster_scratch *scratch, int32_t W, int32_t 
     if (tile_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_last, im.tile_last, nt * 4 * TILE_PATCHES, cudaMemcpyDeviceToDevice, st));
     if (tile_src) FNX_CUDA_TRY(cudaMemcpyAsync(tile_src, im.tile_src, nt * 4, cudaMemcpyDeviceToDevice, st));
     if (tile_dyn_last) FNX_CUDA_TRY(cudaMemcpyAsync(tile_dyn_last, im.tile_dyn_last, nt * 4, cudaMemcpyDeviceToDevice, st));
+    return FNX_OK;
+}
+int fnx_raster_overflow_flag(const fnx_raster_scratch *scratch, const int32_t **flag_dev) {
+    FNX_REQUIRE(scratch && scratch->geom && flag_dev, "bad arguments");
+    *flag_dev = &reinterpret_cast<const GeomHeader *>(scratch->geom)->overflow;
+    return FNX_OK;
+}
+int fnx_raster_tile_cache_set(const fnx_raster_scratch *dyn, int32_t W, int32_t H, int32_t V, int32_t valid, fnx_stream_t stream) {
+    FNX_REQUIRE(dyn && dyn->image && W > 0 && H > 0 && V > 0, "bad arguments");
+    ImageView im = image_view(dyn->image, W, H, V);
+    const size_t nt = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
+    // (0x01010101 != 0 reads as "valid" just like 1: the flags are only ever compared with zero)
+    FNX_CUDA_TRY(cudaMemsetAsync(im.tile_cached, valid ? 0x01 : 0x00, sizeof(uint32_t) * nt * TILE_PATCHES, (cudaStream_t)stream));
+    return FNX_OK;
+}
+int fnx_raster_tile_order(const fnx_raster_scratch *scratch, const fnx_raster_scratch *stat, int32_t W, int32_t H, int32_t V,
+                          uint32_t *order, fnx_stream_t stream) {
+    FNX_REQUIRE(scratch && scratch->image && order && W > 0 && H > 0 && V > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    ImageView im = image_view(scratch->image, W, H, V);
+    const int nunits = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) * V;
+    const uint32_t *src = nullptr, *cached = nullptr;
+    if (stat != nullptr) {   // merged streams: tiles served from the tile cache did no work
+        src = im.tile_src;
+        cached = im.tile_cached;
+    }
+    tile_order_kernel<<<1, 1024, 0, st>>>(nunits, im.tile_last, src, cached, order);
+    FNX_LAUNCH_CHECK("tile_order_kernel");
     return FNX_OK;
 }
 int fnx_raster_backward_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,

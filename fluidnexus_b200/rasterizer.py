@@ -18,7 +18,8 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace", "MergedRasterWorkspace"]
+__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace", "MergedRasterWorkspace",
+           "StaticStream"]
 
 
 def _ptr(t):
@@ -114,6 +115,7 @@ def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_
         a.prefiltered = int(bool(prefiltered))
         a.flags = (L.FNX_EXACT_RECT if exact_rect else 0) | (L.FNX_BUCKET_BINNING if BUCKET_BINNING else 0)
         a.grad_begin, a.grad_end = (0, 0) if grad_range is None else (int(grad_range[0]), int(grad_range[1]))
+        a.tile_order, a.static_view_map, a.static_views = None, None, 0
         key = (dev.index, C_, V, W, H, P)
         a.instance_capacity_hint = _capacity_hint.get(key, 0) if speculative else 0
         bufs = (_Buf(dev), _Buf(dev), _Buf(dev))
@@ -163,6 +165,14 @@ def raster_backward(ctx, dL_dout_color, want_means2D=True):
     return g
 
 
+def _overflow_flag(geom):
+    sc = L.RasterScratch()
+    sc.geom, sc.geom_bytes = geom.data_ptr(), geom.numel()
+    p = C.c_void_p()
+    L.check(L.lib().fnx_raster_overflow_flag(C.byref(sc), C.byref(p)))
+    return p.value
+
+
 class RasterWorkspace:
     """Persistent buffers for repeated forward/backward of one fixed-size problem with NO allocation, NO host
     synchronisation and no events inside the calls (FNX_NO_HOST_SYNC), so a whole training iteration can be captured
@@ -182,9 +192,12 @@ class RasterWorkspace:
             shapes = dict(means3D=(P, 3), means2D=(V, P, 3), colors=(P, C_), opacity=(P, 1), scales=(P, 3), rotations=(P, 4),
                           cov3D=(P, 6))
             self.grads = {k: torch.empty(shapes[k], device=self.dev) for k in want}
+            # start order of the (view, tile) units for the blend kernels; identity until update_tile_order() ranks them by work
+            self.tile_order = torch.arange(V * ((W + 15) // 16) * ((H + 15) // 16), dtype=torch.int32, device=self.dev)
         self.count = torch.full((1,), -1, dtype=torch.int64).pin_memory()
         self._cbs = tuple(L.ALLOC_FN(self._fixed(t)) for t in (self.geom, self.binning, self.image))
         self.args, self.scratch, self._keep = L.RasterArgs(), L.RasterScratch(), None
+        self.forwards = 0
 
     @staticmethod
     def _fixed(t):
@@ -204,13 +217,21 @@ class RasterWorkspace:
         a.prefiltered, a.flags = 0, L.FNX_NO_HOST_SYNC | (L.FNX_EXACT_RECT if exact_rect else 0) | (L.FNX_BUCKET_BINNING if BUCKET_BINNING else 0)
         a.instance_capacity_hint, a.num_rendered_pinned = self.capacity, self.count.data_ptr()
         a.grad_begin, a.grad_end = (0, 0) if grad_range is None else (int(grad_range[0]), int(grad_range[1]))
+        a.tile_order = self.tile_order.data_ptr()
         self._keep = (bg, means3D, colors, opacities, scales, rotations, view_matrix, proj_matrix)
         nr = C.c_int64(0)
         fwd = L.lib().fnx_raster_forward_ch3 if self.C == 3 else L.lib().fnx_raster_forward_ch1
         L.check(fwd(C.byref(a), self._cbs[0], None, self._cbs[1], None, self._cbs[2], None, self.color.data_ptr(),
                     self.depth.data_ptr(), self.radii.data_ptr(), C.byref(nr), C.byref(self.scratch),
                     torch.cuda.current_stream(self.dev).cuda_stream))
+        self.forwards += 1
         return self.color
+
+    def update_tile_order(self):
+        """Rank the (view, tile) units by the work of the last forward, longest first (fnx_raster_tile_order): later forward /
+        backward calls start their CTAs in that order.  Enqueued on the current stream; scheduling only, results are unchanged."""
+        L.check(L.lib().fnx_raster_tile_order(C.byref(self.scratch), None, self.W, self.H, self.V, self.tile_order.data_ptr(),
+                                              torch.cuda.current_stream(self.dev).cuda_stream))
 
     def backward(self, dL_dout_color):
         gr = L.RasterGrads()
@@ -221,6 +242,10 @@ class RasterWorkspace:
         L.check(bwd(C.byref(self.args), C.byref(self.scratch), -1, self.radii.data_ptr(), dL_dout_color.data_ptr(), C.byref(gr),
                     torch.cuda.current_stream(self.dev).cuda_stream))
         return self.grads
+
+    def overflow_flag(self):
+        """Device address (int) of the forward's "instance capacity overflowed" flag (fnx_raster_overflow_flag)."""
+        return _overflow_flag(self.geom)
 
     def num_rendered(self):
         """Instance count of the last finished forward (call after a synchronisation point)."""
@@ -240,72 +265,111 @@ def _fill_args(a, C_, P, V, H, W, bg, means3D, colors, opacities, scales, rotati
     a.prefiltered, a.flags = 0, flags
     a.instance_capacity_hint, a.num_rendered_pinned = int(capacity), (pinned.data_ptr() if pinned is not None else None)
     a.grad_begin, a.grad_end = 0, 0
+    a.tile_order, a.static_view_map, a.static_views = None, None, 0
     return a
+
+
+class StaticStream:
+    """The frozen Gaussian set of a frame (FD/renderer/pipe_dynamics.py:51-57: the background set concatenated behind the fluid
+    particles), binned ONCE for all `V` cameras of the frame: its depth-sorted, tile-partitioned record stream stays in HBM and,
+    with prepare=True, so does its static-only render (color / depth [V,...]) and how deep that render reaches per tile.
+    Any number of MergedRasterWorkspaces -- one per subset of the cameras that an iteration renders; the reference draws
+    random.sample(cur_viewpoint_set, batch) -- share it through `view_ids`."""
+
+    def __init__(self, dev, V, H, W, bg, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, prepare=True):
+        lib = L.lib()
+        self.dev, self.V, self.H, self.W = torch.device(dev), V, H, W
+        self.P = static["means3D"].size(0)
+        self.cam = (bg, view_matrix, proj_matrix, float(tan_fov_x), float(tan_fov_y))
+        self._static = static
+        self.prepared = bool(prepare)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.device(self.dev):
+            self._bufs = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
+            self.args, self.scratch = L.RasterArgs(), L.RasterScratch()
+            self.radii = torch.empty((V, self.P), dtype=torch.int32, device=self.dev)
+            _fill_args(self.args, 3, self.P, V, H, W, bg, static["means3D"], static["colors"], static["opacities"], static["scales"],
+                       static["rotations"], 1.0, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, L.FNX_BIN_ONLY | L.FNX_ALL_FROZEN)
+            nr = C.c_int64(0)
+            L.check(lib.fnx_raster_forward_ch3(C.byref(self.args), self._bufs[0].cb, None, self._bufs[1].cb, None, self._bufs[2].cb, None,
+                                               None, None, self.radii.data_ptr(), C.byref(nr), C.byref(self.scratch), st))
+            self.R = int(nr.value)
+            nt = ((W + 15) // 16) * ((H + 15) // 16)
+            self.color = self.depth = None
+            self.reach = None            # [V] static records per view that a blend can reach (sum over tiles)
+            if prepare:
+                self.color = torch.empty((V, 3, H, W), device=self.dev)
+                self.depth = torch.empty((V, 1, H, W), device=self.dev)
+                L.check(lib.fnx_raster_static_prepare(C.byref(self.args), C.byref(self.scratch), self.color.data_ptr(), self.depth.data_ptr(), st))
+                last = torch.zeros((V * nt, 4), dtype=torch.int32, device=self.dev)  # per 8x8 patch
+                L.check(lib.fnx_raster_read_tiles(C.byref(self.scratch), W, H, V, 0, None, last.data_ptr(), None, None, st))
+                self.reach = last.max(dim=1).values.view(V, nt).sum(dim=1).cpu()
 
 
 class MergedRasterWorkspace:
     """Rasterizer workspace for [dynamic ; static] Gaussian sets (FD/renderer/pipe_dynamics.py:51-57 concatenates the
-    moving fluid particles with a frozen background set).  The static set's depth-sorted record stream is built once
-    at construction (cameras and the set must not change afterwards); every forward bins only the dynamic set and
-    merges the two streams per tile (fnx_raster_blend_merged).  Results equal one forward over the concatenated set;
-    gradients are produced for the dynamic Gaussians only.  3 channels.  No allocation / host sync / events inside
-    forward() and backward() (CUDA-graph capturable)."""
+    moving fluid particles with a frozen background set).  The static set's record stream lives in a StaticStream (built
+    here for exactly these cameras, or shared: `static_stream` + `view_ids` = which of its cameras this workspace renders);
+    every forward bins only the dynamic set and merges the two streams per tile (fnx_raster_blend_merged).  Results equal
+    one forward over the concatenated set; gradients are produced for the dynamic Gaussians only.  3 channels.  No
+    allocation / host sync / events inside forward() and backward() (CUDA-graph capturable)."""
 
     def __init__(self, dev, P_dyn, V, H, W, bg, dyn, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, margin=1.2,
-                 static_prepare=True, static_tile_cache=True, bucket_binning=True):
-        """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations.
-        static_prepare: blend the static stream alone once (fnx_raster_static_prepare), which bounds the static records
-        every later merge has to copy; static_tile_cache (needs static_prepare): tiles without a dynamic instance keep
-        their static-only pixels in self.color / self.depth instead of being re-blended every forward."""
+                 static_prepare=True, static_tile_cache=True, bucket_binning=True, static_stream=None, view_ids=None, slack=65536):
+        """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations (static may be
+        None when a static_stream is given).  view_matrix / proj_matrix: the V cameras this workspace renders.
+        static_prepare (private stream only): blend the static stream alone once, which bounds the static records every later
+        merge has to copy; static_tile_cache (needs a prepared stream): tiles without a dynamic instance keep their static-only
+        pixels in self.color / self.depth instead of being re-blended every forward."""
         lib = L.lib()
         self.dev, self.C, self.P, self.V, self.H, self.W = torch.device(dev), 3, P_dyn, V, H, W
-        self.P_static = static["means3D"].size(0)
+        if static_stream is None:
+            static_stream = StaticStream(dev, V, H, W, bg, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, prepare=static_prepare)
+            view_ids = list(range(V))
+        assert view_ids is not None and len(view_ids) == V and static_stream.H == H and static_stream.W == W
+        self.static = static_stream
+        self.view_ids = [int(v) for v in view_ids]
+        self.P_static, self.R_static = static_stream.P, static_stream.R
+        self.sscratch = static_stream.scratch
+        identity = self.view_ids == list(range(static_stream.V))
         self.cam = (bg, view_matrix, proj_matrix, float(tan_fov_x), float(tan_fov_y))
-        self._static = static
-        self.static_tile_cache = bool(static_tile_cache and static_prepare)
+        self.static_tile_cache = bool(static_tile_cache and static_stream.prepared)
         self.bucket_binning = bool(bucket_binning)  # per-tile buckets sorted inside the merge instead of two global radix sorts
         st = torch.cuda.current_stream(self.dev).cuda_stream
         with torch.cuda.device(self.dev):
-            self.color = torch.empty((V, 3, H, W), device=self.dev)
-            self.depth = torch.empty((V, 1, H, W), device=self.dev)
-            # ---- static stream: exact sizing, once ----
-            self._sbufs = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
-            self.sargs, self.sscratch = L.RasterArgs(), L.RasterScratch()
-            self.sradii = torch.empty((V, self.P_static), dtype=torch.int32, device=self.dev)
-            _fill_args(self.sargs, 3, self.P_static, V, H, W, bg, static["means3D"], static["colors"], static["opacities"],
-                       static["scales"], static["rotations"], 1.0, view_matrix, proj_matrix, tan_fov_x, tan_fov_y,
-                       L.FNX_BIN_ONLY | L.FNX_ALL_FROZEN)
-            nr = C.c_int64(0)
-            L.check(lib.fnx_raster_forward_ch3(C.byref(self.sargs), self._sbufs[0].cb, None, self._sbufs[1].cb, None, self._sbufs[2].cb,
-                                               None, None, None, self.sradii.data_ptr(), C.byref(nr), C.byref(self.sscratch), st))
-            self.R_static = int(nr.value)
-            if static_prepare:
-                L.check(lib.fnx_raster_static_prepare(C.byref(self.sargs), C.byref(self.sscratch), self.color.data_ptr(),
-                                                      self.depth.data_ptr(), st))
+            self.view_map = None if identity else torch.tensor(self.view_ids, dtype=torch.int32, device=self.dev)
+            if static_stream.prepared:   # start from the static-only render of these cameras: the tile cache's pixels
+                idx = torch.tensor(self.view_ids, dtype=torch.long, device=self.dev)
+                self.color, self.depth = static_stream.color[idx].contiguous(), static_stream.depth[idx].contiguous()
+            else:
+                self.color = torch.empty((V, 3, H, W), device=self.dev)
+                self.depth = torch.empty((V, 1, H, W), device=self.dev)
             # ---- dynamic stream: one exact binning to size the capacity ----
             tmp = (_Buf(self.dev), _Buf(self.dev), _Buf(self.dev))
             targs, tscratch = L.RasterArgs(), L.RasterScratch()
+            nr = C.c_int64(0)
             self.radii = torch.empty((V, P_dyn), dtype=torch.int32, device=self.dev)
             _fill_args(targs, 3, P_dyn, V, H, W, bg, dyn["means3D"], dyn["colors"], dyn["opacities"], dyn["scales"], dyn["rotations"],
                        1.0, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, L.FNX_BIN_ONLY)
             L.check(lib.fnx_raster_forward_ch3(C.byref(targs), tmp[0].cb, None, tmp[1].cb, None, tmp[2].cb, None, None, None,
                                                self.radii.data_ptr(), C.byref(nr), C.byref(tscratch), st))
             torch.cuda.synchronize(self.dev)
-            self.capacity = int(nr.value * margin) + 65536
+            self.capacity = int(nr.value * margin) + int(slack)   # dynamic instances the binning buffers hold
             del tmp
             u8 = lambda n: torch.empty(int(n), dtype=torch.uint8, device=self.dev)
             self.geom, self.image = u8(lib.fnx_raster_geom_bytes(P_dyn, V)), u8(lib.fnx_raster_image_bytes(W, H, V))
             self.binning = u8(lib.fnx_raster_binning_bytes(self.capacity, 3))
             # merged spans hold the tile's dynamic records + the static records a blend can reach: after the static-only
-            # blend that is sum(tile_last) static records instead of all R_static
-            n_static_reach = self.R_static
-            if static_prepare:
-                nt = V * ((W + 15) // 16) * ((H + 15) // 16)
-                last = torch.zeros((nt, 4), dtype=torch.int32, device=self.dev)  # per 8x8 patch
-                L.check(lib.fnx_raster_read_tiles(C.byref(self.sscratch), W, H, V, 0, None, last.data_ptr(), None, None, st))
-                n_static_reach = int(last.max(dim=1).values.sum().item())
+            # blend that is sum(tile_last) static records of these cameras instead of all of them
+            n_static_reach = int(static_stream.reach[self.view_ids].sum()) if static_stream.prepared else self.R_static
             self.merged = u8(48 * (self.capacity + n_static_reach) + 256)
             self.grads = {"means3D": torch.empty((P_dyn, 3), device=self.dev)}
+            self.tile_order = torch.arange(V * ((W + 15) // 16) * ((H + 15) // 16), dtype=torch.int32, device=self.dev)
+            # which tiles of self.color / self.depth hold their static-only pixels: all of them (copied above) or none
+            sc = L.RasterScratch()
+            sc.image, sc.image_bytes = self.image.data_ptr(), self.image.numel()
+            L.check(lib.fnx_raster_tile_cache_set(C.byref(sc), W, H, V, int(static_stream.prepared), st))
+        self.forwards = 0
         self.count = torch.full((1,), -1, dtype=torch.int64).pin_memory()
         self._cbs = tuple(L.ALLOC_FN(RasterWorkspace._fixed(t)) for t in (self.geom, self.binning, self.image))
         self.args, self.scratch, self._keep = L.RasterArgs(), L.RasterScratch(), None
@@ -316,6 +380,9 @@ class MergedRasterWorkspace:
         _fill_args(self.args, 3, self.P, self.V, self.H, self.W, bg, means3D, colors, opacities, scales, rotations, 1.0, vm, pm, tfx, tfy,
                    L.FNX_BIN_ONLY | L.FNX_NO_HOST_SYNC | (L.FNX_STATIC_TILE_CACHE if self.static_tile_cache else 0)
                    | (L.FNX_BUCKET_BINNING if self.bucket_binning else 0), self.capacity, self.count)
+        self.args.tile_order = self.tile_order.data_ptr()
+        self.args.static_view_map = None if self.view_map is None else self.view_map.data_ptr()
+        self.args.static_views = self.static.V
         self._keep = (means3D, colors, opacities, scales, rotations)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         nr = C.c_int64(0)
@@ -323,7 +390,13 @@ class MergedRasterWorkspace:
                                            self.radii.data_ptr(), C.byref(nr), C.byref(self.scratch), st))
         L.check(lib.fnx_raster_blend_merged(C.byref(self.args), C.byref(self.scratch), C.byref(self.sscratch), self.P_static,
                                             self.merged.data_ptr(), self.color.data_ptr(), self.depth.data_ptr(), st))
+        self.forwards += 1
         return self.color
+
+    def update_tile_order(self):
+        """See RasterWorkspace.update_tile_order; tiles served from the static tile cache rank last."""
+        L.check(L.lib().fnx_raster_tile_order(C.byref(self.scratch), C.byref(self.sscratch), self.W, self.H, self.V, self.tile_order.data_ptr(),
+                                              torch.cuda.current_stream(self.dev).cuda_stream))
 
     def backward(self, dL_dout_color):
         gr = L.RasterGrads()
@@ -346,6 +419,9 @@ class MergedRasterWorkspace:
         pl = last.cpu().numpy().astype("int64")   # per 8x8 patch of the tile
         return dict(begin=r[:, 0], end=r[:, 1], tile_last=pl.max(axis=1), patch_last=pl, tile_src=src.cpu().numpy(),
                     tile_dyn_last=dyn.cpu().numpy().astype("int64"))
+
+    def overflow_flag(self):
+        return _overflow_flag(self.geom)
 
     def num_rendered(self):
         """Dynamic instances of the last finished forward + the static stream's instances."""

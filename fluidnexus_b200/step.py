@@ -18,6 +18,7 @@ evaluated once (the reference re-evaluates them per view and averages, which giv
 hand-written gather kernel (no edge lists, no autograd graph); there is no host synchronisation inside the step
 (losses stay on the device until the caller reads them).
 """
+import os
 from dataclasses import dataclass
 
 import torch
@@ -105,7 +106,9 @@ class FrameState:
         self.zero_dmeans = None
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # Adam step count (device side: graph-replay safe)
         self.bc_dev = torch.zeros(2, dtype=torch.float32, device=dev)
-        self.ws = {}       # number of views -> RasterWorkspace
+        self.static_stream = None   # the frozen set binned once for ALL cameras (rasterizer.StaticStream), shared by the workspaces
+        self.skipped_iterations = 0  # iterations voided on the device because the rasterizer's instance capacity overflowed
+        self.ws = {}       # sorted view ids -> rasterizer workspace
         self.graphs = {}   # (view ids, update, batch, physics) -> two alternating (CUDAGraph, outputs, gt buffer, events) slots
 
     def bind_flat(self, param, exp_avg, exp_avg_sq, grad, loss_row=None):
@@ -136,9 +139,11 @@ class PhysicalStep:
         self.tan_fov_x, self.tan_fov_y = math.tan(c0.FoVx * 0.5), math.tan(c0.FoVy * 0.5)
         self.bg = _dev_f32([0.0] * channels if bg_color is None else bg_color, self.dev)
         self._loss_scratch, self._views = {}, {}
-        self.capacity_margin = 1.2   # binning capacity = margin * instances of the sizing forward + 64k
+        self.capacity_margin = 1.2   # binning capacity = margin * instances of the sizing forward + slack
+        self.capacity_slack = 65536
         self.static_cache = static_cache  # bin the frozen background once per frame (MergedRasterWorkspace)
         self.static_tile_cache = static_tile_cache  # ... and keep the pixels of tiles that hold no fluid instance
+        self.lpt_order = os.environ.get("FNX_LPT_ORDER", "1") != "0"   # longest-tile-first start order of the blend CTAs
         self.lib = L.lib()
         # the view-independent physics terms run on a side stream next to the rasterizer (fork/join with events, also
         # inside a captured graph); overlap=False keeps everything on one stream
@@ -220,13 +225,20 @@ class PhysicalStep:
         return self._views[key]
 
     def workspace(self, fr: FrameState, nviews, view_ids):
-        """Persistent rasterizer buffers for this frame; sized from one exact forward (the only one that blocks).
-        With a frozen background set (3 channels) the static stream is binned here once and only the fluid rows are
-        re-binned per iteration (MergedRasterWorkspace)."""
-        key = (nviews, tuple(view_ids))
+        """Persistent rasterizer buffers for this frame and this (sorted) set of cameras; sized from one exact forward (the only
+        one that blocks).  With a frozen background set (3 channels) the static stream is binned ONCE per frame for all cameras
+        (FrameState.static_stream) and shared by the workspaces of every camera subset an iteration may draw -- the reference
+        samples random.sample(cur_viewpoint_set, batch) cameras per iteration (train_physical_particle.py:337); only the fluid
+        rows are re-binned per iteration (MergedRasterWorkspace).  A workspace whose last forward overflowed its instance
+        capacity is dropped here and rebuilt with a fresh sizing forward."""
+        key = tuple(view_ids)
         ws = fr.ws.get(key)
         if ws is not None and ws.overflowed():   # the last finished forward overflowed: grow
             torch.cuda.synchronize(self.dev)
+            fr.ws.pop(key)
+            fr.graphs.clear()
+            fr.skipped_iterations += 1
+            self.capacity_margin = max(self.capacity_margin, 1.5)
             ws = None
         if ws is None:
             vm, pm = self._view_mats(view_ids)
@@ -235,15 +247,19 @@ class PhysicalStep:
                 sl = lambda t, a, b: t[a:b]
                 dyn = dict(means3D=sl(fr.means3D, 0, V), colors=sl(fr.colors, 0, V), opacities=sl(fr.opacity, 0, V),
                            scales=sl(fr.scales, 0, V), rotations=sl(fr.rotations, 0, V))
-                sta = dict(means3D=sl(fr.means3D, V, fr.P), colors=sl(fr.colors, V, fr.P), opacities=sl(fr.opacity, V, fr.P),
-                           scales=sl(fr.scales, V, fr.P), rotations=sl(fr.rotations, V, fr.P))
-                ws = R.MergedRasterWorkspace(self.dev, V, nviews, self.H, self.W, self.bg, dyn, sta, vm, pm, self.tan_fov_x,
-                                             self.tan_fov_y, margin=self.capacity_margin, static_tile_cache=self.static_tile_cache)
+                if fr.static_stream is None:
+                    sta = dict(means3D=sl(fr.means3D, V, fr.P), colors=sl(fr.colors, V, fr.P), opacities=sl(fr.opacity, V, fr.P),
+                               scales=sl(fr.scales, V, fr.P), rotations=sl(fr.rotations, V, fr.P))
+                    fr.static_stream = R.StaticStream(self.dev, self.view_all.size(0), self.H, self.W, self.bg, sta, self.view_all, self.proj_all,
+                                                      self.tan_fov_x, self.tan_fov_y)
+                ws = R.MergedRasterWorkspace(self.dev, V, nviews, self.H, self.W, self.bg, dyn, None, vm, pm, self.tan_fov_x,
+                                             self.tan_fov_y, margin=self.capacity_margin, static_tile_cache=self.static_tile_cache,
+                                             static_stream=fr.static_stream, view_ids=list(view_ids), slack=self.capacity_slack)
                 ws.dyn = dyn
             else:
                 ctx, _, _, _ = R.raster_forward(self.C, self.bg, fr.means3D, fr.colors, fr.opacity, fr.scales, fr.rotations, 1.0, None,
                                                 vm, pm, self.tan_fov_x, self.tan_fov_y, self.H, self.W, speculative=False)
-                cap = int(ctx.num_rendered * self.capacity_margin) + 65536
+                cap = int(ctx.num_rendered * self.capacity_margin) + self.capacity_slack
                 del ctx
                 ws = R.RasterWorkspace(self.dev, self.C, fr.P, nviews, self.H, self.W, cap)
             fr.ws[key] = ws
@@ -252,6 +268,15 @@ class PhysicalStep:
 
     def render(self, fr: FrameState, view_ids):
         ws = self.workspace(fr, len(view_ids), view_ids)
+        first = ws.forwards == 0
+        ws = self._render(fr, ws, view_ids)
+        if first and self.lpt_order:
+            # rank the tiles by the work of this first forward: every later blend launch (also the captured ones) starts the long
+            # tiles first.  The scene of a frame barely moves between iterations, so the order is taken once.
+            ws.update_tile_order()
+        return ws
+
+    def _render(self, fr: FrameState, ws, view_ids):
         if isinstance(ws, R.MergedRasterWorkspace):
             d = ws.dyn
             ws.forward(d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"])
@@ -281,7 +306,7 @@ class PhysicalStep:
                                    l1.data_ptr(), ss.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
         return l1, ss, g
 
-    def physics_backward_and_update(self, fr: FrameState, dL_dmeans3D, grad_extra=None, update=True, physics=True):
+    def physics_backward_and_update(self, fr: FrameState, dL_dmeans3D, grad_extra=None, update=True, physics=True, skip_flag=None):
         """P1-backward (image + distance gradients -> hidden particles), P3 chain, P4, Adam."""
         lib, prm, st = self.lib, self.prm, torch.cuda.current_stream(self.dev).cuda_stream
         N, V = fr.N, fr.V
@@ -299,28 +324,32 @@ class PhysicalStep:
         if grad_extra is not None:
             fr.de.add_(grad_extra)
         if update:
-            self.adam(fr)
+            self.adam(fr, skip_flag=skip_flag)
 
-    def adam(self, fr: FrameState, grad=None, grad_scale=1.0):
+    def adam(self, fr: FrameState, grad=None, grad_scale=1.0, skip_flag=None):
+        """torch.optim.Adam(eps=1e-15) step on the frame's trainable tensor.  skip_flag: device address of an int32 that voids the
+        update when non-zero (the rasterizer's overflow flag: a forward that overflowed its instance capacity renders only the
+        background, its image gradient is zero and the physics-only update must not be applied)."""
         g = fr.de if grad is None else grad
-        L.check(self.lib.fnx_adam_step_dev(fr.e.numel(), fr.e.data_ptr(), g.data_ptr(), fr.m.data_ptr(), fr.v.data_ptr(), grad_scale,
-                                           self.prm.lr, 0.9, 0.999, self.prm.adam_eps, fr.step_dev.data_ptr(), fr.bc_dev.data_ptr(),
-                                           torch.cuda.current_stream(self.dev).cuda_stream))
+        L.check(self.lib.fnx_adam_step_dev_gated(fr.e.numel(), fr.e.data_ptr(), g.data_ptr(), fr.m.data_ptr(), fr.v.data_ptr(), grad_scale,
+                                                 self.prm.lr, 0.9, 0.999, self.prm.adam_eps, fr.step_dev.data_ptr(), fr.bc_dev.data_ptr(),
+                                                 skip_flag, torch.cuda.current_stream(self.dev).cuda_stream))
 
     # -- the step -------------------------------------------------------------------------------------------
     def _iteration(self, fr: FrameState, view_ids, gt, update, batch, physics=True):
         self.physics_forward(fr, physics)
-        out = {}
+        out, skip = {}, None
         if len(view_ids):
             ws = self.render(fr, view_ids)
             l1, ss, g = self.image_loss(ws.color, gt, batch, fr)
             dmeans = ws.backward(g)["means3D"]
-            out.update(l1=l1, ssim=ss, images=ws.color, radii=ws.radii, ws=ws)
+            skip = ws.overflow_flag()
+            out.update(l1=l1, ssim=ss, images=ws.color, radii=ws.radii, ws=ws, view_ids=list(view_ids))
         else:
             if fr.zero_dmeans is None:
                 fr.zero_dmeans = torch.zeros((fr.P, 3), device=self.dev)
             dmeans = fr.zero_dmeans
-        self.physics_backward_and_update(fr, dmeans, update=update, physics=physics)
+        self.physics_backward_and_update(fr, dmeans, update=update, physics=physics, skip_flag=skip)
         out.update(gas=fr.scalars[0], next_gas=fr.scalars[1], exyz=fr.scalars[2], dist=fr.scalars[3], grad=fr.de)
         return out
 
@@ -332,6 +361,15 @@ class PhysicalStep:
         into a CUDA graph on first use and replays it afterwards (one host call per iteration).
         Returns device tensors that are overwritten by the next step; there is no host synchronisation."""
         batch = len(view_ids) if batch is None else batch
+        # canonical camera order: the workspaces / captured graphs of a frame are keyed by the SET of cameras, so drawing the
+        # same cameras in another order (random.sample) reuses them; the per-view outputs (l1, ssim, images) come back in
+        # ascending camera order (out["view_ids"])
+        ids = [int(v) for v in view_ids]
+        perm = sorted(range(len(ids)), key=ids.__getitem__)
+        if perm != list(range(len(ids))):
+            view_ids, gt = [ids[k] for k in perm], gt[perm]
+        else:
+            view_ids = ids
         with torch.cuda.device(self.dev):
             if not graph:
                 if not gt.is_cuda:
@@ -339,6 +377,14 @@ class PhysicalStep:
                 return self._iteration(fr, view_ids, gt, update, batch, physics)
             key = (tuple(view_ids), bool(update), batch, bool(physics))
             ent = fr.graphs.get(key)
+            if ent is not None:
+                ws = ent["slots"][0][1].get("ws")
+                if ws is not None and ws.overflowed():
+                    # A replay overflowed the workspace's instance capacity (the fluid moved into many more tiles).  That
+                    # iteration rendered only the background and its update was voided ON THE DEVICE (adam: skip_flag), so the
+                    # state is intact: drop the workspace and its graphs, re-size, re-capture and carry on.
+                    self.workspace(fr, len(view_ids), view_ids)
+                    ent = None
             if ent is None:
                 # everything that allocates or blocks happens eagerly first (workspace sizing, visual grid, scratch)
                 gt_bufs = [torch.empty((len(view_ids), self.C, self.H, self.W), device=self.dev) for _ in range(2)]
@@ -363,10 +409,6 @@ class PhysicalStep:
                 fr.graphs[key] = ent
             g, out, gt_buf, ev_copied, ev_done = ent["slots"][ent["next"]]
             ent["next"] ^= 1
-            ws = out.get("ws")
-            if ws is not None and ws.overflowed():
-                raise RuntimeError("rasterizer instance capacity exceeded inside a captured iteration; re-capture "
-                                   f"(capacity {ws.capacity})")
             main = torch.cuda.current_stream(self.dev)
             if gt.is_cuda:
                 gt_buf.copy_(gt, non_blocking=True)

@@ -68,10 +68,13 @@ unsigned long long fnx_launch_count(void);
 #define FNX_BIN_ONLY 4u     /* forward: stop after the record stream is packed (no blending; out_color/out_depth may be
                                NULL).  Used to build a stream that fnx_raster_blend_merged consumes. */
 #define FNX_ALL_FROZEN 8u   /* every Gaussian of this call is frozen (no gradients): marks all its records */
-#define FNX_STATIC_TILE_CACHE 16u /* fnx_raster_blend_merged only: tiles without any dynamic instance keep the pixels that
-                               fnx_raster_static_prepare (or an earlier call) left in out_color / out_depth instead of being
-                               blended again -- the frozen set and the cameras are fixed, so those pixels cannot change.
-                               The SAME out_color / out_depth buffers must be passed to every call. */
+#define FNX_STATIC_TILE_CACHE 16u /* fnx_raster_blend_merged only: tiles without any dynamic instance keep the pixels that are
+                               already in out_color / out_depth instead of being blended again -- the frozen set and the
+                               cameras are fixed, so those pixels cannot change.  Which tiles of out_color / out_depth hold valid
+                               static-only pixels is tracked per 8x8 patch in the DYNAMIC scratch's image buffer: reset with
+                               fnx_raster_tile_cache_set(valid = 0) for fresh buffers, or (valid = 1) after copying the
+                               static-only render of fnx_raster_static_prepare into them.  The SAME out_color / out_depth
+                               buffers and image scratch must be passed to every call. */
 
 #define FNX_BUCKET_BINNING 32u /* no global sorts: instances are histogrammed per tile and dropped into per-tile buckets, each
                                bucket is sorted by (depth, index) in shared memory.  Results are identical to the sorted
@@ -107,6 +110,17 @@ typedef struct fnx_raster_args {
                                        FROZEN (e.g. the background set that FD/renderer/pipe_dynamics.py:51-57 concatenates
                                        behind the fluid particles): they still occlude, but their gradient rows are
                                        written as zeros.  grad_end <= grad_begin means "all" (the reference's behaviour). */
+    const uint32_t *tile_order;     /* optional DEVICE array of V * tiles entries (tiles = ceil(W/16) * ceil(H/16)): a permutation
+                                       of the (view, tile) units, view * tiles + tile, in the order the blend kernels should start
+                                       them (fnx_raster_tile_order: longest first).  NULL = natural order.  Scheduling only:
+                                       results do not depend on it. */
+    const int32_t *static_view_map; /* fnx_raster_blend_merged only: DEVICE array of V entries, static_view_map[v] = index of this
+                                       call's view v among the `static_views` cameras the static stream was built for, so that ONE
+                                       static stream per frame serves every subset of its cameras (the reference draws
+                                       random.sample(cur_viewpoint_set, batch) cameras per iteration,
+                                       FD/entries_fluid_nexus/train_physical_particle.py:337).  NULL = identity (static_views == V). */
+    int32_t static_views;           /* cameras of the static stream (0 = V) */
+    int32_t reserved0;
 } fnx_raster_args;
 
 /* Opaque handles to the three scratch buffers of one forward (what the reference returns as
@@ -188,6 +202,23 @@ int fnx_raster_static_prepare(const fnx_raster_args *static_args, const fnx_rast
 int fnx_raster_backward_merged(const fnx_raster_args *dyn_args, const fnx_raster_scratch *dyn, const fnx_raster_scratch *stat,
                                const void *merged_records, const int32_t *radii, const float *dL_dout_color,
                                const fnx_raster_grads *g, fnx_stream_t stream);
+
+/* Device address of the "instance capacity overflowed" flag (int32, 0 / 1) that every forward on `scratch` (its geom buffer must
+ * be set) writes: lets later kernels of the same stream -- fnx_adam_step_dev_gated -- drop the work of a void forward without a
+ * host round trip. */
+int fnx_raster_overflow_flag(const fnx_raster_scratch *scratch, const int32_t **flag_dev);
+
+/* Marks every tile of the out_color / out_depth buffers that go with the dynamic scratch `dyn` as holding (valid != 0) or not
+ * holding (0) its static-only pixels; see FNX_STATIC_TILE_CACHE.  `dyn->image` must be set. */
+int fnx_raster_tile_cache_set(const fnx_raster_scratch *dyn, int32_t W, int32_t H, int32_t V, int32_t valid, fnx_stream_t stream);
+
+/* Longest-first order of the (view, tile) units by the work of the LAST forward on `scratch` (for merged streams pass the
+ * static stream's scratch as `stat`, else NULL), for fnx_raster_args.tile_order of later forward / backward calls on the same
+ * scene.  order: V * tiles uint32 (device).  The reference dispatches one block per tile in raster order
+ * (R3/cuda_rasterizer/forward.cu:389); with a few hundred long tiles among thousands of short ones that leaves the SMs idle
+ * for the last ~20 % of the kernel. */
+int fnx_raster_tile_order(const fnx_raster_scratch *scratch, const fnx_raster_scratch *stat, int32_t W, int32_t H, int32_t V,
+                          uint32_t *order, fnx_stream_t stream);
 
 /* After a FNX_NO_HOST_SYNC forward: blocks until the forward's instance count is known and returns FNX_OK or
  * FNX_ERR_CAPACITY; *num_rendered_host is set either way. */
@@ -324,6 +355,13 @@ int fnx_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, fl
  * safe to capture once into a CUDA graph and replay. */
 int fnx_adam_step_dev(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale,
                       float lr, float beta1, float beta2, float eps, int32_t *step_dev, float *bc_dev, fnx_stream_t stream);
+
+/* The same, gated: when skip_flag (device int32, may be NULL) is non-zero at execution time the call leaves parameters, moments and
+ * *step_dev untouched.  The fused step passes the rasterizer's overflow flag (fnx_raster_overflow_flag): a forward whose instance
+ * capacity overflowed renders only the background, its gradient is void, and the update must not be applied. */
+int fnx_adam_step_dev_gated(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float grad_scale,
+                            float lr, float beta1, float beta2, float eps, int32_t *step_dev, float *bc_dev,
+                            const int32_t *skip_flag, fnx_stream_t stream);
 
 /* torch_scatter.scatter_min(src, index, dim_size=n_out) for 1-D fp32 src and int64 index (gm_fluid.py:1088,1272):
  * out [n_out] (0 for empty groups), arg [n_out] int64 (n for empty groups). */

@@ -149,12 +149,16 @@ class StockTrainer:
     CASES = {3: ("fluid_nexus_smoke_dynamics", "fluid_nexus_physical_current", "render_dynamics"),
              1: ("scalar_real", "scalar_real_physical_current", "render_fluid")}
 
-    def __init__(self, prm, hidden, visual_scaled, fluid, background, channels, cams, gts_cpu, with_distance=True, config=None):
+    def __init__(self, prm, hidden, visual_scaled, fluid, background, channels, cams, gts_cpu, with_distance=True, config=None,
+                 native="reference"):
+        """native="reference": the reference arm (compiled reference rasterizer, particle state and physics on the host).
+        native="fnx": the same stock Python with the five plugin imports bound to libfnx's drop-ins and EVERYTHING on the GPU,
+        as the reference runs it with torch_cluster installed -- what a user of the unchanged scripts gets from the drop-ins."""
         import random
         import tempfile
 
         from . import ref_python as RP
-        RP.use_reference_python("reference")
+        RP.use_reference_python(native)
         from helpers.helper_gaussian import get_model
         from helpers.helper_pipe import get_render_pipe
         from scene.camera import Camera
@@ -166,15 +170,16 @@ class StockTrainer:
         optim_args.p0, optim_args.buoyancy_max_y = prm.p0, prm.buoyancy_max_y
         optim_args.distance_threshold_visual = prm.distance_threshold_visual
         optim_args.batch = len(cams)
-        gm = make_host_physics_model(get_model(model_args.model))(model_args.sh_degree)
+        gm = make_host_physics_model(get_model(model_args.model))(model_args.sh_degree)   # (on the GPU the overrides are no-ops)
         gm.setup_constants(optim_args)
         gm.spatial_lr_scale = 1.0
-        f32 = lambda a: torch.as_tensor(a, dtype=torch.float32)
+        pdev = "cpu" if native == "reference" else "cuda"
+        f32 = lambda a: torch.as_tensor(a, dtype=torch.float32).to(pdev)
         gm._xyz, gm._estimate_xyz = f32(hidden.xyz), f32(hidden.estimate_xyz)
         gm._velocity, gm._force, gm._buoyancy, gm._imass = f32(hidden.velocity), f32(hidden.force), f32(hidden.buoyancy), f32(hidden.imass)
-        gm._counts = torch.zeros((hidden.N, 1))
+        gm._counts = torch.zeros((hidden.N, 1), device=pdev)
         gm._visual_xyz = f32(visual_scaled)
-        gm.training_setup_current(optim_args)           # CPU Parameter: _estimate_xyz is on the CPU
+        gm.training_setup_current(optim_args)           # the Parameter lives where _estimate_xyz lives
         # rendering attributes of the fluid particles and the frozen background set: on the GPU, as raw (pre-activation) values
         dev = "cuda"
         g = lambda s, k: f32(getattr(s, k)).to(dev)

@@ -12,7 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-COMMON = ["--workload", "tiny", "--steps", "4", "--warmup", "3", "--min-leg-seconds", "0.2", "--no-cpu-baseline", "--verify"]
+COMMON = ["--workload", "tiny", "--steps", "4", "--warmup", "3", "--min-leg-seconds", "0.2", "--no-cpu-baseline", "--no-dropin", "--verify"]
 
 
 def _free_port():

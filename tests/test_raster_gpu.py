@@ -299,3 +299,78 @@ def test_bucket_binning_equals_sorted_binning(libfnx, monkeypatch):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and a[3] == b[3], name
         for k in ("means3D", "means2D", "colors", "opacity", "scales", "rotations"):
             assert rel(b[4][k].cpu().numpy(), a[4][k].cpu().numpy()) < 2e-5, (name, k)
+
+
+def test_tile_order_is_a_work_sorted_permutation_and_changes_nothing(libfnx):
+    """fnx_raster_tile_order: a permutation of the (view, tile) units, longest tile first (8-record bins); forward images and
+    backward gradients with the order are those without it (bit-identical images; gradients to float-atomic noise)."""
+    gs = S.cat_sets(S.fluid_gaussians(3000, 3, seed=10), S.background_gaussians(3000, 3, seed=11))
+    cams = S.make_cameras(5, 128)
+    dev = torch.device("cuda")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+    inp = S.raster_inputs(gs, cams[0], np.array([0.1, 0.2, 0.3], np.float32))
+    view = torch.stack([c.world_view_transform for c in cams]).to(dev).contiguous()
+    proj = torch.stack([c.full_proj_transform for c in cams]).to(dev).contiguous()
+    ws = R.RasterWorkspace(dev, 3, gs.P, 5, 128, 128, 400_000, want=("means3D", "colors", "opacity"))
+    args = (t(inp["bg"]), t(inp["means3D"]), t(inp["colors"]), t(inp["opacities"]).reshape(-1).contiguous(), t(inp["scales"]), t(inp["rotations"]), 1.0,
+            view, proj, inp["tan_fov_x"], inp["tan_fov_y"])
+    img0 = ws.forward(*args).clone()
+    dL = torch.randn(img0.shape, device=dev, generator=torch.Generator("cuda").manual_seed(3))
+    g0 = {k: v.clone() for k, v in ws.backward(dL).items()}
+    ws.update_tile_order()
+    torch.cuda.synchronize()
+    order = ws.tile_order.cpu().numpy()
+    n = 5 * 8 * 8
+    assert sorted(order.tolist()) == list(range(n))
+    st = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+    import ctypes as C
+    from fluidnexus_b200 import _lib as L
+    L.check(L.lib().fnx_raster_read_tiles(C.byref(ws.scratch), 128, 128, 5, 0, None, st.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream))
+    work = st.max(dim=1).values.cpu().numpy()[order]
+    bins = (work + 7) // 8
+    assert (np.diff(bins) <= 0).all() and work[0] == work.max() and work.max() > 8 * work[work > 0].min()
+    img1 = ws.forward(*args)
+    assert torch.equal(img1, img0)
+    g1 = ws.backward(dL)
+    for k in g0:
+        assert float((g1[k] - g0[k]).norm() / g0[k].norm()) < 1e-5, k
+
+
+@pytest.mark.parametrize("subset", [[1, 3], [4, 0, 2], [2]])
+def test_one_static_stream_serves_every_camera_subset(libfnx, subset):
+    """the static stream of a frame is built ONCE for all cameras (StaticStream); MergedRasterWorkspaces for subsets of
+    the cameras (in any order -- the reference draws random.sample(view_set, batch)) share it through static_view_map and give
+    exactly the image / depth / gradient of one plain forward over [dynamic ; static] with those cameras."""
+    import math
+    dev = torch.device("cuda")
+    size, nd = 128, 900
+    cams = S.make_cameras(5, size, device=dev)
+    view_all = torch.stack([c.world_view_transform.float() for c in cams]).contiguous()
+    proj_all = torch.stack([c.full_proj_transform.float() for c in cams]).contiguous()
+    tfx, tfy = math.tan(cams[0].FoVx * 0.5), math.tan(cams[0].FoVy * 0.5)
+    d, s = S.fluid_gaussians(nd, 3, seed=60, log_scale=-4.8).torch(dev), S.background_gaussians(5000, 3, seed=61).torch(dev)
+    key = dict(means3D="xyz", colors="colors", opacities="opacity", scales="scales", rotations="rotations")
+    dyn = {k: d[v].reshape(-1).contiguous() if k == "opacities" else d[v].contiguous() for k, v in key.items()}
+    sta = {k: s[v].reshape(-1).contiguous() if k == "opacities" else s[v].contiguous() for k, v in key.items()}
+    bg = torch.tensor([0.05, 0.1, 0.2], device=dev)
+    stream = R.StaticStream(dev, 5, size, size, bg, sta, view_all, proj_all, tfx, tfy)
+    idx = torch.tensor(subset, device=dev)
+    view, proj = view_all[idx].contiguous(), proj_all[idx].contiguous()
+    ws = R.MergedRasterWorkspace(dev, nd, len(subset), size, size, bg, dyn, None, view, proj, tfx, tfy, margin=3.0, static_stream=stream,
+                                 view_ids=subset)
+    base = dyn["means3D"].clone()
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    for it, off in enumerate([(0.0, 0.0, 0.0), (0.08, 0.0, 0.0), (5.0, 0.0, 0.0), (0.02, -0.04, 0.0)]):
+        dyn["means3D"].copy_(base + torch.tensor(off, device=dev))
+        img = ws.forward(dyn["means3D"], dyn["colors"], dyn["opacities"], dyn["scales"], dyn["rotations"])
+        dL = torch.randn(len(subset), 3, size, size, generator=gen).to(dev)
+        g = ws.backward(dL)["means3D"].clone()
+        cat = lambda k: torch.cat([dyn[k], sta[k]], 0).contiguous()
+        ctx, ref_img, _, ref_depth = R.raster_forward(3, bg, cat("means3D"), cat("colors"), cat("opacities"), cat("scales"), cat("rotations"), 1.0,
+                                                      None, view, proj, tfx, tfy, size, size, speculative=False)
+        assert torch.equal(img, ref_img), (it, float((img - ref_img).abs().max()))
+        assert torch.equal(ws.depth, ref_depth), it
+        gref = R.raster_backward(ctx, dL)["means3D"][:nd]
+        r = rel(g.cpu().numpy(), gref.cpu().numpy()) if float(gref.abs().max()) > 0 else float(g.abs().max())
+        assert r < 2e-5, (it, r)
+    assert (ws.tile_state()["tile_src"] != 0).sum() > 0

@@ -175,3 +175,52 @@ def test_frame_lanes_equal_sequential_frames(libfnx):
     assert np.allclose(res[1][0], res[2][0], rtol=1e-5)
     for a, b in zip(res[1][1], res[2][1]):
         assert (a - b).abs().max() < 1e-6
+
+
+def test_view_subsets_share_the_static_stream_and_any_order_gives_the_same_step(libfnx):
+    """one static stream per frame whatever cameras an iteration draws; the same cameras in another order reuse the
+    workspace (and give the same update)."""
+    hp, vis, fluid, bg, cams = _scene(3, True, seed=5)
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    ps = PhysicalStep(cams, 3, prm)
+    gt = torch.rand(5, 3, 64, 64, device="cuda") * 0.5
+    fa, fb = FrameState(hp, vis, fluid, bg, prm=prm), FrameState(hp, vis, fluid, bg, prm=prm)
+    for views in ([0, 2, 4], [1, 3], [2, 0, 4], [3]):
+        idx = torch.tensor(views, device="cuda")
+        ps.step(fa, views, gt[idx])
+        ps.step(fb, sorted(views), gt[torch.tensor(sorted(views), device="cuda")])
+    torch.cuda.synchronize()
+    assert len(fa.ws) == 3 and fa.static_stream is not None and all(w.static is fa.static_stream for w in fa.ws.values())
+    assert float((fa.e - fb.e).abs().max()) < 1e-7
+
+
+def test_overflowed_iteration_is_voided_on_the_device_and_recovered(libfnx):
+    """when the fluid spreads over many more tiles than the workspace was sized for, the forward overflows its instance
+    capacity and renders only the background.  The update of that iteration must not be applied (Adam is gated by the device-side
+    overflow flag: parameters, moments and step count untouched), and the next step re-sizes (re-captures) and carries on."""
+    hp, vis, fluid, bg, cams = _scene(3, True, seed=6)
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    gt = torch.rand(5, 3, 64, 64, device="cuda") * 0.5
+    views = [0, 1, 2, 3, 4]
+    for graph in (False, True):
+        ps = PhysicalStep(cams, 3, prm)
+        ps.capacity_slack = 256                      # (the default slack of 64k instances exceeds what this tiny scene can produce)
+        fr = FrameState(hp, vis, fluid, bg, prm=prm)
+        ps.step(fr, views, gt, graph=graph)
+        ps.step(fr, views, gt, graph=graph)
+        torch.cuda.synchronize()
+        ws = fr.ws[tuple(views)]
+        assert not ws.overflowed() and int(fr.step_dev) == 2
+        # blow the splats up: every fluid Gaussian now touches every tile -> far beyond the capacity
+        scales0 = fr.scales[:fr.V].clone()
+        fr.scales[:fr.V] *= 60.0
+        e0, m0, v0 = fr.e.clone(), fr.m.clone(), fr.v.clone()
+        ps.step(fr, views, gt, graph=graph)
+        torch.cuda.synchronize()
+        assert ws.overflowed()
+        assert torch.equal(fr.e, e0) and torch.equal(fr.m, m0) and torch.equal(fr.v, v0) and int(fr.step_dev) == 2
+        fr.scales[:fr.V] = scales0
+        ps.step(fr, views, gt, graph=graph)          # notices the overflow, rebuilds the workspace (graph: re-captures), steps
+        torch.cuda.synchronize()
+        assert fr.skipped_iterations == 1 and not fr.ws[tuple(views)].overflowed() and fr.ws[tuple(views)] is not ws
+        assert int(fr.step_dev) == 3 and float((fr.e - e0).abs().max()) > 0
