@@ -22,6 +22,7 @@
 //     and merged per tile; tiles without a moving instance keep their pixels; the backward starts at the tile's last
 //     moving record from a snapshot the forward took there.
 #include <cub/cub.cuh>
+#include <mutex>
 
 #include "raster.cuh"
 
@@ -1442,8 +1443,12 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, co
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-struct PinnedSlots {  // ring of pinned int64 slots + events for the sync-free instance count read-back
-    static constexpr int N = 64;
+// Ring of pinned int64 slots + events for the instance-count read-back of forwards that are allowed to wait for it.  One ring
+// per DEVICE, shared by all host threads (a forward and the fnx_raster_check that goes with it may run on different threads --
+// PyTorch's autograd worker -- so nothing here is thread_local); slots are handed out under a mutex.  A slot is reused after N
+// later forwards on the same device: fnx_raster_check must be called before that (documented in include/fnx.h).
+struct PinnedSlots {
+    static constexpr int N = 256;
     long long *host = nullptr;
     cudaEvent_t ev[N];
     int next = 0;
@@ -1456,7 +1461,14 @@ struct PinnedSlots {  // ring of pinned int64 slots + events for the sync-free i
         return FNX_OK;
     }
 };
-static thread_local PinnedSlots g_slots;
+constexpr int MAX_DEVICES = 32;
+static PinnedSlots g_slots_of_device[MAX_DEVICES];
+static std::mutex g_slots_mutex;
+static int current_device_index() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+    return d;
+}
 
 static int validate(const fnx_raster_args *a) {
     FNX_REQUIRE(a != nullptr, "args is NULL");
@@ -1562,11 +1574,8 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
         const bool use_mask = (long long)P * V < (1ll << SLOT_BITS);
         const bool all_frozen = (a->flags & FNX_ALL_FROZEN) != 0;
         const bool all_grad = !all_frozen && a->grad_end <= a->grad_begin;
-        static bool attr_set = false;
-        if (!attr_set) {
-            FNX_CUDA_TRY(cudaFuncSetAttribute(pack_bucket_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SORT_CAP * 8));
-            attr_set = true;
-        }
+        // (per device / context, so set on every call: it is a host-side table update, not a launch)
+        FNX_CUDA_TRY(cudaFuncSetAttribute(pack_bucket_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SORT_CAP * 8));
         FNX_CUDA_TRY(cudaMemsetAsync(im.tile_cursor, 0, sizeof(uint32_t) * (size_t)ntiles * V, st));
         prof_begin(SEC_EMIT, st);
         emit_bucket_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, P, gx, gy, exact_rect, radii, g, im.ranges, im.tile_cursor, b.bkeys);
@@ -1642,7 +1651,8 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
     FNX_REQUIRE(!no_sync || a->instance_capacity_hint > 0, "FNX_NO_HOST_SYNC needs instance_capacity_hint > 0");
     int rc = FNX_OK;
     if (!no_sync) {
-        rc = g_slots.init();
+        std::lock_guard<std::mutex> lock(g_slots_mutex);
+        rc = g_slots_of_device[current_device_index()].init();
         if (rc) return rc;
     }
 
@@ -1736,8 +1746,14 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         return rc;
     }
 
-    const int slot_id = g_slots.next;
-    g_slots.next = (g_slots.next + 1) % PinnedSlots::N;
+    const int dev_id = current_device_index();
+    PinnedSlots &g_slots = g_slots_of_device[dev_id];
+    int slot_id;
+    {
+        std::lock_guard<std::mutex> lock(g_slots_mutex);
+        slot_id = g_slots.next;
+        g_slots.next = (g_slots.next + 1) % PinnedSlots::N;
+    }
     long long *pinned = g_slots.host + slot_id;
     *pinned = -1;
     rc = write_header(cap, pinned);
@@ -1776,6 +1792,7 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
     *num_rendered_host = R;
     if (a->num_rendered_pinned) *a->num_rendered_pinned = R;
     scratch->check_slot = slot_id;
+    scratch->reserved = dev_id;   // the device whose ring holds the slot
     return FNX_OK;
 }
 
@@ -2212,6 +2229,8 @@ int fnx_raster_check(const fnx_raster_scratch *scratch, int64_t *num_rendered_ho
     FNX_REQUIRE(scratch && num_rendered_host, "scratch / num_rendered_host must be given");
     long long R = -1;
     if (scratch->check_slot >= 0) {
+        FNX_REQUIRE(scratch->reserved >= 0 && scratch->reserved < MAX_DEVICES, "no forward to check");
+        PinnedSlots &g_slots = g_slots_of_device[scratch->reserved];
         FNX_REQUIRE(g_slots.ok && scratch->check_slot < PinnedSlots::N, "no forward to check");
         FNX_CUDA_TRY(cudaEventSynchronize(g_slots.ev[scratch->check_slot]));
         R = g_slots.host[scratch->check_slot];

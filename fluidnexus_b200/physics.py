@@ -124,6 +124,27 @@ def scatter_min(src, index, dim=-1, out=None, dim_size=None):
     return res.to(src.dtype), arg
 
 
+def _spacing_cell(p):
+    """Grid cell for the 3-nearest-neighbour search: ~1.5 x the typical inter-point spacing.  The spacing is estimated from the
+    5 %..95 % quantile box of (a sample of) the points -- a few far outliers must not inflate it -- over the axes along which
+    the cloud actually extends: a planar or linear cloud (an extent below 1e-4 of the largest) is treated as 2-D / 1-D, where the
+    bounding-box VOLUME would give a cell orders of magnitude below the spacing and send every query into the exhaustive
+    fallback of knn3_kernel."""
+    n = p.size(0)
+    q = p if n <= 65536 else p[torch.randint(0, n, (65536,), device=p.device)]
+    lo, hi = torch.quantile(q, 0.05, dim=0), torch.quantile(q, 0.95, dim=0)
+    ext = (hi - lo).cpu().double()
+    big = float(ext.max())
+    if big <= 0.0:                                   # (nearly) all points coincide: any cell works
+        full = (p.max(0).values - p.min(0).values).cpu().double()
+        big = float(full.max())
+        return max(big, 1e-9)
+    live = ext[ext > 1e-4 * big]
+    measure = float(torch.prod(live))                # length / area / volume of the central 90 % box
+    inside = max(0.9 ** live.numel() * n, 1.0)       # points expected in it
+    return max(1.5 * (measure / inside) ** (1.0 / live.numel()), 1e-9)
+
+
 def distCUDA2(points):
     """simple_knn._C.distCUDA2: mean squared distance to the 3 nearest other points, float32 [P]."""
     _need_cuda(points, "distCUDA2")
@@ -132,11 +153,7 @@ def distCUDA2(points):
     out = torch.zeros(n, dtype=torch.float32, device=p.device)
     if n == 0:
         return out
-    # cell ~ 1.5 x the mean inter-point spacing of the bounding box
-    ext = (p.max(0).values - p.min(0).values).clamp_min(1e-12)
-    vol = float(torch.prod(ext).item())
-    cell = max(1.5 * (vol / max(n, 1)) ** (1.0 / 3.0), 1e-9)
-    g = Grid(p, cell)
+    g = Grid(p, _spacing_cell(p))
     with torch.cuda.device(p.device):
         L.check(L.lib().fnx_knn3_mean_dist2(g.buf.data_ptr(), p.data_ptr(), n, g.cell, out.data_ptr(), _stream(p.device)))
     return out

@@ -130,8 +130,9 @@ typedef struct fnx_raster_scratch {
     void *binning; size_t binning_bytes;
     void *image;   size_t image_bytes;
     int64_t binning_capacity; /* instances the binning buffer was sized for */
-    int32_t check_slot;       /* private: which read-back slot carries this forward's instance count */
-    int32_t reserved;
+    int32_t check_slot;       /* private: which read-back slot carries this forward's instance count (a ring of 256 per device:
+                                 call fnx_raster_check before 256 later forwards on that device) */
+    int32_t reserved;         /* private: the device of that ring */
 } fnx_raster_scratch;
 
 /* Sizes, for callers that pre-allocate instead of using callbacks. */

@@ -63,6 +63,35 @@ def test_scatter_min_and_knn(libfnx):
     assert rel(got, O.knn3_mean_dist2(pts)) < 1e-5
 
 
+@pytest.mark.parametrize("shape", ["planar", "line", "outliers", "coincident"])
+def test_distcuda2_degenerate_clouds(libfnx, shape):
+    """planar / linear clouds and clouds with far outliers (an initial point cloud on a wall; a few stray points) must
+    neither change the result nor send every query into the exhaustive fallback (the call has to stay fast)."""
+    import time
+    rng = np.random.default_rng(4)
+    n = 60_000
+    if shape == "planar":
+        pts = np.stack([rng.uniform(0, 3, n), rng.uniform(0, 2, n), np.full(n, 0.7)], 1)
+    elif shape == "line":
+        pts = np.stack([rng.uniform(0, 50, n), np.full(n, 1.0), np.full(n, -2.0)], 1)
+    elif shape == "outliers":
+        pts = np.concatenate([rng.uniform(0, 1, (n - 5, 3)), rng.uniform(1e3, 1e4, (5, 3))])
+    else:
+        pts = np.concatenate([np.zeros((n - 3, 3)), rng.uniform(0, 1, (3, 3))])
+    pts = pts.astype(np.float32)
+    P.distCUDA2(torch.tensor(pts[:100]).cuda())
+    torch.cuda.synchronize()
+    t0 = time.time()
+    got = P.distCUDA2(torch.tensor(pts).cuda()).cpu().numpy()
+    dt = time.time() - t0
+    sub = rng.choice(n, 300, replace=False)            # brute-force check on a sample
+    d2 = ((pts[sub, None, :].astype(np.float64) - pts[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    d2[np.arange(300), sub] = np.inf
+    ref = np.sort(d2, axis=1)[:, :3].mean(1)
+    assert np.allclose(got[sub], ref, rtol=1e-4, atol=1e-12), shape
+    assert dt < 5.0, (shape, dt)
+
+
 @pytest.mark.parametrize("K,bmax", [(100, 0.0), (100, 0.8), (20, 0.8)])
 def test_density_and_next_tick_match_oracle(libfnx, K, bmax):
     prm = O.PBFParams(KNN_K=K, buoyancy_max_y=bmax, p0=1.5)
