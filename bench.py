@@ -561,25 +561,40 @@ def dropin_leg(args, cfg, frame, bg, cams, prm, dev):
     from oracle import ref_python as RP
     if not RP.staged():
         return {"unavailable": "oracle/_ref/FluidDynamics not staged"}
+    from fluidnexus_b200 import accelerate
     from oracle.ref_step import StockTrainer
     oprm = O.PBFParams(p0=cfg["p0"], buoyancy_max_y=cfg["bmax"], distance_threshold_visual=cfg["thr"])
-    with_dist = cfg["nf"] <= 20_000
     zeros = [torch.zeros(cfg["C"], cfg["size"], cfg["size"]) for _ in cams]
-    tr = StockTrainer(oprm, frame["hidden"], frame["visual"], frame["fluid"], bg, cfg["C"], cams, zeros, with_distance=with_dist, native="fnx")
     rng = np.random.default_rng(300)
     pert = torch.tensor(frame["fluid"].xyz + rng.normal(0, 0.002, frame["fluid"].xyz.shape), dtype=torch.float32, device=dev)
-    tr.set_ground_truth([tr.render_gt(k, pert).cpu() for k in range(len(cams))])
-    for _ in range(3):
-        tr.iteration()
-    torch.cuda.synchronize()
-    t0, n = time.time(), 10
-    for _ in range(n):
-        tr.iteration()
-    torch.cuda.synchronize()
-    dt = (time.time() - t0) / n
-    return {"value": round(1.0 / dt, 3), "unit": "iters/s", "ms_per_iteration": round(dt * 1e3, 3), "frames_in_flight": 1,
-            "loop_body": f"{tr.where[0]}:{tr.where[1][0]}-{tr.where[1][1]}", "distance_loss": "dense cdist (stock)" if with_dist else "off (O(V^2))",
-            "what": "the reference's own training-loop body and Python modules, unchanged, on the GPU through libfnx's drop-in packages"}
+
+    def run(with_dist):
+        tr = StockTrainer(oprm, frame["hidden"], frame["visual"], frame["fluid"], bg, cfg["C"], cams, zeros, with_distance=with_dist, native="fnx")
+        tr.set_ground_truth([tr.render_gt(k, pert).cpu() for k in range(len(cams))])
+        for _ in range(3):
+            tr.iteration()
+        torch.cuda.synchronize()
+        t0, n = time.time(), 10
+        for _ in range(n):
+            tr.iteration()
+        torch.cuda.synchronize()
+        return (time.time() - t0) / n, tr
+    dense_ok = cfg["nf"] <= 20_000
+    dt, tr = run(dense_ok)
+    out = {"value": round(1.0 / dt, 3), "unit": "iters/s", "ms_per_iteration": round(dt * 1e3, 3), "frames_in_flight": 1,
+           "loop_body": f"{tr.where[0]}:{tr.where[1][0]}-{tr.where[1][1]}", "distance_loss": "dense cdist (stock)" if dense_ok else "off (O(V^2))",
+           "what": "the reference's own training-loop body and Python modules, unchanged, on the GPU through libfnx's drop-in packages"}
+    del tr
+    try:   # the same with the opt-in accelerators (fluidnexus_b200/accelerate.py): fused l1 / ssim, grid-hash distance_loss, cached ground truth
+        accelerate.install_accelerators()
+        dt2, tr2 = run(True)
+        out["with_accelerators"] = {"value": round(1.0 / dt2, 3), "unit": "iters/s", "ms_per_iteration": round(dt2 * 1e3, 3),
+                                    "distance_loss": "grid hash (fnx_pair_distance_loss)",
+                                    "what": "same loop; utils.loss_utils.{l1_loss, ssim, distance_loss} and Camera.original_image patched by "
+                                            "an import hook (no file of the reference edited)"}
+    finally:
+        accelerate.uninstall_accelerators()
+    return out
 
 
 def cpu_baseline(args, cfg, frame, bg, cams):

@@ -71,6 +71,16 @@ class GsHparams(C.Structure):
     _fields_ = [("lr_xyz", C.c_float), ("lr_color", C.c_float), ("lr_opacity", C.c_float), ("lr_scaling", C.c_float),
                 ("lr_rotation", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int32),
                 ("update_stats", C.c_int32), ("lambda_reg_scaling", C.c_float), ("reg_ratio_threshold", C.c_float)]
+class GsLevelTwo(C.Structure):
+    _fields_ = [("prev_color", C.c_void_p), ("prev_opacity", C.c_void_p), ("prev_scales", C.c_void_p), ("prev_rotation", C.c_void_p),
+                ("prev_num", C.c_int32), ("color_channels", C.c_int32), ("fit_color", C.c_int32), ("fit_opacity", C.c_int32),
+                ("fit_scales", C.c_int32), ("fit_rotation", C.c_int32), ("lambda_consistency_color", C.c_float),
+                ("lambda_consistency_opacity", C.c_float), ("lambda_consistency_scales", C.c_float), ("lambda_consistency_rotation", C.c_float),
+                ("lambda_reg_scaling", C.c_float), ("reg_ratio_threshold", C.c_float), ("lr_color", C.c_float), ("lr_opacity", C.c_float),
+                ("lr_scaling", C.c_float), ("lr_rotation", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("step", C.c_int32)]
+
+
 _FWD = (_I, [C.POINTER(RasterArgs), ALLOC_FN, _V, ALLOC_FN, _V, ALLOC_FN, _V, _V, _V, _V, C.POINTER(_I64),
              C.POINTER(RasterScratch), _V])
 _BWD = (_I, [C.POINTER(RasterArgs), C.POINTER(RasterScratch), _I64, _V, _V, C.POINTER(RasterGrads), _V])
@@ -100,6 +110,7 @@ SYMBOLS = {
     "fnx_radius_fill": (_I, [_V, _I, _F, _V, _I, _F, _V, _V, _V, _V, _V]),
     "fnx_pbf_density_fwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V]),
     "fnx_gs_activate": (_I, [_I, _V, _V, _V, _V, _V, _V, _V]),
+    "fnx_gs_update_level_two": (_I, [_I, _I, C.POINTER(GsState), C.POINTER(GsGrads), C.POINTER(GsLevelTwo), _V, _V]),
     "fnx_gs_update": (_I, [_I, _I, C.POINTER(GsState), C.POINTER(GsGrads), C.POINTER(GsHparams), _V, _V, _V]),
     "fnx_pbf_guess_hidden": (_I, [_I, _V, _V, _V, _V, _V, _V, C.POINTER(_F), _F, _F, _F, _F, _F, _I, C.POINTER(_F), _F, _F, _V]),
     "fnx_pbf_project_gas_constraints": (_I, [_V, _V, _I, _V, _V, _V, _V, _F, _F, _F, _I, _F, _F, _I, _F, _V, _V, _V, _V, _V]),
@@ -109,6 +120,7 @@ SYMBOLS = {
     "fnx_pbf_update_visual": (_I, [_V, _V, _V, _I, _V, _I, _I, _F, _F, _V, _V]),
     "fnx_pbf_density_fwd_counted": (_I, [_V, _V, _I, _V, _I, _F, _F, _V, _V, _V, _V]),
     "fnx_pbf_density_bwd": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _V, _I, _V]),
+    "fnx_pbf_density_bwd_ratio": (_I, [_V, _V, _I, _V, _V, _F, _F, _V, _F, _V, _V, _V, _I, _V]),
     "fnx_visual_advect_fwd": (_I, [_V, _V, _V, _I, _V, _I, _V, _F, _F, _F, _V, _V, _V, _V]),
     "fnx_visual_advect_fwd_counted": (_I, [_V, _V, _V, _I, _V, _I, _I, _F, _F, _F, _V, _V, _V, _V, _V]),
     "fnx_visual_advect_bwd": (_I, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _V, _F, _F, _F, _V, _I, _V]),
@@ -116,6 +128,7 @@ SYMBOLS = {
     "fnx_knn3_mean_dist2": (_I, [_V, _V, _I, _F, _V, _V]),
     "fnx_pbf_next_tick_fwd": (_I, [_I, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V]),
     "fnx_pbf_combine_grad": (_I, [_I, _V, _V, _F, _F, _F, _V, _V, _V, _F, _V, _V, _V]),
+    "fnx_pbf_combine_grad_adam": (_I, [_I, _V, _V, _F, _F, _F, _V, _V, _V, _F, _V, _V, _V, _V, _F, _F, _F, _F, _V, _V, _V, _V]),
     "fnx_pbf_ratio_loss": (_I, [_I, _V, _F, _V, _V, _V]),
     "fnx_adam_step": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _I, _V]),
     "fnx_adam_step_dev": (_I, [_I64, _V, _V, _V, _V, _F, _F, _F, _F, _F, _V, _V, _V]),

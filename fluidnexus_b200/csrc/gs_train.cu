@@ -119,6 +119,126 @@ gs_update_kernel(int P, fnx_gs_state s, fnx_gs_grads g, fnx_gs_hparams h, AdamCo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Level-two ("visual particle") stage: FD/entries_fluid_nexus/train_visual_particle.py:133-222 (ScalarReal twin :129-218).
+// Positions are fixed (loaded from the physical stage); colour / opacity / scales / rotation of the V visual particles are
+// nn.Parameters (gm_dynamics.py:380-397 training_setup_current_level_two, one Adam group each, eps 1e-15).  Per view the loss
+// is the image term + lambda_consistency_X * l2_loss_consistency(X, prev_X) (= mse over the first prev_num rows,
+// loss_utils.py:138-146; on the RAW tensors) + lambda_reg_scaling * mean(max(s_max / s_min - threshold, 0)); gradients are
+// summed over the views and scaled by 1 / batch (gm_dynamics.py:474-503), so the view-independent terms enter with weight 1.
+// One thread per particle: chain the rasterizer's gradients through the activations, add the consistency / regulariser
+// gradients, accumulate the loss scalars, Adam-update the tensors that are fitted.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CP>   // colour channels of the PARAMETER (1: grey particles, repeated to 3 render channels by pipe_dynamics.py:118-120)
+__global__ void __launch_bounds__(256)
+gs_level_two_kernel(int V, fnx_gs_state s, fnx_gs_grads g, fnx_gs_level_two h, AdamCoef c, int render_channels, float *__restrict__ losses) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float l_col = 0.f, l_op = 0.f, l_sc = 0.f, l_rot = 0.f, reg = 0.f;
+    if (i < V) {
+        const bool has_prev = i < h.prev_num;
+        // ---- colour (identity activation) ----
+        if (h.fit_color) {
+#pragma unroll
+            for (int k = 0; k < CP; k++) {
+                float gc = 0.f;
+                if (g.dL_dcolors) {
+                    if (CP == 1) for (int ch = 0; ch < render_channels; ch++) gc += g.dL_dcolors[(size_t)render_channels * i + ch];
+                    else gc = g.dL_dcolors[(size_t)CP * i + k];
+                }
+                if (has_prev && h.prev_color) {
+                    const float d = s.color[(size_t)CP * i + k] - h.prev_color[(size_t)CP * i + k];
+                    l_col += d * d;
+                    gc += h.lambda_consistency_color * 2.0f * d / ((float)h.prev_num * CP);
+                }
+                adam_update(s.color[(size_t)CP * i + k], s.m_color[(size_t)CP * i + k], s.v_color[(size_t)CP * i + k], gc, h.lr_color, c);
+            }
+        }
+        // ---- opacity: o = sigmoid(raw) ----
+        if (h.fit_opacity) {
+            const float raw = s.opacity[i];
+            const float o = sigmoidf(raw);
+            float go = (g.dL_dopacity ? g.dL_dopacity[i] : 0.f) * o * (1.0f - o);
+            if (has_prev && h.prev_opacity) {
+                const float d = raw - h.prev_opacity[i];
+                l_op += d * d;
+                go += h.lambda_consistency_opacity * 2.0f * d / (float)h.prev_num;
+            }
+            adam_update(s.opacity[i], s.m_opacity[i], s.v_opacity[i], go, h.lr_opacity, c);
+        }
+        // ---- scales: s = exp(raw), regulariser on the activated values ----
+        if (h.fit_scales) {
+            float raw_s[3], sc[3], gs[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                raw_s[k] = s.scaling[3 * i + k];
+                sc[k] = expf(raw_s[k]);
+                gs[k] = (g.dL_dscales ? g.dL_dscales[3 * i + k] : 0.f) * sc[k];
+            }
+            if (h.lambda_reg_scaling > 0.f) {
+                int imax = 0, imin = 0;   // torch.max / torch.min(dim=1): first extremal index, gradient routed there
+#pragma unroll
+                for (int k = 1; k < 3; k++) {
+                    if (sc[k] > sc[imax]) imax = k;
+                    if (sc[k] < sc[imin]) imin = k;
+                }
+                const float ratio = sc[imax] / sc[imin] - h.reg_ratio_threshold;
+                if (ratio > 0.f) {
+                    reg = ratio;
+                    const float w = h.lambda_reg_scaling / (float)V;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        gs[k] += ((k == imax ? w / sc[imin] : 0.f) + (k == imin ? -w * sc[imax] / (sc[imin] * sc[imin]) : 0.f)) * sc[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (has_prev && h.prev_scales) {
+                    const float d = raw_s[k] - h.prev_scales[3 * i + k];
+                    l_sc += d * d;
+                    gs[k] += h.lambda_consistency_scales * 2.0f * d / ((float)h.prev_num * 3.0f);
+                }
+                adam_update(s.scaling[3 * i + k], s.m_scaling[3 * i + k], s.v_scaling[3 * i + k], gs[k], h.lr_scaling, c);
+            }
+        }
+        // ---- rotation: q_n = q / max(|q|, 1e-12) ----
+        if (h.fit_rotation) {
+            float4 q = *reinterpret_cast<const float4 *>(s.rotation + 4 * (size_t)i);
+            const float4 gq = g.dL_drotations ? *reinterpret_cast<const float4 *>(g.dL_drotations + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float nrm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+            const float n = fmaxf(nrm, 1e-12f);
+            const float4 qn = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+            const float dot = nrm > 1e-12f ? (qn.x * gq.x + qn.y * gq.y + qn.z * gq.z + qn.w * gq.w) : 0.f;
+            float gr[4] = {(gq.x - qn.x * dot) / n, (gq.y - qn.y * dot) / n, (gq.z - qn.z * dot) / n, (gq.w - qn.w * dot) / n};
+            if (has_prev && h.prev_rotation) {
+                const float4 pq = *reinterpret_cast<const float4 *>(h.prev_rotation + 4 * (size_t)i);
+                const float d[4] = {q.x - pq.x, q.y - pq.y, q.z - pq.z, q.w - pq.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    l_rot += d[k] * d[k];
+                    gr[k] += h.lambda_consistency_rotation * 2.0f * d[k] / ((float)h.prev_num * 4.0f);
+                }
+            }
+            float4 m4 = *reinterpret_cast<float4 *>(s.m_rotation + 4 * (size_t)i), v4 = *reinterpret_cast<float4 *>(s.v_rotation + 4 * (size_t)i);
+            adam_update(q.x, m4.x, v4.x, gr[0], h.lr_rotation, c);
+            adam_update(q.y, m4.y, v4.y, gr[1], h.lr_rotation, c);
+            adam_update(q.z, m4.z, v4.z, gr[2], h.lr_rotation, c);
+            adam_update(q.w, m4.w, v4.w, gr[3], h.lr_rotation, c);
+            *reinterpret_cast<float4 *>(s.rotation + 4 * (size_t)i) = q;
+            *reinterpret_cast<float4 *>(s.m_rotation + 4 * (size_t)i) = m4;
+            *reinterpret_cast<float4 *>(s.v_rotation + 4 * (size_t)i) = v4;
+        }
+    }
+    if (losses != nullptr) {   // {color, opacity, scales, rotation consistency (mse), scaling regulariser (mean)}
+        const float pn = (float)max(h.prev_num, 1);
+        const float vals[5] = {l_col / (pn * CP), l_op / pn, l_sc / (pn * 3.0f), l_rot / (pn * 4.0f), reg / (float)V};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float r = warp_sum(vals[k]);
+            if ((threadIdx.x & 31) == 0 && r != 0.f) atomicAdd(losses + k, r);
+        }
+    }
+}
+
 }  // namespace fnx
 
 using namespace fnx;
@@ -153,6 +273,29 @@ int fnx_gs_update(int32_t P, int32_t C, const fnx_gs_state *state, const fnx_gs_
     if (C == 3) gs_update_kernel<3><<<(P + 255) / 256, 256, 0, st>>>(P, s, *grads, *hp, c, radii, reg_loss);
     else gs_update_kernel<1><<<(P + 255) / 256, 256, 0, st>>>(P, s, *grads, *hp, c, radii, reg_loss);
     FNX_LAUNCH_CHECK("gs_update_kernel");
+    return FNX_OK;
+}
+
+int fnx_gs_update_level_two(int32_t V, int32_t render_channels, const fnx_gs_state *state, const fnx_gs_grads *grads,
+                            const fnx_gs_level_two *hp, float *losses5, fnx_stream_t stream) {
+    FNX_REQUIRE(V >= 0 && (render_channels == 1 || render_channels == 3) && state && grads && hp, "bad arguments");
+    FNX_REQUIRE(hp->step >= 1 && (hp->color_channels == 1 || hp->color_channels == 3) && hp->color_channels <= render_channels,
+                "step counts from 1; colour parameter channels must be 1 or 3 and not exceed the render channels");
+    FNX_REQUIRE(hp->prev_num >= 0 && hp->prev_num <= V, "prev_num must be in [0, V]");
+    const fnx_gs_state &s = *state;
+    FNX_REQUIRE((!hp->fit_color || (s.color && s.m_color && s.v_color)) && (!hp->fit_opacity || (s.opacity && s.m_opacity && s.v_opacity)) &&
+                    (!hp->fit_scales || (s.scaling && s.m_scaling && s.v_scaling)) && (!hp->fit_rotation || (s.rotation && s.m_rotation && s.v_rotation)),
+                "state tensors of a fitted attribute missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (losses5) FNX_CUDA_TRY(cudaMemsetAsync(losses5, 0, 5 * sizeof(float), st));
+    if (V == 0) return FNX_OK;
+    AdamCoef c;
+    c.beta1 = hp->beta1; c.beta2 = hp->beta2; c.eps = hp->eps;
+    c.bc1 = (float)(1.0 - pow((double)hp->beta1, hp->step));
+    c.bc2_sqrt = (float)sqrt(1.0 - pow((double)hp->beta2, hp->step));
+    if (hp->color_channels == 1) gs_level_two_kernel<1><<<(V + 255) / 256, 256, 0, st>>>(V, s, *grads, *hp, c, render_channels, losses5);
+    else gs_level_two_kernel<3><<<(V + 255) / 256, 256, 0, st>>>(V, s, *grads, *hp, c, render_channels, losses5);
+    FNX_LAUNCH_CHECK("gs_level_two_kernel");
     return FNX_OK;
 }
 

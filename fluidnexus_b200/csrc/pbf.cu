@@ -131,6 +131,54 @@ __global__ void grid_header_kernel(GridHeader *h, int n, int M, float cell, uint
     bucket_start[M] = (uint32_t)n;  // the scan below writes entries [0, M)
 }
 
+// Exclusive prefix sum of the M bucket counts by ONE CTA (M is a power of two and a multiple of 1024; up to SCAN_ONE_CTA_MAX
+// buckets: 256 KB of counters read and written once by one SM, ~3 us), which also clears the counters for the scatter pass that
+// follows.  Replaces two library launches (cub::DeviceScan init + scan) and a memset per grid build; the particle grids of the
+// training step are this small (N = 28 000 -> M = 65 536) and are rebuilt three times per iteration.
+constexpr int SCAN_ONE_CTA_MAX = 131072;
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(int M, uint32_t *__restrict__ fill, uint32_t *__restrict__ start) {
+    __shared__ uint32_t warp_tot[32];
+    const int per = M / 1024;                      // consecutive counters per thread (a multiple of 4 for M >= 4096)
+    const int base = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (int k = 0; k < per; k += 4) {
+        const uint4 c = *reinterpret_cast<const uint4 *>(fill + base + k);
+        sum += c.x + c.y + c.z + c.w;
+    }
+    // block-wide exclusive scan of the per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_tot[lane] = w;                        // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = inc - sum + (warp > 0 ? warp_tot[warp - 1] : 0u);
+    for (int k = 0; k < per; k += 4) {
+        const uint4 c = *reinterpret_cast<const uint4 *>(fill + base + k);
+        uint4 o;
+        o.x = run; run += c.x;
+        o.y = run; run += c.y;
+        o.z = run; run += c.z;
+        o.w = run; run += c.w;
+        *reinterpret_cast<uint4 *>(start + base + k) = o;
+        *reinterpret_cast<uint4 *>(fill + base + k) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 static int grid_build(const float *pts, int n, float cell, void *scratch, cudaStream_t st) {
     GridView g = grid_view(scratch, n);
     const float inv_cell = 1.0f / cell;
@@ -142,9 +190,14 @@ static int grid_build(const float *pts, int n, float cell, void *scratch, cudaSt
         grid_header_kernel<<<1, 1, 0, st>>>(g.hdr, n, g.M, cell, g.bucket_start);
         FNX_LAUNCH_CHECK("grid_header_kernel");
     }
-    size_t tb = g.cub_temp_bytes;
-    FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, g.bucket_fill, g.bucket_start, g.M, st));
-    FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
+    if (g.M >= 4096 && g.M <= SCAN_ONE_CTA_MAX && (g.M & (g.M - 1)) == 0) {
+        grid_scan_kernel<<<1, 1024, 0, st>>>(g.M, g.bucket_fill, g.bucket_start);
+        FNX_LAUNCH_CHECK("grid_scan_kernel");
+    } else {
+        size_t tb = g.cub_temp_bytes;
+        FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, g.bucket_fill, g.bucket_start, g.M, st));
+        FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
+    }
     if (n > 0) {
         grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_start, g.bucket_fill, g.tmp_idx);
         FNX_LAUNCH_CHECK("grid_scatter_kernel");
@@ -366,6 +419,25 @@ __global__ void density_bwd_pack_kernel(GridView g, int N, const float *__restri
     if (a >= N) return;
     const uint32_t i = g.sorted_idx[a];
     g.aux1[a] = make_float4(dL_dpratio[i] / imass[i] / p0, __int_as_float(kth[i]), 0.f, 0.f);
+}
+// the same pre-pass for the training step, where dL/dp_ratio is that of loss = weight * mean((p_ratio - 1)^2)
+// (train_physical_particle.py:336-342): computes it on the fly (and stores it: density_bwd_kernel reads it for its own particle),
+// and accumulates the un-weighted loss -- the separate ratio_loss launch folded into a pass that exists anyway
+__global__ void density_bwd_pack_ratio_kernel(GridView g, int N, const float *__restrict__ imass, const int *__restrict__ kth, float p0,
+                                              const float *__restrict__ p_ratio, float weight, float *__restrict__ dL_dpratio,
+                                              float *__restrict__ loss) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (a < N) {
+        const uint32_t i = g.sorted_idx[a];
+        const float d = p_ratio[i] - 1.0f;
+        const float gp = weight * 2.0f * d / N;
+        l = d * d;
+        dL_dpratio[i] = gp;
+        g.aux1[a] = make_float4(gp / imass[i] / p0, __int_as_float(kth[i]), 0.f, 0.f);
+    }
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss, l / N);
 }
 __global__ void __launch_bounds__(128)
 density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
@@ -808,13 +880,22 @@ __global__ void next_tick_fwd_kernel(int N, const float *__restrict__ e, const f
     }
 }
 // dL/de = scale*dL/dX + (dY/de)^T dL/dY + 2*lambda_exyz*scale*(scale*e - estimate_xyz)/(3N)
+// With adam_p != NULL the Adam update of torch.optim.Adam (see adam_dev_kernel; bc = {1 - beta1^t, sqrt(1 - beta2^t)} from
+// adam_prepare_kernel, bc[0] == 0: gated off) is applied to the same element right away: `e` and `adam_p` are the same tensor,
+// every thread reads its own three components before it writes them.
+struct AdamFused {
+    float *p, *m, *v;
+    const float *bc;
+    float lr, beta1, beta2, eps;
+};
 __global__ void combine_grad_kernel(int N, const float *__restrict__ e, const float *__restrict__ buoy, float secs, float bmax,
                                     float scale, const float *__restrict__ dL_dX, const float *__restrict__ dL_dY,
                                     const float *__restrict__ estimate_xyz, float w_exyz, float *__restrict__ dL_de,
-                                    float *__restrict__ exyz_loss) {
+                                    float *__restrict__ exyz_loss, AdamFused adam) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float l = 0.f;
     if (i < N) {
+        const float e3[3] = {e[3 * i], e[3 * i + 1], e[3 * i + 2]};
         float gy[3] = {0.f, 0.f, 0.f};
         float cross = 0.f;
         if (dL_dY) {
@@ -829,11 +910,23 @@ __global__ void combine_grad_kernel(int N, const float *__restrict__ e, const fl
             float gsum = (dL_dX ? scale * dL_dX[3 * i + k] : 0.f) + 2.0f * scale * gy[k];
             if (k == 1) gsum += cross;
             if (estimate_xyz) {
-                const float d = e[3 * i + k] * scale - estimate_xyz[3 * i + k];
+                const float d = e3[k] * scale - estimate_xyz[3 * i + k];
                 l += d * d;
                 gsum += w_exyz * 2.0f * scale * d / (3.0f * N);
             }
             dL_de[3 * i + k] = gsum;
+            if (adam.p != nullptr) {
+                const float bc1 = adam.bc[0], bc2_sqrt = adam.bc[1];
+                if (bc1 != 0.f) {
+                    const int q = 3 * i + k;
+                    const float mi = adam.m[q] + (gsum - adam.m[q]) * (1.0f - adam.beta1);
+                    const float vi = adam.beta2 * adam.v[q] + (1.0f - adam.beta2) * gsum * gsum;
+                    adam.m[q] = mi;
+                    adam.v[q] = vi;
+                    const float denom = sqrtf(vi) / bc2_sqrt + adam.eps;
+                    adam.p[q] = e3[k] - (adam.lr / bc1) * (mi / denom);
+                }
+            }
         }
     }
     l = warp_sum(l);
@@ -994,6 +1087,22 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
     density_bwd_pack_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, imass, kth, p0, dL_dpratio);
     FNX_LAUNCH_CHECK("density_bwd_pack_kernel");
+    density_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
+    FNX_LAUNCH_CHECK("density_bwd_kernel");
+    return FNX_OK;
+}
+
+int fnx_pbf_density_bwd_ratio(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H, float p0,
+                              const float *p_ratio, float weight, float *loss, float *dL_dpratio, float *dL_dX, int32_t accumulate,
+                              fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(grid && X && imass && kth && p_ratio && loss && dL_dpratio && dL_dX && N >= 0, "bad arguments");
+    FNX_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+    if (N == 0) return FNX_OK;
+    GridView g = grid_view((void *)grid, N);
+    const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
+    density_bwd_pack_ratio_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, imass, kth, p0, p_ratio, weight, dL_dpratio, loss);
+    FNX_LAUNCH_CHECK("density_bwd_pack_ratio_kernel");
     density_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("density_bwd_kernel");
     return FNX_OK;
@@ -1205,7 +1314,24 @@ int fnx_pbf_combine_grad(int32_t N, const float *e, const float *buoyancy, float
     if (exyz_loss) FNX_CUDA_TRY(cudaMemsetAsync(exyz_loss, 0, sizeof(float), (cudaStream_t)stream));
     if (N == 0) return FNX_OK;
     combine_grad_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, e, buoyancy, secs, buoyancy_max_y, scale_factor, dL_dX, dL_dY,
-                                                                         estimate_xyz, lambda_exyz, dL_de, exyz_loss);
+                                                                         estimate_xyz, lambda_exyz, dL_de, exyz_loss, AdamFused{});
+    FNX_LAUNCH_CHECK("combine_grad_kernel");
+    return FNX_OK;
+}
+
+int fnx_pbf_combine_grad_adam(int32_t N, float *e, const float *buoyancy, float secs, float buoyancy_max_y, float scale_factor,
+                              const float *dL_dX, const float *dL_dY, const float *estimate_xyz, float lambda_exyz, float *dL_de,
+                              float *exyz_loss, float *exp_avg, float *exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                              int32_t *step_dev, float *bc_dev, const int32_t *skip_flag, fnx_stream_t stream) {
+    ProfScope _ps(SEC_PHYSICS, (cudaStream_t)stream);
+    FNX_REQUIRE(N >= 0 && e && buoyancy && dL_de && exp_avg && exp_avg_sq && step_dev && bc_dev, "bad arguments");
+    if (exyz_loss) FNX_CUDA_TRY(cudaMemsetAsync(exyz_loss, 0, sizeof(float), (cudaStream_t)stream));
+    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, beta1, beta2, bc_dev, skip_flag);
+    FNX_LAUNCH_CHECK("adam_prepare_kernel");
+    if (N == 0) return FNX_OK;
+    AdamFused ad{e, exp_avg, exp_avg_sq, bc_dev, lr, beta1, beta2, eps};
+    combine_grad_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, e, buoyancy, secs, buoyancy_max_y, scale_factor, dL_dX, dL_dY,
+                                                                         estimate_xyz, lambda_exyz, dL_de, exyz_loss, ad);
     FNX_LAUNCH_CHECK("combine_grad_kernel");
     return FNX_OK;
 }

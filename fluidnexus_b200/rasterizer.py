@@ -315,7 +315,8 @@ class MergedRasterWorkspace:
     allocation / host sync / events inside forward() and backward() (CUDA-graph capturable)."""
 
     def __init__(self, dev, P_dyn, V, H, W, bg, dyn, static, view_matrix, proj_matrix, tan_fov_x, tan_fov_y, margin=1.2,
-                 static_prepare=True, static_tile_cache=True, bucket_binning=True, static_stream=None, view_ids=None, slack=65536):
+                 static_prepare=True, static_tile_cache=True, bucket_binning=True, static_stream=None, view_ids=None, slack=65536,
+                 want=("means3D",)):
         """dyn / static: dicts of contiguous float32 CUDA tensors means3D, colors, opacities, scales, rotations (static may be
         None when a static_stream is given).  view_matrix / proj_matrix: the V cameras this workspace renders.
         static_prepare (private stream only): blend the static stream alone once, which bounds the static records every later
@@ -363,7 +364,10 @@ class MergedRasterWorkspace:
             # blend that is sum(tile_last) static records of these cameras instead of all of them
             n_static_reach = int(static_stream.reach[self.view_ids].sum()) if static_stream.prepared else self.R_static
             self.merged = u8(48 * (self.capacity + n_static_reach) + 256)
-            self.grads = {"means3D": torch.empty((P_dyn, 3), device=self.dev)}
+            # gradients of the DYNAMIC Gaussians the backward writes (the physical stage needs the means only, level two the attributes)
+            shapes = dict(means3D=(P_dyn, 3), means2D=(V, P_dyn, 3), colors=(P_dyn, 3), opacity=(P_dyn, 1), scales=(P_dyn, 3), rotations=(P_dyn, 4),
+                          cov3D=(P_dyn, 6))
+            self.grads = {k: torch.empty(shapes[k], device=self.dev) for k in want}
             self.tile_order = torch.arange(V * ((W + 15) // 16) * ((H + 15) // 16), dtype=torch.int32, device=self.dev)
             # which tiles of self.color / self.depth hold their static-only pixels: all of them (copied above) or none
             sc = L.RasterScratch()
@@ -400,7 +404,9 @@ class MergedRasterWorkspace:
 
     def backward(self, dL_dout_color):
         gr = L.RasterGrads()
-        gr.dL_dmeans3D = self.grads["means3D"].data_ptr()
+        for name, field in (("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("colors", "dL_dcolors"), ("opacity", "dL_dopacity"),
+                            ("scales", "dL_dscales"), ("rotations", "dL_drotations"), ("cov3D", "dL_dcov3D")):
+            setattr(gr, field, self.grads[name].data_ptr() if name in self.grads else None)
         L.check(L.lib().fnx_raster_backward_merged(C.byref(self.args), C.byref(self.scratch), C.byref(self.sscratch), self.merged.data_ptr(),
                                                    self.radii.data_ptr(), dL_dout_color.data_ptr(), C.byref(gr),
                                                    torch.cuda.current_stream(self.dev).cuda_stream))

@@ -199,9 +199,10 @@ class PhysicalStep:
                     ck(lib.fnx_grid_build(pos.data_ptr(), N, prm.H, grid.data_ptr(), st))
                 ck(lib.fnx_pbf_density_fwd_counted(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), prm.KNN_K, prm.H, prm.p0,
                                                    kth.data_ptr(), p.data_ptr(), fr.cap_flag[k:].data_ptr(), st))
-                ck(lib.fnx_pbf_ratio_loss(N, p.data_ptr(), lam, fr.scalars[k:].data_ptr(), gp.data_ptr(), st))
-                ck(lib.fnx_pbf_density_bwd(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
-                                           gp.data_ptr(), dpos.data_ptr(), 0, st))
+                # l2_loss(p_ratio, 1) * lambda and its chain to the positions (the loss scalar and dL/dp_ratio are produced inside
+                # the backward's own pre-pass)
+                ck(lib.fnx_pbf_density_bwd_ratio(grid.data_ptr(), pos.data_ptr(), N, fr.imass.data_ptr(), kth.data_ptr(), prm.H, prm.p0,
+                                                 p.data_ptr(), lam, fr.scalars[k:].data_ptr(), gp.data_ptr(), dpos.data_ptr(), 0, st))
             # P5 on the render-unit positions written by P1
             if prm.lambda_current_distance > 0:
                 if self.side is not None:
@@ -317,6 +318,15 @@ class PhysicalStep:
         ck(lib.fnx_visual_advect_bwd(fr.gridVis.data_ptr(), fr.X.data_ptr(), fr.xyz.data_ptr(), N, V, fr.kthV.data_ptr(), fr.num.data_ptr(),
                                      fr.den.data_ptr(), dL_dmeans3D.data_ptr(), fr.dDist.data_ptr(), 1.0 / prm.scale_factor, prm.H,
                                      prm.secs, fr.dX.data_ptr(), 1, st))
+        if update and grad_extra is None:
+            # gradient assembly + Adam in one element-wise pass (the whole batch of views ran here: set_batch_gradient_current +
+            # optimizer.step); voided on the device when the forward overflowed its instance capacity (skip_flag)
+            ck(lib.fnx_pbf_combine_grad_adam(N, fr.e.data_ptr(), fr.buoyancy.data_ptr(), prm.secs, prm.buoyancy_max_y, prm.scale_factor,
+                                             fr.dX.data_ptr(), fr.dY.data_ptr() if physics else None,
+                                             fr.estimate_xyz.data_ptr() if physics else None, prm.lambda_exyz, fr.de.data_ptr(),
+                                             fr.scalars[2:].data_ptr() if physics else None, fr.m.data_ptr(), fr.v.data_ptr(), prm.lr, 0.9,
+                                             0.999, prm.adam_eps, fr.step_dev.data_ptr(), fr.bc_dev.data_ptr(), skip_flag, st))
+            return
         ck(lib.fnx_pbf_combine_grad(N, fr.e.data_ptr(), fr.buoyancy.data_ptr(), prm.secs, prm.buoyancy_max_y, prm.scale_factor,
                                     fr.dX.data_ptr(), fr.dY.data_ptr() if physics else None,
                                     fr.estimate_xyz.data_ptr() if physics else None, prm.lambda_exyz, fr.de.data_ptr(),

@@ -261,6 +261,12 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
                         float p0, float *p_ratio, fnx_stream_t stream);
 int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H,
                         float p0, const float *dL_dpratio, float *dL_dX, int32_t accumulate, fnx_stream_t stream);
+/* fnx_pbf_ratio_loss + fnx_pbf_density_bwd in one call for the training step's loss = weight * mean((p_ratio - 1)^2)
+ * (FD/entries_scalar_real/train_physical_particle.py:336-342): *loss (device scalar) receives the un-weighted mean, dL_dpratio [N]
+ * the gradient w.r.t. p_ratio (scratch the caller may inspect), dL_dX as fnx_pbf_density_bwd. */
+int fnx_pbf_density_bwd_ratio(const void *grid, const float *X, int32_t N, const float *imass, const int32_t *kth, float H,
+                              float p0, const float *p_ratio, float weight, float *loss, float *dL_dpratio, float *dL_dX,
+                              int32_t accumulate, fnx_stream_t stream);
 /* fnx_radius_count(grid(X), X, K) + fnx_pbf_density_fwd in one neighbour walk: kth_out [N] is written for the backward;
  * cap_flag is one int32 of device scratch (raised when some particle has more than K neighbours; p_ratio is then
  * recomputed with the cut-offs, so the result always equals the two-call sequence). */
@@ -304,6 +310,13 @@ int fnx_pbf_next_tick_fwd(int32_t N, const float *e, const float *xyz, const flo
 int fnx_pbf_combine_grad(int32_t N, const float *e, const float *buoyancy, float secs, float buoyancy_max_y,
                          float scale_factor, const float *dL_dX, const float *dL_dY, const float *estimate_xyz,
                          float lambda_exyz, float *dL_de, float *exyz_loss, fnx_stream_t stream);
+/* fnx_pbf_combine_grad followed by fnx_adam_step_dev_gated(grad = dL_de, grad_scale = 1) on `e` itself, in one element-wise pass
+ * (set_batch_gradient_current + optimizer.step of FD/entries_scalar_real/train_physical_particle.py:379-380 for a step whose views
+ * all ran in this process).  dL_de is still written (callers log / reduce it). */
+int fnx_pbf_combine_grad_adam(int32_t N, float *e, const float *buoyancy, float secs, float buoyancy_max_y, float scale_factor,
+                              const float *dL_dX, const float *dL_dY, const float *estimate_xyz, float lambda_exyz, float *dL_de,
+                              float *exyz_loss, float *exp_avg, float *exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                              int32_t *step_dev, float *bc_dev, const int32_t *skip_flag, fnx_stream_t stream);
 /* *loss = mean((p_ratio-1)^2) (l2_loss vs ones, train_physical_particle.py:336-342); dL_dpratio = weight * d loss. */
 int fnx_pbf_ratio_loss(int32_t N, const float *p_ratio, float weight, float *loss, float *dL_dpratio, fnx_stream_t stream);
 
@@ -400,6 +413,28 @@ typedef struct fnx_gs_hparams {
  * be NULL) receives the un-weighted regulariser value. */
 int fnx_gs_update(int32_t P, int32_t C, const fnx_gs_state *state, const fnx_gs_grads *grads, const fnx_gs_hparams *hp,
                   const int32_t *radii, float *reg_loss, fnx_stream_t stream);
+
+/* Level-two ("visual particle") stage, FD/entries_fluid_nexus/train_visual_particle.py:133-222 (ScalarReal twin :129-218): the
+ * positions are fixed; colour / opacity / scales / rotation of the V visual particles are trained (one Adam group each,
+ * gm_dynamics.py:380-397) on the image loss + lambda_consistency_X * mse(X[:prev_num], prev_X) on the RAW tensors
+ * (l2_loss_consistency, loss_utils.py:138-146) + the scaling regulariser.  One launch chains the rasterizer's gradients through
+ * the activations, adds the consistency / regulariser gradients and applies Adam to the fitted tensors.  `state`: only color /
+ * opacity / scaling / rotation and their moments are used (color is [V, color_channels]); `grads`: what the rasterizer's backward
+ * produced for the V particles, dL_dcolors [V, render_channels] (summed over the channels when the colour parameter has one).
+ * losses5 (device, may be NULL) receives {color, opacity, scales, rotation consistency, scaling regulariser}, un-weighted. */
+typedef struct fnx_gs_level_two {
+    const float *prev_color, *prev_opacity, *prev_scales, *prev_rotation;   /* raw tensors of the previous frame (NULL: no term) */
+    int32_t prev_num;               /* rows of the prev_* tensors (particles are appended over time: prev_num <= V) */
+    int32_t color_channels;         /* channels of the colour PARAMETER: 1 (grey particles) or 3 */
+    int32_t fit_color, fit_opacity, fit_scales, fit_rotation;   /* which tensors are trained (configs: fit_*) */
+    float lambda_consistency_color, lambda_consistency_opacity, lambda_consistency_scales, lambda_consistency_rotation;
+    float lambda_reg_scaling, reg_ratio_threshold;
+    float lr_color, lr_opacity, lr_scaling, lr_rotation;
+    float beta1, beta2, eps;
+    int32_t step;                   /* Adam step count AFTER this update (>= 1) */
+} fnx_gs_level_two;
+int fnx_gs_update_level_two(int32_t V, int32_t render_channels, const fnx_gs_state *state, const fnx_gs_grads *grads,
+                            const fnx_gs_level_two *hp, float *losses5, fnx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused image loss  (replaces l1_loss + ssim of FD/utils/loss_utils.py:9-64, the grey conversion of
