@@ -131,54 +131,6 @@ __global__ void grid_header_kernel(GridHeader *h, int n, int M, float cell, uint
     bucket_start[M] = (uint32_t)n;  // the scan below writes entries [0, M)
 }
 
-// Exclusive prefix sum of the M bucket counts by ONE CTA (M is a power of two and a multiple of 1024; up to SCAN_ONE_CTA_MAX
-// buckets: 256 KB of counters read and written once by one SM, ~3 us), which also clears the counters for the scatter pass that
-// follows.  Replaces two library launches (cub::DeviceScan init + scan) and a memset per grid build; the particle grids of the
-// training step are this small (N = 28 000 -> M = 65 536) and are rebuilt three times per iteration.
-constexpr int SCAN_ONE_CTA_MAX = 131072;
-__global__ void __launch_bounds__(1024)
-grid_scan_kernel(int M, uint32_t *__restrict__ fill, uint32_t *__restrict__ start) {
-    __shared__ uint32_t warp_tot[32];
-    const int per = M / 1024;                      // consecutive counters per thread (a multiple of 4 for M >= 4096)
-    const int base = threadIdx.x * per;
-    uint32_t sum = 0;
-    for (int k = 0; k < per; k += 4) {
-        const uint4 c = *reinterpret_cast<const uint4 *>(fill + base + k);
-        sum += c.x + c.y + c.z + c.w;
-    }
-    // block-wide exclusive scan of the per-thread sums
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_tot[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        warp_tot[lane] = w;                        // inclusive over warps
-    }
-    __syncthreads();
-    uint32_t run = inc - sum + (warp > 0 ? warp_tot[warp - 1] : 0u);
-    for (int k = 0; k < per; k += 4) {
-        const uint4 c = *reinterpret_cast<const uint4 *>(fill + base + k);
-        uint4 o;
-        o.x = run; run += c.x;
-        o.y = run; run += c.y;
-        o.z = run; run += c.z;
-        o.w = run; run += c.w;
-        *reinterpret_cast<uint4 *>(start + base + k) = o;
-        *reinterpret_cast<uint4 *>(fill + base + k) = make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-
 static int grid_build(const float *pts, int n, float cell, void *scratch, cudaStream_t st) {
     GridView g = grid_view(scratch, n);
     const float inv_cell = 1.0f / cell;
@@ -190,14 +142,12 @@ static int grid_build(const float *pts, int n, float cell, void *scratch, cudaSt
         grid_header_kernel<<<1, 1, 0, st>>>(g.hdr, n, g.M, cell, g.bucket_start);
         FNX_LAUNCH_CHECK("grid_header_kernel");
     }
-    if (g.M >= 4096 && g.M <= SCAN_ONE_CTA_MAX && (g.M & (g.M - 1)) == 0) {
-        grid_scan_kernel<<<1, 1024, 0, st>>>(g.M, g.bucket_fill, g.bucket_start);
-        FNX_LAUNCH_CHECK("grid_scan_kernel");
-    } else {
-        size_t tb = g.cub_temp_bytes;
-        FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, g.bucket_fill, g.bucket_start, g.M, st));
-        FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
-    }
+    // (a single-CTA scan of the 65 536 counters that also clears them was tried in round 2 to save CUB's two launches: 16.5 us per
+    // build against 8 us for the library's decoupled look-back pair -- one CTA cannot hide the memory latency -- and no gain in
+    // the step: reverted)
+    size_t tb = g.cub_temp_bytes;
+    FNX_CUDA_TRY(cub::DeviceScan::ExclusiveSum(g.cub_temp, tb, g.bucket_fill, g.bucket_start, g.M, st));
+    FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
     if (n > 0) {
         grid_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_start, g.bucket_fill, g.tmp_idx);
         FNX_LAUNCH_CHECK("grid_scatter_kernel");
