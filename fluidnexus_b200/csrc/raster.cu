@@ -90,6 +90,7 @@ ImageView image_view(void *chunk, int W, int H, int V) {
     im.mranges = carve<uint2>(p, nt);
     im.tile_src = carve<uint32_t>(p, nt);
     im.tile_dyn_last = carve<uint32_t>(p, nt);
+    im.tile_dyn_first = carve<uint32_t>(p, nt);
     im.tile_cached = carve<uint32_t>(p, nt * TILE_PATCHES);  // per 8x8 patch
     im.tile_count = carve<uint32_t>(p, 2 * nt);  // count and cursor are contiguous: one memset clears both
     im.tile_cursor = im.tile_count + nt;
@@ -1045,7 +1046,7 @@ template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_BWD_MIN_CTAS)
 blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__restrict__ tile_order, const char *__restrict__ records_own,
                  const char *__restrict__ records_static, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_src,
-                 const uint32_t *__restrict__ tile_dyn_last, const float4 *__restrict__ snap,
+                 const uint32_t *__restrict__ tile_dyn_last, const uint32_t *__restrict__ tile_dyn_first, const float4 *__restrict__ snap,
                  const float *__restrict__ bg, const GeomHeader *__restrict__ hdr, ImageView im,
                  const float *__restrict__ dL_dpixels, float *__restrict__ accum) {
     constexpr int REC = RecBytes<C>::value;
@@ -1081,10 +1082,15 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
     // merged streams: everything at or behind L is frozen; the forward left {T, colour behind} at L in `snap`
     const int L = (snap != nullptr && tile_dyn_last != nullptr) ? (int)tile_dyn_last[tslot] : 0x7FFFFFFF;
     total = min(total, L);
+    // ... and everything in FRONT of the tile's first dynamic record F is frozen too.  The back-to-front walk exists to hand every
+    // record with a gradient its transmittance and the colour behind it; once it has passed the nearest one, the records further
+    // to the front (about half of a tile's static span in the bench scenes: the near side of the background shell) change
+    // nothing that is written.
+    const int F = (tile_dyn_first != nullptr && snap != nullptr) ? min((int)tile_dyn_first[tslot], total) : 0;
     if (hdr->overflow) total = 0;
-    if (total == 0) return;
-    const int nbatch = (total + BATCH - 1) / BATCH;
-    // batch bi (processing order) covers span indices [lo, hi) with hi = total - bi*BATCH
+    if (total - F <= 0) return;
+    const int nbatch = (total - F + BATCH - 1) / BATCH;
+    // batch bi (processing order) covers span indices [lo, hi) with hi = total - bi*BATCH, lo = max(F, hi - BATCH)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) mbar_init(&s_bar[s], 1);
@@ -1095,7 +1101,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
 #pragma unroll
         for (int s = 0; s < STAGES; s++)
             if (s < nbatch) {
-                const int hi = total - s * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+                const int hi = total - s * BATCH, lo = max(F, hi - BATCH), n = hi - lo;
                 mbar_arrive_expect_tx(&s_bar[s], n * REC);
                 bulk_g2s(s_rec[s], records + ((size_t)range.x + lo) * REC, n * REC, &s_bar[s]);
             }
@@ -1152,13 +1158,13 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
             cta_sync();  // everyone finished reading the stage that is about to be refilled
             if (threadIdx.x == 0 && bi + STAGES - 1 < nbatch) {
                 const int nb = bi + STAGES - 1, ns = nb % STAGES;
-                const int hi = total - nb * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+                const int hi = total - nb * BATCH, lo = max(F, hi - BATCH), n = hi - lo;
                 mbar_arrive_expect_tx(&s_bar[ns], n * REC);
                 bulk_g2s(s_rec[ns], records + ((size_t)range.x + lo) * REC, n * REC, &s_bar[ns]);
             }
         }
         mbar_wait(&s_bar[s], (bi / STAGES) & 1);
-        const int hi = total - bi * BATCH, lo = max(0, hi - BATCH), n = hi - lo;
+        const int hi = total - bi * BATCH, lo = max(F, hi - BATCH), n = hi - lo;
         if (lo >= warp_last) continue;  // nothing in this batch reaches this warp's pixels
         const float4 *rec = reinterpret_cast<const float4 *>(s_rec[s]);
         uint32_t words[BATCH / 32];
@@ -1821,7 +1827,7 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
     dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), a->tile_order, b.records, nullptr, im.ranges,
-                                                        nullptr, nullptr, nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
+                                                        nullptr, nullptr, nullptr, nullptr, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
     prof_begin(SEC_GEOM_BWD, st);
@@ -1851,7 +1857,8 @@ __global__ void __launch_bounds__(256)
 merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__restrict__ ranges_stat, const char *__restrict__ rec_dyn,
              const char *__restrict__ rec_stat, char *__restrict__ rec_merged, GeomHeader *__restrict__ hdr_dyn,
              const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, const int32_t *__restrict__ view_map,
-             uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
+             uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last,
+             uint32_t *__restrict__ tile_dyn_first) {
     __shared__ float s_depth[MERGE_SMEM];
     __shared__ unsigned long long s_base;
     const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
@@ -1866,7 +1873,7 @@ merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__re
     if (hdr_stat->static_prepared) nb = min(nb, (int)max(max(static_last[4 * ts], static_last[4 * ts + 1]), max(static_last[4 * ts + 2], static_last[4 * ts + 3])));
     if (hdr_dyn->overflow) nf = 0;
     if (nf == 0) {
-        if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
+        if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; tile_dyn_first[t] = 0u; }
         return;
     }
     // the merged span of this tile is bump-allocated (tile order inside the merged stream does not matter; the ranges
@@ -1908,6 +1915,7 @@ merge_kernel(int ntiles, const uint2 *__restrict__ ranges_dyn, const uint2 *__re
         float4 *dst = reinterpret_cast<float4 *>(rec_merged + (ms + i + lo) * 48);
         dst[0] = r0; dst[1] = r1; dst[2] = r2;
         if (i == nf - 1) tile_dyn_last[t] = (uint32_t)(i + lo + 1);  // dynamic depths ascend: this is the deepest one
+        if (i == 0) tile_dyn_first[t] = (uint32_t)lo;                // ... and this the nearest: `lo` static records lie in front of it
     }
 }
 
@@ -1918,7 +1926,8 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
                     const unsigned long long *__restrict__ bkeys, unsigned long long *__restrict__ bkeys2, GeomView g,
                     const float *__restrict__ colors, const char *__restrict__ rec_stat, char *__restrict__ rec_merged,
                     const GeomHeader *__restrict__ hdr_stat, const uint32_t *__restrict__ static_last, const int32_t *__restrict__ view_map,
-                    uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last) {
+                    uint2 *__restrict__ mranges, uint32_t *__restrict__ tile_src, uint32_t *__restrict__ tile_dyn_last,
+                    uint32_t *__restrict__ tile_dyn_first) {
     __shared__ unsigned long long s_key[SORT_CAP];
     __shared__ unsigned long long s_base;
     const size_t t = (size_t)blockIdx.y * ntiles + blockIdx.x;
@@ -1930,7 +1939,7 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
         nb = min(nb, (int)max(max(static_last[4 * ts], static_last[4 * ts + 1]), max(static_last[4 * ts + 2], static_last[4 * ts + 3])));
     if (g.hdr->overflow) nf = 0;
     if (nf == 0) {
-        if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; }
+        if (threadIdx.x == 0) { mranges[t] = make_uint2(b.x, b.x + nb); tile_src[t] = 1u; tile_dyn_last[t] = 0u; tile_dyn_first[t] = 0u; }
         return;
     }
     if (threadIdx.x == 0) {
@@ -1982,6 +1991,7 @@ merge_bucket_kernel(int ntiles, int P, int gx, bool exact_rect, const uint2 *__r
         dst[1] = make_float4(co.z, co.w, c0, c1);
         dst[2] = make_float4(c2, __uint_as_float(slot), __uint_as_float(d), 0.f);
         if (i == nf - 1) tile_dyn_last[t] = (uint32_t)(i + lo + 1);
+        if (i == 0) tile_dyn_first[t] = (uint32_t)lo;
     }
 }
 
@@ -2011,10 +2021,10 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     if (a->flags & FNX_BUCKET_BINNING)
         merge_bucket_kernel<<<grid, 256, 0, st>>>(ntiles, P, gx, (a->flags & FNX_EXACT_RECT) != 0, im.ranges, ims.ranges, b.bkeys, b.bkeys2, g,
                                                   a->colors, bs.records, (char *)merged_records, gs.hdr, ims.tile_last, a->static_view_map,
-                                                  im.mranges, im.tile_src, im.tile_dyn_last);
+                                                  im.mranges, im.tile_src, im.tile_dyn_last, im.tile_dyn_first);
     else
         merge_kernel<<<grid, 256, 0, st>>>(ntiles, im.ranges, ims.ranges, b.records, bs.records, (char *)merged_records, g.hdr, gs.hdr,
-                                           ims.tile_last, a->static_view_map, im.mranges, im.tile_src, im.tile_dyn_last);
+                                           ims.tile_last, a->static_view_map, im.mranges, im.tile_src, im.tile_dyn_last, im.tile_dyn_first);
     prof_end(SEC_PACK, st);
     FNX_LAUNCH_CHECK("merge_kernel");
     prof_begin(SEC_BLEND_FWD, st);
@@ -2065,7 +2075,7 @@ static int backward_merged(const fnx_raster_args *a, const fnx_raster_scratch *d
     dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_BWD, st);
     blend_bwd_kernel<3><<<grid, BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, a->tile_order, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
-                                                        im.tile_dyn_last, im.snap, a->bg, g.hdr, im, dL_dout_color, g.accum);
+                                                        im.tile_dyn_last, im.tile_dyn_first, im.snap, a->bg, g.hdr, im, dL_dout_color, g.accum);
     prof_end(SEC_BLEND_BWD, st);
     FNX_LAUNCH_CHECK("blend_bwd_kernel");
     prof_begin(SEC_GEOM_BWD, st);

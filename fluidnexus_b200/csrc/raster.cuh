@@ -72,6 +72,7 @@ struct ImageView {
     uint2 *mranges;          // [V*ntiles] merged ranges (static + dynamic streams), see fnx_raster_blend_merged
     uint32_t *tile_src;      // [V*ntiles] 0: the tile's span lives in the call's own record stream, 1: in the static one
     uint32_t *tile_dyn_last; // [V*ntiles] merged streams: 1 + span index of the tile's last dynamic record (0: none)
+    uint32_t *tile_dyn_first; // [V*ntiles] merged streams: span index of the tile's FIRST dynamic record (everything in front is frozen)
     uint32_t *tile_cached;   // [V*ntiles*4] static stream, per patch: 1 <=> the caller's out_color/out_depth hold its static-only render
     float4 *snap;            // [V*H*W] merged streams: {T, colour behind} right after the tile's last dynamic record
     uint32_t *tile_count;    // [V*ntiles] bucket binning: instances per tile (histogram written by the preprocess)
