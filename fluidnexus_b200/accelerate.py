@@ -12,6 +12,10 @@ the reference: an import hook patches two of its modules as they are imported,
   utils.loss_utils.distance_loss       -> fluidnexus_b200.physics.pair_distance_loss (grid hash, O(V) memory, same value)
   scene.camera.Camera.original_image   -> a tensor that answers `.float().cuda()` / `.cuda()` with a device copy made once
                                           (the image of a camera never changes; the reference re-uploads it ~10^5 times per run)
+  gaussian_splatting.gm_fluid / gm_dynamics GaussianModel.get_visual_xyz_from_nn, get_gas_constraints_from_exyz_nn,
+  get_gas_constraints_from_vel_nn_guess -> fluidnexus_b200.physics.visual_advect / density_ratio (one fused forward and one fused
+                                          backward gather each instead of an int64 edge list + ~12 gather / index_add_ kernels and
+                                          their autograd twins, gm_fluid.py:1107-1158, 1291-1336; same values and gradients)
 
 Everything else -- the loop, the model classes, the render pipes, logging with .item() -- stays the reference's.  This is a
 convenience layer on top of the drop-in boundary, not part of it: nothing in fluidnexus_b200 depends on it, and the parity tests
@@ -84,6 +88,42 @@ def _patch_loss_utils(mod):
     mod.l1_loss, mod.ssim, mod.distance_loss = l1_loss, ssim, distance_loss
 
 
+def _patch_model(mod):
+    from . import physics
+    gm = mod.GaussianModel
+    if getattr(gm, "_fnx_patched", False):
+        return
+    gm._fnx_original = {k: getattr(gm, k) for k in ("get_visual_xyz_from_nn", "get_gas_constraints_from_exyz_nn", "get_gas_constraints_from_vel_nn_guess")}
+
+    def get_visual_xyz_from_nn(self):                       # gm_fluid.py:1291-1336
+        if not self._estimate_xyz_nn.is_cuda:
+            return gm._fnx_original["get_visual_xyz_from_nn"](self)
+        return physics.visual_advect(self._estimate_xyz_nn * self.scale_factor, self._xyz, self._visual_xyz.detach(), self.H, self._secs, self.KNN_K)
+
+    def get_gas_constraints_from_exyz_nn(self):             # gm_fluid.py:1107-1132
+        if not self._estimate_xyz_nn.is_cuda:
+            return gm._fnx_original["get_gas_constraints_from_exyz_nn"](self)
+        return physics.density_ratio(self._estimate_xyz_nn * self.scale_factor, self._imass, self.H, self.p0, self.KNN_K)
+
+    def get_gas_constraints_from_vel_nn_guess(self):        # gm_fluid.py:1134-1158 (the next-tick map itself stays the reference's)
+        if not self._estimate_xyz_nn.is_cuda:
+            return gm._fnx_original["get_gas_constraints_from_vel_nn_guess"](self)
+        return physics.density_ratio(self.get_guess_hidden_particles_from_nn(), self._imass, self.H, self.p0, self.KNN_K)
+
+    gm.get_visual_xyz_from_nn = get_visual_xyz_from_nn
+    gm.get_gas_constraints_from_exyz_nn = get_gas_constraints_from_exyz_nn
+    gm.get_gas_constraints_from_vel_nn_guess = get_gas_constraints_from_vel_nn_guess
+    gm._fnx_patched = True
+
+
+def _unpatch_model(mod):
+    gm = mod.GaussianModel
+    if getattr(gm, "_fnx_patched", False):
+        for k, v in gm._fnx_original.items():
+            setattr(gm, k, v)
+        gm._fnx_patched = False
+
+
 def _patch_camera(mod):
     cam = mod.Camera
     if getattr(cam, "_fnx_patched", False):
@@ -127,13 +167,16 @@ class _PatchFinder(importlib.abc.MetaPathFinder):
         return None
 
 
-def install_accelerators(loss_utils=True, ground_truth_cache=True):
-    """Patch the reference's `utils.loss_utils` and `scene.camera` as (or if already) imported; see the module docstring.
-    Call after fluidnexus_b200.install_compat() and before the reference's entry script imports its modules."""
+def install_accelerators(loss_utils=True, ground_truth_cache=True, physics_terms=True):
+    """Patch the reference's `utils.loss_utils`, `scene.camera` and model classes as (or if already) imported; see the module
+    docstring.  Call after fluidnexus_b200.install_compat() and before the reference's entry script imports its modules."""
     if loss_utils:
         _PATCHERS["utils.loss_utils"] = _patch_loss_utils
     if ground_truth_cache:
         _PATCHERS["scene.camera"] = _patch_camera
+    if physics_terms:
+        _PATCHERS["gaussian_splatting.gm_fluid"] = _patch_model
+        _PATCHERS["gaussian_splatting.gm_dynamics"] = _patch_model
     for name, fn in list(_PATCHERS.items()):
         if name in sys.modules:
             fn(sys.modules[name])
@@ -152,4 +195,7 @@ def uninstall_accelerators():
         for k, v in mod._fnx_original.items():
             setattr(mod, k, v)
         del mod._fnx_original
+    for name in ("gaussian_splatting.gm_fluid", "gaussian_splatting.gm_dynamics"):
+        if name in sys.modules:
+            _unpatch_model(sys.modules[name])
     _PATCHERS.clear()

@@ -153,6 +153,12 @@ class PhysicalStep:
         # host ground truth is uploaded on its own stream so that the copy for the next frame / iteration overlaps the
         # kernels of the current one (the reference uploads it inline, train_physical_particle.py:325)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        # Host ground truth that is handed in again and again (the images of a frame's cameras do not change over the 250-1000
+        # iterations of the frame; the reference uploads them every time, train_physical_particle.py:353) is uploaded ONCE: device
+        # copies keyed by the host tensor's storage, shape and version counter.  Off by default: the caller
+        # opts in per call (step(..., cache_gt=True)) or per object.
+        self.cache_gt = False
+        self._gt_cache = {}
 
     # -- pieces ---------------------------------------------------------------------------------------------
     def physics_forward(self, fr: FrameState, physics=True):
@@ -363,7 +369,17 @@ class PhysicalStep:
         out.update(gas=fr.scalars[0], next_gas=fr.scalars[1], exyz=fr.scalars[2], dist=fr.scalars[3], grad=fr.de)
         return out
 
-    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None, graph=False, physics=True):
+    def _cached_gt(self, gt):
+        key = (gt.data_ptr(), tuple(gt.shape), gt.dtype)
+        hit = self._gt_cache.get(key)
+        if hit is None or hit[1] != gt._version:
+            if len(self._gt_cache) >= 256:               # bounded: frames come and go
+                self._gt_cache.pop(next(iter(self._gt_cache)))
+            hit = (gt.to(self.dev, non_blocking=True).float().contiguous(), gt._version)
+            self._gt_cache[key] = hit
+        return hit[0]
+
+    def step(self, fr: FrameState, view_ids, gt, update=True, batch=None, graph=False, physics=True, cache_gt=None):
         """One optimiser iteration for one frame.  view_ids: camera indices rendered by THIS process; gt
         [len(view_ids),C,H,W] (device tensor, or a pinned host tensor); `batch` = global number of views of the step
         (defaults to len(view_ids); larger when views are sharded over ranks); physics=False skips the
@@ -371,6 +387,8 @@ class PhysicalStep:
         into a CUDA graph on first use and replays it afterwards (one host call per iteration).
         Returns device tensors that are overwritten by the next step; there is no host synchronisation."""
         batch = len(view_ids) if batch is None else batch
+        if not gt.is_cuda and (self.cache_gt if cache_gt is None else cache_gt):
+            gt = self._cached_gt(gt)                      # a host tensor seen before: its device copy (uploaded once)
         # canonical camera order: the workspaces / captured graphs of a frame are keyed by the SET of cameras, so drawing the
         # same cameras in another order (random.sample) reuses them; the per-view outputs (l1, ssim, images) come back in
         # ascending camera order (out["view_ids"])

@@ -191,6 +191,8 @@ def _loop_body_vs_fused_step(case, accelerated):
     if accelerated:
         from fluidnexus_b200.accelerate import CachedImage
         assert ssim.__module__ == "fluidnexus_b200.accelerate" and distance_loss.__module__ == "fluidnexus_b200.accelerate"
+        from helpers.helper_gaussian import get_model
+        assert get_model(CASES[case][1]).get_visual_xyz_from_nn.__module__ == "fluidnexus_b200.accelerate"
     else:
         assert ssim.__module__ == "utils.loss_utils"
     config, model, body_name, pipe, C, with_bg, grey, bmax = CASES[case]
