@@ -30,7 +30,8 @@ class RasterArgs(C.Structure):
         ("tan_fov_x", C.c_float), ("tan_fov_y", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("flags", C.c_uint32), ("instance_capacity_hint", C.c_int64),
         ("num_rendered_pinned", C.c_void_p), ("grad_begin", C.c_int32), ("grad_end", C.c_int32),
-        ("tile_order", C.c_void_p), ("static_view_map", C.c_void_p), ("static_views", C.c_int32), ("reserved0", C.c_int32),
+        ("tile_order", C.c_void_p), ("static_view_map", C.c_void_p), ("static_views", C.c_int32), ("sh_degree", C.c_int32),
+        ("sh_coeffs", C.c_int32), ("reserved0", C.c_int32), ("campos", C.c_void_p),
     ]
 
 
@@ -44,7 +45,7 @@ class RasterScratch(C.Structure):
 
 class RasterGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D")]
+                ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D", "dL_dsh")]
 
 
 class FnxError(RuntimeError):

@@ -664,7 +664,7 @@ __device__ __forceinline__ uint32_t patch_mask(const float2 xy, const float4 co,
 template <int C>
 __global__ void __launch_bounds__(256)
 pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_mask, int grad_begin, int grad_end,
-            const float *__restrict__ colors, GeomView g, BinView b, uint2 *__restrict__ ranges) {
+            const float *__restrict__ colors, bool colors_per_slot, GeomView g, BinView b, uint2 *__restrict__ ranges) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long R = g.hdr->num_rendered;
     if (i >= R || i >= cap || g.hdr->overflow) return;
@@ -673,6 +673,7 @@ pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_
     const float2 xy = g.xy[slot];
     const float4 co = g.conic_o[slot];
     const uint32_t gi = slot % (uint32_t)P;
+    const uint32_t ci = colors_per_slot ? slot : gi;   // SH colours depend on the view: one row per (view, Gaussian)
     const float depth = g.depth[slot];
     if (use_mask) {
         const uint32_t tl = tile % (uint32_t)ntiles;
@@ -682,11 +683,11 @@ pack_kernel(long long cap, int P, int gx, int ntiles, bool exact_rect, bool use_
     float4 *rec = reinterpret_cast<float4 *>(b.records + (size_t)i * RecBytes<C>::value);
     rec[0] = make_float4(xy.x, xy.y, co.x, co.y);
     if (C == 3) {
-        const float c0 = colors[3 * (size_t)gi], c1 = colors[3 * (size_t)gi + 1], c2 = colors[3 * (size_t)gi + 2];
+        const float c0 = colors[3 * (size_t)ci], c1 = colors[3 * (size_t)ci + 1], c2 = colors[3 * (size_t)ci + 2];
         rec[1] = make_float4(co.z, co.w, c0, c1);
         rec[2] = make_float4(c2, __uint_as_float(slot), depth, 0.f);
     } else {
-        rec[1] = make_float4(co.z, co.w, colors[gi], __uint_as_float(slot));
+        rec[1] = make_float4(co.z, co.w, colors[ci], __uint_as_float(slot));
     }
     if (i == 0) ranges[tile].x = 0;
     else {
@@ -1447,6 +1448,143 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Spherical-harmonics colours (R3/cuda_rasterizer/forward.cu:20-67, backward.cu:20-132).  Dead on FluidNexus' own pipes (they
+// pass colors_precomp, FD/renderer/pipe_fluid.py:107-118), kept so that the drop-in accepts everything the reference module
+// accepts.  colour(view, Gaussian) = max(0, 0.5 + sum_k B_k(dir) sh_k), dir = normalize(mean - campos), real SH basis up to
+// degree 3 in the ordering and sign convention of the 3DGS code base.  Implemented as two small kernels next to the existing
+// pipeline: the forward fills a per-(view, Gaussian) colour array (+ which channels were clamped) that the pack kernel reads
+// instead of colors_precomp; the backward turns the per-(view, Gaussian) colour gradients into dL/dsh and adds the view-direction
+// term to dL/dmeans3D.  The basis and its gradient are written out as polynomials in (x, y, z) and their partial derivatives.
+// ---------------------------------------------------------------------------------------------------------------
+struct ShView {
+    float *color;        // [V*P, 3]
+    uint32_t *clamped;   // [V*P] bit c: channel c was clamped at 0 (no gradient through it)
+};
+static size_t sh_extra_bytes(int P, int V) { return align_up((size_t)P * V * 12, 256) + align_up((size_t)P * V * 4, 256) + 512; }
+static char *geom_end(const GeomView &g) { return (char *)align_up((size_t)((char *)g.cub_temp + g.cub_temp_bytes), 256); }
+static ShView sh_view(char *p, int P, int V) {
+    ShView s;
+    s.color = carve<float>(p, (size_t)P * V * 3);
+    s.clamped = carve<uint32_t>(p, (size_t)P * V);
+    return s;
+}
+
+constexpr float SH_C0 = 0.28209479177387814f, SH_C1 = 0.4886025119029199f;
+__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f, -0.4570457994644658f,
+                               1.445305721320277f, -0.5900435899266435f};
+
+// B_k(x, y, z) for k < (deg+1)^2 and, if wanted, its partial derivatives
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float *b, float *bx, float *by, float *bz) {
+    const bool grad = bx != nullptr;
+    b[0] = SH_C0;
+    if (grad) bx[0] = by[0] = bz[0] = 0.f;
+    if (deg < 1) return;
+    b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+    if (grad) {
+        bx[1] = 0.f; by[1] = -SH_C1; bz[1] = 0.f;
+        bx[2] = 0.f; by[2] = 0.f; bz[2] = SH_C1;
+        bx[3] = -SH_C1; by[3] = 0.f; bz[3] = 0.f;
+    }
+    if (deg < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.f * zz - xx - yy); b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
+    if (grad) {
+        bx[4] = SH_C2[0] * y; by[4] = SH_C2[0] * x; bz[4] = 0.f;
+        bx[5] = 0.f; by[5] = SH_C2[1] * z; bz[5] = SH_C2[1] * y;
+        bx[6] = -2.f * SH_C2[2] * x; by[6] = -2.f * SH_C2[2] * y; bz[6] = 4.f * SH_C2[2] * z;
+        bx[7] = SH_C2[3] * z; by[7] = 0.f; bz[7] = SH_C2[3] * x;
+        bx[8] = 2.f * SH_C2[4] * x; by[8] = -2.f * SH_C2[4] * y; bz[8] = 0.f;
+    }
+    if (deg < 3) return;
+    b[9] = SH_C3[0] * y * (3.f * xx - yy);
+    b[10] = SH_C3[1] * xy * z;
+    b[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+    b[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    b[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
+    b[14] = SH_C3[5] * z * (xx - yy);
+    b[15] = SH_C3[6] * x * (xx - 3.f * yy);
+    if (grad) {
+        bx[9] = SH_C3[0] * 6.f * xy; by[9] = SH_C3[0] * 3.f * (xx - yy); bz[9] = 0.f;
+        bx[10] = SH_C3[1] * yz; by[10] = SH_C3[1] * xz; bz[10] = SH_C3[1] * xy;
+        bx[11] = SH_C3[2] * (-2.f * xy); by[11] = SH_C3[2] * (4.f * zz - xx - 3.f * yy); bz[11] = SH_C3[2] * 8.f * yz;
+        bx[12] = SH_C3[3] * (-6.f * xz); by[12] = SH_C3[3] * (-6.f * yz); bz[12] = SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy);
+        bx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy); by[13] = SH_C3[4] * (-2.f * xy); bz[13] = SH_C3[4] * 8.f * xz;
+        bx[14] = SH_C3[5] * 2.f * xz; by[14] = SH_C3[5] * (-2.f * yz); bz[14] = SH_C3[5] * (xx - yy);
+        bx[15] = SH_C3[6] * 3.f * (xx - yy); by[15] = SH_C3[6] * (-6.f * xy); bz[15] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sh_color_kernel(int P, int V, int deg, int M, const float *__restrict__ means3D, const float *__restrict__ campos,
+                const float *__restrict__ sh, const int *__restrict__ radii, ShView out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (i >= P) return;
+    const size_t slot = (size_t)v * P + i;
+    if (radii[slot] <= 0) { out.clamped[slot] = 0u; return; }
+    float dx = means3D[3 * i] - campos[3 * v], dy = means3D[3 * i + 1] - campos[3 * v + 1], dz = means3D[3 * i + 2] - campos[3 * v + 2];
+    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv; dy *= inv; dz *= inv;
+    float b[16];
+    sh_basis(deg, dx, dy, dz, b, nullptr, nullptr, nullptr);
+    const int nb = (deg + 1) * (deg + 1);
+    const float *c = sh + (size_t)i * M * 3;
+    float rgb[3] = {0.5f, 0.5f, 0.5f};
+    for (int k = 0; k < nb; k++) {
+        rgb[0] += b[k] * c[3 * k]; rgb[1] += b[k] * c[3 * k + 1]; rgb[2] += b[k] * c[3 * k + 2];
+    }
+    uint32_t cl = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        if (rgb[ch] < 0.f) { cl |= 1u << ch; rgb[ch] = 0.f; }
+        out.color[3 * slot + ch] = rgb[ch];
+    }
+    out.clamped[slot] = cl;
+}
+
+// per Gaussian, summed over the views: dL/dsh [P, M, 3] (overwritten) and the SH term ADDED to dL/dmeans3D
+__global__ void __launch_bounds__(256)
+sh_bwd_kernel(int P, int V, int deg, int M, const float *__restrict__ means3D, const float *__restrict__ campos,
+              const float *__restrict__ sh, const int *__restrict__ radii, ShView f, const float *__restrict__ accum,
+              float *__restrict__ dL_dsh, float *__restrict__ dL_dmeans3D) {
+    constexpr int ACC = AccFloats<3>::value;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int nb = (deg + 1) * (deg + 1);
+    const float *c = sh + (size_t)i * M * 3;
+    float gsh[16][3];
+    for (int k = 0; k < 16; k++) gsh[k][0] = gsh[k][1] = gsh[k][2] = 0.f;
+    float gm[3] = {0.f, 0.f, 0.f};
+    for (int v = 0; v < V; v++) {
+        const size_t slot = (size_t)v * P + i;
+        if (radii[slot] <= 0) continue;
+        const float *row = accum + slot * ACC;
+        const uint32_t cl = f.clamped[slot];
+        const float g[3] = {(cl & 1u) ? 0.f : row[6], (cl & 2u) ? 0.f : row[7], (cl & 4u) ? 0.f : row[8]};
+        const float vx = means3D[3 * i] - campos[3 * v], vy = means3D[3 * i + 1] - campos[3 * v + 1], vz = means3D[3 * i + 2] - campos[3 * v + 2];
+        const float len2 = vx * vx + vy * vy + vz * vz, inv = rsqrtf(len2);
+        const float x = vx * inv, y = vy * inv, z = vz * inv;
+        float b[16], bx[16], by[16], bz[16];
+        sh_basis(deg, x, y, z, b, bx, by, bz);
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;   // dL/ddir
+        for (int k = 0; k < nb; k++) {
+            const float w = c[3 * k] * g[0] + c[3 * k + 1] * g[1] + c[3 * k + 2] * g[2];
+            ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+            gsh[k][0] += b[k] * g[0]; gsh[k][1] += b[k] * g[1]; gsh[k][2] += b[k] * g[2];
+        }
+        // through dir = v / |v|:  (I - dir dir^T) / |v|
+        const float dot = x * ddx + y * ddy + z * ddz;
+        gm[0] += (ddx - x * dot) * inv; gm[1] += (ddy - y * dot) * inv; gm[2] += (ddz - z * dot) * inv;
+    }
+    if (dL_dsh != nullptr)
+        for (int k = 0; k < M; k++)
+            for (int ch = 0; ch < 3; ch++) dL_dsh[((size_t)i * M + k) * 3 + ch] = k < nb ? gsh[k][ch] : 0.f;
+    if (dL_dmeans3D != nullptr) {
+        dL_dmeans3D[3 * i] += gm[0]; dL_dmeans3D[3 * i + 1] += gm[1]; dL_dmeans3D[3 * i + 2] += gm[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 // Ring of pinned int64 slots + events for the instance-count read-back of forwards that are allowed to wait for it.  One ring
@@ -1481,11 +1619,18 @@ static int validate(const fnx_raster_args *a) {
     FNX_REQUIRE(a->C == 1 || a->C == 3, "C must be 1 or 3 (got %d)", a->C);
     FNX_REQUIRE(a->P >= 0 && a->V >= 1 && a->W > 0 && a->H > 0, "bad sizes P=%d V=%d W=%d H=%d", a->P, a->V, a->W, a->H);
     if (a->sh != nullptr) {
-        set_error("SH colours are not supported: FluidNexus pipes always pass colors_precomp (FD/renderer/pipe_fluid.py:107-118)");
-        return FNX_ERR_UNSUPPORTED;
+        FNX_REQUIRE(a->C == 3, "For non-RGB, provide precomputed Gaussian colors!");   // rasterizer_impl.cu:226-228
+        FNX_REQUIRE(a->colors == nullptr, "provide exactly one of sh / colors");
+        FNX_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3 && a->sh_coeffs >= (a->sh_degree + 1) * (a->sh_degree + 1) && a->sh_coeffs <= 16,
+                    "sh_degree must be 0..3 and sh_coeffs in [(degree+1)^2, 16]");
+        FNX_REQUIRE(a->campos != nullptr, "campos [V,3] must be given with sh");
+        if (a->flags & (FNX_BUCKET_BINNING | FNX_BIN_ONLY | FNX_NO_HOST_SYNC)) {
+            set_error("SH colours are implemented for the plain forward / backward (no workspaces, no merged streams)");
+            return FNX_ERR_UNSUPPORTED;
+        }
     }
     if (a->P > 0) {
-        FNX_REQUIRE(a->means3D && a->colors && a->opacities, "means3D / colors / opacities must be given");
+        FNX_REQUIRE(a->means3D && (a->colors || a->sh) && a->opacities, "means3D / colors (or sh) / opacities must be given");
         FNX_REQUIRE((a->scales && a->rotations) || a->cov3D_precomp, "need scales+rotations or cov3D_precomp");
         FNX_REQUIRE(a->view_matrix && a->proj_matrix && a->bg, "view_matrix / proj_matrix / bg must be given");
     }
@@ -1616,8 +1761,8 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
         const bool all_grad = !all_frozen && a->grad_end <= a->grad_begin;
         pack_kernel<C><<<(unsigned)((sort_items + 255) / 256), 256, 0, st>>>(cap, P, gx, ntiles, exact_rect, use_mask,
                                                                             all_grad ? 0 : (all_frozen ? 0 : a->grad_begin),
-                                                                            all_grad ? P : (all_frozen ? 0 : a->grad_end), a->colors, g, b,
-                                                                            im.ranges);
+                                                                            all_grad ? P : (all_frozen ? 0 : a->grad_end), a->sh ? sh_view(geom_end(g), P, V).color : a->colors,
+                                                                            a->sh != nullptr, g, b, im.ranges);
         prof_end(SEC_PACK, st);
         FNX_LAUNCH_CHECK("pack_kernel");
     }
@@ -1662,7 +1807,7 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
         if (rc) return rc;
     }
 
-    scratch->geom_bytes = geom_bytes(P, V);
+    scratch->geom_bytes = geom_bytes(P, V) + (a->sh ? sh_extra_bytes(P, V) : 0);
     scratch->geom = ag(cg, scratch->geom_bytes);
     scratch->image_bytes = image_bytes(W, H, V);
     scratch->image = ai(ci, scratch->image_bytes);
@@ -1686,6 +1831,9 @@ static int forward_impl(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, fnx
                                              (const float4 *)a->rotations, a->opacities, a->cov3D_precomp, a->view_matrix,
                                              a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y, gx, gy,
                                              exact_rect, radii, g, bucket ? im.tile_count : nullptr);
+    if (a->sh != nullptr) {
+        sh_color_kernel<<<pgrid, 256, 0, st>>>(P, V, a->sh_degree, a->sh_coeffs, a->means3D, a->campos, a->sh, radii, sh_view(geom_end(g), P, V));
+    }
     prof_end(SEC_PREPROCESS, st);
     FNX_LAUNCH_CHECK("preprocess_kernel");
     if (bucket_dyn) {  // histogram -> bucket offsets -> unsorted per-tile buckets; fnx_raster_blend_merged sorts and merges them
@@ -1836,6 +1984,12 @@ static int backward_impl(const fnx_raster_args *a, const fnx_raster_scratch *scr
                                                         a->proj_matrix, W, H, a->tan_fov_x, a->tan_fov_y, focal_x, focal_y,
                                                         radii, g.cov3D, g.accum, (a->grad_end <= a->grad_begin) ? 0 : a->grad_begin,
                                                         (a->grad_end <= a->grad_begin) ? P : a->grad_end, *gr);
+    if (a->sh != nullptr) {
+        if constexpr (C == 3) {
+            sh_bwd_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, V, a->sh_degree, a->sh_coeffs, a->means3D, a->campos, a->sh, radii,
+                                                           sh_view(geom_end(g), P, V), g.accum, gr->dL_dsh, gr->dL_dmeans3D);
+        }
+    }
     prof_end(SEC_GEOM_BWD, st);
     FNX_LAUNCH_CHECK("geom_bwd_kernel");
     return FNX_OK;

@@ -72,7 +72,7 @@ _capacity_hint = {}
 
 def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_modifier, cov3D_precomp, view_matrix,
                    proj_matrix, tan_fov_x, tan_fov_y, H, W, sh=None, prefiltered=False, exact_rect=False,
-                   speculative=True, grad_range=None):
+                   speculative=True, grad_range=None, sh_degree=0, campos=None):
     """One forward through libfnx.  view_matrix/proj_matrix may be [4,4] (one camera, reference API) or
     [V,4,4] (V cameras batched into one launch sequence).  Returns (ctx, color, radii, depth) with shapes
     [C,H,W]/[P]/[1,H,W] for a single camera and [V,C,H,W]/[V,P]/[V,1,H,W] for a batch."""
@@ -85,21 +85,28 @@ def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_
     P = means3D.size(0)
     batched = view_matrix.dim() == 3
     V = view_matrix.size(0) if batched else 1
-    if sh is not None and sh.numel() != 0:
-        raise RuntimeError("SH colours are not supported by libfnx: FluidNexus always passes colors_precomp")
+    use_sh = sh is not None and sh.numel() != 0
     if P and (colors is None or colors.numel() == 0):
         if C_ != 3:
             raise RuntimeError("For non-RGB, provide precomputed Gaussian colors!")  # rasterizer_impl.cu:226-228
-        raise RuntimeError("SH colours are not supported by libfnx: FluidNexus always passes colors_precomp")
+        if not use_sh:
+            raise RuntimeError("Please provide exactly one of either SHs or precomputed colors!")
+    if use_sh:
+        if sh.dim() != 3 or sh.size(0) != P or sh.size(2) != 3:
+            raise RuntimeError("shs must have dimensions (num_points, num_coefficients, 3)")
+        if campos is None:
+            raise RuntimeError("campos is needed to evaluate SH colours")
+        colors = None
 
     keep = dict(
-        means3D=_f32c(means3D), colors=_f32c(colors), opacities=_f32c(opacities),
+        means3D=_f32c(means3D), colors=_f32c(colors), opacities=_f32c(opacities), sh=_f32c(sh) if use_sh else None,
+        campos=_f32c(campos).reshape(-1, 3).expand(V, 3).contiguous() if use_sh else None,
         scales=_f32c(scales) if scales is not None and scales.numel() else None,
         rotations=_f32c(rotations) if rotations is not None and rotations.numel() else None,
         cov=_f32c(cov3D_precomp) if cov3D_precomp is not None and cov3D_precomp.numel() else None,
         view=_f32c(view_matrix), proj=_f32c(proj_matrix), bg=_f32c(bg),
     )
-    if P and keep["colors"].numel() != P * C_:
+    if P and not use_sh and keep["colors"].numel() != P * C_:
         raise RuntimeError(f"colors_precomp must have {C_} channels per Gaussian")
     out_shape = (V, C_, H, W) if batched else (C_, H, W)
     with torch.cuda.device(dev):
@@ -109,7 +116,9 @@ def raster_forward(C_, bg, means3D, colors, opacities, scales, rotations, scale_
         a = L.RasterArgs()
         a.P, a.V, a.C, a.W, a.H = P, V, C_, W, H
         a.means3D, a.colors, a.opacities = _ptr(keep["means3D"]), _ptr(keep["colors"]), _ptr(keep["opacities"])
-        a.scales, a.rotations, a.cov3D_precomp, a.sh = _ptr(keep["scales"]), _ptr(keep["rotations"]), _ptr(keep["cov"]), None
+        a.scales, a.rotations, a.cov3D_precomp, a.sh = _ptr(keep["scales"]), _ptr(keep["rotations"]), _ptr(keep["cov"]), _ptr(keep["sh"])
+        if use_sh:
+            a.sh_degree, a.sh_coeffs, a.campos = int(sh_degree), int(sh.size(1)), keep["campos"].data_ptr()
         a.view_matrix, a.proj_matrix, a.bg = _ptr(keep["view"]), _ptr(keep["proj"]), _ptr(keep["bg"])
         a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
         a.prefiltered = int(bool(prefiltered))
@@ -143,7 +152,10 @@ def raster_backward(ctx, dL_dout_color, want_means2D=True):
     with torch.cuda.device(dev):
         g["means3D"] = torch.empty((P, 3), dtype=torch.float32, device=dev)
         g["means2D"] = torch.empty((V, P, 3) if V > 1 or ctx.radii.dim() == 2 else (P, 3), dtype=torch.float32, device=dev)
-        g["colors"] = torch.empty((P, C_), dtype=torch.float32, device=dev)
+        use_sh = ctx.keep.get("sh") is not None
+        g["colors"] = torch.zeros((P, C_), dtype=torch.float32, device=dev) if use_sh else torch.empty((P, C_), dtype=torch.float32, device=dev)
+        if use_sh:
+            g["sh"] = torch.empty(ctx.keep["sh"].shape, dtype=torch.float32, device=dev)
         g["opacity"] = torch.empty((P, 1), dtype=torch.float32, device=dev)
         g["cov3D"] = torch.empty((P, 6), dtype=torch.float32, device=dev)
         has_sr = ctx.keep["scales"] is not None
@@ -155,7 +167,8 @@ def raster_backward(ctx, dL_dout_color, want_means2D=True):
         dpix = _f32c(dL_dout_color)
         gr = L.RasterGrads()
         gr.dL_dmeans3D, gr.dL_dmeans2D = g["means3D"].data_ptr(), g["means2D"].data_ptr() if want_means2D else None
-        gr.dL_dcolors, gr.dL_dopacity, gr.dL_dcov3D = g["colors"].data_ptr(), g["opacity"].data_ptr(), g["cov3D"].data_ptr()
+        gr.dL_dcolors, gr.dL_dopacity, gr.dL_dcov3D = None if use_sh else g["colors"].data_ptr(), g["opacity"].data_ptr(), g["cov3D"].data_ptr()
+        gr.dL_dsh = g["sh"].data_ptr() if use_sh else None
         gr.dL_dscales = g["scales"].data_ptr() if has_sr else None
         gr.dL_drotations = g["rotations"].data_ptr() if has_sr else None
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -473,7 +486,7 @@ def make_module(C_):
             fctx, color, radii, depth = raster_forward(
                 C_, rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.view_matrix, rs.proj_matrix, rs.tan_fov_x, rs.tan_fov_y, rs.image_height, rs.image_width, sh=sh,
-                prefiltered=rs.prefiltered)
+                prefiltered=rs.prefiltered, sh_degree=rs.sh_degree, campos=rs.campos)
             ctx.fctx = fctx
             ctx.mark_non_differentiable(radii, depth)
             return color, radii, depth
@@ -483,7 +496,7 @@ def make_module(C_):
             g = raster_backward(ctx.fctx, grad_out_color)
             has_cov = ctx.fctx.keep["cov"] is not None
             # order of R3/diff_gaussian_rasterization_ch3/__init__.py:128-138
-            return (g["means3D"], g["means2D"], None, g["colors"], g["opacity"],
+            return (g["means3D"], g["means2D"], g.get("sh"), g["colors"], g["opacity"],
                     None if has_cov else g["scales"], None if has_cov else g["rotations"],
                     g["cov3D"] if has_cov else None, None)
 

@@ -13,9 +13,9 @@
  *   - view / proj matrices: 16 floats each, the row-major storage of the TRANSPOSED matrices, exactly
  *     what Camera.world_view_transform / full_proj_transform hold (FD/scene/camera.py:90-108).
  *   - quaternions are (r,x,y,z) and are NOT normalised inside (R3/cuda_rasterizer/forward.cu:121).
- *   - colours are always "precomputed" [P,C]; the SH path is dead in FluidNexus (all pipes pass
- *     colors_precomp, FD/renderer/pipe_fluid.py:107-118) and passing sh != NULL returns
- *     FNX_ERR_UNSUPPORTED.
+ *   - colours are "precomputed" [P,C] on every FluidNexus pipe (FD/renderer/pipe_fluid.py:107-118); the reference module's
+ *     other colour input, spherical harmonics (sh [P,M,3] + degree + campos), is accepted by the plain forward / backward for
+ *     3 channels, like the reference.
  *   - all scratch is caller-owned and grown through an allocation callback, like the reference's
  *     resize lambdas (R3/rasterize_points.cu:27-33); its layout is private to the library.
  */
@@ -95,7 +95,9 @@ typedef struct fnx_raster_args {
     const float *scales;        /* [P,3] or NULL when cov3D_precomp is given */
     const float *rotations;     /* [P,4] or NULL */
     const float *cov3D_precomp; /* [P,6] or NULL */
-    const float *sh;            /* must be NULL (FNX_ERR_UNSUPPORTED otherwise) */
+    const float *sh;            /* [P, sh_coeffs, 3] spherical-harmonics coefficients INSTEAD of colors (C == 3 only; colours are
+                                   max(0, 0.5 + sum_k B_k(dir) sh_k), R3/cuda_rasterizer/forward.cu:20-67); plain forward / backward
+                                   only (FNX_ERR_UNSUPPORTED with workspaces / merged streams).  NULL on every FluidNexus pipe. */
     /* per-view inputs */
     const float *view_matrix;   /* [V,16] */
     const float *proj_matrix;   /* [V,16] */
@@ -120,7 +122,10 @@ typedef struct fnx_raster_args {
                                        random.sample(cur_viewpoint_set, batch) cameras per iteration,
                                        FD/entries_fluid_nexus/train_physical_particle.py:337).  NULL = identity (static_views == V). */
     int32_t static_views;           /* cameras of the static stream (0 = V) */
+    int32_t sh_degree;              /* with sh: active degree 0..3 (`degree` of R3/rasterize_points.h:18-37) */
+    int32_t sh_coeffs;              /* with sh: coefficients per Gaussian M (sh is [P, M, 3]), (sh_degree+1)^2 <= M <= 16 */
     int32_t reserved0;
+    const float *campos;            /* with sh: camera centres [V,3] (`campos`) */
 } fnx_raster_args;
 
 /* Opaque handles to the three scratch buffers of one forward (what the reference returns as
@@ -166,6 +171,7 @@ typedef struct fnx_raster_grads {
     float *dL_dscales;   /* [P,3] (written only when scales were given) */
     float *dL_drotations;/* [P,4] raw un-normalised quaternion gradient (backward.cu:326) */
     float *dL_dcov3D;    /* [P,6] */
+    float *dL_dsh;       /* [P,sh_coeffs,3] (written only when sh was given) */
 } fnx_raster_grads;
 
 /* Backward.  dL_dout_color [V,C,H,W].  `a` must equal the forward's args; `scratch` is what forward reported;

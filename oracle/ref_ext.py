@@ -48,10 +48,13 @@ class RefRaster:
         self.mod = load("ch3" if channels == 3 else "ch1")
 
     def forward(self, bg, means3D, colors, opacities, scales, rotations, scale_modifier, view, proj, tan_fov_x, tan_fov_y,
-                H, W, campos=None):
+                H, W, campos=None, sh=None, degree=0):
+        """colors [P,C] or, with sh [P,M,3] + degree + campos, colors=None (the reference's SH colour path)."""
         campos = torch.zeros(3, device=means3D.device) if campos is None else campos
+        colors = _e() if sh is not None else colors
+        self._sh, self._degree = (_e() if sh is None else sh), int(degree)
         args = (bg, means3D, colors, opacities, scales, rotations, float(scale_modifier), _e(), view, proj, float(tan_fov_x),
-                float(tan_fov_y), int(H), int(W), _e(), 0, campos, False)
+                float(tan_fov_y), int(H), int(W), self._sh, self._degree, campos, False)
         num_rendered, color, radii, geom, binning, img, depth = self.mod.rasterize_gaussians(*args)
         self.saved = dict(bg=bg, means3D=means3D, radii=radii, colors=colors, scales=scales, rotations=rotations,
                           scale_modifier=float(scale_modifier), view=view, proj=proj, tfx=float(tan_fov_x),
@@ -61,10 +64,10 @@ class RefRaster:
     def backward(self, dL_dcolor):
         s = self.saved
         args = (s["bg"], s["means3D"], s["radii"], s["colors"], s["scales"], s["rotations"], s["scale_modifier"], _e(),
-                s["view"], s["proj"], s["tfx"], s["tfy"], dL_dcolor, _e(), 0, s["campos"], s["geom"], s["R"], s["binning"],
+                s["view"], s["proj"], s["tfx"], s["tfy"], dL_dcolor, self._sh, self._degree, s["campos"], s["geom"], s["R"], s["binning"],
                 s["img"])
         m2, col, op, m3, cov, sh, sc, rot = self.mod.rasterize_gaussians_backward(*args)
-        return dict(means2D=m2, colors=col, opacity=op, means3D=m3, cov3D=cov, scales=sc, rotations=rot)
+        return dict(means2D=m2, colors=col, opacity=op, means3D=m3, cov3D=cov, scales=sc, rotations=rot, sh=sh)
 
 
 def carve_geom(buf, P):

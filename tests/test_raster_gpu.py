@@ -13,6 +13,7 @@ import torch
 import scenes
 from fluidnexus_b200 import rasterizer as R
 from fluidnexus_b200 import synthetic as S
+from oracle import ref_ext
 from oracle.raster_oracle import RasterOracle
 
 pytestmark = pytest.mark.gpu
@@ -374,3 +375,41 @@ def test_one_static_stream_serves_every_camera_subset(libfnx, subset):
         r = rel(g.cpu().numpy(), gref.cpu().numpy()) if float(gref.abs().max()) > 0 else float(g.abs().max())
         assert r < 2e-5, (it, r)
     assert (ws.tile_state()["tile_src"] != 0).sum() > 0
+
+
+@pytest.mark.skipif(not ref_ext.available("ch3"), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("degree,M", [(0, 1), (1, 4), (2, 16), (3, 16)])
+def test_sh_colour_path_matches_compiled_reference(libfnx, degree, M):
+    """The reference module's other colour input (shs + sh_degree + campos instead of colors_precomp; dead on FluidNexus' pipes,
+    R3/cuda_rasterizer/forward.cu:20-67, backward.cu:20-132) through the drop-in GaussianRasterizer: image / depth / radii and the
+    gradients w.r.t. means3D, shs, opacity, scales, rotations against the compiled reference run live, incl. clamped channels."""
+    import math
+    from fluidnexus_b200 import rasterizer as RZ
+    dev = torch.device("cuda")
+    gs = S.random_gaussians(2500, 3, seed=70, spread=0.2, log_scale=(-4.6, -3.2))
+    cam = S.make_cameras(5, 112, device=dev)[1]
+    rng = np.random.default_rng(degree)
+    sh = rng.normal(0, 0.6, (gs.P, M, 3)).astype(np.float32)          # strong enough to clamp some channels at zero
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+    means, op, sc, rot, shs = t(gs.xyz).requires_grad_(True), t(gs.opacity).requires_grad_(True), t(gs.scales).requires_grad_(True), \
+        t(gs.rotations).requires_grad_(True), t(sh).requires_grad_(True)
+    Settings, Rasterizer, _, _ = RZ.make_module(3)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    rs = Settings(image_height=112, image_width=112, tan_fov_x=math.tan(cam.FoVx * 0.5), tan_fov_y=math.tan(cam.FoVy * 0.5), bg=bg,
+                  scale_modifier=1.0, view_matrix=cam.world_view_transform, proj_matrix=cam.full_proj_transform, sh_degree=degree,
+                  campos=cam.camera_center, prefiltered=False)
+    img, radii, depth = Rasterizer(rs)(means3D=means, means2D=torch.zeros_like(means, requires_grad=True), opacities=op, shs=shs,
+                                       colors_precomp=None, scales=sc, rotations=rot, cov3D_precomp=None)
+    dL = torch.randn(img.shape, device=dev, generator=torch.Generator("cuda").manual_seed(11))
+    (img * dL).sum().backward()
+    rr = ref_ext.RefRaster(3)
+    ro = rr.forward(bg, means.detach(), None, op.detach(), sc.detach(), rot.detach(), 1.0, cam.world_view_transform, cam.full_proj_transform,
+                    rs.tan_fov_x, rs.tan_fov_y, 112, 112, campos=cam.camera_center, sh=shs.detach(), degree=degree)
+    rg = rr.backward(dL.contiguous())
+    assert torch.equal(radii, ro["radii"]) and torch.equal(depth, ro["depth"])
+    assert float((img - ro["color"]).abs().max()) < 1e-5
+    rel_ = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    nb = (degree + 1) ** 2
+    assert rel_(shs.grad[:, :nb], rg["sh"][:, :nb]) < 1e-4 and float(shs.grad[:, nb:].abs().max() if nb < M else 0.0) == 0.0
+    for k, mine in (("means3D", means.grad), ("opacity", op.grad), ("scales", sc.grad), ("rotations", rot.grad)):
+        assert rel_(mine.reshape(rg[k].shape), rg[k]) < 1e-4, (k, rel_(mine.reshape(rg[k].shape), rg[k]))
