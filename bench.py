@@ -450,10 +450,11 @@ def run_fnx(args):
                    "instances_per_iteration": R_per_iter,
                    "timing": f"median of >= 5 intervals of exactly {args.steps} steps (barrier + synchronize on both sides, CUDA events, max "
                              f"over ranks), repeated until the leg lasted >= {args.min_leg_seconds} s",
-                   "l2": f"no explicit flush: {G} frames cycle between iterations and one iteration touches "
+                   "l2": f"no explicit flush: {len(mine)} frame(s) per GPU cycle between iterations and one iteration of a frame touches "
                          f"~{((tile_info['records_in_merged_spans'] if tile_info else R_per_iter) * rec + 5 * HW * (16 * Cc + 44)) / 1e6:.0f} MB "
-                         "(record spans + images, ground truth, gradient and SSIM maps), so a frame's data has left the 126 MB L2 "
-                         "by the time its next iteration starts"},
+                         "(record spans + images, ground truth, gradient and SSIM maps) of its own buffers, "
+                         f"{len(mine) * ((tile_info['records_in_merged_spans'] if tile_info else R_per_iter) * rec + 5 * HW * (16 * Cc + 44)) / 1e6:.0f} MB "
+                         "per GPU between two iterations of the same frame, against a 126 MB L2"},
         "e2e": {"value": round(e2e, 3), "unit": "iters/s",
                 "h2d_bytes_per_step": int(G * len(views) * Cc * HW * 4),   # whole job: every (frame, view) image, fp32
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4), "leg": leg_e2e,
