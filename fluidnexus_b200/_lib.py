@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfnx.so")
+LIB_PATH = os.environ.get("FNX_LIBFNX") or os.path.join(_HERE, "libfnx.so")   # (the override is a development switch: A/B builds)
 
 FNX_OK = 0
 FNX_ERR_INVALID, FNX_ERR_CUDA, FNX_ERR_UNSUPPORTED, FNX_ERR_CAPACITY, FNX_ERR_ALLOC = 1, 2, 3, 4, 5

@@ -22,6 +22,7 @@
 //     and merged per tile; tiles without a moving instance keep their pixels; the backward starts at the tile's last
 //     moving record from a snapshot the forward took there.
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <mutex>
 
 #include "raster.cuh"
@@ -792,10 +793,12 @@ __device__ __forceinline__ uint32_t work_unit(const uint32_t *__restrict__ tile_
 //                  backward needs from them only the transmittance T and the colour behind, per pixel, at L.  The
 //                  forward snapshots {T, C} when it passes L and stores {T, (C_final - C) / T} in `snap`, so the
 //                  backward starts at L instead of at the last contributor.
-// Minimum resident CTAs per SM the forward is compiled for (register cap).  Measured (whole bench, it/s): unconstrained
-// (77 registers, 6 CTAs/SM) 1454, 10 (48 registers) 1511, 12 (40 registers, 84 B of spills) 1512.
+// Minimum resident CTAs per SM the forward is compiled for (register cap).  Round 1 (whole bench, it/s): unconstrained
+// (77 registers, 6 CTAs/SM) 1454, 10 (48 registers) 1511, 12 (40 registers, 84 B of spills) 1512.  Round 2, with the accurate expf
+// on kept pairs (more live registers): 10 (48 registers, 44 B of spills) 2016 it/s, forward 3.60 ms per 16-frame step, one frame
+// alone 0.683 ms; 9 (56 registers, 12 B) 2020 / 3.41 / 0.665; 8 (64 registers) 2003 / 3.31 / 0.660.
 #ifndef FNX_FWD_MIN_CTAS
-#define FNX_FWD_MIN_CTAS 10
+#define FNX_FWD_MIN_CTAS 9
 #endif
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_FWD_MIN_CTAS)
@@ -1614,6 +1617,14 @@ static int current_device_index() {
     return d;
 }
 
+// The longest-first start order pays in the BACKWARD (-10 % on the bench workload: its CTAs run 8 per SM and the tail of a launch
+// is a few long tiles); in the forward it measured 3-4 % SLOWER than raster order (A/B in bench.py, round 2), so the forward keeps
+// raster order unless FNX_LPT_FWD=1 is set in the environment (measurement switch).
+static const uint32_t *fwd_tile_order(const fnx_raster_args *a) {
+    static const bool on = [] { const char *e = getenv("FNX_LPT_FWD"); return e != nullptr && e[0] == '1'; }();
+    return on ? a->tile_order : nullptr;
+}
+
 static int validate(const fnx_raster_args *a) {
     FNX_REQUIRE(a != nullptr, "args is NULL");
     FNX_REQUIRE(a->C == 1 || a->C == 3, "C must be 1 or 3 (got %d)", a->C);
@@ -1769,7 +1780,7 @@ static int bin_and_blend(const fnx_raster_args *a, cudaStream_t st, GeomView &g,
     if (a->flags & FNX_BIN_ONLY) return FNX_OK;  // the caller blends a merged stream (fnx_raster_blend_merged)
     dim3 grid(ntiles * CTAS_PER_TILE, V);
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), a->tile_order, b.records, nullptr,
+    blend_fwd_kernel<C><<<grid, BLEND_THREADS, 0, st>>>(a->W, a->H, gx, gy, (long long)P * V < (1ll << SLOT_BITS), fwd_tile_order(a), b.records, nullptr,
                                                         im.ranges, nullptr, nullptr, nullptr, nullptr, g.depth, a->bg, g.hdr, im, out_color,
                                                         out_depth);
     prof_end(SEC_BLEND_FWD, st);
@@ -2182,7 +2193,7 @@ static int blend_merged(const fnx_raster_args *a, const fnx_raster_scratch *dyn,
     prof_end(SEC_PACK, st);
     FNX_LAUNCH_CHECK("merge_kernel");
     prof_begin(SEC_BLEND_FWD, st);
-    blend_fwd_kernel<3><<<dim3(ntiles * CTAS_PER_TILE, V), BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, a->tile_order, (const char *)merged_records, bs.records, im.mranges, im.tile_src,
+    blend_fwd_kernel<3><<<dim3(ntiles * CTAS_PER_TILE, V), BLEND_THREADS, 0, st>>>(W, H, gx, gy, true, fwd_tile_order(a), (const char *)merged_records, bs.records, im.mranges, im.tile_src,
                                                         tile_cache ? im.tile_cached : nullptr, im.tile_dyn_last, im.snap, g.depth, a->bg,
                                                         g.hdr, im, out_color, out_depth);
     prof_end(SEC_BLEND_FWD, st);

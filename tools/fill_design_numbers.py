@@ -1,0 +1,75 @@
+"""Dev tool: fills the @@...@@ placeholders of DESIGN.md / README.md from the bench lines committed under profiles/ (r2_*)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def L(name):
+    return json.loads(open(os.path.join(P, name)).read().strip().splitlines()[0])
+
+
+def main():
+    d, r = L("r2_bench_fnx_n1.json"), L("r2_bench_reference_n1.json")
+    G = d["config"]["frames_in_flight"]
+    rep = {
+        "V1": f"{d['value']:.0f}", "MS1": f"{d['ms_per_step'] / G:.3f}", "E1": f"{d['e2e']['value']:.0f}", "EC1": f"{d['e2e']['with_gt_cache']['value']:.0f}",
+        "NC1": f"{d['static_tile_cache']['value_with_cache_off']:.0f}", "NCE1": f"{d['static_tile_cache']['e2e_with_cache_off']:.0f}",
+        "L1": f"{d['value_lanes1']:.0f}", "LAT": f"{d['latency_one_frame_ms']:.2f}", "LPI": f"{d['launches_per_iteration']:.0f}",
+        "CORES": str(r["cpu_baseline"]["cores"]), "R1": f"{r['value']:.3f}", "RMS": f"{r['ms_per_step'] / 1e3:.2f}",
+        "RG": f"{r['reference_gpu_part_ms_per_iteration']:.1f}",
+        "X_THR": f"{r['reference_gpu_part_ms_per_iteration'] / (d['ms_per_step'] / G):.1f}",
+        "X_LAT": f"{r['reference_gpu_part_ms_per_iteration'] / d['latency_one_frame_ms']:.1f}",
+        "D0": f"{d['dropin_unchanged_python']['value']:.1f}", "D1": f"{d['dropin_unchanged_python']['with_accelerators']['value']:.1f}",
+        "CPU": f"{d['cpu_baseline']['value']:.3f}",
+    }
+    for wl, tag in (("scalar", "SC"), ("c2", "C2"), ("ball", "BA")):
+        x, y = L(f"r2_bench_{wl}_n1.json"), L(f"r2_bench_reference_{wl}.json")
+        rf = x["roofline"]
+        rep[tag] = f"{x['value']:.0f} / {x['e2e']['value']:.0f}"
+        rep[tag + "L"] = f"{x['latency_one_frame_ms']:.2f}"
+        rep[tag + "R"] = f"{y['value']:.3f} iters/s ({y['reference_gpu_part_ms_per_iteration']:.1f} ms)"
+        rep[tag + "K"] = f"`{rf['kernel']}` {rf['ms_per_launch']:.3f} ms / launch, {100 * rf['frac']:.1f} %, {100 * rf['issue_rate']['frac']:.0f} %"
+        if wl == "scalar":
+            sec = x["sections_ms_per_step"]
+            rast = sum(sec[k] for k in ("preprocess", "depth_sort", "emit", "tile_sort", "pack", "blend_fwd", "blend_bwd", "geom_bwd", "image_loss") if k in sec) / x["config"]["frames_in_flight"]
+            rep["SCRAST"] = f"{rast:.2f}"
+            rep["SCRG"] = f"{y['reference_gpu_part_ms_per_iteration']:.1f}"
+    rows = ["| GPUs | `value` iters/s | × 1 GPU | efficiency | `e2e` iters/s | efficiency | `e2e` with ground-truth cache | cache-off `value` | sharded == single-rank (max abs param delta) |", "|---|---|---|---|---|---|---|---|---|"]
+    for n in (1, 2, 4, 8):
+        try:
+            x = L(f"r2_bench_fnx_n{n}.json")
+        except FileNotFoundError:
+            continue
+        sp = x.get("sharding_parity") or {}
+        rows.append(f"| {n} | {x['value']:.0f} | {x['value'] / d['value']:.2f} | {x['value'] / d['value'] / n:.3f} | {x['e2e']['value']:.0f} | {x['e2e']['value'] / d['e2e']['value'] / n:.3f} | "
+                    f"{x['e2e']['with_gt_cache']['value']:.0f} | {x['static_tile_cache']['value_with_cache_off']:.0f} | {sp.get('max_abs_param_delta', '—')} |")
+    rep["SCALING"] = "\n".join(rows)
+    one = L("r2_bench_fnx_n1_oneframe.json")
+    v = [f"1 GPU {one['value']:.0f} iters/s"]
+    for n in (2, 4):
+        try:
+            x = L(f"r2_bench_fnx_n{n}_views.json")
+            v.append(f"{n} GPUs {x['value']:.0f} ({x['value'] / one['value']:.2f} ×; parity max|Δ| {x['sharding_parity']['max_abs_param_delta']:.0e})")
+        except FileNotFoundError:
+            pass
+    rep["VIEWS"] = ", ".join(v) + " (`profiles/r2_bench_fnx_n{1_oneframe,2_views,4_views}.json`). One iteration of one frame is a latency chain (0.69 ms at 1 GPU, of which the five views' blend launches are ~0.4 ms); splitting the views shortens only that part, the physics stays on the frame's owner, and every step adds an all-reduce of 0.34 MB."
+    rep["README_NUMBERS"] = (f"{rep['V1']} train-step iterations/s at 1 GPU on the smoke workload (200k Gaussians, 5 views 512², 28k hidden particles; "
+                             f"{rep['E1']} end to end with host ground truth uploaded every iteration; {rep['L1']} with the frames one after the other on one stream, "
+                             f"{rep['LAT']} ms per iteration for a single frame); the reference's GPU part alone takes {rep['RG']} ms per iteration, its full iteration "
+                             f"with host-side physics {rep['RMS']} s. Rendered pixels and median depth are bit-identical to the compiled reference at 50k–300k "
+                             "Gaussians; the reference's own Python and training-loop bodies run unchanged on CUDA through the drop-ins.")
+    for fn in ("DESIGN.md", "README.md"):
+        p = os.path.join(ROOT, fn)
+        s = open(p).read()
+        for k, val in rep.items():
+            s = s.replace(f"@@{k}@@", val)
+        left = [w for w in s.split("@@")[1::2] if w.isupper() or "_" in w]
+        open(p, "w").write(s)
+        print(fn, "unfilled:", sorted(set(left))[:10])
+
+
+if __name__ == "__main__":
+    main()
