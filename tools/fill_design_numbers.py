@@ -45,7 +45,7 @@ def main():
             continue
         sp = x.get("sharding_parity") or {}
         rows.append(f"| {n} | {x['value']:.0f} | {x['value'] / d['value']:.2f} | {x['value'] / d['value'] / n:.3f} | {x['e2e']['value']:.0f} | {x['e2e']['value'] / d['e2e']['value'] / n:.3f} | "
-                    f"{x['e2e']['with_gt_cache']['value']:.0f} | {x['static_tile_cache']['value_with_cache_off']:.0f} | {sp.get('max_abs_param_delta', '—')} |")
+                    f"{x['e2e']['with_gt_cache']['value']:.0f} | {x['static_tile_cache']['value_with_cache_off']:.0f} | {('%.1e' % sp['max_abs_param_delta']) if sp else '—'} |")
     rep["SCALING"] = "\n".join(rows)
     one = L("r2_bench_fnx_n1_oneframe.json")
     v = [f"1 GPU {one['value']:.0f} iters/s"]
