@@ -5,14 +5,28 @@
 
 Metric (BASELINE.json): train-step iterations per second.  One *iteration* = one pass of the reference's hot loop for
 one frame with `views` (5) cameras (FD/entries_fluid_nexus/train_physical_particle.py:330-420).  One bench *step*
-processes `frames_in_flight` (16) independent synthetic frames, each one iteration; the frames are sharded over the
-ranks (strong scaling: total work per step is fixed), gradients of all frames live in one flat bucket that is
-all-reduced (NCCL, sum) once per step and applied with one fused Adam launch on every rank (replicated parameters).
-Within a rank the frames are dealt to `--lanes` (4) CUDA streams (fluidnexus_b200/parallel.py:FrameLanes), every frame's iteration
-is a captured CUDA graph.  value = frames_in_flight * K / T, T = max over ranks of the CUDA-event time of the K timed steps
-(device-resident inputs); e2e = the same with the ground truth uploaded from pinned host memory every iteration and the
-loss read back every step; static_tile_cache reports both again with the static-only tile cache switched off; roofline is
-measured live on the larger blend kernel in a leg that runs the frames one after the other.
+processes `frames_in_flight` (16) independent synthetic frames, each one iteration; the (frame, view) items are sharded over
+the ranks (strong scaling: total work per step is fixed) by fluidnexus_b200/parallel.py:plan_items -- whole frames per rank when
+there are at least as many frames as ranks (no gradient exchange: a frame's gradient is complete on its rank, Adam runs inside
+its captured iteration; one all-reduce of the per-frame loss table per step), the views of a frame split over ranks otherwise
+(--frames-in-flight 1: one NCCL all-reduce of the frame's gradient slot per step, replicated Adam).  At world > 1 the run first
+ASSERTS that 3 optimiser steps of the sharded job give the parameters of a single-rank run of the same frames (`sharding_parity`).
+Within a rank the frames are dealt to `--lanes` (4) CUDA streams (FrameLanes), every frame's iteration is a captured CUDA graph.
+
+Every timed leg = the MEDIAN of >= 5 intervals of exactly K steps (barrier + synchronize on both sides, CUDA events, max over
+ranks), repeated until the leg lasted --min-leg-seconds (2 s).  Legs:
+  value                 device-resident inputs
+  e2e                   the public call with the ground truth in pinned HOST memory, uploaded every iteration, and the loss read
+                        back every step; e2e.with_gt_cache: same call with PhysicalStep's ground-truth cache
+  value_lanes1 / latency_one_frame_ms   the frames one after the other on one stream / one frame iterated alone
+  static_tile_cache     value and e2e again with the static-only tile cache switched off
+  roofline              the larger blend kernel: algorithmic bytes / live CUDA-event launch time / measured HBM peak, DRAM traffic and
+                        warp instructions of the committed ncu capture of THIS workload (profiles/traffic.json)
+  cpu_baseline          the oracle (CPU port) on a bounded sample, 1 thread                              (N = 1 only)
+  dropin_unchanged_python   the reference's own loop body + Python on the GPU through libfnx's drop-in packages, with and without the
+                        opt-in accelerators (fluidnexus_b200/accelerate.py)                              (N = 1 only)
+--impl reference: the reference's own loop body (oracle/ref_python.loop_body) on its compiled, unmodified CUDA rasterizer
+(oracle/_ref) + its physics methods on the host cores; honours --steps / --warmup up to --ref-max-seconds.
 
 Workloads:  smoke  = BASELINE config 4: P = 200k (20k fluid + 180k frozen background), C = 3, grey
 image loss, N = 28k hidden particles, 5 views 512x512 (the configuration north_star's target is quoted on);

@@ -132,5 +132,6 @@ def test_r2_view_sharded_lines(n):
     d = _load(f"r2_bench_fnx_n{n}_views.json")
     assert d["n_gpus"] == n and d["config"]["frames_in_flight"] == 1 and f"split over {n} ranks" in d["config"]["parallelism"]
     sp = d["sharding_parity"]
-    assert sp["ok"] is True and sp["owners"] == [list(range(min(n, 5) if n < 5 else 5))][:1] or sp["ok"] is True
-    assert d["value"] > 0
+    assert sp["ok"] is True and len(sp["owners"][0]) > 1 and sp["max_abs_param_delta"] <= sp["tolerance"]   # frame 0 lives on several ranks
+    one = _load("r2_bench_fnx_n1_oneframe.json")
+    assert d["value"] > one["value"]                       # splitting the views of one frame is faster than one GPU, if modestly
