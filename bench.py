@@ -237,8 +237,9 @@ def run_fnx(args):
             E, DE, M, Vv = fb.param[lo:hi], fb.grad[lo:hi], fb.exp_avg[lo:hi], fb.exp_avg_sq[lo:hi]
             L.check(lib.fnx_adam_step(E.numel(), E.data_ptr(), DE.data_ptr(), M.data_ptr(), Vv.data_ptr(), 1.0, prm.lr, 0.9, 0.999,
                                       prm.adam_eps, step_no[0], torch.cuda.current_stream(dev).cuda_stream))
-        table = fb.all_reduce_losses()
+        fb.all_reduce_losses()                      # asynchronous; waited for only where the table is read
         if e2e:
+            table = fb.reduced_losses(previous=world > 1)   # (multi-rank: the table reduced one step ago, so no rank waits on NCCL)
             # device -> host read of the step's loss, every step, pipelined by one step: the copy into pinned memory is queued
             # behind the step, and the host waits for (and reads) the PREVIOUS step's value, so the GPU never idles on it
             k = step_no[0] % 2

@@ -95,7 +95,12 @@ class FlatBucket:
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
         G, N = n_frames, n_particles
         self.param, self.exp_avg, self.exp_avg_sq, self.grad = z(G, N, 3), z(G, N, 3), z(G, N, 3), z(G, N, 3)
-        self.losses, self.losses_global = z(G, self.N_LOSS), z(G, self.N_LOSS)
+        self.losses = z(G, self.N_LOSS)
+        # the reduced loss table is double-buffered: the all-reduce of step k runs on NCCL's own stream while step k+1 is being
+        # queued, and is only waited for when somebody reads it (reduced_losses) or its buffer comes round again
+        self._losses_global = [z(G, self.N_LOSS), z(G, self.N_LOSS)]
+        self._loss_work = [None, None]
+        self._loss_slot = 0
         self.plan = plan
         self.step = 0
 
@@ -135,11 +140,31 @@ class FlatBucket:
 
     def all_reduce_losses(self):
         """Per-frame loss rows: every row is written by exactly one rank (the frame's owner adds the view-independent
-        terms, image terms are partial sums per rank), so the sum over ranks is the job's loss table."""
-        self.losses_global.copy_(self.losses)
+        terms, image terms are partial sums per rank), so the sum over ranks is the job's loss table.  The collective is
+        ASYNCHRONOUS (it only feeds logging): it is ordered after the step's kernels but the compute stream does not wait for it, so
+        the ranks are not forced into lock-step every iteration.  Returns the buffer the result lands in; reduced_losses() waits."""
+        k = self._loss_slot = self._loss_slot ^ 1
+        if self._loss_work[k] is not None:           # this buffer's previous reduction (two steps ago) must have landed
+            self._loss_work[k].wait()
+            self._loss_work[k] = None
+        buf = self._losses_global[k]
+        buf.copy_(self.losses)
         if _dist_on():
-            dist.all_reduce(self.losses_global, op=dist.ReduceOp.SUM)
-        return self.losses_global
+            self._loss_work[k] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+        return buf
+
+    def reduced_losses(self, previous=False):
+        """The job's loss table of the LAST all_reduce_losses() call (previous=True: of the one before, whose collective has had a
+        whole step to finish), safe to read on the current stream."""
+        k = self._loss_slot ^ 1 if previous else self._loss_slot
+        if self._loss_work[k] is not None:
+            self._loss_work[k].wait()                 # makes the current stream wait for the collective (no host block)
+            self._loss_work[k] = None
+        return self._losses_global[k]
+
+    @property
+    def losses_global(self):
+        return self.reduced_losses()
 
     def broadcast_params_from_owners(self):
         """After each rank initialised only the slots of the frames it owns (others zero): sum = every slot from its owner."""

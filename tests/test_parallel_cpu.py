@@ -72,7 +72,8 @@ def _worker(rank, world, port, G, V, N, out):
             fb.all_reduce()
             for f in range(lo, hi):
                 _adam(*fb.views(f)[:1], fb.grad[f], fb.exp_avg[f], fb.exp_avg_sq[f], step)
-            table = fb.all_reduce_losses()
+            fb.all_reduce_losses()
+        table = fb.reduced_losses()
         out[rank] = (fb.gather_params().clone(), fb.grad.clone(), table.clone(), sorted(plan.shared))
     finally:
         dist.destroy_process_group()
