@@ -734,6 +734,14 @@ __device__ __forceinline__ bool pair_alpha(float x, float y, float a, float b, f
     return !(alpha < ALPHA_MIN);
 }
 
+// 1/x for x in the normal range as ONE MUFU.RCP (__fdividef(1.f, x) wraps the same instruction in a denormal / overflow guard of
+// five more; the blend backward only ever inverts 1 - alpha, which lies in [0.01, 1])
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 constexpr int BATCH = BLEND_WARPS == 1 ? 64 : 128;  // records per smem stage (32 one-warp CTAs per SM need <= 7 KB each)
 constexpr int STAGES = 2;
 
@@ -921,28 +929,44 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
                     const float4 r0 = rec[j * (REC / 16)];
                     const float4 r1 = rec[j * (REC / 16) + 1];
                     const float pc = pcut[j];
+                    // Both pixels' powers first (independent chains, one divergent branch for the common "neither pixel is touched"
+                    // case), then the kept pixels.  Same operations in the same order as pair_alpha.
+                    const float dxs = r0.x - pxf;
+                    const float adx = __fmul_rn(r0.z, dxs), bdx = __fmul_rn(r0.w, dxs);
+                    float power[PPT];
+                    bool keep[PPT], any_keep = false;
 #pragma unroll
                     for (int p = 0; p < PPT; p++) {
-                        if (done[p]) continue;
-                        float dx, dy, G, alpha;
-                        if (!pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pc, pxf, pyf[p], dx, dy, G, alpha)) continue;
+                        const float dy = r0.y - pyf[p];
+                        const float s = __fmaf_rn(dxs, adx, __fmul_rn(__fmul_rn(r1.x, dy), dy));
+                        power[p] = __fmaf_rn(s, -0.5f, -__fmul_rn(bdx, dy));
+                        keep[p] = (T[p] > 0.0f) && !(power[p] > 0.0f) && !(power[p] < pc);
+                        any_keep = any_keep || keep[p];
+                    }
+                    if (!any_keep) continue;
+                    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (C == 3) r2 = rec[j * 3 + 2];
+                    const uint32_t pos = (uint32_t)(bi * BATCH + j + 1);
+#pragma unroll
+                    for (int p = 0; p < PPT; p++) {
+                        if (!keep[p]) continue;
+                        const float alpha = min(ALPHA_MAX, r1.y * expf(power[p]));
+                        if (alpha < ALPHA_MIN) continue;
                         const float test_T = T[p] * (1 - alpha);
                         if (test_T < T_EPS) {
-                            done[p] = 1;
+                            T[p] = -T[p];   // finished: the sign is the flag (see the declaration of T)
                             continue;
                         }
+                        Cacc[p][0] += r1.z * alpha * T[p];
                         if (C == 3) {
-                            const float4 r2 = rec[j * 3 + 2];
-                            Cacc[p][0] += r1.z * alpha * T[p];
                             Cacc[p][1 % C] += r1.w * alpha * T[p];
                             Cacc[p][2 % C] += r2.x * alpha * T[p];
                             if (T[p] > 0.5f && test_T < 0.5) D[p] = r2.z;
                         } else {
-                            Cacc[p][0] += r1.z * alpha * T[p];
                             if (T[p] > 0.5f && test_T < 0.5) D[p] = depth_of_slot[__float_as_uint(r1.w) & slot_mask];
                         }
                         T[p] = test_T;
-                        last_contributor[p] = (uint32_t)(bi * BATCH + j + 1);
+                        last_contributor[p] = pos;
                     }
                 }
             }
@@ -964,16 +988,18 @@ blend_fwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
     for (int p = 0; p < PPT; p++) {
         if (!inside[p]) continue;
         const size_t pix = (size_t)(py0 + 4 * p) * W + px;
-        im.final_T[(size_t)v * HW + pix] = T[p];
+        const float Tf = fabsf(T[p]);
+        im.final_T[(size_t)v * HW + pix] = Tf;
         im.n_contrib[(size_t)v * HW + pix] = last_contributor[p];
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) out_color[((size_t)v * C + ch) * HW + pix] = Cacc[p][ch] + T[p] * bg[ch];
+        for (int ch = 0; ch < C; ch++) out_color[((size_t)v * C + ch) * HW + pix] = Cacc[p][ch] + Tf * bg[ch];
         out_depth[(size_t)v * HW + pix] = D[p];
         if (L >= 0) {
             // colour accumulated behind the snapshot position, normalised by the transmittance there: what the
             // reference's back-to-front recursion (backward.cu:488-496) holds in accum_rec when it arrives at L
-            const float inv = 1.f / T_snap[p];
-            snap[(size_t)v * HW + pix] = make_float4(T_snap[p], (Cacc[p][0] - C_snap[p][0]) * inv, (Cacc[p][1 % C] - C_snap[p][1 % C]) * inv,
+            const float Ts = fabsf(T_snap[p]);
+            const float inv = 1.f / Ts;
+            snap[(size_t)v * HW + pix] = make_float4(Ts, (Cacc[p][0] - C_snap[p][0]) * inv, (Cacc[p][1 % C] - C_snap[p][1 % C]) * inv,
                                                      (Cacc[p][2 % C] - C_snap[p][2 % C]) * inv);
         }
     }
@@ -1185,16 +1211,30 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
                 const float4 r0 = rec[j * (REC / 16)];
                 const float4 r1 = rec[j * (REC / 16) + 1];
                 const float pc = pcut[j];
-                float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
+                // both pixels' powers first (independent chains), ONE warp vote for the common "no pixel of the patch is touched"
+                // case, then the exponentials of the pixels that passed -- the operations and their order are pair_alpha's
+                const float dx = r0.x - pxf;
+                const float adx = __fmul_rn(r0.z, dx), bdx = __fmul_rn(r0.w, dx);
+                float dy[PPT], G[PPT], alpha[PPT];
                 bool contrib[PPT], any = false;
 #pragma unroll
                 for (int p = 0; p < PPT; p++) {
-                    dx[p] = dy[p] = G[p] = alpha[p] = 0.f;
-                    contrib[p] = (idx < last_contributor[p]) &&
-                                 pair_alpha(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, pc, pxf, pyf[p], dx[p], dy[p], G[p], alpha[p]);
+                    dy[p] = r0.y - pyf[p];
+                    const float s = __fmaf_rn(dx, adx, __fmul_rn(__fmul_rn(r1.x, dy[p]), dy[p]));
+                    G[p] = __fmaf_rn(s, -0.5f, -__fmul_rn(bdx, dy[p]));   // the power, for now
+                    contrib[p] = (idx < last_contributor[p]) && !(G[p] > 0.0f) && !(G[p] < pc);
                     any = any || contrib[p];
                 }
                 if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+                for (int p = 0; p < PPT; p++) {
+                    alpha[p] = 0.f;
+                    if (contrib[p]) {
+                        G[p] = expf(G[p]);
+                        alpha[p] = min(ALPHA_MAX, r1.y * G[p]);
+                        contrib[p] = !(alpha[p] < ALPHA_MIN);
+                    }
+                }
 
                 float vals[NV];
 #pragma unroll
@@ -1215,7 +1255,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
 #pragma unroll
                     for (int p = 0; p < PPT; p++) {
                         if (!contrib[p]) continue;
-                        T[p] = T[p] * __fdividef(1.f, 1.f - alpha[p]);
+                        T[p] = T[p] * rcp_approx(1.f - alpha[p]);
                         accum_dot[p] = last_alpha[p] * last_dot[p] + (1.f - last_alpha[p]) * accum_dot[p];
                         float cd = 0.f;
 #pragma unroll
@@ -1230,7 +1270,7 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
                     if (!contrib[p]) continue;
                     // one approximate reciprocal (MUFU.RCP, 1-alpha is in [0.01, 1)) replaces the reference's two IEEE
                     // divisions (backward.cu:484,513): ~2 ulp per step, far inside the gradient tolerance
-                    const float inv_1ma = __fdividef(1.f, 1.f - alpha[p]);
+                    const float inv_1ma = rcp_approx(1.f - alpha[p]);
                     T[p] = T[p] * inv_1ma;
                     const float dchannel_dcolor = alpha[p] * T[p];
                     accum_dot[p] = last_alpha[p] * last_dot[p] + (1.f - last_alpha[p]) * accum_dot[p];
@@ -1247,10 +1287,10 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
                     // geometric terms without their constant factors (-0.5 W, -0.5 H, -0.5: applied once per record after
                     // the warp reduction, see `post_scale`): A = dL/dG * G * dx, B = dL/dG * G * dy
                     const float gG = r1.y * dL_dalpha * G[p];
-                    const float A = gG * dx[p], B = gG * dy[p];
+                    const float A = gG * dx, B = gG * dy[p];
                     vals[0] += A * r0.z + B * r0.w;      // -(dG/ddelx) dL/dG
                     vals[1] += B * r1.x + A * r0.w;      // -(dG/ddely) dL/dG
-                    vals[2] += A * dx[p];
+                    vals[2] += A * dx;
                     vals[3] += A * dy[p];
                     vals[4] += B * dy[p];
                     vals[5] += G[p] * dL_dalpha;
