@@ -10,8 +10,8 @@
 //   P5 distance_loss (dense cdist, O(V^2))       FD/utils/loss_utils.py:98-121
 //   simple_knn distCUDA2                          FD/submodules/simple-knn/simple_knn.cu:134-202
 //   torch_scatter.scatter_min                     gm_fluid.py:1088,1272
-// Design: a hashed uniform grid (cell = search radius) built with a counting sort; every term is a *gather* over the
-// 27 neighbouring cells with no materialised edge list and no atomics in the gradient passes (deterministic).
+// Design: a hashed uniform grid (cell = search radius) built with a counting sort; every term is a *gather* over the 27
+// neighbouring cells, walked as 9 x-contiguous bucket rows by 8 lanes per query, with no materialised edge list and no atomics in the gradient passes (deterministic).
 // torch_cluster's `max_num_neighbors` rule ("first K hits in index order") is kept exactly through a per-query
 // index cut-off kth[c] (= K-th smallest neighbour index, INT_MAX when fewer than K+1 neighbours exist):
 //   edge (j -> c) exists  <=>  |x_j - y_c|^2 < r^2  and  j <= kth[c].
@@ -77,14 +77,30 @@ static size_t grid_bytes(int n) {
     return (size_t)((char *)g.cub_temp - (char *)0) + g.cub_temp_bytes + 256;
 }
 
-__device__ __forceinline__ int3 cell_of(float x, float y, float z, float inv_cell) {
-    return make_int3(__float2int_rd(x * inv_cell), __float2int_rd(y * inv_cell), __float2int_rd(z * inv_cell));
+// The table is built on sub-cells of edge cell / SUB (callers pass the search cell, cell >= r); a query visits (2 SUB + 1)^3
+// sub-cells as (2 SUB + 1)^2 x-contiguous rows (walk_neighbors).  SUB = 1: 9 rows of 3 cells, ~33 candidates per row at the
+// reference's lattice spacing.  SUB = 2 (125 sub-cells, 15.6 r^3 of candidates instead of 27 r^3 -- the sphere is 4.2 r^3) was
+// measured and is SLOWER: 25 rows of ~7 candidates leave the 8 lanes of a query group mostly idle and triple the dependent
+// range loads (smoke bench, round 2: SUB = 1 2165 it/s, SUB = 2 1929 it/s; the per-cell walk this replaced: 2072 it/s).
+#ifndef FNX_GRID_SUB
+#define FNX_GRID_SUB 1
+#endif
+constexpr int SUB = FNX_GRID_SUB;
+constexpr int REACH = SUB;                                   // sub-cells visited on each side of the query's
+constexpr int ROW_CELLS = 2 * REACH + 1;                     // x-contiguous buckets of one (dy, dz) row
+constexpr int ROWS = ROW_CELLS * ROW_CELLS;                  // rows per query
+__device__ __forceinline__ float sub_inv(float inv_cell) { return inv_cell * (float)SUB; }   // exact (power of two)
+__device__ __forceinline__ int3 cell_of(float x, float y, float z, float inv_sub) {
+    return make_int3(__float2int_rd(x * inv_sub), __float2int_rd(y * inv_sub), __float2int_rd(z * inv_sub));
 }
-// Cell -> bucket: the table is a periodic A x B x C box of cells (powers of two, each >= 8, A*B*C = M): bucket =
-// (x mod A, y mod B, z mod C).  Unlike a multiplicative hash this makes the 27 cells around any query map to 27
-// DIFFERENT buckets, and a point that shares a bucket with a neighbour cell without being in it lies at least A-1 >= 7
-// cells away along some axis, i.e. farther than the search radius (<= one cell): gathers therefore need no
-// "is this point really in that cell" test and no de-duplication, the distance test does it all.
+// Sub-cell -> bucket: the table is a periodic A x B x C box of sub-cells (powers of two, each >= 8, A*B*C = M): bucket =
+// (x mod A, y mod B, z mod C), x in the low bits.  Unlike a multiplicative hash this makes the (2 REACH + 1)^3 sub-cells around
+// any query map to DIFFERENT buckets (2 REACH + 1 <= 5 <= 8), and a point that shares a bucket with a visited sub-cell without
+// being in it lies at least A - 2 REACH - 1 sub-cells (>= 5 cells at SUB = 1, 1.5 cells at SUB = 2) away along some axis, i.e.
+// farther than the search radius (<= one cell): gathers therefore need no "is this point really in that sub-cell" test and no
+// de-duplication, the distance test does it all.
+// With x in the low bits the ROW_CELLS sub-cells of one (dy, dz) row are CONTIGUOUS buckets (one [start, end) range of the
+// counting sort) unless the row wraps around the period A, when they are two ranges (walk_neighbors).
 __device__ __forceinline__ uint32_t hash_cell(int3 c, int M) {
     const int m = 31 - __clz(M);          // M = 2^m, m >= 10
     const int ax = m / 3, az = m / 3, ay = m - ax - az;
@@ -133,7 +149,7 @@ __global__ void grid_header_kernel(GridHeader *h, int n, int M, float cell, uint
 
 static int grid_build(const float *pts, int n, float cell, void *scratch, cudaStream_t st) {
     GridView g = grid_view(scratch, n);
-    const float inv_cell = 1.0f / cell;
+    const float inv_cell = (1.0f / cell) * (float)SUB;   // of the SUB-cell: the same expression the walkers use (sub_inv)
     FNX_CUDA_TRY(cudaMemsetAsync(g.bucket_fill, 0, sizeof(uint32_t) * (size_t)g.M, st));
     if (n > 0) {
         grid_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, inv_cell, g.M, g.bucket_fill, g.hdr, cell, g.bucket_start);
@@ -157,53 +173,74 @@ static int grid_build(const float *pts, int n, float cell, void *scratch, cudaSt
     return FNX_OK;
 }
 
-// Visit every grid point within sqrt(r2) of q.  f(j, pj, d2).  Requires cell >= r (see hash_cell for why the distance
-// test alone is exact).
-template <typename F>
-__device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, F f) {
-    const int3 c = cell_of(q.x, q.y, q.z, inv_cell);
+// Visit every grid point within sqrt(r2) of q: f(j, pj, d2, a) with a = the point's position in the bucket-sorted arrays.
+// Requires cell >= r (see hash_cell for why the distance test alone is exact).  LANES consecutive lanes share ONE query and
+// stride together over each row's contiguous candidates (coalesced float4 loads, no lane idles while another walks a fuller
+// bucket); the next row's ranges are fetched before the current row is walked.  Callers reduce their per-lane partials with
+// group_sum().  LANES = 1: one thread per query.
+template <int LANES, typename F>
+__device__ __forceinline__ void walk_neighbors(const GridView &g, float inv_cell, float3 q, float r2, int lane, F f) {
+    const int3 c = cell_of(q.x, q.y, q.z, sub_inv(inv_cell));
+    const int m = 31 - __clz(g.M);   // bucket = x | y << ax | z << (ax + ay), see hash_cell
+    const int ax = m / 3, ay = m - 2 * ax;
+    const uint32_t my = (1u << ay) - 1u, mz = (1u << ax) - 1u;
+    const int A = 1 << ax;
+    // the row's x-extent: sub-cells x0 .. x0 + len1 - 1 and, when it wraps around the period, 0 .. ROW_CELLS - len1 - 1
+    const int x0 = (c.x - REACH) & (A - 1);
+    const int len1 = min(ROW_CELLS, A - x0);
+    const uint32_t *__restrict__ bs = g.bucket_start;
+    // bucket ranges of row (dy, dz): [x, y) and, for a wrapped row, [z, w)   (bs[base + A] is the next row's first entry, bs[M] = n)
+    auto ranges = [&](int dy, int dz) {
+        const uint32_t base = (((uint32_t)(c.y + dy) & my) << ax) | (((uint32_t)(c.z + dz) & mz) << (ax + ay));
+        uint4 r;
+        r.x = __ldg(bs + base + x0);
+        r.y = __ldg(bs + base + x0 + len1);
+        r.z = r.w = 0u;
+        if (len1 < ROW_CELLS) {
+            r.z = __ldg(bs + base);
+            r.w = __ldg(bs + base + (ROW_CELLS - len1));
+        }
+        return r;
+    };
+    int dy = -REACH, dz = -REACH;
+    uint4 next = ranges(dy, dz);
 #pragma unroll 1
-    for (int dz = -1; dz <= 1; dz++)
+    for (int row = 0; row < ROWS; row++) {
+        const uint4 cur = next;
+        if (++dy > REACH) { dy = -REACH; dz++; }
+        if (row + 1 < ROWS) next = ranges(dy, dz);
 #pragma unroll 1
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll 1
-            for (int dx = -1; dx <= 1; dx++) {
-                const uint32_t b = hash_cell(make_int3(c.x + dx, c.y + dy, c.z + dz), g.M);
-                const uint32_t s = g.bucket_start[b], e = g.bucket_start[b + 1];
-                for (uint32_t a = s; a < e; a++) {
-                    const float4 p = g.sorted_pos[a];
-                    const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-                    const float d2 = ex * ex + ey * ey + ez * ez;
-                    if (d2 < r2) f((int)__float_as_uint(p.w), p, d2);
-                }
+        for (int seg = 0; seg < 2; seg++) {
+            const uint32_t s = seg == 0 ? cur.x : cur.z, e = seg == 0 ? cur.y : cur.w;
+            for (uint32_t a = s + lane; a < e; a += LANES) {
+                const float4 p = __ldg(g.sorted_pos + a);
+                const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+                const float d2 = ex * ex + ey * ey + ez * ez;
+                if (d2 < r2) f((int)__float_as_uint(p.w), p, d2, a);
             }
-}
-
-// Group-cooperative variant: GROUP = 8 consecutive lanes share ONE query; lane l walks neighbour cells l, l+8, l+16
-// (and l+24 < 27).  Callers reduce their per-lane partials with group_sum().  One thread per query is latency bound
-// (28k queries x 27 dependent bucket walks); a whole warp per query leaves 2/3 of the lanes idle (27 cells of ~11
-// points with very uneven fill: the first profile of density_bwd showed 10 of 32 lanes active per instruction and the
-// kernel issue bound); 8 lanes x 3-4 cells evens the fill out and still gives 16 independent queries per 128 threads.
-constexpr int GROUP = 8;
-constexpr int QPB = 128 / GROUP;  // queries per 128-thread block
-template <typename F>
-__device__ __forceinline__ void warp_for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, int lane, F f) {
-    const int3 c = cell_of(q.x, q.y, q.z, inv_cell);
-#pragma unroll 1
-    for (int ci = lane; ci < 27; ci += GROUP) {
-        const uint32_t b = hash_cell(make_int3(c.x + (ci % 3) - 1, c.y + ((ci / 3) % 3) - 1, c.z + (ci / 9) - 1), g.M);
-        const uint32_t s = g.bucket_start[b], e = g.bucket_start[b + 1];
-        for (uint32_t a = s; a < e; a++) {
-            const float4 p = g.sorted_pos[a];
-            const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
-            const float d2 = ex * ex + ey * ey + ez * ez;
-            if (d2 < r2) f((int)__float_as_uint(p.w), p, d2, a);
         }
     }
 }
+template <typename F>
+__device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, F f) {
+    walk_neighbors<1>(g, inv_cell, q, r2, 0, [&](int j, const float4 &p, float d2, uint32_t) { f(j, p, d2); });
+}
+
+// Group-cooperative variant: GROUP = 8 consecutive lanes share ONE query.  One thread per query is latency bound (28k queries x
+// 9 dependent range walks of ~33 candidates); a whole warp per query leaves half of the lanes idle on a row and gives only 4
+// independent queries per 128 threads; 8 lanes walk a row in 4-5 trips and give 16.
+#ifndef FNX_GROUP
+#define FNX_GROUP 8
+#endif
+constexpr int GROUP = FNX_GROUP;
+constexpr int QPB = 128 / GROUP;  // queries per 128-thread block
+template <typename F>
+__device__ __forceinline__ void warp_for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, int lane, F f) {
+    walk_neighbors<GROUP>(g, inv_cell, q, r2, lane, f);
+}
 // sums over the 8 lanes of a query group (xor shuffles stay inside an aligned group; only the group's lanes are named
 // in the mask, so groups of one warp may diverge)
-__device__ __forceinline__ unsigned group_mask() { return 0xFFu << ((threadIdx.x & 31) & ~(GROUP - 1)); }
+__device__ __forceinline__ unsigned group_mask() { return ((1u << GROUP) - 1u) << ((threadIdx.x & 31) & ~(GROUP - 1)); }
 __device__ __forceinline__ float group_sum(float v) {
     const unsigned m = group_mask();
 #pragma unroll
@@ -732,7 +769,7 @@ __global__ void advect_pack_vel_kernel(GridView gh, int N, const float *__restri
 __global__ void __launch_bounds__(128)
 pair_distance_kernel(GridView g, float inv_cell, const float *__restrict__ pts, int n, float thr, float grad_scale,
                      float *__restrict__ loss_out, float *__restrict__ dL_dp) {
-    // 8 lanes per point (the grid is sparse at cell = threshold: 27 mostly empty buckets per query are pure latency for
+    // 8 lanes per point (the grid is sparse at cell = threshold: 25 mostly empty rows per query are pure latency for
     // one thread); out-of-range groups keep running with no work so that the warp-wide loss reduction stays convergent
     const int i = blockIdx.x * QPB + (threadIdx.x / GROUP);
     const int lane = threadIdx.x % GROUP;
@@ -772,7 +809,8 @@ __global__ void __launch_bounds__(128)
 knn3_kernel(GridView g, float cell, const float *__restrict__ pts, int n, int max_ring, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float inv_cell = 1.0f / cell;
+    const float inv_cell = sub_inv(1.0f / cell);   // the table's sub-cells (grid_build)
+    cell /= (float)SUB;
     const float3 q = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
     const int3 c = cell_of(q.x, q.y, q.z, inv_cell);
     float best[3] = {3.4e38f, 3.4e38f, 3.4e38f};
@@ -1241,7 +1279,7 @@ int fnx_knn3_mean_dist2(const void *grid, const float *pts, int32_t n, float cel
     FNX_REQUIRE(grid && mean_dist2 && (pts || n == 0) && cell > 0.f, "bad arguments");
     if (n == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, n);
-    knn3_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, cell, pts, n, 24, mean_dist2);
+    knn3_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, cell, pts, n, 24 * SUB, mean_dist2);
     FNX_LAUNCH_CHECK("knn3_kernel");
     return FNX_OK;
 }
