@@ -804,9 +804,11 @@ __device__ __forceinline__ uint32_t work_unit(const uint32_t *__restrict__ tile_
 // Minimum resident CTAs per SM the forward is compiled for (register cap).  Round 1 (whole bench, it/s): unconstrained
 // (77 registers, 6 CTAs/SM) 1454, 10 (48 registers) 1511, 12 (40 registers, 84 B of spills) 1512.  Round 2, with the accurate expf
 // on kept pairs (more live registers): 10 (48 registers, 44 B of spills) 2016 it/s, forward 3.60 ms per 16-frame step, one frame
-// alone 0.683 ms; 9 (56 registers, 12 B) 2020 / 3.41 / 0.665; 8 (64 registers) 2003 / 3.31 / 0.660.
+// alone 0.683 ms; 9 (56 registers, 12 B) 2020 / 3.41 / 0.665; 8 (64 registers) 2003 / 3.31 / 0.660.  With the restructured pair
+// loop (both pixels' powers ahead of one branch): 9 (56 registers, 28 B of spills) 2215 it/s, 0.200 ms per launch, one frame alone
+// 0.636 ms; 8 (64 registers, no spills) 2225 / 0.186 / 0.621.
 #ifndef FNX_FWD_MIN_CTAS
-#define FNX_FWD_MIN_CTAS 9
+#define FNX_FWD_MIN_CTAS 8
 #endif
 template <int C>
 __global__ void __launch_bounds__(BLEND_THREADS, FNX_FWD_MIN_CTAS)
