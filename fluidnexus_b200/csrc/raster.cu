@@ -742,7 +742,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-constexpr int BATCH = BLEND_WARPS == 1 ? 64 : 128;  // records per smem stage (32 one-warp CTAs per SM need <= 7 KB each)
+#ifndef FNX_BLEND_BATCH
+#define FNX_BLEND_BATCH 128
+#endif
+constexpr int BATCH = BLEND_WARPS == 1 ? 64 : FNX_BLEND_BATCH;  // records per smem stage (32 one-warp CTAs per SM need <= 7 KB each)
 constexpr int STAGES = 2;
 
 // ---------------------------------------------------------------------------------------------------------------
