@@ -1697,11 +1697,70 @@ static int validate(const fnx_raster_args *a) {
 constexpr int SORT_CAP = 2048;  // keys sorted in shared memory; larger buckets take the rank-sort path through bkeys2
 constexpr int STATIC_DEPTH_SMEM = 2048;  // static depths staged per tile by merge_bucket_kernel
 
-// Sorts the nf keys bkeys[base, base+nf) of one tile (whole CTA participates; ends with a barrier).  Up to `cap` keys:
-// bitonic network in the shared array s_key (cap entries); more: rank sort (keys are unique) into bkeys2.  Returns
-// where the sorted keys are.
+// Bitonic sort of up to 256 * E keys held E per thread by a 256-thread CTA; the key with index e * 256 + tid lives in v[e] of
+// thread tid.  Partners at distance j < 32 are exchanged by warp shuffles, at 32 <= j < 256 through shared memory, at j >= 256 inside
+// the thread's own registers: of the 36 (E = 1) .. 66 (E = 8) stages of the network only 6 .. 15 need the CTA barrier that EVERY stage
+// of a network over a shared array needs.  n2 = padded size (power of two >= the key count; the padding keys are ~0): the stages
+// beyond it would only order padding.  The keys end up ascending in s_key[0, 256 * E); ends with a barrier.
+template <int E>
+__device__ __forceinline__ void sort_bucket_regs(unsigned long long *s_key, const unsigned long long *__restrict__ bkeys, size_t base, int nf,
+                                                 int n2) {
+    constexpr int N = 256 * E;
+    const int tid = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) v[e] = (e * 256 + tid) < nf ? bkeys[base + e * 256 + tid] : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+        if (k > n2) continue;   // (uniform over the CTA; not a break: the loops must unroll so that v[] stays in registers)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 256) {
+                const int je = j / 256;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if (e & je) continue;
+                    const bool up = (((e * 256) | tid) & k) == 0;
+                    const unsigned long long a = v[e], b = v[e | je];
+                    const bool sw = (a > b) == up;
+                    v[e] = sw ? b : a;
+                    v[e | je] = sw ? a : b;
+                }
+            } else {
+                if (j >= 32) {
+#pragma unroll
+                    for (int e = 0; e < E; e++) s_key[e * 256 + tid] = v[e];
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const unsigned long long other = j >= 32 ? s_key[e * 256 + (tid ^ j)] : __shfl_xor_sync(0xffffffffu, v[e], j);
+                    const bool up = (((e * 256) | tid) & k) == 0, lower = (tid & j) == 0;
+                    v[e] = (lower == up) ? min(v[e], other) : max(v[e], other);
+                }
+                if (j >= 32) __syncthreads();
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) s_key[e * 256 + tid] = v[e];
+    __syncthreads();
+}
+
+// Sorts the nf keys bkeys[base, base+nf) of one tile (whole CTA participates; ends with a barrier).  Up to 2048 keys (and a CTA of
+// 256 threads): register / shuffle bitonic network (sort_bucket_regs); up to `cap` keys: bitonic network in the shared array s_key
+// (cap entries); more: rank sort (keys are unique) into bkeys2.  Returns where the sorted keys are.
 __device__ __forceinline__ const unsigned long long *sort_bucket(unsigned long long *s_key, int cap, const unsigned long long *__restrict__ bkeys,
                                                                  unsigned long long *__restrict__ bkeys2, size_t base, int nf) {
+    if (nf <= 2048 && cap >= 2048 && blockDim.x == 256) {
+        int n2 = 2;
+        while (n2 < nf) n2 <<= 1;
+        if (nf <= 256) sort_bucket_regs<1>(s_key, bkeys, base, nf, n2);
+        else if (nf <= 512) sort_bucket_regs<2>(s_key, bkeys, base, nf, n2);
+        else if (nf <= 1024) sort_bucket_regs<4>(s_key, bkeys, base, nf, n2);
+        else sort_bucket_regs<8>(s_key, bkeys, base, nf, n2);
+        return s_key;
+    }
     if (nf <= cap) {
         int n2 = 2;
         while (n2 < nf) n2 <<= 1;
