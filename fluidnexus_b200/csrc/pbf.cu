@@ -234,23 +234,35 @@ __device__ __forceinline__ void for_each_neighbor(const GridView &g, float inv_c
 #endif
 constexpr int GROUP = FNX_GROUP;
 constexpr int QPB = 128 / GROUP;  // queries per 128-thread block
-template <typename F>
+// The density kernels (P2 / P3) run on the step's side stream, off the critical path of an iteration: they use groups of 4 lanes --
+// fewer idle lanes on a row's last trip (33 candidates: 9 trips of 4 against 5 trips of 8), i.e. fewer instructions for the same
+// work, at the price of a longer dependent chain per query.  Measured with ALL gathers at 4 lanes (smoke / scalar): throughput
+// +2.2 % / +1.1 %, one frame alone -2 % / -6 % (the advection gathers sit on the critical path): so 8 lanes there, 4 here.
+#ifndef FNX_GROUP_SIDE
+#define FNX_GROUP_SIDE 4
+#endif
+constexpr int GROUP_SIDE = FNX_GROUP_SIDE;
+constexpr int QPB_SIDE = 128 / GROUP_SIDE;
+template <int G = GROUP, typename F>
 __device__ __forceinline__ void warp_for_each_neighbor(const GridView &g, float inv_cell, float3 q, float r2, int lane, F f) {
-    walk_neighbors<GROUP>(g, inv_cell, q, r2, lane, f);
+    walk_neighbors<G>(g, inv_cell, q, r2, lane, f);
 }
-// sums over the 8 lanes of a query group (xor shuffles stay inside an aligned group; only the group's lanes are named
+// sums over the G lanes of a query group (xor shuffles stay inside an aligned group; only the group's lanes are named
 // in the mask, so groups of one warp may diverge)
-__device__ __forceinline__ unsigned group_mask() { return ((1u << GROUP) - 1u) << ((threadIdx.x & 31) & ~(GROUP - 1)); }
+template <int G = GROUP>
+__device__ __forceinline__ unsigned group_mask() { return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)); }
+template <int G = GROUP>
 __device__ __forceinline__ float group_sum(float v) {
-    const unsigned m = group_mask();
+    const unsigned m = group_mask<G>();
 #pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
     return v;
 }
+template <int G = GROUP>
 __device__ __forceinline__ int group_sum(int v) {
-    const unsigned m = group_mask();
+    const unsigned m = group_mask<G>();
 #pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
     return v;
 }
 
@@ -259,13 +271,14 @@ __device__ __forceinline__ int group_sum(int v) {
 // ---------------------------------------------------------------------------------------------------------------
 // K-th smallest neighbour index of query q by bisection on the index value (rare path: only when more than K points
 // lie within the radius).  Warp-cooperative; every lane returns the same value.
+template <int G = GROUP>
 __device__ __forceinline__ int kth_by_bisection(const GridView &g, float inv_cell, float3 q, float r2, int lane, int K, int n_x) {
     int lo = 0, hi = n_x - 1;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         int below = 0;
-        warp_for_each_neighbor(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float, uint32_t) { below += (j <= mid); });
-        below = group_sum(below);
+        warp_for_each_neighbor<G>(g, inv_cell, q, r2, lane, [&](int j, const float4 &, float, uint32_t) { below += (j <= mid); });
+        below = group_sum<G>(below);
         if (below >= K) hi = mid; else lo = mid + 1;
     }
     return lo;
@@ -338,15 +351,15 @@ __device__ __forceinline__ float dpoly6_dd2(float d2, float H2, float term1) {
 __global__ void __launch_bounds__(128)
 density_fwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio) {
-    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
-    const int lane = threadIdx.x % GROUP;
+    const int r = blockIdx.x * QPB_SIDE + (threadIdx.x / GROUP_SIDE);
+    const int lane = threadIdx.x % GROUP_SIDE;
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
+    warp_for_each_neighbor<GROUP_SIDE>(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
         if (r <= kth[c]) pi += poly6(d2, H2, term1);
     });
-    pi = group_sum(pi);
+    pi = group_sum<GROUP_SIDE>(pi);
     if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
 }
 
@@ -358,21 +371,21 @@ __global__ void __launch_bounds__(128)
 density_fwd_counted_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass, int K,
                            float H2, float term1, float p0, int *__restrict__ kth, float *__restrict__ p_ratio,
                            int *__restrict__ cap_flag) {
-    const int r = blockIdx.x * QPB + (threadIdx.x / GROUP);
-    const int lane = threadIdx.x % GROUP;
+    const int r = blockIdx.x * QPB_SIDE + (threadIdx.x / GROUP_SIDE);
+    const int lane = threadIdx.x % GROUP_SIDE;
     if (r >= N) return;
     const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
     float pi = 0.f;
     int cnt = 0;
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int, const float4 &, float d2, uint32_t) {
+    warp_for_each_neighbor<GROUP_SIDE>(g, inv_cell, q, H2, lane, [&](int, const float4 &, float d2, uint32_t) {
         cnt++;
         pi += poly6(d2, H2, term1);
     });
-    pi = group_sum(pi);
-    cnt = group_sum(cnt);
+    pi = group_sum<GROUP_SIDE>(pi);
+    cnt = group_sum<GROUP_SIDE>(cnt);
     int cut = 0x7fffffff;
     if (cnt > K) {
-        cut = kth_by_bisection(g, inv_cell, q, H2, lane, K, N);
+        cut = kth_by_bisection<GROUP_SIDE>(g, inv_cell, q, H2, lane, K, N);
         if (lane == 0) *cap_flag = 1;
     }
     if (lane == 0) {
@@ -385,14 +398,14 @@ density_fwd_if_capped_kernel(GridView g, float inv_cell, const float *__restrict
                              const int *__restrict__ kth, float H2, float term1, float p0, float *__restrict__ p_ratio,
                              const int *__restrict__ cap_flag) {
     if (*cap_flag == 0) return;  // the normal case: a small fixed grid returns at once
-    const int lane = threadIdx.x % GROUP;
-    for (int r = blockIdx.x * QPB + (threadIdx.x / GROUP); r < N; r += gridDim.x * QPB) {  // (r is uniform over a query group)
+    const int lane = threadIdx.x % GROUP_SIDE;
+    for (int r = blockIdx.x * QPB_SIDE + (threadIdx.x / GROUP_SIDE); r < N; r += gridDim.x * QPB_SIDE) {  // (r is uniform over a query group)
         const float3 q = make_float3(X[3 * r], X[3 * r + 1], X[3 * r + 2]);
         float pi = 0.f;
-        warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
+        warp_for_each_neighbor<GROUP_SIDE>(g, inv_cell, q, H2, lane, [&](int c, const float4 &, float d2, uint32_t) {
             if (r <= kth[c]) pi += poly6(d2, H2, term1);
         });
-        pi = group_sum(pi);
+        pi = group_sum<GROUP_SIDE>(pi);
         if (lane == 0) p_ratio[r] = pi / imass[r] / p0;
     }
 }
@@ -430,14 +443,14 @@ __global__ void __launch_bounds__(128)
 density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int N, const float *__restrict__ imass,
                    const int *__restrict__ kth, float H2, float term1, float p0, const float *__restrict__ dL_dpratio,
                    float *__restrict__ dL_dX, int accumulate) {
-    const int k = blockIdx.x * QPB + (threadIdx.x / GROUP);
-    const int lane = threadIdx.x % GROUP;
+    const int k = blockIdx.x * QPB_SIDE + (threadIdx.x / GROUP_SIDE);
+    const int lane = threadIdx.x % GROUP_SIDE;
     if (k >= N) return;
     const float3 q = make_float3(X[3 * k], X[3 * k + 1], X[3 * k + 2]);
     const float gpk = dL_dpratio[k] / imass[k] / p0;
     const int kth_k = kth[k];
     float3 acc = make_float3(0.f, 0.f, 0.f);
-    warp_for_each_neighbor(g, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2, uint32_t a) {
+    warp_for_each_neighbor<GROUP_SIDE>(g, inv_cell, q, H2, lane, [&](int j, const float4 &pj, float d2, uint32_t a) {
         const float4 pay = g.aux1[a];  // { gp_j, kth_j }
         float w = 0.f;
         if (k <= __float_as_int(pay.y)) w += gpk;
@@ -445,7 +458,7 @@ density_bwd_kernel(GridView g, float inv_cell, const float *__restrict__ X, int 
         const float s = 2.f * dpoly6_dd2(d2, H2, term1) * w;
         acc.x += s * (q.x - pj.x); acc.y += s * (q.y - pj.y); acc.z += s * (q.z - pj.z);
     });
-    acc.x = group_sum(acc.x); acc.y = group_sum(acc.y); acc.z = group_sum(acc.z);
+    acc.x = group_sum<GROUP_SIDE>(acc.x); acc.y = group_sum<GROUP_SIDE>(acc.y); acc.z = group_sum<GROUP_SIDE>(acc.z);
     if (lane < 3) {
         const float v = lane == 0 ? acc.x : (lane == 1 ? acc.y : acc.z);
         if (accumulate) dL_dX[3 * k + lane] += v; else dL_dX[3 * k + lane] = v;
@@ -1044,7 +1057,7 @@ int fnx_pbf_density_fwd(const void *grid, const float *X, int32_t N, const float
     if (N == 0) return FNX_OK;
     GridView g = grid_view((void *)grid, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
-    density_fwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, p_ratio);
+    density_fwd_kernel<<<(N + QPB_SIDE - 1) / QPB_SIDE, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, p_ratio);
     FNX_LAUNCH_CHECK("density_fwd_kernel");
     return FNX_OK;
 }
@@ -1058,10 +1071,10 @@ int fnx_pbf_density_fwd_counted(const void *grid, const float *X, int32_t N, con
     GridView g = grid_view((void *)grid, N);
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
     FNX_CUDA_TRY(cudaMemsetAsync(cap_flag, 0, sizeof(int32_t), st));
-    density_fwd_counted_kernel<<<(N + QPB - 1) / QPB, 128, 0, st>>>(g, 1.0f / H, X, N, imass, max_num_neighbors, H * H, term1, p0, kth_out,
+    density_fwd_counted_kernel<<<(N + QPB_SIDE - 1) / QPB_SIDE, 128, 0, st>>>(g, 1.0f / H, X, N, imass, max_num_neighbors, H * H, term1, p0, kth_out,
                                                                     p_ratio, cap_flag);
     FNX_LAUNCH_CHECK("density_fwd_counted_kernel");
-    density_fwd_if_capped_kernel<<<min((N + QPB - 1) / QPB, 148 * 8), 128, 0, st>>>(g, 1.0f / H, X, N, imass, kth_out, H * H, term1, p0, p_ratio, cap_flag);
+    density_fwd_if_capped_kernel<<<min((N + QPB_SIDE - 1) / QPB_SIDE, 148 * 8), 128, 0, st>>>(g, 1.0f / H, X, N, imass, kth_out, H * H, term1, p0, p_ratio, cap_flag);
     FNX_LAUNCH_CHECK("density_fwd_if_capped_kernel");
     return FNX_OK;
 }
@@ -1075,7 +1088,7 @@ int fnx_pbf_density_bwd(const void *grid, const float *X, int32_t N, const float
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
     density_bwd_pack_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, imass, kth, p0, dL_dpratio);
     FNX_LAUNCH_CHECK("density_bwd_pack_kernel");
-    density_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
+    density_bwd_kernel<<<(N + QPB_SIDE - 1) / QPB_SIDE, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("density_bwd_kernel");
     return FNX_OK;
 }
@@ -1091,7 +1104,7 @@ int fnx_pbf_density_bwd_ratio(const void *grid, const float *X, int32_t N, const
     const float term1 = (float)(315.0 / (64.0 * 3.14159265358979323846 * pow((double)H, 9)));
     density_bwd_pack_ratio_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, N, imass, kth, p0, p_ratio, weight, dL_dpratio, loss);
     FNX_LAUNCH_CHECK("density_bwd_pack_ratio_kernel");
-    density_bwd_kernel<<<(N + QPB - 1) / QPB, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
+    density_bwd_kernel<<<(N + QPB_SIDE - 1) / QPB_SIDE, 128, 0, (cudaStream_t)stream>>>(g, 1.0f / H, X, N, imass, kth, H * H, term1, p0, dL_dpratio, dL_dX, accumulate);
     FNX_LAUNCH_CHECK("density_bwd_kernel");
     return FNX_OK;
 }

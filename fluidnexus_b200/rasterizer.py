@@ -12,6 +12,7 @@ Everything runs on torch's *current* stream and the tensors' device (the referen
 default stream, rasterizer_impl.cu:137,272,296 -- that breaks multi-GPU ranks and stream capture).
 """
 import ctypes as C
+import os
 from typing import NamedTuple
 
 import torch
@@ -60,10 +61,10 @@ class RasterContext:
 
 # General (single-stream) path: bin by per-tile buckets sorted in shared memory (FNX_BUCKET_BINNING) instead of two global
 # radix sorts.  Results are identical.  Measured on B200: a win for small sets spread over many tiles (it is always used for
-# the dynamic set of MergedRasterWorkspace), a small loss for dense all-dynamic plumes (scalar workload 581 -> 534 it/s, c2
-# 1259 -> 1243: 1600+ instances per tile contend on the tile's histogram / cursor atomics and make long bitonic sorts), so
-# it is off by default here.
-BUCKET_BINNING = False
+# the dynamic set of MergedRasterWorkspace), a loss for dense all-dynamic plumes (1600+ instances per tile contend on the tile's
+# histogram / cursor atomics and make long sorts: scalar workload 673 -> 610 it/s, c2 1473 -> 1446 it/s -- though one c2 frame alone
+# runs 1.013 -> 0.975 ms -- measured again in round 2 with the register / shuffle bucket sort), so it is off by default here.
+BUCKET_BINNING = os.environ.get("FNX_BUCKET_BINNING", "0") == "1"   # (the environment variable is a measurement switch)
 
 # running estimate of the instance count per (device, C, V, W, H): lets the forward size its binning buffers
 # without blocking on the device-side count (see FNX_NO_HOST_SYNC / instance_capacity_hint in include/fnx.h)
