@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "geom_grad.cuh"
 #include "raster.cuh"
 
 namespace fnx {
@@ -1308,8 +1309,9 @@ blend_bwd_kernel(int W, int H, int gx, int gy, bool use_mask, const uint32_t *__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K9: per-Gaussian backward, fusing computeCov2DCUDA (backward.cu:137-263), preprocessCUDA (:332-381) and
-// computeCov3D (:267-327), summed over the V views.
+// K9: per-Gaussian backward: what computeCov2DCUDA (backward.cu:137-263), preprocessCUDA's backward (:332-381) and
+// computeCov3D's backward (:267-327) compute, in one pass over the V views.  The chain rule itself lives in geom_grad.cuh
+// (matrix form, host-compilable: tests/test_geom_grad_host.py runs it on the CPU against the oracle).
 // ---------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256)
@@ -1340,16 +1342,18 @@ geom_bwd_kernel(int P, int V, const float *__restrict__ means3D, const float3 *_
         }
         return;
     }
-    const float3 mean = make_float3(means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    namespace gg = geomgrad;
+    const float mean[3] = {means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]};
     const float *cov3D = (cov3D_precomp != nullptr ? cov3D_precomp : cov3D_geom) + 6 * (size_t)i;
     float c6[6];
     bool any_visible = false;
     for (int v = 0; v < V; v++) any_visible |= radii[(size_t)v * P + i] > 0;
 #pragma unroll
     for (int k = 0; k < 6; k++) c6[k] = any_visible ? cov3D[k] : 0.f;
-    const M3 Vrk = vrk_of(c6);
+    float Sig[3][3];
+    gg::sym3_from6(c6, Sig);
 
-    float3 d_mean = make_float3(0.f, 0.f, 0.f);
+    float d_mean[3] = {0.f, 0.f, 0.f};
     float d_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float d_op = 0.f, d_col[C];
 #pragma unroll
@@ -1358,12 +1362,11 @@ geom_bwd_kernel(int P, int V, const float *__restrict__ means3D, const float3 *_
     for (int v = 0; v < V; v++) {
         const size_t slot = (size_t)v * P + i;
         const float *row = accum + slot * ACC;
-        const float4 a0 = *reinterpret_cast<const float4 *>(row);
-        const float4 a1 = *reinterpret_cast<const float4 *>(row + 4);
-        const float g2x = a0.x, g2y = a0.y;
+        const float4 a0 = *reinterpret_cast<const float4 *>(row);   // {dmean2D.x, dmean2D.y, dconic.xx, dconic.xy}
+        const float4 a1 = *reinterpret_cast<const float4 *>(row + 4);   // {dconic.yy, dopacity, dcol0, dcol1}
         if (out.dL_dmeans2D) {
-            out.dL_dmeans2D[3 * slot] = g2x;
-            out.dL_dmeans2D[3 * slot + 1] = g2y;
+            out.dL_dmeans2D[3 * slot] = a0.x;
+            out.dL_dmeans2D[3 * slot + 1] = a0.y;
             out.dL_dmeans2D[3 * slot + 2] = 0.f;
         }
         d_op += a1.y;
@@ -1373,65 +1376,17 @@ geom_bwd_kernel(int P, int V, const float *__restrict__ means3D, const float3 *_
             d_col[2 % C] += row[8];
         }
         if (!(radii[slot] > 0)) continue;
-        const float *Vm = view_matrix + 16 * v;
-        const float *Pm = proj_matrix + 16 * v;
-        const float3 dL_dconic = make_float3(a0.z, a0.w, a1.x);
-
-        // ---- cov2D backward ----
-        ProjJac pj = proj_jacobian(mean, focal_x, focal_y, tan_fov_x, tan_fov_y, Vm);
-        const float limx = 1.3f * tan_fov_x, limy = 1.3f * tan_fov_y;
-        const float x_grad_mul = pj.txtz < -limx || pj.txtz > limx ? 0 : 1;
-        const float y_grad_mul = pj.tytz < -limy || pj.tytz > limy ? 0 : 1;
-        const M3 &T = pj.T;
-        const M3 &Wm = pj.W;
-        M3 cov2D = m3_mul(m3_mul(m3_T(T), m3_T(Vrk)), T);
-        const float a = cov2D.m[0][0] + 0.3f, b = cov2D.m[0][1], c = cov2D.m[1][1] + 0.3f;
-        const float denom = a * c - b * b;
-        float dL_da = 0, dL_db = 0, dL_dc = 0;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-        if (denom2inv != 0) {
-            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
-            dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
-            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
-            d_cov[0] += (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
-            d_cov[3] += (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
-            d_cov[5] += (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
-            d_cov[1] += 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
-            d_cov[2] += 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
-            d_cov[4] += 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
-        }
-        const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da + (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
-        const float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da + (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
-        const float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da + (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
-        const float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc + (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
-        const float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc + (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
-        const float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc + (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
-        const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
-        const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
-        const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
-        const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
-        const float tz = 1.f / pj.t.z, tz2 = tz * tz, tz3 = tz2 * tz;
-        const float dL_dtx = x_grad_mul * -focal_x * tz2 * dL_dJ02;
-        const float dL_dty = y_grad_mul * -focal_y * tz2 * dL_dJ12;
-        const float dL_dtz = -focal_x * tz2 * dL_dJ00 - focal_y * tz2 * dL_dJ11 + (2 * focal_x * pj.t.x) * tz3 * dL_dJ02 + (2 * focal_y * pj.t.y) * tz3 * dL_dJ12;
-        // transformVec4x3Transpose (auxiliary.h:79-86)
-        float3 dm = make_float3(Vm[0] * dL_dtx + Vm[1] * dL_dty + Vm[2] * dL_dtz, Vm[4] * dL_dtx + Vm[5] * dL_dty + Vm[6] * dL_dtz,
-                                Vm[8] * dL_dtx + Vm[9] * dL_dty + Vm[10] * dL_dtz);
-        // ---- projection backward (backward.cu:357-372) ----
-        const float4 m_hom = xform4x4(mean, Pm);
-        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-        const float mul1 = (Pm[0] * mean.x + Pm[4] * mean.y + Pm[8] * mean.z + Pm[12]) * m_w * m_w;
-        const float mul2 = (Pm[1] * mean.x + Pm[5] * mean.y + Pm[9] * mean.z + Pm[13]) * m_w * m_w;
-        float3 dm2;
-        dm2.x = (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
-        dm2.y = (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
-        dm2.z = (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
-        dm.x += dm2.x; dm.y += dm2.y; dm.z += dm2.z;
-        d_mean.x += dm.x; d_mean.y += dm.y; d_mean.z += dm.z;
+        // screen covariance -> 3-D covariance and, through A = J R, the mean; screen mean -> mean (geom_grad.cuh)
+        float A[2][3], t[3], dA[2][3];
+        bool x_free, y_free;
+        gg::view_jacobian(mean, view_matrix + 16 * v, focal_x, focal_y, tan_fov_x, tan_fov_y, A, t, x_free, y_free);
+        gg::screen_cov_backward(A, Sig, a0.z, a0.w, a1.x, d_cov, dA);
+        gg::perspective_backward(dA, view_matrix + 16 * v, t, focal_x, focal_y, x_free, y_free, d_mean);
+        gg::ndc_backward(proj_matrix + 16 * v, mean, a0.x, a0.y, d_mean);
     }
 
     if (out.dL_dmeans3D) {
-        out.dL_dmeans3D[3 * i] = d_mean.x; out.dL_dmeans3D[3 * i + 1] = d_mean.y; out.dL_dmeans3D[3 * i + 2] = d_mean.z;
+        out.dL_dmeans3D[3 * i] = d_mean[0]; out.dL_dmeans3D[3 * i + 1] = d_mean[1]; out.dL_dmeans3D[3 * i + 2] = d_mean[2];
     }
     if (out.dL_dopacity) out.dL_dopacity[i] = d_op;
     if (out.dL_dcolors) {
@@ -1443,46 +1398,18 @@ geom_bwd_kernel(int P, int V, const float *__restrict__ means3D, const float3 *_
         for (int k = 0; k < 6; k++) out.dL_dcov3D[6 * (size_t)i + k] = d_cov[k];
     }
     if (scales != nullptr && (out.dL_dscales || out.dL_drotations)) {
-        float3 ds = make_float3(0.f, 0.f, 0.f);
-        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
         if (any_visible) {
-            // computeCov3D backward (backward.cu:267-327)
-            const float4 q = rotations[i];
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            const M3 R = quat_to_R(q);
+            const float4 q4 = rotations[i];
             const float3 sc = scales[i];
-            const float3 s = make_float3(scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z);
-            M3 S = m3_cols(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
-            S.m[0][0] = s.x; S.m[1][1] = s.y; S.m[2][2] = s.z;
-            const M3 M = m3_mul(S, R);
-            const M3 dSig = m3_cols(d_cov[0], 0.5f * d_cov[1], 0.5f * d_cov[2], 0.5f * d_cov[1], d_cov[3], 0.5f * d_cov[4],
-                                    0.5f * d_cov[2], 0.5f * d_cov[4], d_cov[5]);
-            M3 M2;
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++)
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) M2.m[cc][rr] = 2.0f * M.m[cc][rr];
-            const M3 dM = m3_mul(M2, dSig);
-            const M3 Rt = m3_T(R);
-            M3 dMt = m3_T(dM);
-            ds.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-            ds.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-            ds.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-                dMt.m[0][rr] *= s.x;
-                dMt.m[1][rr] *= s.y;
-                dMt.m[2][rr] *= s.z;
-            }
-            dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
-            dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
-            dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
-            dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+            const float s[3] = {scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z};
+            gg::cov3d_backward(s, q, d_cov, ds, dq);
         }
         if (out.dL_dscales) {
-            out.dL_dscales[3 * i] = ds.x; out.dL_dscales[3 * i + 1] = ds.y; out.dL_dscales[3 * i + 2] = ds.z;
+            out.dL_dscales[3 * i] = ds[0]; out.dL_dscales[3 * i + 1] = ds[1]; out.dL_dscales[3 * i + 2] = ds[2];
         }
-        if (out.dL_drotations) *reinterpret_cast<float4 *>(out.dL_drotations + 4 * (size_t)i) = dq;
+        if (out.dL_drotations) *reinterpret_cast<float4 *>(out.dL_drotations + 4 * (size_t)i) = make_float4(dq[0], dq[1], dq[2], dq[3]);
     }
 }
 
