@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["make_module", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace", "MergedRasterWorkspace",
+__all__ = ["make_module", "make_C", "raster_forward", "raster_backward", "mark_visible", "RasterContext", "RasterWorkspace", "MergedRasterWorkspace",
            "StaticStream"]
 
 
@@ -530,6 +530,70 @@ def make_module(C_):
                 empty if cov3D_precomp is None else cov3D_precomp, rs)
 
     return GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, _RasterizeGaussians
+
+
+def make_C(C_):
+    """The reference's pybind module `_C` (R3/ext.cpp:15-19; signatures R3/rasterize_points.h:18-64) for a channel count, on
+    libfnx: (rasterize_gaussians, rasterize_gaussians_backward, mark_visible) with the reference's positional arguments, return
+    tuples and buffer hand-over, so that the reference's OWN wrapper package (`diff_gaussian_rasterization_ch3/__init__.py`:
+    `from . import _C`) runs unchanged on top of it.  geomBuffer / binningBuffer / imgBuffer are the three uint8 scratch tensors of
+    the forward (private layout, like the reference's); the backward gets them back together with `R` and rebuilds the scratch
+    handle from them.  The forward sizes its binning buffer exactly (one host sync, like rasterizer_impl.cu:263-264), so its
+    capacity IS the returned instance count."""
+
+    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                            projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered):
+        ctx, color, radii, depth = raster_forward(
+            C_, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
+            tan_fovx, tan_fovy, int(image_height), int(image_width), sh=sh, prefiltered=prefiltered, speculative=False,
+            sh_degree=int(degree), campos=campos)
+        empty = lambda: torch.empty(0, dtype=torch.uint8, device=means3D.device)
+        geom, binning, img = (b.t if b.t is not None else empty() for b in ctx.bufs)
+        return ctx.num_rendered, color, radii, geom, binning, img, depth
+
+    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                                     projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                     imageBuffer):
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        P = means3D.size(0)
+        H, W = int(dL_dout_color.size(-2)), int(dL_dout_color.size(-1))
+        use_sh = sh is not None and sh.numel() != 0
+        some = lambda t: t is not None and t.numel() != 0
+        keep = dict(means3D=_f32c(means3D), colors=None if use_sh else _f32c(colors), opacities=None, sh=_f32c(sh) if use_sh else None,
+                    campos=_f32c(campos).reshape(-1, 3)[:1].contiguous() if use_sh else None,
+                    scales=_f32c(scales) if some(scales) else None, rotations=_f32c(rotations) if some(rotations) else None,
+                    cov=_f32c(cov3D_precomp) if some(cov3D_precomp) else None,
+                    view=_f32c(viewmatrix), proj=_f32c(projmatrix), bg=_f32c(background),
+                    buffers=(geomBuffer, binningBuffer, imageBuffer))
+        a = L.RasterArgs()
+        a.P, a.V, a.C, a.W, a.H = P, 1, C_, W, H
+        a.means3D, a.colors = _ptr(keep["means3D"]), _ptr(keep["colors"])
+        # the reference's backward is not handed the opacities (they sit in the forward's buffers, as they do in libfnx's record
+        # stream); the ABI's argument check wants the pointer non-NULL, nothing dereferences it in the backward
+        a.opacities = _ptr(keep["means3D"])
+        a.scales, a.rotations, a.cov3D_precomp, a.sh = _ptr(keep["scales"]), _ptr(keep["rotations"]), _ptr(keep["cov"]), _ptr(keep["sh"])
+        if use_sh:
+            a.sh_degree, a.sh_coeffs, a.campos = int(degree), int(sh.size(1)), keep["campos"].data_ptr()
+        a.view_matrix, a.proj_matrix, a.bg = _ptr(keep["view"]), _ptr(keep["proj"]), _ptr(keep["bg"])
+        a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+        a.prefiltered, a.flags, a.instance_capacity_hint = 0, 0, 0
+        a.grad_begin, a.grad_end = 0, 0
+        a.tile_order, a.static_view_map, a.static_views = None, None, 0
+        sc = L.RasterScratch()
+        sc.geom, sc.geom_bytes = _ptr(geomBuffer), geomBuffer.numel()
+        sc.binning, sc.binning_bytes = _ptr(binningBuffer), binningBuffer.numel()
+        sc.image, sc.image_bytes = _ptr(imageBuffer), imageBuffer.numel()
+        sc.binning_capacity, sc.check_slot = int(R), -1
+        ctx = RasterContext()
+        ctx.args, ctx.scratch, ctx.bufs, ctx.num_rendered, ctx.radii, ctx.keep = a, sc, None, int(R), radii, keep
+        ctx.C, ctx.V, ctx.P = C_, 1, P
+        g = raster_backward(ctx, dL_dout_color)
+        dsh = g["sh"] if use_sh else torch.zeros((P, 0, 3), dtype=torch.float32, device=means3D.device)
+        # order of R3/rasterize_points.cu:193
+        return g["means2D"], g["colors"], g["opacity"], g["means3D"], g["cov3D"], dsh, g["scales"], g["rotations"]
+
+    return rasterize_gaussians, rasterize_gaussians_backward, mark_visible
 
 
 def read_geom(ctx):

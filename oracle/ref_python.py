@@ -96,6 +96,22 @@ def use_reference_python(native="fnx"):
     _STATE["native"] = native
 
 
+def reference_wrapper_on(pkg, c_module, alias):
+    """The reference's own wrapper package `pkg` (`diff_gaussian_rasterization_ch3` / `_ch1`: its unmodified __init__, staged
+    bytecode) executed under the module name `alias` with its `from . import _C` bound to `c_module` -- e.g. libfnx's `_C`-level
+    drop-in (fluidnexus_b200/compat/<pkg>/_C.py).  Independent of use_reference_python()'s per-process binding."""
+    import zipimport
+    if not staged():
+        raise FileNotFoundError("oracle/_ref/FluidDynamics is missing: run `python oracle/build_ref.py` where /root/reference exists")
+    code = zipimport.zipimporter(build_ref.PKG_ZIP).get_code(pkg)
+    mod = types.ModuleType(alias)
+    mod.__path__, mod.__package__ = [], alias
+    mod._C = c_module
+    sys.modules[alias], sys.modules[alias + "._C"] = mod, c_module
+    exec(code, mod.__dict__)
+    return mod
+
+
 def loop_body(name):
     """Code object of one optimisation-loop body of the reference's entry scripts (see build_ref.LOOPS), and where it
     was cut from: (relative path, (first line, last line))."""

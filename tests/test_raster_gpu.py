@@ -413,3 +413,62 @@ def test_sh_colour_path_matches_compiled_reference(libfnx, degree, M):
     assert rel_(shs.grad[:, :nb], rg["sh"][:, :nb]) < 1e-4 and float(shs.grad[:, nb:].abs().max() if nb < M else 0.0) == 0.0
     for k, mine in (("means3D", means.grad), ("opacity", op.grad), ("scales", sc.grad), ("rotations", rot.grad)):
         assert rel_(mine.reshape(rg[k].shape), rg[k]) < 1e-4, (k, rel_(mine.reshape(rg[k].shape), rg[k]))
+
+
+@pytest.mark.parametrize("C_", [3, 1])
+def test_reference_wrapper_package_runs_unchanged_on_the_C_level_dropin(libfnx, C_):
+    """The level at which the reference itself binds native code: its wrapper package (`diff_gaussian_rasterization_chN/__init__.py`,
+    unmodified, staged bytecode) on top of libfnx's `_C` drop-in (rasterize_gaussians / rasterize_gaussians_backward / mark_visible
+    with the pybind signatures of R3/rasterize_points.h:18-64, buffers handed back to the backward like the reference's).  Same
+    kernels as the package-level drop-in: images / depth / radii must be bit-identical, gradients equal up to the order of the
+    float reductions."""
+    from oracle import ref_python
+    if not ref_python.staged():
+        pytest.skip("staged reference Python (oracle/_ref) not present")
+    from fluidnexus_b200 import install_compat
+    install_compat()
+    import importlib
+    pkg = f"diff_gaussian_rasterization_ch{C_}"
+    wrap = ref_python.reference_wrapper_on(pkg, importlib.import_module(pkg + "._C"), f"refwrap_ch{C_}")
+    drop = importlib.import_module(pkg)
+    assert wrap.GaussianRasterizer is not drop.GaussianRasterizer
+    name = "mixed_ch3_96" if C_ == 3 else "fluid_ch1_112"
+    gs, cam, bg, inp = scenes.build(name)
+    dL = _t(scenes.dL_dpix(name, (C_, inp["H"], inp["W"])))
+    res = {}
+    for tag, m in (("wrap", wrap), ("drop", drop)):
+        t = {k: _t(inp[k]).requires_grad_(True) for k in ("means3D", "colors", "opacities", "scales", "rotations")}
+        rs = m.GaussianRasterizationSettings(
+            image_height=inp["H"], image_width=inp["W"], tan_fov_x=inp["tan_fov_x"], tan_fov_y=inp["tan_fov_y"], bg=_t(inp["bg"]),
+            scale_modifier=1.0, view_matrix=_t(inp["view"]), proj_matrix=_t(inp["proj"]), sh_degree=0, campos=torch.zeros(3, device="cuda"),
+            prefiltered=False)
+        rz = m.GaussianRasterizer(raster_settings=rs)
+        means2D = torch.zeros_like(t["means3D"], requires_grad=True) + 0
+        means2D.retain_grad()
+        color, radii, depth = rz(means3D=t["means3D"], means2D=means2D, shs=None, colors_precomp=t["colors"], opacities=t["opacities"],
+                                 scales=t["scales"], rotations=t["rotations"], cov3D_precomp=None)
+        (color * dL).sum().backward()
+        res[tag] = dict(color=color.detach(), radii=radii, depth=depth, vis=rz.mark_visible(t["means3D"].detach()), means2D=means2D.grad,
+                        **{k: v.grad for k, v in t.items()})
+    w, d = res["wrap"], res["drop"]
+    assert torch.equal(w["color"], d["color"]) and torch.equal(w["radii"], d["radii"]) and torch.equal(w["depth"], d["depth"])
+    assert torch.equal(w["vis"], d["vis"]) and w["vis"].dtype == torch.bool
+    for k in ("means3D", "means2D", "colors", "opacities", "scales", "rotations"):
+        assert w[k] is not None and w[k].shape == d[k].shape, k
+        assert rel(w[k].cpu().numpy(), d[k].cpu().numpy()) < 2e-5, k
+    # and against the oracle, like every other path
+    o = RasterOracle("f64")
+    ref = o.forward(**inp)
+    assert np.abs(w["color"].cpu().numpy() - ref["color"]).max() < PIX_TOL
+    gref = o.backward(dL.cpu().numpy())
+    assert rel(w["means3D"].cpu().numpy(), gref["means3D"]) < GRAD_TOL and rel(w["rotations"].cpu().numpy(), gref["rotations"]) < GRAD_TOL
+    # P == 0 short-circuit through the reference's wrapper (rasterize_points.cu:81,160): zero image, empty buffers, empty grads
+    C3 = importlib.import_module(pkg + "._C")
+    e = lambda *s: torch.zeros(s, device="cuda")
+    nr, col, rad, geo, binb, img, dep = C3.rasterize_gaussians(_t(inp["bg"]), e(0, 3), e(0, C_), e(0, 1), e(0, 3), e(0, 4), 1.0, torch.Tensor([]),
+                                                               _t(inp["view"]), _t(inp["proj"]), inp["tan_fov_x"], inp["tan_fov_y"], inp["H"],
+                                                               inp["W"], torch.Tensor([]), 0, e(3), False)
+    assert nr == 0 and col.abs().max() == 0 and rad.numel() == 0 and geo.numel() == 0
+    g8 = C3.rasterize_gaussians_backward(_t(inp["bg"]), e(0, 3), rad, e(0, C_), e(0, 3), e(0, 4), 1.0, torch.Tensor([]), _t(inp["view"]),
+                                         _t(inp["proj"]), inp["tan_fov_x"], inp["tan_fov_y"], dL, torch.Tensor([]), 0, e(3), geo, nr, binb, img)
+    assert len(g8) == 8 and all(x.numel() == 0 for x in g8)

@@ -78,3 +78,40 @@ def test_cached_image_is_a_plain_tensor_everywhere_else():
     v0 = c._version
     c.mul_(0.5)
     assert c._version == v0 + 1      # an in-place edit is visible to the cache (the device copy would be refreshed)
+
+
+def test_reference_wrapper_package_binds_to_the_C_level_dropin():
+    """`diff_gaussian_rasterization_chN._C` of the drop-in packages has the reference's three pybind functions; the reference's OWN
+    wrapper package (unmodified __init__, staged bytecode) imports on top of it and reaches libfnx -- which, on this GPU-less box,
+    refuses CPU tensors loudly (there is no CPU path) after the wrapper's own argument checks have run."""
+    out = _run("""
+import importlib, inspect, torch
+import fluidnexus_b200
+fluidnexus_b200.install_compat()
+from oracle import ref_python as RP
+for C_ in (3, 1):
+    pkg = f"diff_gaussian_rasterization_ch{C_}"
+    c = importlib.import_module(pkg + "._C")
+    # positional signatures of R3/rasterize_points.h:18-64 (18 / 20 / 3 arguments)
+    assert [len(inspect.signature(getattr(c, n)).parameters) for n in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible")] == [18, 20, 3]
+    w = RP.reference_wrapper_on(pkg, c, f"refwrap_ch{C_}")
+    assert w.GaussianRasterizer.forward.__code__.co_filename.startswith("FluidDynamics/submodules/")     # the reference's code, not ours
+    assert w._C is c and w.GaussianRasterizationSettings._fields == importlib.import_module(pkg).GaussianRasterizationSettings._fields
+    rs = w.GaussianRasterizationSettings(image_height=32, image_width=32, tan_fov_x=0.5, tan_fov_y=0.5, bg=torch.zeros(C_), scale_modifier=1.0,
+                                         view_matrix=torch.eye(4), proj_matrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3), prefiltered=False)
+    rz = w.GaussianRasterizer(raster_settings=rs)
+    P = 7
+    kw = dict(means3D=torch.rand(P, 3), means2D=torch.zeros(P, 3), opacities=torch.rand(P, 1), scales=torch.rand(P, 3), rotations=torch.rand(P, 4))
+    try:
+        rz(**kw)                                        # the wrapper's own check (__init__.py:184-185)
+        raise SystemExit("no exception")
+    except Exception as e:
+        assert "exactly one of either SHs or precomputed colors" in str(e), e
+    try:
+        rz(colors_precomp=torch.rand(P, C_), **kw)
+        raise SystemExit("no exception")
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e), e
+print("ok")
+""")
+    assert out.strip().endswith("ok")
