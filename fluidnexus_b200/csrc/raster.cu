@@ -1597,7 +1597,7 @@ static const uint32_t *fwd_tile_order(const fnx_raster_args *a) {
     return on ? a->tile_order : nullptr;
 }
 
-static int validate(const fnx_raster_args *a) {
+static int validate(const fnx_raster_args *a, bool backward = false) {
     FNX_REQUIRE(a != nullptr, "args is NULL");
     FNX_REQUIRE(a->C == 1 || a->C == 3, "C must be 1 or 3 (got %d)", a->C);
     FNX_REQUIRE(a->P >= 0 && a->V >= 1 && a->W > 0 && a->H > 0, "bad sizes P=%d V=%d W=%d H=%d", a->P, a->V, a->W, a->H);
@@ -1613,7 +1613,9 @@ static int validate(const fnx_raster_args *a) {
         }
     }
     if (a->P > 0) {
-        FNX_REQUIRE(a->means3D && (a->colors || a->sh) && a->opacities, "means3D / colors (or sh) / opacities must be given");
+        // the backward reads colours and opacities from the forward's record stream: like the reference's backward
+        // (rasterize_points.h:39-59 has no opacity argument) it does not need the pointer
+        FNX_REQUIRE(a->means3D && (a->colors || a->sh) && (a->opacities || backward), "means3D / colors (or sh) / opacities must be given");
         FNX_REQUIRE((a->scales && a->rotations) || a->cov3D_precomp, "need scales+rotations or cov3D_precomp");
         FNX_REQUIRE(a->view_matrix && a->proj_matrix && a->bg, "view_matrix / proj_matrix / bg must be given");
     }
@@ -2359,7 +2361,7 @@ int fnx_raster_forward_ch3(const fnx_raster_args *a, fnx_alloc_fn ag, void *cg, 
 
 int fnx_raster_backward(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,
                         const int32_t *radii, const float *dL_dout_color, const fnx_raster_grads *g, fnx_stream_t stream) {
-    int rc = validate(a);
+    int rc = validate(a, /*backward=*/true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (a->C == 3) return backward_impl<3>(a, scratch, num_rendered, radii, dL_dout_color, g, st);

@@ -569,9 +569,7 @@ def make_C(C_):
         a = L.RasterArgs()
         a.P, a.V, a.C, a.W, a.H = P, 1, C_, W, H
         a.means3D, a.colors = _ptr(keep["means3D"]), _ptr(keep["colors"])
-        # the reference's backward is not handed the opacities (they sit in the forward's buffers, as they do in libfnx's record
-        # stream); the ABI's argument check wants the pointer non-NULL, nothing dereferences it in the backward
-        a.opacities = _ptr(keep["means3D"])
+        a.opacities = None   # the reference's backward is not handed them; libfnx's reads them from the forward's record stream
         a.scales, a.rotations, a.cov3D_precomp, a.sh = _ptr(keep["scales"]), _ptr(keep["rotations"]), _ptr(keep["cov"]), _ptr(keep["sh"])
         if use_sh:
             a.sh_degree, a.sh_coeffs, a.campos = int(degree), int(sh.size(1)), keep["campos"].data_ptr()

@@ -174,7 +174,8 @@ typedef struct fnx_raster_grads {
     float *dL_dsh;       /* [P,sh_coeffs,3] (written only when sh was given) */
 } fnx_raster_grads;
 
-/* Backward.  dL_dout_color [V,C,H,W].  `a` must equal the forward's args; `scratch` is what forward reported;
+/* Backward.  dL_dout_color [V,C,H,W].  `a` must equal the forward's args (`opacities` may be NULL here: like the reference's
+ * backward, which is not handed them, it reads them from the forward's buffers); `scratch` is what forward reported;
  * `num_rendered` what it returned.  Depth has no gradient (R3/README.md:13).
  * Replaces RasterizeGaussiansBackwardCUDA, R3/rasterize_points.cu:117-194. */
 int fnx_raster_backward(const fnx_raster_args *a, const fnx_raster_scratch *scratch, int64_t num_rendered,

@@ -118,6 +118,11 @@ def test_backward_and_helpers_reject_bad_arguments(libfnx):
     assert "scratch buffers missing" in libfnx.fnx_last_error().decode()
     assert libfnx.fnx_raster_backward_ch1(C.byref(a), C.byref(sc), 0, 0x1000, 0x1000, C.byref(gr), None) == L.FNX_ERR_INVALID
     assert "needs C == 1" in libfnx.fnx_last_error().decode()
+    # opacities: needed by the forward, not by the backward (the reference's backward has no such argument, rasterize_points.h:39-59)
+    assert _fwd(libfnx, "fnx_raster_forward", _args(opacities=None)) == L.FNX_ERR_INVALID and "opacities" in libfnx.fnx_last_error().decode()
+    b = _args(opacities=None)
+    assert libfnx.fnx_raster_backward(C.byref(b), C.byref(sc), 0, 0x1000, 0x1000, C.byref(gr), None) == L.FNX_ERR_INVALID
+    assert "scratch buffers missing" in libfnx.fnx_last_error().decode()       # i.e. the argument block itself was accepted
     p = C.c_void_p()
     assert libfnx.fnx_raster_overflow_flag(C.byref(sc), C.byref(p)) == L.FNX_ERR_INVALID
     nr = C.c_int64(0)
