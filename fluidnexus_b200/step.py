@@ -53,6 +53,33 @@ def _dev_f32(x, dev):
     return t.to(dev).contiguous()
 
 
+class HostTensorCache:
+    """Device copies of host tensors that are handed in again and again, keyed by the tensor OBJECT: an entry is valid only while
+    its weak reference still points at the very tensor that is asked for and that tensor's version counter is unchanged (in-place
+    edits bump it).  An address is not an identity -- a freed image's storage can be handed to the next frame's image of the same
+    shape -- so neither data_ptr() nor id() alone is trusted.  Bounded (frames come and go); dead entries are dropped first."""
+
+    def __init__(self, max_entries=256):
+        self.max_entries = int(max_entries)
+        self._entries = {}     # id(tensor) -> (weakref to the tensor, version, device copy)
+
+    def __len__(self):
+        return len(self._entries)
+
+    def get(self, t, upload):
+        import weakref
+        ent = self._entries.get(id(t))
+        if ent is not None and ent[0]() is t and ent[1] == t._version:
+            return ent[2]
+        if len(self._entries) >= self.max_entries:
+            dead = [k for k, e in self._entries.items() if e[0]() is None]
+            for k in dead or [next(iter(self._entries))]:
+                self._entries.pop(k)
+        dev_copy = upload(t)
+        self._entries[id(t)] = (weakref.ref(t), t._version, dev_copy)
+        return dev_copy
+
+
 LOSS_ROW = 16      # floats per frame in the loss table (FrameState.loss_row)
 MAX_ROW_VIEWS = 5  # views whose l1 / ssim fit into the row
 
@@ -155,10 +182,10 @@ class PhysicalStep:
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         # Host ground truth that is handed in again and again (the images of a frame's cameras do not change over the 250-1000
         # iterations of the frame; the reference uploads them every time, train_physical_particle.py:353) is uploaded ONCE: device
-        # copies keyed by the host tensor's storage, shape and version counter.  Off by default: the caller
+        # copies keyed by the host tensor object and its version counter (HostTensorCache).  Off by default: the caller
         # opts in per call (step(..., cache_gt=True)) or per object.
         self.cache_gt = False
-        self._gt_cache = {}
+        self._gt_cache = HostTensorCache()
 
     # -- pieces ---------------------------------------------------------------------------------------------
     def physics_forward(self, fr: FrameState, physics=True):
@@ -370,14 +397,7 @@ class PhysicalStep:
         return out
 
     def _cached_gt(self, gt):
-        key = (gt.data_ptr(), tuple(gt.shape), gt.dtype)
-        hit = self._gt_cache.get(key)
-        if hit is None or hit[1] != gt._version:
-            if len(self._gt_cache) >= 256:               # bounded: frames come and go
-                self._gt_cache.pop(next(iter(self._gt_cache)))
-            hit = (gt.to(self.dev, non_blocking=True).float().contiguous(), gt._version)
-            self._gt_cache[key] = hit
-        return hit[0]
+        return self._gt_cache.get(gt, lambda t: t.to(self.dev, non_blocking=True).float().contiguous())
 
     def step(self, fr: FrameState, view_ids, gt, update=True, batch=None, graph=False, physics=True, cache_gt=None):
         """One optimiser iteration for one frame.  view_ids: camera indices rendered by THIS process; gt
