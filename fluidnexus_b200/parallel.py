@@ -201,9 +201,22 @@ class FrameLanes:
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n)] if self.n > 1 else [None]
         self._fork = torch.cuda.Event() if self.n > 1 else None
         self._join = [torch.cuda.Event() for _ in range(self.n)] if self.n > 1 else []
+        self._lane_of = {}   # frame -> lane, fixed at first sight
+
+    def lane_of(self, frame):
+        """A frame keeps the lane it was first dealt to (round-robin in order of first appearance), whatever subset of the frames
+        a later run() is given: its captured iterations use that lane's PhysicalStep (side stream, loss scratch), and two frames
+        that share a scratch must never run concurrently."""
+        try:
+            lane = self._lane_of.get(frame)
+            if lane is None:
+                lane = self._lane_of[frame] = len(self._lane_of) % self.n
+            return lane
+        except TypeError:        # unhashable frame objects: positional dealing is the caller's responsibility
+            return None
 
     def run(self, frames, call):
-        """call(step, frame) for every frame, frame k on lane k % lanes; everything is ordered after the work already
+        """call(step, frame) for every frame on the frame's lane (lane_of); everything is ordered after the work already
         queued on the current stream, and the current stream waits for all lanes before this returns.  Returns the
         list of results in frame order."""
         if self.n == 1:
@@ -212,7 +225,9 @@ class FrameLanes:
         self._fork.record(main)
         used, out = set(), []
         for k, fr in enumerate(frames):
-            lane = k % self.n
+            lane = self.lane_of(fr)
+            if lane is None:
+                lane = k % self.n
             st = self.streams[lane]
             if lane not in used:
                 st.wait_event(self._fork)

@@ -127,3 +127,14 @@ def test_frame_lanes_single_lane_runs_frames_in_order():
     seen = []
     out = lanes.run([3, 1, 2], lambda step, fr: seen.append((step, fr)) or fr * 10)
     assert out == [30, 10, 20] and seen == [("step0", 3), ("step0", 1), ("step0", 2)]
+
+
+def test_a_frame_keeps_its_lane_whatever_subset_is_run():
+    """Captured iterations of a frame use its lane's PhysicalStep (side stream, loss scratch): the dealing must not depend on
+    which subset of the frames a later run() is handed."""
+    from fluidnexus_b200.parallel import FrameLanes
+    lanes = FrameLanes(lambda k: f"step{k}", 1, "cpu")
+    lanes.n = 3                                       # (several lanes need CUDA streams; the dealing itself does not)
+    assert [lanes.lane_of(f) for f in (10, 11, 12, 13, 14)] == [0, 1, 2, 0, 1]
+    assert [lanes.lane_of(f) for f in (14, 12, 10)] == [1, 2, 0]          # a subset, in another order: same lanes
+    assert lanes.lane_of(99) == 2 and lanes.lane_of([1, 2]) is None       # new frame: next lane; unhashable: positional
