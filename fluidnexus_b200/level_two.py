@@ -120,7 +120,10 @@ class LevelTwoStep:
     def _workspace(self, st: LevelTwoState, view_ids):
         key = tuple(view_ids)
         ws = st.ws.get(key)
-        if ws is not None and ws.overflowed():
+        # The positions are fixed in this stage, so the instance count only creeps (scales and opacities are trained at small
+        # learning rates): re-size as soon as the last FINISHED forward used more than 90 % of the capacity, well before a forward can
+        # overflow it (an overflowed forward renders only the background, and this stage's update is not gated on the device).
+        if ws is not None and int(ws.count[0]) > 0.9 * ws.capacity:
             torch.cuda.synchronize(self.dev)
             st.ws.pop(key)
             ws = None
