@@ -224,3 +224,33 @@ def test_overflowed_iteration_is_voided_on_the_device_and_recovered(libfnx):
         torch.cuda.synchronize()
         assert fr.skipped_iterations == 1 and not fr.ws[tuple(views)].overflowed() and fr.ws[tuple(views)] is not ws
         assert int(fr.step_dev) == 3 and float((fr.e - e0).abs().max()) > 0
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_ground_truth_cache_uploads_once_and_follows_edits(libfnx, graph):
+    """step(..., cache_gt=True): a host ground-truth tensor handed in again is served from its device copy,
+    an in-place edit of it is seen, and another tensor of the same shape gets its own copy -- the results must equal the uncached
+    path's at every step."""
+    hp, vis, fluid, bg, cams = _scene(3, True, seed=9)
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    views = [0, 2, 3]
+    gen = torch.Generator().manual_seed(1)
+    gt_a = (torch.rand(3, 3, 64, 64, generator=gen) * 0.5).pin_memory()
+    gt_b = (torch.rand(3, 3, 64, 64, generator=gen) * 0.5).pin_memory()
+    res = {}
+    for cached in (False, True):
+        ps = PhysicalStep(cams, 3, prm)
+        fr = FrameState(hp, vis, fluid, bg, prm=prm)
+        a, b = gt_a.clone().pin_memory(), gt_b.clone().pin_memory()
+        l1 = []
+        for it, gt in enumerate((a, a, a, b, a)):
+            if it == 2:
+                a.mul_(0.25)                                   # in-place edit: the cache must upload the new content
+            out = ps.step(fr, views, gt, graph=graph, cache_gt=cached)
+            l1.append(out["l1"].clone())
+        torch.cuda.synchronize()
+        res[cached] = (torch.stack(l1).cpu(), fr.e.clone(), len(ps._gt_cache))
+    assert res[False][2] == 0 and res[True][2] == 2            # two host tensors seen -> two device copies
+    assert torch.allclose(res[False][0], res[True][0], rtol=1e-6, atol=1e-8)
+    assert float((res[False][0][1] - res[False][0][2]).abs().max()) > 1e-3     # the edit really changed the loss
+    assert (res[False][1] - res[True][1]).abs().max() < 1e-6
