@@ -541,18 +541,18 @@ def make_C(C_):
     handle from them.  The forward sizes its binning buffer exactly (one host sync, like rasterizer_impl.cu:263-264), so its
     capacity IS the returned instance count."""
 
-    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
-                            projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered):
+    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, view_matrix,
+                            proj_matrix, tan_fov_x, tan_fov_y, image_height, image_width, sh, degree, campos, prefiltered):
         ctx, color, radii, depth = raster_forward(
-            C_, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
-            tan_fovx, tan_fovy, int(image_height), int(image_width), sh=sh, prefiltered=prefiltered, speculative=False,
+            C_, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, view_matrix, proj_matrix,
+            tan_fov_x, tan_fov_y, int(image_height), int(image_width), sh=sh, prefiltered=prefiltered, speculative=False,
             sh_degree=int(degree), campos=campos)
         empty = lambda: torch.empty(0, dtype=torch.uint8, device=means3D.device)
         geom, binning, img = (b.t if b.t is not None else empty() for b in ctx.bufs)
         return ctx.num_rendered, color, radii, geom, binning, img, depth
 
-    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
-                                     projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, view_matrix,
+                                     proj_matrix, tan_fov_x, tan_fov_y, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
                                      imageBuffer):
         if means3D.dim() != 2 or means3D.size(1) != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -564,7 +564,7 @@ def make_C(C_):
                     campos=_f32c(campos).reshape(-1, 3)[:1].contiguous() if use_sh else None,
                     scales=_f32c(scales) if some(scales) else None, rotations=_f32c(rotations) if some(rotations) else None,
                     cov=_f32c(cov3D_precomp) if some(cov3D_precomp) else None,
-                    view=_f32c(viewmatrix), proj=_f32c(projmatrix), bg=_f32c(background),
+                    view=_f32c(view_matrix), proj=_f32c(proj_matrix), bg=_f32c(background),
                     buffers=(geomBuffer, binningBuffer, imageBuffer))
         a = L.RasterArgs()
         a.P, a.V, a.C, a.W, a.H = P, 1, C_, W, H
@@ -574,7 +574,7 @@ def make_C(C_):
         if use_sh:
             a.sh_degree, a.sh_coeffs, a.campos = int(degree), int(sh.size(1)), keep["campos"].data_ptr()
         a.view_matrix, a.proj_matrix, a.bg = _ptr(keep["view"]), _ptr(keep["proj"]), _ptr(keep["bg"])
-        a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+        a.tan_fov_x, a.tan_fov_y, a.scale_modifier = float(tan_fov_x), float(tan_fov_y), float(scale_modifier)
         a.prefiltered, a.flags, a.instance_capacity_hint = 0, 0, 0
         a.grad_begin, a.grad_end = 0, 0
         a.tile_order, a.static_view_map, a.static_views = None, None, 0

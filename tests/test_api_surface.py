@@ -69,6 +69,28 @@ def test_compat_packages_export_the_reference_names():
     assert "distCUDA2" in open(os.path.join(compat, "simple_knn", "_C.py")).read()
 
 
+def test_C_level_dropin_has_the_pybind_signatures():
+    """`diff_gaussian_rasterization_chN._C` of the drop-in packages against the reference's pybind module: the functions ext.cpp
+    binds, with the parameter names, order and count of their declarations in rasterize_points.h (parsed by tools/make_api_golden.py)."""
+    import inspect
+    from fluidnexus_b200 import rasterizer as R
+    gold = GOLD["_C"]
+    assert sorted(gold) == ["mark_visible", "rasterize_gaussians", "rasterize_gaussians_backward"]
+    for C_ in (1, 3):
+        fns = dict(zip(("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"), R.make_C(C_)))
+        for name, g in gold.items():
+            params = list(inspect.signature(fns[name]).parameters.values())
+            got = [p.name for p in params]
+            want = ["positions" if (name == "mark_visible" and a == "means3D") else a for a in g["args"]]
+            assert got == want, (name, got, want)
+            assert all(p.default is inspect.Parameter.empty for p in params), name      # pybind functions have no defaults
+    assert (gold["rasterize_gaussians"]["returns"], gold["rasterize_gaussians_backward"]["returns"], gold["mark_visible"]["returns"]) == (7, 8, 1)
+    import fluidnexus_b200
+    for pkg in ("diff_gaussian_rasterization_ch1", "diff_gaussian_rasterization_ch3"):
+        src = open(os.path.join(fluidnexus_b200.COMPAT_DIR, pkg, "_C.py")).read()
+        assert all(n in src for n in gold), pkg
+
+
 def test_hard_coded_constants_equal_the_reference_configs():
     """StepParams defaults, bench.py's per-workload constants, the solver defaults and the background learning rates against the
     reference's effective configs (arguments/__init__.py overridden by configs/*.json; tools/make_config_golden.py)."""

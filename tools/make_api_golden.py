@@ -42,6 +42,26 @@ def method_sig(path, cls, name):
     raise KeyError((cls, name))
 
 
+def pybind_sigs(header, ext):
+    """The three functions the reference's `_C` module exports (ext.cpp: m.def(python name, &C++ function)) with the parameter names
+    and C++ types of their declarations in rasterize_points.h and the arity of their std::tuple return types."""
+    import re
+    h = open(header).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    binds = dict(re.findall(r'm\.def\("(\w+)",\s*&(\w+)\)', open(ext).read()))
+    out = {}
+    for py, cpp in binds.items():
+        m = re.search(r"([\w:<>,\s]+?)\s+" + cpp + r"\s*\((.*?)\)\s*;", h, flags=re.S)
+        ret, params = m.group(1).strip(), m.group(2)
+        names, types = [], []
+        for prm in params.split(","):
+            toks = prm.replace("&", " ").split()
+            names.append(toks[-1])
+            types.append("Tensor" if "Tensor" in prm else [t for t in toks[:-1] if t != "const"][-1])
+        out[py] = {"cpp": cpp, "args": names, "types": types, "returns": ret.count("Tensor") + ret.count("int")}
+    return out
+
+
 def main():
     r3 = os.path.join(REF, "submodules/gaussian_rasterization_ch3/diff_gaussian_rasterization_ch3/__init__.py")
     gm = os.path.join(REF, "gaussian_splatting/gm_fluid.py")
@@ -52,6 +72,8 @@ def main():
         "GaussianRasterizationSettings": class_fields(r3, "GaussianRasterizationSettings"),
         "GaussianRasterizer.forward": method_sig(r3, "GaussianRasterizer", "forward"),
         "GaussianRasterizer.mark_visible": method_sig(r3, "GaussianRasterizer", "mark_visible"),
+        "_C": pybind_sigs(os.path.join(REF, "submodules/gaussian_rasterization_ch3/rasterize_points.h"),
+                          os.path.join(REF, "submodules/gaussian_rasterization_ch3/ext.cpp")),
         "solver": {m: method_sig(gm, "GaussianModel", m) for m in
                    ("guess_hidden_particles", "project_gas_constraints", "confirm_guess_hidden_particles", "update_visual_particles",
                     "remove_invalid_particles", "update_solver_counts")},
