@@ -1,0 +1,184 @@
+"""Particle creation and emission between frames -- the host-side set-up around the solver tick.
+
+Mirrors, with the reference's method and attribute names, what FluidNexus' entries call on `gm_dynamics.GaussianModel` before and
+between the optimised / simulated frames (FD/entries_fluid_nexus/train_physical_particle.py:82,192,236,286,496;
+future_simulation.py:102,132):
+
+    create_particles_visual(model_args)                       gm_dynamics.py:510-555   random pillar of visual particles
+    create_particles_hidden(model_args)                       gm_dynamics.py:558-609   lattice pillar of hidden particles + state
+    prepare_emitter_points(model_args, is_future=False)       gm_dynamics.py:674-745   discs of emitter sites
+    prepare_emitter_future_first_points(model_args)           gm_dynamics.py:747-788   stacked discs for the first future frames
+    emit_new_particles(future_time_index=-1)                  gm_dynamics.py:844-976   append one tick's worth of new particles
+
+This is plain torch / numpy bookkeeping (no kernels): a few hundred points per frame.  What matters is that a run seeded like the
+reference's produces the SAME particles: the sites are enumerated in the reference's order (x outermost, then y, then z), and the
+global numpy / torch random streams are consumed by the same calls in the same order (np.random.uniform / random for the visual
+pillar; torch.randperm for fractional emit ratios; torch.randperm + torch.rand_like for the "extra" visual particles).  Pinned
+against the reference's own methods by tests/test_reference_emitter_golden.py (tools/make_emitter_golden.py).
+
+`EmitterMixin` works on any object that carries the solver's state attributes (`_xyz, _estimate_xyz, _buoyancy, _force, _velocity,
+_imass, _counts, _visual_xyz`) and a `dev` device; fluidnexus_b200.solver.PBFSolver inherits it.
+"""
+import numpy as np
+import torch
+
+# optim_args fields read by setup_constants (gm_dynamics.py:76-160) that steer the emission, with the defaults of
+# FD/arguments/__init__.py:314-344
+EMIT_DEFAULTS = dict(emit_ratio_hidden=1.32, emit_ratio_visual=1.32, extra_visual_ratio=0.0, extra_visual_num=0, extra_visual_y_min=0.16,
+                     extra_visual_min_num=0, init_hidden_velocity=0.0)
+
+
+def disc_sites(center_x, center_z, radius, delta, ys):
+    """Sites (x, y, z) of a regular lattice of pitch `delta` inside the vertical cylinder of `radius` around (center_x, ., center_z),
+    one layer per entry of `ys`, ordered x-major, then y, then z -- float64 [n, 3]."""
+    xs = np.arange(center_x - radius, center_x + radius + delta, delta)   # (the stop is exclusive: one pitch is added)
+    zs = np.arange(center_z - radius, center_z + radius + delta, delta)
+    ys = np.asarray(ys, dtype=np.float64).reshape(-1)
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    keep = (X - center_x) ** 2 + (Z - center_z) ** 2 <= radius ** 2
+    return np.stack([X[keep], Y[keep], Z[keep]], axis=1).reshape(-1, 3)
+
+
+def _f32(points, dev):
+    return torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)).float().to(dev)
+
+
+class EmitterMixin:
+    """See the module docstring.  Needs: self.dev, self.scale_factor, self.alpha, gravity as self._gravity_t ([1,3] tensor) or
+    self._gravity (3 floats), and the state attributes; emission settings are attributes with the reference's names
+    (EMIT_DEFAULTS unless set)."""
+
+    # -- settings -------------------------------------------------------------------------------------------------------------
+    def setup_emitter(self, optim_args=None, **overrides):
+        """The emission settings of setup_constants (gm_dynamics.py:76-160): attributes of `optim_args` where present, then
+        keyword overrides, else the reference's defaults."""
+        for k, v in EMIT_DEFAULTS.items():
+            val = getattr(optim_args, k, v) if optim_args is not None else v
+            setattr(self, k, overrides.get(k, val))
+        self.emit_counter = 0
+
+    def _emit_setting(self, name):
+        return getattr(self, name, EMIT_DEFAULTS[name])
+
+    def _gravity_row(self):
+        g = getattr(self, "_gravity_t", None)
+        if g is None:
+            g = torch.tensor([float(c) for c in self._gravity], dtype=torch.float32, device=self.dev).reshape(1, 3)
+        return g
+
+    def _fresh_hidden_state(self, n):
+        """State rows of n new hidden particles: estimate 0, buoyancy = gravity * alpha, no force, initial upward velocity, unit mass."""
+        z3 = torch.zeros((n, 3), dtype=torch.float32, device=self.dev)
+        vel = z3.clone()
+        vel[:, 1] = self._emit_setting("init_hidden_velocity")
+        buoy = torch.ones((n, 3), dtype=torch.float32, device=self.dev) * (self._gravity_row() * self.alpha)
+        return dict(_estimate_xyz=z3, _buoyancy=buoy, _force=z3.clone(), _velocity=vel,
+                    _imass=torch.ones((n, 1), dtype=torch.float32, device=self.dev))
+
+    # -- first frame ----------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def create_particles_visual(self, model_args):
+        """A random pillar: `init_visual_num_pts` particles within `init_visual_radius_small_max` of the axis over the whole height
+        plus `init_thick_visual_num_pts` within `init_visual_radius_max` over the upper part (render units, NOT scaled)."""
+        n, nt = int(model_args.init_visual_num_pts), max(int(model_args.init_thick_visual_num_pts), 0)
+        self.visual_x_mid, self.visual_z_mid = model_args.init_x_mid, model_args.init_z_mid
+        y = np.random.uniform(model_args.init_visual_y_min, model_args.init_visual_y_max, (n, 1))
+        if nt > 0:
+            y = np.concatenate((y, np.random.uniform(model_args.init_visual_y_thick_min, model_args.init_visual_y_max, (nt, 1))), axis=0)
+        r = np.random.random((n, 1)) * model_args.init_visual_radius_small_max
+        if nt > 0:
+            r = np.concatenate((r, np.random.random((nt, 1)) * model_args.init_visual_radius_max), axis=0)
+        theta = np.random.random((n + nt, 1)) * 2 * np.pi
+        pts = np.concatenate((r * np.cos(theta) + self.visual_x_mid, y, r * np.sin(theta) + self.visual_z_mid), axis=1)
+        self._visual_xyz = _f32(pts, self.dev)
+        self.visual_particles_created = True
+
+    @torch.no_grad()
+    def create_particles_hidden(self, model_args):
+        """A lattice pillar of pitch `init_hidden_delta` (scaled units) with fresh state."""
+        d = model_args.init_hidden_delta
+        ys = np.arange(model_args.init_hidden_y_min, model_args.init_hidden_y_max, d)
+        pts = disc_sites(model_args.init_x_mid, model_args.init_z_mid, model_args.init_hidden_radius_max, d, ys)
+        self._xyz = _f32(pts * self.scale_factor, self.dev)
+        n = self._xyz.shape[0]
+        for name, t in self._fresh_hidden_state(n).items():
+            setattr(self, name, t)
+        self._counts = torch.zeros((n, 1), dtype=torch.float32, device=self.dev)
+        self._particle_id = torch.arange(n, device=self.dev).unsqueeze(1)
+        self._particle_id_max = n
+        self.hidden_particles_created = True
+
+    # -- emitter sites --------------------------------------------------------------------------------------------------------
+    def _emitter_geometry(self, model_args):
+        dh, dv = model_args.emitter_hidden_delta, model_args.emitter_visual_delta
+        return (dh, dv, model_args.init_x_mid, model_args.init_z_mid, dv * model_args.emitter_visual_radius_ratio,
+                dh * model_args.emitter_hidden_radius_ratio)
+
+    @torch.no_grad()
+    def prepare_emitter_points(self, model_args, is_future=False):
+        """One disc of sites each for the visual and the hidden particles at the emitter heights (render units); for future
+        simulation the visual disc sits half a radius lower."""
+        dh, dv, cx, cz, rv, rh = self._emitter_geometry(model_args)
+        self.hidden_delta_offset, self.visual_delta_offset = dh, dv
+        y_vis = model_args.emitter_center_y_visual - rv / 2 if is_future else model_args.emitter_center_y_visual
+        self.visual_emitter_points = _f32(disc_sites(cx, cz, rv, dv, [y_vis]), self.dev)
+        self.hidden_emitter_points = _f32(disc_sites(cx, cz, rh, dh, [model_args.emitter_center_y_hidden]), self.dev)
+
+    @torch.no_grad()
+    def prepare_emitter_future_first_points(self, model_args):
+        """Stacks of discs (one diameter high) that the first two future frames emit at once."""
+        dh, dv, cx, cz, rv, rh = self._emitter_geometry(model_args)
+        yv0, yh0 = model_args.emitter_center_y_visual, model_args.emitter_center_y_hidden
+        self.visual_emitter_first_points = _f32(disc_sites(cx, cz, rv, dv, np.arange(yv0, yv0 + rv * 2 + dv, dv)), self.dev)
+        self.hidden_emitter_first_points = _f32(disc_sites(cx, cz, rh, dh, np.arange(yh0, yh0 + rh * 2 + dh, dh)), self.dev)
+
+    # -- per tick -------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _copies_of(sites, ratio, scale):
+        """`ratio` copies of the site set: int(ratio) whole copies, then a random subset holding the fractional part of one more."""
+        whole, frac = int(ratio), ratio - int(ratio)
+        out = [sites.clone() * scale for _ in range(whole)]
+        if frac > 0:
+            cand = sites.clone() * scale
+            out.append(cand[torch.randperm(cand.shape[0])[: int(frac * cand.shape[0])]])
+        return out
+
+    def _extra_visual(self, count_of):
+        """Copies of randomly chosen visual particles above `extra_visual_y_min`, jittered by 5 % of the visual pitch."""
+        sf = self.scale_factor
+        high = self._visual_xyz[self._visual_xyz[:, 1] > self._emit_setting("extra_visual_y_min") * sf]
+        pick = torch.randperm(high.shape[0])[: count_of(high.shape[0])]
+        chosen = high[pick] / sf
+        jitter = self.visual_delta_offset * (torch.rand_like(chosen) - 0.5) * 0.05
+        return (chosen + jitter) * sf
+
+    @torch.no_grad()
+    def emit_new_particles(self, future_time_index=-1):
+        self.emit_counter = getattr(self, "emit_counter", 0) + 1
+        sf = self.scale_factor
+        if 0 <= future_time_index < 2:
+            new_hidden = [self.hidden_emitter_first_points.clone() * sf]
+            new_visual = [self.visual_emitter_first_points.clone() * sf]
+        else:
+            new_hidden = self._copies_of(self.hidden_emitter_points, self._emit_setting("emit_ratio_hidden"), sf)
+            new_visual = self._copies_of(self.visual_emitter_points, self._emit_setting("emit_ratio_visual"), sf)
+            ratio, min_num = self._emit_setting("extra_visual_ratio"), self._emit_setting("extra_visual_min_num")
+            if ratio > 0.0:
+                new_visual.append(self._extra_visual(lambda n_high: max(int(n_high * ratio), min_num)))
+            if self._emit_setting("extra_visual_num") > 0:
+                new_visual.append(self._extra_visual(lambda n_high: self._emit_setting("extra_visual_num")))
+        if new_hidden:
+            add = torch.cat(new_hidden, dim=0)
+            n_new = add.shape[0]
+            self._xyz = torch.cat((self._xyz, add), dim=0)
+            for name, t in self._fresh_hidden_state(n_new).items():
+                setattr(self, name, torch.cat((getattr(self, name), t), dim=0))
+            # the solver counts of ALL particles start over (gm_dynamics.py:962)
+            self._counts = torch.zeros((self._xyz.shape[0], 1), dtype=torch.float32, device=self.dev)
+            if hasattr(self, "_particle_id"):
+                ids = torch.arange(self._particle_id_max, self._particle_id_max + n_new, device=self.dev).unsqueeze(1)
+                self._particle_id = torch.cat((self._particle_id, ids), dim=0)
+                self._particle_id_max += n_new
+        if new_visual:
+            add = torch.cat(new_visual, dim=0)
+            self._visual_xyz = add if self._visual_xyz.shape[0] == 0 else torch.cat((self._visual_xyz, add), dim=0)

@@ -10,6 +10,8 @@ future_simulation.py:135-162:
     confirm_guess_hidden_particles()                gm_fluid.py:1160-1175
     update_visual_particles()                       gm_fluid.py:1197-1239
     remove_invalid_particles()                      gm_fluid.py:864-891
+    create_particles_* / prepare_emitter_points / emit_new_particles   gm_dynamics.py:510-609, 674-788, 844-976 (emitter.py: host-side
+                                                    set-up between frames, same particles as the reference under the same seeds)
 
 Same method names, same in-place state updates (attributes `_xyz, _estimate_xyz, _velocity, _force, _buoyancy, _imass,
 _counts, _visual_xyz`), no CPU fallback.  One solver iteration is 9 kernel launches (grid build, neighbour count, two
@@ -21,9 +23,10 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from .emitter import EmitterMixin
 
 
-class PBFSolver:
+class PBFSolver(EmitterMixin):
     """State + the reference's solver methods.  Constants default to gm_fluid.py:98-106 / FD/arguments/__init__.py."""
 
     def __init__(self, xyz, velocity=None, imass=None, visual_xyz=None, H=2.0, p0=1.5, k=10.0, KNN_K=100, secs=0.033, alpha=-0.2,
@@ -34,7 +37,7 @@ class PBFSolver:
             raise RuntimeError("PBFSolver runs on CUDA tensors only (no CPU fallback)")
         f = lambda t: torch.as_tensor(t, dtype=torch.float32).to(dev).contiguous().clone()
         self.dev = dev
-        self._xyz = f(xyz)
+        self._xyz = f(xyz) if xyz is not None else torch.zeros((0, 3), device=dev)   # None: start empty (create_particles_hidden / emitter)
         N = self._xyz.size(0)
         self._velocity = f(velocity) if velocity is not None else torch.zeros((N, 3), device=dev)
         self._imass = f(imass).reshape(N, 1) if imass is not None else torch.ones((N, 1), device=dev)

@@ -69,6 +69,17 @@ def test_compat_packages_export_the_reference_names():
     assert "distCUDA2" in open(os.path.join(compat, "simple_knn", "_C.py")).read()
 
 
+def test_emitter_method_surface():
+    """Particle creation / emission methods of the solver class against gm_dynamics.GaussianModel's (names, arguments, defaults)."""
+    import inspect
+    from fluidnexus_b200.solver import PBFSolver
+    for name, g in GOLD["emitter"].items():
+        sig = inspect.signature(getattr(PBFSolver, name))
+        pos = [p.name for p in sig.parameters.values()]
+        defaults = [repr(p.default) for p in sig.parameters.values() if p.default is not inspect.Parameter.empty]
+        assert pos == g["args"] and defaults == g["defaults"], (name, pos, defaults, g)
+
+
 def test_C_level_dropin_has_the_pybind_signatures():
     """`diff_gaussian_rasterization_chN._C` of the drop-in packages against the reference's pybind module: the functions ext.cpp
     binds, with the parameter names, order and count of their declarations in rasterize_points.h (parsed by tools/make_api_golden.py)."""

@@ -74,6 +74,9 @@ def main():
         "GaussianRasterizer.mark_visible": method_sig(r3, "GaussianRasterizer", "mark_visible"),
         "_C": pybind_sigs(os.path.join(REF, "submodules/gaussian_rasterization_ch3/rasterize_points.h"),
                           os.path.join(REF, "submodules/gaussian_rasterization_ch3/ext.cpp")),
+        "emitter": {m: method_sig(os.path.join(REF, "gaussian_splatting/gm_dynamics.py"), "GaussianModel", m) for m in
+                    ("create_particles_visual", "create_particles_hidden", "prepare_emitter_points", "prepare_emitter_future_first_points",
+                     "emit_new_particles")},
         "solver": {m: method_sig(gm, "GaussianModel", m) for m in
                    ("guess_hidden_particles", "project_gas_constraints", "confirm_guess_hidden_particles", "update_visual_particles",
                     "remove_invalid_particles", "update_solver_counts")},

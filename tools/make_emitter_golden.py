@@ -1,0 +1,102 @@
+"""Run in the build container (needs /root/reference): executes the reference's OWN particle creation / emission methods
+(FluidDynamics/gaussian_splatting/gm_dynamics.py: create_particles_visual, create_particles_hidden, prepare_emitter_points,
+prepare_emitter_future_first_points, emit_new_particles) on the CPU under fixed numpy / torch seeds and stores the settings, the
+emitter sites and the particle state after every call in tests/golden/pyref_emitter.npz.  tests/test_reference_emitter_golden.py
+replays the same calls through fluidnexus_b200/emitter.py under the same seeds and requires identical arrays.
+
+The model object is created without its constructor (GPU-only); `model_args` / `optim_args` are the reference's own
+arguments.ModelParams / OptimizationParams defaults (overridden per case below).  device="cuda" / .cuda() land on the CPU
+(tools/make_physics_golden.py:cuda_as_cpu)."""
+import contextlib
+import io
+import os
+import sys
+from argparse import ArgumentParser
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/FluidDynamics"
+OUT = os.path.join(ROOT, "tests", "golden", "pyref_emitter.npz")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from make_physics_golden import cuda_as_cpu, install_stubs  # noqa: E402
+
+MODEL_KEYS = ["init_visual_num_pts", "init_thick_visual_num_pts", "init_visual_radius_small_max", "init_visual_radius_max", "init_x_mid",
+              "init_visual_y_min", "init_visual_y_max", "init_z_mid", "init_visual_y_thick_min", "init_hidden_radius_max", "init_hidden_delta",
+              "init_hidden_y_min", "init_hidden_y_max", "emitter_hidden_delta", "emitter_visual_delta", "emitter_center_y_hidden",
+              "emitter_center_y_visual", "emitter_center_y_hidden_max", "emitter_center_y_visual_max", "emitter_visual_radius_ratio",
+              "emitter_hidden_radius_ratio"]
+OPTIM_KEYS = ["emit_ratio_hidden", "emit_ratio_visual", "extra_visual_ratio", "extra_visual_num", "extra_visual_y_min", "extra_visual_min_num",
+              "init_hidden_velocity", "alpha"]
+CASES = {
+    # the reference's defaults (arguments/__init__.py): emit ratio 1.32 (one whole copy + a random 32 %), no extra particles
+    "default": dict(seed=7, is_future=False, optim={"alpha": -0.2}, model={}),
+    # everything switched on: several whole copies, a fraction below one, both kinds of extra visual particles, an initial velocity
+    "busy": dict(seed=11, is_future=True, model={"init_thick_visual_num_pts": 0, "init_visual_num_pts": 400},
+                 optim={"alpha": -0.35, "emit_ratio_hidden": 2.5, "emit_ratio_visual": 0.4, "extra_visual_ratio": 0.1, "extra_visual_min_num": 5,
+                        "extra_visual_num": 7, "extra_visual_y_min": 0.05, "init_hidden_velocity": 3.0}),
+}
+STATE = ["_xyz", "_estimate_xyz", "_buoyancy", "_force", "_velocity", "_imass", "_counts", "_particle_id", "_visual_xyz"]
+
+
+def snapshot(out, tag, gm):
+    for k in STATE:
+        out[f"{tag}{k}"] = getattr(gm, k).detach().cpu().numpy().copy()
+
+
+def main():
+    install_stubs()
+    import types
+    ply = types.ModuleType("plyfile")          # imported at gm_dynamics.py:7 for load_ply only; not installed here, not used by these methods
+    ply.PlyData, ply.PlyElement = object, object
+    sys.modules.setdefault("plyfile", ply)
+    sys.path.insert(0, REF)
+    import arguments
+    from gaussian_splatting.gm_dynamics import GaussianModel as GM
+    out = {}
+    for case, spec in CASES.items():
+        margs, oargs = arguments.ModelParams(ArgumentParser()), arguments.OptimizationParams(ArgumentParser())
+        for k, v in spec["model"].items():
+            setattr(margs, k, v)
+        for k, v in spec["optim"].items():
+            setattr(oargs, k, v)
+        for k in MODEL_KEYS:
+            out[f"{case}/model/{k}"] = getattr(margs, k)
+        for k in OPTIM_KEYS:
+            out[f"{case}/optim/{k}"] = getattr(oargs, k)
+        out[f"{case}/seed"], out[f"{case}/is_future"] = spec["seed"], spec["is_future"]
+        np.random.seed(spec["seed"])
+        torch.manual_seed(spec["seed"])
+        gm = object.__new__(GM)
+        with cuda_as_cpu(), contextlib.redirect_stdout(io.StringIO()):
+            # what setup_constants (gm_dynamics.py:76-160) would set, for the attributes these methods read
+            gm._gravity = torch.tensor([0.0, -9.8, 0.0], dtype=torch.float, device="cuda").reshape((1, 3))
+            gm.scale_factor, gm.emit_counter = 100.0, 0
+            for k in OPTIM_KEYS:
+                setattr(gm, k, getattr(oargs, k))
+            gm.create_particles_visual(margs)
+            out[f"{case}/visual_created"] = gm._visual_xyz.numpy().copy()
+            gm.detach_visual_and_scale()                   # the entries scale the visual particles before the first emission
+            gm.create_particles_hidden(margs)
+            gm.prepare_emitter_points(margs, is_future=spec["is_future"])
+            gm.prepare_emitter_future_first_points(margs)
+            for k in ("visual_emitter_points", "hidden_emitter_points", "visual_emitter_first_points", "hidden_emitter_first_points"):
+                out[f"{case}/{k}"] = getattr(gm, k).numpy().copy()
+            snapshot(out, f"{case}/created", gm)
+            for it in range(3):
+                gm.emit_new_particles()
+                snapshot(out, f"{case}/emit{it}", gm)
+            gm.emit_new_particles(future_time_index=0)
+            snapshot(out, f"{case}/future0", gm)
+            out[f"{case}/emit_counter"] = gm.emit_counter
+        print(case, "visual", out[f"{case}/visual_created"].shape, "hidden", out[f"{case}/created_xyz"].shape, "sites",
+              out[f"{case}/visual_emitter_points"].shape, out[f"{case}/hidden_emitter_points"].shape, "after 3 ticks",
+              out[f"{case}/emit2_xyz"].shape, out[f"{case}/emit2_visual_xyz"].shape, "future", out[f"{case}/future0_xyz"].shape)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()
