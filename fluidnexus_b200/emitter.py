@@ -9,6 +9,7 @@ future_simulation.py:102,132):
     prepare_emitter_points(model_args, is_future=False)       gm_dynamics.py:674-745   discs of emitter sites
     prepare_emitter_future_first_points(model_args)           gm_dynamics.py:747-788   stacked discs for the first future frames
     emit_new_particles(future_time_index=-1)                  gm_dynamics.py:844-976   append one tick's worth of new particles
+    create_rigid_body()                                       gm_dynamics.py:612-672   surface samples of the cuboid / sphere / cylinder
 
 This is plain torch / numpy bookkeeping (no kernels): a few hundred points per frame.  What matters is that a run seeded like the
 reference's produces the SAME particles: the sites are enumerated in the reference's order (x outermost, then y, then z), and the
@@ -107,6 +108,36 @@ class EmitterMixin:
         self._particle_id = torch.arange(n, device=self.dev).unsqueeze(1)
         self._particle_id_max = n
         self.hidden_particles_created = True
+
+    # -- rigid body -----------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def create_rigid_body(self):
+        """Surface samples of the rigid body (gm_dynamics.py:612-672) around `rigid_body_center` (scaled units): the shell of a
+        `rigid_cuboid_num` lattice of pitch `rigid_particle_diameter`, `rigid_sphere_num` uniformly random points on a sphere, or
+        `rigid_cylinder_num` = (around, along) points on a cylinder about the z axis.  Reads the attributes of the reference's
+        setup_constants (`rigid_body`, `rigid_particle_diameter`, ...); writes `_rigid_xyz` [n,3] and `_rigid_imass` [n,1] = 0."""
+        diam = self.rigid_particle_diameter
+        if self.rigid_body == "cuboid":
+            nx, ny, nz = self.rigid_cuboid_num
+            axes = [np.arange(n) * diam - n // 2 * diam for n in (nx, ny, nz)]
+            I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+            shell = (I == 0) | (I == nx - 1) | (J == 0) | (J == ny - 1) | (K == 0) | (K == nz - 1)   # faces only, no interior
+            pts = np.stack([axes[0][I[shell]], axes[1][J[shell]], axes[2][K[shell]]], axis=1)
+        elif self.rigid_body == "sphere":
+            n, radius = self.rigid_sphere_num, self.rigid_sphere_radius
+            phi = np.random.uniform(0, 2 * np.pi, n)
+            theta = np.arccos(np.random.uniform(-1, 1, n))           # uniform in cos(theta): uniform on the sphere
+            pts = np.vstack((radius * np.sin(theta) * np.cos(phi), radius * np.sin(theta) * np.sin(phi), radius * np.cos(theta))).T
+        elif self.rigid_body == "cylinder":
+            around, along = self.rigid_cylinder_num
+            theta = np.repeat(np.arange(around) * 2 * np.pi / around, along)
+            z = np.tile((np.arange(along) - along / 2) * diam, around)
+            pts = np.stack([self.rigid_cylinder_radius * np.cos(theta), self.rigid_cylinder_radius * np.sin(theta), z], axis=1)
+        else:
+            raise ValueError(f"rigid_body must be cuboid, sphere or cylinder (got {self.rigid_body!r})")
+        center = torch.as_tensor(self.rigid_body_center, dtype=torch.float32).to(self.dev)
+        self._rigid_xyz = _f32(pts, self.dev) + center
+        self._rigid_imass = torch.zeros((pts.shape[0], 1), dtype=torch.float32, device=self.dev)
 
     # -- emitter sites --------------------------------------------------------------------------------------------------------
     def _emitter_geometry(self, model_args):

@@ -154,6 +154,23 @@ class PBFSolver(EmitterMixin):
             prm = [float(cylinder_radius), cylinder_num[1] * 2.0 * particle_radius / 2.0, 0.0]
         self._rigid_prm = (C.c_float * 3)(*prm)
 
+    def setup_rigid_body(self, optim_args):
+        """The rigid-body block of the reference's setup_constants (gm_dynamics.py:139-157; fields of FD/arguments/__init__.py:423-431)
+        followed by create_rigid_body(): reads `rigid_body`, `rigid_body_center` (render units), `rigid_particle_radius`,
+        `rigid_cuboid_num`, `rigid_sphere_radius` / `_num`, `rigid_cylinder_radius` / `_num` from `optim_args`, samples the body's
+        surface (emitter.py) and registers it for the projections."""
+        self.rigid_body = optim_args.rigid_body
+        self.rigid_particle_radius = float(optim_args.rigid_particle_radius)
+        self.rigid_particle_diameter = 2 * self.rigid_particle_radius
+        self.rigid_body_center = torch.tensor(optim_args.rigid_body_center, dtype=torch.float32) * self.scale_factor
+        self.rigid_cuboid_num = list(optim_args.rigid_cuboid_num)
+        self.rigid_sphere_radius, self.rigid_sphere_num = float(optim_args.rigid_sphere_radius), int(optim_args.rigid_sphere_num)
+        self.rigid_cylinder_radius, self.rigid_cylinder_num = float(optim_args.rigid_cylinder_radius), list(optim_args.rigid_cylinder_num)
+        self.create_rigid_body()
+        self.set_rigid_body(self.rigid_body, self.rigid_body_center.tolist(), self._rigid_xyz, cuboid_num=self.rigid_cuboid_num,
+                            particle_radius=self.rigid_particle_radius, sphere_radius=self.rigid_sphere_radius,
+                            cylinder_radius=self.rigid_cylinder_radius, cylinder_num=self.rigid_cylinder_num)
+
     def _rigid_project(self, pts, cap):
         M, N = self._rigid_xyz.size(0), pts.size(0)
         if N == 0 or M == 0:

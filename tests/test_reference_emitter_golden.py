@@ -90,8 +90,56 @@ def test_emission_bookkeeping():
     assert bool((np.diff(s[:, 0]) >= 0).all()) and set(np.unique(s[:, 1])) == {0.0, 0.5}
 
 
+@pytest.mark.parametrize("kind", ["cuboid", "sphere", "cylinder"])
+def test_rigid_body_samples_equal_the_reference(kind):
+    """create_rigid_body (gm_dynamics.py:612-672): the same surface samples, in the same order, as the reference's own method."""
+    np.random.seed(21)
+    p = _Particles(alpha=-0.2)
+    p.rigid_body, p.rigid_particle_diameter = kind, 2 * 0.25
+    prefix = f"rigid/{kind}/"
+    for k in G.files:
+        if k.startswith(prefix) and k[len(prefix):] not in ("xyz", "imass"):
+            v = G[k]
+            setattr(p, k[len(prefix):], v.tolist() if v.ndim else v.item())
+    p.rigid_body_center = torch.tensor([0.34, 0.3, -0.225]) * 100.0
+    p.create_rigid_body()
+    assert np.array_equal(p._rigid_xyz.numpy(), G[prefix + "xyz"]) and np.array_equal(p._rigid_imass.numpy(), G[prefix + "imass"])
+    if kind == "cuboid":                                   # 5 x 4 x 6 lattice without its 3 x 2 x 4 interior
+        assert p._rigid_xyz.shape[0] == 5 * 4 * 6 - 3 * 2 * 4
+    with pytest.raises(ValueError):
+        p.rigid_body = "torus"
+        p.create_rigid_body()
+
+
 def test_solver_class_carries_the_emitter():
     from fluidnexus_b200.solver import PBFSolver
     for name in ("create_particles_visual", "create_particles_hidden", "prepare_emitter_points", "prepare_emitter_future_first_points",
-                 "emit_new_particles"):
+                 "emit_new_particles", "create_rigid_body"):
         assert getattr(PBFSolver, name) is getattr(EmitterMixin, name), name
+
+
+@pytest.mark.parametrize("kind", ["cuboid", "sphere", "cylinder"])
+def test_setup_rigid_body_registers_the_sampled_body(kind):
+    """PBFSolver.setup_rigid_body = the rigid block of setup_constants + create_rigid_body + set_rigid_body: the half extents it hands
+    to fnx_rigid_project are those of the reference's check_inside_rigid_body (gm_dynamics.py:1138-1170).  The solver object is made
+    without its (CUDA-only) constructor; nothing here launches a kernel."""
+    from fluidnexus_b200.solver import PBFSolver
+    sol = object.__new__(PBFSolver)
+    sol.dev, sol.scale_factor = torch.device("cpu"), 100.0
+    oargs = types.SimpleNamespace(rigid_body=kind, rigid_body_center=[0.34, 0.5, -0.225], rigid_particle_radius=0.25, rigid_cuboid_num=[5, 10, 55],
+                                  rigid_sphere_radius=5, rigid_sphere_num=1000, rigid_cylinder_radius=4, rigid_cylinder_num=[50, 50])
+    np.random.seed(3)
+    sol.setup_rigid_body(oargs)
+    n = {"cuboid": 5 * 10 * 55 - 3 * 8 * 53, "sphere": 1000, "cylinder": 50 * 50}[kind]
+    assert sol._rigid_xyz.shape == (n, 3) and sol._rigid_imass.shape == (n, 1) and sol.rigid_body == kind
+    assert np.allclose(list(sol._rigid_center), [34.0, 50.0, -22.5])
+    want = {"cuboid": [5 * 0.5 / 2, 10 * 0.5 / 2, 55 * 0.5 / 2], "sphere": [5.0, 0.0, 0.0], "cylinder": [4.0, 50 * 0.5 / 2, 0.0]}[kind]
+    assert np.allclose(list(sol._rigid_prm), want)
+    # every sample lies on the body registered for the inside test (cuboid: lattice offset by -n//2, so within one pitch of the box)
+    d = (sol._rigid_xyz - torch.tensor([34.0, 50.0, -22.5])).abs()
+    if kind == "sphere":
+        assert torch.allclose(d.norm(dim=1), torch.full((n,), 5.0), atol=1e-4)
+    elif kind == "cylinder":
+        assert torch.allclose(d[:, :2].norm(dim=1), torch.full((n,), 4.0), atol=1e-4) and float(d[:, 2].max()) <= 50 * 0.5 / 2 + 1e-4
+    else:
+        assert bool((d <= torch.tensor(want) + 0.5 + 1e-4).all())

@@ -94,6 +94,20 @@ def main():
         print(case, "visual", out[f"{case}/visual_created"].shape, "hidden", out[f"{case}/created_xyz"].shape, "sites",
               out[f"{case}/visual_emitter_points"].shape, out[f"{case}/hidden_emitter_points"].shape, "after 3 ticks",
               out[f"{case}/emit2_xyz"].shape, out[f"{case}/emit2_visual_xyz"].shape, "future", out[f"{case}/future0_xyz"].shape)
+    # ---- create_rigid_body (gm_dynamics.py:612-672) for the three body kinds ----
+    for kind, attrs in {"cuboid": dict(rigid_cuboid_num=[5, 4, 6]), "sphere": dict(rigid_sphere_num=300, rigid_sphere_radius=6.5),
+                        "cylinder": dict(rigid_cylinder_radius=4.0, rigid_cylinder_num=[24, 9])}.items():
+        np.random.seed(21)
+        gm = object.__new__(GM)
+        gm.rigid_body, gm.rigid_particle_diameter = kind, 2 * 0.25
+        for k, v in attrs.items():
+            setattr(gm, k, v)
+            out[f"rigid/{kind}/{k}"] = np.asarray(v)
+        with cuda_as_cpu():
+            gm.rigid_body_center = torch.tensor([0.34, 0.3, -0.225], dtype=torch.float, device="cuda") * 100.0
+            gm.create_rigid_body()
+        out[f"rigid/{kind}/xyz"], out[f"rigid/{kind}/imass"] = gm._rigid_xyz.numpy().copy(), gm._rigid_imass.numpy().copy()
+        print("rigid", kind, out[f"rigid/{kind}/xyz"].shape)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
