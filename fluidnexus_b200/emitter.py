@@ -10,6 +10,7 @@ future_simulation.py:102,132):
     prepare_emitter_future_first_points(model_args)           gm_dynamics.py:747-788   stacked discs for the first future frames
     emit_new_particles(future_time_index=-1)                  gm_dynamics.py:844-976   append one tick's worth of new particles
     create_rigid_body()                                       gm_dynamics.py:612-672   surface samples of the cuboid / sphere / cylinder
+    prepare_{hidden,visual,future_visual,rigid_body}_particles_for_rendering()   gm_dynamics.py:1636-1700   constant raw appearance
 
 This is plain torch / numpy bookkeeping (no kernels): a few hundred points per frame.  What matters is that a run seeded like the
 reference's produces the SAME particles: the sites are enumerated in the reference's order (x outermost, then y, then z), and the
@@ -138,6 +139,43 @@ class EmitterMixin:
         center = torch.as_tensor(self.rigid_body_center, dtype=torch.float32).to(self.dev)
         self._rigid_xyz = _f32(pts, self.dev) + center
         self._rigid_imass = torch.zeros((pts.shape[0], 1), dtype=torch.float32, device=self.dev)
+
+    # -- raw attributes the render pipes read for particle sets that have no trained appearance ------------------------------------
+    # (gm_dynamics.py:1636-1700; constants of setup_constants :158-160: colour 0.7, log-scale -5.9, opacity 0.1; rigid body: 0.9 / -5.5 / 0.3)
+    constant_color, constant_scale, constant_opacity = 0.7, -5.9, 0.1
+
+    def _constant_appearance(self, n, color, log_scale, opacity):
+        """Raw (pre-activation) colour [n,1], log-scales [n,3], identity quaternions [n,4], opacity logits [n,1]."""
+        full = lambda cols, v: torch.zeros((n, cols), dtype=torch.float32, device=self.dev) + v
+        rot = full(4, 0.0)
+        rot[:, 0] = 1.0
+        op = opacity * torch.ones((n, 1), dtype=torch.float32, device=self.dev)
+        return full(1, color), full(3, log_scale), rot, torch.log(op / (1 - op))          # inv_sigmoid, general_utils.py:10-11
+
+    def prepare_hidden_particles_for_rendering(self):
+        assert self._xyz.shape[0] > 0, "No hidden particles to render"
+        self._color_dummy, self._scales_dummy, self._rotation_dummy, self._opacity_dummy = self._constant_appearance(
+            self._xyz.shape[0], self.constant_color, self.constant_scale, self.constant_opacity)
+
+    def prepare_visual_particles_for_rendering(self):
+        assert self._visual_xyz.shape[0] > 0, "No visual particles to render"
+        self._visual_color, self._visual_scales, self._visual_rotation, self._visual_opacity = self._constant_appearance(
+            self._visual_xyz.shape[0], self.constant_color, self.constant_scale, self.constant_opacity)
+
+    def prepare_future_visual_particles_for_rendering(self, use_level_two_future=False):
+        """Future simulation: particles emitted since the last call get the constant appearance, the earlier ones keep theirs (the
+        level-two result) when use_level_two_future, else all are reset."""
+        if not use_level_two_future:
+            return self.prepare_visual_particles_for_rendering()
+        new = self._constant_appearance(self._visual_xyz.shape[0] - self._visual_color.shape[0], self.constant_color, self.constant_scale,
+                                        self.constant_opacity)
+        for name, t in zip(("_visual_color", "_visual_scales", "_visual_rotation", "_visual_opacity"), new):
+            setattr(self, name, torch.cat((getattr(self, name), t), dim=0))
+
+    def prepare_rigid_body_particles_for_rendering(self):
+        assert self._rigid_xyz.shape[0] > 0, "No rigid body particles to render"
+        self._rigid_color, self._rigid_scales, self._rigid_rotation, self._rigid_opacity = self._constant_appearance(
+            self._rigid_xyz.shape[0], 0.9, -5.5, 0.3)
 
     # -- emitter sites --------------------------------------------------------------------------------------------------------
     def _emitter_geometry(self, model_args):

@@ -63,6 +63,18 @@ def test_creation_and_emission_reproduce_the_reference_particle_for_particle(cas
     p.emit_new_particles(future_time_index=0)
     _same(p, case, "future0")
     assert p.emit_counter == int(G[f"{case}/emit_counter"]) == 4
+    # constant raw appearance the render pipes read for these sets (gm_dynamics.py:1636-1700)
+    p.prepare_hidden_particles_for_rendering()
+    p.prepare_visual_particles_for_rendering()
+    for k in ("_color_dummy", "_scales_dummy", "_rotation_dummy", "_opacity_dummy", "_visual_color", "_visual_scales", "_visual_rotation",
+              "_visual_opacity"):
+        assert np.array_equal(getattr(p, k).numpy(), G[f"{case}/render{k}"]), k
+    p._visual_color = p._visual_color * 0.5 + 0.1
+    p.emit_new_particles()
+    p.prepare_future_visual_particles_for_rendering(True)               # earlier particles keep theirs, new ones get the constants
+    for k in ("_visual_color", "_visual_scales", "_visual_rotation", "_visual_opacity"):
+        assert np.array_equal(getattr(p, k).numpy(), G[f"{case}/render_future{k}"]), k
+    assert p._visual_color.shape[0] == p._visual_xyz.shape[0]
 
 
 def test_emission_bookkeeping():
@@ -98,12 +110,15 @@ def test_rigid_body_samples_equal_the_reference(kind):
     p.rigid_body, p.rigid_particle_diameter = kind, 2 * 0.25
     prefix = f"rigid/{kind}/"
     for k in G.files:
-        if k.startswith(prefix) and k[len(prefix):] not in ("xyz", "imass"):
+        if k.startswith(prefix) and k[len(prefix):] not in ("xyz", "imass") and not k[len(prefix):].startswith("render"):
             v = G[k]
             setattr(p, k[len(prefix):], v.tolist() if v.ndim else v.item())
     p.rigid_body_center = torch.tensor([0.34, 0.3, -0.225]) * 100.0
     p.create_rigid_body()
     assert np.array_equal(p._rigid_xyz.numpy(), G[prefix + "xyz"]) and np.array_equal(p._rigid_imass.numpy(), G[prefix + "imass"])
+    p.prepare_rigid_body_particles_for_rendering()
+    for k in ("_rigid_color", "_rigid_scales", "_rigid_rotation", "_rigid_opacity"):
+        assert np.array_equal(getattr(p, k).numpy(), G[prefix + "render" + k]), k
     if kind == "cuboid":                                   # 5 x 4 x 6 lattice without its 3 x 2 x 4 interior
         assert p._rigid_xyz.shape[0] == 5 * 4 * 6 - 3 * 2 * 4
     with pytest.raises(ValueError):

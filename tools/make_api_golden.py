@@ -76,7 +76,9 @@ def main():
                           os.path.join(REF, "submodules/gaussian_rasterization_ch3/ext.cpp")),
         "emitter": {m: method_sig(os.path.join(REF, "gaussian_splatting/gm_dynamics.py"), "GaussianModel", m) for m in
                     ("create_particles_visual", "create_particles_hidden", "prepare_emitter_points", "prepare_emitter_future_first_points",
-                     "emit_new_particles")},
+                     "emit_new_particles", "create_rigid_body", "prepare_hidden_particles_for_rendering",
+                     "prepare_visual_particles_for_rendering", "prepare_future_visual_particles_for_rendering",
+                     "prepare_rigid_body_particles_for_rendering")},
         "solver": {m: method_sig(gm, "GaussianModel", m) for m in
                    ("guess_hidden_particles", "project_gas_constraints", "confirm_guess_hidden_particles", "update_visual_particles",
                     "remove_invalid_particles", "update_solver_counts")},

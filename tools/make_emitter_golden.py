@@ -91,6 +91,18 @@ def main():
             gm.emit_new_particles(future_time_index=0)
             snapshot(out, f"{case}/future0", gm)
             out[f"{case}/emit_counter"] = gm.emit_counter
+            # ---- constant raw appearance for rendering (gm_dynamics.py:1636-1700) ----
+            gm.constant_color, gm.constant_scale, gm.constant_opacity = 0.7, -5.9, 0.1        # setup_constants :158-160
+            gm.prepare_hidden_particles_for_rendering()
+            gm.prepare_visual_particles_for_rendering()
+            for k in ("_color_dummy", "_scales_dummy", "_rotation_dummy", "_opacity_dummy", "_visual_color", "_visual_scales", "_visual_rotation",
+                      "_visual_opacity"):
+                out[f"{case}/render{k}"] = getattr(gm, k).numpy().copy()
+            gm._visual_color = gm._visual_color * 0.5 + 0.1          # stand-in for a level-two result on the existing particles
+            gm.emit_new_particles()
+            gm.prepare_future_visual_particles_for_rendering(True)
+            for k in ("_visual_color", "_visual_scales", "_visual_rotation", "_visual_opacity"):
+                out[f"{case}/render_future{k}"] = getattr(gm, k).numpy().copy()
         print(case, "visual", out[f"{case}/visual_created"].shape, "hidden", out[f"{case}/created_xyz"].shape, "sites",
               out[f"{case}/visual_emitter_points"].shape, out[f"{case}/hidden_emitter_points"].shape, "after 3 ticks",
               out[f"{case}/emit2_xyz"].shape, out[f"{case}/emit2_visual_xyz"].shape, "future", out[f"{case}/future0_xyz"].shape)
@@ -107,6 +119,10 @@ def main():
             gm.rigid_body_center = torch.tensor([0.34, 0.3, -0.225], dtype=torch.float, device="cuda") * 100.0
             gm.create_rigid_body()
         out[f"rigid/{kind}/xyz"], out[f"rigid/{kind}/imass"] = gm._rigid_xyz.numpy().copy(), gm._rigid_imass.numpy().copy()
+        with cuda_as_cpu():
+            gm.prepare_rigid_body_particles_for_rendering()
+        for k in ("_rigid_color", "_rigid_scales", "_rigid_rotation", "_rigid_opacity"):
+            out[f"rigid/{kind}/render{k}"] = getattr(gm, k).numpy().copy()
         print("rigid", kind, out[f"rigid/{kind}/xyz"].shape)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
