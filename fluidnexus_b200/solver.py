@@ -194,6 +194,72 @@ class PBFSolver(EmitterMixin):
         """Same for the visual particles; the reference's radius() call keeps torch_cluster's default cap of 32."""
         return self._rigid_project(self._visual_xyz, 32)
 
+    # -- per-frame checkpoints in the reference's on-disk layout (gm_fluid.py:1653-1911; fluidnexus_b200/io.py) ------------------
+    _SCALAR_ATTRS = dict(secs="_secs", particle_id_max="_particle_id_max")   # scalar key -> attribute, where the names differ
+
+    def _scalar_values(self):
+        """The dictionary save_hidden writes to frame_XXX_scalar_values.json (gm_fluid.py:1694-1716), from the solver's attributes;
+        counters this class does not keep (total_*_iterations, remove_out_boundary) are written as 0 / False unless set."""
+        from . import io as IO
+        fallback = dict(remove_out_boundary=False, emit_counter=0, total_iterations=0, total_sim_iterations=0, total_tb_log_iterations=0,
+                        particle_id_max=int(self._xyz.shape[0]), emit_ratio_hidden=self._emit_setting("emit_ratio_hidden"),
+                        emit_ratio_visual=self._emit_setting("emit_ratio_visual"))
+        out = {}
+        for k in IO.SCALAR_KEYS:
+            attr = self._SCALAR_ATTRS.get(k, k)
+            out[k] = getattr(self, attr) if hasattr(self, attr) else fallback[k]
+        return out
+
+    @torch.no_grad()
+    def save_hidden(self, checkpoint_path, frame_idx):
+        from . import io as IO
+        N = self._xyz.shape[0]
+        state = {k: getattr(self, "_" + k) for k in ("xyz", "estimate_xyz", "buoyancy", "force", "velocity", "imass", "counts")}
+        state["gravity"] = torch.tensor([float(c) for c in self._gravity], dtype=torch.float32).reshape(1, 3)
+        state["particle_id"] = getattr(self, "_particle_id", None)
+        if state["particle_id"] is None:
+            state["particle_id"] = torch.arange(N).unsqueeze(1)
+        IO.save_hidden(checkpoint_path, frame_idx, state, self._scalar_values())
+
+    @torch.no_grad()
+    def load_hidden(self, checkpoint_path, frame_idx):
+        """Restores the hidden-particle state and the scalars the reference restores (gm_fluid.py:1811-1884)."""
+        from . import io as IO
+        state, scal = IO.load_hidden(checkpoint_path, frame_idx, defaults=dict(emit_ratio_hidden=self._emit_setting("emit_ratio_hidden"),
+                                                                              emit_ratio_visual=self._emit_setting("emit_ratio_visual")))
+        for k in ("xyz", "estimate_xyz", "buoyancy", "force", "velocity", "imass", "counts"):
+            setattr(self, "_" + k, torch.from_numpy(state[k]).to(self.dev).contiguous())
+        self._gravity = (C.c_float * 3)(*[float(c) for c in state["gravity"].reshape(-1)])
+        self._particle_id = torch.from_numpy(state["particle_id"].astype("int64")).to(self.dev).reshape(-1, 1)
+        self.scale_factor, self.buoyancy_decay_rate = float(scal["scale_factor"]), float(scal["buoyancy_decay_rate"])
+        self.remove_out_boundary = bool(scal["remove_out_boundary"])
+        self._secs, self.alpha, self.k, self.p0 = float(scal["secs"]), float(scal["alpha"]), float(scal["k"]), float(scal["p0"])
+        self.buoyancy_max_y, self.min_neighbors = float(scal["buoyancy_max_y"]), int(scal["min_neighbors"])
+        self.emit_ratio_hidden, self.emit_ratio_visual = scal["emit_ratio_hidden"], scal["emit_ratio_visual"]
+        self.emit_counter, self.total_iterations = int(scal["emit_counter"]), int(scal["total_iterations"])
+        self.total_sim_iterations, self.total_tb_log_iterations = int(scal["total_sim_iterations"]), int(scal["total_tb_log_iterations"])
+        self._particle_id_max = int(scal["particle_id_max"]) or int(self._xyz.shape[0])
+        return scal
+
+    @torch.no_grad()
+    def save_visual(self, checkpoint_path, frame_idx, scale=True):
+        from . import io as IO
+        IO.save_visual(checkpoint_path, frame_idx, {k: getattr(self, "_" + k) for k in IO.VISUAL_ARRAYS}, self.scale_factor, scale=scale)
+
+    @torch.no_grad()
+    def load_visual(self, checkpoint_path, frame_idx, scale=True):
+        from . import io as IO
+        for k, a in IO.load_visual(checkpoint_path, frame_idx, self.scale_factor, scale=scale).items():
+            setattr(self, "_" + k, torch.from_numpy(a).to(self.dev).contiguous())
+
+    def save_all(self, checkpoint_path, frame_idx):
+        self.save_hidden(checkpoint_path, frame_idx)
+        self.save_visual(checkpoint_path, frame_idx)
+
+    def load_all(self, checkpoint_path, frame_idx):
+        self.load_hidden(checkpoint_path, frame_idx)
+        self.load_visual(checkpoint_path, frame_idx)
+
     # -- one simulation tick as the entries run it ---------------------------------------------------------------
     @torch.no_grad()
     def tick(self, solver_iterations=3, stable=False, use_wind=False, count_first=False):
