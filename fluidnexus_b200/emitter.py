@@ -110,6 +110,14 @@ class EmitterMixin:
         self._particle_id_max = n
         self.hidden_particles_created = True
 
+    @torch.no_grad()
+    def remove_invisible_bottom_visual_particles(self):
+        """Drops the visual particles below y = -0.017 (render units), i.e. under the visible volume (gm_dynamics.py:1062-1070; called
+        once before the first future frame).  Only the positions are filtered, like the reference."""
+        keep = self._visual_xyz[:, 1] >= -0.017 * self.scale_factor
+        if int(keep.sum()) < keep.shape[0]:
+            self._visual_xyz = self._visual_xyz[keep]
+
     # -- rigid body -----------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def create_rigid_body(self):

@@ -260,6 +260,38 @@ class PBFSolver(EmitterMixin):
         self.load_hidden(checkpoint_path, frame_idx)
         self.load_visual(checkpoint_path, frame_idx)
 
+    # -- future prediction: the loop of FD/entries_fluid_nexus/future_simulation.py:118-175 ---------------------------------------
+    @staticmethod
+    def future_p0(p0_recon, p0_future, future_time_index, decay_frames):
+        """Rest density of future frame t: decays linearly from the reconstruction's p0 to p0_future over `decay_frames` frames
+        (future_simulation.py:120)."""
+        return p0_future + (p0_recon - p0_future) * (1 - min(1, future_time_index / decay_frames))
+
+    def predict(self, future_pred_frames, first_frame_index=0, solver_iterations_future=3, p0_future=1.5, decay_frames_future_p0=30,
+                wind_since=-1, use_level_two_in_future=False, on_frame=None):
+        """Simulates `future_pred_frames` frames past the last reconstructed one, in the reference's order per frame: p0 schedule,
+        remove_invalid_particles, (first frame) remove_invisible_bottom_visual_particles, emit_new_particles, guess_hidden_particles
+        (wind from frame `wind_since` on), `solver_iterations_future` x project_gas_constraints, confirm_guess_hidden_particles,
+        update_visual_particles, prepare_future_visual_particles_for_rendering; then `on_frame(self, future_frame_index)` -- where
+        the script renders and saves.  Defaults: FD/arguments/__init__.py:310,330,332,418.  Emitter sites must have been prepared
+        (prepare_emitter_points(model_args, is_future=True))."""
+        p0_recon = self.p0
+        for t in range(int(future_pred_frames)):
+            frame = first_frame_index + t
+            self.p0 = self.future_p0(p0_recon, p0_future, t, decay_frames_future_p0)
+            self.remove_invalid_particles()
+            if t == 0:
+                self.remove_invisible_bottom_visual_particles()
+            self.emit_new_particles()
+            self.guess_hidden_particles(use_wind=wind_since >= 0 and frame >= wind_since)
+            for _ in range(int(solver_iterations_future)):
+                self.project_gas_constraints()
+            self.confirm_guess_hidden_particles()
+            self.update_visual_particles()
+            self.prepare_future_visual_particles_for_rendering(use_level_two_in_future)
+            if on_frame is not None:
+                on_frame(self, frame)
+
     # -- one simulation tick as the entries run it ---------------------------------------------------------------
     @torch.no_grad()
     def tick(self, solver_iterations=3, stable=False, use_wind=False, count_first=False):

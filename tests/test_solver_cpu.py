@@ -65,3 +65,35 @@ def test_solver_class_refuses_cpu():
     from fluidnexus_b200.solver import PBFSolver
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         PBFSolver(np.zeros((4, 3), np.float32), device="cpu")
+
+
+def test_predict_runs_the_future_simulation_loop_in_the_reference_order():
+    """PBFSolver.predict = the per-frame sequence of future_simulation.py:118-175 (kernel-calling methods replaced by recorders: no
+    GPU here), with the p0 decay schedule of :120 and wind from `wind_since` on."""
+    import torch
+    from fluidnexus_b200.solver import PBFSolver
+    sol = object.__new__(PBFSolver)
+    sol.dev, sol.scale_factor, sol.p0 = torch.device("cpu"), 100.0, 2.0
+    sol._visual_xyz = torch.tensor([[0.0, -5.0, 0.0], [0.0, 3.0, 0.0], [1.0, -1.7, 0.0]])      # y = -5 lies below -0.017 * 100
+    sol._visual_color = torch.zeros((0, 1))
+    log = []
+    for name in ("remove_invalid_particles", "emit_new_particles", "project_gas_constraints", "confirm_guess_hidden_particles",
+                 "update_visual_particles"):
+        setattr(sol, name, (lambda n: lambda *a, **k: log.append(n))(name))
+    sol.guess_hidden_particles = lambda stable=False, use_wind=False: log.append(("guess", use_wind))
+    sol.prepare_future_visual_particles_for_rendering = lambda lvl2=False: log.append(("prepare", lvl2))
+    frames = []
+    sol.predict(3, first_frame_index=120, solver_iterations_future=2, p0_future=1.5, decay_frames_future_p0=4, wind_since=121,
+                use_level_two_in_future=True, on_frame=lambda s, f: frames.append((f, s.p0, s._visual_xyz.shape[0])))
+    per_frame = ["remove_invalid_particles", "emit_new_particles", ("guess", None), "project_gas_constraints", "project_gas_constraints",
+                 "confirm_guess_hidden_particles", "update_visual_particles", ("prepare", True)]
+    assert len(log) == 3 * len(per_frame)
+    for t in range(3):
+        got = log[t * len(per_frame):(t + 1) * len(per_frame)]
+        want = [("guess", 120 + t >= 121) if x == ("guess", None) else x for x in per_frame]
+        assert got == want, (t, got)
+    # p0: 2.0 -> 1.5 linearly over 4 frames; the bottom particle is dropped before the first frame only
+    assert [f for f, _, _ in frames] == [120, 121, 122]
+    assert [round(p, 6) for _, p, _ in frames] == [2.0, 1.875, 1.75]
+    assert [n for _, _, n in frames] == [2, 2, 2]
+    assert PBFSolver.future_p0(2.0, 1.5, 10, 4) == 1.5
