@@ -134,8 +134,9 @@ class PBFSolver(EmitterMixin):
                                                     degree.data_ptr(), self._st()))
         mask = degree[:N] >= self.min_neighbors
         if not bool(mask.all()):
-            for name in ("_xyz", "_estimate_xyz", "_buoyancy", "_force", "_velocity", "_imass", "_counts"):
-                setattr(self, name, getattr(self, name)[mask].contiguous())
+            for name in ("_xyz", "_estimate_xyz", "_buoyancy", "_force", "_velocity", "_imass", "_counts", "_particle_id"):
+                if hasattr(self, name):      # (_particle_id exists once particles were created / emitted / loaded here)
+                    setattr(self, name, getattr(self, name)[mask].contiguous())
 
     # -- rigid coupling (gm_fluid.py:1023-1105, 1241-1289) ---------------------------------------------------------
     def set_rigid_body(self, kind, center, rigid_xyz, cuboid_num=None, particle_radius=None, sphere_radius=None, cylinder_radius=None,
