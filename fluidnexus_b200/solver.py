@@ -109,6 +109,32 @@ class PBFSolver(EmitterMixin):
             L.check(L.lib().fnx_pbf_confirm_guess(self._xyz.size(0), self._xyz.data_ptr(), self._estimate_xyz.data_ptr(),
                                                   self._velocity.data_ptr(), self._secs, self._st()))
 
+    # the reference has a second method with the same body (gm_fluid.py:1177-1191), called after a frame's optimisation
+    confirm_guess_hidden_particles_wo_velocity = confirm_guess_hidden_particles
+
+    @torch.no_grad()
+    def confirm_guess_hidden_particles_from_nn(self, estimate_xyz_nn):
+        """After a frame's optimisation (train_physical_particle.py:432): the optimised positions (render units, the trainable tensor
+        of the fused step: FrameState.e) become the solver's estimate (gm_fluid.py:1193-1195)."""
+        self._estimate_xyz = (estimate_xyz_nn.detach().to(self.dev, torch.float32) * self.scale_factor).contiguous()
+
+    @torch.no_grad()
+    def update_visual_xyz_from_nn(self):
+        """The visual particles move with the optimised hidden velocities (P1 forward once more, gm_fluid.py:1339-1340); call after
+        confirm_guess_hidden_particles_from_nn."""
+        from . import physics
+        if self._visual_xyz.size(0):
+            self._visual_xyz = physics.visual_advect(self._estimate_xyz, self._xyz, self._visual_xyz, self.H, self._secs, self.KNN_K).detach()
+
+    # what fluidnexus_b200.step.FrameState reads from its `hidden` argument: FrameState(sol, sol._visual_xyz, fluid, background)
+    # builds the optimisation state of the current frame straight from the solver (training_setup_current, gm_fluid.py:330-334)
+    N = property(lambda self: int(self._xyz.size(0)))
+    xyz = property(lambda self: self._xyz)
+    estimate_xyz = property(lambda self: self._estimate_xyz)
+    buoyancy = property(lambda self: self._buoyancy)
+    force = property(lambda self: self._force)
+    imass = property(lambda self: self._imass)
+
     @torch.no_grad()
     def update_visual_particles(self):
         V, N = self._visual_xyz.size(0), self._estimate_xyz.size(0)

@@ -97,3 +97,20 @@ def test_predict_runs_the_future_simulation_loop_in_the_reference_order():
     assert [round(p, 6) for _, p, _ in frames] == [2.0, 1.875, 1.75]
     assert [n for _, _, n in frames] == [2, 2, 2]
     assert PBFSolver.future_p0(2.0, 1.5, 10, 4) == 1.5
+
+
+def test_solver_hands_its_state_to_the_fused_step_and_takes_the_result_back():
+    """The seams between the solver tick and a frame's optimisation (train_physical_particle.py:300-301, 432-434): the solver exposes
+    what step.FrameState reads, and confirm_guess_hidden_particles_from_nn takes the optimised tensor back in scaled units."""
+    import torch
+    from fluidnexus_b200.solver import PBFSolver
+    sol = object.__new__(PBFSolver)
+    sol.dev, sol.scale_factor = torch.device("cpu"), 100.0
+    for k, cols in (("_xyz", 3), ("_estimate_xyz", 3), ("_buoyancy", 3), ("_force", 3), ("_imass", 1)):
+        setattr(sol, k, torch.rand(7, cols))
+    assert sol.N == 7 and sol.xyz is sol._xyz and sol.estimate_xyz is sol._estimate_xyz and sol.buoyancy is sol._buoyancy
+    assert sol.force is sol._force and sol.imass is sol._imass
+    e = (sol._estimate_xyz / 100.0 + 0.001).requires_grad_(True)          # FrameState.e after some Adam steps
+    sol.confirm_guess_hidden_particles_from_nn(e)
+    assert torch.allclose(sol._estimate_xyz, e.detach() * 100.0) and not sol._estimate_xyz.requires_grad
+    assert PBFSolver.confirm_guess_hidden_particles_wo_velocity is PBFSolver.confirm_guess_hidden_particles
