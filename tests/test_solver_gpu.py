@@ -147,3 +147,64 @@ def test_rigid_projection_matches_reference_golden(libfnx, kind):
         assert int(n.item()) == int(mask.sum())
         got = getattr(sol, attr).cpu().numpy()
         assert np.abs(got - g[f"rigid_{kind}_{after}"]).max() < 1e-5, kind
+
+
+def test_creation_emission_future_prediction_checkpoints_and_frame_handoff(libfnx, tmp_path):
+    """The solver class end to end on the GPU, the way the reference's entries drive their model: particles created and emitted
+    (emitter.py, pinned to the reference's own methods on the CPU), two future frames (PBFSolver.predict = the loop of
+    future_simulation.py:118-175), the reference's checkpoint layout (save_all / load_all), and one frame's hand-off to the fused
+    optimisation step and back (train_physical_particle.py:300-301, 432-434)."""
+    import types
+    from fluidnexus_b200.step import FrameState, PhysicalStep, StepParams
+    margs = types.SimpleNamespace(
+        init_visual_num_pts=300, init_thick_visual_num_pts=50, init_visual_radius_small_max=0.014, init_visual_radius_max=0.028, init_x_mid=0.326,
+        init_visual_y_min=-0.09, init_visual_y_max=0.32, init_z_mid=-0.3, init_visual_y_thick_min=0.16, init_hidden_radius_max=0.042,
+        init_hidden_delta=0.009, init_hidden_y_min=-0.11, init_hidden_y_max=0.35, emitter_hidden_delta=0.009, emitter_visual_delta=0.004,
+        emitter_center_y_hidden=-0.11, emitter_center_y_visual=-0.09, emitter_center_y_hidden_max=0.25, emitter_center_y_visual_max=0.16,
+        emitter_visual_radius_ratio=3, emitter_hidden_radius_ratio=5)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    sol = PBFSolver(None)
+    sol.create_particles_visual(margs)
+    sol._visual_xyz = sol._visual_xyz * sol.scale_factor                 # detach_visual_and_scale
+    sol.create_particles_hidden(margs)
+    sol.prepare_emitter_points(margs, is_future=True)
+    n0, sites_h, sites_v = sol.N, sol.hidden_emitter_points.shape[0], sol.visual_emitter_points.shape[0]
+    assert n0 > 3000 and sol._xyz.is_cuda and sol._imass.shape == (n0, 1)
+    # ---- two future frames ----
+    frames = []
+    sol.predict(2, first_frame_index=5, solver_iterations_future=2, on_frame=lambda s, f: frames.append((f, s.N, s._visual_xyz.shape[0], s.p0)))
+    per_h, per_v = sites_h + int(0.32 * sites_h), sites_v + int(0.32 * sites_v)          # emit ratio 1.32
+    assert [f[0] for f in frames] == [5, 6] and [f[1] for f in frames] == [n0 + per_h, n0 + 2 * per_h]
+    assert frames[1][2] == frames[0][2] + per_v and frames[0][3] == pytest.approx(1.5)
+    for t in (sol._xyz, sol._estimate_xyz, sol._velocity, sol._visual_xyz):
+        assert bool(torch.isfinite(t).all())
+    assert sol._visual_color.shape[0] == sol._visual_xyz.shape[0] and float((sol._velocity.abs().max())) > 0
+    # ---- checkpoint round trip in the reference's layout ----
+    sol.save_all(str(tmp_path), 7)
+    back = PBFSolver(None)
+    back.load_all(str(tmp_path), 7)
+    for k in ("_xyz", "_estimate_xyz", "_velocity", "_force", "_buoyancy", "_imass", "_counts", "_visual_xyz", "_visual_opacity"):
+        a, b = getattr(back, k), getattr(sol, k)
+        assert a.is_cuda and a.shape == b.shape and torch.allclose(a, b, rtol=1e-6, atol=1e-6), k
+    assert back.emit_counter == 2 and back.p0 == pytest.approx(sol.p0)
+    # ---- one optimised frame: solver tick -> FrameState -> fused step -> back into the solver ----
+    sol.emit_new_particles()
+    sol.guess_hidden_particles()
+    sol.project_gas_constraints()
+    V = sol._visual_xyz.shape[0]
+    fluid = S.fluid_gaussians(V, 3, seed=2, log_scale=-4.6)
+    fluid.xyz = sol._visual_xyz.cpu().numpy() / 100.0
+    prm = StepParams(grey=True, distance_threshold_visual=0.004)
+    fr = FrameState(sol, sol._visual_xyz, fluid, S.background_gaussians(400, 3, seed=3), prm=prm)
+    assert fr.N == sol.N and fr.V == V
+    ps = PhysicalStep(S.make_cameras(5, 64), 3, prm)
+    e0 = fr.e.clone()
+    out = ps.step(fr, [1, 3], torch.rand(2, 3, 64, 64, device="cuda") * 0.5)
+    assert bool(torch.isfinite(ps.total_loss(out))) and float((fr.e - e0).abs().max()) > 0
+    vis0, x0 = sol._visual_xyz.clone(), sol._xyz.clone()
+    sol.confirm_guess_hidden_particles_from_nn(fr.e)
+    sol.update_visual_xyz_from_nn()
+    sol.confirm_guess_hidden_particles_wo_velocity()
+    assert torch.allclose(sol._estimate_xyz, fr.e * 100.0) and sol._visual_xyz.shape == vis0.shape
+    assert bool(torch.isfinite(sol._visual_xyz).all()) and float((sol._xyz - x0).abs().max()) > 0
