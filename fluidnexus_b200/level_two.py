@@ -84,6 +84,31 @@ class LevelTwoState:
         self.losses = torch.zeros(5, device=dev)   # consistency colour / opacity / scales / rotation, scaling regulariser
 
 
+def init_quantities_current_level_two(visual_xyz, color, opacity, scales, rotation, prev=None, fit_color=True, fit_opacity=True,
+                                      fit_scales=True, fit_rotation=True, init_scales_w_xyz_dist=False, inherit_prev_color=False,
+                                      inherit_prev_opacity=False, inherit_prev_scales=False, inherit_prev_rotation=False, dist2_fn=None):
+    """Raw attributes a frame's level-two fit starts from (gm_dynamics.py:363-378, called at train_visual_particle.py:111 right after
+    load_visual): optionally log-scales from the mean distance to the 3 nearest particles (distCUDA2, clamped to [-10, 1]); then, for
+    every fitted attribute whose `inherit_prev_*` flag is set, the first `prev[X].shape[0]` particles -- the ones that already existed
+    in the previous frame, new particles are appended -- take the previous frame's fitted values.  `prev`: dict with any of
+    color / opacity / scales / rotation (or None for the first frame).  Flag defaults: FD/arguments/__init__.py:395-401 (the
+    FluidNexus configs inherit all four).  Returns new tensors (color, opacity, scales, rotation)."""
+    color, opacity, scales, rotation = color.clone(), opacity.clone(), scales.clone(), rotation.clone()
+    if fit_scales and init_scales_w_xyz_dist:
+        if dist2_fn is None:
+            from .physics import distCUDA2 as dist2_fn
+        d2 = torch.clamp_min(dist2_fn(visual_xyz.float()), 0.0000001)
+        scales = torch.clamp(torch.log(torch.sqrt(d2))[..., None].repeat(1, 3), -10, 1.0)
+    out = dict(color=color, opacity=opacity, scales=scales, rotation=rotation)
+    flags = dict(color=fit_color and inherit_prev_color, opacity=fit_opacity and inherit_prev_opacity, scales=fit_scales and inherit_prev_scales,
+                 rotation=fit_rotation and inherit_prev_rotation)
+    for name, on in flags.items():
+        p = None if prev is None else prev.get(name)
+        if on and p is not None:
+            out[name][: p.shape[0]] = p.to(out[name].device, out[name].dtype).reshape(p.shape[0], -1)
+    return out["color"], out["opacity"], out["scales"], out["rotation"]
+
+
 class LevelTwoStep:
     """step(state, view_ids, gt) -> dict of device scalars; `cams` as for PhysicalStep."""
 

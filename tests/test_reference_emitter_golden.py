@@ -158,3 +158,26 @@ def test_setup_rigid_body_registers_the_sampled_body(kind):
         assert torch.allclose(d[:, :2].norm(dim=1), torch.full((n,), 4.0), atol=1e-4) and float(d[:, 2].max()) <= 50 * 0.5 / 2 + 1e-4
     else:
         assert bool((d <= torch.tensor(want) + 0.5 + 1e-4).all())
+
+
+@pytest.mark.parametrize("case", ["inherit", "dist_scales"])
+def test_level_two_initial_quantities_equal_the_reference(case):
+    """init_quantities_current_level_two (gm_dynamics.py:363-378): inherited rows and distance-based log-scales exactly as the
+    reference's own method produces them (distCUDA2 stood in for by the oracle's kNN on both sides)."""
+    from fluidnexus_b200.level_two import init_quantities_current_level_two
+    from oracle import pbf_ref as O
+    pre = f"l2init/{case}/"
+    t = lambda k: torch.from_numpy(G[pre + k])
+    flags = {k[len(pre) + 5:]: bool(G[k]) for k in G.files if k.startswith(pre + "flag/")}
+    prev = {k: t("prev_" + k) for k in ("color", "opacity", "scales", "rotation")}
+    got = init_quantities_current_level_two(t("in_visual_xyz"), t("in_visual_color"), t("in_visual_opacity"), t("in_visual_scales"),
+                                            t("in_visual_rotation"), prev=prev, dist2_fn=lambda p: torch.tensor(O.knn3_mean_dist2(p.numpy())), **flags)
+    for name, a in zip(("_visual_color", "_visual_opacity", "_visual_scales", "_visual_rotation"), got):
+        want = G[pre + "out" + name]
+        assert a.numpy().shape == want.shape and np.array_equal(a.numpy(), want), name
+    # inputs are not modified; without `prev` nothing is inherited
+    assert np.array_equal(t("in_visual_color").numpy(), G[pre + "in_visual_color"])
+    first = init_quantities_current_level_two(t("in_visual_xyz"), t("in_visual_color"), t("in_visual_opacity"), t("in_visual_scales"),
+                                              t("in_visual_rotation"), prev=None, **{**flags, "init_scales_w_xyz_dist": False})
+    for name, a in zip(("color", "opacity", "scales", "rotation"), first):
+        assert torch.equal(a, t("in_visual_" + name)), name

@@ -124,6 +124,34 @@ def main():
         for k in ("_rigid_color", "_rigid_scales", "_rigid_rotation", "_rigid_opacity"):
             out[f"rigid/{kind}/render{k}"] = getattr(gm, k).numpy().copy()
         print("rigid", kind, out[f"rigid/{kind}/xyz"].shape)
+    # ---- init_quantities_current_level_two (gm_dynamics.py:363-378): what a frame's level-two fit starts from ----
+    import types as _types
+    for case, (flags, fit) in {
+            "inherit": (dict(init_scales_w_xyz_dist=False, inherit_prev_color=True, inherit_prev_opacity=True, inherit_prev_scales=True,
+                             inherit_prev_rotation=True), dict(fit_color=True, fit_opacity=True, fit_scales=True, fit_rotation=True)),
+            "dist_scales": (dict(init_scales_w_xyz_dist=True, inherit_prev_color=False, inherit_prev_opacity=True, inherit_prev_scales=True,
+                                 inherit_prev_rotation=True), dict(fit_color=True, fit_opacity=True, fit_scales=True, fit_rotation=False))}.items():
+        g = torch.Generator().manual_seed(3)
+        V, Vp = 90, 60
+        gm = object.__new__(GM)
+        gm._visual_xyz = torch.rand(V, 3, generator=g) * 20.0
+        gm._visual_color, gm._visual_opacity = torch.rand(V, 1, generator=g), torch.randn(V, 1, generator=g)
+        gm._visual_scales, gm._visual_rotation = torch.randn(V, 3, generator=g) - 5.0, torch.randn(V, 4, generator=g)
+        prev = dict(color=torch.rand(Vp, 1, generator=g), opacity=torch.randn(Vp, 1, generator=g), scales=torch.randn(Vp, 3, generator=g) - 5.0,
+                    rotation=torch.randn(Vp, 4, generator=g))
+        for k, v in fit.items():
+            setattr(gm, k, v)
+        for k in ("_visual_xyz", "_visual_color", "_visual_opacity", "_visual_scales", "_visual_rotation"):
+            out[f"l2init/{case}/in{k}"] = getattr(gm, k).numpy().copy()
+        for k, v in prev.items():
+            out[f"l2init/{case}/prev_{k}"] = v.numpy().copy()
+        for k, v in {**flags, **fit}.items():
+            out[f"l2init/{case}/flag/{k}"] = v
+        with cuda_as_cpu():
+            gm.init_quantities_current_level_two(_types.SimpleNamespace(**flags), prev["color"], prev["opacity"], prev["scales"], prev["rotation"])
+        for k in ("_visual_color", "_visual_opacity", "_visual_scales", "_visual_rotation"):
+            out[f"l2init/{case}/out{k}"] = getattr(gm, k).numpy().copy()
+        print("l2init", case, out[f"l2init/{case}/out_visual_scales"].dtype, float(out[f"l2init/{case}/out_visual_scales"].mean()))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
