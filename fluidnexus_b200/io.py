@@ -82,13 +82,16 @@ def save_visual(checkpoint_path, frame_idx, state, scale_factor, scale=True):
         np.save(_frame_file(checkpoint_path, frame_idx, name), a / float(scale_factor) if (name == "visual_xyz" and scale) else a)
 
 
-def load_visual(checkpoint_path, frame_idx, scale_factor, scale=True):
+def load_visual(checkpoint_path, frame_idx, scale_factor, scale=True, color_3ch=False):
+    """color_3ch (gm_dynamics.py:2067-2078, the level-two stage of 3-channel scenes): a one-channel colour is repeated to three."""
     state = {}
     for name in VISUAL_ARRAYS:
         path = _frame_file(checkpoint_path, frame_idx, name)
         assert os.path.exists(path), f"File not found: {path}"
         a = np.load(path).astype(np.float32)
         state[name] = a * np.float32(scale_factor) if (name == "visual_xyz" and scale) else a
+    if color_3ch and state["visual_color"].shape[1] == 1:
+        state["visual_color"] = np.repeat(state["visual_color"], 3, axis=1)
     return state
 
 

@@ -274,10 +274,11 @@ class PBFSolver(EmitterMixin):
         IO.save_visual(checkpoint_path, frame_idx, {k: getattr(self, "_" + k) for k in IO.VISUAL_ARRAYS}, self.scale_factor, scale=scale)
 
     @torch.no_grad()
-    def load_visual(self, checkpoint_path, frame_idx, scale=True):
+    def load_visual(self, checkpoint_path, frame_idx, scale=True, color_3ch=False):
         from . import io as IO
-        for k, a in IO.load_visual(checkpoint_path, frame_idx, self.scale_factor, scale=scale).items():
+        for k, a in IO.load_visual(checkpoint_path, frame_idx, self.scale_factor, scale=scale, color_3ch=color_3ch).items():
             setattr(self, "_" + k, torch.from_numpy(a).to(self.dev).contiguous())
+        return int(self._visual_xyz.shape[0])
 
     def save_all(self, checkpoint_path, frame_idx):
         self.save_hidden(checkpoint_path, frame_idx)

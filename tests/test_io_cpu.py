@@ -93,3 +93,17 @@ def test_ply_reader_accepts_ascii_and_reordered_columns(tmp_path):
     with pytest.raises(AssertionError):
         (tmp_path / "b.ply").write_text("not a ply\n")
         IO.read_ply_vertices(str(tmp_path / "b.ply"))
+
+
+def test_load_visual_repeats_a_grey_colour_for_three_channel_scenes(tmp_path):
+    """gm_dynamics.load_visual(..., color_3ch=True), gm_dynamics.py:2076-2078."""
+    rng = np.random.default_rng(0)
+    vis = dict(visual_xyz=rng.random((9, 3)).astype(np.float32), visual_color=rng.random((9, 1)).astype(np.float32),
+               visual_scales=rng.random((9, 3)).astype(np.float32), visual_rotation=rng.random((9, 4)).astype(np.float32),
+               visual_opacity=rng.random((9, 1)).astype(np.float32))
+    IO.save_visual(str(tmp_path), 3, vis, 100.0, scale=False)
+    plain = IO.load_visual(str(tmp_path), 3, 100.0, scale=False)
+    rgb = IO.load_visual(str(tmp_path), 3, 100.0, scale=False, color_3ch=True)
+    assert plain["visual_color"].shape == (9, 1) and rgb["visual_color"].shape == (9, 3)
+    assert all(np.array_equal(rgb["visual_color"][:, c], vis["visual_color"][:, 0]) for c in range(3))
+    assert np.array_equal(rgb["visual_xyz"], vis["visual_xyz"])                      # scale=False: render units kept
