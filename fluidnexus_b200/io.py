@@ -82,11 +82,15 @@ def save_visual(checkpoint_path, frame_idx, state, scale_factor, scale=True):
         np.save(_frame_file(checkpoint_path, frame_idx, name), a / float(scale_factor) if (name == "visual_xyz" and scale) else a)
 
 
-def load_visual(checkpoint_path, frame_idx, scale_factor, scale=True, color_3ch=False):
-    """color_3ch (gm_dynamics.py:2067-2078, the level-two stage of 3-channel scenes): a one-channel colour is repeated to three."""
+def load_visual(checkpoint_path, frame_idx, scale_factor, scale=True, color_3ch=False, smoothed_window=None,
+                smoothed=("visual_color", "visual_scales", "visual_rotation", "visual_opacity")):
+    """color_3ch (gm_dynamics.py:2067-2078, the level-two stage of 3-channel scenes): a one-channel colour is repeated to three.
+    smoothed_window = w (load_visual_smoothed, gm_dynamics.py:2093-2150): the attributes named in `smoothed` are read from the
+    temporally smoothed files `frame_XXX_<name>_smoothed_ws<w>.npy` that the reference's post-processing writes next to the plain ones."""
     state = {}
     for name in VISUAL_ARRAYS:
-        path = _frame_file(checkpoint_path, frame_idx, name)
+        stem = f"{name}_smoothed_ws{int(smoothed_window)}" if (smoothed_window is not None and name in smoothed) else name
+        path = _frame_file(checkpoint_path, frame_idx, stem)
         assert os.path.exists(path), f"File not found: {path}"
         a = np.load(path).astype(np.float32)
         state[name] = a * np.float32(scale_factor) if (name == "visual_xyz" and scale) else a

@@ -280,6 +280,17 @@ class PBFSolver(EmitterMixin):
             setattr(self, "_" + k, torch.from_numpy(a).to(self.dev).contiguous())
         return int(self._visual_xyz.shape[0])
 
+    @torch.no_grad()
+    def load_visual_smoothed(self, checkpoint_path, frame_idx, scale=True, window_size=5, smoothed_color=True, smoothed_scales=True,
+                             smoothed_rotation=True, smoothed_opacity=True):
+        """gm_dynamics.py:2093-2150: the temporally smoothed level-two attributes (files *_smoothed_ws<window>.npy) for future prediction."""
+        from . import io as IO
+        which = tuple(n for n, on in (("visual_color", smoothed_color), ("visual_scales", smoothed_scales),
+                                      ("visual_rotation", smoothed_rotation), ("visual_opacity", smoothed_opacity)) if on)
+        for k, a in IO.load_visual(checkpoint_path, frame_idx, self.scale_factor, scale=scale, smoothed_window=window_size, smoothed=which).items():
+            setattr(self, "_" + k, torch.from_numpy(a).to(self.dev).contiguous())
+        return int(self._visual_xyz.shape[0])
+
     def save_all(self, checkpoint_path, frame_idx):
         self.save_hidden(checkpoint_path, frame_idx)
         self.save_visual(checkpoint_path, frame_idx)

@@ -107,3 +107,24 @@ def test_load_visual_repeats_a_grey_colour_for_three_channel_scenes(tmp_path):
     assert plain["visual_color"].shape == (9, 1) and rgb["visual_color"].shape == (9, 3)
     assert all(np.array_equal(rgb["visual_color"][:, c], vis["visual_color"][:, 0]) for c in range(3))
     assert np.array_equal(rgb["visual_xyz"], vis["visual_xyz"])                      # scale=False: render units kept
+
+
+def test_load_visual_smoothed_reads_the_smoothed_files_where_asked(tmp_path):
+    """load_visual_smoothed (gm_dynamics.py:2093-2150) through the solver class, made without its CUDA-only constructor."""
+    import torch
+    from fluidnexus_b200.solver import PBFSolver
+    rng = np.random.default_rng(1)
+    vis = {k: rng.random((6, c)).astype(np.float32) for k, c in (("visual_xyz", 3), ("visual_color", 1), ("visual_scales", 3),
+                                                                  ("visual_rotation", 4), ("visual_opacity", 1))}
+    IO.save_visual(str(tmp_path), 4, vis, 100.0)
+    smooth = {k: v + 1.0 for k, v in vis.items() if k != "visual_xyz"}
+    for k, v in smooth.items():
+        np.save(tmp_path / f"frame_004_{k}_smoothed_ws5.npy", v)
+    sol = object.__new__(PBFSolver)
+    sol.dev, sol.scale_factor = torch.device("cpu"), 100.0
+    assert sol.load_visual_smoothed(str(tmp_path), 4, smoothed_rotation=False) == 6
+    assert np.allclose(sol._visual_xyz.numpy(), vis["visual_xyz"], rtol=1e-6)                   # saved / 100, loaded * 100
+    assert np.array_equal(sol._visual_color.numpy(), smooth["visual_color"]) and np.array_equal(sol._visual_scales.numpy(), smooth["visual_scales"])
+    assert np.array_equal(sol._visual_rotation.numpy(), vis["visual_rotation"]) and np.array_equal(sol._visual_opacity.numpy(), smooth["visual_opacity"])
+    with pytest.raises(AssertionError, match="File not found"):
+        sol.load_visual_smoothed(str(tmp_path), 4, window_size=7)
