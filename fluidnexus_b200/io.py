@@ -100,6 +100,38 @@ def load_visual(checkpoint_path, frame_idx, scale_factor, scale=True, color_3ch=
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# "quantities": the .npy snapshots the entries drop for visualisation / debugging (gm_dynamics.py:1938-2017).  One table instead of
+# seven methods: kind -> (file-name prefix, ((file stem, key into `tensors`, stored in render units?, skipped when empty?), ...))
+# ---------------------------------------------------------------------------------------------------------------------
+QUANTITIES = {
+    "rigid_body": ("frame_{a:03d}_", (("rigid_xyz", "rigid_xyz", True, False),)),
+    "frame": ("frame_{a:03d}_", (("xyz", "xyz", True, False), ("visual_xyz", "visual_xyz", True, True))),
+    "simulation": ("{a:03d}_", (("xyz", "xyz", True, False), ("estimated_xyz", "estimate_xyz", True, False), ("visual_xyz", "visual_xyz", True, True))),
+    "simulation_guess": ("{a:03d}_", (("guess_estimated_xyz", "estimate_xyz", True, False),)),
+    "optimization_first": ("{a:03d}_{b:05d}_", (("visual_xyz", "visual_xyz", False, False),)),
+    # estimate_xyz_nn is the trainable tensor (already in render units); visual_xyz here is the advected set handed in by the loop
+    "optimization": ("{a:03d}_{b:05d}_", (("estimate_xyz_nn", "estimate_xyz_nn", False, False), ("visual_xyz", "visual_xyz", False, True))),
+    "optimization_level_two": ("{a:03d}_{b:05d}_", tuple((n, n, False, False) for n in VISUAL_ARRAYS[1:])),
+}
+
+
+def save_particles(kind, quantities_path, tensors, a, b=0, scale_factor=100.0):
+    """save_particles_<kind>(quantities_path, a[, b]) of the reference: a = frame / simulation index, b = iteration.  `tensors`: dict
+    of arrays / tensors in the units the model holds them (scaled for positions).  Returns the files written."""
+    prefix, entries = QUANTITIES[kind]
+    os.makedirs(quantities_path, exist_ok=True)
+    written = []
+    for stem, key, render_units, skip_empty in entries:
+        arr = _np(tensors[key])
+        if skip_empty and arr.shape[0] == 0:
+            continue
+        path = os.path.join(quantities_path, prefix.format(a=a, b=b) + stem + ".npy")
+        np.save(path, arr / float(scale_factor) if render_units else arr)
+        written.append(path)
+    return written
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # background point cloud (PLY)
 # ---------------------------------------------------------------------------------------------------------------------
 def background_ply_properties(n_color, n_scale=3, n_rot=4):

@@ -299,6 +299,24 @@ class PBFSolver(EmitterMixin):
         self.load_hidden(checkpoint_path, frame_idx)
         self.load_visual(checkpoint_path, frame_idx)
 
+    # -- quantity snapshots (gm_dynamics.py:1938-1976), same method names -----------------------------------------------------------
+    def _snapshot(self, kind, path, a):
+        from . import io as IO
+        t = dict(xyz=self._xyz, estimate_xyz=self._estimate_xyz, visual_xyz=self._visual_xyz, rigid_xyz=getattr(self, "_rigid_xyz", None))
+        return IO.save_particles(kind, path, t, a, scale_factor=self.scale_factor)
+
+    def save_particles_frame(self, quantities_path, frame_idx):
+        return self._snapshot("frame", quantities_path, frame_idx)
+
+    def save_particles_simulation(self, quantities_path, index):
+        return self._snapshot("simulation", quantities_path, index)
+
+    def save_particles_simulation_guess(self, quantities_path, index):
+        return self._snapshot("simulation_guess", quantities_path, index)
+
+    def save_particles_rigid_body(self, quantities_path, frame_idx):
+        return self._snapshot("rigid_body", quantities_path, frame_idx)
+
     # -- future prediction: the loop of FD/entries_fluid_nexus/future_simulation.py:118-175 ---------------------------------------
     @staticmethod
     def future_p0(p0_recon, p0_future, future_time_index, decay_frames):

@@ -181,3 +181,28 @@ def test_level_two_initial_quantities_equal_the_reference(case):
                                               t("in_visual_rotation"), prev=None, **{**flags, "init_scales_w_xyz_dist": False})
     for name, a in zip(("color", "opacity", "scales", "rotation"), first):
         assert torch.equal(a, t("in_visual_" + name)), name
+
+
+def test_quantity_snapshots_equal_the_reference_writers(tmp_path):
+    """save_particles_* (gm_dynamics.py:1938-2017): same file names, shapes, dtypes and contents as the reference's own methods."""
+    from fluidnexus_b200 import io as IO
+    from fluidnexus_b200.solver import PBFSolver
+    t = lambda k: torch.from_numpy(G["quant/in" + k])
+    sol = object.__new__(PBFSolver)
+    sol.dev, sol.scale_factor = torch.device("cpu"), 100.0
+    sol._xyz, sol._estimate_xyz, sol._visual_xyz, sol._rigid_xyz = t("_xyz"), t("_estimate_xyz"), t("_visual_xyz"), t("_rigid_xyz")
+    d = str(tmp_path)
+    sol.save_particles_rigid_body(d, 3)
+    sol.save_particles_frame(d, 3)
+    sol.save_particles_simulation(d, 41)
+    sol.save_particles_simulation_guess(d, 41)
+    IO.save_particles("optimization_first", d, dict(visual_xyz=t("_visual_xyz")), 0, 250)
+    IO.save_particles("optimization", d, dict(estimate_xyz_nn=t("_estimate_xyz_nn"), visual_xyz=t("_advected")), 7, 120)
+    IO.save_particles("optimization_level_two", d, {k: t("_" + k) for k in IO.VISUAL_ARRAYS[1:]}, 7, 30)
+    assert sorted(os.listdir(d)) == [str(f) for f in G["quant/files"]]
+    for f in G["quant/files"]:
+        a, b = np.load(os.path.join(d, str(f))), G["quant/file/" + str(f)]
+        assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b), f
+    # an empty visual set writes no visual file (gm_dynamics.py:1953, 1970)
+    sol._visual_xyz = torch.zeros((0, 3))
+    assert [os.path.basename(p) for p in sol.save_particles_frame(str(tmp_path / "e"), 1)] == ["frame_001_xyz.npy"]

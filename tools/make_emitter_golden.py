@@ -152,6 +152,32 @@ def main():
         for k in ("_visual_color", "_visual_opacity", "_visual_scales", "_visual_rotation"):
             out[f"l2init/{case}/out{k}"] = getattr(gm, k).numpy().copy()
         print("l2init", case, out[f"l2init/{case}/out_visual_scales"].dtype, float(out[f"l2init/{case}/out_visual_scales"].mean()))
+    # ---- save_particles_* (gm_dynamics.py:1938-2017): file names and contents of the quantity snapshots ----
+    import tempfile
+    g = torch.Generator().manual_seed(9)
+    gm = object.__new__(GM)
+    gm.scale_factor = 100.0
+    gm._xyz, gm._estimate_xyz, gm._visual_xyz = torch.rand(12, 3, generator=g) * 30, torch.rand(12, 3, generator=g) * 30, torch.rand(5, 3, generator=g) * 30
+    gm._rigid_xyz, gm._estimate_xyz_nn = torch.rand(4, 3, generator=g) * 30, torch.rand(12, 3, generator=g)
+    gm._visual_color, gm._visual_scales = torch.rand(5, 1, generator=g), torch.rand(5, 3, generator=g)
+    gm._visual_rotation, gm._visual_opacity = torch.rand(5, 4, generator=g), torch.rand(5, 1, generator=g)
+    for k in ("_xyz", "_estimate_xyz", "_visual_xyz", "_rigid_xyz", "_estimate_xyz_nn", "_visual_color", "_visual_scales", "_visual_rotation", "_visual_opacity"):
+        out[f"quant/in{k}"] = getattr(gm, k).numpy().copy()
+    advected = torch.rand(5, 3, generator=g)
+    out["quant/in_advected"] = advected.numpy().copy()
+    with tempfile.TemporaryDirectory() as d:
+        gm.save_particles_rigid_body(d, 3)
+        gm.save_particles_frame(d, 3)
+        gm.save_particles_simulation(d, 41)
+        gm.save_particles_simulation_guess(d, 41)
+        gm.save_particles_optimization_first(d, 0, 250)
+        gm.save_particles_optimization(d, advected, 7, 120)
+        gm.save_particles_optimization_level_two(d, 7, 30)
+        files = sorted(os.listdir(d))
+        out["quant/files"] = np.array(files)
+        for f in files:
+            out["quant/file/" + f] = np.load(os.path.join(d, f))
+    print("quantities", len(files), "files")
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
