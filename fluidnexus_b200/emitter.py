@@ -11,6 +11,7 @@ future_simulation.py:102,132):
     emit_new_particles(future_time_index=-1)                  gm_dynamics.py:844-976   append one tick's worth of new particles
     create_rigid_body()                                       gm_dynamics.py:612-672   surface samples of the cuboid / sphere / cylinder
     prepare_{hidden,visual,future_visual,rigid_body}_particles_for_rendering()   gm_dynamics.py:1636-1700   constant raw appearance
+    get_* accessors, load_ply(path)                           gm_dynamics.py:200-338, 1702-1744   what the render pipes read
 
 This is plain torch / numpy bookkeeping (no kernels): a few hundred points per frame.  What matters is that a run seeded like the
 reference's produces the SAME particles: the sites are enumerated in the reference's order (x outermost, then y, then z), and the
@@ -147,6 +148,47 @@ class EmitterMixin:
         center = torch.as_tensor(self.rigid_body_center, dtype=torch.float32).to(self.dev)
         self._rigid_xyz = _f32(pts, self.dev) + center
         self._rigid_imass = torch.zeros((pts.shape[0], 1), dtype=torch.float32, device=self.dev)
+
+    # -- what the render pipes read (renderer.py / FD/renderer/pipe_*.py): the reference's accessors, gm_dynamics.py:200-338 --------
+    # raw tensors -> activated attributes: exp (scales), sigmoid (opacity), normalise (rotation); colours and positions as stored
+    active_sh_degree = 0
+    scaling_activation = staticmethod(torch.exp)
+    opacity_activation = staticmethod(torch.sigmoid)
+    rotation_activation = staticmethod(torch.nn.functional.normalize)
+    get_xyz = property(lambda s: s._xyz)
+    get_estimate_xyz = property(lambda s: s._estimate_xyz)
+    get_force = property(lambda s: s._force)
+    get_velocity = property(lambda s: s._velocity)
+    get_imass = property(lambda s: s._imass)
+    get_color_dummy = property(lambda s: s._color_dummy)
+    get_scaling_dummy = property(lambda s: s.scaling_activation(s._scales_dummy))
+    get_rotation_dummy = property(lambda s: s.rotation_activation(s._rotation_dummy))
+    get_opacity_dummy = property(lambda s: s.opacity_activation(s._opacity_dummy))
+    get_visual_xyz = property(lambda s: s._visual_xyz)
+    get_visual_color = property(lambda s: s._visual_color)
+    get_visual_scaling = property(lambda s: s.scaling_activation(s._visual_scales))
+    get_visual_rotation = property(lambda s: s.rotation_activation(s._visual_rotation))
+    get_visual_opacity = property(lambda s: s.opacity_activation(s._visual_opacity))
+    get_rigid_xyz = property(lambda s: s._rigid_xyz)
+    get_rigid_color = property(lambda s: s._rigid_color)
+    get_rigid_scaling = property(lambda s: s.scaling_activation(s._rigid_scales))
+    get_rigid_rotation = property(lambda s: s.rotation_activation(s._rigid_rotation))
+    get_rigid_opacity = property(lambda s: s.opacity_activation(s._rigid_opacity))
+    get_gs_xyz = property(lambda s: s._gs_xyz)
+    get_gs_color = property(lambda s: s._gs_color)
+    get_gs_scaling = property(lambda s: s.scaling_activation(s._gs_scales))
+    get_gs_rotation = property(lambda s: s.rotation_activation(s._gs_rotation))
+    get_gs_opacity = property(lambda s: s.opacity_activation(s._gs_opacity))
+
+    def load_ply(self, path):
+        """The frozen background set that render_dynamics concatenates behind the particles (gm_dynamics.py:1702-1744): the point
+        cloud the background stage wrote, raw attributes, x / y un-negated (fluidnexus_b200/io.py:load_background_ply)."""
+        from . import io as IO
+        d = IO.load_background_ply(path)
+        for mine, key in (("_gs_xyz", "xyz"), ("_gs_color", "color"), ("_gs_opacity", "opacity"), ("_gs_scales", "scaling"), ("_gs_rotation", "rotation")):
+            setattr(self, mine, torch.from_numpy(np.ascontiguousarray(d[key], dtype=np.float32)).to(self.dev))
+        self.active_sh_degree = 0
+        return int(self._gs_xyz.shape[0])
 
     # -- raw attributes the render pipes read for particle sets that have no trained appearance ------------------------------------
     # (gm_dynamics.py:1636-1700; constants of setup_constants :158-160: colour 0.7, log-scale -5.9, opacity 0.1; rigid body: 0.9 / -5.5 / 0.3)

@@ -206,3 +206,37 @@ def test_quantity_snapshots_equal_the_reference_writers(tmp_path):
     # an empty visual set writes no visual file (gm_dynamics.py:1953, 1970)
     sol._visual_xyz = torch.zeros((0, 3))
     assert [os.path.basename(p) for p in sol.save_particles_frame(str(tmp_path / "e"), 1)] == ["frame_001_xyz.npy"]
+
+
+def test_particle_state_renders_through_the_render_glue_mirror():
+    """The solver-side state (emitter.py accessors + load_ply) is what renderer.render_dynamics / render_fluid read: with the
+    recording rasterizer of the render-glue golden, the particles arrive in render units with their constant appearance activated
+    (sigmoid / exp / normalise), grey repeated to RGB, followed by the frozen background set of the reference-written point cloud."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from fluidnexus_b200 import renderer as RD
+    from fluidnexus_b200 import synthetic as S
+    from make_render_glue_golden import run_case
+    margs = _args("default", "model")
+    np.random.seed(0)
+    p = _Particles(alpha=-0.2)
+    p.create_particles_visual(margs)
+    p._visual_xyz = p._visual_xyz * p.scale_factor
+    p.create_particles_hidden(margs)
+    p.prepare_visual_particles_for_rendering()
+    p.prepare_hidden_particles_for_rendering()
+    n_bg = p.load_ply(os.path.join(os.path.dirname(__file__), "golden", "pyref_background_ply.bin"))
+    V = p._visual_xyz.shape[0]
+    assert n_bg > 0 and p.get_gs_xyz.shape == (n_bg, 3) and p.get_gs_color.shape[1] == 3
+    cam = S.make_cameras(5, 32, height=24)[1]
+    rec = run_case(RD.render_dynamics, p, cam, dict(pos_type="visual", scale=True))
+    assert rec["in_means3D"].shape == (V + n_bg, 3)
+    assert np.allclose(rec["in_means3D"][:V], p._visual_xyz.numpy() / 100.0, rtol=1e-6) and np.array_equal(rec["in_means3D"][V:], p._gs_xyz.numpy())
+    assert np.allclose(rec["in_opacities"][:V], 0.1, atol=1e-6) and np.allclose(rec["in_scales"][:V], np.exp(-5.9), rtol=1e-6)
+    assert np.allclose(rec["in_colors_precomp"][:V], 0.7) and rec["in_colors_precomp"].shape == (V + n_bg, 3)
+    assert np.array_equal(rec["in_rotations"][:V], np.tile([1.0, 0, 0, 0], (V, 1)).astype(np.float32))
+    assert np.allclose(np.linalg.norm(rec["in_rotations"][V:], axis=1), 1.0, atol=1e-5)                 # normalised background quaternions
+    assert np.allclose(rec["in_opacities"][V:, 0], 1 / (1 + np.exp(-p._gs_opacity.numpy()[:, 0])), rtol=1e-5)
+    hid = run_case(RD.render_fluid, p, cam, dict(pos_type="hidden", scale=True))
+    assert hid["in_means3D"].shape == (p._xyz.shape[0], 3) and np.allclose(hid["in_means3D"], p._xyz.numpy() / 100.0, rtol=1e-6)
+    assert hid["in_colors_precomp"].shape[1] == 1 and np.allclose(hid["in_opacities"], 0.1, atol=1e-6)
